@@ -1,0 +1,116 @@
+// Shared device/host helpers for the immtsf sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <math.h>
+
+#define IMMTSF_OK 0
+#define IMMTSF_ERR_ARG (-1)
+#define IMMTSF_ERR_UNSUPPORTED (-2)
+#define IMMTSF_ERR_LAUNCH (-3)
+#define IMMTSF_ERR_ARCH (-4)
+
+void immtsf_set_error(const char* fmt, ...);
+
+#define IMMTSF_REQUIRE(cond, ...)            \
+  do {                                       \
+    if (!(cond)) {                           \
+      immtsf_set_error(__VA_ARGS__);         \
+      return IMMTSF_ERR_ARG;                 \
+    }                                        \
+  } while (0)
+
+#define IMMTSF_CHECK_LAUNCH(name)                                             \
+  do {                                                                        \
+    cudaError_t e__ = cudaGetLastError();                                     \
+    if (e__ != cudaSuccess) {                                                 \
+      immtsf_set_error("%s: launch failed: %s", name, cudaGetErrorString(e__)); \
+      return IMMTSF_ERR_LAUNCH;                                               \
+    }                                                                         \
+  } while (0)
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------- reductions
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// Block-wide sum; `red` is >= 32 floats of shared memory. All threads get the result.
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();  // protect `red` from a previous use
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  float r = (lane < nw) ? red[lane] : 0.f;
+  r = warp_sum(r);
+  return r;
+}
+
+// ---------------------------------------------------------------- Philox4x32-10
+// Counter-based RNG for dropout: the mask is a pure function of
+// (seed, site, element index), so backward regenerates it instead of storing it
+// and the tests can rebuild the same mask on the host (tests/philox_ref.py).
+struct Philox4 {
+  uint32_t x, y, z, w;
+};
+__host__ __device__ __forceinline__ void philox_mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
+  const uint64_t p = (uint64_t)a * (uint64_t)b;
+  hi = (uint32_t)(p >> 32);
+  lo = (uint32_t)p;
+}
+__host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                          uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0, lo0, hi1, lo1;
+    philox_mulhilo(0xD2511F53u, c0, hi0, lo0);
+    philox_mulhilo(0xCD9E8D57u, c2, hi1, lo1);
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return Philox4{c0, c1, c2, c3};
+}
+// Random word for flat element index `idx` at dropout site `site`:
+// word (idx & 3) of philox(counter = (idx>>2 lo, idx>>2 hi, site, 0), key = seed).
+__device__ __forceinline__ uint32_t dropout_word(uint64_t seed, uint32_t site, uint64_t idx) {
+  const uint64_t c = idx >> 2;
+  const Philox4 r = philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), site, 0u, (uint32_t)seed, (uint32_t)(seed >> 32));
+  const uint32_t k = (uint32_t)(idx & 3);
+  return k == 0 ? r.x : (k == 1 ? r.y : (k == 2 ? r.z : r.w));
+}
+// keep-scale for one element: 0 if dropped else 1/(1-p).  thr = floor(p * 2^32).
+__device__ __forceinline__ float dropout_scale(uint64_t seed, uint32_t site, uint64_t idx, uint32_t thr, float inv_keep) {
+  if (thr == 0u) return 1.f;
+  return dropout_word(seed, site, idx) >= thr ? inv_keep : 0.f;
+}
+
+#define IMMTSF_SITE_TTF_DROPOUT 1u
+#define IMMTSF_SITE_TTF_ATTN 2u
+#define IMMTSF_SITE_MMF_DROPOUT 3u
+#define IMMTSF_SITE_MMF_ATTN 4u
+
+// NaN flag slots (int32[4], set with atomicOr-free plain stores of 1).
+#define IMMTSF_FLAG_V 0
+#define IMMTSF_FLAG_Y 1
+#define IMMTSF_FLAG_E 2
+#define IMMTSF_FLAG_OUT 3
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+// ragged row count: min(M, *m_dev) when m_dev != nullptr
+__device__ __forceinline__ int ragged_rows(int M, const int32_t* __restrict__ m_dev) {
+  if (m_dev == nullptr) return M;
+  const int v = *m_dev;
+  return v < M ? v : M;
+}

@@ -1,0 +1,294 @@
+// Exact-fp32 GEMM on the CUDA cores (FFMA), any transposition / leading
+// dimension / alignment, with ragged row or contraction bounds read from the
+// device.  This is the universal backend of immtsf_gemm: it serves the skinny
+// projections (K or N = C), unaligned operands, and is the numerical
+// reference the tcgen05 3xTF32 backend (gemm_tc.cu) is validated against.
+//
+// C[M,N] = alpha * op(A) op(B) + beta * C + bias
+//
+// Tiling: BM x BN x 16 per CTA, 256 threads, each thread owns TM x TN
+// outputs split in 4-wide chunks so that shared-memory reads are
+// conflict-free float4; register-prefetched double buffering of the global
+// loads (one __syncthreads per k-block).
+#include "common.cuh"
+#include "../../include/immtsf.h"
+
+int immtsf_gemm_tc(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda,
+                   const float* B, int ldb, float beta, float* C, int ldc, const float* bias,
+                   const int32_t* ragged, int ragged_dim, cudaStream_t st);
+int immtsf_gemm_tc_eligible(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B,
+                            int ldb, const float* C, int ldc);
+
+struct GemmArgs {
+  int M, N, K;
+  float alpha, beta;
+  const float* A;
+  int lda;
+  const float* B;
+  int ldb;
+  float* C;
+  int ldc;
+  const float* bias;
+  const int32_t* ragged;
+  int ragged_dim;
+  int vecA, vecB, vecC;
+};
+
+constexpr int BK = 16;
+
+// Load one operand tile of TILE x BK elements into registers.
+//   kcontig = true : memory is [tile_dim][k] (k contiguous)  -> float4 along k
+//   kcontig = false: memory is [k][tile_dim] (tile_dim contiguous) -> float4 along tile_dim
+// Each thread loads NV float4 (TILE*BK/4/256).
+template <int TILE, bool KCONTIG>
+__device__ __forceinline__ void load_tile(const float* __restrict__ P, int ld, int vec, int x0, int xmax, int k0,
+                                          int kmax, float4 (&r)[TILE * BK / 1024]) {
+  constexpr int NV = TILE * BK / 1024;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int idx = threadIdx.x + i * 256;
+    int x, k;
+    if (KCONTIG) {
+      x = idx / (BK / 4);
+      k = (idx % (BK / 4)) * 4;
+    } else {
+      k = idx / (TILE / 4);
+      x = (idx % (TILE / 4)) * 4;
+    }
+    const int gx = x0 + x, gk = k0 + k;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (KCONTIG) {
+      if (gx < xmax) {
+        const float* p = P + (size_t)gx * ld + gk;
+        if (vec && gk + 3 < kmax) {
+          v = __ldg(reinterpret_cast<const float4*>(p));
+        } else {
+          if (gk + 0 < kmax) v.x = __ldg(p + 0);
+          if (gk + 1 < kmax) v.y = __ldg(p + 1);
+          if (gk + 2 < kmax) v.z = __ldg(p + 2);
+          if (gk + 3 < kmax) v.w = __ldg(p + 3);
+        }
+      }
+    } else {
+      if (gk < kmax) {
+        const float* p = P + (size_t)gk * ld + gx;
+        if (vec && gx + 3 < xmax) {
+          v = __ldg(reinterpret_cast<const float4*>(p));
+        } else {
+          if (gx + 0 < xmax) v.x = __ldg(p + 0);
+          if (gx + 1 < xmax) v.y = __ldg(p + 1);
+          if (gx + 2 < xmax) v.z = __ldg(p + 2);
+          if (gx + 3 < xmax) v.w = __ldg(p + 3);
+        }
+      }
+    }
+    r[i] = v;
+  }
+}
+
+// Store the register tile into shared memory laid out [BK][TILE + 4].
+template <int TILE, bool KCONTIG>
+__device__ __forceinline__ void store_tile(float* __restrict__ S, const float4 (&r)[TILE * BK / 1024]) {
+  constexpr int NV = TILE * BK / 1024;
+  constexpr int LDS = TILE + 4;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int idx = threadIdx.x + i * 256;
+    if (KCONTIG) {
+      const int x = idx / (BK / 4);
+      const int k = (idx % (BK / 4)) * 4;
+      S[(k + 0) * LDS + x] = r[i].x;
+      S[(k + 1) * LDS + x] = r[i].y;
+      S[(k + 2) * LDS + x] = r[i].z;
+      S[(k + 3) * LDS + x] = r[i].w;
+    } else {
+      const int k = idx / (TILE / 4);
+      const int x = (idx % (TILE / 4)) * 4;
+      *reinterpret_cast<float4*>(&S[k * LDS + x]) = r[i];
+    }
+  }
+}
+
+template <int BM, int BN, int TM, int TN, bool TA, bool TB>
+__global__ void __launch_bounds__(256) gemm_ffma_kernel(const GemmArgs g) {
+  static_assert((BM / TM) * (BN / TN) == 256, "256 threads");
+  constexpr int RM = TM / 4, RN = TN / 4;  // 4-wide chunks per thread
+  constexpr int LDA_S = BM + 4, LDB_S = BN + 4;
+  __shared__ __align__(16) float As[2][BK * LDA_S];
+  __shared__ __align__(16) float Bs[2][BK * LDB_S];
+
+  int M = g.M, K = g.K;
+  if (g.ragged_dim == 1) M = ragged_rows(M, g.ragged);
+  if (g.ragged_dim == 2) K = ragged_rows(K, g.ragged);
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  if (m0 >= M && g.ragged_dim == 1) return;  // tile entirely beyond the ragged end: untouched
+
+  const int tx = threadIdx.x % (BN / TN), ty = threadIdx.x / (BN / TN);
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  float4 ra[BM * BK / 1024], rb[BN * BK / 1024];
+  const int nkb = (K + BK - 1) / BK;
+  if (nkb > 0) {
+    // A' (m,k): TA ? A[k*lda+m] (m contiguous) : A[m*lda+k] (k contiguous)
+    load_tile<BM, !TA>(g.A, g.lda, g.vecA, m0, M, 0, K, ra);
+    // B' (k,n): TB ? B[n*ldb+k] (k contiguous) : B[k*ldb+n] (n contiguous)
+    load_tile<BN, TB>(g.B, g.ldb, g.vecB, n0, g.N, 0, K, rb);
+    store_tile<BM, !TA>(As[0], ra);
+    store_tile<BN, TB>(Bs[0], rb);
+  }
+  __syncthreads();
+  for (int kb = 0; kb < nkb; ++kb) {
+    const int cur = kb & 1;
+    if (kb + 1 < nkb) {
+      load_tile<BM, !TA>(g.A, g.lda, g.vecA, m0, M, (kb + 1) * BK, K, ra);
+      load_tile<BN, TB>(g.B, g.ldb, g.vecB, n0, g.N, (kb + 1) * BK, K, rb);
+    }
+    const float* as = As[cur];
+    const float* bs = Bs[cur];
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float a[TM], b[TN];
+#pragma unroll
+      for (int c = 0; c < RM; ++c) {
+        const float4 v = *reinterpret_cast<const float4*>(&as[kk * LDA_S + c * (BM / RM) + ty * 4]);
+        a[c * 4 + 0] = v.x; a[c * 4 + 1] = v.y; a[c * 4 + 2] = v.z; a[c * 4 + 3] = v.w;
+      }
+#pragma unroll
+      for (int c = 0; c < RN; ++c) {
+        const float4 v = *reinterpret_cast<const float4*>(&bs[kk * LDB_S + c * (BN / RN) + tx * 4]);
+        b[c * 4 + 0] = v.x; b[c * 4 + 1] = v.y; b[c * 4 + 2] = v.z; b[c * 4 + 3] = v.w;
+      }
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (kb + 1 < nkb) {
+      store_tile<BM, !TA>(As[cur ^ 1], ra);
+      store_tile<BN, TB>(Bs[cur ^ 1], rb);
+    }
+    __syncthreads();
+  }
+
+  // epilogue
+#pragma unroll
+  for (int ci = 0; ci < RM; ++ci) {
+#pragma unroll
+    for (int ii = 0; ii < 4; ++ii) {
+      const int m = m0 + ci * (BM / RM) + ty * 4 + ii;
+      if (m >= g.M) continue;
+      const bool live = m < M;  // rows in [M, g.M) inside a touched tile are written as zeros
+#pragma unroll
+      for (int cj = 0; cj < RN; ++cj) {
+        const int n = n0 + cj * (BN / RN) + tx * 4;
+        if (n >= g.N) continue;
+        float* cp = g.C + (size_t)m * g.ldc + n;
+        float v[4];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          float x = g.alpha * acc[ci * 4 + ii][cj * 4 + jj];
+          if (g.bias != nullptr && n + jj < g.N) x += __ldg(g.bias + n + jj);
+          v[jj] = live ? x : 0.f;
+        }
+        if (g.vecC && n + 3 < g.N) {
+          float4 o = make_float4(v[0], v[1], v[2], v[3]);
+          if (g.beta != 0.f && live) {
+            const float4 c = *reinterpret_cast<const float4*>(cp);
+            o.x = fmaf(g.beta, c.x, o.x); o.y = fmaf(g.beta, c.y, o.y);
+            o.z = fmaf(g.beta, c.z, o.z); o.w = fmaf(g.beta, c.w, o.w);
+          }
+          *reinterpret_cast<float4*>(cp) = o;
+        } else {
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            if (n + jj < g.N) {
+              float o = v[jj];
+              if (g.beta != 0.f && live) o = fmaf(g.beta, cp[jj], o);
+              cp[jj] = o;
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int BM, int BN, int TM, int TN>
+static void launch_ffma(const GemmArgs& g, int transA, int transB, cudaStream_t st) {
+  dim3 grid(ceil_div(g.N, BN), ceil_div(g.M, BM));
+  if (!transA && transB) gemm_ffma_kernel<BM, BN, TM, TN, false, true><<<grid, 256, 0, st>>>(g);
+  else if (!transA && !transB) gemm_ffma_kernel<BM, BN, TM, TN, false, false><<<grid, 256, 0, st>>>(g);
+  else if (transA && !transB) gemm_ffma_kernel<BM, BN, TM, TN, true, false><<<grid, 256, 0, st>>>(g);
+  else gemm_ffma_kernel<BM, BN, TM, TN, true, true><<<grid, 256, 0, st>>>(g);
+}
+
+static inline int aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+extern "C" int immtsf_gemm(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda,
+                           const float* B, int ldb, float beta, float* C, int ldc, const float* bias,
+                           const int32_t* ragged, int ragged_dim, int backend, void* stream) {
+  IMMTSF_REQUIRE(M >= 0 && N >= 0 && K >= 0, "gemm: negative dimension");
+  if (M == 0 || N == 0) return IMMTSF_OK;
+  IMMTSF_REQUIRE(A && B && C, "gemm: null operand");
+  IMMTSF_REQUIRE(ragged_dim >= 0 && ragged_dim <= 2, "gemm: ragged_dim must be 0,1,2");
+  IMMTSF_REQUIRE(ragged_dim == 0 || ragged != nullptr, "gemm: ragged_dim set but ragged pointer is null");
+  IMMTSF_REQUIRE(lda >= (transA ? M : K) && ldb >= (transB ? K : N) && ldc >= N, "gemm: leading dimension too small");
+  IMMTSF_REQUIRE(backend >= 0 && backend <= 2, "gemm: backend must be 0 (auto), 1 (ffma) or 2 (tcgen05)");
+  cudaStream_t st = (cudaStream_t)stream;
+
+  if (backend != 1) {
+    const int ok = immtsf_gemm_tc_eligible(transA, transB, M, N, K, A, lda, B, ldb, C, ldc);
+    if (ok) return immtsf_gemm_tc(transA, transB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, ragged, ragged_dim, st);
+    if (backend == 2) {
+      immtsf_set_error("gemm: tcgen05 backend requested but shape/alignment is not eligible");
+      return IMMTSF_ERR_UNSUPPORTED;
+    }
+  }
+
+  GemmArgs g;
+  g.M = M; g.N = N; g.K = K; g.alpha = alpha; g.beta = beta;
+  g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = C; g.ldc = ldc; g.bias = bias;
+  g.ragged = ragged; g.ragged_dim = ragged_dim;
+  g.vecA = aligned16(A) && (lda % 4 == 0);
+  g.vecB = aligned16(B) && (ldb % 4 == 0);
+  g.vecC = aligned16(C) && (ldc % 4 == 0);
+  // big tiles only when they still give every SM work
+  const long tiles128 = (long)ceil_div(M, 128) * ceil_div(N, 128);
+  if (tiles128 >= 148 && N >= 96) launch_ffma<128, 128, 8, 8>(g, transA, transB, st);
+  else launch_ffma<64, 64, 4, 4>(g, transA, transB, st);
+  IMMTSF_CHECK_LAUNCH("gemm_ffma");
+  return IMMTSF_OK;
+}
+
+// ------------------------------------------------------------------ colsum
+// out[n] = beta*out[n] + sum_m X[m,n]; grid.x over column tiles of 32, each CTA
+// walks all rows with 32x8 threads (coalesced along n) then reduces in smem.
+__global__ void colsum_kernel(const float* __restrict__ X, int M, int N, int ldx, float* __restrict__ out, float beta,
+                              const int32_t* __restrict__ ragged) {
+  __shared__ float red[8][33];
+  const int m_eff = ragged_rows(M, ragged);
+  const int n = blockIdx.x * 32 + threadIdx.x;
+  float s = 0.f;
+  if (n < N)
+    for (int m = threadIdx.y; m < m_eff; m += 8) s += X[(size_t)m * ldx + n];
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && n < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
+    out[n] = (beta != 0.f ? beta * out[n] : 0.f) + t;
+  }
+}
+extern "C" int immtsf_colsum(const float* X, int M, int N, int ldx, float* out, float beta, const int32_t* ragged,
+                             void* stream) {
+  if (N == 0) return IMMTSF_OK;
+  IMMTSF_REQUIRE(X && out, "colsum: null pointer");
+  colsum_kernel<<<ceil_div(N, 32), dim3(32, 8), 0, (cudaStream_t)stream>>>(X, M, N, ldx, out, beta, ragged);
+  IMMTSF_CHECK_LAUNCH("colsum");
+  return IMMTSF_OK;
+}

@@ -1,0 +1,381 @@
+// K2: TTF_RecAvg pooling, forward and backward.
+//
+// Forward replaces fusions/TTF_RecAvg.py:94-106:
+//   delta = clamp_min(t_hat - tau, 0); w = exp(-(delta/sigma)^2) (masked notes
+//   simply do not exist in the ragged layout); E_raw = sum_n w V'_n /
+//   clamp_min(sum_n w, 1e-6); E_drop = dropout(LayerNorm(E_raw)).
+// One CTA per (sample, tile of TT query times).  Each thread owns NCH float4
+// column groups of the d-wide row and TT accumulators per group; every V'
+// row of the segment is streamed once per query tile with 128-bit loads
+// (re-reads across tiles hit L1/L2: a segment is N_i * d * 4 B ~ 48 KB), the
+// recency weights are computed once per (note, t) into shared memory, the
+// LayerNorm statistics are block reductions over the register tile, and the
+// dropout mask is Philox on the flat [B,T,d] index.
+//
+// Algorithmic HBM bytes per sample (fp32): 4*(N_i*d [V'] + N_i [tau] + T
+// [t_hat] + T*d [E_drop out] (+ T*d E_raw when training)).
+//
+// Backward (autograd of the same lines): LayerNorm backward per row, then
+//   dS_t = dE_raw_t / den_t,  dV'_n = sum_t w_nt dS_t,
+//   dlog_sigma = sum_{n,t} (dS_t . V'_n + dwsum_t) * w_nt * 2 (delta/sigma)^2
+// where the (n,t) dot products are never formed: sum_n c_nt (dS_t . V'_n) =
+// dS_t . (sum_n c_nt V'_n), a second pooled vector accumulated in the same
+// pass.  d(den) uses the closed form sum_j dE_raw_j E_raw_j = s2*eps*rstd^2
+// (LayerNorm is scale invariant up to eps).
+#include "rowtile.cuh"
+#include "../../include/immtsf.h"
+
+struct PoolArgs {
+  const float* Vp; int ldv;
+  const float* tau; const int32_t* offsets;
+  const float* t_hat; int t_bstride;
+  const float* log_sigma; const float* gamma; const float* beta;
+  int B, T, d; float eps; uint32_t thr; uint64_t seed;
+  float* E_drop; float* E_raw; float* mean; float* rstd; float* wsum;
+  // backward only
+  const float* dE_drop; float* dVp; int lddv; float* dgamma; float* dbeta; float* dlog_sigma;
+};
+
+constexpr int POOL_NB = 32;  // notes per shared-memory weight block
+
+template <int NCH>
+__global__ void __launch_bounds__(256) recavg_pool_fwd_kernel(const PoolArgs a) {
+  constexpr int TT = 8 / NCH;
+  __shared__ float s_w[POOL_NB][TT];
+  __shared__ float s_red[32 * TT];
+  __shared__ float s_th[TT];
+  const int b = blockIdx.x, t0 = blockIdx.y * TT;
+  const int nb = a.offsets[b], ne = a.offsets[b + 1];
+  const float sigma = expf(__ldg(a.log_sigma));
+  const int d4 = a.d >> 2;
+  if (threadIdx.x < TT)
+    s_th[threadIdx.x] = (t0 + threadIdx.x < a.T) ? a.t_hat[(size_t)b * a.t_bstride + t0 + threadIdx.x] : 0.f;
+
+  float4 acc[TT][NCH];
+  float wsum[TT];
+#pragma unroll
+  for (int t = 0; t < TT; ++t) {
+    wsum[t] = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) acc[t][c] = f4_zero();
+  }
+  for (int n0 = nb; n0 < ne; n0 += POOL_NB) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < POOL_NB * TT; i += blockDim.x) {
+      const int nn = i / TT, t = i % TT, n = n0 + nn;
+      float w = 0.f;
+      if (n < ne) {
+        const float delta = fmaxf(s_th[t] - __ldg(a.tau + n), 0.f);
+        const float r = delta / sigma;
+        w = expf(-(r * r));
+      }
+      s_w[nn][t] = w;
+    }
+    __syncthreads();
+    const int cnt = min(POOL_NB, ne - n0);
+    for (int nn = 0; nn < cnt; ++nn) {
+      const float4* row = reinterpret_cast<const float4*>(a.Vp + (size_t)(n0 + nn) * a.ldv);
+      float4 v[NCH];
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const int col4 = threadIdx.x + c * blockDim.x;
+        v[c] = col4 < d4 ? __ldg(row + col4) : f4_zero();
+      }
+#pragma unroll
+      for (int t = 0; t < TT; ++t) {
+        const float w = s_w[nn][t];
+        wsum[t] += w;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) f4_fma(acc[t][c], w, v[c]);
+      }
+    }
+  }
+  // E_raw = E_wsum / clamp_min(denom, 1e-6)
+  float s1[TT];
+#pragma unroll
+  for (int t = 0; t < TT; ++t) {
+    const float den = fmaxf(wsum[t], 1e-6f);
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      acc[t][c].x /= den; acc[t][c].y /= den; acc[t][c].z /= den; acc[t][c].w /= den;
+      s += f4_sum(acc[t][c]);  // columns >= d are exactly 0
+    }
+    s1[t] = s;
+  }
+  block_sum_multi<TT>(s1, s_red);
+  float s2[TT];
+#pragma unroll
+  for (int t = 0; t < TT; ++t) {
+    const float mu = s1[t] / (float)a.d;
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int col4 = threadIdx.x + c * blockDim.x;
+      if (col4 < d4) {
+        const float dx = acc[t][c].x - mu, dy = acc[t][c].y - mu, dz = acc[t][c].z - mu, dw = acc[t][c].w - mu;
+        s += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+      }
+    }
+    s2[t] = s;
+  }
+  block_sum_multi<TT>(s2, s_red);
+  const float inv_keep = inv_keep_from_thr(a.thr);
+#pragma unroll
+  for (int t = 0; t < TT; ++t) {
+    const int tt = t0 + t;
+    if (tt >= a.T) continue;
+    const float mu = s1[t] / (float)a.d;
+    const float rs = 1.f / sqrtf(s2[t] / (float)a.d + a.eps);
+    const size_t rowi = (size_t)b * a.T + tt;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int col4 = threadIdx.x + c * blockDim.x;
+      if (col4 >= d4) continue;
+      const float4 x = acc[t][c];
+      const float4 g = __ldg(reinterpret_cast<const float4*>(a.gamma) + col4);
+      const float4 be = __ldg(reinterpret_cast<const float4*>(a.beta) + col4);
+      const float4 ks = dropout_scale4(a.seed, IMMTSF_SITE_TTF_DROPOUT, rowi * d4 + col4, a.thr, inv_keep);
+      float4 y;
+      y.x = ((x.x - mu) * rs * g.x + be.x) * ks.x;
+      y.y = ((x.y - mu) * rs * g.y + be.y) * ks.y;
+      y.z = ((x.z - mu) * rs * g.z + be.z) * ks.z;
+      y.w = ((x.w - mu) * rs * g.w + be.w) * ks.w;
+      reinterpret_cast<float4*>(a.E_drop + rowi * a.d)[col4] = y;
+      if (a.E_raw) reinterpret_cast<float4*>(a.E_raw + rowi * a.d)[col4] = x;
+    }
+    if (threadIdx.x == 0) {
+      if (a.mean) a.mean[rowi] = mu;
+      if (a.rstd) a.rstd[rowi] = rs;
+      if (a.wsum) a.wsum[rowi] = wsum[t];
+    }
+  }
+}
+
+template <int NCH>
+__global__ void __launch_bounds__(256) recavg_pool_bwd_kernel(const PoolArgs a) {
+  constexpr int TT = 8 / NCH;
+  __shared__ float s_w[POOL_NB][TT];
+  __shared__ float s_c[POOL_NB][TT];
+  __shared__ float s_red[32 * TT];
+  __shared__ float s_th[TT];
+  const int b = blockIdx.x;
+  const int nb = a.offsets[b], ne = a.offsets[b + 1];
+  const float sigma = expf(__ldg(a.log_sigma));
+  const int d4 = a.d >> 2;
+  const float inv_keep = inv_keep_from_thr(a.thr);
+  const float inv_d = 1.f / (float)a.d;
+
+  float4 dgam[NCH], dbet[NCH];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) { dgam[c] = f4_zero(); dbet[c] = f4_zero(); }
+  float dls = 0.f;
+
+  for (int t0 = 0; t0 < a.T; t0 += TT) {
+    __syncthreads();
+    if (threadIdx.x < TT)
+      s_th[threadIdx.x] = (t0 + threadIdx.x < a.T) ? a.t_hat[(size_t)b * a.t_bstride + t0 + threadIdx.x] : 0.f;
+    // ---- phase 1: LayerNorm backward for TT rows -> dS (in place of g)
+    float4 g[TT][NCH], xh[TT][NCH];
+    float s1[TT], s2[TT], rs[TT], den[TT], dwsum[TT];
+#pragma unroll
+    for (int t = 0; t < TT; ++t) {
+      const int tt = t0 + t;
+      const bool ok = tt < a.T;
+      const size_t rowi = (size_t)b * a.T + (ok ? tt : 0);
+      const float mu = ok ? a.mean[rowi] : 0.f;
+      rs[t] = ok ? a.rstd[rowi] : 0.f;
+      const float ws = ok ? a.wsum[rowi] : 1.f;
+      den[t] = fmaxf(ws, 1e-6f);
+      dwsum[t] = (ok && ws >= 1e-6f) ? 1.f : 0.f;  // clamp_min passes gradient where wsum >= 1e-6
+      float p1 = 0.f, p2 = 0.f;
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const int col4 = threadIdx.x + c * blockDim.x;
+        g[t][c] = f4_zero();
+        xh[t][c] = f4_zero();
+        if (ok && col4 < d4) {
+          float4 dy = __ldg(reinterpret_cast<const float4*>(a.dE_drop + rowi * a.d) + col4);
+          const float4 ks = dropout_scale4(a.seed, IMMTSF_SITE_TTF_DROPOUT, rowi * d4 + col4, a.thr, inv_keep);
+          dy.x *= ks.x; dy.y *= ks.y; dy.z *= ks.z; dy.w *= ks.w;
+          const float4 x = __ldg(reinterpret_cast<const float4*>(a.E_raw + rowi * a.d) + col4);
+          float4 h;
+          h.x = (x.x - mu) * rs[t]; h.y = (x.y - mu) * rs[t]; h.z = (x.z - mu) * rs[t]; h.w = (x.w - mu) * rs[t];
+          dgam[c].x = fmaf(dy.x, h.x, dgam[c].x); dgam[c].y = fmaf(dy.y, h.y, dgam[c].y);
+          dgam[c].z = fmaf(dy.z, h.z, dgam[c].z); dgam[c].w = fmaf(dy.w, h.w, dgam[c].w);
+          f4_add(dbet[c], dy);
+          const float4 ga = __ldg(reinterpret_cast<const float4*>(a.gamma) + col4);
+          float4 gg;
+          gg.x = dy.x * ga.x; gg.y = dy.y * ga.y; gg.z = dy.z * ga.z; gg.w = dy.w * ga.w;
+          g[t][c] = gg;
+          xh[t][c] = h;
+          p1 += f4_sum(gg);
+          p2 += f4_dot(gg, h);
+        }
+      }
+      s1[t] = p1;
+      s2[t] = p2;
+    }
+    block_sum_multi<TT>(s1, s_red);
+    block_sum_multi<TT>(s2, s_red);
+#pragma unroll
+    for (int t = 0; t < TT; ++t) {
+      const float m1 = s1[t] * inv_d, m2 = s2[t] * inv_d;
+      const float sc = rs[t] / den[t];
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        // dE_raw = rstd * (g - mean(g) - xhat * mean(g*xhat));  dS = dE_raw / den
+        float4 o;
+        o.x = sc * (g[t][c].x - m1 - xh[t][c].x * m2);
+        o.y = sc * (g[t][c].y - m1 - xh[t][c].y * m2);
+        o.z = sc * (g[t][c].z - m1 - xh[t][c].z * m2);
+        o.w = sc * (g[t][c].w - m1 - xh[t][c].w * m2);
+        const int col4 = threadIdx.x + c * blockDim.x;
+        g[t][c] = (col4 < d4 && t0 + t < a.T) ? o : f4_zero();
+      }
+      // d(den) = -sum_j dE_raw_j E_raw_j / den = -(s2 * eps * rstd^2) / den
+      dwsum[t] *= -(s2[t] * a.eps * rs[t] * rs[t]) / den[t];
+    }
+    // ---- phase 2: stream the segment: dV'_n, P2_t = sum_n c_nt V'_n, csum_t
+    float4 p2acc[TT][NCH];
+    float csum[TT];
+#pragma unroll
+    for (int t = 0; t < TT; ++t) {
+      csum[t] = 0.f;
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) p2acc[t][c] = f4_zero();
+    }
+    for (int n0 = nb; n0 < ne; n0 += POOL_NB) {
+      __syncthreads();
+      for (int i = threadIdx.x; i < POOL_NB * TT; i += blockDim.x) {
+        const int nn = i / TT, t = i % TT, n = n0 + nn;
+        float w = 0.f, cc = 0.f;
+        if (n < ne && t0 + t < a.T) {
+          const float delta = fmaxf(s_th[t] - __ldg(a.tau + n), 0.f);
+          const float r = delta / sigma;
+          w = expf(-(r * r));
+          cc = w * 2.f * r * r;  // dw/dlog_sigma
+        }
+        s_w[nn][t] = w;
+        s_c[nn][t] = cc;
+      }
+      __syncthreads();
+      const int cnt = min(POOL_NB, ne - n0);
+      for (int nn = 0; nn < cnt; ++nn) {
+        const size_t n = (size_t)(n0 + nn);
+        const float4* row = reinterpret_cast<const float4*>(a.Vp + n * a.ldv);
+        float4* drow = reinterpret_cast<float4*>(a.dVp + n * a.lddv);
+        float4 v[NCH], dv[NCH];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          const int col4 = threadIdx.x + c * blockDim.x;
+          v[c] = col4 < d4 ? __ldg(row + col4) : f4_zero();
+          dv[c] = f4_zero();
+        }
+#pragma unroll
+        for (int t = 0; t < TT; ++t) {
+          const float w = s_w[nn][t], cc = s_c[nn][t];
+          csum[t] += cc;
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+            f4_fma(p2acc[t][c], cc, v[c]);
+            f4_fma(dv[c], w, g[t][c]);
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          const int col4 = threadIdx.x + c * blockDim.x;
+          if (col4 < d4) {
+            if (t0 == 0) drow[col4] = dv[c];
+            else { float4 o = drow[col4]; f4_add(o, dv[c]); drow[col4] = o; }
+          }
+        }
+      }
+    }
+    // ---- phase 3: dlog_sigma contribution of this tile
+    float part[TT];
+#pragma unroll
+    for (int t = 0; t < TT; ++t) {
+      float s = 0.f;
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) s += f4_dot(g[t][c], p2acc[t][c]);
+      part[t] = s;
+    }
+    block_sum_multi<TT>(part, s_red);
+#pragma unroll
+    for (int t = 0; t < TT; ++t) dls += part[t] + dwsum[t] * csum[t];
+  }
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int col4 = threadIdx.x + c * blockDim.x;
+    if (col4 < d4) {
+      float* pg = a.dgamma + col4 * 4;
+      float* pb = a.dbeta + col4 * 4;
+      atomicAdd(pg + 0, dgam[c].x); atomicAdd(pg + 1, dgam[c].y); atomicAdd(pg + 2, dgam[c].z); atomicAdd(pg + 3, dgam[c].w);
+      atomicAdd(pb + 0, dbet[c].x); atomicAdd(pb + 1, dbet[c].y); atomicAdd(pb + 2, dbet[c].z); atomicAdd(pb + 3, dbet[c].w);
+    }
+  }
+  if (threadIdx.x == 0) atomicAdd(a.dlog_sigma, dls);
+}
+
+static int pool_geometry(int d, int& nch, int& threads) {
+  if (d <= 0 || (d & 3)) return -1;
+  const int d4 = d >> 2;
+  if (d4 <= 256) nch = 1;
+  else if (d4 <= 512) nch = 2;
+  else if (d4 <= 1024) nch = 4;
+  else return -1;
+  threads = ((ceil_div(d4, nch) + 31) / 32) * 32;
+  return 0;
+}
+
+extern "C" int immtsf_recavg_pool_fwd(const float* Vp, int ldv, const float* tau_flat, const int32_t* offsets,
+                                      const float* t_hat, int t_hat_bstride, const float* log_sigma,
+                                      const float* gamma, const float* beta, int B, int T, int d, float eps,
+                                      uint32_t drop_thr, uint64_t seed, float* E_drop, float* E_raw, float* mean,
+                                      float* rstd, float* wsum, void* stream) {
+  if (B == 0 || T == 0) return IMMTSF_OK;
+  IMMTSF_REQUIRE(Vp && tau_flat && offsets && t_hat && log_sigma && gamma && beta && E_drop, "recavg_pool_fwd: null pointer");
+  int nch, threads;
+  IMMTSF_REQUIRE(pool_geometry(d, nch, threads) == 0, "recavg_pool_fwd: d=%d must be a multiple of 4 and <= 4096", d);
+  IMMTSF_REQUIRE((ldv & 3) == 0 && ((uintptr_t)Vp & 15) == 0, "recavg_pool_fwd: Vp must be 16B aligned with ldv %% 4 == 0");
+  PoolArgs a = {};
+  a.Vp = Vp; a.ldv = ldv; a.tau = tau_flat; a.offsets = offsets; a.t_hat = t_hat; a.t_bstride = t_hat_bstride;
+  a.log_sigma = log_sigma; a.gamma = gamma; a.beta = beta; a.B = B; a.T = T; a.d = d; a.eps = eps;
+  a.thr = drop_thr; a.seed = seed; a.E_drop = E_drop; a.E_raw = E_raw; a.mean = mean; a.rstd = rstd; a.wsum = wsum;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int TT = 8 / nch;
+  dim3 grid(B, ceil_div(T, TT));
+  if (nch == 1) recavg_pool_fwd_kernel<1><<<grid, threads, 0, st>>>(a);
+  else if (nch == 2) recavg_pool_fwd_kernel<2><<<grid, threads, 0, st>>>(a);
+  else recavg_pool_fwd_kernel<4><<<grid, threads, 0, st>>>(a);
+  IMMTSF_CHECK_LAUNCH("recavg_pool_fwd");
+  return IMMTSF_OK;
+}
+
+extern "C" int immtsf_recavg_pool_bwd(const float* dE_drop, const float* E_raw, const float* mean, const float* rstd,
+                                      const float* wsum, const float* Vp, int ldv, const float* tau_flat,
+                                      const int32_t* offsets, const float* t_hat, int t_hat_bstride,
+                                      const float* log_sigma, const float* gamma, int B, int T, int d,
+                                      uint32_t drop_thr, uint64_t seed, float* dVp, int lddv, float* dgamma,
+                                      float* dbeta, float* dlog_sigma, void* stream) {
+  if (B == 0 || T == 0) return IMMTSF_OK;
+  IMMTSF_REQUIRE(dE_drop && E_raw && mean && rstd && wsum && Vp && tau_flat && offsets && t_hat && log_sigma && gamma &&
+                     dVp && dgamma && dbeta && dlog_sigma, "recavg_pool_bwd: null pointer");
+  int nch, threads;
+  IMMTSF_REQUIRE(pool_geometry(d, nch, threads) == 0, "recavg_pool_bwd: d=%d must be a multiple of 4 and <= 4096", d);
+  IMMTSF_REQUIRE((ldv & 3) == 0 && (lddv & 3) == 0 && ((uintptr_t)Vp & 15) == 0 && ((uintptr_t)dVp & 15) == 0,
+                 "recavg_pool_bwd: Vp/dVp must be 16B aligned with ld %% 4 == 0");
+  PoolArgs a = {};
+  a.Vp = Vp; a.ldv = ldv; a.tau = tau_flat; a.offsets = offsets; a.t_hat = t_hat; a.t_bstride = t_hat_bstride;
+  a.log_sigma = log_sigma; a.gamma = gamma; a.B = B; a.T = T; a.d = d; a.eps = 1e-5f;
+  a.thr = drop_thr; a.seed = seed; a.E_raw = const_cast<float*>(E_raw); a.mean = const_cast<float*>(mean);
+  a.rstd = const_cast<float*>(rstd); a.wsum = const_cast<float*>(wsum);
+  a.dE_drop = dE_drop; a.dVp = dVp; a.lddv = lddv; a.dgamma = dgamma; a.dbeta = dbeta; a.dlog_sigma = dlog_sigma;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (nch == 1) recavg_pool_bwd_kernel<1><<<B, threads, 0, st>>>(a);
+  else if (nch == 2) recavg_pool_bwd_kernel<2><<<B, threads, 0, st>>>(a);
+  else recavg_pool_bwd_kernel<4><<<B, threads, 0, st>>>(a);
+  IMMTSF_CHECK_LAUNCH("recavg_pool_bwd");
+  return IMMTSF_OK;
+}

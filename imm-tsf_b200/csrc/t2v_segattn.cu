@@ -1,0 +1,336 @@
+// K3 pieces of TTF_T2V_XAttn: Time2Vec features and the single-learned-query
+// attention over each ragged note segment.
+//
+// The reference (fusions/TTF_T2V_XAttn.py:143-166) broadcasts ONE learned query
+// to every (sample, query time), copies K/V T_f times and re-projects them
+// inside nn.MultiheadAttention.  Here K/V projections run once per note
+// (immtsf_gemm over sumN rows) and this kernel does, per sample and head:
+//   s_n = q_h . K_{n,h};  p = softmax_n(s);  o_{t,h} = sum_n drop_t(p_n) V_{n,h}
+// In eval / dropout 0 the output does not depend on t and is produced once
+// per sample (R = B rows); with attention dropout every (t,h,n) weight gets
+// its own Philox keep bit and R = B*T rows.
+#include "rowtile.cuh"
+#include "../../include/immtsf.h"
+
+// ------------------------------------------------------------------ Time2Vec
+// out[n, 0] = w_lin*tau + b_lin ; out[n, k] = sin(w_per[k-1]*tau + b_per[k-1])
+__global__ void time2vec_fwd_kernel(const float* __restrict__ tau, const float* __restrict__ w_lin,
+                                    const float* __restrict__ b_lin, const float* __restrict__ w_per,
+                                    const float* __restrict__ b_per, int d_tau, float* __restrict__ out, int ld,
+                                    const int32_t* __restrict__ m_dev, int M_alloc) {
+  const int m = ragged_rows(M_alloc, m_dev);
+  int end = (m + 127) / 128 * 128;
+  if (end > M_alloc) end = M_alloc;
+  for (int n = blockIdx.x; n < end; n += gridDim.x) {
+    float* o = out + (size_t)n * ld;
+    if (n < m) {
+      const float t = tau[n];
+      for (int k = threadIdx.x; k < d_tau; k += blockDim.x)
+        o[k] = (k == 0) ? fmaf(w_lin[0], t, b_lin[0]) : sinf(fmaf(w_per[k - 1], t, b_per[k - 1]));
+    } else {
+      for (int k = threadIdx.x; k < d_tau; k += blockDim.x) o[k] = 0.f;
+    }
+  }
+}
+
+// grid.x over feature tiles of 32, grid.y over row chunks; 32x8 threads
+__global__ void time2vec_bwd_kernel(const float* __restrict__ dphi, int ld, const float* __restrict__ tau,
+                                    const float* __restrict__ w_per, const float* __restrict__ b_per, int d_tau,
+                                    float* __restrict__ dw_lin, float* __restrict__ db_lin, float* __restrict__ dw_per,
+                                    float* __restrict__ db_per, const int32_t* __restrict__ m_dev, int M_alloc) {
+  __shared__ float rw[8][33], rb[8][33];
+  const int m = ragged_rows(M_alloc, m_dev);
+  const int k = blockIdx.x * 32 + threadIdx.x;
+  float sw = 0.f, sb = 0.f;
+  if (k < d_tau) {
+    const float wk = k == 0 ? 0.f : w_per[k - 1], bk = k == 0 ? 0.f : b_per[k - 1];
+    for (int n = blockIdx.y * 8 + threadIdx.y; n < m; n += gridDim.y * 8) {
+      const float t = tau[n];
+      const float g = dphi[(size_t)n * ld + k];
+      const float dpre = k == 0 ? g : g * cosf(fmaf(wk, t, bk));
+      sw = fmaf(dpre, t, sw);
+      sb += dpre;
+    }
+  }
+  rw[threadIdx.y][threadIdx.x] = sw;
+  rb[threadIdx.y][threadIdx.x] = sb;
+  __syncthreads();
+  if (threadIdx.y == 0 && k < d_tau) {
+    float a = 0.f, c = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a += rw[i][threadIdx.x]; c += rb[i][threadIdx.x]; }
+    if (k == 0) { atomicAdd(dw_lin, a); atomicAdd(db_lin, c); }
+    else { atomicAdd(dw_per + k - 1, a); atomicAdd(db_per + k - 1, c); }
+  }
+}
+
+extern "C" int immtsf_time2vec_fwd(const float* tau_flat, const float* w_lin, const float* b_lin, const float* w_per,
+                                   const float* b_per, int d_tau, float* out, int ld, const int32_t* m_dev,
+                                   int M_alloc, void* stream) {
+  if (M_alloc == 0) return IMMTSF_OK;
+  IMMTSF_REQUIRE(tau_flat && w_lin && b_lin && w_per && b_per && out && m_dev, "time2vec_fwd: null pointer");
+  IMMTSF_REQUIRE(d_tau > 1 && ld >= d_tau, "time2vec_fwd: d_tau must be > 1 (TTF_T2V_XAttn.py:14) and ld >= d_tau");
+  int grid = M_alloc < 148 * 8 ? M_alloc : 148 * 8;
+  time2vec_fwd_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(tau_flat, w_lin, b_lin, w_per, b_per, d_tau, out, ld, m_dev, M_alloc);
+  IMMTSF_CHECK_LAUNCH("time2vec_fwd");
+  return IMMTSF_OK;
+}
+
+extern "C" int immtsf_time2vec_bwd(const float* dphi, int ld, const float* tau_flat, const float* w_per,
+                                   const float* b_per, int d_tau, float* dw_lin, float* db_lin, float* dw_per,
+                                   float* db_per, const int32_t* m_dev, int M_alloc, void* stream) {
+  if (M_alloc == 0) return IMMTSF_OK;
+  IMMTSF_REQUIRE(dphi && tau_flat && w_per && b_per && dw_lin && db_lin && dw_per && db_per && m_dev, "time2vec_bwd: null pointer");
+  int gy = ceil_div(M_alloc, 64);
+  if (gy > 64) gy = 64;
+  dim3 grid(ceil_div(d_tau, 32), gy);
+  time2vec_bwd_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(dphi, ld, tau_flat, w_per, b_per, d_tau, dw_lin, db_lin,
+                                                                       dw_per, db_per, m_dev, M_alloc);
+  IMMTSF_CHECK_LAUNCH("time2vec_bwd");
+  return IMMTSF_OK;
+}
+
+// ------------------------------------------------------------- segment attention
+struct SegArgs {
+  const float* q; const float* KVp; const int32_t* offsets;
+  int B, T, H, d, hd, N_max, per_query, TT; uint32_t thr; uint64_t seed;
+  float* attn_cat; float* probs;
+  const float* dO; float* dKVp; float* dq_partial;
+};
+
+// warp-cooperative dot of two length-n vectors (coalesced scalar loads)
+__device__ __forceinline__ float warp_dot(const float* __restrict__ a, const float* __restrict__ b, int n, int lane) {
+  float s = 0.f;
+  for (int j = lane; j < n; j += 32) s = fmaf(a[j], b[j], s);
+  return warp_sum(s);
+}
+
+// smem: s_p [H][N_max] | s_pt [TT][H][N_max]
+__global__ void __launch_bounds__(256) segattn_fwd_kernel(const SegArgs a) {
+  extern __shared__ float smem[];
+  const int H = a.H, d = a.d, hd = a.hd, NM = a.N_max, TT = a.TT;
+  float* s_p = smem;
+  float* s_pt = smem + (size_t)H * NM;
+  const int b = blockIdx.x;
+  const int nb = a.offsets[b], ne = a.offsets[b + 1], nn = ne - nb;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int ld = 2 * d, d4 = d >> 2;
+  const int Teff = a.per_query ? a.T : 1;
+  const float inv_keep = inv_keep_from_thr(a.thr);
+  if (nn == 0) {  // no notes: attention output is defined as 0 (reference zeroes it, :171-173)
+    for (int t = 0; t < Teff; ++t)
+      for (int c = threadIdx.x; c < d; c += blockDim.x) a.attn_cat[((size_t)b * Teff + t) * d + c] = 0.f;
+    return;
+  }
+  // 1) scores
+  for (int i = w; i < nn * H; i += nw) {
+    const int n = i / H, h = i % H;
+    const float s = warp_dot(a.q + h * hd, a.KVp + (size_t)(nb + n) * ld + h * hd, hd, lane);
+    if (lane == 0) s_p[h * NM + n] = s;
+  }
+  __syncthreads();
+  // 2) softmax over the segment, one warp per head
+  for (int h = w; h < H; h += nw) {
+    float mx = -INFINITY;
+    for (int n = lane; n < nn; n += 32) mx = fmaxf(mx, s_p[h * NM + n]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int n = lane; n < nn; n += 32) {
+      const float e = expf(s_p[h * NM + n] - mx);
+      s_p[h * NM + n] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    for (int n = lane; n < nn; n += 32) {
+      const float p = s_p[h * NM + n] / sum;
+      s_p[h * NM + n] = p;
+      if (a.probs) a.probs[(size_t)(nb + n) * H + h] = p;
+    }
+  }
+  __syncthreads();
+  // 3) weighted sums, TT query times at a time
+  for (int t0 = 0; t0 < Teff; t0 += TT) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < TT * H * nn; i += blockDim.x) {
+      const int tt = i / (H * nn), r = i % (H * nn), h = r / nn, n = r % nn;
+      const int t = t0 + tt;
+      float p = 0.f;
+      if (t < Teff) {
+        p = s_p[h * NM + n];
+        if (a.per_query)
+          p *= dropout_scale(a.seed, IMMTSF_SITE_TTF_ATTN, (((uint64_t)b * a.T + t) * H + h) * NM + n, a.thr, inv_keep);
+      }
+      s_pt[((size_t)tt * H + h) * NM + n] = p;
+    }
+    __syncthreads();
+    for (int col4 = threadIdx.x; col4 < d4; col4 += blockDim.x) {
+      const int h = (col4 * 4) / hd;
+      float4 acc[4];
+#pragma unroll
+      for (int tt = 0; tt < 4; ++tt) acc[tt] = f4_zero();
+      for (int n = 0; n < nn; ++n) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(a.KVp + (size_t)(nb + n) * ld + d) + col4);
+#pragma unroll
+        for (int tt = 0; tt < 4; ++tt)
+          if (tt < TT) f4_fma(acc[tt], s_pt[((size_t)tt * H + h) * NM + n], v);
+      }
+#pragma unroll
+      for (int tt = 0; tt < 4; ++tt)
+        if (tt < TT && t0 + tt < Teff)
+          reinterpret_cast<float4*>(a.attn_cat + ((size_t)b * Teff + t0 + tt) * d)[col4] = acc[tt];
+    }
+  }
+}
+
+// smem: s_p [H][NM] | s_ds [H][NM] | s_dp [TT][H][NM]
+__global__ void __launch_bounds__(256) segattn_bwd_kernel(const SegArgs a) {
+  extern __shared__ float smem[];
+  const int H = a.H, d = a.d, hd = a.hd, NM = a.N_max, TT = a.TT;
+  float* s_p = smem;
+  float* s_ds = s_p + (size_t)H * NM;
+  float* s_dp = s_ds + (size_t)H * NM;
+  const int b = blockIdx.x;
+  const int nb = a.offsets[b], ne = a.offsets[b + 1], nn = ne - nb;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int ld = 2 * d, d4 = d >> 2;
+  const int Teff = a.per_query ? a.T : 1;
+  const float inv_keep = inv_keep_from_thr(a.thr);
+  if (nn == 0) {
+    for (int c = threadIdx.x; c < d; c += blockDim.x) a.dq_partial[(size_t)b * d + c] = 0.f;
+    return;
+  }
+  for (int i = threadIdx.x; i < H * nn; i += blockDim.x) {
+    const int h = i / nn, n = i % nn;
+    s_p[h * NM + n] = a.probs[(size_t)(nb + n) * H + h];
+    s_ds[h * NM + n] = 0.f;
+  }
+  for (int t0 = 0; t0 < Teff; t0 += TT) {
+    __syncthreads();
+    // a) dp~[tt][h][n] = dO[t, head h] . V[n, head h]
+    for (int i = w; i < TT * H * nn; i += nw) {
+      const int tt = i / (H * nn), r = i % (H * nn), h = r / nn, n = r % nn;
+      const int t = t0 + tt;
+      float s = 0.f;
+      if (t < Teff)
+        s = warp_dot(a.dO + ((size_t)b * Teff + t) * d + h * hd, a.KVp + (size_t)(nb + n) * ld + d + h * hd, hd, lane);
+      if (lane == 0) s_dp[((size_t)tt * H + h) * NM + n] = s;
+    }
+    __syncthreads();
+    // b) softmax backward (accumulated over t) ; s_dp <- dropped probabilities p~
+    for (int h = w; h < H; h += nw) {
+      for (int tt = 0; tt < TT; ++tt) {
+        const int t = t0 + tt;
+        if (t >= Teff) {
+          for (int n = lane; n < nn; n += 32) s_dp[((size_t)tt * H + h) * NM + n] = 0.f;
+          continue;
+        }
+        float D = 0.f;
+        for (int n = lane; n < nn; n += 32) {
+          float ks = 1.f;
+          if (a.per_query)
+            ks = dropout_scale(a.seed, IMMTSF_SITE_TTF_ATTN, (((uint64_t)b * a.T + t) * H + h) * NM + n, a.thr, inv_keep);
+          const float dp = s_dp[((size_t)tt * H + h) * NM + n] * ks;
+          s_dp[((size_t)tt * H + h) * NM + n] = dp;  // temporarily dp
+          D = fmaf(s_p[h * NM + n], dp, D);
+        }
+        D = warp_sum(D);
+        for (int n = lane; n < nn; n += 32) {
+          float ks = 1.f;
+          if (a.per_query)
+            ks = dropout_scale(a.seed, IMMTSF_SITE_TTF_ATTN, (((uint64_t)b * a.T + t) * H + h) * NM + n, a.thr, inv_keep);
+          const float p = s_p[h * NM + n];
+          const float dp = s_dp[((size_t)tt * H + h) * NM + n];
+          s_ds[h * NM + n] += p * (dp - D);
+          s_dp[((size_t)tt * H + h) * NM + n] = p * ks;
+        }
+      }
+    }
+    __syncthreads();
+    // c) dV[n] += sum_tt p~[tt][h][n] dO[t]
+    for (int col4 = threadIdx.x; col4 < d4; col4 += blockDim.x) {
+      const int h = (col4 * 4) / hd;
+      float4 go[4];
+#pragma unroll
+      for (int tt = 0; tt < 4; ++tt)
+        go[tt] = (tt < TT && t0 + tt < Teff)
+                     ? __ldg(reinterpret_cast<const float4*>(a.dO + ((size_t)b * Teff + t0 + tt) * d) + col4)
+                     : f4_zero();
+      for (int n = 0; n < nn; ++n) {
+        float4 dv = f4_zero();
+#pragma unroll
+        for (int tt = 0; tt < 4; ++tt)
+          if (tt < TT) f4_fma(dv, s_dp[((size_t)tt * H + h) * NM + n], go[tt]);
+        float4* dst = reinterpret_cast<float4*>(a.dKVp + (size_t)(nb + n) * ld + d) + col4;
+        if (t0 == 0) *dst = dv;
+        else { float4 o = *dst; f4_add(o, dv); *dst = o; }
+      }
+    }
+  }
+  __syncthreads();
+  // d) dK[n] = ds[h][n] q ; dq_b = sum_n ds[h][n] K[n]
+  for (int col4 = threadIdx.x; col4 < d4; col4 += blockDim.x) {
+    const int h = (col4 * 4) / hd;
+    const float4 qv = __ldg(reinterpret_cast<const float4*>(a.q) + col4);
+    float4 dq = f4_zero();
+    for (int n = 0; n < nn; ++n) {
+      const float ds = s_ds[h * NM + n];
+      const float4 kv = __ldg(reinterpret_cast<const float4*>(a.KVp + (size_t)(nb + n) * ld) + col4);
+      f4_fma(dq, ds, kv);
+      float4 dk;
+      dk.x = ds * qv.x; dk.y = ds * qv.y; dk.z = ds * qv.z; dk.w = ds * qv.w;
+      reinterpret_cast<float4*>(a.dKVp + (size_t)(nb + n) * ld)[col4] = dk;
+    }
+    reinterpret_cast<float4*>(a.dq_partial + (size_t)b * d)[col4] = dq;
+  }
+}
+
+static int seg_setup(SegArgs& a, int extra_planes, size_t& smem) {
+  // planes of [H][N_max] floats: extra_planes fixed + TT for the per-t tile
+  const size_t plane = (size_t)a.H * a.N_max * sizeof(float);
+  int TT = 4;
+  while (TT > 1 && (extra_planes + TT) * plane > 200 * 1024) TT >>= 1;
+  if ((extra_planes + TT) * plane > 200 * 1024) return -1;
+  if (!a.per_query) TT = 1;
+  a.TT = TT;
+  smem = (extra_planes + TT) * plane;
+  return 0;
+}
+
+extern "C" int immtsf_segattn_fwd(const float* q, const float* KVp, const int32_t* offsets, int B, int T, int H, int d,
+                                  int N_max, int per_query, uint32_t drop_thr, uint64_t seed, float* attn_cat,
+                                  float* probs, void* stream) {
+  if (B == 0) return IMMTSF_OK;
+  IMMTSF_REQUIRE(q && KVp && offsets && attn_cat, "segattn_fwd: null pointer");
+  IMMTSF_REQUIRE(H >= 1 && d % H == 0 && ((d / H) & 3) == 0, "segattn_fwd: head_dim = d/H must be a multiple of 4 (d=%d H=%d)", d, H);
+  IMMTSF_REQUIRE(((uintptr_t)KVp & 15) == 0 && ((uintptr_t)attn_cat & 15) == 0, "segattn_fwd: buffers must be 16B aligned");
+  IMMTSF_REQUIRE(N_max >= 1 && T >= 1, "segattn_fwd: N_max and T must be >= 1");
+  SegArgs a = {};
+  a.q = q; a.KVp = KVp; a.offsets = offsets; a.B = B; a.T = T; a.H = H; a.d = d; a.hd = d / H; a.N_max = N_max;
+  a.per_query = per_query ? 1 : 0; a.thr = per_query ? drop_thr : 0u; a.seed = seed; a.attn_cat = attn_cat; a.probs = probs;
+  size_t smem;
+  if (seg_setup(a, 1, smem)) { immtsf_set_error("segattn_fwd: H*N_max=%d too large for shared memory", H * N_max); return IMMTSF_ERR_UNSUPPORTED; }
+  if (smem > 48 * 1024) cudaFuncSetAttribute(segattn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  segattn_fwd_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(a);
+  IMMTSF_CHECK_LAUNCH("segattn_fwd");
+  return IMMTSF_OK;
+}
+
+extern "C" int immtsf_segattn_bwd(const float* d_attn_cat, const float* q, const float* KVp, const float* probs,
+                                  const int32_t* offsets, int B, int T, int H, int d, int N_max, int per_query,
+                                  uint32_t drop_thr, uint64_t seed, float* dKVp, float* dq_partial, void* stream) {
+  if (B == 0) return IMMTSF_OK;
+  IMMTSF_REQUIRE(d_attn_cat && q && KVp && probs && offsets && dKVp && dq_partial, "segattn_bwd: null pointer");
+  IMMTSF_REQUIRE(H >= 1 && d % H == 0 && ((d / H) & 3) == 0, "segattn_bwd: head_dim = d/H must be a multiple of 4 (d=%d H=%d)", d, H);
+  IMMTSF_REQUIRE(((uintptr_t)KVp & 15) == 0 && ((uintptr_t)dKVp & 15) == 0 && ((uintptr_t)d_attn_cat & 15) == 0 &&
+                     ((uintptr_t)q & 15) == 0 && ((uintptr_t)dq_partial & 15) == 0, "segattn_bwd: buffers must be 16B aligned");
+  SegArgs a = {};
+  a.q = q; a.KVp = KVp; a.offsets = offsets; a.B = B; a.T = T; a.H = H; a.d = d; a.hd = d / H; a.N_max = N_max;
+  a.per_query = per_query ? 1 : 0; a.thr = per_query ? drop_thr : 0u; a.seed = seed; a.probs = const_cast<float*>(probs);
+  a.dO = d_attn_cat; a.dKVp = dKVp; a.dq_partial = dq_partial;
+  size_t smem;
+  if (seg_setup(a, 2, smem)) { immtsf_set_error("segattn_bwd: H*N_max=%d too large for shared memory", H * N_max); return IMMTSF_ERR_UNSUPPORTED; }
+  if (smem > 48 * 1024) cudaFuncSetAttribute(segattn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  segattn_bwd_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(a);
+  IMMTSF_CHECK_LAUNCH("segattn_bwd");
+  return IMMTSF_OK;
+}

@@ -1,0 +1,72 @@
+"""FusionModel -- the plugin surface of the hot path, unchanged for callers
+(reference: fusions/FusionModel.py:24-113): `FusionModel(args)` with the same
+Namespace attributes, `forward(notes_input, tau, t_hat, Y_ts) -> Y_out`, the
+same `--TTF_module` / `--MMF_module` registries, the same state_dict.
+
+Differences in schedule only: the padded batch is converted to the ragged CSR
+layout once and shared by TTF and MMF; the reference's three isnan().any()
+host syncs (:103-112) plus the ones inside the TTF/MMF modules are folded into
+device flags read once at the end of forward (still raising ValueError)."""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from immtsf import ops, runtime
+from fusions import _common as cm
+from fusions.TTF_RecAvg import TTF_RecAvg
+from fusions.TTF_T2V_XAttn import TTF_T2V_XAttn
+from fusions.MMF_GR_Add import MMF_GR_Add
+from fusions.MMF_XAttn_Add import MMF_XAttn_Add
+
+_TTF_CLASSES = {"TTF_RecAvg": TTF_RecAvg, "TTF_T2V_XAttn": TTF_T2V_XAttn}
+_MMF_CLASSES = {"MMF_GR_Add": MMF_GR_Add, "MMF_XAttn_Add": MMF_XAttn_Add}
+
+
+class FusionModel(nn.Module):
+    def __init__(self, args):
+        super().__init__()
+        TTF_ref, MMF_ref = args.TTF_module, args.MMF_module
+        TTF_cls = _TTF_CLASSES.get(TTF_ref, TTF_ref) if isinstance(TTF_ref, str) else TTF_ref
+        MMF_cls = _MMF_CLASSES.get(MMF_ref, MMF_ref) if isinstance(MMF_ref, str) else MMF_ref
+        print(f"Using TTF module: {args.TTF_module}")
+        print(f"Using MMF module: {args.MMF_module}")
+        common = dict(max_length=args.max_length, device=args.device, use_text_embeddings=args.use_text_embeddings,
+                      dropout=args.dropout, d_txt=args.d_txt)
+        if TTF_cls is TTF_RecAvg:
+            self.ttf = TTF_cls(args.llm_model_fusion, args.llm_layers_fusion, recency_sigma=args.recency_sigma, **common)
+        else:
+            self.ttf = TTF_cls(args.llm_model_fusion, args.llm_layers_fusion, n_heads_fusion=args.n_heads_fusion, **common)
+        d_txt = self.ttf.d_txt
+        if MMF_cls is MMF_GR_Add:
+            self.mmf = MMF_cls(d_txt=d_txt, C=args.C, hidden_dim=args.C, dropout=args.dropout)
+        else:
+            self.mmf = MMF_cls(d_txt=d_txt, C=args.C, d_attn=d_txt, n_heads_fusion=args.n_heads_fusion,
+                               dropout=args.dropout, kappa=args.kappa)
+
+    def forward(self, notes_input, tau, t_hat, Y_ts):
+        cm.require_cuda(notes_input, "FusionModel")
+        if not (hasattr(self.ttf, "forward_ragged") and hasattr(self.mmf, "forward_flags")):
+            # a user-supplied TTF/MMF class: plain composition, reference order of checks
+            if torch.isnan(Y_ts).any():
+                raise ValueError("Y_ts contains NaN values.")
+            E_txt, M_txt = self.ttf(notes_input, tau, t_hat)
+            if torch.isnan(E_txt).any():
+                raise ValueError("E_txt contains NaN values.")
+            Y_out = self.mmf(Y_ts, E_txt, M_txt)
+            if torch.isnan(Y_out).any():
+                raise ValueError("Y_out contains NaN values.")
+            return Y_out
+        flags = runtime.new_flags(Y_ts.device)
+        check = runtime.nan_check_enabled()
+        Y32 = cm.as_f32(Y_ts)
+        if check:
+            ops.nan_check(Y32, flags, ops.FLAG_Y)
+        r = ops.csr_build(cm.as_f32(notes_input), cm.as_f32(tau), flags)
+        E_txt, M_txt = self.ttf.forward_ragged(r, t_hat)
+        if check:
+            # the broadcast view of T2V eval mode has B distinct rows: check those only
+            ops.nan_check(E_txt[:, :1] if E_txt.stride(1) == 0 else E_txt, flags, ops.FLAG_E)
+        Y_out = self.mmf.forward_flags(Y32, E_txt, M_txt, flags)
+        runtime.raise_on_flags(flags)
+        return Y_out

@@ -1,0 +1,44 @@
+"""Shared host logic of the drop-in fusion modules."""
+from __future__ import annotations
+
+import torch
+
+from immtsf import ops, runtime
+
+
+def require_cuda(t: torch.Tensor, who: str):
+    if not isinstance(t, torch.Tensor):
+        raise NotImplementedError(
+            f"{who}: raw note strings (use_text_embeddings=False) are not supported by the B200 path; "
+            "pass precomputed embeddings [B, N_max, d_model]."
+        )
+    if not t.is_cuda:
+        raise RuntimeError(f"{who}: inputs must be CUDA tensors -- the immtsf path has no CPU fallback")
+
+
+def as_f32(t: torch.Tensor) -> torch.Tensor:
+    return t if t.dtype == torch.float32 else t.float()
+
+
+def fix_t_hat(t_hat: torch.Tensor, B: int):
+    """Reference: fusions/TTF_RecAvg.py:86-91 / fusions/TTF_T2V_XAttn.py:128-133.
+    A 1-D t_hat is shared by all samples (no repeat: kernels take a batch stride of 0)."""
+    if t_hat.dim() == 1:
+        return as_f32(t_hat).contiguous(), t_hat.shape[0]
+    if t_hat.shape[0] != B:
+        raise ValueError(f"Expected t_hat shape (B, T_f) or (T_f,), got {t_hat.shape}")
+    return as_f32(t_hat).contiguous(), t_hat.shape[1]
+
+
+def m_txt_bool(r: ops.RaggedNotes) -> torch.Tensor:
+    return r.m_txt[: r.B].view(r.B, 1).bool()
+
+
+def m_txt_u8(M_txt: torch.Tensor, B: int) -> torch.Tensor:
+    return M_txt.reshape(B).to(torch.uint8).contiguous()
+
+
+def dropout_args(module_p: float, training: bool):
+    thr = ops.drop_thr(module_p) if training else 0
+    seed = runtime.SEEDS.next() if thr else 0
+    return thr, seed

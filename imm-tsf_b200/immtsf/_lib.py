@@ -1,0 +1,87 @@
+"""ctypes binding of libimmtsf.so (the C ABI declared in include/immtsf.h).
+
+There is deliberately no fallback: if the shared library is missing the import
+of any compute path raises, and every entry point returns an error on a device
+that is not sm_100.  Build the library with ``python __graft_entry__.py`` (or
+``make -C imm-tsf_b200/csrc``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "libimmtsf.so")
+
+P = C.c_void_p
+I = C.c_int
+F = C.c_float
+U32 = C.c_uint32
+U64 = C.c_uint64
+SZ = C.c_size_t
+
+# name -> argtypes, in the order of include/immtsf.h
+SIGNATURES = {
+    "immtsf_version": [],
+    "immtsf_device_supported": [I],
+    "immtsf_csr_build": [P, P, I, I, I, P, P, P, P, P, P, P, P, I, P],
+    "immtsf_nan_check": [P, SZ, P, I, P],
+    "immtsf_zero_pad_rows": [P, I, I, P, I, P],
+    "immtsf_gemm": [I, I, I, I, I, F, P, I, P, I, F, P, I, P, P, I, I, P],
+    "immtsf_colsum": [P, I, I, I, P, F, P, P],
+    "immtsf_recavg_pool_fwd": [P, I, P, P, P, I, P, P, P, I, I, I, F, U32, U64, P, P, P, P, P, P],
+    "immtsf_recavg_pool_bwd": [P, P, P, P, P, P, I, P, P, P, I, P, P, I, I, I, U32, U64, P, I, P, P, P, P],
+    "immtsf_time2vec_fwd": [P, P, P, P, P, I, P, I, P, I, P],
+    "immtsf_time2vec_bwd": [P, I, P, P, P, I, P, P, P, P, P, I, P],
+    "immtsf_segattn_fwd": [P, P, P, I, I, I, I, I, I, U32, U64, P, P, P],
+    "immtsf_segattn_bwd": [P, P, P, P, P, I, I, I, I, I, I, U32, U64, P, P, P],
+    "immtsf_ln_fwd": [P, I, P, P, I, P, P, I, I, F, U32, U64, U32, P, P, P, P],
+    "immtsf_ln_bwd": [P, P, I, P, P, I, P, P, P, I, I, U32, U64, U32, P, P, P, P, P],
+    "immtsf_gru_scan_fwd": [P, P, P, I, I, I, P, P, P],
+    "immtsf_gr_tail_fwd": [P, P, P, P, P, P, P, P, I, I, I, F, U32, U64, P, P, P],
+    "immtsf_gr_tail_bwd": [P, P, P, P, P, P, P, P, I, I, I, F, U32, U64, P, P, P, P, P, P],
+    "immtsf_gru_scan_bwd": [P, P, P, P, P, I, I, I, P, P, P],
+    "immtsf_xattn_core_fwd": [P, I, P, I, P, I, P, I, I, I, I, U32, U64, P, I, P, P],
+    "immtsf_xattn_core_bwd": [P, I, P, I, P, I, P, I, P, P, I, I, I, I, U32, U64, P, I, P, I, P, I, P],
+    "immtsf_xattn_tail_fwd": [P, P, P, P, P, I, I, I, F, F, U32, U64, P, P, P],
+    "immtsf_xattn_tail_bwd": [P, P, P, P, I, I, I, F, F, U32, U64, P, P, P, P],
+    "immtsf_axpby": [P, F, P, I, SZ, P],
+    "immtsf_group_sum_rows": [P, I, I, I, I, P, P],
+}
+
+_lib = None
+
+
+class ImmtsfError(RuntimeError):
+    pass
+
+
+def load():
+    """Load libimmtsf.so once; raise loudly when it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImmtsfError(
+            f"{LIB_PATH} not found: the immtsf CUDA library is not built. "
+            "Run `python __graft_entry__.py` (nvcc, sm_100a). There is no CPU fallback."
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = I
+    lib.immtsf_last_error_string.argtypes = []
+    lib.immtsf_last_error_string.restype = C.c_char_p
+    _lib = lib
+    return lib
+
+
+def call(name, *args):
+    """Call an entry point; raise ImmtsfError with the library's message on failure."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        msg = lib.immtsf_last_error_string()
+        raise ImmtsfError(f"{name} failed (rc={rc}): {msg.decode() if msg else ''}")
+    return rc

@@ -1,0 +1,244 @@
+"""autograd.Function wrappers: one per reference module, forward and backward
+composed from the immtsf CUDA kernels (imm-tsf_b200/csrc).  No torch math op
+sits on the compute path; torch provides memory, views and the autograd tape.
+
+Reference semantics (file:line):
+  RecAvgFn     fusions/TTF_RecAvg.py:54-112
+  T2VXAttnFn   fusions/TTF_T2V_XAttn.py:93-184 (+ nn.MultiheadAttention internals)
+  GRAddFn      fusions/MMF_GR_Add.py:31-61
+  XAttnAddFn   fusions/MMF_XAttn_Add.py:56-103
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import ops
+from .ops import RaggedNotes
+
+_f32 = torch.float32
+
+
+def _need_save(*params) -> bool:
+    return torch.is_grad_enabled() and any(p is not None and p.requires_grad for p in params)
+
+
+# ============================================================== TTF_RecAvg
+class RecAvgFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, r: RaggedNotes, t_hat, T, thr, seed, save, log_sigma, W_in, b_in, gamma, beta, W_p, b_p):
+        B = r.B
+        d = W_p.shape[0]
+        Vp = ops.linear_fwd(r.emb_flat, W_in, b_in, ragged=r.m_dev) if W_in is not None else r.emb_flat
+        E_drop, E_raw, mean, rstd, wsum = ops.recavg_pool_fwd(Vp, r, t_hat, log_sigma, gamma, beta, T, d, thr, seed, save)
+        E_txt = ops.linear_fwd(E_drop.view(B * T, d), W_p, b_p).view(B, T, d)
+        if save:
+            ctx.r, ctx.T, ctx.thr, ctx.seed, ctx.has_in = r, T, thr, seed, W_in is not None
+            ctx.save_for_backward(t_hat, log_sigma, W_in, gamma, W_p, Vp, E_drop, E_raw, mean, rstd, wsum)
+        return E_txt
+
+    @staticmethod
+    def backward(ctx, dE_txt):
+        t_hat, log_sigma, W_in, gamma, W_p, Vp, E_drop, E_raw, mean, rstd, wsum = ctx.saved_tensors
+        r, T = ctx.r, ctx.T
+        B, d = r.B, W_p.shape[0]
+        dE = dE_txt.contiguous().view(B * T, d)
+        dW_p = ops.linear_wgrad(dE, E_drop.view(B * T, d))
+        db_p = ops.colsum(dE)
+        dE_drop = ops.linear_dgrad(dE, W_p)
+        dVp, dgamma, dbeta, dls = ops.recavg_pool_bwd(dE_drop, E_raw, mean, rstd, wsum, Vp, r, t_hat, log_sigma, gamma, T, d,
+                                                      ctx.thr, ctx.seed)
+        dW_in = db_in = None
+        if ctx.has_in:
+            dW_in = ops.linear_wgrad(dVp, r.emb_flat, ragged=r.m_dev)
+            db_in = ops.colsum(dVp, ragged=r.m_dev)
+        return None, None, None, None, None, None, dls, dW_in, db_in, dgamma, dbeta, dW_p, db_p
+
+
+# ============================================================== TTF_T2V_XAttn
+class T2VXAttnFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, r: RaggedNotes, T, H, thr, seed, save, Qp, W_in, b_in, w_lin, b_lin, w_per, b_per, W_kv, b_kv,
+                in_w, in_b, out_w, out_b, gamma, beta, W_po, b_po):
+        B = r.B
+        d = W_po.shape[0]
+        dt = d // 2
+        dev = Qp.device
+        per_query = thr != 0  # attention dropout makes every (sample, query) row distinct
+        # [V' ; phi] concat buffer (TTF_T2V_XAttn.py:139), written in place by the two producers
+        Xcat = torch.empty(r.M_alloc, d + dt, dtype=_f32, device=dev)
+        if W_in is not None:
+            ops.gemm(r.emb_flat, W_in, Xcat[:, :d], transB=True, bias=b_in, ragged=r.m_dev, ragged_dim=1)
+        else:
+            Xcat[:, :d].copy_(r.emb_flat)
+        ops.time2vec_fwd(r, w_lin, b_lin, w_per, b_per, dt, Xcat[:, d:])
+        X = ops.linear_fwd(Xcat, W_kv, b_kv, ragged=r.m_dev)  # :140
+        KVp = ops.linear_fwd(X, in_w[d:], in_b[d:], ragged=r.m_dev)  # MHA k/v in-projection, once per note
+        scale = math.sqrt(1.0 / float(d // H))
+        q0 = ops.linear_fwd(Qp.view(1, d), in_w[:d], in_b[:d])
+        q = ops.axpby(q0, scale, torch.empty_like(q0), False)
+        attn_cat, probs = ops.segattn_fwd(q, KVp, r, T, H, d, per_query, thr, seed, save)
+        attn_out = ops.linear_fwd(attn_cat, out_w, out_b)
+        rps = T if per_query else 1
+        y, mean, rstd = ops.ln_fwd(attn_out, Qp.view(d), r.m_txt, rps, gamma, beta, thr, seed, ops.SITE_TTF_DROPOUT, save)
+        E = ops.linear_fwd(y, W_po, b_po)
+        if save:
+            ctx.r, ctx.T, ctx.H, ctx.thr, ctx.seed = r, T, H, thr, seed
+            ctx.has_in, ctx.per_query, ctx.scale = W_in is not None, per_query, scale
+            ctx.save_for_backward(Qp, w_per, b_per, W_kv, in_w, out_w, gamma, W_po, Xcat, X, KVp, q, attn_cat, probs,
+                                  attn_out, y, mean, rstd)
+        return E.view(B, T, d) if per_query else E.view(B, 1, d).expand(B, T, d)
+
+    @staticmethod
+    def backward(ctx, dE_txt):
+        (Qp, w_per, b_per, W_kv, in_w, out_w, gamma, W_po, Xcat, X, KVp, q, attn_cat, probs, attn_out, y, mean,
+         rstd) = ctx.saved_tensors
+        r, T, H, thr, seed = ctx.r, ctx.T, ctx.H, ctx.thr, ctx.seed
+        B, d = r.B, W_po.shape[0]
+        dt = d // 2
+        per_query = ctx.per_query
+        dEc = dE_txt.contiguous()
+        dE = dEc.view(B * T, d) if per_query else ops.group_sum_rows(dEc.view(B * T, d), B, T, d)
+        dW_po = ops.linear_wgrad(dE, y)
+        db_po = ops.colsum(dE)
+        dy = ops.linear_dgrad(dE, W_po)
+        rps = T if per_query else 1
+        dx, dres, dgamma, dbeta = ops.ln_bwd(dy, attn_out, Qp.view(d), r.m_txt, rps, gamma, mean, rstd, thr, seed,
+                                             ops.SITE_TTF_DROPOUT)
+        dW_o = ops.linear_wgrad(dx, attn_cat)
+        db_o = ops.colsum(dx)
+        d_attn_cat = ops.linear_dgrad(dx, out_w)
+        dKVp, dq_partial = ops.segattn_bwd(d_attn_cat, q, KVp, probs, r, T, H, d, per_query, thr, seed)
+        # query path: q = (Qp W_q^T + b_q) * scale
+        dq = ops.colsum(dq_partial)
+        dq_pre = ops.axpby(dq, ctx.scale, torch.empty_like(dq), False).view(1, d)
+        d_in_w = torch.empty_like(in_w)
+        d_in_b = torch.empty(3 * d, dtype=_f32, device=in_w.device)
+        ops.linear_wgrad(dq_pre, Qp.view(1, d), out=d_in_w[:d])
+        d_in_b[:d].copy_(dq_pre.view(d))
+        dQp = ops.linear_dgrad(dq_pre, in_w[:d])  # [1,d]
+        ops.axpby(dres, 1.0, dQp.view(d), True)
+        # key/value path, once per note
+        ops.linear_wgrad(dKVp, X, out=d_in_w[d:], ragged=r.m_dev)
+        ops.colsum(dKVp, out=d_in_b[d:], ragged=r.m_dev)
+        dX = ops.linear_dgrad(dKVp, in_w[d:], ragged=r.m_dev)
+        dW_kv = ops.linear_wgrad(dX, Xcat, ragged=r.m_dev)
+        db_kv = ops.colsum(dX, ragged=r.m_dev)
+        dXcat = ops.linear_dgrad(dX, W_kv, ragged=r.m_dev)
+        dwl, dbl, dwp, dbp = ops.time2vec_bwd(dXcat[:, d:], r, w_per, b_per, dt)
+        dW_in = db_in = None
+        if ctx.has_in:
+            dW_in = ops.linear_wgrad(dXcat[:, :d], r.emb_flat, ragged=r.m_dev)
+            db_in = ops.colsum(dXcat[:, :d], ragged=r.m_dev)
+        return (None, None, None, None, None, None, dQp.view(1, 1, d), dW_in, db_in, dwl, dbl, dwp, dbp, dW_kv, db_kv,
+                d_in_w, d_in_b, dW_o, db_o, dgamma, dbeta, dW_po, db_po)
+
+
+# ============================================================== MMF_GR_Add
+class GRAddFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, Y, E, m_txt, thr, seed, save, flags, W_ih, W_hh, b_ih, b_hh, W_r, b_r, W_g, b_g, gamma, beta):
+        B, T, C = Y.shape
+        d = E.shape[2]
+        Yc = Y.contiguous()
+        X = torch.cat([Yc, E], dim=-1).view(B * T, C + d)  # MMF_GR_Add.py:43
+        Wcat = torch.cat([W_ih, W_g], dim=0)  # [4C, C+d]: GRU input map and gate net read x once
+        bcat = torch.cat([b_ih, b_g], dim=0)
+        G4 = ops.linear_fwd(X, Wcat, bcat)
+        W_hh_c, b_hh_c, W_r_c = W_hh.contiguous(), b_hh.contiguous(), W_r.contiguous()
+        h_all, h_prev = ops.gru_scan_fwd(G4, W_hh_c, b_hh_c, B, T, C)
+        Y_out = ops.gr_tail_fwd(Yc, G4, h_all, W_r_c, b_r, gamma, beta, m_txt, B, T, C, thr, seed, flags)
+        if save:
+            ctx.thr, ctx.seed, ctx.dims = thr, seed, (B, T, C, d)
+            ctx.save_for_backward(m_txt, X, Wcat, G4, h_all, h_prev, W_hh_c, b_hh_c, W_r_c, b_r, gamma, beta)
+        return Y_out
+
+    @staticmethod
+    def backward(ctx, dY_out):
+        m_txt, X, Wcat, G4, h_all, h_prev, W_hh, b_hh, W_r, b_r, gamma, beta = ctx.saved_tensors
+        B, T, C, d = ctx.dims
+        dY_out = dY_out.contiguous()
+        dG4 = torch.empty_like(G4)
+        d_delta, dh_out, dgamma, dbeta = ops.gr_tail_bwd(dY_out, G4, h_all, W_r, b_r, gamma, beta, m_txt, B, T, C, ctx.thr,
+                                                         ctx.seed, dG4)
+        dGh = ops.gru_scan_bwd(G4, h_prev, W_hh, b_hh, dh_out, B, T, C, dG4)
+        dW_r = ops.linear_wgrad(d_delta, h_all)
+        db_r = ops.colsum(d_delta)
+        dW_hh = ops.linear_wgrad(dGh, h_prev)
+        db_hh = ops.colsum(dGh)
+        dWcat = ops.linear_wgrad(dG4, X)
+        dbcat = ops.colsum(dG4)
+        # dY = dY_out (blend passes Y straight through) + dG4 Wcat[:, :C] ;  dE = dG4 Wcat[:, C:]
+        dY = dY_out.view(B * T, C).clone()
+        ops.gemm(dG4, Wcat[:, :C], dY, beta=1.0)
+        dE = torch.empty(B * T, d, dtype=_f32, device=X.device)
+        ops.gemm(dG4, Wcat[:, C:], dE)
+        return (dY.view(B, T, C), dE.view(B, T, d), None, None, None, None, None, dWcat[: 3 * C], dW_hh, dbcat[: 3 * C], db_hh,
+                dW_r, db_r, dWcat[3 * C:], dbcat[3 * C:], dgamma, dbeta)
+
+
+# ============================================================== MMF_XAttn_Add
+class XAttnAddFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, Y, E, m_txt, H, kappa, thr, seed, save, flags, W_Q, W_K, W_V, in_w, in_b, out_w, out_b, W_r, b_r,
+                gamma, beta):
+        B, T, C = Y.shape
+        d = W_Q.shape[0]
+        Y2 = Y.contiguous().view(B * T, C)
+        E2 = E.contiguous().view(B * T, E.shape[2])
+        Q0 = ops.linear_fwd(Y2, W_Q, None)  # :68
+        K0 = ops.linear_fwd(E2, W_K, None)  # :69
+        V0 = ops.linear_fwd(E2, W_V, None)  # :70
+        q = ops.linear_fwd(Q0, in_w[:d], in_b[:d])
+        k = ops.linear_fwd(K0, in_w[d:2 * d], in_b[d:2 * d])
+        v = ops.linear_fwd(V0, in_w[2 * d:], in_b[2 * d:])
+        o, probs = ops.xattn_core_fwd(q, k, v, m_txt, B, T, H, d, thr, seed, save)
+        ao = ops.linear_fwd(o, out_w, out_b)
+        delta_y = ops.linear_fwd(ao, W_r, b_r)  # :83
+        Y_out = ops.xattn_tail_fwd(Y2, delta_y, gamma, beta, m_txt, B, T, C, kappa, thr, seed, flags)
+        if save:
+            ctx.H, ctx.kappa, ctx.thr, ctx.seed, ctx.dims = H, kappa, thr, seed, (B, T, C, d)
+            ctx.save_for_backward(m_txt, Y2, E2, W_Q, W_K, W_V, in_w, out_w, W_r, gamma, Q0, K0, V0, q, k, v, o, probs, ao,
+                                  delta_y)
+        return Y_out
+
+    @staticmethod
+    def backward(ctx, dY_out):
+        (m_txt, Y2, E2, W_Q, W_K, W_V, in_w, out_w, W_r, gamma, Q0, K0, V0, q, k, v, o, probs, ao,
+         delta_y) = ctx.saved_tensors
+        B, T, C, d = ctx.dims
+        H, kappa, thr, seed = ctx.H, ctx.kappa, ctx.thr, ctx.seed
+        dev = Y2.device
+        dY_out = dY_out.contiguous()
+        d_delta, dgamma, dbeta = ops.xattn_tail_bwd(dY_out, delta_y, gamma, m_txt, B, T, C, kappa, thr, seed)
+        dW_r = ops.linear_wgrad(d_delta, ao)
+        db_r = ops.colsum(d_delta)
+        dao = ops.linear_dgrad(d_delta, W_r)
+        dW_o = ops.linear_wgrad(dao, o)
+        db_o = ops.colsum(dao)
+        do = ops.linear_dgrad(dao, out_w)
+        dq = torch.empty(B * T, d, dtype=_f32, device=dev)
+        dk = torch.empty(B * T, d, dtype=_f32, device=dev)
+        dv = torch.empty(B * T, d, dtype=_f32, device=dev)
+        ops.xattn_core_bwd(do, q, k, v, probs, m_txt, B, T, H, d, thr, seed, dq, dk, dv)
+        d_in_w = torch.empty_like(in_w)
+        d_in_b = torch.empty(3 * d, dtype=_f32, device=dev)
+        ops.linear_wgrad(dq, Q0, out=d_in_w[:d])
+        ops.linear_wgrad(dk, K0, out=d_in_w[d:2 * d])
+        ops.linear_wgrad(dv, V0, out=d_in_w[2 * d:])
+        ops.colsum(dq, out=d_in_b[:d])
+        ops.colsum(dk, out=d_in_b[d:2 * d])
+        ops.colsum(dv, out=d_in_b[2 * d:])
+        dQ0 = ops.linear_dgrad(dq, in_w[:d])
+        dK0 = ops.linear_dgrad(dk, in_w[d:2 * d])
+        dV0 = ops.linear_dgrad(dv, in_w[2 * d:])
+        dW_Q = ops.linear_wgrad(dQ0, Y2)
+        dW_K = ops.linear_wgrad(dK0, E2)
+        dW_V = ops.linear_wgrad(dV0, E2)
+        dY = ops.axpby(dY_out.view(B * T, C), 1.0 / (1.0 + kappa), torch.empty(B * T, C, dtype=_f32, device=dev), False)
+        ops.linear_dgrad(dQ0, W_Q, out=dY, beta=1.0)
+        dE = ops.linear_dgrad(dK0, W_K)
+        ops.linear_dgrad(dV0, W_V, out=dE, beta=1.0)
+        return (dY.view(B, T, C), dE.view(B, T, E2.shape[1]), None, None, None, None, None, None, None, dW_Q, dW_K, dW_V,
+                d_in_w, d_in_b, dW_o, db_o, dW_r, db_r, dgamma, dbeta)

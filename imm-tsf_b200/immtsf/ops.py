@@ -1,0 +1,324 @@
+"""Tensor-level wrappers over the C ABI: argument checking, pointer extraction,
+current-stream plumbing.  PyTorch is used only for device memory and streams."""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+BACKEND_AUTO, BACKEND_FFMA, BACKEND_TC = 0, 1, 2
+SITE_TTF_DROPOUT, SITE_TTF_ATTN, SITE_MMF_DROPOUT, SITE_MMF_ATTN = 1, 2, 3, 4
+FLAG_V, FLAG_Y, FLAG_E, FLAG_OUT = 0, 1, 2, 3
+LN_EPS = 1e-5
+
+
+def gemm_backend() -> int:
+    v = os.environ.get("IMMTSF_GEMM", "auto").lower()
+    return {"auto": BACKEND_AUTO, "ffma": BACKEND_FFMA, "tc": BACKEND_TC}.get(v, BACKEND_AUTO)
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _chk(t: torch.Tensor, name: str, dtype=torch.float32):
+    if not t.is_cuda:
+        raise _lib.ImmtsfError(f"{name}: tensor must live on a CUDA device (no CPU fallback)")
+    if t.dtype != dtype:
+        raise _lib.ImmtsfError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    return t
+
+
+def drop_thr(p: float) -> int:
+    """floor(p * 2^32) clamped to uint32; 0 disables dropout."""
+    if p <= 0.0:
+        return 0
+    return min(int(p * 4294967296.0), 4294967295)
+
+
+def new_seed() -> int:
+    """63-bit seed drawn from torch's CPU generator (so torch.manual_seed governs it)."""
+    return int(torch.randint(0, 2**62, (1,), dtype=torch.int64).item())
+
+
+def round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+# ------------------------------------------------------------------ CSR layout
+@dataclass
+class RaggedNotes:
+    """Ragged (CSR) view of a padded note batch.  sumN = offsets[B] stays on the device."""
+    B: int
+    N: int
+    d_m: int
+    M_alloc: int
+    note_mask: torch.Tensor  # [B*N] u8
+    offsets: torch.Tensor  # [B+1] i32
+    rows: torch.Tensor  # [B*N] i32
+    seg: torch.Tensor  # [B*N] i32
+    emb_flat: torch.Tensor  # [M_alloc, d_m]
+    tau_flat: torch.Tensor  # [M_alloc]
+    m_txt: torch.Tensor  # [B] u8
+    flags: torch.Tensor  # [4] i32
+
+    @property
+    def m_dev(self) -> torch.Tensor:
+        return self.offsets[self.B:]
+
+
+def csr_build(notes: torch.Tensor, tau: torch.Tensor, flags: Optional[torch.Tensor] = None) -> RaggedNotes:
+    _chk(notes, "notes"), _chk(tau, "tau")
+    if notes.dim() != 3 or tau.dim() != 2 or tau.shape[0] != notes.shape[0] or tau.shape[1] != notes.shape[1]:
+        raise ValueError(f"notes must be [B,N,d_model] and tau [B,N]; got {tuple(notes.shape)} and {tuple(tau.shape)}")
+    notes, tau = notes.contiguous(), tau.contiguous()
+    B, N, d_m = notes.shape
+    dev = notes.device
+    M_alloc = max(round_up(B * N, 128), 128)
+    i32, u8 = torch.int32, torch.uint8
+    r = RaggedNotes(
+        B, N, d_m, M_alloc,
+        torch.empty(max(B * N, 1), dtype=u8, device=dev), torch.empty(B + 1, dtype=i32, device=dev),
+        torch.empty(max(B * N, 1), dtype=i32, device=dev), torch.empty(max(B * N, 1), dtype=i32, device=dev),
+        torch.empty(M_alloc, max(d_m, 1), dtype=torch.float32, device=dev),
+        torch.empty(M_alloc, dtype=torch.float32, device=dev), torch.empty(max(B, 1), dtype=u8, device=dev),
+        flags if flags is not None else torch.zeros(4, dtype=i32, device=dev),
+    )
+    _lib.call("immtsf_csr_build", _p(notes), _p(tau), B, N, d_m, _p(r.note_mask), _p(r.offsets), _p(r.rows), _p(r.seg),
+              _p(r.emb_flat), _p(r.tau_flat), _p(r.m_txt), _p(r.flags), M_alloc, _stream())
+    return r
+
+
+def nan_check(x: torch.Tensor, flags: torch.Tensor, slot: int):
+    x = _chk(x, "nan_check").contiguous()
+    _lib.call("immtsf_nan_check", _p(x), x.numel(), _p(flags), slot, _stream())
+
+
+def zero_pad_rows(X: torch.Tensor, ncols: int, m_dev: torch.Tensor, M_alloc: int):
+    _lib.call("immtsf_zero_pad_rows", _p(X), X.stride(0), ncols, _p(m_dev), M_alloc, _stream())
+
+
+# ------------------------------------------------------------------ GEMM
+def _mat(t: torch.Tensor, name: str):
+    _chk(t, name)
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise _lib.ImmtsfError(f"{name}: need a 2-D row-major matrix (unit column stride), got strides {t.stride()}")
+    return t
+
+
+def gemm(A, B, C, transA=False, transB=False, bias=None, alpha=1.0, beta=0.0, ragged=None, ragged_dim=0, backend=None):
+    """C[M,N] = alpha*op(A)*op(B) + beta*C + bias (shapes per include/immtsf.h)."""
+    _mat(A, "A"), _mat(B, "B"), _mat(C, "C")
+    M, N = C.shape
+    K = A.shape[0] if transA else A.shape[1]
+    ea = (K, M) if transA else (M, K)
+    eb = (N, K) if transB else (K, N)
+    if tuple(A.shape) != ea or tuple(B.shape) != eb:
+        raise _lib.ImmtsfError(f"gemm: shape mismatch A{tuple(A.shape)} (want {ea}) B{tuple(B.shape)} (want {eb}) C{tuple(C.shape)}")
+    if bias is not None:
+        _chk(bias, "bias")
+        assert bias.numel() == N and bias.is_contiguous()
+    _lib.call("immtsf_gemm", int(transA), int(transB), M, N, K, float(alpha), _p(A), A.stride(0), _p(B), B.stride(0),
+              float(beta), _p(C), C.stride(0), _p(bias), _p(ragged), ragged_dim,
+              gemm_backend() if backend is None else backend, _stream())
+    return C
+
+
+def linear_fwd(x, w, b, out=None, ragged=None):
+    """out[M,N] = x[M,K] w[N,K]^T + b."""
+    if out is None:
+        out = torch.empty(x.shape[0], w.shape[0], dtype=torch.float32, device=x.device)
+    return gemm(x, w, out, transB=True, bias=b, ragged=ragged, ragged_dim=1 if ragged is not None else 0)
+
+
+def linear_dgrad(dy, w, out=None, ragged=None, beta=0.0):
+    """dx[M,K] = dy[M,N] w[N,K]."""
+    if out is None:
+        out = torch.empty(dy.shape[0], w.shape[1], dtype=torch.float32, device=dy.device)
+    return gemm(dy, w, out, beta=beta, ragged=ragged, ragged_dim=1 if ragged is not None else 0)
+
+
+def linear_wgrad(dy, x, out=None, ragged=None, beta=0.0):
+    """dw[N,K] = dy[M,N]^T x[M,K]."""
+    if out is None:
+        out = torch.empty(dy.shape[1], x.shape[1], dtype=torch.float32, device=dy.device)
+    return gemm(dy, x, out, transA=True, beta=beta, ragged=ragged, ragged_dim=2 if ragged is not None else 0)
+
+
+def colsum(X, out=None, ragged=None, beta=0.0):
+    _mat(X, "X")
+    if out is None:
+        out = torch.empty(X.shape[1], dtype=torch.float32, device=X.device)
+    _lib.call("immtsf_colsum", _p(X), X.shape[0], X.shape[1], X.stride(0), _p(out), float(beta), _p(ragged), _stream())
+    return out
+
+
+def axpby(x, alpha, y, accumulate):
+    _lib.call("immtsf_axpby", _p(x), float(alpha), _p(y), int(accumulate), x.numel(), _stream())
+    return y
+
+
+def group_sum_rows(x, R, T, d):
+    out = torch.empty(R, d, dtype=torch.float32, device=x.device)
+    _lib.call("immtsf_group_sum_rows", _p(x), d, R, T, d, _p(out), _stream())
+    return out
+
+
+# ------------------------------------------------------------------ RecAvg pooling
+def recavg_pool_fwd(Vp, r: RaggedNotes, t_hat, log_sigma, gamma, beta, T, d, thr, seed, save):
+    B = r.B
+    dev = Vp.device
+    E_drop = torch.empty(B, T, d, dtype=torch.float32, device=dev)
+    E_raw = torch.empty(B, T, d, dtype=torch.float32, device=dev) if save else None
+    mean = torch.empty(B, T, dtype=torch.float32, device=dev) if save else None
+    rstd = torch.empty(B, T, dtype=torch.float32, device=dev) if save else None
+    wsum = torch.empty(B, T, dtype=torch.float32, device=dev) if save else None
+    bstride = 0 if t_hat.dim() == 1 else t_hat.stride(0)
+    _lib.call("immtsf_recavg_pool_fwd", _p(Vp), Vp.stride(0), _p(r.tau_flat), _p(r.offsets), _p(t_hat), bstride,
+              _p(log_sigma), _p(gamma), _p(beta), B, T, d, LN_EPS, thr, seed, _p(E_drop), _p(E_raw), _p(mean), _p(rstd),
+              _p(wsum), _stream())
+    return E_drop, E_raw, mean, rstd, wsum
+
+
+def recavg_pool_bwd(dE_drop, E_raw, mean, rstd, wsum, Vp, r: RaggedNotes, t_hat, log_sigma, gamma, T, d, thr, seed):
+    dev = Vp.device
+    dVp = torch.empty(r.M_alloc, d, dtype=torch.float32, device=dev)
+    dgamma = torch.zeros(d, dtype=torch.float32, device=dev)
+    dbeta = torch.zeros(d, dtype=torch.float32, device=dev)
+    dls = torch.zeros((), dtype=torch.float32, device=dev)
+    bstride = 0 if t_hat.dim() == 1 else t_hat.stride(0)
+    _lib.call("immtsf_recavg_pool_bwd", _p(dE_drop), _p(E_raw), _p(mean), _p(rstd), _p(wsum), _p(Vp), Vp.stride(0),
+              _p(r.tau_flat), _p(r.offsets), _p(t_hat), bstride, _p(log_sigma), _p(gamma), r.B, T, d, thr, seed,
+              _p(dVp), d, _p(dgamma), _p(dbeta), _p(dls), _stream())
+    zero_pad_rows(dVp, d, r.m_dev, r.M_alloc)
+    return dVp, dgamma, dbeta, dls
+
+
+# ------------------------------------------------------------------ Time2Vec / segment attention / LN
+def time2vec_fwd(r: RaggedNotes, w_lin, b_lin, w_per, b_per, d_tau, out_view):
+    """out_view: [M_alloc, d_tau] column slice of the concat buffer."""
+    _lib.call("immtsf_time2vec_fwd", _p(r.tau_flat), _p(w_lin), _p(b_lin), _p(w_per), _p(b_per), d_tau, _p(out_view),
+              out_view.stride(0), _p(r.m_dev), r.M_alloc, _stream())
+
+
+def time2vec_bwd(dphi_view, r: RaggedNotes, w_per, b_per, d_tau):
+    dev = dphi_view.device
+    dwl = torch.zeros(1, 1, dtype=torch.float32, device=dev)
+    dbl = torch.zeros(1, dtype=torch.float32, device=dev)
+    dwp = torch.zeros(d_tau - 1, 1, dtype=torch.float32, device=dev)
+    dbp = torch.zeros(d_tau - 1, dtype=torch.float32, device=dev)
+    _lib.call("immtsf_time2vec_bwd", _p(dphi_view), dphi_view.stride(0), _p(r.tau_flat), _p(w_per), _p(b_per), d_tau,
+              _p(dwl), _p(dbl), _p(dwp), _p(dbp), _p(r.m_dev), r.M_alloc, _stream())
+    return dwl, dbl, dwp, dbp
+
+
+def segattn_fwd(q, KVp, r: RaggedNotes, T, H, d, per_query, thr, seed, save):
+    R = r.B * T if per_query else r.B
+    attn_cat = torch.empty(R, d, dtype=torch.float32, device=KVp.device)
+    probs = torch.empty(r.M_alloc, H, dtype=torch.float32, device=KVp.device) if save else None
+    _lib.call("immtsf_segattn_fwd", _p(q), _p(KVp), _p(r.offsets), r.B, T, H, d, max(r.N, 1), int(per_query), thr, seed,
+              _p(attn_cat), _p(probs), _stream())
+    return attn_cat, probs
+
+
+def segattn_bwd(d_attn_cat, q, KVp, probs, r: RaggedNotes, T, H, d, per_query, thr, seed):
+    dKVp = torch.empty(r.M_alloc, 2 * d, dtype=torch.float32, device=KVp.device)
+    dq_partial = torch.empty(r.B, d, dtype=torch.float32, device=KVp.device)
+    _lib.call("immtsf_segattn_bwd", _p(d_attn_cat), _p(q), _p(KVp), _p(probs), _p(r.offsets), r.B, T, H, d, max(r.N, 1),
+              int(per_query), thr, seed, _p(dKVp), _p(dq_partial), _stream())
+    zero_pad_rows(dKVp, 2 * d, r.m_dev, r.M_alloc)
+    return dKVp, dq_partial
+
+
+def ln_fwd(x, res, valid, rows_per_sample, gamma, beta, thr, seed, site, save):
+    R, d = x.shape
+    y = torch.empty(R, d, dtype=torch.float32, device=x.device)
+    mean = torch.empty(R, dtype=torch.float32, device=x.device) if save else None
+    rstd = torch.empty(R, dtype=torch.float32, device=x.device) if save else None
+    _lib.call("immtsf_ln_fwd", _p(x), x.stride(0), _p(res), _p(valid), rows_per_sample, _p(gamma), _p(beta), R, d, LN_EPS,
+              thr, seed, site, _p(y), _p(mean), _p(rstd), _stream())
+    return y, mean, rstd
+
+
+def ln_bwd(dy, x, res, valid, rows_per_sample, gamma, mean, rstd, thr, seed, site):
+    R, d = x.shape
+    dev = x.device
+    dx = torch.empty(R, d, dtype=torch.float32, device=dev)
+    dres = torch.zeros(d, dtype=torch.float32, device=dev) if res is not None else None
+    dgamma = torch.zeros(d, dtype=torch.float32, device=dev)
+    dbeta = torch.zeros(d, dtype=torch.float32, device=dev)
+    _lib.call("immtsf_ln_bwd", _p(dy), _p(x), x.stride(0), _p(res), _p(valid), rows_per_sample, _p(gamma), _p(mean), _p(rstd),
+              R, d, thr, seed, site, _p(dx), _p(dres), _p(dgamma), _p(dbeta), _stream())
+    return dx, dres, dgamma, dbeta
+
+
+# ------------------------------------------------------------------ GR_Add
+def gru_scan_fwd(G4, w_hh, b_hh, B, T, C):
+    h_all = torch.empty(B * T, C, dtype=torch.float32, device=G4.device)
+    h_prev = torch.empty(B * T, C, dtype=torch.float32, device=G4.device)
+    _lib.call("immtsf_gru_scan_fwd", _p(G4), _p(w_hh), _p(b_hh), B, T, C, _p(h_all), _p(h_prev), _stream())
+    return h_all, h_prev
+
+
+def gr_tail_fwd(Y, G4, h_all, w_r, b_r, gamma, beta, m_txt, B, T, C, thr, seed, flags):
+    Y_out = torch.empty(B, T, C, dtype=torch.float32, device=Y.device)
+    _lib.call("immtsf_gr_tail_fwd", _p(Y), _p(G4), _p(h_all), _p(w_r), _p(b_r), _p(gamma), _p(beta), _p(m_txt), B, T, C,
+              LN_EPS, thr, seed, _p(Y_out), _p(flags), _stream())
+    return Y_out
+
+
+def gr_tail_bwd(dY_out, G4, h_all, w_r, b_r, gamma, beta, m_txt, B, T, C, thr, seed, dG4):
+    dev = G4.device
+    d_delta = torch.empty(B * T, C, dtype=torch.float32, device=dev)
+    dh_out = torch.empty(B * T, C, dtype=torch.float32, device=dev)
+    dgamma = torch.zeros(C, dtype=torch.float32, device=dev)
+    dbeta = torch.zeros(C, dtype=torch.float32, device=dev)
+    _lib.call("immtsf_gr_tail_bwd", _p(dY_out), _p(G4), _p(h_all), _p(w_r), _p(b_r), _p(gamma), _p(beta), _p(m_txt), B, T, C,
+              LN_EPS, thr, seed, _p(dG4), _p(d_delta), _p(dh_out), _p(dgamma), _p(dbeta), _stream())
+    return d_delta, dh_out, dgamma, dbeta
+
+
+def gru_scan_bwd(G4, h_prev, w_hh, b_hh, dh_out, B, T, C, dG4):
+    dGh = torch.empty(B * T, 3 * C, dtype=torch.float32, device=G4.device)
+    _lib.call("immtsf_gru_scan_bwd", _p(G4), _p(h_prev), _p(w_hh), _p(b_hh), _p(dh_out), B, T, C, _p(dG4), _p(dGh), _stream())
+    return dGh
+
+
+# ------------------------------------------------------------------ XAttn_Add
+def xattn_core_fwd(q, k, v, m_txt, B, T, H, d, thr, seed, save):
+    o = torch.empty(B * T, d, dtype=torch.float32, device=q.device)
+    probs = torch.empty(B, H, T, T, dtype=torch.float32, device=q.device) if save else None
+    _lib.call("immtsf_xattn_core_fwd", _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(m_txt), B, T, H, d,
+              thr, seed, _p(o), o.stride(0), _p(probs), _stream())
+    return o, probs
+
+
+def xattn_core_bwd(d_o, q, k, v, probs, m_txt, B, T, H, d, thr, seed, dq, dk, dv):
+    _lib.call("immtsf_xattn_core_bwd", _p(d_o), d_o.stride(0), _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0),
+              _p(probs), _p(m_txt), B, T, H, d, thr, seed, _p(dq), dq.stride(0), _p(dk), dk.stride(0), _p(dv), dv.stride(0),
+              _stream())
+
+
+def xattn_tail_fwd(Y, delta_y, gamma, beta, m_txt, B, T, C, kappa, thr, seed, flags):
+    Y_out = torch.empty(B, T, C, dtype=torch.float32, device=Y.device)
+    _lib.call("immtsf_xattn_tail_fwd", _p(Y), _p(delta_y), _p(gamma), _p(beta), _p(m_txt), B, T, C, LN_EPS, float(kappa), thr,
+              seed, _p(Y_out), _p(flags), _stream())
+    return Y_out
+
+
+def xattn_tail_bwd(dY_out, delta_y, gamma, m_txt, B, T, C, kappa, thr, seed):
+    dev = delta_y.device
+    d_delta = torch.empty(B * T, C, dtype=torch.float32, device=dev)
+    dgamma = torch.zeros(C, dtype=torch.float32, device=dev)
+    dbeta = torch.zeros(C, dtype=torch.float32, device=dev)
+    _lib.call("immtsf_xattn_tail_bwd", _p(dY_out), _p(delta_y), _p(gamma), _p(m_txt), B, T, C, LN_EPS, float(kappa), thr, seed,
+              _p(d_delta), _p(dgamma), _p(dbeta), _stream())
+    return d_delta, dgamma, dbeta

@@ -1,0 +1,175 @@
+/*
+ * immtsf.h -- C ABI of the B200-native (sm_100a) IMM-TSF text->time-series
+ * fusion kernels.
+ *
+ * This is the drop-in boundary for the hot path named in BASELINE.json: the
+ * reference's `fusions/FusionModel.py:98-113` (ttf -> mmf) and the four modules
+ * behind it.  The reference has no FFI of its own (it is pure PyTorch); these
+ * entry points are what a binding for that path calls instead of the ATen op
+ * sequences listed in SURVEY.md section 2.2.  Each entry cites the reference
+ * lines it replaces.
+ *
+ * Conventions:
+ *   - every pointer is a DEVICE pointer owned by the caller (fp32 unless the
+ *     type says otherwise); nothing is allocated, freed or synchronised here;
+ *   - `stream` is a cudaStream_t passed as void*;
+ *   - return value: 0 on success, negative on error (IMMTSF_ERR_*); the text
+ *     of the last error on the calling thread is immtsf_last_error_string();
+ *   - there is no CPU fallback and no other backend: on a device that is not
+ *     compute capability 10.x every launch fails with IMMTSF_ERR_ARCH/LAUNCH;
+ *   - ragged layout: notes are stored compacted, sample-major, in
+ *     `[M_alloc, d]` row buffers with `offsets[B+1]` (int32).  `sumN =
+ *     offsets[B]` lives on the device; kernels take it as `const int32_t*
+ *     m_dev` so no host sync is needed.  Producers zero rows
+ *     [sumN, roundup(sumN,128)) so that reductions over rows stay clean.
+ *   - dropout masks are Philox4x32-10 functions of (seed, site, element index)
+ *     (csrc/common.cuh), regenerated in backward; `drop_thr = floor(p*2^32)`,
+ *     0 disables dropout.
+ */
+#ifndef IMMTSF_H_
+#define IMMTSF_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IMMTSF_ABI_VERSION 1
+
+/* ---- library ---------------------------------------------------------- */
+int immtsf_version(void);
+const char* immtsf_last_error_string(void);
+/* 1 if `device` is compute capability 10.x (B200), 0 otherwise, <0 on error */
+int immtsf_device_supported(int device);
+
+/* ---- K1: padded -> ragged CSR (replaces the content mask of
+ * fusions/TTF_RecAvg.py:69 / fusions/TTF_T2V_XAttn.py:107, the NaN guard of
+ * :75 / :116 and M_txt of :110 / :124) ----------------------------------
+ * notes [B,N,d_m], tau [B,N]  ->  note_mask [B*N] u8, offsets [B+1],
+ * rows [B*N] (flat index b*N+n of each valid note), seg [B*N] (owning
+ * sample), emb_flat [M_alloc,d_m], tau_flat [M_alloc], m_txt [B] u8.
+ * flags[0] is set to 1 if any NaN is present in notes. */
+int immtsf_csr_build(const float* notes, const float* tau, int B, int N, int d_m,
+                     uint8_t* note_mask, int32_t* offsets, int32_t* rows, int32_t* seg,
+                     float* emb_flat, float* tau_flat, uint8_t* m_txt, int32_t* flags,
+                     int M_alloc, void* stream);
+/* flags[slot] = 1 if x[0..n) holds a NaN (FusionModel.py:103,107,111) */
+int immtsf_nan_check(const float* x, size_t n, int32_t* flags, int slot, void* stream);
+/* zero rows [sumN, min(roundup(sumN,128), M_alloc)) of X[M_alloc, ncols] (ld) */
+int immtsf_zero_pad_rows(float* X, int ld, int ncols, const int32_t* m_dev, int M_alloc, void* stream);
+
+/* ---- dense projections (nn.Linear call sites: TTF_RecAvg.py:80,109;
+ * TTF_T2V_XAttn.py:121,140,182; the in/out projections inside
+ * nn.MultiheadAttention; MMF_GR_Add.py:46-47,54; MMF_XAttn_Add.py:68-70,83)
+ * C[M,N] = alpha * op(A)[M,K] * op(B)[K,N] + beta * C + bias[N]
+ *   transA=0: A is [M,K] row-major (lda)   transA=1: A is [K,M] row-major
+ *   transB=0: B is [K,N] row-major (ldb)   transB=1: B is [N,K] row-major
+ * ragged_dim: 0 none; 1: rows M bounded by *ragged (rows >= it are written
+ * as 0 inside touched tiles); 2: contraction K bounded by *ragged (wgrad).
+ * backend: 0 auto, 1 FFMA (CUDA cores, exact fp32), 2 tcgen05 3xTF32. */
+int immtsf_gemm(int transA, int transB, int M, int N, int K, float alpha,
+                const float* A, int lda, const float* B, int ldb, float beta,
+                float* C, int ldc, const float* bias, const int32_t* ragged,
+                int ragged_dim, int backend, void* stream);
+/* out[N] = beta*out + sum_m X[m, :]  (bias gradients) */
+int immtsf_colsum(const float* X, int M, int N, int ldx, float* out, float beta,
+                  const int32_t* ragged, void* stream);
+
+/* ---- K2: TTF_RecAvg pooling (TTF_RecAvg.py:94-106): recency weights,
+ * weighted mean over each ragged segment, LayerNorm, dropout ------------- */
+int immtsf_recavg_pool_fwd(const float* Vp, int ldv, const float* tau_flat, const int32_t* offsets,
+                           const float* t_hat, int t_hat_bstride, const float* log_sigma,
+                           const float* gamma, const float* beta, int B, int T, int d, float eps,
+                           uint32_t drop_thr, uint64_t seed, float* E_drop, float* E_raw,
+                           float* mean, float* rstd, float* wsum, void* stream);
+int immtsf_recavg_pool_bwd(const float* dE_drop, const float* E_raw, const float* mean, const float* rstd,
+                           const float* wsum, const float* Vp, int ldv, const float* tau_flat,
+                           const int32_t* offsets, const float* t_hat, int t_hat_bstride,
+                           const float* log_sigma, const float* gamma, int B, int T, int d,
+                           uint32_t drop_thr, uint64_t seed, float* dVp, int lddv, float* dgamma,
+                           float* dbeta, float* dlog_sigma, void* stream);
+
+/* ---- Time2Vec (TTF_T2V_XAttn.py:20-24,136) written straight into the
+ * [V' ; phi] concat buffer (:139) ---------------------------------------- */
+int immtsf_time2vec_fwd(const float* tau_flat, const float* w_lin, const float* b_lin, const float* w_per,
+                        const float* b_per, int d_tau, float* out, int ld, const int32_t* m_dev,
+                        int M_alloc, void* stream);
+int immtsf_time2vec_bwd(const float* dphi, int ld, const float* tau_flat, const float* w_per,
+                        const float* b_per, int d_tau, float* dw_lin, float* db_lin, float* dw_per,
+                        float* db_per, const int32_t* m_dev, int M_alloc, void* stream);
+
+/* ---- K3: single-learned-query attention over each ragged segment
+ * (TTF_T2V_XAttn.py:143-166 + the softmax/dropout/bmm inside
+ * nn.MultiheadAttention), computed ONCE per note instead of once per
+ * (note, query).  q [d] is already scaled by hd^-1/2.  KVp [M_alloc, 2d]:
+ * keys in columns [0,d), values in [d,2d).  R = B*T rows when per_query
+ * (training with attention dropout) else B rows. ------------------------- */
+int immtsf_segattn_fwd(const float* q, const float* KVp, const int32_t* offsets, int B, int T, int H,
+                       int d, int N_max, int per_query, uint32_t drop_thr, uint64_t seed,
+                       float* attn_cat, float* probs, void* stream);
+int immtsf_segattn_bwd(const float* d_attn_cat, const float* q, const float* KVp, const float* probs,
+                       const int32_t* offsets, int B, int T, int H, int d, int N_max, int per_query,
+                       uint32_t drop_thr, uint64_t seed, float* dKVp, float* dq_partial, void* stream);
+
+/* ---- residual + LayerNorm + dropout over d (TTF_T2V_XAttn.py:171-179) ---
+ * z = (valid[row / rows_per_sample] ? x : 0) + res;  y = dropout(LN(z)) */
+int immtsf_ln_fwd(const float* x, int ldx, const float* res, const uint8_t* valid, int rows_per_sample,
+                  const float* gamma, const float* beta, int R, int d, float eps, uint32_t drop_thr,
+                  uint64_t seed, uint32_t site, float* y, float* mean, float* rstd, void* stream);
+int immtsf_ln_bwd(const float* dy, const float* x, int ldx, const float* res, const uint8_t* valid,
+                  int rows_per_sample, const float* gamma, const float* mean, const float* rstd, int R,
+                  int d, uint32_t drop_thr, uint64_t seed, uint32_t site, float* dx, float* dres,
+                  float* dgamma, float* dbeta, void* stream);
+
+/* ---- K5: MMF_GR_Add (MMF_GR_Add.py:43-60).  G4 [B*T, 4C] = [Y;E] [W_ih;W_g]^T
+ * + [b_ih;b_g] comes from immtsf_gemm; the scan consumes columns [0,3C) and
+ * the tail columns [3C,4C). ----------------------------------------------- */
+int immtsf_gru_scan_fwd(const float* G4, const float* w_hh, const float* b_hh, int B, int T, int C,
+                        float* h_all, float* h_prev, void* stream);
+int immtsf_gr_tail_fwd(const float* Y, const float* G4, const float* h_all, const float* w_r,
+                       const float* b_r, const float* gamma, const float* beta, const uint8_t* m_txt,
+                       int B, int T, int C, float eps, uint32_t drop_thr, uint64_t seed, float* Y_out,
+                       int32_t* flags, void* stream);
+/* backward returns pre-activation gradients; every weight gradient is then an
+ * immtsf_gemm / immtsf_colsum over rows:
+ *   dG4[:, 3C:4C] (gate logits), d_delta [B*T,C] (-> dW_r = d_delta^T h_all),
+ *   dh_out [B*T,C] (into the scan) */
+int immtsf_gr_tail_bwd(const float* dY_out, const float* G4, const float* h_all, const float* w_r,
+                       const float* b_r, const float* gamma, const float* beta, const uint8_t* m_txt,
+                       int B, int T, int C, float eps, uint32_t drop_thr, uint64_t seed, float* dG4,
+                       float* d_delta, float* dh_out, float* dgamma, float* dbeta, void* stream);
+/*   dG4[:, 0:3C] = [da_r,da_z,da_n], dGh [B*T,3C] = [da_r,da_z,da_n*r]
+ *   (-> dW_hh = dGh^T h_prev, db_hh = colsum dGh) */
+int immtsf_gru_scan_bwd(const float* G4, const float* h_prev, const float* w_hh, const float* b_hh,
+                        const float* dh_out, int B, int T, int C, float* dG4, float* dGh, void* stream);
+
+/* ---- K6: MMF_XAttn_Add core (MMF_XAttn_Add.py:73-80 + MHA internals):
+ * per (sample, head) T x T attention; q,k,v are [B*T, d] with leading dims. */
+int immtsf_xattn_core_fwd(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv,
+                          const uint8_t* m_txt, int B, int T, int H, int d, uint32_t drop_thr,
+                          uint64_t seed, float* o, int ldo, float* probs, void* stream);
+int immtsf_xattn_core_bwd(const float* d_o, int lddo, const float* q, int ldq, const float* k, int ldk,
+                          const float* v, int ldv, const float* probs, const uint8_t* m_txt, int B, int T,
+                          int H, int d, uint32_t drop_thr, uint64_t seed, float* dq, int lddq, float* dk,
+                          int lddk, float* dv, int lddv, void* stream);
+/* tail (MMF_XAttn_Add.py:84-102): Y_out = (Y + kappa * m * dropout(LN_C(delta_y))) / (1+kappa) */
+int immtsf_xattn_tail_fwd(const float* Y, const float* delta_y, const float* gamma, const float* beta,
+                          const uint8_t* m_txt, int B, int T, int C, float eps, float kappa,
+                          uint32_t drop_thr, uint64_t seed, float* Y_out, int32_t* flags, void* stream);
+int immtsf_xattn_tail_bwd(const float* dY_out, const float* delta_y, const float* gamma,
+                          const uint8_t* m_txt, int B, int T, int C, float eps, float kappa,
+                          uint32_t drop_thr, uint64_t seed, float* d_delta_y, float* dgamma, float* dbeta,
+                          void* stream);
+
+/* ---- small helpers ----------------------------------------------------- */
+/* y[n] = alpha * x[n] (+ y[n] if accumulate) */
+int immtsf_axpby(const float* x, float alpha, float* y, int accumulate, size_t n, void* stream);
+/* out[r, c] = sum_{t<T} x[r*T + t, c]   ([R*T, d] -> [R, d]) */
+int immtsf_group_sum_rows(const float* x, int ldx, int R, int T, int d, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IMMTSF_H_ */

@@ -1,0 +1,317 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle and the
+golden vectors generated from the reference.  Tolerances (BASELINE.json north_star):
+fp32 outputs within 1e-5 max-norm relative; integer / mask / offset work bit-exact.
+Gradients: 5e-5 max-norm relative with an absolute floor for structurally-zero grads
+(the reference's own fp32-vs-fp64 gradient gap reaches 2.5e-5)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import golden_names, load_golden
+import gpu_common as G
+from oracle import immtsf_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+OUT_TOL = 1e-5
+GRAD_TOL = 5e-5
+
+
+@pytest.fixture(autouse=True)
+def _fixed_seed():
+    from immtsf import runtime
+
+    runtime.SEEDS.fixed = 0x5EED1234ABCD
+    yield
+    runtime.SEEDS.fixed = None
+
+
+def test_library_and_device():
+    from immtsf import _lib
+
+    lib = _lib.load()
+    assert lib.immtsf_version() == 1
+    assert lib.immtsf_device_supported(0) == 1, "tests must run on an sm_100 device"
+
+
+# ------------------------------------------------------------------ K1: CSR (bit-exact)
+@pytest.mark.parametrize("B,N,d_m", [(5, 6, 48), (1, 1, 4), (3, 40, 7), (64, 16, 768), (300, 3, 5), (2, 1030, 8)])
+def test_csr_bit_exact(B, N, d_m):
+    from immtsf import ops
+
+    notes, tau, *_ = G.synth_batch(B, N, 2, d_m, 1, seed=B * 1000 + N)
+    if N >= 3:
+        notes[0, 1] = 0.0  # all-zero real row mid-sequence
+    if B >= 3:
+        notes[2] = 0.0  # a sample with no notes at all
+    notes[0, 0, 0] = 1e-42  # a denormal still counts as non-zero (sum(|v|) > 0)
+    notes[0, 0, 1:] = 0.0
+    off, rows, seg, mask = O.csr_from_padded(notes)
+    r = ops.csr_build(notes.cuda(), tau.cuda())
+    torch.cuda.synchronize()
+    total = int(off[-1])
+    assert torch.equal(r.note_mask[: B * N].cpu().bool(), mask.reshape(-1))
+    assert torch.equal(r.offsets.cpu(), off)
+    assert torch.equal(r.rows[:total].cpu(), rows)
+    assert torch.equal(r.seg[:total].cpu(), seg)
+    assert torch.equal(r.m_txt[:B].cpu().bool(), mask.any(dim=1))
+    flat = notes.reshape(B * N, d_m)[rows.long()]
+    assert torch.equal(r.emb_flat[:total].cpu(), flat)  # gather is a bit-exact copy
+    assert torch.equal(r.tau_flat[:total].cpu(), tau.reshape(-1)[rows.long()])
+    pad_end = min((total + 127) // 128 * 128, r.M_alloc)
+    assert (r.emb_flat[total:pad_end] == 0).all() and (r.tau_flat[total:pad_end] == 0).all()
+    assert r.flags.cpu().tolist() == [0, 0, 0, 0]
+
+
+def test_csr_empty_batch_and_nan_flag():
+    from immtsf import ops
+
+    r = ops.csr_build(torch.zeros(3, 4, 8).cuda(), torch.zeros(3, 4).cuda())
+    assert r.offsets.cpu().tolist() == [0, 0, 0, 0] and r.m_txt[:3].cpu().tolist() == [0, 0, 0]
+    x = torch.randn(2, 3, 8)
+    x[1, 2, 5] = float("nan")
+    r = ops.csr_build(x.cuda(), torch.zeros(2, 3).cuda())
+    assert r.flags.cpu().tolist()[0] == 1
+
+
+# ------------------------------------------------------------------ GEMM (FFMA backend)
+@pytest.mark.parametrize("tA,tB", [(0, 1), (0, 0), (1, 0), (1, 1)])
+@pytest.mark.parametrize("M,N,K", [(1, 32, 32), (37, 19, 53), (200, 96, 48), (513, 768, 772), (4096, 4, 768), (300, 772, 4)])
+def test_gemm_ffma(tA, tB, M, N, K):
+    from immtsf import ops
+
+    g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
+    A = torch.randn((K, M) if tA else (M, K), generator=g)
+    Bm = torch.randn((N, K) if tB else (K, N), generator=g)
+    bias = torch.randn(N, generator=g)
+    C0 = torch.randn(M, N, generator=g)
+    ref = 0.75 * ((A.double().T if tA else A.double()) @ (Bm.double().T if tB else Bm.double())) + 0.5 * C0.double() + bias.double()
+    C = C0.clone().cuda()
+    ops.gemm(A.cuda(), Bm.cuda(), C, transA=bool(tA), transB=bool(tB), bias=bias.cuda(), alpha=0.75, beta=0.5,
+             backend=ops.BACKEND_FFMA)
+    G.assert_close("gemm", C.cpu(), ref, 2e-6)
+
+
+def test_gemm_ffma_strided_and_ragged():
+    from immtsf import ops
+
+    g = torch.Generator().manual_seed(5)
+    M, N, K = 300, 40, 52
+    big = torch.randn(M, K + 3, generator=g).cuda()
+    A = big[:, 3:]  # unaligned column offset, lda = K+3
+    W = torch.randn(N, K, generator=g).cuda()
+    out = torch.full((M, N + 4), 7.0).cuda()
+    m_dev = torch.tensor([130], dtype=torch.int32).cuda()
+    ops.gemm(A, W, out[:, :N], transB=True, ragged=m_dev, ragged_dim=1, backend=ops.BACKEND_FFMA)
+    ref = A.double().cpu() @ W.double().cpu().T
+    G.assert_close("rows<m", out[:130, :N].cpu(), ref[:130], 2e-6)
+    assert (out[130:192, :N] == 0).all()  # rest of the touched 64-row tile is zeroed
+    assert (out[192:, :N] == 7.0).all() and (out[:, N:] == 7.0).all()  # untouched tiles / columns stay
+    # wgrad with a ragged contraction
+    dy = torch.randn(M, N, generator=g).cuda()
+    dw = ops.linear_wgrad(dy, A, ragged=m_dev)
+    G.assert_close("wgrad", dw.cpu(), dy[:130].double().cpu().T @ A[:130].double().cpu(), 2e-6)
+    cs = ops.colsum(dy, ragged=m_dev)
+    G.assert_close("colsum", cs.cpu(), dy[:130].double().cpu().sum(0), 2e-6)
+
+
+# ------------------------------------------------------------------ golden vectors from the reference
+@pytest.mark.parametrize("name", golden_names())
+def test_forward_matches_reference_golden(name):
+    cfg, params, inp, ref = load_golden(name)
+    fm = G.build_model(cfg, inp["notes"].shape[2], params)
+    fm.eval()
+    with torch.no_grad():
+        E, M = fm.ttf(inp["notes"].cuda(), inp["tau"].cuda(), inp["t_hat"].cuda())
+        Yo = fm(inp["notes"].cuda(), inp["tau"].cuda(), inp["t_hat"].cuda(), inp["Y_ts"].cuda())
+    assert M.dtype == torch.bool and tuple(M.shape) == (inp["notes"].shape[0], 1)
+    assert np.array_equal(M.cpu().numpy(), ref["eval:M_txt"])  # bit-exact
+    G.assert_close("E_txt", E.cpu(), ref["eval64:E_txt"], OUT_TOL)
+    G.assert_close("Y_out", Yo.cpu(), ref["eval64:Y_out"], OUT_TOL)
+    G.assert_close("Y_out vs fp32 reference", Yo.cpu(), ref["eval:Y_out"], OUT_TOL)
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names() if not n.endswith("nonote")])
+def test_gradients_match_reference_golden(name):
+    cfg, params, inp, ref = load_golden(name)
+    fm = G.build_model(cfg, inp["notes"].shape[2], params)
+    out = G.gpu_run(fm, inp["notes"], inp["tau"], inp["t_hat"], inp["Y_ts"], inp["G"], train=True)
+    G.assert_close("Y_out(train,p=0)", out["Y_out"], ref["grad64:Y_out"], OUT_TOL)
+    G.assert_close("dY_ts", out["dY"], ref["grad64:Y_ts"], GRAD_TOL)
+    gmax = max(float(np.abs(ref[f"grad64:{k}"]).max()) for k in out["grads"])
+    for k, g in out["grads"].items():
+        G.assert_close(f"grad {k}", g, ref[f"grad64:{k}"], GRAD_TOL, floor=1e-3 * gmax)
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names() if n.endswith("nonote")])
+def test_no_note_sample_backward_is_finite(name):
+    """Documented divergence: the reference's backward is NaN for a sample
+    without notes; this implementation returns finite (zero) contributions."""
+    cfg, params, inp, ref = load_golden(name)
+    fm = G.build_model(cfg, inp["notes"].shape[2], params)
+    out = G.gpu_run(fm, inp["notes"], inp["tau"], inp["t_hat"], inp["Y_ts"], inp["G"], train=True)
+    assert torch.isfinite(out["dY"]).all()
+    assert all(torch.isfinite(g).all() for g in out["grads"].values())
+    G.assert_close("Y_out", out["Y_out"], ref["eval64:Y_out"], OUT_TOL)
+
+
+# ------------------------------------------------------------------ oracle at real widths, with and without dropout
+COMBOS = [
+    ("TTF_RecAvg", "MMF_GR_Add"), ("TTF_RecAvg", "MMF_XAttn_Add"),
+    ("TTF_T2V_XAttn", "MMF_GR_Add"), ("TTF_T2V_XAttn", "MMF_XAttn_Add"),
+]
+
+
+def _vs_oracle(cfg, d_model, B, N, T, p, train, seed, t1d=False, no_note=False):
+    from immtsf import runtime
+
+    C = cfg["C"]
+    fm = G.build_model(cfg, d_model, dropout=p, seed=seed)
+    G.randomise_(fm, seed + 1)
+    notes, tau, t_hat, Y, Gw = G.synth_batch(B, N, T, d_model, C, seed + 2, t1d=t1d, no_note=no_note)
+    params = {k: v.detach().cpu() for k, v in fm.state_dict().items()}
+    d = fm.ttf.d_txt
+    masks = G.oracle_masks(cfg, notes, T, C, d, p if train else 0.0, runtime.SEEDS.fixed)
+    grads = train and not no_note
+    ref = G.oracle_run(cfg, params, notes, tau, t_hat, Y, Gw, p=p if train else 0.0, masks=masks, grads=grads)
+    out = G.gpu_run(fm, notes, tau, t_hat, Y, Gw, train=train, grads=grads)
+    G.assert_close("Y_out", out["Y_out"], ref["Y_out"], OUT_TOL)
+    if grads:
+        G.assert_close("dY_ts", out["dY"], ref["dY"], GRAD_TOL)
+        gmax = max(float(v.abs().max()) for v in ref["grads"].values())
+        for k, g in out["grads"].items():
+            G.assert_close(f"grad {k}", g, ref["grads"][k], GRAD_TOL, floor=1e-3 * gmax)
+
+
+@pytest.mark.parametrize("ttf,mmf", COMBOS)
+@pytest.mark.parametrize("p", [0.0, 0.1])
+def test_small_train_vs_oracle(ttf, mmf, p):
+    """Odd sizes (d_model 40 -> d_txt 24, C 5, H 2), ragged, train mode; with p=0.1 the oracle
+    is fed the very keep-masks the kernels draw (tests/philox_ref.py)."""
+    cfg = dict(ttf=ttf, mmf=mmf, d_txt=24, C=5, H=2, kappa=0.5)
+    _vs_oracle(cfg, 40, B=6, N=9, T=11, p=p, train=True, seed=11)
+
+
+@pytest.mark.parametrize("ttf,mmf", COMBOS)
+def test_eval_1d_t_hat_and_no_note(ttf, mmf):
+    cfg = dict(ttf=ttf, mmf=mmf, d_txt=None, C=3, H=1, kappa=1.0)
+    _vs_oracle(cfg, 32, B=5, N=7, T=13, p=0.1, train=False, seed=23, t1d=True, no_note=True)
+
+
+@pytest.mark.parametrize("ttf,mmf", COMBOS)
+@pytest.mark.parametrize("p", [0.0, 0.1])
+def test_gpt2_width_train_vs_oracle(ttf, mmf, p):
+    """cfg1-shaped: B 32, N_max 16, T_f 24, C 4, GPT-2 width 768."""
+    cfg = dict(ttf=ttf, mmf=mmf, d_txt=768, C=4, H=1, kappa=0.5)
+    _vs_oracle(cfg, 768, B=32, N=16, T=24, p=p, train=True, seed=31)
+
+
+def test_llama_width_projected_vs_oracle():
+    """cfg3-shaped: d_model 4096 -> d_txt 768, C 5, T2V_XAttn + GR_Add, N_max 64, T_f 28."""
+    cfg = dict(ttf="TTF_T2V_XAttn", mmf="MMF_GR_Add", d_txt=768, C=5, H=4, kappa=0.5)
+    _vs_oracle(cfg, 4096, B=8, N=64, T=28, p=0.1, train=True, seed=41)
+
+
+def test_many_channels_vs_oracle():
+    """cfg5-shaped channel count: C 96 exercises the multi-register GRU / LayerNorm_C paths."""
+    for ttf, mmf in (("TTF_RecAvg", "MMF_GR_Add"), ("TTF_T2V_XAttn", "MMF_XAttn_Add")):
+        cfg = dict(ttf=ttf, mmf=mmf, d_txt=64, C=96, H=2, kappa=0.5)
+        _vs_oracle(cfg, 64, B=4, N=8, T=20, p=0.1, train=True, seed=51)
+
+
+# ------------------------------------------------------------------ size-independent properties at full size
+def test_cfg2_properties_full_size():
+    """BASELINE cfg2 (B 256, N_max 16, T_f 24, d 768, C 4, T2V_XAttn + XAttn_Add):
+    (1) eval output is constant over the T_f axis of E_txt and independent of t_hat values;
+    (2) permuting the notes of every sample leaves Y_out unchanged (permutation invariance, 8a);
+    (3) padding more all-zero note rows leaves Y_out bit-identical (ragged layout ignores padding)."""
+    cfg = dict(ttf="TTF_T2V_XAttn", mmf="MMF_XAttn_Add", d_txt=768, C=4, H=1, kappa=0.5)
+    fm = G.build_model(cfg, 768, dropout=0.1, seed=3)
+    fm.eval()
+    notes, tau, t_hat, Y, _ = G.synth_batch(256, 16, 24, 768, 4, 77, full=True)
+    n, ta, th, Yc = notes.cuda(), tau.cuda(), t_hat.cuda(), Y.cuda()
+    with torch.no_grad():
+        E, _ = fm.ttf(n, ta, th)
+        y0 = fm(n, ta, th, Yc)
+        y1 = fm(n, ta, torch.rand_like(th), Yc)
+        perm = torch.randperm(16)
+        y2 = fm(n[:, perm], ta[:, perm], th, Yc)
+        pad_n = torch.cat([n, torch.zeros(256, 5, 768, device="cuda")], 1)
+        pad_t = torch.cat([ta, torch.zeros(256, 5, device="cuda")], 1)
+        y3 = fm(pad_n, pad_t, th, Yc)
+    assert (E - E[:, :1]).abs().max().item() == 0.0
+    assert torch.equal(y0, y1)
+    G.assert_close("permutation invariance", y2.cpu(), y0.cpu(), OUT_TOL)
+    assert torch.equal(y3, y0)
+
+
+def test_recavg_properties_full_size():
+    """RecAvg + GR_Add at B 256: sigma -> inf turns the recency pooling into a plain mean of the notes;
+    compare E_raw-normalised output against the same model fed the per-sample mean as a single note."""
+    cfg = dict(ttf="TTF_RecAvg", mmf="MMF_GR_Add", d_txt=None, C=4, H=1, kappa=0.5)
+    fm = G.build_model(cfg, 768, dropout=0.0, seed=5)
+    fm.eval()
+    with torch.no_grad():
+        fm.ttf.log_recency_sigma.fill_(30.0)
+    notes, tau, t_hat, Y, _ = G.synth_batch(256, 16, 24, 768, 4, 78)
+    cnt = (notes.abs().sum(2) > 0).sum(1).clamp_min(1).float()
+    mean_note = (notes.sum(1) / cnt[:, None]).unsqueeze(1)
+    with torch.no_grad():
+        a, _ = fm.ttf(notes.cuda(), tau.cuda(), t_hat.cuda())
+        b, _ = fm.ttf(mean_note.cuda(), torch.zeros(256, 1).cuda(), t_hat.cuda())
+    G.assert_close("mean-pooling limit", a.cpu(), b.cpu(), 2e-5)
+
+
+# ------------------------------------------------------------------ boundary behaviour
+def test_error_conventions():
+    cfg = dict(ttf="TTF_RecAvg", mmf="MMF_GR_Add", d_txt=16, C=4, H=1, kappa=0.5)
+    fm = G.build_model(cfg, 32)
+    notes, tau, t_hat, Y, _ = G.synth_batch(4, 5, 6, 32, 4, 9)
+    n, ta, th, Yc = notes.cuda(), tau.cuda(), t_hat.cuda(), Y.cuda()
+    bad = n.clone(); bad[0, 0, 0] = float("nan")
+    with pytest.raises(ValueError, match="V contain NaN"):
+        fm(bad, ta, th, Yc)
+    with pytest.raises(ValueError, match="V contain NaN"):
+        fm.ttf(bad, ta, th)
+    badY = Yc.clone(); badY[1, 2, 3] = float("nan")
+    with pytest.raises(ValueError, match="Y_ts contains NaN"):
+        fm(n, ta, th, badY)
+    with pytest.raises(ValueError, match="Expected t_hat shape"):
+        fm(n, ta, th[:2], Yc)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        fm(notes, tau, t_hat, Y)
+    with torch.no_grad():
+        fm.mmf.residual_head.bias[0] = float("nan")
+    with pytest.raises(ValueError, match="Y_out contains NaN"):
+        fm(n, ta, th, Yc)
+
+
+def test_standalone_modules_match_composition():
+    cfg = dict(ttf="TTF_T2V_XAttn", mmf="MMF_XAttn_Add", d_txt=32, C=4, H=2, kappa=0.5)
+    fm = G.build_model(cfg, 32)
+    fm.eval()
+    notes, tau, t_hat, Y, _ = G.synth_batch(4, 5, 6, 32, 4, 10)
+    with torch.no_grad():
+        E, M = fm.ttf(notes.cuda(), tau.cuda(), t_hat.cuda())
+        y_a = fm.mmf(Y.cuda(), E, M)
+        y_b = fm(notes.cuda(), tau.cuda(), t_hat.cuda(), Y.cuda())
+    assert torch.equal(y_a, y_b)
+
+
+def test_dropout_is_statistically_right():
+    """Train-mode dropout keeps ~(1-p) of the elements and differs between calls when no seed is pinned."""
+    from immtsf import runtime
+
+    runtime.SEEDS.fixed = None
+    cfg = dict(ttf="TTF_RecAvg", mmf="MMF_GR_Add", d_txt=256, C=4, H=1, kappa=0.5)
+    fm = G.build_model(cfg, 64, dropout=0.25)
+    fm.train()
+    with torch.no_grad():
+        fm.ttf.proj.weight.copy_(torch.eye(256)); fm.ttf.proj.bias.zero_()
+    notes, tau, t_hat, Y, _ = G.synth_batch(16, 5, 12, 64, 4, 12)
+    with torch.no_grad():
+        E1, _ = fm.ttf(notes.cuda(), tau.cuda(), t_hat.cuda())
+        E2, _ = fm.ttf(notes.cuda(), tau.cuda(), t_hat.cuda())
+    frac = (E1 == 0).float().mean().item()
+    assert abs(frac - 0.25) < 0.02, frac
+    assert not torch.equal(E1, E2)
