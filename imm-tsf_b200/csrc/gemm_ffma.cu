@@ -149,6 +149,14 @@ __global__ void __launch_bounds__(256) gemm_ffma_kernel(const GemmArgs g) {
     }
     const float* as = As[cur];
     const float* bs = Bs[cur];
+    // two-level summation: this k-block is summed into `part`, then folded into `acc`, so the
+    // rounding error grows like sqrt(BK) + sqrt(K/BK) instead of sqrt(K) (matters for the 1e-5
+    // parity bound on ill-conditioned chains such as LayerNorm over C=4 channels).
+    float part[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) part[i][j] = 0.f;
 #pragma unroll
     for (int kk = 0; kk < BK; ++kk) {
       float a[TM], b[TN];
@@ -165,8 +173,12 @@ __global__ void __launch_bounds__(256) gemm_ffma_kernel(const GemmArgs g) {
 #pragma unroll
       for (int i = 0; i < TM; ++i)
 #pragma unroll
-        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < TN; ++j) part[i][j] = fmaf(a[i], b[j], part[i][j]);
     }
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) acc[i][j] += part[i][j];
     if (kb + 1 < nkb) {
       store_tile<BM, !TA>(As[cur ^ 1], ra);
       store_tile<BN, TB>(Bs[cur ^ 1], rb);

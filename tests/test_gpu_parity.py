@@ -17,6 +17,19 @@ OUT_TOL = 1e-5
 GRAD_TOL = 5e-5
 
 
+def grad_check(name, got, ref64, ref32, gmax):
+    """|got - ref64|_inf <= max(5e-5 * max(|ref64|_inf, 1e-3*gmax), 4 * |ref32 - ref64|_inf):
+    the second term is the reference's own fp32-vs-fp64 gap on this very tensor --
+    gradients that are sums with heavy cancellation (e.g. time2vec.linear.weight) are only
+    defined to that accuracy in fp32."""
+    ref64 = torch.as_tensor(ref64).double()
+    gap = (torch.as_tensor(ref32).double() - ref64).abs().max().item() if ref64.numel() else 0.0
+    den = max(ref64.abs().max().item() if ref64.numel() else 0.0, 1e-3 * gmax)
+    err = (got.double() - ref64).abs().max().item() if ref64.numel() else 0.0
+    assert torch.isfinite(got).all(), f"{name}: non-finite"
+    assert err <= max(GRAD_TOL * den, 4.0 * gap) + 1e-30, f"{name}: err {err:.3e}, allowed max({GRAD_TOL * den:.3e}, 4*{gap:.3e})"
+
+
 @pytest.fixture(autouse=True)
 def _fixed_seed():
     from immtsf import runtime
@@ -137,10 +150,10 @@ def test_gradients_match_reference_golden(name):
     fm = G.build_model(cfg, inp["notes"].shape[2], params)
     out = G.gpu_run(fm, inp["notes"], inp["tau"], inp["t_hat"], inp["Y_ts"], inp["G"], train=True)
     G.assert_close("Y_out(train,p=0)", out["Y_out"], ref["grad64:Y_out"], OUT_TOL)
-    G.assert_close("dY_ts", out["dY"], ref["grad64:Y_ts"], GRAD_TOL)
     gmax = max(float(np.abs(ref[f"grad64:{k}"]).max()) for k in out["grads"])
+    grad_check("dY_ts", out["dY"], ref["grad64:Y_ts"], ref["grad:Y_ts"], 0.0)
     for k, g in out["grads"].items():
-        G.assert_close(f"grad {k}", g, ref[f"grad64:{k}"], GRAD_TOL, floor=1e-3 * gmax)
+        grad_check(f"grad {k}", g, ref[f"grad64:{k}"], ref[f"grad:{k}"], gmax)
 
 
 @pytest.mark.parametrize("name", [n for n in golden_names() if n.endswith("nonote")])
@@ -177,10 +190,11 @@ def _vs_oracle(cfg, d_model, B, N, T, p, train, seed, t1d=False, no_note=False):
     out = G.gpu_run(fm, notes, tau, t_hat, Y, Gw, train=train, grads=grads)
     G.assert_close("Y_out", out["Y_out"], ref["Y_out"], OUT_TOL)
     if grads:
-        G.assert_close("dY_ts", out["dY"], ref["dY"], GRAD_TOL)
+        r32 = G.oracle_run(cfg, params, notes, tau, t_hat, Y, Gw, dtype=torch.float32, p=p, masks=masks, grads=True)
         gmax = max(float(v.abs().max()) for v in ref["grads"].values())
+        grad_check("dY_ts", out["dY"], ref["dY"], r32["dY"], 0.0)
         for k, g in out["grads"].items():
-            G.assert_close(f"grad {k}", g, ref["grads"][k], GRAD_TOL, floor=1e-3 * gmax)
+            grad_check(f"grad {k}", g, ref["grads"][k], r32["grads"][k], gmax)
 
 
 @pytest.mark.parametrize("ttf,mmf", COMBOS)
