@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""Benchmark of the IMM-TSF text->time-series fusion hot path (BASELINE.json metric:
+fused TTF+MMF samples/s, forward+backward, with roofline fraction and the host-CPU
+reference beside it).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2|cfg1|cfg3]
+    python bench.py --impl reference ...     # CPU arm: the oracle port on the host cores
+
+One "step" = FusionModel forward + backward (every parameter gradient and dY_ts) over one
+synthetic Time-IMM-shaped batch; train mode, dropout 0.1, loss = mean(Y_out^2).  The
+optimizer is not part of the fusion path and is not timed.
+
+  value     samples/s with the batch already resident in HBM; per-step CUDA-event times,
+            L2 flushed (256 MiB write) before every timed step, max over ranks.
+  e2e       same step through the public FusionModel API fed from pinned HOST buffers:
+            H2D of notes/tau/t_hat/Y_ts and D2H of the loss inside the timed region.
+  roofline  the dominant kernel family of the workload (dense projections: immtsf_gemm),
+            algorithmic FLOPs / summed CUDA-event launch durations vs the measured bf16 peak.
+  cpu_baseline  the oracle port (oracle/immtsf_oracle.py, follows the reference line by line
+            incl. its T_f-fold K/V expansion) on the host cores, bounded sample.
+N > 1: launched by torchrun, one rank per GPU; every rank runs its own B-sized shard (weak
+scaling) and the step ends with one NCCL all-reduce of the flat gradient bucket.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "imm-tsf_b200"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # BASELINE.json configs[1]: the configuration the metric is quoted on
+    "cfg2": dict(ttf="TTF_T2V_XAttn", mmf="MMF_XAttn_Add", B=256, N=16, T=24, d_model=768, d_txt=768, C=4, H=1, kappa=0.5,
+                 history=7.0, pred=7.0, cpu_sample_B=32,
+                 name="cfg2: T2V_XAttn+XAttn_Add, B256 N<=16 T24 d768 C4 H1 (BASELINE.json configs[1])"),
+    # configs[0]: the reference's own CPU-runnable case
+    "cfg1": dict(ttf="TTF_RecAvg", mmf="MMF_GR_Add", B=32, N=16, T=24, d_model=768, d_txt=768, C=4, H=1, kappa=0.5,
+                 history=7.0, pred=7.0, cpu_sample_B=32,
+                 name="cfg1: RecAvg+GR_Add, B32 N<=16 T24 d768 C4 (BASELINE.json configs[0])"),
+    # configs[2]: LLaMA-width embeddings, GDELT-shaped
+    "cfg3": dict(ttf="TTF_T2V_XAttn", mmf="MMF_GR_Add", B=256, N=64, T=28, d_model=4096, d_txt=768, C=5, H=1, kappa=0.5,
+                 history=14.0, pred=14.0, cpu_sample_B=16,
+                 name="cfg3: T2V_XAttn+GR_Add, B256 N<=64 T28 d_model4096->768 C5 (BASELINE.json configs[2])"),
+}
+DROPOUT = 0.1
+METRIC = "fused TTF+MMF fwd+bwd throughput"
+UNIT = "samples/s"
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            pk = json.load(f)
+        return dict(hbm=float(pk["hbm_gbs"]), tensor=float(pk.get("bf16_tflops_sustained", pk["bf16_tflops"])),
+                    src="MEASURED_PEAKS.json (bf16 sustained)")
+    except Exception:
+        return dict(hbm=6650.0, tensor=1400.0, src="fallback (B200_PROFILING.md)")
+
+
+def make_batch(w, seed):
+    import gpu_common as G
+
+    return G.synth_batch(w["B"], w["N"], w["T"], w["d_model"], w["C"], seed, history=w["history"], pred=w["pred"])
+
+
+def algorithmic_flops(w, sumN, per_query=True):
+    """SURVEY.md 8(d) 'Algorithmic FLOPs per batch' (deduplicated), forward; backward = 2x except input_proj (1x)."""
+    B, T, d_m, d, C = w["B"], w["T"], w["d_model"], w["d_txt"], w["C"]
+    ST = B * T
+    f_in = 2 * sumN * d_m * d
+    if w["ttf"] == "TTF_RecAvg":
+        ttf = 2 * sumN * T * d + 2 * ST * d * d  # pool (upper bound sum_i T_i N_i d) + proj
+    else:
+        R = ST if per_query else B
+        ttf = 2 * sumN * (d + d // 2) * d + 2 * sumN * d * 2 * d + 2 * d * d + 2 * sumN * d + 2 * sumN * T * d + 2 * R * d * d * 2
+    if w["mmf"] == "MMF_GR_Add":
+        mmf = 2 * ST * (C + d) * 4 * C + 2 * ST * 3 * C * C + 2 * ST * C * C
+    else:
+        mmf = 2 * ST * C * d + 2 * 2 * ST * d * d + 3 * 2 * ST * d * d + 4 * B * T * T * d + 2 * ST * d * d + 2 * ST * d * C
+    return f_in + ttf + mmf, f_in + 3 * (ttf + mmf) + f_in
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def cpu_oracle_step_fn(w, sample_B, threads):
+    """Returns (fn, samples): one fwd+bwd of the oracle port on `sample_B` samples of the workload."""
+    import gpu_common as G
+    from oracle import immtsf_oracle as O
+
+    torch.set_num_threads(threads)
+    cfg = dict(ttf=w["ttf"], mmf=w["mmf"], d_txt=w["d_txt"], C=w["C"], H=w["H"], kappa=w["kappa"])
+    shapes = O.param_shapes(w["ttf"], w["mmf"], w["d_model"], w["d_txt"], w["C"])
+    g = torch.Generator().manual_seed(7)
+    P = {}
+    for k, s in shapes.items():
+        if k.endswith("log_recency_sigma"):
+            P[k] = torch.tensor(0.0)
+        elif k.endswith("layer_norm.weight"):
+            P[k] = torch.ones(s)
+        else:
+            fan = s[-1] if len(s) >= 2 else 1
+            P[k] = (torch.rand(s, generator=g) * 2 - 1) / max(fan, 1) ** 0.5
+    for v in P.values():
+        v.requires_grad_(True)
+    notes, tau, t_hat, Y, _ = G.synth_batch(sample_B, w["N"], w["T"], w["d_model"], w["C"], 1234, history=w["history"], pred=w["pred"])
+    B, N, T, C, H, d = sample_B, w["N"], w["T"], w["C"], w["H"], w["d_txt"]
+    keep = lambda *s: (torch.rand(*s, generator=g) >= DROPOUT).float()
+    masks = {"ttf.dropout": keep(B, T, d), "mmf.dropout": keep(B, T, C)}
+    if w["ttf"] == "TTF_T2V_XAttn":
+        masks["ttf.attn_dropout"] = keep(B, T, H, N)
+    if w["mmf"] == "MMF_XAttn_Add":
+        masks["mmf.attn_dropout"] = keep(B, H, T, T)
+
+    def step():
+        for v in P.values():
+            v.grad = None
+        Yr = Y.clone().requires_grad_(True)
+        out = O.fusion_forward(P, cfg["ttf"], cfg["mmf"], notes, tau, t_hat, Yr, n_heads=H, kappa=cfg["kappa"], p=DROPOUT,
+                               masks=masks, faithful_expand=True)
+        out.square().mean().backward()
+        return float(out.detach()[0, 0, 0])
+
+    return step, sample_B
+
+
+def time_cpu(w, steps, warmup, threads):
+    step, nB = cpu_oracle_step_fn(w, w["cpu_sample_B"], threads)
+    for _ in range(warmup):
+        step()
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step()
+        ts.append(time.perf_counter() - t0)
+    med = statistics.median(ts)
+    return nB / med, med, nB
+
+
+def run_reference_arm(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    steps = max(1, min(args.steps, 5))
+    warm = max(1, min(args.warmup, 2))
+    sps, med, nB = time_cpu(w, steps, warm, threads)
+    sample = f"{nB} of {w['B']} samples per step, fwd+bwd, dropout {DROPOUT}, {steps} timed steps (median), {warm} warm-up"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": sps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+        "ms_per_step": med * 1e3 * (w["B"] / nB), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": {"workload": w["name"], "parallelism": "host CPU threads"},
+        "cpu_baseline": {"value": sps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": sps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- GPU arm
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, dev):
+        self.dev, self.proc, self.path = dev, None, f"/tmp/immtsf_clocks_{os.getpid()}.csv"
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.dev)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in open(self.path):
+            c = [x.strip() for x in ln.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_gpu_arm(args, w):
+    import torch.distributed as dist
+    import gpu_common as G
+    from immtsf import _lib, dp, ops, runtime
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    os.environ.setdefault("IMMTSF_NAN_CHECK", "0")  # the guard's single host sync is measured separately in e2e_checked
+
+    cfg = dict(ttf=w["ttf"], mmf=w["mmf"], d_txt=w["d_txt"], C=w["C"], H=w["H"], kappa=w["kappa"])
+    fm = G.build_model(cfg, w["d_model"], dropout=DROPOUT, seed=1)  # same init on every rank
+    fm.train()
+    params = [p for p in fm.parameters()]
+    notes, tau, t_hat, Y, _ = make_batch(w, 1234 + rank)
+    sumN = int((notes.abs().sum(2) > 0).sum())
+    h_in = [t.pin_memory() for t in (notes, tau, t_hat, Y)]
+    d_in = [t.to(dev) for t in h_in]
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+
+    def step(inp):
+        for p in params:
+            p.grad = None
+        Yr = inp[3].detach().requires_grad_(True)
+        out = fm(inp[0], inp[1], inp[2], Yr)
+        loss = out.square().mean()
+        loss.backward()
+        if world > 1:
+            dp.allreduce_grads(params)
+        return loss
+
+    def timed(n, resident):
+        total_ms = 0.0
+        for _ in range(n):
+            flush.fill_(1.0)  # L2 flush, outside the timed events
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            if resident:
+                loss = step(d_in)
+            else:
+                inp = [t.to(dev, non_blocking=True) for t in h_in]
+                loss = step(inp)
+                loss_host.copy_(loss.detach(), non_blocking=True)
+            e1.record()
+            e1.synchronize()
+            total_ms += e0.elapsed_time(e1)
+        return total_ms
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    W, K = max(args.warmup, 3), args.steps
+    timed(W, True)
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    l0 = _lib.launch_count()
+    ms_res = timed(K, True)
+    launches = _lib.launch_count() - l0
+    barrier()
+    ms_res = max_over_ranks(ms_res)
+    timed(2, False)
+    barrier()
+    ms_e2e = max_over_ranks(timed(K, False))
+    barrier()
+    clk = clocks.stop() if rank == 0 else None
+
+    # instrumented pass: per-launch CUDA events around every dense projection
+    ops.PROFILE = []
+    nprof = min(K, 5)
+    timed(nprof, True)
+    torch.cuda.synchronize()
+    gemm_ms = sum(e0.elapsed_time(e1) for (_, _, e0, e1) in ops.PROFILE)
+    gemm_flops = sum(2.0 * m * n * k for (_, (m, n, k, rd), _, _) in ops.PROFILE)
+    n_gemm = len(ops.PROFILE)
+    ops.PROFILE = None
+    # ragged GEMMs are issued over M_alloc rows but only sumN are live: count live work only
+    # (ragged launches are the ones whose M or K equals M_alloc)
+    M_alloc = max((w["B"] * w["N"] + 127) // 128 * 128, 128)
+    live = 0.0
+    ops.PROFILE = []
+    timed(1, True)
+    torch.cuda.synchronize()
+    for (_, (m, n, k, rd), _, _) in ops.PROFILE:
+        if rd == 1:
+            m = min(m, sumN)
+        elif rd == 2:
+            k = min(k, sumN)
+        live += 2.0 * m * n * k
+    ops.PROFILE = None
+    gemm_flops_live = live * nprof
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = load_peaks()
+    samples = w["B"] * world * K
+    value = samples / (ms_res / 1e3)
+    e2e = samples / (ms_e2e / 1e3)
+    h2d = sum(t.numel() * t.element_size() for t in h_in)
+    fwd_f, fb_f = algorithmic_flops(w, sumN)
+    achieved = gemm_flops_live / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+    threads = os.cpu_count() or 1
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        sps, med, nB = time_cpu(w, 2, 1, threads)
+        cpu = {"value": sps, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{nB} of {w['B']} samples per step, fwd+bwd, dropout {DROPOUT}, 2 timed steps (median), 1 warm-up; "
+                         f"{med * 1e3:.0f} ms/step"}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_res / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": w["name"], "step": "FusionModel forward+backward (all param grads + dY_ts), train mode, dropout 0.1",
+                   "per_gpu_batch": w["B"], "global_batch": w["B"] * world, "sum_notes_rank0": sumN,
+                   "parallelism": f"dp{world}" if world > 1 else "single",
+                   "l2": "256 MiB flush write before every timed step", "gemm_backend": os.environ.get("IMMTSF_GEMM", "auto"),
+                   "algorithmic_gflop_fwd_bwd": fb_f / 1e9},
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / K},
+        "gpu_launches": launches,
+        "clocks": clk,
+        "roofline": {"bound": "tensor", "kernel": "immtsf_gemm (dense projections, %d launches/step)" % (n_gemm // max(nprof, 1)),
+                     "achieved": achieved, "peak": peaks["tensor"], "unit": "TFLOP/s", "frac": achieved / peaks["tensor"],
+                     "traffic": None, "peak_source": peaks["src"],
+                     "gemm_share_of_step": (gemm_ms / nprof) / (ms_res / K) if ms_res > 0 else None,
+                     "step_tflops_algorithmic": fb_f / (ms_res / K / 1e3) / 1e12},
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference_arm(args, w)
+    else:
+        run_gpu_arm(args, w)
+
+
+if __name__ == "__main__":
+    main()

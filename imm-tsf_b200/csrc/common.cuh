@@ -12,6 +12,7 @@
 #define IMMTSF_ERR_ARCH (-4)
 
 void immtsf_set_error(const char* fmt, ...);
+void immtsf_count_launch();  // host-side counter of kernel launches (bench.py's gpu_launches)
 
 #define IMMTSF_REQUIRE(cond, ...)            \
   do {                                       \
@@ -23,6 +24,7 @@ void immtsf_set_error(const char* fmt, ...);
 
 #define IMMTSF_CHECK_LAUNCH(name)                                             \
   do {                                                                        \
+    immtsf_count_launch();                                                    \
     cudaError_t e__ = cudaGetLastError();                                     \
     if (e__ != cudaSuccess) {                                                 \
       immtsf_set_error("%s: launch failed: %s", name, cudaGetErrorString(e__)); \

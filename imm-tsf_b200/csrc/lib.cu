@@ -13,6 +13,10 @@ void immtsf_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static unsigned long long g_launches = 0;
+void immtsf_count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
+extern "C" unsigned long long immtsf_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+
 extern "C" int immtsf_version(void) { return IMMTSF_ABI_VERSION; }
 extern "C" const char* immtsf_last_error_string(void) { return g_err; }
 

@@ -73,8 +73,14 @@ def load():
         fn.restype = I
     lib.immtsf_last_error_string.argtypes = []
     lib.immtsf_last_error_string.restype = C.c_char_p
+    lib.immtsf_launch_count.argtypes = []
+    lib.immtsf_launch_count.restype = C.c_ulonglong
     _lib = lib
     return lib
+
+
+def launch_count() -> int:
+    return int(load().immtsf_launch_count())
 
 
 def call(name, *args):

@@ -15,6 +15,9 @@ SITE_TTF_DROPOUT, SITE_TTF_ATTN, SITE_MMF_DROPOUT, SITE_MMF_ATTN = 1, 2, 3, 4
 FLAG_V, FLAG_Y, FLAG_E, FLAG_OUT = 0, 1, 2, 3
 LN_EPS = 1e-5
 
+# bench.py sets this to a list to collect (label, flops, start_event, end_event) per GEMM launch
+PROFILE = None
+
 
 def gemm_backend() -> int:
     v = os.environ.get("IMMTSF_GEMM", "auto").lower()
@@ -126,9 +129,16 @@ def gemm(A, B, C, transA=False, transB=False, bias=None, alpha=1.0, beta=0.0, ra
     if bias is not None:
         _chk(bias, "bias")
         assert bias.numel() == N and bias.is_contiguous()
+    prof = PROFILE
+    if prof is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
     _lib.call("immtsf_gemm", int(transA), int(transB), M, N, K, float(alpha), _p(A), A.stride(0), _p(B), B.stride(0),
               float(beta), _p(C), C.stride(0), _p(bias), _p(ragged), ragged_dim,
               gemm_backend() if backend is None else backend, _stream())
+    if prof is not None:
+        ev1.record()
+        prof.append(("gemm", (M, N, K, ragged_dim), ev0, ev1))
     return C
 
 

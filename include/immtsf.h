@@ -43,6 +43,8 @@ int immtsf_version(void);
 const char* immtsf_last_error_string(void);
 /* 1 if `device` is compute capability 10.x (B200), 0 otherwise, <0 on error */
 int immtsf_device_supported(int device);
+/* number of kernel launches issued by this library in this process (monotonic) */
+unsigned long long immtsf_launch_count(void);
 
 /* ---- K1: padded -> ragged CSR (replaces the content mask of
  * fusions/TTF_RecAvg.py:69 / fusions/TTF_T2V_XAttn.py:107, the NaN guard of

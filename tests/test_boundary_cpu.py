@@ -21,7 +21,7 @@ def _header_decls():
     src = open(HEADER).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     decls = {}
-    for m in re.finditer(r"\b(?:int|const char\*)\s+(immtsf_\w+)\s*\(([^)]*)\)\s*;", src):
+    for m in re.finditer(r"\b(?:int|const char\*|unsigned long long)\s+(immtsf_\w+)\s*\(([^)]*)\)\s*;", src):
         name, args = m.group(1), m.group(2).strip()
         decls[name] = [] if args in ("", "void") else [a.strip() for a in args.split(",")]
     return decls
@@ -54,7 +54,7 @@ def test_binding_signatures_match_header():
             else:
                 base = carg.split()[-2] if len(carg.split()) >= 2 else carg
                 assert ct.__name__ == C2CT[base], (name, carg, ct.__name__)
-    assert set(decls) - set(_lib.SIGNATURES) == {"immtsf_last_error_string"}
+    assert set(decls) - set(_lib.SIGNATURES) == {"immtsf_last_error_string", "immtsf_launch_count"}
 
 
 def test_library_contains_sm100a_code_only():
