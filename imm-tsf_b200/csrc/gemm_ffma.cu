@@ -15,9 +15,10 @@
 
 int immtsf_gemm_tc(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda,
                    const float* B, int ldb, float beta, float* C, int ldc, const float* bias,
-                   const int32_t* ragged, int ragged_dim, cudaStream_t st);
-int immtsf_gemm_tc_eligible(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B,
-                            int ldb, const float* C, int ldc);
+                   const int32_t* ragged, int ragged_dim, void* workspace, size_t workspace_bytes, cudaStream_t st);
+size_t immtsf_gemm_tc_workspace(int transA, int transB, int M, int N, int K);
+int immtsf_gemm_tc_eligible(int forced, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+                            const float* C, int ldc);
 
 struct GemmArgs {
   int M, N, K;
@@ -242,7 +243,8 @@ static inline int aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
 extern "C" int immtsf_gemm(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda,
                            const float* B, int ldb, float beta, float* C, int ldc, const float* bias,
-                           const int32_t* ragged, int ragged_dim, int backend, void* stream) {
+                           const int32_t* ragged, int ragged_dim, int backend, void* workspace,
+                           size_t workspace_bytes, void* stream) {
   IMMTSF_REQUIRE(M >= 0 && N >= 0 && K >= 0, "gemm: negative dimension");
   if (M == 0 || N == 0) return IMMTSF_OK;
   IMMTSF_REQUIRE(A && B && C, "gemm: null operand");
@@ -253,8 +255,10 @@ extern "C" int immtsf_gemm(int transA, int transB, int M, int N, int K, float al
   cudaStream_t st = (cudaStream_t)stream;
 
   if (backend != 1) {
-    const int ok = immtsf_gemm_tc_eligible(transA, transB, M, N, K, A, lda, B, ldb, C, ldc);
-    if (ok) return immtsf_gemm_tc(transA, transB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, ragged, ragged_dim, st);
+    const int ok = immtsf_gemm_tc_eligible(backend == 2, M, N, K, A, lda, B, ldb, C, ldc);
+    if (ok && (backend == 2 || workspace != nullptr))
+      return immtsf_gemm_tc(transA, transB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, ragged, ragged_dim, workspace,
+                            workspace_bytes, st);
     if (backend == 2) {
       immtsf_set_error("gemm: tcgen05 backend requested but shape/alignment is not eligible");
       return IMMTSF_ERR_UNSUPPORTED;
@@ -274,6 +278,10 @@ extern "C" int immtsf_gemm(int transA, int transB, int M, int N, int K, float al
   else launch_ffma<64, 64, 4, 4>(g, transA, transB, st);
   IMMTSF_CHECK_LAUNCH("gemm_ffma");
   return IMMTSF_OK;
+}
+
+extern "C" size_t immtsf_gemm_workspace_bytes(int transA, int transB, int M, int N, int K) {
+  return immtsf_gemm_tc_workspace(transA, transB, M, N, K);
 }
 
 // ------------------------------------------------------------------ colsum

@@ -1,10 +1,435 @@
-// tcgen05 / TMEM / TMA 3xTF32 GEMM backend (placeholder until the tensor-core
-// path lands): reports "not eligible" so immtsf_gemm routes to the FFMA kernel.
+// tcgen05 / TMEM / TMA GEMM backend with fp32 accuracy (3xTF32).
+//
+//   C[M,N] = alpha * op(A) op(B) + beta * C + bias
+//
+// fp32 parity (1e-5) rules out a single TF32 pass (10-bit mantissa, ~1e-3).
+// Every operand x is split in global memory into x_hi = x with the low 13
+// mantissa bits cleared (exactly representable in TF32) and x_lo = x - x_hi
+// (exact in fp32, |x_lo| <= 2^-11 |x|), and the tensor core accumulates
+//   A_lo*B_hi + A_hi*B_lo + A_hi*B_hi      (small terms first)
+// in fp32 in TMEM; the dropped A_lo*B_lo term is ~2^-22 relative.
+//
+// Kernel (one CTA per 128 x 128 output tile, 256 threads, warp-specialised):
+//   warp 0   TMA producer: per 32-wide k-block four 128B-swizzled tiles
+//            (A_hi, A_lo, B_hi, B_lo; 64 KiB) into a 3-stage smem ring,
+//            completion on mbarriers (cp.async.bulk.tensor.2d).
+//   warp 1   MMA issuer: one lane issues 12 tcgen05.mma.kind::tf32
+//            (3 products x 4 k-steps of 8) per k-block, accumulator =
+//            128 lanes x 128 fp32 columns of TMEM; tcgen05.commit frees the
+//            smem stage and finally signals the epilogue.
+//   warp 2   TMEM allocation / deallocation.
+//   warps 4-7 epilogue: the tensor core's fp32 accumulator adds with truncation,
+//            so a long K chain drifts (measured 6e-6 at K=768).  The K loop is
+//            therefore cut in chunks of KC k-blocks (K=128): each chunk is
+//            accumulated in one of two TMEM buffers, drained with tcgen05.ld
+//            (lane == output row) and promoted into fp32 registers with
+//            round-to-nearest adds while the next chunk's MMAs run.  Then
+//            alpha / bias / beta, ragged-row zeroing, 128-bit stores.
+// Operands may be K-major or MN-major in memory (all four transposition
+// cases): the UMMA shared-memory descriptor and instruction descriptor carry
+// the major-ness.  K-major tiles use the 128B swizzle; MN-major fp32/tf32
+// tiles must use the "128B swizzle with 32B atoms" layout (UMMA layout type 1,
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) and are fetched as 32x32 boxes.
+//
+// Roofline: tensor pipe.  12 MMAs of 128x128x8 per k-block = 768 tensor
+// cycles for 2*128*128*32 useful FLOP -> 3xTF32 ceiling = 1/3 of the TF32
+// peak (= 1/6 of the bf16 peak used as roofline.peak in bench.py).
+#include <cuda.h>
 #include "common.cuh"
 
-int immtsf_gemm_tc_eligible(int, int, int, int, int, const float*, int, const float*, int, const float*, int) { return 0; }
-int immtsf_gemm_tc(int, int, int, int, int, float, const float*, int, const float*, int, float, float*, int,
-                   const float*, const int32_t*, int, cudaStream_t) {
-  immtsf_set_error("gemm_tc: not built");
-  return IMMTSF_ERR_UNSUPPORTED;
+namespace {
+
+constexpr int BM = 128, BN = 128, BKT = 32, STAGES = 3;
+constexpr int TILE_A = BM * BKT * 4;                  // 16 KiB
+constexpr int TILE_B = BN * BKT * 4;                  // 16 KiB
+constexpr int STAGE_BYTES = 2 * TILE_A + 2 * TILE_B;  // hi+lo of both operands
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int KC = 4;                                 // k-blocks per TMEM accumulation chunk (K = 128)
+constexpr int TMEM_COLS = 2 * BN;                     // two accumulator buffers
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory descriptor, version 1 (Blackwell).
+//   K-major  (layout 2, SWIZZLE_128B): rows of 128 B (32 fp32 of K); 8-row groups SBO = 1024 B apart; LBO unused.
+//   MN-major (layout 1, SWIZZLE_128B_BASE32B -- the only one legal for 32-bit MN-major operands): 32x32 boxes of
+//             4096 B; k-rows of 128 B (32 fp32 of M/N); 4-row k-groups SBO = 512 B apart; blocks of 32 along M/N
+//             LBO = 4096 B apart.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, bool mn_major) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)(mn_major ? (4096u >> 4) : 1u) << 16;
+  d |= (uint64_t)(mn_major ? (512u >> 4) : (1024u >> 4)) << 32;
+  d |= (uint64_t)1 << 46;                     // version
+  d |= (uint64_t)(mn_major ? 1u : 2u) << 61;  // layout type
+  return d;
+}
+
+struct TcArgs {
+  float* C;
+  int ldc;
+  int M, N, K;
+  float alpha, beta;
+  const float* bias;
+  const int32_t* ragged;
+  int ragged_dim;
+};
+
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(256, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
+               const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl, const TcArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  int M = g.M, K = g.K;
+  if (g.ragged_dim == 1) M = ragged_rows(M, g.ragged);
+  if (g.ragged_dim == 2) K = ragged_rows(K, g.ragged);
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  if (g.ragged_dim == 1 && m0 >= M) return;  // whole tile beyond the ragged end (uniform per CTA)
+  const int nkb = (K + BKT - 1) / BKT;
+
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = base + STAGES * STAGE_BYTES;  // full[STAGES], empty[STAGES], tfull[2], tempty[2], tmem_ptr
+  const uint32_t bar_full = bars, bar_empty = bars + 8 * STAGES, bar_tfull = bars + 16 * STAGES;
+  const uint32_t bar_tempty = bar_tfull + 16, tmem_slot = bar_tempty + 16;
+  const int nchunks = (nkb + KC - 1) / KC;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_tfull + 8 * b, 1);
+      mbar_init(bar_tempty + 8 * b, 4);  // one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0 && lane == 0) {
+    // ===== TMA producer =====
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % STAGES, ph = (kb / STAGES) & 1;
+      mbar_wait(bar_empty + 8 * s, ph ^ 1);
+      const uint32_t sa_h = base + s * STAGE_BYTES, sa_l = sa_h + TILE_A, sb_h = sa_l + TILE_A, sb_l = sb_h + TILE_B;
+      const uint32_t fb = bar_full + 8 * s;
+      mbar_expect_tx(fb, STAGE_BYTES);
+      const int k0 = kb * BKT;
+      if (!A_MN) {
+        tma_load_2d(sa_h, &mapAh, fb, k0, m0);
+        tma_load_2d(sa_l, &mapAl, fb, k0, m0);
+      } else {
+#pragma unroll
+        for (int j = 0; j < BM / 32; ++j) {
+          tma_load_2d(sa_h + j * 4096, &mapAh, fb, m0 + 32 * j, k0);
+          tma_load_2d(sa_l + j * 4096, &mapAl, fb, m0 + 32 * j, k0);
+        }
+      }
+      if (!B_MN) {
+        tma_load_2d(sb_h, &mapBh, fb, k0, n0);
+        tma_load_2d(sb_l, &mapBl, fb, k0, n0);
+      } else {
+#pragma unroll
+        for (int j = 0; j < BN / 32; ++j) {
+          tma_load_2d(sb_h + j * 4096, &mapBh, fb, n0 + 32 * j, k0);
+          tma_load_2d(sb_l + j * 4096, &mapBl, fb, n0 + 32 * j, k0);
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===== MMA issuer =====
+    // instruction descriptor: D=f32, A=B=tf32, majors, N>>3, M>>4
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                           ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    for (int c = 0; c < nchunks; ++c) {
+      const int buf = c & 1;
+      mbar_wait(bar_tempty + 8 * buf, ((c >> 1) & 1) ^ 1);  // epilogue has drained this TMEM buffer
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tacc = tmem_base + (uint32_t)(buf * BN);
+      const int kb_end = min(nkb, (c + 1) * KC);
+      for (int kb = c * KC; kb < kb_end; ++kb) {
+        const int s = kb % STAGES, ph = (kb / STAGES) & 1;
+        mbar_wait(bar_full + 8 * s, ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sa_h = base + s * STAGE_BYTES, sa_l = sa_h + TILE_A, sb_h = sa_l + TILE_A, sb_l = sb_h + TILE_B;
+#pragma unroll
+        for (int prod = 0; prod < 3; ++prod) {
+          const uint32_t sa = prod == 0 ? sa_l : sa_h;  // lo*hi, hi*lo, hi*hi
+          const uint32_t sb = prod == 1 ? sb_l : sb_h;
+#pragma unroll
+          for (int ks = 0; ks < BKT / 8; ++ks) {
+            const uint64_t ad = make_desc(sa + (A_MN ? ks * 1024 : ks * 32), A_MN);
+            const uint64_t bd = make_desc(sb + (B_MN ? ks * 1024 : ks * 32), B_MN);
+            umma_tf32(tacc, ad, bd, idesc, (kb != c * KC || prod != 0 || ks != 0) ? 1u : 0u);
+          }
+        }
+        umma_commit(bar_empty + 8 * s);  // arrives when the MMAs that read this stage have completed
+      }
+      umma_commit(bar_tfull + 8 * buf);
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue =====
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    float acc[BN];
+#pragma unroll
+    for (int j = 0; j < BN; ++j) acc[j] = 0.f;
+    for (int c = 0; c < nchunks; ++c) {
+      const int buf = c & 1;
+      mbar_wait(bar_tfull + 8 * buf, (c >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c0), v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(v[j]);  // fp32 round-to-nearest promotion
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+    }
+    const int row = m0 + q * 32 + lane;
+    const bool live = row < M;
+    if (row < g.M) {
+      float* crow = g.C + (size_t)row * g.ldc + n0;
+#pragma unroll
+      for (int j4 = 0; j4 < BN / 4; ++j4) {
+        const int n = n0 + j4 * 4;
+        if (n < g.N) {
+          float o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float x = g.alpha * acc[j4 * 4 + e];
+            if (g.bias != nullptr && n + e < g.N) x += __ldg(g.bias + n + e);
+            o[e] = live ? x : 0.f;
+          }
+          if (n + 3 < g.N) {
+            float4 ov = make_float4(o[0], o[1], o[2], o[3]);
+            if (g.beta != 0.f && live) {
+              const float4 cc = *reinterpret_cast<const float4*>(crow + j4 * 4);
+              ov.x = fmaf(g.beta, cc.x, ov.x); ov.y = fmaf(g.beta, cc.y, ov.y);
+              ov.z = fmaf(g.beta, cc.z, ov.z); ov.w = fmaf(g.beta, cc.w, ov.w);
+            }
+            *reinterpret_cast<float4*>(crow + j4 * 4) = ov;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              if (n + e < g.N) {
+                float x = o[e];
+                if (g.beta != 0.f && live) x = fmaf(g.beta, crow[j4 * 4 + e], x);
+                crow[j4 * 4 + e] = x;
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS));
+  }
+}
+
+// ---------------------------------------------------------------- operand split
+// hi = x & 0xFFFFE000 (TF32-exact), lo = x - hi.  rows x cols (ld_src) -> dense [rows][ld_dst].
+__global__ void split_tf32_kernel(const float* __restrict__ src, int ld_src, int rows, int cols, float* __restrict__ hi,
+                                  float* __restrict__ lo, int ld_dst, const int32_t* __restrict__ ragged, int ragged_rows_flag) {
+  int live_rows = rows;
+  if (ragged_rows_flag) {
+    const int m = ragged_rows(rows, ragged);
+    live_rows = (m + 127) / 128 * 128;  // pad rows are zeros written by the producers
+    if (live_rows > rows) live_rows = rows;
+  }
+  const int c4n = ld_dst >> 2;
+  const size_t total = (size_t)live_rows * c4n;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / c4n), c = (int)(i % c4n) * 4;
+    const float* p = src + (size_t)r * ld_src + c;
+    float4 x;
+    if (c + 3 < cols) x = *reinterpret_cast<const float4*>(p);
+    else {
+      x.x = c + 0 < cols ? p[0] : 0.f; x.y = c + 1 < cols ? p[1] : 0.f;
+      x.z = c + 2 < cols ? p[2] : 0.f; x.w = c + 3 < cols ? p[3] : 0.f;
+    }
+    float4 h, l;
+    h.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u); l.x = x.x - h.x;
+    h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u); l.y = x.y - h.y;
+    h.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u); l.z = x.z - h.z;
+    h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u); l.w = x.w - h.w;
+    *reinterpret_cast<float4*>(hi + (size_t)r * ld_dst + c) = h;
+    *reinterpret_cast<float4*>(lo + (size_t)r * ld_dst + c) = l;
+  }
+}
+
+// ---------------------------------------------------------------- tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+    else
+      (void)cudaGetLastError();
+  }
+  return fn;
+}
+
+// 2-D fp32 row-major [rows][cols] (ld), box = {32 cols, box_rows}, 128B swizzle
+int make_map(CUtensorMap* m, const float* ptr, int rows, int cols, int ld, int box_rows, bool mn_major) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return -1;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -2;
+}
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace
+
+// workspace: A_hi | A_lo | B_hi | B_lo, each dense with ld rounded up to 4 floats, 256 B aligned
+size_t immtsf_gemm_tc_workspace(int transA, int transB, int M, int N, int K) {
+  const size_t ra = transA ? K : M, ca = transA ? M : K, rb = transB ? N : K, cb = transB ? K : N;
+  const size_t a = align_up(ra * align_up(ca, 4) * 4, 256), b = align_up(rb * align_up(cb, 4) * 4, 256);
+  return 2 * a + 2 * b + 256;
+}
+
+// forced != 0: only hard requirements (alignment, driver entry point); else also the size heuristic
+int immtsf_gemm_tc_eligible(int forced, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+                            const float* C, int ldc) {
+  if (M < 1 || N < 1 || K < 1) return 0;
+  if (((uintptr_t)A & 15) != 0 || (lda & 3) != 0 || ((uintptr_t)B & 15) != 0 || (ldb & 3) != 0) return 0;  // split reads 128-bit
+  if (((uintptr_t)C & 15) != 0 || (ldc & 3) != 0) return 0;  // epilogue stores 128-bit
+  if (!forced) {
+    if (M < 64 || N < 32 || K < 32) return 0;  // tiny / skinny: CUDA cores
+    if ((double)M * N * K < 4.0e6) return 0;
+  }
+  return get_encode() != nullptr;
+}
+
+int immtsf_gemm_tc(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda, const float* B,
+                   int ldb, float beta, float* C, int ldc, const float* bias, const int32_t* ragged, int ragged_dim,
+                   void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  const size_t need = immtsf_gemm_tc_workspace(transA, transB, M, N, K);
+  if (workspace == nullptr || workspace_bytes < need) {
+    immtsf_set_error("gemm_tc: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
+    return IMMTSF_ERR_ARG;
+  }
+  const int ra = transA ? K : M, ca = transA ? M : K, rb = transB ? N : K, cb = transB ? K : N;
+  const int lda2 = (int)align_up(ca, 4), ldb2 = (int)align_up(cb, 4);
+  const size_t abytes = align_up((size_t)ra * lda2 * 4, 256), bbytes = align_up((size_t)rb * ldb2 * 4, 256);
+  uint8_t* w = (uint8_t*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+  float* Ah = (float*)w; float* Al = (float*)(w + abytes);
+  float* Bh = (float*)(w + 2 * abytes); float* Bl = (float*)(w + 2 * abytes + bbytes);
+  // rows of A are ragged when (ragged_dim==1 && !transA) or (ragged_dim==2 && transA); rows of B when ragged_dim==2 && !transB
+  const int a_ragged = (ragged_dim == 1 && !transA) || (ragged_dim == 2 && transA);
+  const int b_ragged = (ragged_dim == 2 && !transB);
+  {
+    size_t tot = (size_t)ra * (lda2 / 4);
+    int grid = (int)((tot + 255) / 256); if (grid > 148 * 16) grid = 148 * 16; if (grid < 1) grid = 1;
+    split_tf32_kernel<<<grid, 256, 0, st>>>(A, lda, ra, ca, Ah, Al, lda2, ragged, a_ragged);
+    tot = (size_t)rb * (ldb2 / 4);
+    grid = (int)((tot + 255) / 256); if (grid > 148 * 16) grid = 148 * 16; if (grid < 1) grid = 1;
+    split_tf32_kernel<<<grid, 256, 0, st>>>(B, ldb, rb, cb, Bh, Bl, ldb2, ragged, b_ragged);
+    IMMTSF_CHECK_LAUNCH("split_tf32");
+    immtsf_count_launch();
+  }
+  CUtensorMap mAh, mAl, mBh, mBl;
+  // K-major operand [rows=MN][cols=K]: box 32 x 128 ; MN-major operand [rows=K][cols=MN]: box 32 x 32
+  const int boxA = transA ? 32 : BM, boxB = transB ? BN : 32;
+  if (make_map(&mAh, Ah, ra, ca, lda2, boxA, transA != 0) || make_map(&mAl, Al, ra, ca, lda2, boxA, transA != 0) ||
+      make_map(&mBh, Bh, rb, cb, ldb2, boxB, transB == 0) || make_map(&mBl, Bl, rb, cb, ldb2, boxB, transB == 0)) {
+    immtsf_set_error("gemm_tc: cuTensorMapEncodeTiled failed");
+    return IMMTSF_ERR_LAUNCH;
+  }
+  TcArgs g;
+  g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K; g.alpha = alpha; g.beta = beta; g.bias = bias;
+  g.ragged = ragged; g.ragged_dim = ragged_dim;
+  dim3 grid(ceil_div(N, BN), ceil_div(M, BM));
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(gemm_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaFuncSetAttribute(gemm_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaFuncSetAttribute(gemm_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaFuncSetAttribute(gemm_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    attr_done = true;
+  }
+  // UMMA "B is K-major" means stored [N][K], i.e. transB=1
+  if (!transA && transB) gemm_tc_kernel<false, false><<<grid, 256, SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, g);
+  else if (!transA && !transB) gemm_tc_kernel<false, true><<<grid, 256, SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, g);
+  else if (transA && !transB) gemm_tc_kernel<true, true><<<grid, 256, SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, g);
+  else gemm_tc_kernel<true, false><<<grid, 256, SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, g);
+  IMMTSF_CHECK_LAUNCH("gemm_tc");
+  return IMMTSF_OK;
 }

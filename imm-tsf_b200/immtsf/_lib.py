@@ -27,7 +27,7 @@ SIGNATURES = {
     "immtsf_csr_build": [P, P, I, I, I, P, P, P, P, P, P, P, P, I, P],
     "immtsf_nan_check": [P, SZ, P, I, P],
     "immtsf_zero_pad_rows": [P, I, I, P, I, P],
-    "immtsf_gemm": [I, I, I, I, I, F, P, I, P, I, F, P, I, P, P, I, I, P],
+    "immtsf_gemm": [I, I, I, I, I, F, P, I, P, I, F, P, I, P, P, I, I, P, SZ, P],
     "immtsf_colsum": [P, I, I, I, P, F, P, P],
     "immtsf_recavg_pool_fwd": [P, I, P, P, P, I, P, P, P, I, I, I, F, U32, U64, P, P, P, P, P, P],
     "immtsf_recavg_pool_bwd": [P, P, P, P, P, P, I, P, P, P, I, P, P, I, I, I, U32, U64, P, I, P, P, P, P],
@@ -75,6 +75,8 @@ def load():
     lib.immtsf_last_error_string.restype = C.c_char_p
     lib.immtsf_launch_count.argtypes = []
     lib.immtsf_launch_count.restype = C.c_ulonglong
+    lib.immtsf_gemm_workspace_bytes.argtypes = [I, I, I, I, I]
+    lib.immtsf_gemm_workspace_bytes.restype = SZ
     _lib = lib
     return lib
 

@@ -110,6 +110,19 @@ def zero_pad_rows(X: torch.Tensor, ncols: int, m_dev: torch.Tensor, M_alloc: int
 
 
 # ------------------------------------------------------------------ GEMM
+_WS = {}
+
+
+def _workspace(dev, nbytes: int) -> torch.Tensor:
+    """Per-device scratch for the tcgen05 backend's operand split.  Grows on demand; reuse across GEMMs is
+    safe because every launch is ordered on the current stream."""
+    w = _WS.get(dev)
+    if w is None or w.numel() < nbytes:
+        w = torch.empty(max(nbytes, 64 << 20), dtype=torch.uint8, device=dev)
+        _WS[dev] = w
+    return w
+
+
 def _mat(t: torch.Tensor, name: str):
     _chk(t, name)
     if t.dim() != 2 or t.stride(1) != 1:
@@ -133,9 +146,14 @@ def gemm(A, B, C, transA=False, transB=False, bias=None, alpha=1.0, beta=0.0, ra
     if prof is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
+    be = gemm_backend() if backend is None else backend
+    ws, ws_bytes = None, 0
+    if be == BACKEND_TC or (be == BACKEND_AUTO and M >= 64 and N >= 32 and K >= 32):
+        ws_bytes = 8 * (M * (K + 4) + (K + 4) * (N + 4)) + 2048  # >= immtsf_gemm_workspace_bytes
+        ws = _workspace(C.device, ws_bytes)
+        ws_bytes = ws.numel()
     _lib.call("immtsf_gemm", int(transA), int(transB), M, N, K, float(alpha), _p(A), A.stride(0), _p(B), B.stride(0),
-              float(beta), _p(C), C.stride(0), _p(bias), _p(ragged), ragged_dim,
-              gemm_backend() if backend is None else backend, _stream())
+              float(beta), _p(C), C.stride(0), _p(bias), _p(ragged), ragged_dim, be, _p(ws), ws_bytes, _stream())
     if prof is not None:
         ev1.record()
         prof.append(("gemm", (M, N, K, ragged_dim), ev0, ev1))

@@ -70,11 +70,16 @@ int immtsf_zero_pad_rows(float* X, int ld, int ncols, const int32_t* m_dev, int 
  *   transB=0: B is [K,N] row-major (ldb)   transB=1: B is [N,K] row-major
  * ragged_dim: 0 none; 1: rows M bounded by *ragged (rows >= it are written
  * as 0 inside touched tiles); 2: contraction K bounded by *ragged (wgrad).
- * backend: 0 auto, 1 FFMA (CUDA cores, exact fp32), 2 tcgen05 3xTF32. */
+ * backend: 0 auto, 1 FFMA (CUDA cores, exact fp32), 2 tcgen05 3xTF32.
+ * workspace: caller-owned device scratch for the tcgen05 backend's hi/lo
+ * operand split (>= immtsf_gemm_workspace_bytes); with backend 0 and a NULL
+ * workspace the FFMA kernel is used. */
 int immtsf_gemm(int transA, int transB, int M, int N, int K, float alpha,
                 const float* A, int lda, const float* B, int ldb, float beta,
                 float* C, int ldc, const float* bias, const int32_t* ragged,
-                int ragged_dim, int backend, void* stream);
+                int ragged_dim, int backend, void* workspace, size_t workspace_bytes,
+                void* stream);
+size_t immtsf_gemm_workspace_bytes(int transA, int transB, int M, int N, int K);
 /* out[N] = beta*out + sum_m X[m, :]  (bias gradients) */
 int immtsf_colsum(const float* X, int M, int N, int ldx, float* out, float beta,
                   const int32_t* ragged, void* stream);

@@ -21,7 +21,7 @@ def _header_decls():
     src = open(HEADER).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     decls = {}
-    for m in re.finditer(r"\b(?:int|const char\*|unsigned long long)\s+(immtsf_\w+)\s*\(([^)]*)\)\s*;", src):
+    for m in re.finditer(r"\b(?:int|const char\*|unsigned long long|size_t)\s+(immtsf_\w+)\s*\(([^)]*)\)\s*;", src):
         name, args = m.group(1), m.group(2).strip()
         decls[name] = [] if args in ("", "void") else [a.strip() for a in args.split(",")]
     return decls
@@ -54,7 +54,7 @@ def test_binding_signatures_match_header():
             else:
                 base = carg.split()[-2] if len(carg.split()) >= 2 else carg
                 assert ct.__name__ == C2CT[base], (name, carg, ct.__name__)
-    assert set(decls) - set(_lib.SIGNATURES) == {"immtsf_last_error_string", "immtsf_launch_count"}
+    assert set(decls) - set(_lib.SIGNATURES) == {"immtsf_last_error_string", "immtsf_launch_count", "immtsf_gemm_workspace_bytes"}
 
 
 def test_library_contains_sm100a_code_only():
@@ -72,7 +72,7 @@ def test_arg_validation_without_a_gpu():
     from immtsf import _lib
 
     lib = _lib.load()
-    rc = lib.immtsf_gemm(0, 1, 4, 4, 4, 1.0, None, 4, None, 4, 0.0, None, 4, None, None, 0, 0, None)
+    rc = lib.immtsf_gemm(0, 1, 4, 4, 4, 1.0, None, 4, None, 4, 0.0, None, 4, None, None, 0, 0, None, 0, None)
     assert rc == -1 and b"null operand" in lib.immtsf_last_error_string()
     rc = lib.immtsf_recavg_pool_fwd(1, 6, 1, 1, 1, 0, 1, 1, 1, 2, 2, 6, 1e-5, 0, 0, 1, None, None, None, None, None)
     assert rc == -1 and b"multiple of 4" in lib.immtsf_last_error_string()

@@ -1,0 +1,89 @@
+"""tcgen05 3xTF32 GEMM backend vs an fp64 reference (and vs the FFMA backend): all four
+transposition cases, tile-unaligned sizes, leading dimensions, bias/alpha/beta, ragged bounds.
+Tolerance: 4e-6 max-norm relative (fp32-class accuracy; a single TF32 pass would be ~1e-3)."""
+import pytest
+import torch
+
+import gpu_common as G
+
+pytestmark = pytest.mark.gpu
+TOL = 4e-6
+
+
+def _ref(A, B, tA, tB):
+    return (A.double().T if tA else A.double()) @ (B.double().T if tB else B.double())
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("tA,tB", [(0, 1), (0, 0), (1, 0), (1, 1)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (128, 128, 64), (256, 256, 768), (200, 96, 72), (6144, 768, 768), (2200, 1152, 768), (768, 1536, 2216)])
+def test_gemm_tc_matches_fp64(tA, tB, M, N, K):
+    from immtsf import ops
+
+    g = torch.Generator().manual_seed(M + 3 * N + 7 * K + tA * 2 + tB)
+    A = torch.randn((K, M) if tA else (M, K), generator=g).cuda()
+    B = (torch.randn((N, K) if tB else (K, N), generator=g) * 0.3).cuda()
+    C = torch.empty(M, N, device="cuda")
+    ops.gemm(A, B, C, transA=bool(tA), transB=bool(tB), backend=ops.BACKEND_TC)
+    torch.cuda.synchronize()
+    G.assert_close("gemm_tc", C.cpu(), _ref(A.cpu(), B.cpu(), tA, tB), TOL)
+
+
+@pytest.mark.timeout(120)
+def test_gemm_tc_epilogue_and_strides():
+    from immtsf import ops
+
+    g = torch.Generator().manual_seed(9)
+    M, N, K = 300, 200, 136
+    Abig = torch.randn(M, K + 8, generator=g).cuda()
+    A = Abig[:, 4:4 + K]  # 16B-aligned column offset, lda = K+8
+    W = torch.randn(N, K, generator=g).cuda()
+    bias = torch.randn(N, generator=g).cuda()
+    Cbig = torch.randn(M, N + 4, generator=g).cuda()
+    C0 = Cbig.clone()
+    ops.gemm(A, W, Cbig[:, :N], transB=True, bias=bias, alpha=0.5, beta=2.0, backend=ops.BACKEND_TC)
+    ref = 0.5 * (A.double().cpu() @ W.double().cpu().T) + 2.0 * C0[:, :N].double().cpu() + bias.double().cpu()
+    G.assert_close("gemm_tc epilogue", Cbig[:, :N].cpu(), ref, TOL)
+    assert torch.equal(Cbig[:, N:], C0[:, N:])  # columns outside N untouched
+
+
+@pytest.mark.timeout(120)
+def test_gemm_tc_ragged():
+    from immtsf import ops
+
+    g = torch.Generator().manual_seed(10)
+    M, N, K = 640, 256, 128
+    m = 300
+    A = torch.randn(M, K, generator=g).cuda()
+    A[m:] = 0.0  # producers zero the pad rows
+    W = torch.randn(N, K, generator=g).cuda()
+    m_dev = torch.tensor([m], dtype=torch.int32, device="cuda")
+    out = torch.full((M, N), 7.0, device="cuda")
+    ops.gemm(A, W, out, transB=True, ragged=m_dev, ragged_dim=1, backend=ops.BACKEND_TC)
+    ref = A.double().cpu() @ W.double().cpu().T
+    G.assert_close("rows<m", out[:m].cpu(), ref[:m], TOL)
+    assert (out[m:384] == 0).all() and (out[384:] == 7.0).all()
+    dy = torch.randn(M, N, generator=g).cuda()
+    dy[m:] = 0.0
+    dw = torch.empty(N, K, device="cuda")
+    ops.gemm(dy, A, dw, transA=True, ragged=m_dev, ragged_dim=2, backend=ops.BACKEND_TC)
+    G.assert_close("wgrad ragged", dw.cpu(), dy[:m].double().cpu().T @ A[:m].double().cpu(), TOL)
+    # K bound of zero: output is bias/beta only
+    z = torch.zeros(1, dtype=torch.int32, device="cuda")
+    dw2 = torch.full((N, K), 3.0, device="cuda")
+    ops.gemm(dy, A, dw2, transA=True, ragged=z, ragged_dim=2, beta=1.0, backend=ops.BACKEND_TC)
+    assert (dw2 == 3.0).all()
+
+
+@pytest.mark.timeout(120)
+def test_auto_backend_uses_tc_for_big_and_ffma_for_skinny():
+    from immtsf import ops
+
+    g = torch.Generator().manual_seed(11)
+    A = torch.randn(512, 768, generator=g).cuda()
+    W = torch.randn(768, 768, generator=g).cuda()
+    Wc = torch.randn(4, 768, generator=g).cuda()
+    big = ops.linear_fwd(A, W, None)
+    skinny = ops.linear_fwd(A, Wc, None)
+    G.assert_close("auto big", big.cpu(), A.double().cpu() @ W.double().cpu().T, TOL)
+    G.assert_close("auto skinny", skinny.cpu(), A.double().cpu() @ Wc.double().cpu().T, TOL)
