@@ -23,7 +23,10 @@
 //            therefore cut in chunks of KC k-blocks (K=128): each chunk is
 //            accumulated in one of two TMEM buffers, drained with tcgen05.ld
 //            (lane == output row) and promoted into fp32 registers with
-//            round-to-nearest adds while the next chunk's MMAs run.  Then
+//            round-to-nearest adds while the next chunk's MMAs run.  The two
+//            small cross products (lo*hi, hi*lo) go to their own TMEM
+//            accumulator so that they do not add truncation steps to the
+//            large hi*hi sum (16 instead of 48 truncating adds per chunk).  Then
 //            alpha / bias / beta, ragged-row zeroing, 128-bit stores.
 // Operands may be K-major or MN-major in memory (all four transposition
 // cases): the UMMA shared-memory descriptor and instruction descriptor carry
@@ -45,7 +48,7 @@ constexpr int TILE_B = BN * BKT * 4;                  // 16 KiB
 constexpr int STAGE_BYTES = 2 * TILE_A + 2 * TILE_B;  // hi+lo of both operands
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int KC = 4;                                 // k-blocks per TMEM accumulation chunk (K = 128)
-constexpr int TMEM_COLS = 2 * BN;                     // two accumulator buffers
+constexpr int TMEM_COLS = 4 * BN;                     // two buffers x (hi*hi accumulator, cross-term accumulator)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -121,6 +124,8 @@ struct TcArgs {
   const float* bias;
   const int32_t* ragged;
   int ragged_dim;
+  float* partial;  // split-K partial tiles [splitk][M][ldp]
+  int ldp;
 };
 
 template <bool A_MN, bool B_MN>
@@ -139,7 +144,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
   const uint32_t bars = base + STAGES * STAGE_BYTES;  // full[STAGES], empty[STAGES], tfull[2], tempty[2], tmem_ptr
   const uint32_t bar_full = bars, bar_empty = bars + 8 * STAGES, bar_tfull = bars + 16 * STAGES;
   const uint32_t bar_tempty = bar_tfull + 16, tmem_slot = bar_tempty + 16;
-  const int nchunks = (nkb + KC - 1) / KC;
+  // split-K: blockIdx.z owns a contiguous range of k-blocks; partial tiles are combined with fp32 atomics
+  const int kb_per = (nkb + (int)gridDim.z - 1) / (int)gridDim.z;
+  const int z_kb0 = min(nkb, (int)blockIdx.z * kb_per), z_kb1 = min(nkb, z_kb0 + kb_per);
+  const int nchunks = (z_kb1 - z_kb0 + KC - 1) / KC;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 1 && lane == 0) {
@@ -165,8 +173,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
 
   if (warp == 0 && lane == 0) {
     // ===== TMA producer =====
-    for (int kb = 0; kb < nkb; ++kb) {
-      const int s = kb % STAGES, ph = (kb / STAGES) & 1;
+    for (int kb = z_kb0; kb < z_kb1; ++kb) {
+      const int it = kb - z_kb0;
+      const int s = it % STAGES, ph = (it / STAGES) & 1;
       mbar_wait(bar_empty + 8 * s, ph ^ 1);
       const uint32_t sa_h = base + s * STAGE_BYTES, sa_l = sa_h + TILE_A, sb_h = sa_l + TILE_A, sb_l = sb_h + TILE_B;
       const uint32_t fb = bar_full + 8 * s;
@@ -202,10 +211,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
       const int buf = c & 1;
       mbar_wait(bar_tempty + 8 * buf, ((c >> 1) & 1) ^ 1);  // epilogue has drained this TMEM buffer
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t tacc = tmem_base + (uint32_t)(buf * BN);
-      const int kb_end = min(nkb, (c + 1) * KC);
-      for (int kb = c * KC; kb < kb_end; ++kb) {
-        const int s = kb % STAGES, ph = (kb / STAGES) & 1;
+      const uint32_t tacc_big = tmem_base + (uint32_t)(buf * 2 * BN), tacc_small = tacc_big + BN;
+      const int kb0 = z_kb0 + c * KC;
+      const int kb_end = min(z_kb1, kb0 + KC);
+      for (int kb = kb0; kb < kb_end; ++kb) {
+        const int it = kb - z_kb0;
+        const int s = it % STAGES, ph = (it / STAGES) & 1;
         mbar_wait(bar_full + 8 * s, ph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t sa_h = base + s * STAGE_BYTES, sa_l = sa_h + TILE_A, sb_h = sa_l + TILE_A, sb_l = sb_h + TILE_B;
@@ -217,7 +228,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
           for (int ks = 0; ks < BKT / 8; ++ks) {
             const uint64_t ad = make_desc(sa + (A_MN ? ks * 1024 : ks * 32), A_MN);
             const uint64_t bd = make_desc(sb + (B_MN ? ks * 1024 : ks * 32), B_MN);
-            umma_tf32(tacc, ad, bd, idesc, (kb != c * KC || prod != 0 || ks != 0) ? 1u : 0u);
+            const bool first = (kb == kb0) && ks == 0 && (prod == 0 || prod == 2);
+            umma_tf32(prod == 2 ? tacc_big : tacc_small, ad, bd, idesc, first ? 0u : 1u);
           }
         }
         umma_commit(bar_empty + 8 * s);  // arrives when the MMAs that read this stage have completed
@@ -236,10 +248,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
       for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c0), v);
+        uint32_t v[32], u[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 2 * BN + c0), v);
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 2 * BN + BN + c0), u);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(v[j]);  // fp32 round-to-nearest promotion
+        for (int j = 0; j < 32; ++j)  // fp32 round-to-nearest promotion
+          acc[c0 + j] += __uint_as_float(v[j]) + __uint_as_float(u[j]);
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
@@ -247,7 +261,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
     }
     const int row = m0 + q * 32 + lane;
     const bool live = row < M;
-    if (row < g.M) {
+    if (gridDim.z > 1) {
+      // split-K: this split's partial tile goes to the workspace [z][M][ldp]; splitk_reduce_kernel sums the
+      // splits in a fixed order (deterministic, unlike atomics) and applies alpha / beta / bias
+      if (row < g.M) {
+        float* prow = g.partial + ((size_t)blockIdx.z * g.M + row) * g.ldp + n0;
+#pragma unroll
+        for (int j4 = 0; j4 < BN / 4; ++j4)
+          if (n0 + j4 * 4 < g.ldp)
+            *reinterpret_cast<float4*>(prow + j4 * 4) = make_float4(acc[j4 * 4], acc[j4 * 4 + 1], acc[j4 * 4 + 2], acc[j4 * 4 + 3]);
+      }
+    } else if (row < g.M) {
       float* crow = g.C + (size_t)row * g.ldc + n0;
 #pragma unroll
       for (int j4 = 0; j4 < BN / 4; ++j4) {
@@ -286,6 +310,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
   __syncthreads();
   if (warp == 2) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS));
+  }
+}
+
+// C = alpha * sum_z partial[z] + beta*C + bias for rows < M_eff; zeros for ragged pad rows inside touched tiles
+__global__ void splitk_reduce_kernel(float* __restrict__ C, int ldc, int M, int N, float alpha, float beta,
+                                     const float* __restrict__ bias, const float* __restrict__ partial, int ldp, int splitk,
+                                     const int32_t* __restrict__ ragged, int ragged_dim) {
+  int Meff = M;
+  if (ragged_dim == 1) Meff = ragged_rows(M, ragged);
+  int Mtouch = (Meff + BM - 1) / BM * BM;
+  if (Mtouch > M) Mtouch = M;
+  const int n4 = ldp >> 2;
+  const size_t total = (size_t)Mtouch * n4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / n4), c = (int)(i % n4) * 4;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < Meff)
+      for (int z = 0; z < splitk; ++z) {
+        const float4 p = *reinterpret_cast<const float4*>(partial + ((size_t)z * M + r) * ldp + c);
+        s.x += p.x; s.y += p.y; s.z += p.z; s.w += p.w;
+      }
+    const float v[4] = {s.x, s.y, s.z, s.w};
+    float* out = C + (size_t)r * ldc + c;
+    for (int e = 0; e < 4 && c + e < N; ++e) {
+      float x = 0.f;
+      if (r < Meff) {
+        x = alpha * v[e];
+        if (beta != 0.f) x = fmaf(beta, out[e], x);
+        if (bias != nullptr) x += bias[c + e];
+      }
+      out[e] = x;
+    }
   }
 }
 
@@ -356,13 +412,28 @@ int make_map(CUtensorMap* m, const float* ptr, int rows, int cols, int ld, int b
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// split-K when the output has too few tiles to occupy the 148 SMs (weight gradients: M, N = d; K = rows)
+inline int choose_splitk(int M, int N, int K) {
+  const int tiles = ceil_div(N, BN) * ceil_div(M, BM), nkb = ceil_div(K, BKT);
+  int splitk = 1;
+  if (tiles * 2 <= 148 && nkb >= 16) {
+    splitk = 148 / tiles;
+    if (splitk > nkb / 8) splitk = nkb / 8;
+    if (splitk > 16) splitk = 16;
+    if (splitk < 1) splitk = 1;
+  }
+  return splitk;
+}
+
 }  // namespace
 
 // workspace: A_hi | A_lo | B_hi | B_lo, each dense with ld rounded up to 4 floats, 256 B aligned
 size_t immtsf_gemm_tc_workspace(int transA, int transB, int M, int N, int K) {
   const size_t ra = transA ? K : M, ca = transA ? M : K, rb = transB ? N : K, cb = transB ? K : N;
   const size_t a = align_up(ra * align_up(ca, 4) * 4, 256), b = align_up(rb * align_up(cb, 4) * 4, 256);
-  return 2 * a + 2 * b + 256;
+  const int sk = choose_splitk(M, N, K);
+  const size_t p = sk > 1 ? align_up((size_t)sk * M * align_up(N, 4) * 4, 256) : 0;
+  return 2 * a + 2 * b + p + 256;
 }
 
 // forced != 0: only hard requirements (alignment, driver entry point); else also the size heuristic
@@ -417,6 +488,13 @@ int immtsf_gemm_tc(int transA, int transB, int M, int N, int K, float alpha, con
   g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K; g.alpha = alpha; g.beta = beta; g.bias = bias;
   g.ragged = ragged; g.ragged_dim = ragged_dim;
   dim3 grid(ceil_div(N, BN), ceil_div(M, BM));
+  const int splitk = choose_splitk(M, N, K);
+  g.partial = nullptr; g.ldp = 0;
+  if (splitk > 1) {
+    grid.z = splitk;
+    g.partial = (float*)(w + 2 * abytes + 2 * bbytes);
+    g.ldp = (int)align_up(N, 4);
+  }
   static bool attr_done = false;
   if (!attr_done) {
     cudaFuncSetAttribute(gemm_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
@@ -431,5 +509,11 @@ int immtsf_gemm_tc(int transA, int transB, int M, int N, int K, float alpha, con
   else if (transA && !transB) gemm_tc_kernel<true, true><<<grid, 256, SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, g);
   else gemm_tc_kernel<true, false><<<grid, 256, SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, g);
   IMMTSF_CHECK_LAUNCH("gemm_tc");
+  if (splitk > 1) {
+    const size_t tot = (size_t)M * (g.ldp / 4);
+    int rg = (int)((tot + 255) / 256); if (rg > 148 * 8) rg = 148 * 8;
+    splitk_reduce_kernel<<<rg, 256, 0, st>>>(C, ldc, M, N, alpha, beta, bias, g.partial, g.ldp, splitk, ragged, ragged_dim);
+    IMMTSF_CHECK_LAUNCH("splitk_reduce");
+  }
   return IMMTSF_OK;
 }

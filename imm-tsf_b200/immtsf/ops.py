@@ -149,7 +149,7 @@ def gemm(A, B, C, transA=False, transB=False, bias=None, alpha=1.0, beta=0.0, ra
     be = gemm_backend() if backend is None else backend
     ws, ws_bytes = None, 0
     if be == BACKEND_TC or (be == BACKEND_AUTO and M >= 64 and N >= 32 and K >= 32):
-        ws_bytes = 8 * (M * (K + 4) + (K + 4) * (N + 4)) + 2048  # >= immtsf_gemm_workspace_bytes
+        ws_bytes = _lib.load().immtsf_gemm_workspace_bytes(int(transA), int(transB), M, N, K)
         ws = _workspace(C.device, ws_bytes)
         ws_bytes = ws.numel()
     _lib.call("immtsf_gemm", int(transA), int(transB), M, N, K, float(alpha), _p(A), A.stride(0), _p(B), B.stride(0),
