@@ -19,6 +19,10 @@ int immtsf_gemm_tc(int transA, int transB, int M, int N, int K, float alpha, con
 size_t immtsf_gemm_tc_workspace(int transA, int transB, int M, int N, int K);
 int immtsf_gemm_tc_eligible(int forced, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
                             const float* C, int ldc);
+int immtsf_gemm_skinny(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda, const float* B,
+                       int ldb, float beta, float* C, int ldc, const float* bias, const int32_t* ragged, int ragged_dim,
+                       void* workspace, size_t workspace_bytes, cudaStream_t st);
+size_t immtsf_gemm_skinny_workspace(int M, int N, int K);
 
 struct GemmArgs {
   int M, N, K;
@@ -254,6 +258,11 @@ extern "C" int immtsf_gemm(int transA, int transB, int M, int N, int K, float al
   IMMTSF_REQUIRE(backend >= 0 && backend <= 2, "gemm: backend must be 0 (auto), 1 (ffma) or 2 (tcgen05)");
   cudaStream_t st = (cudaStream_t)stream;
 
+  if (backend == 0) {  // skinny shapes (a dimension <= 32): dedicated streaming kernels
+    const int rc = immtsf_gemm_skinny(transA, transB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, ragged, ragged_dim,
+                                      workspace, workspace_bytes, st);
+    if (rc <= 0) return rc;
+  }
   if (backend != 1) {
     const int ok = immtsf_gemm_tc_eligible(backend == 2, M, N, K, A, lda, B, ldb, C, ldc);
     if (ok && (backend == 2 || workspace != nullptr))
@@ -281,34 +290,6 @@ extern "C" int immtsf_gemm(int transA, int transB, int M, int N, int K, float al
 }
 
 extern "C" size_t immtsf_gemm_workspace_bytes(int transA, int transB, int M, int N, int K) {
-  return immtsf_gemm_tc_workspace(transA, transB, M, N, K);
-}
-
-// ------------------------------------------------------------------ colsum
-// out[n] = beta*out[n] + sum_m X[m,n]; grid.x over column tiles of 32, each CTA
-// walks all rows with 32x8 threads (coalesced along n) then reduces in smem.
-__global__ void colsum_kernel(const float* __restrict__ X, int M, int N, int ldx, float* __restrict__ out, float beta,
-                              const int32_t* __restrict__ ragged) {
-  __shared__ float red[8][33];
-  const int m_eff = ragged_rows(M, ragged);
-  const int n = blockIdx.x * 32 + threadIdx.x;
-  float s = 0.f;
-  if (n < N)
-    for (int m = threadIdx.y; m < m_eff; m += 8) s += X[(size_t)m * ldx + n];
-  red[threadIdx.y][threadIdx.x] = s;
-  __syncthreads();
-  if (threadIdx.y == 0 && n < N) {
-    float t = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
-    out[n] = (beta != 0.f ? beta * out[n] : 0.f) + t;
-  }
-}
-extern "C" int immtsf_colsum(const float* X, int M, int N, int ldx, float* out, float beta, const int32_t* ragged,
-                             void* stream) {
-  if (N == 0) return IMMTSF_OK;
-  IMMTSF_REQUIRE(X && out, "colsum: null pointer");
-  colsum_kernel<<<ceil_div(N, 32), dim3(32, 8), 0, (cudaStream_t)stream>>>(X, M, N, ldx, out, beta, ragged);
-  IMMTSF_CHECK_LAUNCH("colsum");
-  return IMMTSF_OK;
+  const size_t a = immtsf_gemm_tc_workspace(transA, transB, M, N, K), b = immtsf_gemm_skinny_workspace(M, N, K);
+  return a > b ? a : b;
 }

@@ -38,6 +38,7 @@
 // cycles for 2*128*128*32 useful FLOP -> 3xTF32 ceiling = 1/3 of the TF32
 // peak (= 1/6 of the bf16 peak used as roofline.peak in bench.py).
 #include <cuda.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace {
@@ -479,8 +480,14 @@ int immtsf_gemm_tc(int transA, int transB, int M, int N, int K, float alpha, con
   CUtensorMap mAh, mAl, mBh, mBl;
   // K-major operand [rows=MN][cols=K]: box 32 x 128 ; MN-major operand [rows=K][cols=MN]: box 32 x 32
   const int boxA = transA ? 32 : BM, boxB = transB ? BN : 32;
-  if (make_map(&mAh, Ah, ra, ca, lda2, boxA, transA != 0) || make_map(&mAl, Al, ra, ca, lda2, boxA, transA != 0) ||
-      make_map(&mBh, Bh, rb, cb, ldb2, boxB, transB == 0) || make_map(&mBl, Bl, rb, cb, ldb2, boxB, transB == 0)) {
+  // experiment (IMMTSF_TC_RAWHI=1): feed the unsplit fp32 operand as the "hi" part.  If the tensor core
+  // truncates fp32 inputs to TF32 itself, results are bit-identical and the hi copies are unnecessary.
+  static int rawhi = -1;
+  if (rawhi < 0) { const char* e = getenv("IMMTSF_TC_RAWHI"); rawhi = (e && e[0] == '1') ? 1 : 0; }
+  const float* Ahp = rawhi ? A : Ah; const int ldah = rawhi ? lda : lda2;
+  const float* Bhp = rawhi ? B : Bh; const int ldbh = rawhi ? ldb : ldb2;
+  if (make_map(&mAh, Ahp, ra, ca, ldah, boxA, transA != 0) || make_map(&mAl, Al, ra, ca, lda2, boxA, transA != 0) ||
+      make_map(&mBh, Bhp, rb, cb, ldbh, boxB, transB == 0) || make_map(&mBl, Bl, rb, cb, ldb2, boxB, transB == 0)) {
     immtsf_set_error("gemm_tc: cuTensorMapEncodeTiled failed");
     return IMMTSF_ERR_LAUNCH;
   }

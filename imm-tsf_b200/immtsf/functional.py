@@ -142,8 +142,18 @@ class GRAddFn(torch.autograd.Function):
         B, T, C = Y.shape
         d = E.shape[2]
         Yc = Y.contiguous()
-        X = torch.cat([Yc, E], dim=-1).view(B * T, C + d)  # MMF_GR_Add.py:43
-        Wcat = torch.cat([W_ih, W_g], dim=0)  # [4C, C+d]: GRU input map and gate net read x once
+        # x = [Y ; E] (MMF_GR_Add.py:43) and [W_ih ; W_g] (GRU input map and gate net read x once), both with the
+        # row length C+d padded to a multiple of 4 floats so that every row is 16-byte aligned
+        Kp = ops.round_up(C + d, 4)
+        X = torch.empty(B * T, Kp, dtype=_f32, device=Y.device)
+        X[:, :C].copy_(Yc.view(B * T, C))
+        X[:, C:C + d].copy_(E.reshape(B * T, d))
+        Wcat = torch.empty(4 * C, Kp, dtype=_f32, device=Y.device)
+        Wcat[:3 * C, :C + d].copy_(W_ih)
+        Wcat[3 * C:, :C + d].copy_(W_g)
+        if Kp > C + d:
+            X[:, C + d:].zero_()
+            Wcat[:, C + d:].zero_()
         bcat = torch.cat([b_ih, b_g], dim=0)
         G4 = ops.linear_fwd(X, Wcat, bcat)
         W_hh_c, b_hh_c, W_r_c = W_hh.contiguous(), b_hh.contiguous(), W_r.contiguous()
@@ -173,9 +183,9 @@ class GRAddFn(torch.autograd.Function):
         dY = dY_out.view(B * T, C).clone()
         ops.gemm(dG4, Wcat[:, :C], dY, beta=1.0)
         dE = torch.empty(B * T, d, dtype=_f32, device=X.device)
-        ops.gemm(dG4, Wcat[:, C:], dE)
-        return (dY.view(B, T, C), dE.view(B, T, d), None, None, None, None, None, dWcat[: 3 * C], dW_hh, dbcat[: 3 * C], db_hh,
-                dW_r, db_r, dWcat[3 * C:], dbcat[3 * C:], dgamma, dbeta)
+        ops.gemm(dG4, Wcat[:, C:C + d], dE)
+        return (dY.view(B, T, C), dE.view(B, T, d), None, None, None, None, None, dWcat[: 3 * C, :C + d], dW_hh, dbcat[: 3 * C],
+                db_hh, dW_r, db_r, dWcat[3 * C:, :C + d], dbcat[3 * C:], dgamma, dbeta)
 
 
 # ============================================================== MMF_XAttn_Add

@@ -148,7 +148,7 @@ def gemm(A, B, C, transA=False, transB=False, bias=None, alpha=1.0, beta=0.0, ra
         ev0.record()
     be = gemm_backend() if backend is None else backend
     ws, ws_bytes = None, 0
-    if be == BACKEND_TC or (be == BACKEND_AUTO and M >= 64 and N >= 32 and K >= 32):
+    if be != BACKEND_FFMA:
         ws_bytes = _lib.load().immtsf_gemm_workspace_bytes(int(transA), int(transB), M, N, K)
         ws = _workspace(C.device, ws_bytes)
         ws_bytes = ws.numel()
@@ -185,7 +185,9 @@ def colsum(X, out=None, ragged=None, beta=0.0):
     _mat(X, "X")
     if out is None:
         out = torch.empty(X.shape[1], dtype=torch.float32, device=X.device)
-    _lib.call("immtsf_colsum", _p(X), X.shape[0], X.shape[1], X.stride(0), _p(out), float(beta), _p(ragged), _stream())
+    ws = _workspace(X.device, 16 << 20)
+    _lib.call("immtsf_colsum", _p(X), X.shape[0], X.shape[1], X.stride(0), _p(out), float(beta), _p(ragged), _p(ws), ws.numel(),
+              _stream())
     return out
 
 

@@ -71,18 +71,25 @@ int immtsf_zero_pad_rows(float* X, int ld, int ncols, const int32_t* m_dev, int 
  * ragged_dim: 0 none; 1: rows M bounded by *ragged (rows >= it are written
  * as 0 inside touched tiles); 2: contraction K bounded by *ragged (wgrad).
  * backend: 0 auto, 1 FFMA (CUDA cores, exact fp32), 2 tcgen05 3xTF32.
+ * With backend 0, shapes with a dimension <= 32 (the channel count C) go to
+ * streaming kernels (csrc/gemm_skinny.cu: exact fp32, one coalesced pass over
+ * the wide operand, deterministic row-split reduction).
  * workspace: caller-owned device scratch for the tcgen05 backend's hi/lo
- * operand split (>= immtsf_gemm_workspace_bytes); with backend 0 and a NULL
- * workspace the FFMA kernel is used. */
+ * operand split and the row-split partial sums (>=
+ * immtsf_gemm_workspace_bytes); with backend 0 and a NULL workspace the FFMA
+ * kernel is used. */
 int immtsf_gemm(int transA, int transB, int M, int N, int K, float alpha,
                 const float* A, int lda, const float* B, int ldb, float beta,
                 float* C, int ldc, const float* bias, const int32_t* ragged,
                 int ragged_dim, int backend, void* workspace, size_t workspace_bytes,
                 void* stream);
 size_t immtsf_gemm_workspace_bytes(int transA, int transB, int M, int N, int K);
-/* out[N] = beta*out + sum_m X[m, :]  (bias gradients) */
+/* out[N] = beta*out + sum_m X[m, :]  (bias gradients: the `.sum(0)` autograd
+ * emits for every nn.Linear bias on the path).  Rows bounded by *ragged when
+ * given.  workspace (>= immtsf_gemm_workspace_bytes(0,0,1,N,M)) enables the
+ * row-split two-pass kernel; without it a single-pass kernel is used. */
 int immtsf_colsum(const float* X, int M, int N, int ldx, float* out, float beta,
-                  const int32_t* ragged, void* stream);
+                  const int32_t* ragged, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- K2: TTF_RecAvg pooling (TTF_RecAvg.py:94-106): recency weights,
  * weighted mean over each ragged segment, LayerNorm, dropout ------------- */

@@ -166,3 +166,30 @@ def test_philox_mirror_matches_device_code(tmp_path):
         got = P.philox4x32_10(np.array([cc & 0xFFFFFFFF], np.uint32), np.array([cc >> 32], np.uint32),
                               np.array([3], np.uint32), np.array([0], np.uint32), seed & 0xFFFFFFFF, seed >> 32)
         assert [int(x[0]) for x in got] == w
+
+
+def test_launcher_swaps_fusions_under_an_unmodified_script(tmp_path):
+    """tools/run_with_immtsf.py: a script that lives next to its own `fusions` package (as the reference's
+    main.py does) must get the B200 drop-in from the same import statements (main.py:39-40)."""
+    import subprocess
+
+    decoy = tmp_path / "fusions"
+    decoy.mkdir()
+    (decoy / "__init__.py").write_text("")
+    (decoy / "FusionModel.py").write_text("class FusionModel: pass\n")
+    (decoy / "load_llm.py").write_text("def get_context_window_size(*a, **k): return -1\n")
+    (tmp_path / "main.py").write_text(
+        "import sys\n"
+        "from fusions.FusionModel import FusionModel\n"
+        "from fusions.load_llm import get_context_window_size\n"
+        "import fusions.FusionModel as M\n"
+        "print('FILE', M.__file__)\n"
+        "print('CTX', get_context_window_size('GPT2'))\n"
+        "print('ARGS', sys.argv[1:])\n"
+        "print('REG', sorted(M._TTF_CLASSES), sorted(M._MMF_CLASSES))\n")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "run_with_immtsf.py"), str(tmp_path / "main.py"), "--x", "1"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert os.path.join("imm-tsf_b200", "fusions", "FusionModel.py") in r.stdout
+    assert "CTX 1024" in r.stdout and "ARGS ['--x', '1']" in r.stdout
+    assert "['TTF_RecAvg', 'TTF_T2V_XAttn'] ['MMF_GR_Add', 'MMF_XAttn_Add']" in r.stdout
