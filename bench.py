@@ -53,6 +53,11 @@ WORKLOADS = {
                  name="cfg3: T2V_XAttn+GR_Add, B256 N<=64 T28 d_model4096->768 C5 (BASELINE.json configs[2])"),
 }
 DROPOUT = 0.1
+# dram__bytes_read.sum + dram__bytes_write.sum of one gemm_tc_kernel launch (M6144 N768 K768) from the ncu --set full
+# capture in profiles/r1_ncu_gemm_tc_full_summary.csv; algorithmic operand bytes of that launch: 42.5 MB (the
+# 18.9 MB output stays in the 126 MB L2)
+TRAFFIC_NCU = 43.4e6
+TRAFFIC_NOTE = "bytes per launch, M6144 N768 K768, profiles/r1_ncu_gemm_tc_full_summary.csv (algorithmic operand bytes 42.5e6)"
 METRIC = "fused TTF+MMF fwd+bwd throughput"
 UNIT = "samples/s"
 
@@ -223,7 +228,9 @@ def run_gpu_arm(args, w):
     os.environ.setdefault("IMMTSF_NAN_CHECK", "0")  # the guard's single host sync is measured separately in e2e_checked
 
     cfg = dict(ttf=w["ttf"], mmf=w["mmf"], d_txt=w["d_txt"], C=w["C"], H=w["H"], kappa=w["kappa"])
-    fm = G.build_model(cfg, w["d_model"], dropout=DROPOUT, seed=1)  # same init on every rank
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):  # FusionModel prints its module names like the reference does
+        fm = G.build_model(cfg, w["d_model"], dropout=DROPOUT, seed=1)  # same init on every rank
     fm.train()
     params = [p for p in fm.parameters()]
     notes, tau, t_hat, Y, _ = make_batch(w, 1234 + rank)
@@ -244,17 +251,22 @@ def run_gpu_arm(args, w):
             dp.allreduce_grads(params)
         return loss
 
-    def timed(n, resident):
+    def timed(n, resident, graphed=None):
+        """n steps, each bracketed by its own CUDA-event pair (the 256 MiB L2 flush sits between the pairs)."""
         total_ms = 0.0
         for _ in range(n):
             flush.fill_(1.0)  # L2 flush, outside the timed events
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            if resident:
-                loss = step(d_in)
+            src = d_in if resident else h_in
+            if graphed is not None:
+                loss = graphed(*src)  # copies into the static buffers (H2D when src is pinned host memory) + one replay
+                if world > 1:
+                    dp.allreduce_grads(params)
             else:
-                inp = [t.to(dev, non_blocking=True) for t in h_in]
+                inp = src if resident else [t.to(dev, non_blocking=True) for t in src]
                 loss = step(inp)
+            if not resident:
                 loss_host.copy_(loss.detach(), non_blocking=True)
             e1.record()
             e1.synchronize()
@@ -275,46 +287,50 @@ def run_gpu_arm(args, w):
         return float(t.item())
 
     W, K = max(args.warmup, 3), args.steps
+    # ---- eager path (one Python call per kernel launch)
     timed(W, True)
+    barrier()
+    l0 = _lib.launch_count()
+    ms_eager = max_over_ranks(timed(K, True))
+    launches_per_step = (_lib.launch_count() - l0) // max(K, 1)
+    barrier()
+    # ---- public API for a fixed-shape training loop: the whole step captured in a CUDA graph (runtime.GraphedStep)
+    graphed = None
+    if not args.eager:
+        for p in params:
+            p.grad = None
+        graphed = runtime.GraphedStep(fm, example=d_in, warmup=2)
+    timed(W, True, graphed)
     barrier()
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    l0 = _lib.launch_count()
-    ms_res = timed(K, True)
-    launches = _lib.launch_count() - l0
+    ms_res = timed(K, True, graphed)
+    launches = launches_per_step * K
     barrier()
     ms_res = max_over_ranks(ms_res)
-    timed(2, False)
+    timed(2, False, graphed)
     barrier()
-    ms_e2e = max_over_ranks(timed(K, False))
+    ms_e2e = max_over_ranks(timed(K, False, graphed))
     barrier()
     clk = clocks.stop() if rank == 0 else None
 
-    # instrumented pass: per-launch CUDA events around every dense projection
-    ops.PROFILE = []
+    # instrumented pass: a CUDA-event pair around every gemm_tc_kernel launch, recorded inside the library on the
+    # launch stream (immtsf_profile_begin/end).  Ragged launches are issued over M_alloc rows but only sumN are
+    # live: count live work only.
     nprof = min(K, 5)
-    timed(nprof, True)
-    torch.cuda.synchronize()
-    gemm_ms = sum(e0.elapsed_time(e1) for (_, _, e0, e1) in ops.PROFILE)
-    gemm_flops = sum(2.0 * m * n * k for (_, (m, n, k, rd), _, _) in ops.PROFILE)
-    n_gemm = len(ops.PROFILE)
-    ops.PROFILE = None
-    # ragged GEMMs are issued over M_alloc rows but only sumN are live: count live work only
-    # (ragged launches are the ones whose M or K equals M_alloc)
-    M_alloc = max((w["B"] * w["N"] + 127) // 128 * 128, 128)
-    live = 0.0
-    ops.PROFILE = []
-    timed(1, True)
-    torch.cuda.synchronize()
-    for (_, (m, n, k, rd), _, _) in ops.PROFILE:
+    with _lib.profile_gemm_tc() as recs:
+        timed(nprof, True)
+        torch.cuda.synchronize()
+    gemm_ms = sum(r[4] for r in recs)
+    gemm_flops_live = 0.0
+    for (m, n, k, rd, _ms) in recs:
         if rd == 1:
             m = min(m, sumN)
         elif rd == 2:
             k = min(k, sumN)
-        live += 2.0 * m * n * k
-    ops.PROFILE = None
-    gemm_flops_live = live * nprof
+        gemm_flops_live += 2.0 * m * n * k
+    n_gemm = len(recs)
 
     if rank != 0:
         if world > 1:
@@ -342,16 +358,22 @@ def run_gpu_arm(args, w):
                    "per_gpu_batch": w["B"], "global_batch": w["B"] * world, "sum_notes_rank0": sumN,
                    "parallelism": f"dp{world}" if world > 1 else "single",
                    "l2": "256 MiB flush write before every timed step", "gemm_backend": os.environ.get("IMMTSF_GEMM", "auto"),
+                   "launch": "eager (one host call per kernel)" if args.eager else "runtime.GraphedStep (whole step replayed as one CUDA graph)",
+                   "eager_samples_per_s": samples / (ms_eager / 1e3), "kernels_per_step": launches_per_step,
                    "algorithmic_gflop_fwd_bwd": fb_f / 1e9},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / K},
         "gpu_launches": launches,
         "clocks": clk,
-        "roofline": {"bound": "tensor", "kernel": "immtsf_gemm (dense projections, %d launches/step)" % (n_gemm // max(nprof, 1)),
+        "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 3xTF32 dense projections, %d launches/step)" % (n_gemm // max(nprof, 1)),
                      "achieved": achieved, "peak": peaks["tensor"], "unit": "TFLOP/s", "frac": achieved / peaks["tensor"],
-                     "traffic": None, "peak_source": peaks["src"],
-                     "gemm_share_of_step": (gemm_ms / nprof) / (ms_res / K) if ms_res > 0 else None,
-                     "step_tflops_algorithmic": fb_f / (ms_res / K / 1e3) / 1e12},
+                     "traffic": TRAFFIC_NCU, "traffic_note": TRAFFIC_NOTE, "peak_source": peaks["src"],
+                     "note": "achieved = fp32-exact (algorithmic) FLOPs of the live rows / summed per-launch CUDA-event time; every "
+                             "product costs 3 TF32 MMAs, so the ceiling of this kernel is peak/6 (TF32 = bf16/2, 3 passes)",
+                     "frac_of_3xtf32_ceiling": achieved / (peaks["tensor"] / 6.0),
+                     "tensor_pipe_frac_executed": 3.0 * achieved / (peaks["tensor"] / 2.0),
+                     "kernel_share_of_step": (gemm_ms / nprof) / (ms_res / K) if ms_res > 0 else None,
+                     "step_tflops_algorithmic_reference_schedule": fb_f / (ms_res / K / 1e3) / 1e12},
         "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)
@@ -367,6 +389,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eager", action="store_true", help="time the eager path only (no CUDA-graph replay)")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     if args.impl == "reference":

@@ -97,6 +97,21 @@ __device__ __forceinline__ float dropout_scale(uint64_t seed, uint32_t site, uin
   return dropout_word(seed, site, idx) >= thr ? inv_keep : 0.f;
 }
 
+// Dropout seed as the kernels see it: a host value plus an optional device-resident offset.  The offset lets a
+// CUDA graph that captured one training step draw fresh masks on every replay (immtsf_set_seed_offset_ptr).
+struct SeedArg {
+  uint64_t base;
+  const uint64_t* dev;
+};
+__device__ __forceinline__ uint64_t resolve_seed(const SeedArg& s) { return s.dev != nullptr ? s.base + *s.dev : s.base; }
+const uint64_t* immtsf_seed_dev();
+static inline SeedArg make_seed(uint64_t v) {
+  SeedArg s;
+  s.base = v;
+  s.dev = immtsf_seed_dev();
+  return s;
+}
+
 #define IMMTSF_SITE_TTF_DROPOUT 1u
 #define IMMTSF_SITE_TTF_ATTN 2u
 #define IMMTSF_SITE_MMF_DROPOUT 3u

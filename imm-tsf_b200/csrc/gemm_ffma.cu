@@ -13,9 +13,10 @@
 #include "common.cuh"
 #include "../../include/immtsf.h"
 
-int immtsf_gemm_tc(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda,
-                   const float* B, int ldb, float beta, float* C, int ldc, const float* bias,
-                   const int32_t* ragged, int ragged_dim, void* workspace, size_t workspace_bytes, cudaStream_t st);
+int immtsf_gemm_tc(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda, const float* A_lo,
+                   int lda_lo, const float* B, int ldb, const float* B_lo, int ldb_lo, float beta, float* C, int ldc,
+                   const float* bias, const int32_t* ragged, int ragged_dim, void* workspace, size_t workspace_bytes,
+                   cudaStream_t st);
 size_t immtsf_gemm_tc_workspace(int transA, int transB, int M, int N, int K);
 int immtsf_gemm_tc_eligible(int forced, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
                             const float* C, int ldc);
@@ -245,10 +246,26 @@ static void launch_ffma(const GemmArgs& g, int transA, int transB, cudaStream_t 
 
 static inline int aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
-extern "C" int immtsf_gemm(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda,
-                           const float* B, int ldb, float beta, float* C, int ldc, const float* bias,
-                           const int32_t* ragged, int ragged_dim, int backend, void* workspace,
-                           size_t workspace_bytes, void* stream) {
+// which kernel family immtsf_gemm picks: 1 FFMA, 2 tcgen05 3xTF32, 3 skinny streaming kernels
+static int gemm_plan(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+                     const float* C, int ldc, int backend, int have_workspace) {
+  if (backend == 1) return 1;
+  if (backend == 0 && (M <= 32 || N <= 32 || K <= 16)) return 3;  // may still fall through to FFMA inside
+  const int ok = immtsf_gemm_tc_eligible(backend == 2, M, N, K, A, lda, B, ldb, C, ldc);
+  if (ok && (backend == 2 || have_workspace)) return 2;
+  return backend == 2 ? -1 : 1;
+}
+
+extern "C" int immtsf_gemm_plan(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B,
+                                int ldb, const float* C, int ldc, int backend) {
+  if (M <= 0 || N <= 0 || K <= 0) return 1;
+  return gemm_plan(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, backend, 1);
+}
+
+extern "C" int immtsf_gemm_ex(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda,
+                              const float* A_lo, int lda_lo, const float* B, int ldb, const float* B_lo, int ldb_lo,
+                              float beta, float* C, int ldc, const float* bias, const int32_t* ragged, int ragged_dim,
+                              int backend, void* workspace, size_t workspace_bytes, void* stream) {
   IMMTSF_REQUIRE(M >= 0 && N >= 0 && K >= 0, "gemm: negative dimension");
   if (M == 0 || N == 0) return IMMTSF_OK;
   IMMTSF_REQUIRE(A && B && C, "gemm: null operand");
@@ -258,20 +275,18 @@ extern "C" int immtsf_gemm(int transA, int transB, int M, int N, int K, float al
   IMMTSF_REQUIRE(backend >= 0 && backend <= 2, "gemm: backend must be 0 (auto), 1 (ffma) or 2 (tcgen05)");
   cudaStream_t st = (cudaStream_t)stream;
 
-  if (backend == 0) {  // skinny shapes (a dimension <= 32): dedicated streaming kernels
+  const int plan = gemm_plan(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, backend, workspace != nullptr);
+  if (plan == 3) {  // skinny shapes (a dimension <= 32): dedicated streaming kernels
     const int rc = immtsf_gemm_skinny(transA, transB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, ragged, ragged_dim,
                                       workspace, workspace_bytes, st);
     if (rc <= 0) return rc;
   }
-  if (backend != 1) {
-    const int ok = immtsf_gemm_tc_eligible(backend == 2, M, N, K, A, lda, B, ldb, C, ldc);
-    if (ok && (backend == 2 || workspace != nullptr))
-      return immtsf_gemm_tc(transA, transB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, ragged, ragged_dim, workspace,
-                            workspace_bytes, st);
-    if (backend == 2) {
-      immtsf_set_error("gemm: tcgen05 backend requested but shape/alignment is not eligible");
-      return IMMTSF_ERR_UNSUPPORTED;
-    }
+  if (plan == 2)
+    return immtsf_gemm_tc(transA, transB, M, N, K, alpha, A, lda, A_lo, lda_lo, B, ldb, B_lo, ldb_lo, beta, C, ldc, bias, ragged,
+                          ragged_dim, workspace, workspace_bytes, st);
+  if (plan < 0) {
+    immtsf_set_error("gemm: tcgen05 backend requested but shape/alignment is not eligible");
+    return IMMTSF_ERR_UNSUPPORTED;
   }
 
   GemmArgs g;
@@ -287,6 +302,14 @@ extern "C" int immtsf_gemm(int transA, int transB, int M, int N, int K, float al
   else launch_ffma<64, 64, 4, 4>(g, transA, transB, st);
   IMMTSF_CHECK_LAUNCH("gemm_ffma");
   return IMMTSF_OK;
+}
+
+extern "C" int immtsf_gemm(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda,
+                           const float* B, int ldb, float beta, float* C, int ldc, const float* bias,
+                           const int32_t* ragged, int ragged_dim, int backend, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+  return immtsf_gemm_ex(transA, transB, M, N, K, alpha, A, lda, nullptr, 0, B, ldb, nullptr, 0, beta, C, ldc, bias, ragged,
+                        ragged_dim, backend, workspace, workspace_bytes, stream);
 }
 
 extern "C" size_t immtsf_gemm_workspace_bytes(int transA, int transB, int M, int N, int K) {

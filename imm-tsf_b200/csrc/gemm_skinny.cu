@@ -169,20 +169,32 @@ __global__ void __launch_bounds__(256) gemm_tallt_partial_kernel(const float* __
   for (int s = 0; s < SMAX; ++s) acc[s] = make_float4(0.f, 0.f, 0.f, 0.f);
   if (n < N) {
     const bool full = n + 3 < N;
-#pragma unroll 2
-    for (int k = k0 + w; k < k1; k += TT_WARPS) {
-      const float* wp = W + (long)k * w_rs + n;
-      float4 v;
-      if (full) v = __ldg(reinterpret_cast<const float4*>(wp));
-      else {
-        v.x = wp[0]; v.y = n + 1 < N ? wp[1] : 0.f; v.z = n + 2 < N ? wp[2] : 0.f; v.w = 0.f;
+    for (int kb = k0 + w; kb < k1; kb += 4 * TT_WARPS) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {  // 4 independent rows in flight
+        const int k = kb + u * TT_WARPS;
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k < k1) {
+          const float* wp = W + (long)k * w_rs + n;
+          if (full) v[u] = __ldg(reinterpret_cast<const float4*>(wp));
+          else {
+            v[u].x = wp[0]; v[u].y = n + 1 < N ? wp[1] : 0.f; v[u].z = n + 2 < N ? wp[2] : 0.f;
+          }
+        }
       }
 #pragma unroll
-      for (int s = 0; s < SMAX; ++s) {
-        if (s < Sn) {
-          const float c = S != nullptr ? __ldg(S + (long)k * s_ks + s * s_ss) : 1.f;
-          acc[s].x = fmaf(c, v.x, acc[s].x); acc[s].y = fmaf(c, v.y, acc[s].y);
-          acc[s].z = fmaf(c, v.z, acc[s].z); acc[s].w = fmaf(c, v.w, acc[s].w);
+      for (int u = 0; u < 4; ++u) {
+        const int k = kb + u * TT_WARPS;
+        if (k < k1) {
+#pragma unroll
+          for (int s = 0; s < SMAX; ++s) {
+            if (s < Sn) {
+              const float c = S != nullptr ? __ldg(S + (long)k * s_ks + s * s_ss) : 1.f;
+              acc[s].x = fmaf(c, v[u].x, acc[s].x); acc[s].y = fmaf(c, v[u].y, acc[s].y);
+              acc[s].z = fmaf(c, v[u].z, acc[s].z); acc[s].w = fmaf(c, v[u].w, acc[s].w);
+            }
+          }
         }
       }
     }
@@ -202,31 +214,46 @@ __global__ void __launch_bounds__(256) gemm_tallt_partial_kernel(const float* __
   }
 }
 
-// C(s,n) = alpha * sum_split partial[split][s][n] + beta*C + bias
-__global__ void gemm_tallt_reduce_kernel(const float* __restrict__ partial, int nsplit, int Sn, int N, int ldp, float alpha,
-                                         float beta, const float* __restrict__ bias, int bias_on_s, float* __restrict__ C,
-                                         long c_ss, long c_ns) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= Sn * N) return;
-  const int s = i / N, n = i % N;
+// C(s,n) = alpha * sum_split partial[split][s][n] + beta*C + bias.  Block = 32 outputs x 8 split lanes: the
+// splits of one output are summed by 8 threads in a fixed interleaved order, then across the 8 in shared memory.
+__global__ void __launch_bounds__(256) gemm_tallt_reduce_kernel(const float* __restrict__ partial, int nsplit, int Sn, int N,
+                                                                int ldp, float alpha, float beta, const float* __restrict__ bias,
+                                                                int bias_on_s, float* __restrict__ C, long c_ss, long c_ns) {
+  __shared__ float red[8][33];
+  const int i = blockIdx.x * 32 + threadIdx.x;
+  const bool ok = i < Sn * N;
+  const int s = ok ? i / N : 0, n = ok ? i % N : 0;
   float t = 0.f;
-  for (int z = 0; z < nsplit; ++z) t += partial[((long)z * Sn + s) * ldp + n];
-  float x = alpha * t;
-  if (bias != nullptr) x += bias[bias_on_s ? s : n];
-  float* cp = C + s * c_ss + n * c_ns;
-  if (beta != 0.f) x = fmaf(beta, *cp, x);
-  *cp = x;
+  if (ok)
+    for (int z = threadIdx.y; z < nsplit; z += 8) t += partial[((long)z * Sn + s) * ldp + n];
+  red[threadIdx.y][threadIdx.x] = t;
+  __syncthreads();
+  if (threadIdx.y == 0 && ok) {
+    float x = 0.f;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) x += red[y][threadIdx.x];
+    x *= alpha;
+    if (bias != nullptr) x += bias[bias_on_s ? s : n];
+    float* cp = C + s * c_ss + n * c_ns;
+    if (beta != 0.f) x = fmaf(beta, *cp, x);
+    *cp = x;
+  }
 }
 
 inline bool al16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
 int launch_smalln(const SkArgs& g, cudaStream_t st) {
-  const int R = g.N <= 8 ? 4 : (g.N <= 16 ? 2 : 1);
+  const bool few = g.M < 148 * 16 * 4;  // few rows: one or two rows per warp so that every SM has warps to hide latency
+  const int R = g.N <= 8 ? (few ? (g.M < 148 * 16 * 2 ? 1 : 2) : 4) : (g.N <= 16 ? 2 : 1);
   const int warps = ceil_div(g.M, R);
   int grid = ceil_div(warps, 8);
   if (grid > 148 * 8) grid = 148 * 8;
-  if (g.N <= 4) gemm_smalln_kernel<4, 4><<<grid, 256, 0, st>>>(g);
-  else if (g.N <= 8) gemm_smalln_kernel<8, 4><<<grid, 256, 0, st>>>(g);
+  if (g.N <= 4 && R == 4) gemm_smalln_kernel<4, 4><<<grid, 256, 0, st>>>(g);
+  else if (g.N <= 4 && R == 2) gemm_smalln_kernel<4, 2><<<grid, 256, 0, st>>>(g);
+  else if (g.N <= 4) gemm_smalln_kernel<4, 1><<<grid, 256, 0, st>>>(g);
+  else if (g.N <= 8 && R == 4) gemm_smalln_kernel<8, 4><<<grid, 256, 0, st>>>(g);
+  else if (g.N <= 8 && R == 2) gemm_smalln_kernel<8, 2><<<grid, 256, 0, st>>>(g);
+  else if (g.N <= 8) gemm_smalln_kernel<8, 1><<<grid, 256, 0, st>>>(g);
   else if (g.N <= 16) gemm_smalln_kernel<16, 2><<<grid, 256, 0, st>>>(g);
   else gemm_smalln_kernel<32, 1><<<grid, 256, 0, st>>>(g);
   IMMTSF_CHECK_LAUNCH("gemm_smalln");
@@ -264,7 +291,7 @@ int launch_tallt(const float* S, long s_ks, long s_ss, int Sn, const float* W, l
   }
 #undef TALLT
   IMMTSF_CHECK_LAUNCH("gemm_tallt_partial");
-  gemm_tallt_reduce_kernel<<<ceil_div(Sn * N, 256), 256, 0, st>>>(partial, nsplit, Sn, N, ldp, alpha, beta, bias, bias_on_s, C,
+  gemm_tallt_reduce_kernel<<<ceil_div(Sn * N, 32), dim3(32, 8), 0, st>>>(partial, nsplit, Sn, N, ldp, alpha, beta, bias, bias_on_s, C,
                                                                   c_ss, c_ns);
   IMMTSF_CHECK_LAUNCH("gemm_tallt_reduce");
   return 0;

@@ -347,9 +347,11 @@ __global__ void splitk_reduce_kernel(float* __restrict__ C, int ldc, int M, int 
 }
 
 // ---------------------------------------------------------------- operand split
-// hi = x & 0xFFFFE000 (TF32-exact), lo = x - hi.  rows x cols (ld_src) -> dense [rows][ld_dst].
-__global__ void split_tf32_kernel(const float* __restrict__ src, int ld_src, int rows, int cols, float* __restrict__ hi,
-                                  float* __restrict__ lo, int ld_dst, const int32_t* __restrict__ ragged, int ragged_rows_flag) {
+// tcgen05.mma kind::tf32 reads fp32 containers and ignores the low 13 mantissa bits (measured: feeding the raw
+// operand or its pre-truncated copy gives bit-identical results, round-1 experiment), so the "hi" operand IS the
+// original tensor and only lo = x - trunc_tf32(x) has to be materialised.  rows x cols (ld_src) -> [rows][ld_dst].
+__global__ void split_lo_kernel(const float* __restrict__ src, int ld_src, int rows, int cols, float* __restrict__ lo,
+                                int ld_dst, const int32_t* __restrict__ ragged, int ragged_rows_flag) {
   int live_rows = rows;
   if (ragged_rows_flag) {
     const int m = ragged_rows(rows, ragged);
@@ -362,17 +364,16 @@ __global__ void split_tf32_kernel(const float* __restrict__ src, int ld_src, int
     const int r = (int)(i / c4n), c = (int)(i % c4n) * 4;
     const float* p = src + (size_t)r * ld_src + c;
     float4 x;
-    if (c + 3 < cols) x = *reinterpret_cast<const float4*>(p);
+    if (c + 3 < cols) x = __ldg(reinterpret_cast<const float4*>(p));
     else {
       x.x = c + 0 < cols ? p[0] : 0.f; x.y = c + 1 < cols ? p[1] : 0.f;
       x.z = c + 2 < cols ? p[2] : 0.f; x.w = c + 3 < cols ? p[3] : 0.f;
     }
-    float4 h, l;
-    h.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u); l.x = x.x - h.x;
-    h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u); l.y = x.y - h.y;
-    h.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u); l.z = x.z - h.z;
-    h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u); l.w = x.w - h.w;
-    *reinterpret_cast<float4*>(hi + (size_t)r * ld_dst + c) = h;
+    float4 l;
+    l.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+    l.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+    l.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
+    l.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
     *reinterpret_cast<float4*>(lo + (size_t)r * ld_dst + c) = l;
   }
 }
@@ -428,20 +429,58 @@ inline int choose_splitk(int M, int N, int K) {
 
 }  // namespace
 
-// workspace: A_hi | A_lo | B_hi | B_lo, each dense with ld rounded up to 4 floats, 256 B aligned
+// ---------------------------------------------------------------- per-launch timing (bench.py's roofline)
+namespace {
+struct ProfRec { cudaEvent_t e0, e1; int M, N, K, ragged_dim; };
+ProfRec* g_prof = nullptr;
+int g_prof_cap = 0, g_prof_n = 0, g_prof_on = 0;
+}  // namespace
+
+// Start recording a CUDA-event pair around every gemm_tc_kernel launch (on the launch stream).
+extern "C" int immtsf_profile_begin(int max_records) {
+  IMMTSF_REQUIRE(max_records > 0, "profile_begin: max_records must be > 0");
+  if (g_prof_cap < max_records) {
+    ProfRec* p = (ProfRec*)realloc(g_prof, sizeof(ProfRec) * (size_t)max_records);
+    IMMTSF_REQUIRE(p != nullptr, "profile_begin: out of memory");
+    g_prof = p;
+    for (int i = g_prof_cap; i < max_records; ++i) {
+      cudaEventCreate(&g_prof[i].e0);
+      cudaEventCreate(&g_prof[i].e1);
+    }
+    g_prof_cap = max_records;
+  }
+  g_prof_n = 0;
+  g_prof_on = 1;
+  return IMMTSF_OK;
+}
+// Stop recording; waits for the recorded launches and returns their shapes and durations (ms). Returns the count.
+extern "C" int immtsf_profile_end(int* M, int* N, int* K, int* ragged_dim, float* ms, int cap) {
+  g_prof_on = 0;
+  int n = g_prof_n < cap ? g_prof_n : cap;
+  for (int i = 0; i < n; ++i) {
+    cudaEventSynchronize(g_prof[i].e1);
+    float t = 0.f;
+    cudaEventElapsedTime(&t, g_prof[i].e0, g_prof[i].e1);
+    M[i] = g_prof[i].M; N[i] = g_prof[i].N; K[i] = g_prof[i].K; ragged_dim[i] = g_prof[i].ragged_dim; ms[i] = t;
+  }
+  g_prof_n = 0;
+  return n;
+}
+
+// workspace: A_lo | B_lo (each dense with ld rounded up to 4 floats, 256 B aligned) | split-K partial tiles
 size_t immtsf_gemm_tc_workspace(int transA, int transB, int M, int N, int K) {
   const size_t ra = transA ? K : M, ca = transA ? M : K, rb = transB ? N : K, cb = transB ? K : N;
   const size_t a = align_up(ra * align_up(ca, 4) * 4, 256), b = align_up(rb * align_up(cb, 4) * 4, 256);
   const int sk = choose_splitk(M, N, K);
   const size_t p = sk > 1 ? align_up((size_t)sk * M * align_up(N, 4) * 4, 256) : 0;
-  return 2 * a + 2 * b + p + 256;
+  return a + b + p + 256;
 }
 
 // forced != 0: only hard requirements (alignment, driver entry point); else also the size heuristic
 int immtsf_gemm_tc_eligible(int forced, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
                             const float* C, int ldc) {
   if (M < 1 || N < 1 || K < 1) return 0;
-  if (((uintptr_t)A & 15) != 0 || (lda & 3) != 0 || ((uintptr_t)B & 15) != 0 || (ldb & 3) != 0) return 0;  // split reads 128-bit
+  if (((uintptr_t)A & 15) != 0 || (lda & 3) != 0 || ((uintptr_t)B & 15) != 0 || (ldb & 3) != 0) return 0;  // TMA: 16 B strides
   if (((uintptr_t)C & 15) != 0 || (ldc & 3) != 0) return 0;  // epilogue stores 128-bit
   if (!forced) {
     if (M < 64 || N < 32 || K < 32) return 0;  // tiny / skinny: CUDA cores
@@ -450,44 +489,63 @@ int immtsf_gemm_tc_eligible(int forced, int M, int N, int K, const float* A, int
   return get_encode() != nullptr;
 }
 
-int immtsf_gemm_tc(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda, const float* B,
-                   int ldb, float beta, float* C, int ldc, const float* bias, const int32_t* ragged, int ragged_dim,
-                   void* workspace, size_t workspace_bytes, cudaStream_t st) {
+static int launch_split_lo(const float* src, int ld, int rows, int cols, float* lo, int ld_lo, const int32_t* ragged,
+                           int ragged_flag, cudaStream_t st) {
+  const size_t tot = (size_t)rows * (ld_lo / 4);
+  int grid = (int)((tot + 255) / 256);
+  if (grid > 148 * 16) grid = 148 * 16;
+  if (grid < 1) grid = 1;
+  split_lo_kernel<<<grid, 256, 0, st>>>(src, ld, rows, cols, lo, ld_lo, ragged, ragged_flag);
+  IMMTSF_CHECK_LAUNCH("split_lo");
+  return IMMTSF_OK;
+}
+
+// lo[rows][roundup(cols,4)] = x - trunc_tf32(x); rows bounded by roundup(*ragged, 128) when ragged != NULL
+extern "C" int immtsf_split_lo(const float* src, int ld, int rows, int cols, float* lo, int ld_lo, const int32_t* ragged,
+                               void* stream) {
+  if (rows == 0 || cols == 0) return IMMTSF_OK;
+  IMMTSF_REQUIRE(src && lo, "split_lo: null pointer");
+  IMMTSF_REQUIRE(((uintptr_t)src & 15) == 0 && (ld & 3) == 0 && ((uintptr_t)lo & 15) == 0 && (ld_lo & 3) == 0 && ld_lo >= cols,
+                 "split_lo: operands must be 16B aligned with ld %% 4 == 0 and ld_lo >= cols");
+  return launch_split_lo(src, ld, rows, cols, lo, ld_lo, ragged, ragged != nullptr, (cudaStream_t)stream);
+}
+
+int immtsf_gemm_tc(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda, const float* A_lo,
+                   int lda_lo, const float* B, int ldb, const float* B_lo, int ldb_lo, float beta, float* C, int ldc,
+                   const float* bias, const int32_t* ragged, int ragged_dim, void* workspace, size_t workspace_bytes,
+                   cudaStream_t st) {
   const size_t need = immtsf_gemm_tc_workspace(transA, transB, M, N, K);
   if (workspace == nullptr || workspace_bytes < need) {
     immtsf_set_error("gemm_tc: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
     return IMMTSF_ERR_ARG;
   }
   const int ra = transA ? K : M, ca = transA ? M : K, rb = transB ? N : K, cb = transB ? K : N;
-  const int lda2 = (int)align_up(ca, 4), ldb2 = (int)align_up(cb, 4);
+  int lda2 = (int)align_up(ca, 4), ldb2 = (int)align_up(cb, 4);
   const size_t abytes = align_up((size_t)ra * lda2 * 4, 256), bbytes = align_up((size_t)rb * ldb2 * 4, 256);
   uint8_t* w = (uint8_t*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
-  float* Ah = (float*)w; float* Al = (float*)(w + abytes);
-  float* Bh = (float*)(w + 2 * abytes); float* Bl = (float*)(w + 2 * abytes + bbytes);
+  const float* Al = A_lo; const float* Bl = B_lo;
   // rows of A are ragged when (ragged_dim==1 && !transA) or (ragged_dim==2 && transA); rows of B when ragged_dim==2 && !transB
   const int a_ragged = (ragged_dim == 1 && !transA) || (ragged_dim == 2 && transA);
   const int b_ragged = (ragged_dim == 2 && !transB);
-  {
-    size_t tot = (size_t)ra * (lda2 / 4);
-    int grid = (int)((tot + 255) / 256); if (grid > 148 * 16) grid = 148 * 16; if (grid < 1) grid = 1;
-    split_tf32_kernel<<<grid, 256, 0, st>>>(A, lda, ra, ca, Ah, Al, lda2, ragged, a_ragged);
-    tot = (size_t)rb * (ldb2 / 4);
-    grid = (int)((tot + 255) / 256); if (grid > 148 * 16) grid = 148 * 16; if (grid < 1) grid = 1;
-    split_tf32_kernel<<<grid, 256, 0, st>>>(B, ldb, rb, cb, Bh, Bl, ldb2, ragged, b_ragged);
-    IMMTSF_CHECK_LAUNCH("split_tf32");
-    immtsf_count_launch();
+  if (Al == nullptr) {
+    int rc = launch_split_lo(A, lda, ra, ca, (float*)w, lda2, ragged, a_ragged, st);
+    if (rc) return rc;
+    Al = (const float*)w;
+  } else {
+    lda2 = lda_lo;
+  }
+  if (Bl == nullptr) {
+    int rc = launch_split_lo(B, ldb, rb, cb, (float*)(w + abytes), ldb2, ragged, b_ragged, st);
+    if (rc) return rc;
+    Bl = (const float*)(w + abytes);
+  } else {
+    ldb2 = ldb_lo;
   }
   CUtensorMap mAh, mAl, mBh, mBl;
   // K-major operand [rows=MN][cols=K]: box 32 x 128 ; MN-major operand [rows=K][cols=MN]: box 32 x 32
   const int boxA = transA ? 32 : BM, boxB = transB ? BN : 32;
-  // experiment (IMMTSF_TC_RAWHI=1): feed the unsplit fp32 operand as the "hi" part.  If the tensor core
-  // truncates fp32 inputs to TF32 itself, results are bit-identical and the hi copies are unnecessary.
-  static int rawhi = -1;
-  if (rawhi < 0) { const char* e = getenv("IMMTSF_TC_RAWHI"); rawhi = (e && e[0] == '1') ? 1 : 0; }
-  const float* Ahp = rawhi ? A : Ah; const int ldah = rawhi ? lda : lda2;
-  const float* Bhp = rawhi ? B : Bh; const int ldbh = rawhi ? ldb : ldb2;
-  if (make_map(&mAh, Ahp, ra, ca, ldah, boxA, transA != 0) || make_map(&mAl, Al, ra, ca, lda2, boxA, transA != 0) ||
-      make_map(&mBh, Bhp, rb, cb, ldbh, boxB, transB == 0) || make_map(&mBl, Bl, rb, cb, ldb2, boxB, transB == 0)) {
+  if (make_map(&mAh, A, ra, ca, lda, boxA, transA != 0) || make_map(&mAl, Al, ra, ca, lda2, boxA, transA != 0) ||
+      make_map(&mBh, B, rb, cb, ldb, boxB, transB == 0) || make_map(&mBl, Bl, rb, cb, ldb2, boxB, transB == 0)) {
     immtsf_set_error("gemm_tc: cuTensorMapEncodeTiled failed");
     return IMMTSF_ERR_LAUNCH;
   }
@@ -499,7 +557,7 @@ int immtsf_gemm_tc(int transA, int transB, int M, int N, int K, float alpha, con
   g.partial = nullptr; g.ldp = 0;
   if (splitk > 1) {
     grid.z = splitk;
-    g.partial = (float*)(w + 2 * abytes + 2 * bbytes);
+    g.partial = (float*)(w + abytes + bbytes);
     g.ldp = (int)align_up(N, 4);
   }
   static bool attr_done = false;
@@ -510,11 +568,14 @@ int immtsf_gemm_tc(int transA, int transB, int M, int N, int K, float alpha, con
     cudaFuncSetAttribute(gemm_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     attr_done = true;
   }
+  ProfRec* rec = (g_prof_on && g_prof_n < g_prof_cap) ? &g_prof[g_prof_n++] : nullptr;
+  if (rec) { rec->M = M; rec->N = N; rec->K = K; rec->ragged_dim = ragged_dim; cudaEventRecord(rec->e0, st); }
   // UMMA "B is K-major" means stored [N][K], i.e. transB=1
   if (!transA && transB) gemm_tc_kernel<false, false><<<grid, 256, SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, g);
   else if (!transA && !transB) gemm_tc_kernel<false, true><<<grid, 256, SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, g);
   else if (transA && !transB) gemm_tc_kernel<true, true><<<grid, 256, SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, g);
   else gemm_tc_kernel<true, false><<<grid, 256, SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, g);
+  if (rec) cudaEventRecord(rec->e1, st);
   IMMTSF_CHECK_LAUNCH("gemm_tc");
   if (splitk > 1) {
     const size_t tot = (size_t)M * (g.ldp / 4);

@@ -171,9 +171,10 @@ __global__ void __launch_bounds__(GR_WARPS * 32) gr_tail_fwd_kernel(const float*
                                                                     const float* __restrict__ h_all, const float* __restrict__ w_r,
                                                                     const float* __restrict__ b_r, const float* __restrict__ gamma,
                                                                     const float* __restrict__ beta, const uint8_t* __restrict__ m_txt,
-                                                                    int B, int T, int C, float eps, uint32_t thr, uint64_t seed,
+                                                                    int B, int T, int C, float eps, uint32_t thr, SeedArg seed_,
                                                                     float* __restrict__ Y_out, int32_t* __restrict__ flags) {
   extern __shared__ float smem[];
+  const uint64_t seed = resolve_seed(seed_);
   const int ldw = C + 1;
   float* s_w = smem;                  // [C][C+1]
   float* s_h = s_w + C * ldw;         // [GR_WARPS][C]
@@ -234,11 +235,12 @@ __global__ void __launch_bounds__(GR_WARPS * 32) gr_tail_bwd_kernel(const float*
                                                                     const float* __restrict__ h_all, const float* __restrict__ w_r,
                                                                     const float* __restrict__ b_r, const float* __restrict__ gamma,
                                                                     const float* __restrict__ beta, const uint8_t* __restrict__ m_txt,
-                                                                    int B, int T, int C, float eps, uint32_t thr, uint64_t seed,
+                                                                    int B, int T, int C, float eps, uint32_t thr, SeedArg seed_,
                                                                     float* __restrict__ dG4, float* __restrict__ d_delta,
                                                                     float* __restrict__ dh_out, float* __restrict__ dgamma,
                                                                     float* __restrict__ dbeta) {
   extern __shared__ float smem[];
+  const uint64_t seed = resolve_seed(seed_);
   const int ldw = C + 1;
   float* s_w = smem;                          // [C][C+1]
   float* s_h = s_w + C * ldw;                 // [GR_WARPS][C]
@@ -411,7 +413,7 @@ extern "C" int immtsf_gr_tail_fwd(const float* Y, const float* G4, const float* 
     int rc = set_smem(gr_tail_fwd_kernel<UN>, smem, "gr_tail_fwd");
     if (rc) return rc;
     gr_tail_fwd_kernel<UN><<<grid, GR_WARPS * 32, smem, st>>>(Y, G4, h_all, w_r, b_r, gamma, beta, m_txt, B, T, C, eps,
-                                                                drop_thr, seed, Y_out, flags);
+                                                                drop_thr, make_seed(seed), Y_out, flags);
   });
   IMMTSF_CHECK_LAUNCH("gr_tail_fwd");
   return IMMTSF_OK;
@@ -433,7 +435,7 @@ extern "C" int immtsf_gr_tail_bwd(const float* dY_out, const float* G4, const fl
     int rc = set_smem(gr_tail_bwd_kernel<UN>, smem, "gr_tail_bwd");
     if (rc) return rc;
     gr_tail_bwd_kernel<UN><<<grid, GR_WARPS * 32, smem, st>>>(dY_out, G4, h_all, w_r, b_r, gamma, beta, m_txt, B, T, C, eps,
-                                                                drop_thr, seed, dG4, d_delta, dh_out, dgamma, dbeta);
+                                                                drop_thr, make_seed(seed), dG4, d_delta, dh_out, dgamma, dbeta);
   });
   IMMTSF_CHECK_LAUNCH("gr_tail_bwd");
   return IMMTSF_OK;

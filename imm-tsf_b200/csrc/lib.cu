@@ -17,6 +17,22 @@ static unsigned long long g_launches = 0;
 void immtsf_count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
 extern "C" unsigned long long immtsf_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
+// device-resident dropout seed offset, added to every seed argument when set.  Process-wide (one process per
+// GPU): forward runs on the caller's thread, backward on autograd's, and both must see the same pointer.
+static const uint64_t* g_seed_dev = nullptr;
+const uint64_t* immtsf_seed_dev() { return g_seed_dev; }
+extern "C" int immtsf_set_seed_offset_ptr(const uint64_t* dev_ptr) {
+  g_seed_dev = dev_ptr;
+  return IMMTSF_OK;
+}
+__global__ void seed_advance_kernel(uint64_t* p, uint64_t inc) { *p += inc; }
+extern "C" int immtsf_seed_advance(uint64_t* dev_ptr, uint64_t inc, void* stream) {
+  IMMTSF_REQUIRE(dev_ptr != nullptr, "seed_advance: null pointer");
+  seed_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(dev_ptr, inc);
+  IMMTSF_CHECK_LAUNCH("seed_advance");
+  return IMMTSF_OK;
+}
+
 extern "C" int immtsf_version(void) { return IMMTSF_ABI_VERSION; }
 extern "C" const char* immtsf_last_error_string(void) { return g_err; }
 

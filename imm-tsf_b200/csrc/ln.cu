@@ -10,8 +10,8 @@
 #include "../../include/immtsf.h"
 
 struct LnArgs {
-  const float* x; int ldx; const float* res; const uint8_t* valid; int rps;
-  const float* gamma; const float* beta; int R, d; float eps; uint32_t thr; uint64_t seed; uint32_t site;
+  const float* x; int ldx; const float* xbias; const float* res; const uint8_t* valid; int rps;
+  const float* gamma; const float* beta; int R, d; float eps; uint32_t thr; SeedArg seed; uint32_t site;
   float* y; float* mean; float* rstd;
   const float* dy; float* dx; float* dres; float* dgamma; float* dbeta;
 };
@@ -38,7 +38,10 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const LnArgs a) {
         const int col4 = threadIdx.x + c * blockDim.x;
         float4 q = f4_zero();
         if (ok && col4 < d4) {
-          if (v) q = __ldg(reinterpret_cast<const float4*>(a.x + (size_t)r * a.ldx) + col4);
+          if (v) {
+            q = __ldg(reinterpret_cast<const float4*>(a.x + (size_t)r * a.ldx) + col4);
+            if (a.xbias) f4_add(q, __ldg(reinterpret_cast<const float4*>(a.xbias) + col4));
+          }
           if (a.res) f4_add(q, __ldg(reinterpret_cast<const float4*>(a.res) + col4));
         }
         z[t][c] = q;
@@ -74,7 +77,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const LnArgs a) {
         if (col4 >= d4) continue;
         const float4 g = __ldg(reinterpret_cast<const float4*>(a.gamma) + col4);
         const float4 be = __ldg(reinterpret_cast<const float4*>(a.beta) + col4);
-        const float4 ks = dropout_scale4(a.seed, a.site, (uint64_t)r * d4 + col4, a.thr, inv_keep);
+        const float4 ks = dropout_scale4(resolve_seed(a.seed), a.site, (uint64_t)r * d4 + col4, a.thr, inv_keep);
         float4 y;
         y.x = ((z[t][c].x - mu) * rs * g.x + be.x) * ks.x;
         y.y = ((z[t][c].y - mu) * rs * g.y + be.y) * ks.y;
@@ -121,10 +124,13 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnArgs a) {
         xh[t][c] = f4_zero();
         if (ok && col4 < d4) {
           float4 dy = __ldg(reinterpret_cast<const float4*>(a.dy + (size_t)r * a.d) + col4);
-          const float4 ks = dropout_scale4(a.seed, a.site, (uint64_t)r * d4 + col4, a.thr, inv_keep);
+          const float4 ks = dropout_scale4(resolve_seed(a.seed), a.site, (uint64_t)r * d4 + col4, a.thr, inv_keep);
           dy.x *= ks.x; dy.y *= ks.y; dy.z *= ks.z; dy.w *= ks.w;
           float4 q = f4_zero();
-          if (vrow[t]) q = __ldg(reinterpret_cast<const float4*>(a.x + (size_t)r * a.ldx) + col4);
+          if (vrow[t]) {
+            q = __ldg(reinterpret_cast<const float4*>(a.x + (size_t)r * a.ldx) + col4);
+            if (a.xbias) f4_add(q, __ldg(reinterpret_cast<const float4*>(a.xbias) + col4));
+          }
           if (a.res) f4_add(q, __ldg(reinterpret_cast<const float4*>(a.res) + col4));
           float4 h;
           h.x = (q.x - mu) * rs[t]; h.y = (q.y - mu) * rs[t]; h.z = (q.z - mu) * rs[t]; h.w = (q.w - mu) * rs[t];
@@ -191,7 +197,7 @@ static int ln_geometry(int d, int& nch, int& threads) {
   return 0;
 }
 
-extern "C" int immtsf_ln_fwd(const float* x, int ldx, const float* res, const uint8_t* valid, int rows_per_sample,
+extern "C" int immtsf_ln_fwd(const float* x, int ldx, const float* xbias, const float* res, const uint8_t* valid, int rows_per_sample,
                              const float* gamma, const float* beta, int R, int d, float eps, uint32_t drop_thr,
                              uint64_t seed, uint32_t site, float* y, float* mean, float* rstd, void* stream) {
   if (R == 0) return IMMTSF_OK;
@@ -201,8 +207,8 @@ extern "C" int immtsf_ln_fwd(const float* x, int ldx, const float* res, const ui
   IMMTSF_REQUIRE(ln_geometry(d, nch, threads) == 0, "ln_fwd: d=%d must be a multiple of 4 and <= 4096", d);
   IMMTSF_REQUIRE((ldx & 3) == 0 && ((uintptr_t)x & 15) == 0, "ln_fwd: x must be 16B aligned with ldx %% 4 == 0");
   LnArgs a = {};
-  a.x = x; a.ldx = ldx; a.res = res; a.valid = valid; a.rps = rows_per_sample > 0 ? rows_per_sample : 1;
-  a.gamma = gamma; a.beta = beta; a.R = R; a.d = d; a.eps = eps; a.thr = drop_thr; a.seed = seed; a.site = site;
+  a.x = x; a.ldx = ldx; a.xbias = xbias; a.res = res; a.valid = valid; a.rps = rows_per_sample > 0 ? rows_per_sample : 1;
+  a.gamma = gamma; a.beta = beta; a.R = R; a.d = d; a.eps = eps; a.thr = drop_thr; a.seed = make_seed(seed); a.site = site;
   a.y = y; a.mean = mean; a.rstd = rstd;
   const int TT = 8 / nch;
   int grid = ceil_div(R, TT);
@@ -215,7 +221,7 @@ extern "C" int immtsf_ln_fwd(const float* x, int ldx, const float* res, const ui
   return IMMTSF_OK;
 }
 
-extern "C" int immtsf_ln_bwd(const float* dy, const float* x, int ldx, const float* res, const uint8_t* valid,
+extern "C" int immtsf_ln_bwd(const float* dy, const float* x, int ldx, const float* xbias, const float* res, const uint8_t* valid,
                              int rows_per_sample, const float* gamma, const float* mean, const float* rstd, int R,
                              int d, uint32_t drop_thr, uint64_t seed, uint32_t site, float* dx, float* dres,
                              float* dgamma, float* dbeta, void* stream) {
@@ -225,8 +231,8 @@ extern "C" int immtsf_ln_bwd(const float* dy, const float* x, int ldx, const flo
   IMMTSF_REQUIRE(ln_geometry(d, nch, threads) == 0, "ln_bwd: d=%d must be a multiple of 4 and <= 4096", d);
   IMMTSF_REQUIRE((ldx & 3) == 0 && ((uintptr_t)x & 15) == 0, "ln_bwd: x must be 16B aligned with ldx %% 4 == 0");
   LnArgs a = {};
-  a.x = x; a.ldx = ldx; a.res = res; a.valid = valid; a.rps = rows_per_sample > 0 ? rows_per_sample : 1;
-  a.gamma = gamma; a.R = R; a.d = d; a.thr = drop_thr; a.seed = seed; a.site = site;
+  a.x = x; a.ldx = ldx; a.xbias = xbias; a.res = res; a.valid = valid; a.rps = rows_per_sample > 0 ? rows_per_sample : 1;
+  a.gamma = gamma; a.R = R; a.d = d; a.thr = drop_thr; a.seed = make_seed(seed); a.site = site;
   a.mean = const_cast<float*>(mean); a.rstd = const_cast<float*>(rstd);
   a.dy = dy; a.dx = dx; a.dres = dres; a.dgamma = dgamma; a.dbeta = dbeta;
   const int TT = 8 / nch;

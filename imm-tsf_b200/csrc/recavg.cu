@@ -30,7 +30,7 @@ struct PoolArgs {
   const float* tau; const int32_t* offsets;
   const float* t_hat; int t_bstride;
   const float* log_sigma; const float* gamma; const float* beta;
-  int B, T, d; float eps; uint32_t thr; uint64_t seed;
+  int B, T, d; float eps; uint32_t thr; SeedArg seed;
   float* E_drop; float* E_raw; float* mean; float* rstd; float* wsum;
   // backward only
   const float* dE_drop; float* dVp; int lddv; float* dgamma; float* dbeta; float* dlog_sigma;
@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(256) recavg_pool_fwd_kernel(const PoolArgs a) 
       const float4 x = acc[t][c];
       const float4 g = __ldg(reinterpret_cast<const float4*>(a.gamma) + col4);
       const float4 be = __ldg(reinterpret_cast<const float4*>(a.beta) + col4);
-      const float4 ks = dropout_scale4(a.seed, IMMTSF_SITE_TTF_DROPOUT, rowi * d4 + col4, a.thr, inv_keep);
+      const float4 ks = dropout_scale4(resolve_seed(a.seed), IMMTSF_SITE_TTF_DROPOUT, rowi * d4 + col4, a.thr, inv_keep);
       float4 y;
       y.x = ((x.x - mu) * rs * g.x + be.x) * ks.x;
       y.y = ((x.y - mu) * rs * g.y + be.y) * ks.y;
@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(256) recavg_pool_bwd_kernel(const PoolArgs a) 
         xh[t][c] = f4_zero();
         if (ok && col4 < d4) {
           float4 dy = __ldg(reinterpret_cast<const float4*>(a.dE_drop + rowi * a.d) + col4);
-          const float4 ks = dropout_scale4(a.seed, IMMTSF_SITE_TTF_DROPOUT, rowi * d4 + col4, a.thr, inv_keep);
+          const float4 ks = dropout_scale4(resolve_seed(a.seed), IMMTSF_SITE_TTF_DROPOUT, rowi * d4 + col4, a.thr, inv_keep);
           dy.x *= ks.x; dy.y *= ks.y; dy.z *= ks.z; dy.w *= ks.w;
           const float4 x = __ldg(reinterpret_cast<const float4*>(a.E_raw + rowi * a.d) + col4);
           float4 h;
@@ -342,7 +342,7 @@ extern "C" int immtsf_recavg_pool_fwd(const float* Vp, int ldv, const float* tau
   PoolArgs a = {};
   a.Vp = Vp; a.ldv = ldv; a.tau = tau_flat; a.offsets = offsets; a.t_hat = t_hat; a.t_bstride = t_hat_bstride;
   a.log_sigma = log_sigma; a.gamma = gamma; a.beta = beta; a.B = B; a.T = T; a.d = d; a.eps = eps;
-  a.thr = drop_thr; a.seed = seed; a.E_drop = E_drop; a.E_raw = E_raw; a.mean = mean; a.rstd = rstd; a.wsum = wsum;
+  a.thr = drop_thr; a.seed = make_seed(seed); a.E_drop = E_drop; a.E_raw = E_raw; a.mean = mean; a.rstd = rstd; a.wsum = wsum;
   cudaStream_t st = (cudaStream_t)stream;
   const int TT = 8 / nch;
   dim3 grid(B, ceil_div(T, TT));
@@ -369,7 +369,7 @@ extern "C" int immtsf_recavg_pool_bwd(const float* dE_drop, const float* E_raw, 
   PoolArgs a = {};
   a.Vp = Vp; a.ldv = ldv; a.tau = tau_flat; a.offsets = offsets; a.t_hat = t_hat; a.t_bstride = t_hat_bstride;
   a.log_sigma = log_sigma; a.gamma = gamma; a.B = B; a.T = T; a.d = d; a.eps = 1e-5f;
-  a.thr = drop_thr; a.seed = seed; a.E_raw = const_cast<float*>(E_raw); a.mean = const_cast<float*>(mean);
+  a.thr = drop_thr; a.seed = make_seed(seed); a.E_raw = const_cast<float*>(E_raw); a.mean = const_cast<float*>(mean);
   a.rstd = const_cast<float*>(rstd); a.wsum = const_cast<float*>(wsum);
   a.dE_drop = dE_drop; a.dVp = dVp; a.lddv = lddv; a.dgamma = dgamma; a.dbeta = dbeta; a.dlog_sigma = dlog_sigma;
   cudaStream_t st = (cudaStream_t)stream;

@@ -93,7 +93,7 @@ extern "C" int immtsf_time2vec_bwd(const float* dphi, int ld, const float* tau_f
 // ------------------------------------------------------------- segment attention
 struct SegArgs {
   const float* q; const float* KVp; const int32_t* offsets;
-  int B, T, H, d, hd, N_max, per_query, TT; uint32_t thr; uint64_t seed;
+  int B, T, H, d, hd, N_max, per_query, TT; uint32_t thr; SeedArg seed;
   float* attn_cat; float* probs;
   const float* dO; float* dKVp; float* dq_partial;
 };
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(256) segattn_fwd_kernel(const SegArgs a) {
       if (t < Teff) {
         p = s_p[h * NM + n];
         if (a.per_query)
-          p *= dropout_scale(a.seed, IMMTSF_SITE_TTF_ATTN, (((uint64_t)b * a.T + t) * H + h) * NM + n, a.thr, inv_keep);
+          p *= dropout_scale(resolve_seed(a.seed), IMMTSF_SITE_TTF_ATTN, (((uint64_t)b * a.T + t) * H + h) * NM + n, a.thr, inv_keep);
       }
       s_pt[((size_t)tt * H + h) * NM + n] = p;
     }
@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(256) segattn_bwd_kernel(const SegArgs a) {
         for (int n = lane; n < nn; n += 32) {
           float ks = 1.f;
           if (a.per_query)
-            ks = dropout_scale(a.seed, IMMTSF_SITE_TTF_ATTN, (((uint64_t)b * a.T + t) * H + h) * NM + n, a.thr, inv_keep);
+            ks = dropout_scale(resolve_seed(a.seed), IMMTSF_SITE_TTF_ATTN, (((uint64_t)b * a.T + t) * H + h) * NM + n, a.thr, inv_keep);
           const float dp = s_dp[((size_t)tt * H + h) * NM + n] * ks;
           s_dp[((size_t)tt * H + h) * NM + n] = dp;  // temporarily dp
           D = fmaf(s_p[h * NM + n], dp, D);
@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(256) segattn_bwd_kernel(const SegArgs a) {
         for (int n = lane; n < nn; n += 32) {
           float ks = 1.f;
           if (a.per_query)
-            ks = dropout_scale(a.seed, IMMTSF_SITE_TTF_ATTN, (((uint64_t)b * a.T + t) * H + h) * NM + n, a.thr, inv_keep);
+            ks = dropout_scale(resolve_seed(a.seed), IMMTSF_SITE_TTF_ATTN, (((uint64_t)b * a.T + t) * H + h) * NM + n, a.thr, inv_keep);
           const float p = s_p[h * NM + n];
           const float dp = s_dp[((size_t)tt * H + h) * NM + n];
           s_ds[h * NM + n] += p * (dp - D);
@@ -306,7 +306,7 @@ extern "C" int immtsf_segattn_fwd(const float* q, const float* KVp, const int32_
   IMMTSF_REQUIRE(N_max >= 1 && T >= 1, "segattn_fwd: N_max and T must be >= 1");
   SegArgs a = {};
   a.q = q; a.KVp = KVp; a.offsets = offsets; a.B = B; a.T = T; a.H = H; a.d = d; a.hd = d / H; a.N_max = N_max;
-  a.per_query = per_query ? 1 : 0; a.thr = per_query ? drop_thr : 0u; a.seed = seed; a.attn_cat = attn_cat; a.probs = probs;
+  a.per_query = per_query ? 1 : 0; a.thr = per_query ? drop_thr : 0u; a.seed = make_seed(seed); a.attn_cat = attn_cat; a.probs = probs;
   size_t smem;
   if (seg_setup(a, 1, smem)) { immtsf_set_error("segattn_fwd: H*N_max=%d too large for shared memory", H * N_max); return IMMTSF_ERR_UNSUPPORTED; }
   if (smem > 48 * 1024) cudaFuncSetAttribute(segattn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -325,7 +325,7 @@ extern "C" int immtsf_segattn_bwd(const float* d_attn_cat, const float* q, const
                      ((uintptr_t)q & 15) == 0 && ((uintptr_t)dq_partial & 15) == 0, "segattn_bwd: buffers must be 16B aligned");
   SegArgs a = {};
   a.q = q; a.KVp = KVp; a.offsets = offsets; a.B = B; a.T = T; a.H = H; a.d = d; a.hd = d / H; a.N_max = N_max;
-  a.per_query = per_query ? 1 : 0; a.thr = per_query ? drop_thr : 0u; a.seed = seed; a.probs = const_cast<float*>(probs);
+  a.per_query = per_query ? 1 : 0; a.thr = per_query ? drop_thr : 0u; a.seed = make_seed(seed); a.probs = const_cast<float*>(probs);
   a.dO = d_attn_cat; a.dKVp = dKVp; a.dq_partial = dq_partial;
   size_t smem;
   if (seg_setup(a, 2, smem)) { immtsf_set_error("segattn_bwd: H*N_max=%d too large for shared memory", H * N_max); return IMMTSF_ERR_UNSUPPORTED; }

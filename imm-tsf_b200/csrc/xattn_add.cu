@@ -18,9 +18,18 @@
 
 constexpr int XQ = 8;  // query rows per tile
 
+// T <= 32 fast path (xattn_small.cu)
+int immtsf_xattn_small_ok(int T, int H, int d);
+int immtsf_xattn_small_fwd(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, const uint8_t* m_txt, int B,
+                           int T, int H, int d, uint32_t drop_thr, uint64_t seed, float* o, int ldo, float* probs,
+                           cudaStream_t st);
+int immtsf_xattn_small_bwd(const float* d_o, int lddo, const float* q, int ldq, const float* k, int ldk, const float* v, int ldv,
+                           const float* probs, const uint8_t* m_txt, int B, int T, int H, int d, uint32_t drop_thr,
+                           uint64_t seed, float* dq, int lddq, float* dk, int lddk, float* dv, int lddv, cudaStream_t st);
+
 struct XArgs {
   const float* q; int ldq; const float* k; int ldk; const float* v; int ldv;
-  const uint8_t* m_txt; int B, T, H, d, hd; uint32_t thr; uint64_t seed; float scale;
+  const uint8_t* m_txt; int B, T, H, d, hd; uint32_t thr; SeedArg seed; float scale;
   float* o; int ldo; float* probs;
   const float* d_o; int lddo; float* dq; int lddq; float* dk; int lddk; float* dv; int lddv;
 };
@@ -76,7 +85,7 @@ __global__ void __launch_bounds__(256) xattn_core_fwd_kernel(const XArgs a) {
       const float p = s_s[ii * T + j] / sum;
       const size_t pidx = (((size_t)b * H + h) * T + i) * T + j;
       if (a.probs) a.probs[pidx] = p;
-      s_s[ii * T + j] = p * dropout_scale(a.seed, IMMTSF_SITE_MMF_ATTN, pidx, a.thr, inv_keep);
+      s_s[ii * T + j] = p * dropout_scale(resolve_seed(a.seed), IMMTSF_SITE_MMF_ATTN, pidx, a.thr, inv_keep);
     }
   }
   __syncthreads();
@@ -135,7 +144,7 @@ __global__ void __launch_bounds__(256) xattn_core_bwd_kernel(const XArgs a) {
       float D = 0.f;
       for (int j = lane; j < T; j += 32) {
         const size_t pidx = (((size_t)b * H + h) * T + i) * T + j;
-        const float ks = dropout_scale(a.seed, IMMTSF_SITE_MMF_ATTN, pidx, a.thr, inv_keep);
+        const float ks = dropout_scale(resolve_seed(a.seed), IMMTSF_SITE_MMF_ATTN, pidx, a.thr, inv_keep);
         const float p = a.probs[pidx];
         const float dp = s_ds[ii * T + j] * ks;
         s_ds[ii * T + j] = dp;
@@ -197,9 +206,11 @@ extern "C" int immtsf_xattn_core_fwd(const float* q, int ldq, const float* k, in
   int rc = xattn_check("xattn_core_fwd", B, T, H, d);
   if (rc) return rc;
   IMMTSF_REQUIRE(al16(v, ldv) && al16(o, ldo), "xattn_core_fwd: v/o must be 16B aligned with ld %% 4 == 0");
+  if (immtsf_xattn_small_ok(T, H, d) && al16(q, ldq) && al16(k, ldk))
+    return immtsf_xattn_small_fwd(q, ldq, k, ldk, v, ldv, m_txt, B, T, H, d, drop_thr, seed, o, ldo, probs, (cudaStream_t)stream);
   XArgs a = {};
   a.q = q; a.ldq = ldq; a.k = k; a.ldk = ldk; a.v = v; a.ldv = ldv; a.m_txt = m_txt; a.B = B; a.T = T; a.H = H; a.d = d;
-  a.hd = d / H; a.thr = drop_thr; a.seed = seed; a.scale = (float)sqrt(1.0 / (double)(d / H)); a.o = o; a.ldo = ldo; a.probs = probs;
+  a.hd = d / H; a.thr = drop_thr; a.seed = make_seed(seed); a.scale = (float)sqrt(1.0 / (double)(d / H)); a.o = o; a.ldo = ldo; a.probs = probs;
   const size_t smem = (size_t)XQ * T * sizeof(float);
   if (smem > 48 * 1024) cudaFuncSetAttribute(xattn_core_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dim3 grid(B * H, ceil_div(T, XQ));
@@ -218,9 +229,12 @@ extern "C" int immtsf_xattn_core_bwd(const float* d_o, int lddo, const float* q,
   if (rc) return rc;
   IMMTSF_REQUIRE(al16(d_o, lddo) && al16(q, ldq) && al16(k, ldk) && al16(dq, lddq) && al16(dk, lddk) && al16(dv, lddv),
                  "xattn_core_bwd: operands must be 16B aligned with ld %% 4 == 0");
+  if (immtsf_xattn_small_ok(T, H, d) && al16(v, ldv))
+    return immtsf_xattn_small_bwd(d_o, lddo, q, ldq, k, ldk, v, ldv, probs, m_txt, B, T, H, d, drop_thr, seed, dq, lddq, dk, lddk,
+                                  dv, lddv, (cudaStream_t)stream);
   XArgs a = {};
   a.q = q; a.ldq = ldq; a.k = k; a.ldk = ldk; a.v = v; a.ldv = ldv; a.m_txt = m_txt; a.B = B; a.T = T; a.H = H; a.d = d;
-  a.hd = d / H; a.thr = drop_thr; a.seed = seed; a.scale = (float)sqrt(1.0 / (double)(d / H)); a.probs = const_cast<float*>(probs);
+  a.hd = d / H; a.thr = drop_thr; a.seed = make_seed(seed); a.scale = (float)sqrt(1.0 / (double)(d / H)); a.probs = const_cast<float*>(probs);
   a.d_o = d_o; a.lddo = lddo; a.dq = dq; a.lddq = lddq; a.dk = dk; a.lddk = lddk; a.dv = dv; a.lddv = lddv;
   const size_t smem = (size_t)2 * XQ * T * sizeof(float);
   if (smem > 48 * 1024) cudaFuncSetAttribute(xattn_core_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -234,8 +248,9 @@ extern "C" int immtsf_xattn_core_bwd(const float* d_o, int lddo, const float* q,
 __global__ void __launch_bounds__(256) xattn_tail_fwd_kernel(const float* __restrict__ Y, const float* __restrict__ delta_y,
                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
                                                              const uint8_t* __restrict__ m_txt, int B, int T, int C, float eps,
-                                                             float kappa, uint32_t thr, uint64_t seed, float* __restrict__ Y_out,
+                                                             float kappa, uint32_t thr, SeedArg seed_, float* __restrict__ Y_out,
                                                              int32_t* __restrict__ flags) {
+  const uint64_t seed = resolve_seed(seed_);
   const int lane = threadIdx.x & 31;
   const int rows = B * T;
   const float inv_keep = inv_keep_from_thr(thr);
@@ -264,8 +279,9 @@ __global__ void __launch_bounds__(256) xattn_tail_fwd_kernel(const float* __rest
 __global__ void __launch_bounds__(256) xattn_tail_bwd_kernel(const float* __restrict__ dY_out, const float* __restrict__ delta_y,
                                                              const float* __restrict__ gamma, const uint8_t* __restrict__ m_txt,
                                                              int B, int T, int C, float eps, float kappa, uint32_t thr,
-                                                             uint64_t seed, float* __restrict__ d_delta_y,
+                                                             SeedArg seed_, float* __restrict__ d_delta_y,
                                                              float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const uint64_t seed = resolve_seed(seed_);
   const int lane = threadIdx.x & 31;
   const int rows = B * T;
   const float inv_keep = inv_keep_from_thr(thr);
@@ -322,7 +338,7 @@ extern "C" int immtsf_xattn_tail_fwd(const float* Y, const float* delta_y, const
   IMMTSF_REQUIRE(Y && delta_y && gamma && beta && m_txt && Y_out && C >= 1, "xattn_tail_fwd: bad args");
   int grid = ceil_div(B * T, 8);
   if (grid > 148 * 8) grid = 148 * 8;
-  xattn_tail_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(Y, delta_y, gamma, beta, m_txt, B, T, C, eps, kappa, drop_thr, seed, Y_out, flags);
+  xattn_tail_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(Y, delta_y, gamma, beta, m_txt, B, T, C, eps, kappa, drop_thr, make_seed(seed), Y_out, flags);
   IMMTSF_CHECK_LAUNCH("xattn_tail_fwd");
   return IMMTSF_OK;
 }
@@ -334,7 +350,7 @@ extern "C" int immtsf_xattn_tail_bwd(const float* dY_out, const float* delta_y, 
   IMMTSF_REQUIRE(dY_out && delta_y && gamma && m_txt && d_delta_y && dgamma && dbeta && C >= 1 && C <= 128, "xattn_tail_bwd: C must be in [1,128]");
   int grid = ceil_div(B * T, 8);
   if (grid > 148 * 4) grid = 148 * 4;
-  xattn_tail_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dY_out, delta_y, gamma, m_txt, B, T, C, eps, kappa, drop_thr, seed, d_delta_y, dgamma, dbeta);
+  xattn_tail_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dY_out, delta_y, gamma, m_txt, B, T, C, eps, kappa, drop_thr, make_seed(seed), d_delta_y, dgamma, dbeta);
   IMMTSF_CHECK_LAUNCH("xattn_tail_bwd");
   return IMMTSF_OK;
 }

@@ -1,0 +1,249 @@
+// K6 fast path: MMF_XAttn_Add attention core for T <= 32 query/key times
+// (fusions/MMF_XAttn_Add.py:73-80 + the softmax/dropout/bmm inside
+// nn.MultiheadAttention).  Time-IMM prediction windows are 7..28 steps, so the
+// whole T x T score matrix of one (sample, head) lives in registers/shared
+// memory of ONE CTA and q, k, v, o are each read or written exactly once:
+//
+//   S = scale * Q K^T : Q and K are staged through shared memory in chunks of
+//       XS_DC columns; each of the 8 warps owns an XS_DC/8-wide slice of the
+//       contraction and a full T x T partial (lane = 4 x 8 register tile),
+//       partials are summed across warps through shared memory.
+//   softmax over keys, dropout on the weights (Philox, same indices as the
+//       general kernel), probabilities saved for backward.
+//   O = P~ V          : one thread per float4 column, 16 query rows of
+//       accumulators at a time, V streamed with 128-bit loads.
+// Backward mirrors it: dP = dO V^T with the same routine, softmax backward in
+// shared memory, then dQ = dS K, dK = dS^T Q, dV = P~^T dO as three streamed
+// passes with register accumulators -- no read-modify-write of global memory.
+//
+// HBM-bound: algorithmic bytes per (sample, head) 4*4*T*hd forward (q,k,v in,
+// o out) and 4*7*T*hd backward, against 4*T*T*hd FLOP -- intensity T/4 FLOP/B.
+#include "rowtile.cuh"
+#include "../../include/immtsf.h"
+
+namespace {
+
+constexpr int XS_T = 32;     // max T
+constexpr int XS_DC = 512;   // contraction chunk staged in shared memory
+constexpr int XS_LD = XS_DC + 4;
+constexpr int XS_RH = 16;    // rows of float4 accumulators per pass
+
+struct XsArgs {
+  const float* q; int ldq; const float* k; int ldk; const float* v; int ldv;
+  const uint8_t* m_txt; int B, T, H, hd; uint32_t thr; SeedArg seed; float scale;
+  float* o; int ldo; float* probs;
+  const float* d_o; int lddo; float* dq; int lddq; float* dk; int lddk; float* dv; int lddv;
+};
+
+// S[i][j] = sum_c X[i][c] * Y[j][c] over c in [0, hd): result (unscaled) in s_out[XS_T*XS_T] (row stride XS_T).
+// X, Y: global [T][ld] row pointers of this (sample, head).  s_x, s_y: [XS_T][XS_LD] staging; s_part: [8][XS_T*XS_T].
+__device__ __forceinline__ void tile_xyt(const float* __restrict__ X, int ldx, const float* __restrict__ Y, int ldy, int T, int hd,
+                                         float* s_x, float* s_y, float* s_part, float* s_out) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int ib = lane >> 2, jb = lane & 3;  // rows ib*4 + a (a < 4), cols b*4 + jb (b < 8): conflict-free LDS.128
+  float acc[4][8];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 8; ++b) acc[a][b] = 0.f;
+  for (int c0 = 0; c0 < hd; c0 += XS_DC) {
+    const int cw = min(XS_DC, hd - c0), cw4 = cw >> 2;
+    __syncthreads();  // previous chunk consumed
+    for (int i = threadIdx.x; i < XS_T * (XS_DC / 4); i += blockDim.x) {
+      const int r = i / (XS_DC / 4), c4 = i % (XS_DC / 4);
+      float4 xv = f4_zero(), yv = f4_zero();
+      if (r < T && c4 < cw4) {
+        xv = __ldg(reinterpret_cast<const float4*>(X + (size_t)r * ldx + c0) + c4);
+        yv = __ldg(reinterpret_cast<const float4*>(Y + (size_t)r * ldy + c0) + c4);
+      }
+      *reinterpret_cast<float4*>(s_x + r * XS_LD + c4 * 4) = xv;
+      *reinterpret_cast<float4*>(s_y + r * XS_LD + c4 * 4) = yv;
+    }
+    __syncthreads();
+    const int sl0 = w * (XS_DC / 8);
+#pragma unroll 4
+    for (int c = sl0; c < sl0 + XS_DC / 8; c += 4) {
+      float4 xa[4], yb[8];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) xa[a] = *reinterpret_cast<const float4*>(s_x + (ib * 4 + a) * XS_LD + c);
+#pragma unroll
+      for (int b = 0; b < 8; ++b) yb[b] = *reinterpret_cast<const float4*>(s_y + (b * 4 + jb) * XS_LD + c);
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b)
+          acc[a][b] = fmaf(xa[a].x, yb[b].x, fmaf(xa[a].y, yb[b].y, fmaf(xa[a].z, yb[b].z, fmaf(xa[a].w, yb[b].w, acc[a][b]))));
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 8; ++b) s_part[w * (XS_T * XS_T) + (ib * 4 + a) * XS_T + b * 4 + jb] = acc[a][b];
+  __syncthreads();
+  for (int i = threadIdx.x; i < XS_T * XS_T; i += blockDim.x) {
+    float s = 0.f;
+#pragma unroll
+    for (int ww = 0; ww < 8; ++ww) s += s_part[ww * (XS_T * XS_T) + i];
+    s_out[i] = s;
+  }
+  __syncthreads();
+}
+
+// out[i][:] = sum_j W[i][j] * V[j][:]  for i in [0,T) -- W in shared memory (row stride XS_T), V/out global.
+// transposed = true uses W[j][i] instead (dK = dS^T Q, dV = P~^T dO).
+template <bool TRANSPOSED>
+__device__ __forceinline__ void tile_wv(const float* s_w, const float* __restrict__ V, int ldv, float* __restrict__ out, int ldo,
+                                        int T, int hd) {
+  const int hd4 = hd >> 2;
+  for (int c4 = threadIdx.x; c4 < hd4; c4 += blockDim.x) {
+    for (int i0 = 0; i0 < T; i0 += XS_RH) {
+      float4 acc[XS_RH];
+#pragma unroll
+      for (int a = 0; a < XS_RH; ++a) acc[a] = f4_zero();
+      for (int j = 0; j < T; ++j) {
+        const float4 vv = __ldg(reinterpret_cast<const float4*>(V + (size_t)j * ldv) + c4);
+#pragma unroll
+        for (int a = 0; a < XS_RH; ++a) {
+          const float wgt = TRANSPOSED ? s_w[j * XS_T + i0 + a] : s_w[(i0 + a) * XS_T + j];
+          f4_fma(acc[a], wgt, vv);
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < XS_RH; ++a)
+        if (i0 + a < T) reinterpret_cast<float4*>(out + (size_t)(i0 + a) * ldo)[c4] = acc[a];
+    }
+  }
+}
+
+constexpr size_t XS_SMEM = (size_t)(2 * XS_T * XS_LD + 8 * XS_T * XS_T + 2 * XS_T * XS_T) * sizeof(float);
+
+__global__ void __launch_bounds__(256) xattn_small_fwd_kernel(const XsArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  float* s_x = smem;
+  float* s_y = s_x + XS_T * XS_LD;
+  float* s_part = s_y + XS_T * XS_LD;
+  float* s_s = s_part + 8 * XS_T * XS_T;  // scores -> dropped probabilities
+  const int T = a.T, hd = a.hd, H = a.H;
+  const int bh = blockIdx.x, b = bh / H, h = bh % H;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const size_t rbase = (size_t)b * T;
+  float* o = a.o + rbase * a.ldo + h * hd;
+  if (a.m_txt[b] == 0) {  // every key masked: the reference overwrites the NaN output with zeros (:79-80)
+    for (int i = 0; i < T; ++i)
+      for (int c = threadIdx.x; c < hd; c += blockDim.x) o[(size_t)i * a.ldo + c] = 0.f;
+    if (a.probs)
+      for (int i = threadIdx.x; i < T * T; i += blockDim.x) a.probs[((size_t)b * H + h) * T * T + i] = 0.f;
+    return;
+  }
+  tile_xyt(a.q + rbase * a.ldq + h * hd, a.ldq, a.k + rbase * a.ldk + h * hd, a.ldk, T, hd, s_x, s_y, s_part, s_s);
+  const float inv_keep = inv_keep_from_thr(a.thr);
+  for (int i = w; i < T; i += 8) {  // softmax of row i, then dropout on the weights
+    const float sv = lane < T ? a.scale * s_s[i * XS_T + lane] : -INFINITY;
+    const float mx = warp_max(sv);
+    const float e = lane < T ? expf(sv - mx) : 0.f;
+    const float sum = warp_sum(e);
+    if (lane < T) {
+      const float p = e / sum;
+      const size_t pidx = (((size_t)b * H + h) * T + i) * T + lane;
+      if (a.probs) a.probs[pidx] = p;
+      s_s[i * XS_T + lane] = p * dropout_scale(resolve_seed(a.seed), IMMTSF_SITE_MMF_ATTN, pidx, a.thr, inv_keep);
+    } else {
+      s_s[i * XS_T + lane] = 0.f;
+    }
+  }
+  for (int i = T * XS_T + threadIdx.x; i < XS_T * XS_T; i += blockDim.x) s_s[i] = 0.f;  // rows >= T
+  __syncthreads();
+  tile_wv<false>(s_s, a.v + rbase * a.ldv + h * hd, a.ldv, o, a.ldo, T, hd);
+}
+
+__global__ void __launch_bounds__(256) xattn_small_bwd_kernel(const XsArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  float* s_x = smem;
+  float* s_y = s_x + XS_T * XS_LD;
+  float* s_part = s_y + XS_T * XS_LD;
+  float* s_ds = s_part + 8 * XS_T * XS_T;  // dP -> dS (with the q scale folded in)
+  float* s_pt = s_ds + XS_T * XS_T;        // P~ = P * keep / (1-p)
+  const int T = a.T, hd = a.hd, H = a.H;
+  const int bh = blockIdx.x, b = bh / H, h = bh % H;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const size_t rbase = (size_t)b * T;
+  float* dq = a.dq + rbase * a.lddq + h * hd;
+  float* dk = a.dk + rbase * a.lddk + h * hd;
+  float* dv = a.dv + rbase * a.lddv + h * hd;
+  if (a.m_txt[b] == 0) {
+    for (int i = 0; i < T; ++i)
+      for (int c = threadIdx.x; c < hd; c += blockDim.x) {
+        dq[(size_t)i * a.lddq + c] = 0.f;
+        dk[(size_t)i * a.lddk + c] = 0.f;
+        dv[(size_t)i * a.lddv + c] = 0.f;
+      }
+    return;
+  }
+  const float* go = a.d_o + rbase * a.lddo + h * hd;
+  const float* qp = a.q + rbase * a.ldq + h * hd;
+  const float* kp = a.k + rbase * a.ldk + h * hd;
+  const float* vp = a.v + rbase * a.ldv + h * hd;
+  tile_xyt(go, a.lddo, vp, a.ldv, T, hd, s_x, s_y, s_part, s_ds);  // dP~[i][j] = dO_i . v_j
+  const float inv_keep = inv_keep_from_thr(a.thr);
+  for (int i = w; i < XS_T; i += 8) {
+    float p = 0.f, dp = 0.f, ks = 0.f;
+    if (i < T && lane < T) {
+      const size_t pidx = (((size_t)b * H + h) * T + i) * T + lane;
+      ks = dropout_scale(resolve_seed(a.seed), IMMTSF_SITE_MMF_ATTN, pidx, a.thr, inv_keep);
+      p = a.probs[pidx];
+      dp = s_ds[i * XS_T + lane] * ks;
+    }
+    const float D = warp_sum(p * dp);
+    s_ds[i * XS_T + lane] = a.scale * p * (dp - D);
+    s_pt[i * XS_T + lane] = p * ks;
+  }
+  __syncthreads();
+  tile_wv<false>(s_ds, kp, a.ldk, dq, a.lddq, T, hd);  // dQ = dS K
+  tile_wv<true>(s_ds, qp, a.ldq, dk, a.lddk, T, hd);   // dK = dS^T Q
+  tile_wv<true>(s_pt, go, a.lddo, dv, a.lddv, T, hd);  // dV = P~^T dO
+}
+
+inline bool al16(const void* p, int ld) { return ((uintptr_t)p & 15) == 0 && (ld & 3) == 0; }
+
+}  // namespace
+
+// 1 if the small-T kernels apply to this problem
+int immtsf_xattn_small_ok(int T, int H, int d) { return T >= 1 && T <= XS_T && H >= 1 && d % H == 0 && ((d / H) & 3) == 0; }
+
+int immtsf_xattn_small_fwd(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, const uint8_t* m_txt, int B,
+                           int T, int H, int d, uint32_t drop_thr, uint64_t seed, float* o, int ldo, float* probs,
+                           cudaStream_t st) {
+  IMMTSF_REQUIRE(al16(q, ldq) && al16(k, ldk) && al16(v, ldv) && al16(o, ldo), "xattn_core_fwd: operands must be 16B aligned with ld %% 4 == 0");
+  XsArgs a = {};
+  a.q = q; a.ldq = ldq; a.k = k; a.ldk = ldk; a.v = v; a.ldv = ldv; a.m_txt = m_txt; a.B = B; a.T = T; a.H = H; a.hd = d / H;
+  a.thr = drop_thr; a.seed = make_seed(seed); a.scale = (float)sqrt(1.0 / (double)(d / H)); a.o = o; a.ldo = ldo; a.probs = probs;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(xattn_small_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XS_SMEM);
+    cudaFuncSetAttribute(xattn_small_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XS_SMEM);
+    attr = true;
+  }
+  xattn_small_fwd_kernel<<<B * H, 256, XS_SMEM, st>>>(a);
+  IMMTSF_CHECK_LAUNCH("xattn_small_fwd");
+  return IMMTSF_OK;
+}
+
+int immtsf_xattn_small_bwd(const float* d_o, int lddo, const float* q, int ldq, const float* k, int ldk, const float* v, int ldv,
+                           const float* probs, const uint8_t* m_txt, int B, int T, int H, int d, uint32_t drop_thr,
+                           uint64_t seed, float* dq, int lddq, float* dk, int lddk, float* dv, int lddv, cudaStream_t st) {
+  IMMTSF_REQUIRE(al16(d_o, lddo) && al16(q, ldq) && al16(k, ldk) && al16(v, ldv) && al16(dq, lddq) && al16(dk, lddk) && al16(dv, lddv),
+                 "xattn_core_bwd: operands must be 16B aligned with ld %% 4 == 0");
+  XsArgs a = {};
+  a.q = q; a.ldq = ldq; a.k = k; a.ldk = ldk; a.v = v; a.ldv = ldv; a.m_txt = m_txt; a.B = B; a.T = T; a.H = H; a.hd = d / H;
+  a.thr = drop_thr; a.seed = make_seed(seed); a.scale = (float)sqrt(1.0 / (double)(d / H)); a.probs = const_cast<float*>(probs);
+  a.d_o = d_o; a.lddo = lddo; a.dq = dq; a.lddq = lddq; a.dk = dk; a.lddk = lddk; a.dv = dv; a.lddv = lddv;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(xattn_small_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XS_SMEM);
+    cudaFuncSetAttribute(xattn_small_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XS_SMEM);
+    attr = true;
+  }
+  xattn_small_bwd_kernel<<<B * H, 256, XS_SMEM, st>>>(a);
+  IMMTSF_CHECK_LAUNCH("xattn_small_bwd");
+  return IMMTSF_OK;
+}

@@ -58,7 +58,8 @@ class FusionModel(nn.Module):
                 raise ValueError("Y_out contains NaN values.")
             return Y_out
         flags = runtime.new_flags(Y_ts.device)
-        check = runtime.nan_check_enabled()
+        self._last_flags = flags  # read by runtime.GraphedStep.check_nan()
+        check = runtime.nan_flags_enabled()
         Y32 = cm.as_f32(Y_ts)
         if check:
             ops.nan_check(Y32, flags, ops.FLAG_Y)

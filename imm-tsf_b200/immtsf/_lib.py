@@ -24,10 +24,17 @@ SZ = C.c_size_t
 SIGNATURES = {
     "immtsf_version": [],
     "immtsf_device_supported": [I],
+    "immtsf_set_seed_offset_ptr": [P],
+    "immtsf_seed_advance": [P, U64, P],
+    "immtsf_profile_begin": [I],
+    "immtsf_profile_end": [P, P, P, P, P, I],
     "immtsf_csr_build": [P, P, I, I, I, P, P, P, P, P, P, P, P, I, P],
     "immtsf_nan_check": [P, SZ, P, I, P],
     "immtsf_zero_pad_rows": [P, I, I, P, I, P],
     "immtsf_gemm": [I, I, I, I, I, F, P, I, P, I, F, P, I, P, P, I, I, P, SZ, P],
+    "immtsf_gemm_ex": [I, I, I, I, I, F, P, I, P, I, P, I, P, I, F, P, I, P, P, I, I, P, SZ, P],
+    "immtsf_split_lo": [P, I, I, I, P, I, P, P],
+    "immtsf_gemm_plan": [I, I, I, I, I, P, I, P, I, P, I, I],
     "immtsf_colsum": [P, I, I, I, P, F, P, P, SZ, P],
     "immtsf_recavg_pool_fwd": [P, I, P, P, P, I, P, P, P, I, I, I, F, U32, U64, P, P, P, P, P, P],
     "immtsf_recavg_pool_bwd": [P, P, P, P, P, P, I, P, P, P, I, P, P, I, I, I, U32, U64, P, I, P, P, P, P],
@@ -35,8 +42,8 @@ SIGNATURES = {
     "immtsf_time2vec_bwd": [P, I, P, P, P, I, P, P, P, P, P, I, P],
     "immtsf_segattn_fwd": [P, P, P, I, I, I, I, I, I, U32, U64, P, P, P],
     "immtsf_segattn_bwd": [P, P, P, P, P, I, I, I, I, I, I, U32, U64, P, P, P],
-    "immtsf_ln_fwd": [P, I, P, P, I, P, P, I, I, F, U32, U64, U32, P, P, P, P],
-    "immtsf_ln_bwd": [P, P, I, P, P, I, P, P, P, I, I, U32, U64, U32, P, P, P, P, P],
+    "immtsf_ln_fwd": [P, I, P, P, P, I, P, P, I, I, F, U32, U64, U32, P, P, P, P],
+    "immtsf_ln_bwd": [P, P, I, P, P, P, I, P, P, P, I, I, U32, U64, U32, P, P, P, P, P],
     "immtsf_gru_scan_fwd": [P, P, P, I, I, I, P, P, P],
     "immtsf_gr_tail_fwd": [P, P, P, P, P, P, P, P, I, I, I, F, U32, U64, P, P, P],
     "immtsf_gr_tail_bwd": [P, P, P, P, P, P, P, P, I, I, I, F, U32, U64, P, P, P, P, P, P],
@@ -83,6 +90,27 @@ def load():
 
 def launch_count() -> int:
     return int(load().immtsf_launch_count())
+
+
+def profile_gemm_tc(max_records: int = 4096):
+    """Context manager: device time of every gemm_tc_kernel launch inside the block -> list of (M, N, K, ragged_dim, ms)."""
+    import contextlib
+
+    @contextlib.contextmanager
+    def cm():
+        lib = load()
+        out = []
+        if lib.immtsf_profile_begin(max_records) != 0:
+            raise ImmtsfError("immtsf_profile_begin failed")
+        try:
+            yield out
+        finally:
+            IA, FA = C.c_int * max_records, C.c_float * max_records
+            m, n, k, rd, ms = IA(), IA(), IA(), IA(), FA()
+            cnt = lib.immtsf_profile_end(m, n, k, rd, ms, max_records)
+            out.extend((m[i], n[i], k[i], rd[i], ms[i]) for i in range(cnt))
+
+    return cm()
 
 
 def call(name, *args):

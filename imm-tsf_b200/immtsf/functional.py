@@ -30,34 +30,41 @@ class RecAvgFn(torch.autograd.Function):
     def forward(ctx, r: RaggedNotes, t_hat, T, thr, seed, save, log_sigma, W_in, b_in, gamma, beta, W_p, b_p):
         B = r.B
         d = W_p.shape[0]
-        Vp = ops.linear_fwd(r.emb_flat, W_in, b_in, ragged=r.m_dev) if W_in is not None else r.emb_flat
+        lo = ops.LoCache()
+        Vp = ops.linear_fwd(r.emb_flat, W_in, b_in, ragged=r.m_dev, lo=lo) if W_in is not None else r.emb_flat
         E_drop, E_raw, mean, rstd, wsum = ops.recavg_pool_fwd(Vp, r, t_hat, log_sigma, gamma, beta, T, d, thr, seed, save)
-        E_txt = ops.linear_fwd(E_drop.view(B * T, d), W_p, b_p).view(B, T, d)
+        E_txt = ops.linear_fwd(E_drop.view(B * T, d), W_p, b_p, lo=lo).view(B, T, d)
         if save:
-            ctx.r, ctx.T, ctx.thr, ctx.seed, ctx.has_in = r, T, thr, seed, W_in is not None
+            ctx.r, ctx.T, ctx.thr, ctx.seed, ctx.has_in, ctx.lo = r, T, thr, seed, W_in is not None, lo
             ctx.save_for_backward(t_hat, log_sigma, W_in, gamma, W_p, Vp, E_drop, E_raw, mean, rstd, wsum)
         return E_txt
 
     @staticmethod
     def backward(ctx, dE_txt):
         t_hat, log_sigma, W_in, gamma, W_p, Vp, E_drop, E_raw, mean, rstd, wsum = ctx.saved_tensors
-        r, T = ctx.r, ctx.T
+        r, T, lo = ctx.r, ctx.T, ctx.lo
+        ctx.lo = None
         B, d = r.B, W_p.shape[0]
         dE = dE_txt.contiguous().view(B * T, d)
-        dW_p = ops.linear_wgrad(dE, E_drop.view(B * T, d))
+        dW_p = ops.linear_wgrad(dE, E_drop.view(B * T, d), lo=lo)
         db_p = ops.colsum(dE)
-        dE_drop = ops.linear_dgrad(dE, W_p)
+        dE_drop = ops.linear_dgrad(dE, W_p, lo=lo)
         dVp, dgamma, dbeta, dls = ops.recavg_pool_bwd(dE_drop, E_raw, mean, rstd, wsum, Vp, r, t_hat, log_sigma, gamma, T, d,
                                                       ctx.thr, ctx.seed)
         dW_in = db_in = None
         if ctx.has_in:
-            dW_in = ops.linear_wgrad(dVp, r.emb_flat, ragged=r.m_dev)
+            dW_in = ops.linear_wgrad(dVp, r.emb_flat, ragged=r.m_dev, lo=lo)
             db_in = ops.colsum(dVp, ragged=r.m_dev)
         return None, None, None, None, None, None, dls, dW_in, db_in, dgamma, dbeta, dW_p, db_p
 
 
 # ============================================================== TTF_T2V_XAttn
 class T2VXAttnFn(torch.autograd.Function):
+    """TTF_T2V_XAttn.py:93-184.  K/V projections run once per note.  With one head and attention dropout (train mode:
+    every (sample, query) row is distinct) the MHA out-projection is folded into the value projection in weight
+    space -- sum_n p_n (v_n W_o^T) = (sum_n p_n v_n) W_o^T -- so it also runs once per note instead of once per
+    (sample, query) row; its bias is added inside the LayerNorm kernel (xbias)."""
+
     @staticmethod
     def forward(ctx, r: RaggedNotes, T, H, thr, seed, save, Qp, W_in, b_in, w_lin, b_lin, w_per, b_per, W_kv, b_kv,
                 in_w, in_b, out_w, out_b, gamma, beta, W_po, b_po):
@@ -65,71 +72,100 @@ class T2VXAttnFn(torch.autograd.Function):
         d = W_po.shape[0]
         dt = d // 2
         dev = Qp.device
+        new = lambda *s: torch.empty(*s, dtype=_f32, device=dev)
+        lo = ops.LoCache()
         per_query = thr != 0  # attention dropout makes every (sample, query) row distinct
+        fold = per_query and H == 1
         # [V' ; phi] concat buffer (TTF_T2V_XAttn.py:139), written in place by the two producers
-        Xcat = torch.empty(r.M_alloc, d + dt, dtype=_f32, device=dev)
+        Xcat = new(r.M_alloc, d + dt)
         if W_in is not None:
-            ops.gemm(r.emb_flat, W_in, Xcat[:, :d], transB=True, bias=b_in, ragged=r.m_dev, ragged_dim=1)
+            ops.gemm(r.emb_flat, W_in, Xcat[:, :d], transB=True, bias=b_in, ragged=r.m_dev, ragged_dim=1, lo=lo)
         else:
             Xcat[:, :d].copy_(r.emb_flat)
         ops.time2vec_fwd(r, w_lin, b_lin, w_per, b_per, dt, Xcat[:, d:])
-        X = ops.linear_fwd(Xcat, W_kv, b_kv, ragged=r.m_dev)  # :140
-        KVp = ops.linear_fwd(X, in_w[d:], in_b[d:], ragged=r.m_dev)  # MHA k/v in-projection, once per note
+        X = ops.linear_fwd(Xcat, W_kv, b_kv, ragged=r.m_dev, lo=lo)  # :140
+        if fold:
+            Wkv, bkv = new(2 * d, d), new(2 * d)
+            Wkv[:d].copy_(in_w[d:2 * d])
+            bkv[:d].copy_(in_b[d:2 * d])
+            ops.gemm(out_w, in_w[2 * d:], Wkv[d:], lo=lo)  # W_o W_v
+            ops.gemm(in_b[2 * d:].view(1, d), out_w, bkv[d:].view(1, d), transB=True)  # W_o b_v
+        else:
+            Wkv, bkv = in_w[d:], in_b[d:]
+        KVp = ops.linear_fwd(X, Wkv, bkv, ragged=r.m_dev, lo=lo)  # MHA k/v in-projection, once per note
         scale = math.sqrt(1.0 / float(d // H))
         q0 = ops.linear_fwd(Qp.view(1, d), in_w[:d], in_b[:d])
         q = ops.axpby(q0, scale, torch.empty_like(q0), False)
         attn_cat, probs = ops.segattn_fwd(q, KVp, r, T, H, d, per_query, thr, seed, save)
-        attn_out = ops.linear_fwd(attn_cat, out_w, out_b)
+        attn_out = attn_cat if fold else ops.linear_fwd(attn_cat, out_w, out_b, lo=lo)
         rps = T if per_query else 1
-        y, mean, rstd = ops.ln_fwd(attn_out, Qp.view(d), r.m_txt, rps, gamma, beta, thr, seed, ops.SITE_TTF_DROPOUT, save)
-        E = ops.linear_fwd(y, W_po, b_po)
+        y, mean, rstd = ops.ln_fwd(attn_out, Qp.view(d), r.m_txt, rps, gamma, beta, thr, seed, ops.SITE_TTF_DROPOUT, save,
+                                   xbias=out_b if fold else None)
+        E = ops.linear_fwd(y, W_po, b_po, lo=lo)
         if save:
-            ctx.r, ctx.T, ctx.H, ctx.thr, ctx.seed = r, T, H, thr, seed
-            ctx.has_in, ctx.per_query, ctx.scale = W_in is not None, per_query, scale
-            ctx.save_for_backward(Qp, w_per, b_per, W_kv, in_w, out_w, gamma, W_po, Xcat, X, KVp, q, attn_cat, probs,
-                                  attn_out, y, mean, rstd)
+            ctx.r, ctx.T, ctx.H, ctx.thr, ctx.seed, ctx.lo = r, T, H, thr, seed, lo
+            ctx.has_in, ctx.per_query, ctx.scale, ctx.fold = W_in is not None, per_query, scale, fold
+            ctx.save_for_backward(Qp, w_per, b_per, W_kv, in_w, in_b, out_w, out_b, gamma, W_po, Xcat, X, Wkv, KVp, q, attn_cat,
+                                  probs, attn_out, y, mean, rstd)
         return E.view(B, T, d) if per_query else E.view(B, 1, d).expand(B, T, d)
 
     @staticmethod
     def backward(ctx, dE_txt):
-        (Qp, w_per, b_per, W_kv, in_w, out_w, gamma, W_po, Xcat, X, KVp, q, attn_cat, probs, attn_out, y, mean,
-         rstd) = ctx.saved_tensors
-        r, T, H, thr, seed = ctx.r, ctx.T, ctx.H, ctx.thr, ctx.seed
+        (Qp, w_per, b_per, W_kv, in_w, in_b, out_w, out_b, gamma, W_po, Xcat, X, Wkv, KVp, q, attn_cat, probs, attn_out, y,
+         mean, rstd) = ctx.saved_tensors
+        r, T, H, thr, seed, lo, fold = ctx.r, ctx.T, ctx.H, ctx.thr, ctx.seed, ctx.lo, ctx.fold
+        ctx.lo = None
         B, d = r.B, W_po.shape[0]
         dt = d // 2
+        dev = Qp.device
+        new = lambda *s: torch.empty(*s, dtype=_f32, device=dev)
         per_query = ctx.per_query
         dEc = dE_txt.contiguous()
         dE = dEc.view(B * T, d) if per_query else ops.group_sum_rows(dEc.view(B * T, d), B, T, d)
-        dW_po = ops.linear_wgrad(dE, y)
+        dW_po = ops.linear_wgrad(dE, y, lo=lo)
         db_po = ops.colsum(dE)
-        dy = ops.linear_dgrad(dE, W_po)
+        dy = ops.linear_dgrad(dE, W_po, lo=lo)
         rps = T if per_query else 1
         dx, dres, dgamma, dbeta = ops.ln_bwd(dy, attn_out, Qp.view(d), r.m_txt, rps, gamma, mean, rstd, thr, seed,
-                                             ops.SITE_TTF_DROPOUT)
-        dW_o = ops.linear_wgrad(dx, attn_cat)
+                                             ops.SITE_TTF_DROPOUT, xbias=out_b if fold else None)
         db_o = ops.colsum(dx)
-        d_attn_cat = ops.linear_dgrad(dx, out_w)
+        if fold:
+            d_attn_cat = dx
+        else:
+            dW_o = ops.linear_wgrad(dx, attn_cat, lo=lo)
+            d_attn_cat = ops.linear_dgrad(dx, out_w, lo=lo)
         dKVp, dq_partial = ops.segattn_bwd(d_attn_cat, q, KVp, probs, r, T, H, d, per_query, thr, seed)
         # query path: q = (Qp W_q^T + b_q) * scale
         dq = ops.colsum(dq_partial)
         dq_pre = ops.axpby(dq, ctx.scale, torch.empty_like(dq), False).view(1, d)
         d_in_w = torch.empty_like(in_w)
-        d_in_b = torch.empty(3 * d, dtype=_f32, device=in_w.device)
+        d_in_b = new(3 * d)
         ops.linear_wgrad(dq_pre, Qp.view(1, d), out=d_in_w[:d])
         d_in_b[:d].copy_(dq_pre.view(d))
         dQp = ops.linear_dgrad(dq_pre, in_w[:d])  # [1,d]
         ops.axpby(dres, 1.0, dQp.view(d), True)
         # key/value path, once per note
-        ops.linear_wgrad(dKVp, X, out=d_in_w[d:], ragged=r.m_dev)
-        ops.colsum(dKVp, out=d_in_b[d:], ragged=r.m_dev)
-        dX = ops.linear_dgrad(dKVp, in_w[d:], ragged=r.m_dev)
-        dW_kv = ops.linear_wgrad(dX, Xcat, ragged=r.m_dev)
+        if fold:
+            dWkv = ops.linear_wgrad(dKVp, X, ragged=r.m_dev, lo=lo)  # [2d, d]: rows [d,2d) are d(W_o W_v)
+            dbkv = ops.colsum(dKVp, ragged=r.m_dev)
+            d_in_w[d:2 * d].copy_(dWkv[:d])
+            d_in_b[d:2 * d].copy_(dbkv[:d])
+            # un-fold W_f = W_o W_v, b_f = W_o b_v
+            dW_o = ops.gemm(dWkv[d:], in_w[2 * d:], new(d, d), transB=True, lo=lo)
+            ops.gemm(dbkv[d:].view(d, 1), in_b[2 * d:].view(1, d), dW_o, beta=1.0)
+            ops.gemm(out_w, dWkv[d:], d_in_w[2 * d:], transA=True, lo=lo)
+            ops.gemm(dbkv[d:].view(1, d), out_w, d_in_b[2 * d:].view(1, d))
+        else:
+            ops.linear_wgrad(dKVp, X, out=d_in_w[d:], ragged=r.m_dev, lo=lo)
+            ops.colsum(dKVp, out=d_in_b[d:], ragged=r.m_dev)
+        dX = ops.linear_dgrad(dKVp, Wkv, ragged=r.m_dev, lo=lo)
+        dW_kv = ops.linear_wgrad(dX, Xcat, ragged=r.m_dev, lo=lo)
         db_kv = ops.colsum(dX, ragged=r.m_dev)
-        dXcat = ops.linear_dgrad(dX, W_kv, ragged=r.m_dev)
+        dXcat = ops.linear_dgrad(dX, W_kv, ragged=r.m_dev, lo=lo)
         dwl, dbl, dwp, dbp = ops.time2vec_bwd(dXcat[:, d:], r, w_per, b_per, dt)
         dW_in = db_in = None
         if ctx.has_in:
-            dW_in = ops.linear_wgrad(dXcat[:, :d], r.emb_flat, ragged=r.m_dev)
+            dW_in = ops.linear_wgrad(dXcat[:, :d], r.emb_flat, ragged=r.m_dev, lo=lo)
             db_in = ops.colsum(dXcat[:, :d], ragged=r.m_dev)
         return (None, None, None, None, None, None, dQp.view(1, 1, d), dW_in, db_in, dwl, dbl, dwp, dbp, dW_kv, db_kv,
                 d_in_w, d_in_b, dW_o, db_o, dgamma, dbeta, dW_po, db_po)
@@ -190,65 +226,76 @@ class GRAddFn(torch.autograd.Function):
 
 # ============================================================== MMF_XAttn_Add
 class XAttnAddFn(torch.autograd.Function):
+    """MMF_XAttn_Add.py:56-103.  The reference chains two bias-free projections into each MHA in-projection
+    (proj_q -> in_proj_q, proj_k -> in_proj_k, proj_v -> in_proj_v, :68-76) and the MHA out-projection into
+    residual_head (:76,:83).  Consecutive linear maps are folded in WEIGHT space -- (E W_K^T) W_k^T = E (W_k W_K)^T --
+    so the per-row work is one [B*T, d_txt] x [d_txt, 2d] projection instead of six d x d ones; the folds are d^3
+    (or rank-C) products, and backward un-folds the weight gradients the same way (the chain rule of the fold)."""
+
     @staticmethod
     def forward(ctx, Y, E, m_txt, H, kappa, thr, seed, save, flags, W_Q, W_K, W_V, in_w, in_b, out_w, out_b, W_r, b_r,
                 gamma, beta):
         B, T, C = Y.shape
-        d = W_Q.shape[0]
+        d, de = W_Q.shape[0], E.shape[2]
+        dev = Y.device
         Y2 = Y.contiguous().view(B * T, C)
-        E2 = E.contiguous().view(B * T, E.shape[2])
-        Q0 = ops.linear_fwd(Y2, W_Q, None)  # :68
-        K0 = ops.linear_fwd(E2, W_K, None)  # :69
-        V0 = ops.linear_fwd(E2, W_V, None)  # :70
-        q = ops.linear_fwd(Q0, in_w[:d], in_b[:d])
-        k = ops.linear_fwd(K0, in_w[d:2 * d], in_b[d:2 * d])
-        v = ops.linear_fwd(V0, in_w[2 * d:], in_b[2 * d:])
-        o, probs = ops.xattn_core_fwd(q, k, v, m_txt, B, T, H, d, thr, seed, save)
-        ao = ops.linear_fwd(o, out_w, out_b)
-        delta_y = ops.linear_fwd(ao, W_r, b_r)  # :83
+        E2 = E.contiguous().view(B * T, de)
+        lo = ops.LoCache()
+        # ---- weight-space folds
+        Wq_f = ops.gemm(in_w[:d], W_Q, torch.empty(d, C, dtype=_f32, device=dev))  # [d, C]
+        Wkv_f = torch.empty(2 * d, de, dtype=_f32, device=dev)
+        ops.gemm(in_w[d:2 * d], W_K, Wkv_f[:d], lo=lo)
+        ops.gemm(in_w[2 * d:], W_V, Wkv_f[d:], lo=lo)
+        Wo_f = ops.gemm(W_r, out_w, torch.empty(C, d, dtype=_f32, device=dev))  # [C, d]
+        bo_f = ops.gemm(out_b.view(1, d), W_r, torch.empty(1, C, dtype=_f32, device=dev), transB=True, bias=b_r).view(C)
+        # ---- per-row work
+        q = ops.linear_fwd(Y2, Wq_f, in_b[:d])  # :68 + in_proj_q
+        kv = ops.linear_fwd(E2, Wkv_f, in_b[d:], lo=lo)  # :69-70 + in_proj_k / in_proj_v, E read once
+        o, probs = ops.xattn_core_fwd(q, kv[:, :d], kv[:, d:], m_txt, B, T, H, d, thr, seed, save)
+        delta_y = ops.linear_fwd(o, Wo_f, bo_f)  # out_proj + residual_head (:83)
         Y_out = ops.xattn_tail_fwd(Y2, delta_y, gamma, beta, m_txt, B, T, C, kappa, thr, seed, flags)
         if save:
-            ctx.H, ctx.kappa, ctx.thr, ctx.seed, ctx.dims = H, kappa, thr, seed, (B, T, C, d)
-            ctx.save_for_backward(m_txt, Y2, E2, W_Q, W_K, W_V, in_w, out_w, W_r, gamma, Q0, K0, V0, q, k, v, o, probs, ao,
+            ctx.H, ctx.kappa, ctx.thr, ctx.seed, ctx.dims, ctx.lo = H, kappa, thr, seed, (B, T, C, d, de), lo
+            ctx.save_for_backward(m_txt, Y2, E2, W_Q, W_K, W_V, in_w, out_w, out_b, W_r, gamma, Wq_f, Wkv_f, Wo_f, q, kv, o, probs,
                                   delta_y)
         return Y_out
 
     @staticmethod
     def backward(ctx, dY_out):
-        (m_txt, Y2, E2, W_Q, W_K, W_V, in_w, out_w, W_r, gamma, Q0, K0, V0, q, k, v, o, probs, ao,
+        (m_txt, Y2, E2, W_Q, W_K, W_V, in_w, out_w, out_b, W_r, gamma, Wq_f, Wkv_f, Wo_f, q, kv, o, probs,
          delta_y) = ctx.saved_tensors
-        B, T, C, d = ctx.dims
-        H, kappa, thr, seed = ctx.H, ctx.kappa, ctx.thr, ctx.seed
+        B, T, C, d, de = ctx.dims
+        H, kappa, thr, seed, lo = ctx.H, ctx.kappa, ctx.thr, ctx.seed, ctx.lo
+        ctx.lo = None
         dev = Y2.device
+        new = lambda *s: torch.empty(*s, dtype=_f32, device=dev)
         dY_out = dY_out.contiguous()
         d_delta, dgamma, dbeta = ops.xattn_tail_bwd(dY_out, delta_y, gamma, m_txt, B, T, C, kappa, thr, seed)
-        dW_r = ops.linear_wgrad(d_delta, ao)
-        db_r = ops.colsum(d_delta)
-        dao = ops.linear_dgrad(d_delta, W_r)
-        dW_o = ops.linear_wgrad(dao, o)
-        db_o = ops.colsum(dao)
-        do = ops.linear_dgrad(dao, out_w)
-        dq = torch.empty(B * T, d, dtype=_f32, device=dev)
-        dk = torch.empty(B * T, d, dtype=_f32, device=dev)
-        dv = torch.empty(B * T, d, dtype=_f32, device=dev)
-        ops.xattn_core_bwd(do, q, k, v, probs, m_txt, B, T, H, d, thr, seed, dq, dk, dv)
-        d_in_w = torch.empty_like(in_w)
-        d_in_b = torch.empty(3 * d, dtype=_f32, device=dev)
-        ops.linear_wgrad(dq, Q0, out=d_in_w[:d])
-        ops.linear_wgrad(dk, K0, out=d_in_w[d:2 * d])
-        ops.linear_wgrad(dv, V0, out=d_in_w[2 * d:])
+        # ---- folded out_proj + residual_head
+        dWo_f = ops.linear_wgrad(d_delta, o)  # [C, d]
+        db_r = ops.colsum(d_delta)  # d(bo_f) = d(b_r)
+        do = ops.linear_dgrad(d_delta, Wo_f)
+        dq, dkv = new(B * T, d), new(B * T, 2 * d)
+        ops.xattn_core_bwd(do, q, kv[:, :d], kv[:, d:], probs, m_txt, B, T, H, d, thr, seed, dq, dkv[:, :d], dkv[:, d:])
+        # ---- folded projections
+        d_in_w, d_in_b = torch.empty_like(in_w), new(3 * d)
+        dWq_f = ops.linear_wgrad(dq, Y2)  # [d, C]
         ops.colsum(dq, out=d_in_b[:d])
-        ops.colsum(dk, out=d_in_b[d:2 * d])
-        ops.colsum(dv, out=d_in_b[2 * d:])
-        dQ0 = ops.linear_dgrad(dq, in_w[:d])
-        dK0 = ops.linear_dgrad(dk, in_w[d:2 * d])
-        dV0 = ops.linear_dgrad(dv, in_w[2 * d:])
-        dW_Q = ops.linear_wgrad(dQ0, Y2)
-        dW_K = ops.linear_wgrad(dK0, E2)
-        dW_V = ops.linear_wgrad(dV0, E2)
-        dY = ops.axpby(dY_out.view(B * T, C), 1.0 / (1.0 + kappa), torch.empty(B * T, C, dtype=_f32, device=dev), False)
-        ops.linear_dgrad(dQ0, W_Q, out=dY, beta=1.0)
-        dE = ops.linear_dgrad(dK0, W_K)
-        ops.linear_dgrad(dV0, W_V, out=dE, beta=1.0)
-        return (dY.view(B, T, C), dE.view(B, T, E2.shape[1]), None, None, None, None, None, None, None, dW_Q, dW_K, dW_V,
+        dY = ops.axpby(dY_out.view(B * T, C), 1.0 / (1.0 + kappa), new(B * T, C), False)
+        ops.linear_dgrad(dq, Wq_f, out=dY, beta=1.0)
+        dWkv_f = ops.linear_wgrad(dkv, E2, lo=lo)  # [2d, de]
+        ops.colsum(dkv, out=d_in_b[d:])
+        dE = ops.linear_dgrad(dkv, Wkv_f, lo=lo)
+        # ---- un-fold the weight gradients: W_f = W_a W_b  =>  dW_a = dW_f W_b^T, dW_b = W_a^T dW_f
+        ops.gemm(dWq_f, W_Q, d_in_w[:d], transB=True)
+        dW_Q = ops.gemm(in_w[:d], dWq_f, new(d, C), transA=True)
+        ops.gemm(dWkv_f[:d], W_K, d_in_w[d:2 * d], transB=True, lo=lo)
+        dW_K = ops.gemm(in_w[d:2 * d], dWkv_f[:d], new(d, de), transA=True, lo=lo)
+        ops.gemm(dWkv_f[d:], W_V, d_in_w[2 * d:], transB=True, lo=lo)
+        dW_V = ops.gemm(in_w[2 * d:], dWkv_f[d:], new(d, de), transA=True, lo=lo)
+        dW_r = ops.gemm(dWo_f, out_w, new(C, d), transB=True)
+        ops.gemm(db_r.view(C, 1), out_b.view(1, d), dW_r, beta=1.0)  # bo_f = W_r b_o + b_r also depends on W_r
+        dW_o = ops.gemm(W_r, dWo_f, new(d, d), transA=True)
+        db_o = ops.gemm(db_r.view(1, C), W_r, new(1, d)).view(d)
+        return (dY.view(B, T, C), dE.view(B, T, de), None, None, None, None, None, None, None, dW_Q, dW_K, dW_V,
                 d_in_w, d_in_b, dW_o, db_o, dW_r, db_r, dgamma, dbeta)

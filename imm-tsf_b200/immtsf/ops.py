@@ -130,7 +130,25 @@ def _mat(t: torch.Tensor, name: str):
     return t
 
 
-def gemm(A, B, C, transA=False, transB=False, bias=None, alpha=1.0, beta=0.0, ragged=None, ragged_dim=0, backend=None):
+class LoCache(dict):
+    """Per-step cache of tcgen05 operand splits (lo = x - trunc_tf32(x)), keyed by the operand view.  Nearly every
+    operand of the path is used by two products (forward + weight gradient, or dgrad + wgrad); with a cache it is
+    split once.  Entries keep the source tensor alive so that a recycled allocation can never alias a stale entry."""
+
+    def lo_for(self, t: torch.Tensor, ragged: Optional[torch.Tensor]):
+        key = (t.data_ptr(), tuple(t.shape), t.stride(0), ragged is not None)
+        e = self.get(key)
+        if e is None:
+            rows, cols = t.shape
+            lo = torch.empty(rows, round_up(cols, 4), dtype=torch.float32, device=t.device)
+            _lib.call("immtsf_split_lo", _p(t), t.stride(0), rows, cols, _p(lo), lo.stride(0), _p(ragged), _stream())
+            e = (t, lo)
+            self[key] = e
+        return e[1]
+
+
+def gemm(A, B, C, transA=False, transB=False, bias=None, alpha=1.0, beta=0.0, ragged=None, ragged_dim=0, backend=None,
+         lo: Optional[LoCache] = None):
     """C[M,N] = alpha*op(A)*op(B) + beta*C + bias (shapes per include/immtsf.h)."""
     _mat(A, "A"), _mat(B, "B"), _mat(C, "C")
     M, N = C.shape
@@ -147,38 +165,47 @@ def gemm(A, B, C, transA=False, transB=False, bias=None, alpha=1.0, beta=0.0, ra
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
     be = gemm_backend() if backend is None else backend
+    lib = _lib.load()
     ws, ws_bytes = None, 0
     if be != BACKEND_FFMA:
-        ws_bytes = _lib.load().immtsf_gemm_workspace_bytes(int(transA), int(transB), M, N, K)
+        ws_bytes = lib.immtsf_gemm_workspace_bytes(int(transA), int(transB), M, N, K)
         ws = _workspace(C.device, ws_bytes)
         ws_bytes = ws.numel()
-    _lib.call("immtsf_gemm", int(transA), int(transB), M, N, K, float(alpha), _p(A), A.stride(0), _p(B), B.stride(0),
+    plan = lib.immtsf_gemm_plan(int(transA), int(transB), M, N, K, _p(A), A.stride(0), _p(B), B.stride(0), _p(C), C.stride(0), be)
+    A_lo = B_lo = None
+    if lo is not None and plan == 2:
+        a_ragged = ragged is not None and ((ragged_dim == 1 and not transA) or (ragged_dim == 2 and transA))
+        b_ragged = ragged is not None and (ragged_dim == 2 and not transB)
+        A_lo = lo.lo_for(A, ragged if a_ragged else None)
+        B_lo = lo.lo_for(B, ragged if b_ragged else None)
+    _lib.call("immtsf_gemm_ex", int(transA), int(transB), M, N, K, float(alpha), _p(A), A.stride(0), _p(A_lo),
+              A_lo.stride(0) if A_lo is not None else 0, _p(B), B.stride(0), _p(B_lo), B_lo.stride(0) if B_lo is not None else 0,
               float(beta), _p(C), C.stride(0), _p(bias), _p(ragged), ragged_dim, be, _p(ws), ws_bytes, _stream())
     if prof is not None:
         ev1.record()
-        prof.append(("gemm", (M, N, K, ragged_dim), ev0, ev1))
+        prof.append(("gemm", (M, N, K, ragged_dim), ev0, ev1, plan))
     return C
 
 
-def linear_fwd(x, w, b, out=None, ragged=None):
+def linear_fwd(x, w, b, out=None, ragged=None, lo=None):
     """out[M,N] = x[M,K] w[N,K]^T + b."""
     if out is None:
         out = torch.empty(x.shape[0], w.shape[0], dtype=torch.float32, device=x.device)
-    return gemm(x, w, out, transB=True, bias=b, ragged=ragged, ragged_dim=1 if ragged is not None else 0)
+    return gemm(x, w, out, transB=True, bias=b, ragged=ragged, ragged_dim=1 if ragged is not None else 0, lo=lo)
 
 
-def linear_dgrad(dy, w, out=None, ragged=None, beta=0.0):
+def linear_dgrad(dy, w, out=None, ragged=None, beta=0.0, lo=None):
     """dx[M,K] = dy[M,N] w[N,K]."""
     if out is None:
         out = torch.empty(dy.shape[0], w.shape[1], dtype=torch.float32, device=dy.device)
-    return gemm(dy, w, out, beta=beta, ragged=ragged, ragged_dim=1 if ragged is not None else 0)
+    return gemm(dy, w, out, beta=beta, ragged=ragged, ragged_dim=1 if ragged is not None else 0, lo=lo)
 
 
-def linear_wgrad(dy, x, out=None, ragged=None, beta=0.0):
+def linear_wgrad(dy, x, out=None, ragged=None, beta=0.0, lo=None):
     """dw[N,K] = dy[M,N]^T x[M,K]."""
     if out is None:
         out = torch.empty(dy.shape[1], x.shape[1], dtype=torch.float32, device=dy.device)
-    return gemm(dy, x, out, transA=True, beta=beta, ragged=ragged, ragged_dim=2 if ragged is not None else 0)
+    return gemm(dy, x, out, transA=True, beta=beta, ragged=ragged, ragged_dim=2 if ragged is not None else 0, lo=lo)
 
 
 def colsum(X, out=None, ragged=None, beta=0.0):
@@ -268,24 +295,24 @@ def segattn_bwd(d_attn_cat, q, KVp, probs, r: RaggedNotes, T, H, d, per_query, t
     return dKVp, dq_partial
 
 
-def ln_fwd(x, res, valid, rows_per_sample, gamma, beta, thr, seed, site, save):
+def ln_fwd(x, res, valid, rows_per_sample, gamma, beta, thr, seed, site, save, xbias=None):
     R, d = x.shape
     y = torch.empty(R, d, dtype=torch.float32, device=x.device)
     mean = torch.empty(R, dtype=torch.float32, device=x.device) if save else None
     rstd = torch.empty(R, dtype=torch.float32, device=x.device) if save else None
-    _lib.call("immtsf_ln_fwd", _p(x), x.stride(0), _p(res), _p(valid), rows_per_sample, _p(gamma), _p(beta), R, d, LN_EPS,
+    _lib.call("immtsf_ln_fwd", _p(x), x.stride(0), _p(xbias), _p(res), _p(valid), rows_per_sample, _p(gamma), _p(beta), R, d, LN_EPS,
               thr, seed, site, _p(y), _p(mean), _p(rstd), _stream())
     return y, mean, rstd
 
 
-def ln_bwd(dy, x, res, valid, rows_per_sample, gamma, mean, rstd, thr, seed, site):
+def ln_bwd(dy, x, res, valid, rows_per_sample, gamma, mean, rstd, thr, seed, site, xbias=None):
     R, d = x.shape
     dev = x.device
     dx = torch.empty(R, d, dtype=torch.float32, device=dev)
     dres = torch.zeros(d, dtype=torch.float32, device=dev) if res is not None else None
     dgamma = torch.zeros(d, dtype=torch.float32, device=dev)
     dbeta = torch.zeros(d, dtype=torch.float32, device=dev)
-    _lib.call("immtsf_ln_bwd", _p(dy), _p(x), x.stride(0), _p(res), _p(valid), rows_per_sample, _p(gamma), _p(mean), _p(rstd),
+    _lib.call("immtsf_ln_bwd", _p(dy), _p(x), x.stride(0), _p(xbias), _p(res), _p(valid), rows_per_sample, _p(gamma), _p(mean), _p(rstd),
               R, d, thr, seed, site, _p(dx), _p(dres), _p(dgamma), _p(dbeta), _stream())
     return dx, dres, dgamma, dbeta
 

@@ -23,10 +23,14 @@ _MESSAGES = {
 }
 
 
+def nan_flags_enabled() -> bool:
+    """Whether the flag-setting check kernels are launched at all (IMMTSF_NAN_CHECK=0 removes them)."""
+    return os.environ.get("IMMTSF_NAN_CHECK", "1") != "0"
+
+
 def nan_check_enabled() -> bool:
-    if os.environ.get("IMMTSF_NAN_CHECK", "1") == "0":
-        return False
-    return not torch.cuda.is_current_stream_capturing()
+    """Whether the flags are read back (a device->host sync) at the end of forward; never inside a graph capture."""
+    return nan_flags_enabled() and not torch.cuda.is_current_stream_capturing()
 
 
 def new_flags(device) -> torch.Tensor:
@@ -55,3 +59,93 @@ class SeedSource:
 
 
 SEEDS = SeedSource()
+
+
+class GraphedStep:
+    """One training step of the fusion path -- FusionModel forward, loss, backward (every parameter gradient and
+    dY_ts) -- captured ONCE in a CUDA graph and replayed with a single launch.
+
+    At Time-IMM batch sizes a step is ~140 kernel launches of a few microseconds each, so the eager path is bound
+    by host launch overhead, not by the GPU.  Capture removes that.  What stays dynamic: the ragged content (the
+    number of valid notes per sample lives on the device), the parameter values, and the dropout masks (the
+    by-value seeds are frozen in the graph, so the graph itself bumps a device-resident seed offset that every
+    kernel adds -- include/immtsf.h immtsf_set_seed_offset_ptr).  What is static: tensor shapes; build one
+    GraphedStep per (B, N_max, T) shape.
+
+        step = GraphedStep(fusion, example=(notes, tau, t_hat, Y_ts), loss_fn=lambda out, tgt, m: ..., extras=(tgt, m))
+        loss = step(notes, tau, t_hat, Y_ts, tgt, m)   # host (pinned) or device tensors; returns the static loss
+        step.dY_ts, step.Y_out, [p.grad for p in fusion.parameters()]   # refreshed by every call
+
+    The reference's NaN ValueErrors need a device->host read, which a graph cannot contain: call check_nan() after a
+    step when that guard is wanted (one sync)."""
+
+    def __init__(self, fusion, example, loss_fn=None, extras=(), warmup: int = 3):
+        from . import _lib
+
+        if not torch.cuda.is_available():
+            raise RuntimeError("GraphedStep needs a CUDA device -- the immtsf path has no CPU fallback")
+        self.fusion = fusion
+        self.loss_fn = loss_fn if loss_fn is not None else (lambda out, *_: out.square().mean())
+        dev = next(fusion.parameters()).device
+        self.static_in = [t.detach().to(dev, copy=True) for t in example]
+        self.static_in[3].requires_grad_(True)
+        self.static_extra = [t.detach().to(dev, copy=True) for t in extras]
+        self.params = [p for p in fusion.parameters() if p.requires_grad]
+        self.seed_offset = torch.zeros(1, dtype=torch.int64, device=dev)
+        self._lib = _lib
+        _lib.call("immtsf_set_seed_offset_ptr", self.seed_offset.data_ptr())
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):  # warm-up off the capture stream: lazy allocations (workspaces) happen here
+            for _ in range(max(warmup, 1)):
+                self._eager()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        for p in self.params:
+            p.grad = None
+        self.static_in[3].grad = None
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            _lib.call("immtsf_seed_advance", self.seed_offset.data_ptr(), 1, ops._stream())
+            out, loss = self._eager()
+        self.Y_out, self.loss = out.detach(), loss.detach()
+        self.flags = getattr(fusion, "_last_flags", None)
+
+    def _eager(self):
+        out = self.fusion(self.static_in[0], self.static_in[1], self.static_in[2], self.static_in[3])
+        loss = self.loss_fn(out, *self.static_extra)
+        loss.backward()
+        return out, loss
+
+    @property
+    def dY_ts(self):
+        return self.static_in[3].grad
+
+    def __call__(self, notes, tau, t_hat, Y_ts, *extras):
+        with torch.no_grad():
+            for s, t in zip(self.static_in, (notes, tau, t_hat, Y_ts)):
+                if t is not s:
+                    s.copy_(t, non_blocking=True)
+            for s, t in zip(self.static_extra, extras):
+                if t is not s:
+                    s.copy_(t, non_blocking=True)
+        self.graph.replay()
+        return self.loss
+
+    def check_nan(self):
+        """The reference's ValueErrors (fusions/FusionModel.py:103-112) for the last replay; one device->host read."""
+        if self.flags is None:
+            return
+        host = self.flags.tolist()
+        for s in (ops.FLAG_Y, ops.FLAG_V, ops.FLAG_E, ops.FLAG_OUT):
+            if host[s]:
+                raise ValueError(_MESSAGES[s])
+
+    def close(self):
+        self._lib.call("immtsf_set_seed_offset_ptr", None)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -46,6 +46,19 @@ int immtsf_device_supported(int device);
 /* number of kernel launches issued by this library in this process (monotonic) */
 unsigned long long immtsf_launch_count(void);
 
+/* Dropout seeds are passed by value; when a device pointer is registered here (process-wide, NULL clears it)
+ * every kernel adds *dev_ptr to its seed argument at run time.  A CUDA graph that captured one training step
+ * (immtsf/runtime.py GraphedStep) bumps that word with immtsf_seed_advance inside the graph, so each replay
+ * draws fresh Philox masks although the by-value seeds are frozen in the graph. */
+int immtsf_set_seed_offset_ptr(const uint64_t* dev_ptr);
+int immtsf_seed_advance(uint64_t* dev_ptr, uint64_t inc, void* stream);
+
+/* Per-launch device timing of the tcgen05 GEMM kernel (bench.py's roofline): between begin and end every
+ * gemm_tc_kernel launch is bracketed by a CUDA-event pair on its launch stream.  end() waits for them and returns
+ * the number of records copied (shape, ragged_dim and milliseconds each). */
+int immtsf_profile_begin(int max_records);
+int immtsf_profile_end(int* M, int* N, int* K, int* ragged_dim, float* ms, int cap);
+
 /* ---- K1: padded -> ragged CSR (replaces the content mask of
  * fusions/TTF_RecAvg.py:69 / fusions/TTF_T2V_XAttn.py:107, the NaN guard of
  * :75 / :116 and M_txt of :110 / :124) ----------------------------------
@@ -84,6 +97,22 @@ int immtsf_gemm(int transA, int transB, int M, int N, int K, float alpha,
                 int ragged_dim, int backend, void* workspace, size_t workspace_bytes,
                 void* stream);
 size_t immtsf_gemm_workspace_bytes(int transA, int transB, int M, int N, int K);
+/* Same, with optional pre-split operands for the tcgen05 backend.  kind::tf32 reads fp32 containers and ignores
+ * the low 13 mantissa bits, so the "hi" operand is the tensor itself; A_lo / B_lo = x - trunc_tf32(x) (from
+ * immtsf_split_lo, same shape as the operand, leading dimension lda_lo / ldb_lo) let a caller that uses a tensor
+ * in several products (forward, dgrad, wgrad) split it once.  NULL => split internally into the workspace. */
+int immtsf_gemm_ex(int transA, int transB, int M, int N, int K, float alpha,
+                   const float* A, int lda, const float* A_lo, int lda_lo,
+                   const float* B, int ldb, const float* B_lo, int ldb_lo, float beta,
+                   float* C, int ldc, const float* bias, const int32_t* ragged,
+                   int ragged_dim, int backend, void* workspace, size_t workspace_bytes,
+                   void* stream);
+/* lo[rows][ld_lo] = src - trunc_tf32(src); rows bounded by roundup(*ragged,128) when ragged != NULL */
+int immtsf_split_lo(const float* src, int ld, int rows, int cols, float* lo, int ld_lo,
+                    const int32_t* ragged, void* stream);
+/* kernel family immtsf_gemm would pick for this call: 1 FFMA, 2 tcgen05, 3 skinny streaming kernels */
+int immtsf_gemm_plan(int transA, int transB, int M, int N, int K, const float* A, int lda,
+                     const float* B, int ldb, const float* C, int ldc, int backend);
 /* out[N] = beta*out + sum_m X[m, :]  (bias gradients: the `.sum(0)` autograd
  * emits for every nn.Linear bias on the path).  Rows bounded by *ragged when
  * given.  workspace (>= immtsf_gemm_workspace_bytes(0,0,1,N,M)) enables the
@@ -128,11 +157,12 @@ int immtsf_segattn_bwd(const float* d_attn_cat, const float* q, const float* KVp
                        uint32_t drop_thr, uint64_t seed, float* dKVp, float* dq_partial, void* stream);
 
 /* ---- residual + LayerNorm + dropout over d (TTF_T2V_XAttn.py:171-179) ---
- * z = (valid[row / rows_per_sample] ? x : 0) + res;  y = dropout(LN(z)) */
-int immtsf_ln_fwd(const float* x, int ldx, const float* res, const uint8_t* valid, int rows_per_sample,
+ * z = (valid[row / rows_per_sample] ? x + xbias : 0) + res;  y = dropout(LN(z))
+ * xbias [d] (nullable): a bias that belongs to x (the MHA out_proj bias when out_proj is folded into V). */
+int immtsf_ln_fwd(const float* x, int ldx, const float* xbias, const float* res, const uint8_t* valid, int rows_per_sample,
                   const float* gamma, const float* beta, int R, int d, float eps, uint32_t drop_thr,
                   uint64_t seed, uint32_t site, float* y, float* mean, float* rstd, void* stream);
-int immtsf_ln_bwd(const float* dy, const float* x, int ldx, const float* res, const uint8_t* valid,
+int immtsf_ln_bwd(const float* dy, const float* x, int ldx, const float* xbias, const float* res, const uint8_t* valid,
                   int rows_per_sample, const float* gamma, const float* mean, const float* rstd, int R,
                   int d, uint32_t drop_thr, uint64_t seed, uint32_t site, float* dx, float* dres,
                   float* dgamma, float* dbeta, void* stream);

@@ -1,0 +1,71 @@
+"""runtime.GraphedStep: the whole forward+loss+backward step captured in a CUDA graph must reproduce the eager
+path on NEW inputs of the same shape (different ragged note counts included), and must draw fresh dropout masks
+on every replay."""
+import pytest
+import torch
+
+import gpu_common as G
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("ttf,mmf", [("TTF_RecAvg", "MMF_GR_Add"), ("TTF_T2V_XAttn", "MMF_XAttn_Add"),
+                                     ("TTF_T2V_XAttn", "MMF_GR_Add"), ("TTF_RecAvg", "MMF_XAttn_Add")])
+def test_graph_replay_equals_eager_on_new_inputs(ttf, mmf):
+    from immtsf import runtime
+
+    cfg = dict(ttf=ttf, mmf=mmf, d_txt=64, C=4, H=2, kappa=0.5)
+    fm = G.build_model(cfg, 96, dropout=0.0, seed=1)
+    G.randomise_(fm, 2)
+    fm.train()
+    ex = [t.cuda() for t in G.synth_batch(16, 6, 10, 96, 4, 3)[:4]]
+    Gw = torch.randn(16, 10, 4, generator=torch.Generator().manual_seed(5)).cuda()
+    loss_fn = lambda out, g: (out * g).sum()
+    step = runtime.GraphedStep(fm, example=ex, loss_fn=loss_fn, extras=(Gw,))
+    static_grads = [p.grad for p in step.params]
+    try:
+        for seed in (11, 12):  # new content, new ragged counts, same shapes
+            notes, tau, t_hat, Y, _ = G.synth_batch(16, 6, 10, 96, 4, seed)
+            loss = step(notes.cuda(), tau.cuda(), t_hat.cuda(), Y.cuda(), Gw)
+            got = {"loss": loss.clone(), "Y_out": step.Y_out.clone(), "dY": step.dY_ts.clone(),
+                   "grads": {k: p.grad.clone() for k, p in fm.named_parameters()}}
+            step.check_nan()
+            ref = G.gpu_run(fm, notes, tau, t_hat, Y, Gw.cpu(), train=True)  # eager, fresh grads
+            G.assert_close("Y_out", got["Y_out"].cpu(), ref["Y_out"], 1e-6)
+            G.assert_close("dY", got["dY"].cpu(), ref["dY"], 1e-5)
+            for k, g in ref["grads"].items():
+                G.assert_close(k, got["grads"][k].cpu(), g, 1e-5, floor=1e-3)
+            # the eager run above replaced p.grad with fresh tensors; put the graph's static buffers back
+            for p, g in zip(step.params, static_grads):
+                p.grad = g
+    finally:
+        step.close()
+
+
+def test_graph_replay_draws_fresh_dropout_masks():
+    from immtsf import runtime
+
+    cfg = dict(ttf="TTF_T2V_XAttn", mmf="MMF_XAttn_Add", d_txt=64, C=4, H=1, kappa=0.5)
+    fm = G.build_model(cfg, 96, dropout=0.3, seed=1)
+    G.randomise_(fm, 2)
+    fm.train()
+    ex = [t.cuda() for t in G.synth_batch(8, 6, 10, 96, 4, 3)[:4]]
+    step = runtime.GraphedStep(fm, example=ex)
+    try:
+        outs = []
+        for _ in range(3):
+            step(*ex)
+            outs.append(step.Y_out.clone())
+        assert torch.isfinite(outs[0]).all()
+        assert not torch.equal(outs[0], outs[1]) and not torch.equal(outs[1], outs[2])
+        assert int(step.seed_offset.item()) >= 3
+    finally:
+        step.close()
+    # after close() the eager path is unaffected by the offset
+    runtime.SEEDS.fixed = 77
+    try:
+        a = fm(*ex).detach().clone()
+        b = fm(*ex).detach().clone()
+        assert torch.equal(a, b)
+    finally:
+        runtime.SEEDS.fixed = None
