@@ -43,13 +43,28 @@
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BKT = 32, STAGES = 3;
-constexpr int TILE_A = BM * BKT * 4;                  // 16 KiB
-constexpr int TILE_B = BN * BKT * 4;                  // 16 KiB
-constexpr int STAGE_BYTES = 2 * TILE_A + 2 * TILE_B;  // hi+lo of both operands
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr int KC = 4;                                 // k-blocks per TMEM accumulation chunk (K = 128)
-constexpr int TMEM_COLS = 4 * BN;                     // two buffers x (hi*hi accumulator, cross-term accumulator)
+constexpr int BM = 128, BKT = 32;
+constexpr int TILE_A = BM * BKT * 4;  // 16 KiB
+constexpr int KC = 4;                 // k-blocks per TMEM accumulation chunk (K = 128)
+constexpr int TMEM_COLS = 512;        // both variants use all of it
+
+// Two tile shapes.  The kernel is bound by L2->SM operand bandwidth (~42 B/clk/SM chip-wide, ncu: 49 % tensor-pipe
+// activity with 128x128 tiles = 64 KiB per k-block per CTA), so the wide tile trades TMEM for bytes per FLOP:
+//   BN = 128: 3 stages x 64 KiB, two TMEM accumulators per buffer (hi*hi and the cross terms), 4 epilogue warps.
+//   BN = 256: 2 stages x 96 KiB (0.75x the operand bytes per FLOP), ONE accumulator per buffer (512 TMEM columns
+//             = 2 buffers x 256), 8 epilogue warps (each thread promotes 128 columns of its row in registers;
+//             setmaxnreg moves registers from the 4 control warps to the 8 epilogue warps).
+template <int BN_>
+struct Cfg {
+  static constexpr int BN = BN_;
+  static constexpr int STAGES = BN_ == 128 ? 3 : 2;
+  static constexpr int NACC = BN_ == 128 ? 2 : 1;
+  static constexpr int TILE_B = BN_ * BKT * 4;
+  static constexpr int STAGE_BYTES = 2 * TILE_A + 2 * TILE_B;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int EPI_WARPS = 4 * (BN_ / 128);
+  static constexpr int THREADS = 128 + 32 * EPI_WARPS;
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -129,10 +144,12 @@ struct TcArgs {
   int ldp;
 };
 
-template <bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(256, 1)
+template <bool A_MN, bool B_MN, int BN>
+__global__ void __launch_bounds__(Cfg<BN>::THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
                const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl, const TcArgs g) {
+  using C_ = Cfg<BN>;
+  constexpr int STAGES = C_::STAGES, STAGE_BYTES = C_::STAGE_BYTES, TILE_B = C_::TILE_B, NACC = C_::NACC;
   extern __shared__ uint8_t smem_raw[];
   int M = g.M, K = g.K;
   if (g.ragged_dim == 1) M = ragged_rows(M, g.ragged);
@@ -158,7 +175,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_tfull + 8 * b, 1);
-      mbar_init(bar_tempty + 8 * b, 4);  // one arrive per epilogue warp
+      mbar_init(bar_tempty + 8 * b, C_::EPI_WARPS);  // one arrive per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -172,6 +189,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
+  if (warp < 4) {
+  // 384-thread variant: the control warpgroup hands its registers to the two epilogue warpgroups, whose fp32
+  // promotion tile (128 columns per thread) does not fit the 168-register launch allocation
+  if (BN == 256) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
   if (warp == 0 && lane == 0) {
     // ===== TMA producer =====
     for (int kb = z_kb0; kb < z_kb1; ++kb) {
@@ -212,7 +233,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
       const int buf = c & 1;
       mbar_wait(bar_tempty + 8 * buf, ((c >> 1) & 1) ^ 1);  // epilogue has drained this TMEM buffer
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t tacc_big = tmem_base + (uint32_t)(buf * 2 * BN), tacc_small = tacc_big + BN;
+      const uint32_t tacc_big = tmem_base + (uint32_t)(buf * NACC * BN), tacc_small = tacc_big + (NACC == 2 ? BN : 0);
       const int kb0 = z_kb0 + c * KC;
       const int kb_end = min(z_kb1, kb0 + KC);
       for (int kb = kb0; kb < kb_end; ++kb) {
@@ -229,7 +250,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
           for (int ks = 0; ks < BKT / 8; ++ks) {
             const uint64_t ad = make_desc(sa + (A_MN ? ks * 1024 : ks * 32), A_MN);
             const uint64_t bd = make_desc(sb + (B_MN ? ks * 1024 : ks * 32), B_MN);
-            const bool first = (kb == kb0) && ks == 0 && (prod == 0 || prod == 2);
+            const bool first = (kb == kb0) && ks == 0 && (prod == 0 || (NACC == 2 && prod == 2));
             umma_tf32(prod == 2 ? tacc_big : tacc_small, ad, bd, idesc, first ? 0u : 1u);
           }
         }
@@ -237,24 +258,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
       }
       umma_commit(bar_tfull + 8 * buf);
     }
-  } else if (warp >= 4) {
+  }
+  } else {
     // ===== epilogue =====
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
-    float acc[BN];
+    if (BN == 256) asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    const int q = warp & 3;               // TMEM lane quarter this warp may access
+    const int ch = ((warp - 4) >> 2) * 128;  // this warp's 128-column half of the tile (BN = 256: two warpgroups)
+    float acc[128];
 #pragma unroll
-    for (int j = 0; j < BN; ++j) acc[j] = 0.f;
+    for (int j = 0; j < 128; ++j) acc[j] = 0.f;
     for (int c = 0; c < nchunks; ++c) {
       const int buf = c & 1;
       mbar_wait(bar_tfull + 8 * buf, (c >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t v[32], u[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 2 * BN + c0), v);
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 2 * BN + BN + c0), u);
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * NACC * BN + ch + c0), v);
+        if (NACC == 2) {
+          uint32_t u[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * NACC * BN + BN + ch + c0), u);
 #pragma unroll
-        for (int j = 0; j < 32; ++j)  // fp32 round-to-nearest promotion
-          acc[c0 + j] += __uint_as_float(v[j]) + __uint_as_float(u[j]);
+          for (int j = 0; j < 32; ++j)  // fp32 round-to-nearest promotion
+            acc[c0 + j] += __uint_as_float(v[j]) + __uint_as_float(u[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(v[j]);
+        }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
@@ -266,17 +296,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
       // split-K: this split's partial tile goes to the workspace [z][M][ldp]; splitk_reduce_kernel sums the
       // splits in a fixed order (deterministic, unlike atomics) and applies alpha / beta / bias
       if (row < g.M) {
-        float* prow = g.partial + ((size_t)blockIdx.z * g.M + row) * g.ldp + n0;
+        float* prow = g.partial + ((size_t)blockIdx.z * g.M + row) * g.ldp + n0 + ch;
 #pragma unroll
-        for (int j4 = 0; j4 < BN / 4; ++j4)
-          if (n0 + j4 * 4 < g.ldp)
+        for (int j4 = 0; j4 < 128 / 4; ++j4)
+          if (n0 + ch + j4 * 4 < g.ldp)
             *reinterpret_cast<float4*>(prow + j4 * 4) = make_float4(acc[j4 * 4], acc[j4 * 4 + 1], acc[j4 * 4 + 2], acc[j4 * 4 + 3]);
       }
     } else if (row < g.M) {
-      float* crow = g.C + (size_t)row * g.ldc + n0;
+      float* crow = g.C + (size_t)row * g.ldc + n0 + ch;
 #pragma unroll
-      for (int j4 = 0; j4 < BN / 4; ++j4) {
-        const int n = n0 + j4 * 4;
+      for (int j4 = 0; j4 < 128 / 4; ++j4) {
+        const int n = n0 + ch + j4 * 4;
         if (n < g.N) {
           float o[4];
 #pragma unroll
@@ -415,8 +445,8 @@ int make_map(CUtensorMap* m, const float* ptr, int rows, int cols, int ld, int b
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // split-K when the output has too few tiles to occupy the 148 SMs (weight gradients: M, N = d; K = rows)
-inline int choose_splitk(int M, int N, int K) {
-  const int tiles = ceil_div(N, BN) * ceil_div(M, BM), nkb = ceil_div(K, BKT);
+inline int choose_splitk(int M, int N, int K, int bn) {
+  const int tiles = ceil_div(N, bn) * ceil_div(M, BM), nkb = ceil_div(K, BKT);
   int splitk = 1;
   if (tiles * 2 <= 148 && nkb >= 16) {
     splitk = 148 / tiles;
@@ -425,6 +455,29 @@ inline int choose_splitk(int M, int N, int K) {
     if (splitk < 1) splitk = 1;
   }
   return splitk;
+}
+
+// Tile width: estimated time = waves x k-blocks per CTA x bytes per k-block (the kernel is operand-bandwidth bound).
+// IMMTSF_TC_BN=128|256 forces one variant (tests, experiments).
+inline int choose_bn(int M, int N, int K) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("IMMTSF_TC_BN");
+    forced = e ? atoi(e) : 0;
+  }
+  if (forced == 128 || forced == 256) return forced;
+  if (N <= 128) return 128;
+  double cost[2];
+  const int bns[2] = {128, 256};
+  for (int i = 0; i < 2; ++i) {
+    const int bn = bns[i], sk = choose_splitk(M, N, K, bn);
+    const long ctas = (long)ceil_div(N, bn) * ceil_div(M, BM) * sk;
+    const double waves = (double)((ctas + 147) / 148);
+    // + fixed prologue/epilogue cost per tile, + the partial-tile round trip and reduce launch of split-K
+    const double kb = (double)ceil_div(ceil_div(K, BKT), sk) + 6.0 + (sk > 1 ? 8.0 : 0.0);
+    cost[i] = waves * kb * (bn == 128 ? 64.0 : 96.0);
+  }
+  return cost[1] < cost[0] ? 256 : 128;
 }
 
 }  // namespace
@@ -471,7 +524,7 @@ extern "C" int immtsf_profile_end(int* M, int* N, int* K, int* ragged_dim, float
 size_t immtsf_gemm_tc_workspace(int transA, int transB, int M, int N, int K) {
   const size_t ra = transA ? K : M, ca = transA ? M : K, rb = transB ? N : K, cb = transB ? K : N;
   const size_t a = align_up(ra * align_up(ca, 4) * 4, 256), b = align_up(rb * align_up(cb, 4) * 4, 256);
-  const int sk = choose_splitk(M, N, K);
+  const int sk = choose_splitk(M, N, K, choose_bn(M, N, K));
   const size_t p = sk > 1 ? align_up((size_t)sk * M * align_up(N, 4) * 4, 256) : 0;
   return a + b + p + 256;
 }
@@ -542,8 +595,9 @@ int immtsf_gemm_tc(int transA, int transB, int M, int N, int K, float alpha, con
     ldb2 = ldb_lo;
   }
   CUtensorMap mAh, mAl, mBh, mBl;
-  // K-major operand [rows=MN][cols=K]: box 32 x 128 ; MN-major operand [rows=K][cols=MN]: box 32 x 32
-  const int boxA = transA ? 32 : BM, boxB = transB ? BN : 32;
+  // K-major operand [rows=MN][cols=K]: box 32 x 128 (or 256) ; MN-major operand [rows=K][cols=MN]: box 32 x 32
+  const int bn = choose_bn(M, N, K);
+  const int boxA = transA ? 32 : BM, boxB = transB ? bn : 32;
   if (make_map(&mAh, A, ra, ca, lda, boxA, transA != 0) || make_map(&mAl, Al, ra, ca, lda2, boxA, transA != 0) ||
       make_map(&mBh, B, rb, cb, ldb, boxB, transB == 0) || make_map(&mBl, Bl, rb, cb, ldb2, boxB, transB == 0)) {
     immtsf_set_error("gemm_tc: cuTensorMapEncodeTiled failed");
@@ -552,8 +606,8 @@ int immtsf_gemm_tc(int transA, int transB, int M, int N, int K, float alpha, con
   TcArgs g;
   g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K; g.alpha = alpha; g.beta = beta; g.bias = bias;
   g.ragged = ragged; g.ragged_dim = ragged_dim;
-  dim3 grid(ceil_div(N, BN), ceil_div(M, BM));
-  const int splitk = choose_splitk(M, N, K);
+  dim3 grid(ceil_div(N, bn), ceil_div(M, BM));
+  const int splitk = choose_splitk(M, N, K, bn);
   g.partial = nullptr; g.ldp = 0;
   if (splitk > 1) {
     grid.z = splitk;
@@ -562,19 +616,26 @@ int immtsf_gemm_tc(int transA, int transB, int M, int N, int K, float alpha, con
   }
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(gemm_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    cudaFuncSetAttribute(gemm_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    cudaFuncSetAttribute(gemm_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    cudaFuncSetAttribute(gemm_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+#define TC_ATTR(a, b)                                                                                                      \
+  cudaFuncSetAttribute(gemm_tc_kernel<a, b, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128>::SMEM_BYTES);     \
+  cudaFuncSetAttribute(gemm_tc_kernel<a, b, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<256>::SMEM_BYTES)
+    TC_ATTR(false, false); TC_ATTR(false, true); TC_ATTR(true, false); TC_ATTR(true, true);
+#undef TC_ATTR
     attr_done = true;
   }
   ProfRec* rec = (g_prof_on && g_prof_n < g_prof_cap) ? &g_prof[g_prof_n++] : nullptr;
   if (rec) { rec->M = M; rec->N = N; rec->K = K; rec->ragged_dim = ragged_dim; cudaEventRecord(rec->e0, st); }
   // UMMA "B is K-major" means stored [N][K], i.e. transB=1
-  if (!transA && transB) gemm_tc_kernel<false, false><<<grid, 256, SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, g);
-  else if (!transA && !transB) gemm_tc_kernel<false, true><<<grid, 256, SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, g);
-  else if (transA && !transB) gemm_tc_kernel<true, true><<<grid, 256, SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, g);
-  else gemm_tc_kernel<true, false><<<grid, 256, SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, g);
+#define TC_LAUNCH(a, b)                                                                                                   \
+  do {                                                                                                                    \
+    if (bn == 128) gemm_tc_kernel<a, b, 128><<<grid, Cfg<128>::THREADS, Cfg<128>::SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, g); \
+    else gemm_tc_kernel<a, b, 256><<<grid, Cfg<256>::THREADS, Cfg<256>::SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, g);          \
+  } while (0)
+  if (!transA && transB) TC_LAUNCH(false, false);
+  else if (!transA && !transB) TC_LAUNCH(false, true);
+  else if (transA && !transB) TC_LAUNCH(true, true);
+  else TC_LAUNCH(true, false);
+#undef TC_LAUNCH
   if (rec) cudaEventRecord(rec->e1, st);
   IMMTSF_CHECK_LAUNCH("gemm_tc");
   if (splitk > 1) {

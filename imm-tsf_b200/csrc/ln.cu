@@ -237,7 +237,7 @@ extern "C" int immtsf_ln_bwd(const float* dy, const float* x, int ldx, const flo
   a.dy = dy; a.dx = dx; a.dres = dres; a.dgamma = dgamma; a.dbeta = dbeta;
   const int TT = 8 / nch;
   int grid = ceil_div(R, TT);
-  if (grid > 148) grid = 148;
+  if (grid > 148 * 3) grid = 148 * 3;
   cudaStream_t st = (cudaStream_t)stream;
   if (nch == 1) ln_bwd_kernel<1><<<grid, threads, 0, st>>>(a);
   else if (nch == 2) ln_bwd_kernel<2><<<grid, threads, 0, st>>>(a);

@@ -9,7 +9,7 @@
 // In eval / dropout 0 the output does not depend on t and is produced once
 // per sample (R = B rows); with attention dropout every (t,h,n) weight gets
 // its own Philox keep bit and R = B*T rows.
-#include "rowtile.cuh"
+#include "tile32.cuh"
 #include "../../include/immtsf.h"
 
 // ------------------------------------------------------------------ Time2Vec
@@ -182,11 +182,21 @@ __global__ void __launch_bounds__(256) segattn_fwd_kernel(const SegArgs a) {
   }
 }
 
-// smem: s_p [H][NM] | s_ds [H][NM] | s_dp [TT][H][NM]
+// Backward.  smem: tile32 staging | s_out [32*32] | s_p [H][NM] | s_ds [H][NM] | s_dp [TT][H][NM]
+//  a) dp~[t][h][n] = dO[t, head h] . V[n, head h]: 32 x 32 register-tiled X Y^T (tile32.cuh), dO and V staged
+//     through shared memory once per tile instead of one warp-shuffle dot product per (t, n) pair;
+//  b) softmax backward, accumulated over the query rows of the tile;
+//  c) dV[n] = sum_t p~[t][n] dO[t]: register accumulators over 8 notes, dO rows streamed 4 at a time -- a
+//     single pass (no read-modify-write of dKVp) whenever all T query rows fit one tile (T <= TT);
+//  d) dK[n] = ds[n] q ; dq_b = sum_n ds[n] K[n].
 __global__ void __launch_bounds__(256) segattn_bwd_kernel(const SegArgs a) {
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) float smem[];
   const int H = a.H, d = a.d, hd = a.hd, NM = a.N_max, TT = a.TT;
-  float* s_p = smem;
+  float* s_x = smem;
+  float* s_y = s_x + XS_T * XS_LD;
+  float* s_part = s_y + XS_T * XS_LD;
+  float* s_out = s_part + 8 * XS_T * XS_T;
+  float* s_p = s_out + XS_T * XS_T;
   float* s_ds = s_p + (size_t)H * NM;
   float* s_dp = s_ds + (size_t)H * NM;
   const int b = blockIdx.x;
@@ -195,6 +205,7 @@ __global__ void __launch_bounds__(256) segattn_bwd_kernel(const SegArgs a) {
   const int ld = 2 * d, d4 = d >> 2;
   const int Teff = a.per_query ? a.T : 1;
   const float inv_keep = inv_keep_from_thr(a.thr);
+  const uint64_t seed = resolve_seed(a.seed);
   if (nn == 0) {
     for (int c = threadIdx.x; c < d; c += blockDim.x) a.dq_partial[(size_t)b * d + c] = 0.f;
     return;
@@ -205,80 +216,95 @@ __global__ void __launch_bounds__(256) segattn_bwd_kernel(const SegArgs a) {
     s_ds[h * NM + n] = 0.f;
   }
   for (int t0 = 0; t0 < Teff; t0 += TT) {
-    __syncthreads();
-    // a) dp~[tt][h][n] = dO[t, head h] . V[n, head h]
-    for (int i = w; i < TT * H * nn; i += nw) {
-      const int tt = i / (H * nn), r = i % (H * nn), h = r / nn, n = r % nn;
-      const int t = t0 + tt;
-      float s = 0.f;
-      if (t < Teff)
-        s = warp_dot(a.dO + ((size_t)b * Teff + t) * d + h * hd, a.KVp + (size_t)(nb + n) * ld + d + h * hd, hd, lane);
-      if (lane == 0) s_dp[((size_t)tt * H + h) * NM + n] = s;
-    }
+    const int tcnt = min(TT, Teff - t0);
+    // a) dp~ for this tile of query rows
+    for (int h = 0; h < H; ++h)
+      for (int n0 = 0; n0 < nn; n0 += XS_T) {
+        const int ncnt = min(XS_T, nn - n0);
+        tile_xyt(a.dO + ((size_t)b * Teff + t0) * d + h * hd, d, a.KVp + (size_t)(nb + n0) * ld + d + h * hd, ld, tcnt, ncnt, hd,
+                 s_x, s_y, s_part, s_out);
+        for (int i = threadIdx.x; i < tcnt * ncnt; i += blockDim.x) {
+          const int tt = i / ncnt, j = i % ncnt;
+          s_dp[((size_t)tt * H + h) * NM + n0 + j] = s_out[tt * XS_T + j];
+        }
+      }
     __syncthreads();
     // b) softmax backward (accumulated over t) ; s_dp <- dropped probabilities p~
-    for (int h = w; h < H; h += nw) {
-      for (int tt = 0; tt < TT; ++tt) {
-        const int t = t0 + tt;
-        if (t >= Teff) {
-          for (int n = lane; n < nn; n += 32) s_dp[((size_t)tt * H + h) * NM + n] = 0.f;
-          continue;
+    for (int i = w; i < tcnt * H; i += nw) {
+      const int tt = i / H, h = i % H, t = t0 + tt;
+      float* dprow = s_dp + ((size_t)tt * H + h) * NM;
+      float D = 0.f;
+      for (int n = lane; n < nn; n += 32) {
+        float ks = 1.f;
+        if (a.per_query) ks = dropout_scale(seed, IMMTSF_SITE_TTF_ATTN, (((uint64_t)b * a.T + t) * H + h) * NM + n, a.thr, inv_keep);
+        const float dp = dprow[n] * ks;
+        dprow[n] = dp;
+        D = fmaf(s_p[h * NM + n], dp, D);
+      }
+      D = warp_sum(D);
+      for (int n = lane; n < nn; n += 32) {
+        float ks = 1.f;
+        if (a.per_query) ks = dropout_scale(seed, IMMTSF_SITE_TTF_ATTN, (((uint64_t)b * a.T + t) * H + h) * NM + n, a.thr, inv_keep);
+        const float p = s_p[h * NM + n];
+        atomicAdd(&s_ds[h * NM + n], p * (dprow[n] - D));  // rows t of one head are spread over warps
+        dprow[n] = p * ks;
+      }
+    }
+    __syncthreads();
+    // c) dV[n] (+)= sum_tt p~[tt][h][n] dO[t]
+    for (int col4 = threadIdx.x; col4 < d4; col4 += blockDim.x) {
+      const int h = (col4 * 4) / hd;
+      const float4* gop = reinterpret_cast<const float4*>(a.dO + ((size_t)b * Teff + t0) * d) + col4;
+      for (int n0 = 0; n0 < nn; n0 += 8) {
+        float4 acc[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc[u] = f4_zero();
+        for (int tq = 0; tq < tcnt; tq += 4) {
+          float4 go[4];
+#pragma unroll
+          for (int v = 0; v < 4; ++v) go[v] = tq + v < tcnt ? __ldg(gop + (size_t)(tq + v) * d4) : f4_zero();
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            if (tq + v < tcnt) {
+              const float* pr = s_dp + ((size_t)(tq + v) * H + h) * NM + n0;
+#pragma unroll
+              for (int u = 0; u < 8; ++u)
+                if (n0 + u < nn) f4_fma(acc[u], pr[u], go[v]);
+            }
+          }
         }
-        float D = 0.f;
-        for (int n = lane; n < nn; n += 32) {
-          float ks = 1.f;
-          if (a.per_query)
-            ks = dropout_scale(resolve_seed(a.seed), IMMTSF_SITE_TTF_ATTN, (((uint64_t)b * a.T + t) * H + h) * NM + n, a.thr, inv_keep);
-          const float dp = s_dp[((size_t)tt * H + h) * NM + n] * ks;
-          s_dp[((size_t)tt * H + h) * NM + n] = dp;  // temporarily dp
-          D = fmaf(s_p[h * NM + n], dp, D);
-        }
-        D = warp_sum(D);
-        for (int n = lane; n < nn; n += 32) {
-          float ks = 1.f;
-          if (a.per_query)
-            ks = dropout_scale(resolve_seed(a.seed), IMMTSF_SITE_TTF_ATTN, (((uint64_t)b * a.T + t) * H + h) * NM + n, a.thr, inv_keep);
-          const float p = s_p[h * NM + n];
-          const float dp = s_dp[((size_t)tt * H + h) * NM + n];
-          s_ds[h * NM + n] += p * (dp - D);
-          s_dp[((size_t)tt * H + h) * NM + n] = p * ks;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          if (n0 + u < nn) {
+            float4* dst = reinterpret_cast<float4*>(a.dKVp + (size_t)(nb + n0 + u) * ld + d) + col4;
+            if (t0 == 0) *dst = acc[u];
+            else { float4 o = *dst; f4_add(o, acc[u]); *dst = o; }
+          }
         }
       }
     }
     __syncthreads();
-    // c) dV[n] += sum_tt p~[tt][h][n] dO[t]
-    for (int col4 = threadIdx.x; col4 < d4; col4 += blockDim.x) {
-      const int h = (col4 * 4) / hd;
-      float4 go[4];
-#pragma unroll
-      for (int tt = 0; tt < 4; ++tt)
-        go[tt] = (tt < TT && t0 + tt < Teff)
-                     ? __ldg(reinterpret_cast<const float4*>(a.dO + ((size_t)b * Teff + t0 + tt) * d) + col4)
-                     : f4_zero();
-      for (int n = 0; n < nn; ++n) {
-        float4 dv = f4_zero();
-#pragma unroll
-        for (int tt = 0; tt < 4; ++tt)
-          if (tt < TT) f4_fma(dv, s_dp[((size_t)tt * H + h) * NM + n], go[tt]);
-        float4* dst = reinterpret_cast<float4*>(a.dKVp + (size_t)(nb + n) * ld + d) + col4;
-        if (t0 == 0) *dst = dv;
-        else { float4 o = *dst; f4_add(o, dv); *dst = o; }
-      }
-    }
   }
-  __syncthreads();
   // d) dK[n] = ds[h][n] q ; dq_b = sum_n ds[h][n] K[n]
   for (int col4 = threadIdx.x; col4 < d4; col4 += blockDim.x) {
     const int h = (col4 * 4) / hd;
     const float4 qv = __ldg(reinterpret_cast<const float4*>(a.q) + col4);
     float4 dq = f4_zero();
-    for (int n = 0; n < nn; ++n) {
-      const float ds = s_ds[h * NM + n];
-      const float4 kv = __ldg(reinterpret_cast<const float4*>(a.KVp + (size_t)(nb + n) * ld) + col4);
-      f4_fma(dq, ds, kv);
-      float4 dk;
-      dk.x = ds * qv.x; dk.y = ds * qv.y; dk.z = ds * qv.z; dk.w = ds * qv.w;
-      reinterpret_cast<float4*>(a.dKVp + (size_t)(nb + n) * ld)[col4] = dk;
+    for (int n0 = 0; n0 < nn; n0 += 4) {
+      float4 kv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        kv[u] = n0 + u < nn ? __ldg(reinterpret_cast<const float4*>(a.KVp + (size_t)(nb + n0 + u) * ld) + col4) : f4_zero();
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (n0 + u < nn) {
+          const float ds = s_ds[h * NM + n0 + u];
+          f4_fma(dq, ds, kv[u]);
+          float4 dk;
+          dk.x = ds * qv.x; dk.y = ds * qv.y; dk.z = ds * qv.z; dk.w = ds * qv.w;
+          reinterpret_cast<float4*>(a.dKVp + (size_t)(nb + n0 + u) * ld)[col4] = dk;
+        }
+      }
     }
     reinterpret_cast<float4*>(a.dq_partial + (size_t)b * d)[col4] = dq;
   }
@@ -327,9 +353,18 @@ extern "C" int immtsf_segattn_bwd(const float* d_attn_cat, const float* q, const
   a.q = q; a.KVp = KVp; a.offsets = offsets; a.B = B; a.T = T; a.H = H; a.d = d; a.hd = d / H; a.N_max = N_max;
   a.per_query = per_query ? 1 : 0; a.thr = per_query ? drop_thr : 0u; a.seed = make_seed(seed); a.probs = const_cast<float*>(probs);
   a.dO = d_attn_cat; a.dKVp = dKVp; a.dq_partial = dq_partial;
-  size_t smem;
-  if (seg_setup(a, 2, smem)) { immtsf_set_error("segattn_bwd: H*N_max=%d too large for shared memory", H * N_max); return IMMTSF_ERR_UNSUPPORTED; }
-  if (smem > 48 * 1024) cudaFuncSetAttribute(segattn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  // fixed part: tile32 staging + s_out + s_p + s_ds ; then as many query rows (<= 32) of [H][N_max] planes as fit
+  const size_t plane = (size_t)H * N_max * sizeof(float);
+  const size_t fixed = (size_t)(XS_TILE_FLOATS + XS_T * XS_T) * sizeof(float) + 2 * plane;
+  int TT = 32;
+  while (TT > 1 && fixed + TT * plane > 200 * 1024) TT >>= 1;
+  if (fixed + TT * plane > 200 * 1024) { immtsf_set_error("segattn_bwd: H*N_max=%d too large for shared memory", H * N_max); return IMMTSF_ERR_UNSUPPORTED; }
+  if (!a.per_query) TT = 1;
+  a.TT = TT;
+  const size_t smem = fixed + TT * plane;
+  IMMTSF_REQUIRE((d & 3) == 0, "segattn_bwd: d must be a multiple of 4");
+  static size_t smem_set = 0;
+  if (smem > smem_set) { cudaFuncSetAttribute(segattn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); smem_set = smem; }
   segattn_bwd_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(a);
   IMMTSF_CHECK_LAUNCH("segattn_bwd");
   return IMMTSF_OK;

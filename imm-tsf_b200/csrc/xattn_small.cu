@@ -18,14 +18,11 @@
 //
 // HBM-bound: algorithmic bytes per (sample, head) 4*4*T*hd forward (q,k,v in,
 // o out) and 4*7*T*hd backward, against 4*T*T*hd FLOP -- intensity T/4 FLOP/B.
-#include "rowtile.cuh"
+#include "tile32.cuh"
 #include "../../include/immtsf.h"
 
 namespace {
 
-constexpr int XS_T = 32;     // max T
-constexpr int XS_DC = 512;   // contraction chunk staged in shared memory
-constexpr int XS_LD = XS_DC + 4;
 constexpr int XS_RH = 16;    // rows of float4 accumulators per pass
 
 struct XsArgs {
@@ -34,60 +31,6 @@ struct XsArgs {
   float* o; int ldo; float* probs;
   const float* d_o; int lddo; float* dq; int lddq; float* dk; int lddk; float* dv; int lddv;
 };
-
-// S[i][j] = sum_c X[i][c] * Y[j][c] over c in [0, hd): result (unscaled) in s_out[XS_T*XS_T] (row stride XS_T).
-// X, Y: global [T][ld] row pointers of this (sample, head).  s_x, s_y: [XS_T][XS_LD] staging; s_part: [8][XS_T*XS_T].
-__device__ __forceinline__ void tile_xyt(const float* __restrict__ X, int ldx, const float* __restrict__ Y, int ldy, int T, int hd,
-                                         float* s_x, float* s_y, float* s_part, float* s_out) {
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int ib = lane >> 2, jb = lane & 3;  // rows ib*4 + a (a < 4), cols b*4 + jb (b < 8): conflict-free LDS.128
-  float acc[4][8];
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int b = 0; b < 8; ++b) acc[a][b] = 0.f;
-  for (int c0 = 0; c0 < hd; c0 += XS_DC) {
-    const int cw = min(XS_DC, hd - c0), cw4 = cw >> 2;
-    __syncthreads();  // previous chunk consumed
-    for (int i = threadIdx.x; i < XS_T * (XS_DC / 4); i += blockDim.x) {
-      const int r = i / (XS_DC / 4), c4 = i % (XS_DC / 4);
-      float4 xv = f4_zero(), yv = f4_zero();
-      if (r < T && c4 < cw4) {
-        xv = __ldg(reinterpret_cast<const float4*>(X + (size_t)r * ldx + c0) + c4);
-        yv = __ldg(reinterpret_cast<const float4*>(Y + (size_t)r * ldy + c0) + c4);
-      }
-      *reinterpret_cast<float4*>(s_x + r * XS_LD + c4 * 4) = xv;
-      *reinterpret_cast<float4*>(s_y + r * XS_LD + c4 * 4) = yv;
-    }
-    __syncthreads();
-    const int sl0 = w * (XS_DC / 8);
-#pragma unroll 4
-    for (int c = sl0; c < sl0 + XS_DC / 8; c += 4) {
-      float4 xa[4], yb[8];
-#pragma unroll
-      for (int a = 0; a < 4; ++a) xa[a] = *reinterpret_cast<const float4*>(s_x + (ib * 4 + a) * XS_LD + c);
-#pragma unroll
-      for (int b = 0; b < 8; ++b) yb[b] = *reinterpret_cast<const float4*>(s_y + (b * 4 + jb) * XS_LD + c);
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 8; ++b)
-          acc[a][b] = fmaf(xa[a].x, yb[b].x, fmaf(xa[a].y, yb[b].y, fmaf(xa[a].z, yb[b].z, fmaf(xa[a].w, yb[b].w, acc[a][b]))));
-    }
-  }
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int b = 0; b < 8; ++b) s_part[w * (XS_T * XS_T) + (ib * 4 + a) * XS_T + b * 4 + jb] = acc[a][b];
-  __syncthreads();
-  for (int i = threadIdx.x; i < XS_T * XS_T; i += blockDim.x) {
-    float s = 0.f;
-#pragma unroll
-    for (int ww = 0; ww < 8; ++ww) s += s_part[ww * (XS_T * XS_T) + i];
-    s_out[i] = s;
-  }
-  __syncthreads();
-}
 
 // out[i][:] = sum_j W[i][j] * V[j][:]  for i in [0,T) -- W in shared memory (row stride XS_T), V/out global.
 // transposed = true uses W[j][i] instead (dK = dS^T Q, dV = P~^T dO).
@@ -100,12 +43,19 @@ __device__ __forceinline__ void tile_wv(const float* s_w, const float* __restric
       float4 acc[XS_RH];
 #pragma unroll
       for (int a = 0; a < XS_RH; ++a) acc[a] = f4_zero();
-      for (int j = 0; j < T; ++j) {
-        const float4 vv = __ldg(reinterpret_cast<const float4*>(V + (size_t)j * ldv) + c4);
+      for (int j0 = 0; j0 < T; j0 += 4) {  // 4 rows of V in flight per thread (global-load latency, not bandwidth, binds here)
+        float4 vv[4];
 #pragma unroll
-        for (int a = 0; a < XS_RH; ++a) {
-          const float wgt = TRANSPOSED ? s_w[j * XS_T + i0 + a] : s_w[(i0 + a) * XS_T + j];
-          f4_fma(acc[a], wgt, vv);
+        for (int u = 0; u < 4; ++u)
+          vv[u] = j0 + u < T ? __ldg(reinterpret_cast<const float4*>(V + (size_t)(j0 + u) * ldv) + c4) : f4_zero();
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = min(j0 + u, XS_T - 1);
+#pragma unroll
+          for (int a = 0; a < XS_RH; ++a) {
+            const float wgt = TRANSPOSED ? s_w[j * XS_T + i0 + a] : s_w[(i0 + a) * XS_T + j];
+            f4_fma(acc[a], wgt, vv[u]);
+          }
         }
       }
 #pragma unroll
@@ -117,7 +67,7 @@ __device__ __forceinline__ void tile_wv(const float* s_w, const float* __restric
 
 constexpr size_t XS_SMEM = (size_t)(2 * XS_T * XS_LD + 8 * XS_T * XS_T + 2 * XS_T * XS_T) * sizeof(float);
 
-__global__ void __launch_bounds__(256) xattn_small_fwd_kernel(const XsArgs a) {
+__global__ void __launch_bounds__(256, 2) xattn_small_fwd_kernel(const XsArgs a) {
   extern __shared__ __align__(16) float smem[];
   float* s_x = smem;
   float* s_y = s_x + XS_T * XS_LD;
@@ -135,7 +85,7 @@ __global__ void __launch_bounds__(256) xattn_small_fwd_kernel(const XsArgs a) {
       for (int i = threadIdx.x; i < T * T; i += blockDim.x) a.probs[((size_t)b * H + h) * T * T + i] = 0.f;
     return;
   }
-  tile_xyt(a.q + rbase * a.ldq + h * hd, a.ldq, a.k + rbase * a.ldk + h * hd, a.ldk, T, hd, s_x, s_y, s_part, s_s);
+  tile_xyt(a.q + rbase * a.ldq + h * hd, a.ldq, a.k + rbase * a.ldk + h * hd, a.ldk, T, T, hd, s_x, s_y, s_part, s_s);
   const float inv_keep = inv_keep_from_thr(a.thr);
   for (int i = w; i < T; i += 8) {  // softmax of row i, then dropout on the weights
     const float sv = lane < T ? a.scale * s_s[i * XS_T + lane] : -INFINITY;
@@ -156,7 +106,7 @@ __global__ void __launch_bounds__(256) xattn_small_fwd_kernel(const XsArgs a) {
   tile_wv<false>(s_s, a.v + rbase * a.ldv + h * hd, a.ldv, o, a.ldo, T, hd);
 }
 
-__global__ void __launch_bounds__(256) xattn_small_bwd_kernel(const XsArgs a) {
+__global__ void __launch_bounds__(256, 2) xattn_small_bwd_kernel(const XsArgs a) {
   extern __shared__ __align__(16) float smem[];
   float* s_x = smem;
   float* s_y = s_x + XS_T * XS_LD;
@@ -183,7 +133,7 @@ __global__ void __launch_bounds__(256) xattn_small_bwd_kernel(const XsArgs a) {
   const float* qp = a.q + rbase * a.ldq + h * hd;
   const float* kp = a.k + rbase * a.ldk + h * hd;
   const float* vp = a.v + rbase * a.ldv + h * hd;
-  tile_xyt(go, a.lddo, vp, a.ldv, T, hd, s_x, s_y, s_part, s_ds);  // dP~[i][j] = dO_i . v_j
+  tile_xyt(go, a.lddo, vp, a.ldv, T, T, hd, s_x, s_y, s_part, s_ds);  // dP~[i][j] = dO_i . v_j
   const float inv_keep = inv_keep_from_thr(a.thr);
   for (int i = w; i < XS_T; i += 8) {
     float p = 0.f, dp = 0.f, ks = 0.f;

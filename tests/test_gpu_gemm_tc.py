@@ -87,3 +87,18 @@ def test_auto_backend_uses_tc_for_big_and_ffma_for_skinny():
     skinny = ops.linear_fwd(A, Wc, None)
     G.assert_close("auto big", big.cpu(), A.double().cpu() @ W.double().cpu().T, TOL)
     G.assert_close("auto skinny", skinny.cpu(), A.double().cpu() @ Wc.double().cpu().T, TOL)
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("bn", ["128", "256"])
+def test_gemm_tc_both_tile_widths(bn):
+    """The 128x128 (dual TMEM accumulator) and 128x256 (setmaxnreg, 8 epilogue warps) variants, each forced."""
+    import os
+    import subprocess
+    import sys
+
+    env = dict(os.environ, IMMTSF_TC_BN=bn)
+    r = subprocess.run([sys.executable, os.path.join(os.path.dirname(__file__), "tc_bn_check.py")], env=env,
+                       capture_output=True, text=True, timeout=280)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert f"OK IMMTSF_TC_BN={bn}" in r.stdout

@@ -238,7 +238,8 @@ def test_cfg2_properties_full_size():
     """BASELINE cfg2 (B 256, N_max 16, T_f 24, d 768, C 4, T2V_XAttn + XAttn_Add):
     (1) eval output is constant over the T_f axis of E_txt and independent of t_hat values (SURVEY.md fact 4);
     (2) permuting the notes of every sample leaves Y_out unchanged (permutation invariance, 8a);
-    (3) padding more all-zero note rows leaves Y_out bit-identical (ragged layout ignores padding)."""
+    (3) padding more all-zero note rows leaves Y_out unchanged (the ragged layout ignores padding; the allocation
+        size may change which GEMM tile width is picked, hence a 1e-6 tolerance instead of bit equality)."""
     cfg = dict(ttf="TTF_T2V_XAttn", mmf="MMF_XAttn_Add", d_txt=768, C=4, H=1, kappa=0.5)
     fm = G.build_model(cfg, 768, dropout=0.1, seed=3)
     fm.eval()
@@ -256,7 +257,7 @@ def test_cfg2_properties_full_size():
     assert (E - E[:, :1]).abs().max().item() == 0.0
     assert torch.equal(y0, y1)
     G.assert_close("permutation invariance", y2.cpu(), y0.cpu(), OUT_TOL)
-    assert torch.equal(y3, y0)
+    G.assert_close("padding invariance", y3.cpu(), y0.cpu(), 1e-6)
 
 
 def test_recavg_properties_full_size():
