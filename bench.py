@@ -262,7 +262,7 @@ def run_gpu_arm(args, w):
             if graphed is not None:
                 loss = graphed(*src)  # copies into the static buffers (H2D when src is pinned host memory) + one replay
                 if world > 1:
-                    dp.allreduce_grads(params)
+                    dp.allreduce_grads(params, flat=graphed.flat_grads)
             else:
                 inp = src if resident else [t.to(dev, non_blocking=True) for t in src]
                 loss = step(inp)
@@ -299,7 +299,7 @@ def run_gpu_arm(args, w):
     if not args.eager:
         for p in params:
             p.grad = None
-        graphed = runtime.GraphedStep(fm, example=d_in, warmup=2)
+        graphed = runtime.GraphedStep(fm, example=d_in, warmup=2, flat_grads=world > 1)
     timed(W, True, graphed)
     barrier()
     clocks = ClockSampler(local)

@@ -33,18 +33,21 @@ struct PoolArgs {
   int B, T, d; float eps; uint32_t thr; SeedArg seed;
   float* E_drop; float* E_raw; float* mean; float* rstd; float* wsum;
   // backward only
-  const float* dE_drop; float* dVp; int lddv; float* dgamma; float* dbeta; float* dlog_sigma;
+  const float* dE_drop; float* dVp; int lddv; float* dgamma; float* dbeta; float* dlog_sigma; float* dS; int N_max;
 };
 
 constexpr int POOL_NB = 32;  // notes per shared-memory weight block
 
+// ncu (B 2048, N<=16, T 24, d 768) showed the first version of this kernel issue-bound, not memory-bound (47 % issue
+// utilisation with 18 warps/SM, long-scoreboard stalls ~1): hence the register cap (more resident warps), the
+// reciprocal instead of 32 IEEE divisions per thread, and only two rows of V' in flight.
 template <int NCH>
-__global__ void __launch_bounds__(256) recavg_pool_fwd_kernel(const PoolArgs a) {
+__global__ void __launch_bounds__(256, NCH == 1 ? 4 : 2) recavg_pool_fwd_kernel(const PoolArgs a) {
   constexpr int TT = 8 / NCH;
   __shared__ float s_w[POOL_NB][TT];
   __shared__ float s_red[32 * TT];
   __shared__ float s_th[TT];
-  const int b = blockIdx.x, t0 = blockIdx.y * TT;
+  const int b = blockIdx.y, t0 = blockIdx.x * TT;  // the tiles of one sample are neighbours: they share its V' rows in L2
   const int nb = a.offsets[b], ne = a.offsets[b + 1];
   const float sigma = expf(__ldg(a.log_sigma));
   const int d4 = a.d >> 2;
@@ -73,20 +76,27 @@ __global__ void __launch_bounds__(256) recavg_pool_fwd_kernel(const PoolArgs a) 
     }
     __syncthreads();
     const int cnt = min(POOL_NB, ne - n0);
-    for (int nn = 0; nn < cnt; ++nn) {
-      const float4* row = reinterpret_cast<const float4*>(a.Vp + (size_t)(n0 + nn) * a.ldv);
-      float4 v[NCH];
+    for (int nq = 0; nq < cnt; nq += 2) {  // 2 rows in flight per thread
+      float4 v[2][NCH];
 #pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        const int col4 = threadIdx.x + c * blockDim.x;
-        v[c] = col4 < d4 ? __ldg(row + col4) : f4_zero();
-      }
+      for (int u = 0; u < 2; ++u)
 #pragma unroll
-      for (int t = 0; t < TT; ++t) {
-        const float w = s_w[nn][t];
-        wsum[t] += w;
+        for (int c = 0; c < NCH; ++c) {
+          const int col4 = threadIdx.x + c * blockDim.x;
+          v[u][c] = (nq + u < cnt && col4 < d4)
+                        ? __ldg(reinterpret_cast<const float4*>(a.Vp + (size_t)(n0 + nq + u) * a.ldv) + col4) : f4_zero();
+        }
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) f4_fma(acc[t][c], w, v[c]);
+      for (int u = 0; u < 2; ++u) {
+        if (nq + u < cnt) {
+#pragma unroll
+          for (int t = 0; t < TT; ++t) {
+            const float w = s_w[nq + u][t];
+            wsum[t] += w;
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) f4_fma(acc[t][c], w, v[u][c]);
+          }
+        }
       }
     }
   }
@@ -94,11 +104,11 @@ __global__ void __launch_bounds__(256) recavg_pool_fwd_kernel(const PoolArgs a) 
   float s1[TT];
 #pragma unroll
   for (int t = 0; t < TT; ++t) {
-    const float den = fmaxf(wsum[t], 1e-6f);
+    const float inv_den = 1.f / fmaxf(wsum[t], 1e-6f);  // x * (1/den) is within 1 ulp of x / den
     float s = 0.f;
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
-      acc[t][c].x /= den; acc[t][c].y /= den; acc[t][c].z /= den; acc[t][c].w /= den;
+      acc[t][c].x *= inv_den; acc[t][c].y *= inv_den; acc[t][c].z *= inv_den; acc[t][c].w *= inv_den;
       s += f4_sum(acc[t][c]);  // columns >= d are exactly 0
     }
     s1[t] = s;
@@ -152,159 +162,150 @@ __global__ void __launch_bounds__(256) recavg_pool_fwd_kernel(const PoolArgs a) 
   }
 }
 
+// Backward, phase 1: one CTA per (sample, tile of TT query rows) -- the same decomposition as forward.
+// LayerNorm backward of the tile's rows gives dS_t = dE_raw_t / den_t (written to the dS workspace), then the
+// sample's notes are streamed once to form P2_t = sum_n c_nt V'_n for the dlog_sigma term.
 template <int NCH>
-__global__ void __launch_bounds__(256) recavg_pool_bwd_kernel(const PoolArgs a) {
+__global__ void __launch_bounds__(256) recavg_bwd_rows_kernel(const PoolArgs a) {
   constexpr int TT = 8 / NCH;
-  __shared__ float s_w[POOL_NB][TT];
   __shared__ float s_c[POOL_NB][TT];
   __shared__ float s_red[32 * TT];
   __shared__ float s_th[TT];
-  const int b = blockIdx.x;
+  const int b = blockIdx.y, t0 = blockIdx.x * TT;
   const int nb = a.offsets[b], ne = a.offsets[b + 1];
   const float sigma = expf(__ldg(a.log_sigma));
   const int d4 = a.d >> 2;
   const float inv_keep = inv_keep_from_thr(a.thr);
   const float inv_d = 1.f / (float)a.d;
+  const uint64_t seed = resolve_seed(a.seed);
+  if (threadIdx.x < TT)
+    s_th[threadIdx.x] = (t0 + threadIdx.x < a.T) ? a.t_hat[(size_t)b * a.t_bstride + t0 + threadIdx.x] : 0.f;
 
-  float4 dgam[NCH], dbet[NCH];
+  // ---- LayerNorm backward for TT rows -> dS (kept in g)
+  float4 g[TT][NCH], xh[TT][NCH], dgam[NCH], dbet[NCH];
+  float s1[TT], s2[TT], rs[TT], den[TT], dwsum[TT];
 #pragma unroll
   for (int c = 0; c < NCH; ++c) { dgam[c] = f4_zero(); dbet[c] = f4_zero(); }
-  float dls = 0.f;
-
-  for (int t0 = 0; t0 < a.T; t0 += TT) {
-    __syncthreads();
-    if (threadIdx.x < TT)
-      s_th[threadIdx.x] = (t0 + threadIdx.x < a.T) ? a.t_hat[(size_t)b * a.t_bstride + t0 + threadIdx.x] : 0.f;
-    // ---- phase 1: LayerNorm backward for TT rows -> dS (in place of g)
-    float4 g[TT][NCH], xh[TT][NCH];
-    float s1[TT], s2[TT], rs[TT], den[TT], dwsum[TT];
 #pragma unroll
-    for (int t = 0; t < TT; ++t) {
-      const int tt = t0 + t;
-      const bool ok = tt < a.T;
-      const size_t rowi = (size_t)b * a.T + (ok ? tt : 0);
-      const float mu = ok ? a.mean[rowi] : 0.f;
-      rs[t] = ok ? a.rstd[rowi] : 0.f;
-      const float ws = ok ? a.wsum[rowi] : 1.f;
-      den[t] = fmaxf(ws, 1e-6f);
-      dwsum[t] = (ok && ws >= 1e-6f) ? 1.f : 0.f;  // clamp_min passes gradient where wsum >= 1e-6
-      float p1 = 0.f, p2 = 0.f;
+  for (int t = 0; t < TT; ++t) {
+    const int tt = t0 + t;
+    const bool ok = tt < a.T;
+    const size_t rowi = (size_t)b * a.T + (ok ? tt : 0);
+    const float mu = ok ? a.mean[rowi] : 0.f;
+    rs[t] = ok ? a.rstd[rowi] : 0.f;
+    const float ws = ok ? a.wsum[rowi] : 1.f;
+    den[t] = fmaxf(ws, 1e-6f);
+    dwsum[t] = (ok && ws >= 1e-6f) ? 1.f : 0.f;  // clamp_min passes gradient where wsum >= 1e-6
+    float p1 = 0.f, p2 = 0.f;
 #pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        const int col4 = threadIdx.x + c * blockDim.x;
-        g[t][c] = f4_zero();
-        xh[t][c] = f4_zero();
-        if (ok && col4 < d4) {
-          float4 dy = __ldg(reinterpret_cast<const float4*>(a.dE_drop + rowi * a.d) + col4);
-          const float4 ks = dropout_scale4(resolve_seed(a.seed), IMMTSF_SITE_TTF_DROPOUT, rowi * d4 + col4, a.thr, inv_keep);
-          dy.x *= ks.x; dy.y *= ks.y; dy.z *= ks.z; dy.w *= ks.w;
-          const float4 x = __ldg(reinterpret_cast<const float4*>(a.E_raw + rowi * a.d) + col4);
-          float4 h;
-          h.x = (x.x - mu) * rs[t]; h.y = (x.y - mu) * rs[t]; h.z = (x.z - mu) * rs[t]; h.w = (x.w - mu) * rs[t];
-          dgam[c].x = fmaf(dy.x, h.x, dgam[c].x); dgam[c].y = fmaf(dy.y, h.y, dgam[c].y);
-          dgam[c].z = fmaf(dy.z, h.z, dgam[c].z); dgam[c].w = fmaf(dy.w, h.w, dgam[c].w);
-          f4_add(dbet[c], dy);
-          const float4 ga = __ldg(reinterpret_cast<const float4*>(a.gamma) + col4);
-          float4 gg;
-          gg.x = dy.x * ga.x; gg.y = dy.y * ga.y; gg.z = dy.z * ga.z; gg.w = dy.w * ga.w;
-          g[t][c] = gg;
-          xh[t][c] = h;
-          p1 += f4_sum(gg);
-          p2 += f4_dot(gg, h);
-        }
-      }
-      s1[t] = p1;
-      s2[t] = p2;
-    }
-    block_sum_multi<TT>(s1, s_red);
-    block_sum_multi<TT>(s2, s_red);
-#pragma unroll
-    for (int t = 0; t < TT; ++t) {
-      const float m1 = s1[t] * inv_d, m2 = s2[t] * inv_d;
-      const float sc = rs[t] / den[t];
-#pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        // dE_raw = rstd * (g - mean(g) - xhat * mean(g*xhat));  dS = dE_raw / den
-        float4 o;
-        o.x = sc * (g[t][c].x - m1 - xh[t][c].x * m2);
-        o.y = sc * (g[t][c].y - m1 - xh[t][c].y * m2);
-        o.z = sc * (g[t][c].z - m1 - xh[t][c].z * m2);
-        o.w = sc * (g[t][c].w - m1 - xh[t][c].w * m2);
-        const int col4 = threadIdx.x + c * blockDim.x;
-        g[t][c] = (col4 < d4 && t0 + t < a.T) ? o : f4_zero();
-      }
-      // d(den) = -sum_j dE_raw_j E_raw_j / den = -(s2 * eps * rstd^2) / den
-      dwsum[t] *= -(s2[t] * a.eps * rs[t] * rs[t]) / den[t];
-    }
-    // ---- phase 2: stream the segment: dV'_n, P2_t = sum_n c_nt V'_n, csum_t
-    float4 p2acc[TT][NCH];
-    float csum[TT];
-#pragma unroll
-    for (int t = 0; t < TT; ++t) {
-      csum[t] = 0.f;
-#pragma unroll
-      for (int c = 0; c < NCH; ++c) p2acc[t][c] = f4_zero();
-    }
-    for (int n0 = nb; n0 < ne; n0 += POOL_NB) {
-      __syncthreads();
-      for (int i = threadIdx.x; i < POOL_NB * TT; i += blockDim.x) {
-        const int nn = i / TT, t = i % TT, n = n0 + nn;
-        float w = 0.f, cc = 0.f;
-        if (n < ne && t0 + t < a.T) {
-          const float delta = fmaxf(s_th[t] - __ldg(a.tau + n), 0.f);
-          const float r = delta / sigma;
-          w = expf(-(r * r));
-          cc = w * 2.f * r * r;  // dw/dlog_sigma
-        }
-        s_w[nn][t] = w;
-        s_c[nn][t] = cc;
-      }
-      __syncthreads();
-      const int cnt = min(POOL_NB, ne - n0);
-      for (int nn = 0; nn < cnt; ++nn) {
-        const size_t n = (size_t)(n0 + nn);
-        const float4* row = reinterpret_cast<const float4*>(a.Vp + n * a.ldv);
-        float4* drow = reinterpret_cast<float4*>(a.dVp + n * a.lddv);
-        float4 v[NCH], dv[NCH];
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-          const int col4 = threadIdx.x + c * blockDim.x;
-          v[c] = col4 < d4 ? __ldg(row + col4) : f4_zero();
-          dv[c] = f4_zero();
-        }
-#pragma unroll
-        for (int t = 0; t < TT; ++t) {
-          const float w = s_w[nn][t], cc = s_c[nn][t];
-          csum[t] += cc;
-#pragma unroll
-          for (int c = 0; c < NCH; ++c) {
-            f4_fma(p2acc[t][c], cc, v[c]);
-            f4_fma(dv[c], w, g[t][c]);
-          }
-        }
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-          const int col4 = threadIdx.x + c * blockDim.x;
-          if (col4 < d4) {
-            if (t0 == 0) drow[col4] = dv[c];
-            else { float4 o = drow[col4]; f4_add(o, dv[c]); drow[col4] = o; }
-          }
-        }
+    for (int c = 0; c < NCH; ++c) {
+      const int col4 = threadIdx.x + c * blockDim.x;
+      g[t][c] = f4_zero();
+      xh[t][c] = f4_zero();
+      if (ok && col4 < d4) {
+        float4 dy = __ldg(reinterpret_cast<const float4*>(a.dE_drop + rowi * a.d) + col4);
+        const float4 ks = dropout_scale4(seed, IMMTSF_SITE_TTF_DROPOUT, rowi * d4 + col4, a.thr, inv_keep);
+        dy.x *= ks.x; dy.y *= ks.y; dy.z *= ks.z; dy.w *= ks.w;
+        const float4 x = __ldg(reinterpret_cast<const float4*>(a.E_raw + rowi * a.d) + col4);
+        float4 h;
+        h.x = (x.x - mu) * rs[t]; h.y = (x.y - mu) * rs[t]; h.z = (x.z - mu) * rs[t]; h.w = (x.w - mu) * rs[t];
+        dgam[c].x = fmaf(dy.x, h.x, dgam[c].x); dgam[c].y = fmaf(dy.y, h.y, dgam[c].y);
+        dgam[c].z = fmaf(dy.z, h.z, dgam[c].z); dgam[c].w = fmaf(dy.w, h.w, dgam[c].w);
+        f4_add(dbet[c], dy);
+        const float4 ga = __ldg(reinterpret_cast<const float4*>(a.gamma) + col4);
+        float4 gg;
+        gg.x = dy.x * ga.x; gg.y = dy.y * ga.y; gg.z = dy.z * ga.z; gg.w = dy.w * ga.w;
+        g[t][c] = gg;
+        xh[t][c] = h;
+        p1 += f4_sum(gg);
+        p2 += f4_dot(gg, h);
       }
     }
-    // ---- phase 3: dlog_sigma contribution of this tile
-    float part[TT];
-#pragma unroll
-    for (int t = 0; t < TT; ++t) {
-      float s = 0.f;
-#pragma unroll
-      for (int c = 0; c < NCH; ++c) s += f4_dot(g[t][c], p2acc[t][c]);
-      part[t] = s;
-    }
-    block_sum_multi<TT>(part, s_red);
-#pragma unroll
-    for (int t = 0; t < TT; ++t) dls += part[t] + dwsum[t] * csum[t];
+    s1[t] = p1;
+    s2[t] = p2;
   }
+  block_sum_multi<TT>(s1, s_red);
+  block_sum_multi<TT>(s2, s_red);
+#pragma unroll
+  for (int t = 0; t < TT; ++t) {
+    const float m1 = s1[t] * inv_d, m2 = s2[t] * inv_d;
+    const float sc = rs[t] / den[t];
+    const size_t rowi = (size_t)b * a.T + t0 + t;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      // dE_raw = rstd * (g - mean(g) - xhat * mean(g*xhat));  dS = dE_raw / den
+      float4 o;
+      o.x = sc * (g[t][c].x - m1 - xh[t][c].x * m2);
+      o.y = sc * (g[t][c].y - m1 - xh[t][c].y * m2);
+      o.z = sc * (g[t][c].z - m1 - xh[t][c].z * m2);
+      o.w = sc * (g[t][c].w - m1 - xh[t][c].w * m2);
+      const int col4 = threadIdx.x + c * blockDim.x;
+      const bool live = col4 < d4 && t0 + t < a.T;
+      g[t][c] = live ? o : f4_zero();
+      if (live) reinterpret_cast<float4*>(a.dS + rowi * a.d)[col4] = o;
+    }
+    // d(den) = -sum_j dE_raw_j E_raw_j / den = -(s2 * eps * rstd^2) / den
+    dwsum[t] *= -(s2[t] * a.eps * rs[t] * rs[t]) / den[t];
+  }
+  // ---- stream the segment: P2_t = sum_n c_nt V'_n, csum_t  (dlog_sigma)
+  float4 p2acc[TT][NCH];
+  float csum[TT];
+#pragma unroll
+  for (int t = 0; t < TT; ++t) {
+    csum[t] = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) p2acc[t][c] = f4_zero();
+  }
+  for (int n0 = nb; n0 < ne; n0 += POOL_NB) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < POOL_NB * TT; i += blockDim.x) {
+      const int nn = i / TT, t = i % TT, n = n0 + nn;
+      float cc = 0.f;
+      if (n < ne && t0 + t < a.T) {
+        const float delta = fmaxf(s_th[t] - __ldg(a.tau + n), 0.f);
+        const float r = delta / sigma;
+        cc = expf(-(r * r)) * 2.f * r * r;  // dw/dlog_sigma
+      }
+      s_c[nn][t] = cc;
+    }
+    __syncthreads();
+    const int cnt = min(POOL_NB, ne - n0);
+    for (int nq = 0; nq < cnt; nq += 4) {  // 4 rows in flight per thread
+      float4 v[4][NCH];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          const int col4 = threadIdx.x + c * blockDim.x;
+          v[u][c] = (nq + u < cnt && col4 < d4)
+                        ? __ldg(reinterpret_cast<const float4*>(a.Vp + (size_t)(n0 + nq + u) * a.ldv) + col4) : f4_zero();
+        }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (nq + u < cnt) {
+#pragma unroll
+          for (int t = 0; t < TT; ++t) {
+            const float cc = s_c[nq + u][t];
+            csum[t] += cc;
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) f4_fma(p2acc[t][c], cc, v[u][c]);
+          }
+        }
+      }
+    }
+  }
+  float part[TT];
+#pragma unroll
+  for (int t = 0; t < TT; ++t) {
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) s += f4_dot(g[t][c], p2acc[t][c]);
+    part[t] = s;
+  }
+  block_sum_multi<TT>(part, s_red);
+  float dls = 0.f;
+#pragma unroll
+  for (int t = 0; t < TT; ++t) dls += part[t] + dwsum[t] * csum[t];
 #pragma unroll
   for (int c = 0; c < NCH; ++c) {
     const int col4 = threadIdx.x + c * blockDim.x;
@@ -316,6 +317,74 @@ __global__ void __launch_bounds__(256) recavg_pool_bwd_kernel(const PoolArgs a) 
     }
   }
   if (threadIdx.x == 0) atomicAdd(a.dlog_sigma, dls);
+}
+
+// Backward, phase 2: one CTA per (sample, tile of 8 notes): dV'_n = sum_t w_nt dS_t with register accumulators,
+// dS rows streamed 4 at a time -- every dV' row is written exactly once (no read-modify-write).
+constexpr int POOL_TB = 32;  // query rows per shared-memory weight block
+template <int NCH>
+__global__ void __launch_bounds__(256) recavg_bwd_notes_kernel(const PoolArgs a) {
+  constexpr int POOL_NT = 8 / NCH;  // notes per CTA
+  __shared__ float s_w[POOL_TB][POOL_NT];
+  const int b = blockIdx.y;
+  const int nb = a.offsets[b], ne = a.offsets[b + 1];
+  const int n0 = nb + blockIdx.x * POOL_NT;
+  if (n0 >= ne) return;
+  const int ncnt = min(POOL_NT, ne - n0);
+  const float sigma = expf(__ldg(a.log_sigma));
+  const int d4 = a.d >> 2;
+  float4 acc[POOL_NT][NCH];
+#pragma unroll
+  for (int u = 0; u < POOL_NT; ++u)
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) acc[u][c] = f4_zero();
+  for (int t0 = 0; t0 < a.T; t0 += POOL_TB) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < POOL_TB * POOL_NT; i += blockDim.x) {
+      const int tt = i / POOL_NT, u = i % POOL_NT;
+      float w = 0.f;
+      if (t0 + tt < a.T && u < ncnt) {
+        const float delta = fmaxf(a.t_hat[(size_t)b * a.t_bstride + t0 + tt] - __ldg(a.tau + n0 + u), 0.f);
+        const float r = delta / sigma;
+        w = expf(-(r * r));
+      }
+      s_w[tt][u] = w;
+    }
+    __syncthreads();
+    const int tcnt = min(POOL_TB, a.T - t0);
+    for (int tq = 0; tq < tcnt; tq += 4) {
+      float4 g[4][NCH];
+#pragma unroll
+      for (int v = 0; v < 4; ++v)
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          const int col4 = threadIdx.x + c * blockDim.x;
+          g[v][c] = (tq + v < tcnt && col4 < d4)
+                        ? __ldg(reinterpret_cast<const float4*>(a.dS + ((size_t)b * a.T + t0 + tq + v) * a.d) + col4) : f4_zero();
+        }
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        if (tq + v < tcnt) {
+#pragma unroll
+          for (int u = 0; u < POOL_NT; ++u) {
+            const float w = s_w[tq + v][u];
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) f4_fma(acc[u][c], w, g[v][c]);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < POOL_NT; ++u) {
+    if (u < ncnt) {
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const int col4 = threadIdx.x + c * blockDim.x;
+        if (col4 < d4) reinterpret_cast<float4*>(a.dVp + (size_t)(n0 + u) * a.lddv)[col4] = acc[u][c];
+      }
+    }
+  }
 }
 
 static int pool_geometry(int d, int& nch, int& threads) {
@@ -345,7 +414,7 @@ extern "C" int immtsf_recavg_pool_fwd(const float* Vp, int ldv, const float* tau
   a.thr = drop_thr; a.seed = make_seed(seed); a.E_drop = E_drop; a.E_raw = E_raw; a.mean = mean; a.rstd = rstd; a.wsum = wsum;
   cudaStream_t st = (cudaStream_t)stream;
   const int TT = 8 / nch;
-  dim3 grid(B, ceil_div(T, TT));
+  dim3 grid(ceil_div(T, TT), B);
   if (nch == 1) recavg_pool_fwd_kernel<1><<<grid, threads, 0, st>>>(a);
   else if (nch == 2) recavg_pool_fwd_kernel<2><<<grid, threads, 0, st>>>(a);
   else recavg_pool_fwd_kernel<4><<<grid, threads, 0, st>>>(a);
@@ -356,26 +425,35 @@ extern "C" int immtsf_recavg_pool_fwd(const float* Vp, int ldv, const float* tau
 extern "C" int immtsf_recavg_pool_bwd(const float* dE_drop, const float* E_raw, const float* mean, const float* rstd,
                                       const float* wsum, const float* Vp, int ldv, const float* tau_flat,
                                       const int32_t* offsets, const float* t_hat, int t_hat_bstride,
-                                      const float* log_sigma, const float* gamma, int B, int T, int d,
-                                      uint32_t drop_thr, uint64_t seed, float* dVp, int lddv, float* dgamma,
+                                      const float* log_sigma, const float* gamma, int B, int T, int d, int N_max,
+                                      uint32_t drop_thr, uint64_t seed, float* dS, float* dVp, int lddv, float* dgamma,
                                       float* dbeta, float* dlog_sigma, void* stream) {
   if (B == 0 || T == 0) return IMMTSF_OK;
   IMMTSF_REQUIRE(dE_drop && E_raw && mean && rstd && wsum && Vp && tau_flat && offsets && t_hat && log_sigma && gamma &&
-                     dVp && dgamma && dbeta && dlog_sigma, "recavg_pool_bwd: null pointer");
+                     dS && dVp && dgamma && dbeta && dlog_sigma, "recavg_pool_bwd: null pointer");
   int nch, threads;
   IMMTSF_REQUIRE(pool_geometry(d, nch, threads) == 0, "recavg_pool_bwd: d=%d must be a multiple of 4 and <= 4096", d);
-  IMMTSF_REQUIRE((ldv & 3) == 0 && (lddv & 3) == 0 && ((uintptr_t)Vp & 15) == 0 && ((uintptr_t)dVp & 15) == 0,
-                 "recavg_pool_bwd: Vp/dVp must be 16B aligned with ld %% 4 == 0");
+  IMMTSF_REQUIRE((ldv & 3) == 0 && (lddv & 3) == 0 && ((uintptr_t)Vp & 15) == 0 && ((uintptr_t)dVp & 15) == 0 &&
+                     ((uintptr_t)dS & 15) == 0, "recavg_pool_bwd: Vp/dVp/dS must be 16B aligned with ld %% 4 == 0");
+  IMMTSF_REQUIRE(N_max >= 1, "recavg_pool_bwd: N_max must be >= 1");
   PoolArgs a = {};
   a.Vp = Vp; a.ldv = ldv; a.tau = tau_flat; a.offsets = offsets; a.t_hat = t_hat; a.t_bstride = t_hat_bstride;
   a.log_sigma = log_sigma; a.gamma = gamma; a.B = B; a.T = T; a.d = d; a.eps = 1e-5f;
   a.thr = drop_thr; a.seed = make_seed(seed); a.E_raw = const_cast<float*>(E_raw); a.mean = const_cast<float*>(mean);
   a.rstd = const_cast<float*>(rstd); a.wsum = const_cast<float*>(wsum);
   a.dE_drop = dE_drop; a.dVp = dVp; a.lddv = lddv; a.dgamma = dgamma; a.dbeta = dbeta; a.dlog_sigma = dlog_sigma;
+  a.dS = dS; a.N_max = N_max;
   cudaStream_t st = (cudaStream_t)stream;
-  if (nch == 1) recavg_pool_bwd_kernel<1><<<B, threads, 0, st>>>(a);
-  else if (nch == 2) recavg_pool_bwd_kernel<2><<<B, threads, 0, st>>>(a);
-  else recavg_pool_bwd_kernel<4><<<B, threads, 0, st>>>(a);
-  IMMTSF_CHECK_LAUNCH("recavg_pool_bwd");
+  const int TT = 8 / nch;
+  dim3 grid1(ceil_div(T, TT), B);
+  if (nch == 1) recavg_bwd_rows_kernel<1><<<grid1, threads, 0, st>>>(a);
+  else if (nch == 2) recavg_bwd_rows_kernel<2><<<grid1, threads, 0, st>>>(a);
+  else recavg_bwd_rows_kernel<4><<<grid1, threads, 0, st>>>(a);
+  IMMTSF_CHECK_LAUNCH("recavg_bwd_rows");
+  dim3 grid2(ceil_div(N_max, 8 / nch), B);
+  if (nch == 1) recavg_bwd_notes_kernel<1><<<grid2, threads, 0, st>>>(a);
+  else if (nch == 2) recavg_bwd_notes_kernel<2><<<grid2, threads, 0, st>>>(a);
+  else recavg_bwd_notes_kernel<4><<<grid2, threads, 0, st>>>(a);
+  IMMTSF_CHECK_LAUNCH("recavg_bwd_notes");
   return IMMTSF_OK;
 }

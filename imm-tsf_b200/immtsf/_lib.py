@@ -37,7 +37,7 @@ SIGNATURES = {
     "immtsf_gemm_plan": [I, I, I, I, I, P, I, P, I, P, I, I],
     "immtsf_colsum": [P, I, I, I, P, F, P, P, SZ, P],
     "immtsf_recavg_pool_fwd": [P, I, P, P, P, I, P, P, P, I, I, I, F, U32, U64, P, P, P, P, P, P],
-    "immtsf_recavg_pool_bwd": [P, P, P, P, P, P, I, P, P, P, I, P, P, I, I, I, U32, U64, P, I, P, P, P, P],
+    "immtsf_recavg_pool_bwd": [P, P, P, P, P, P, I, P, P, P, I, P, P, I, I, I, I, U32, U64, P, P, I, P, P, P, P],
     "immtsf_time2vec_fwd": [P, P, P, P, P, I, P, I, P, I, P],
     "immtsf_time2vec_bwd": [P, I, P, P, P, I, P, P, P, P, P, I, P],
     "immtsf_segattn_fwd": [P, P, P, I, I, I, I, I, I, U32, U64, P, P, P],

@@ -31,10 +31,18 @@ def shard_batch(tensors, rank: int, world: int):
     return [t if (t.dim() == 1 and t.shape[0] != B) else t[lo:hi] for t in tensors]
 
 
-def allreduce_grads(params: Iterable[torch.nn.Parameter], group=None, average: bool = False) -> Optional[torch.Tensor]:
-    """One SUM all-reduce over a flat bucket of every existing .grad; results are copied back in place."""
+def allreduce_grads(params: Iterable[torch.nn.Parameter], group=None, average: bool = False,
+                    flat: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
+    """One SUM all-reduce over a flat bucket of every existing .grad; results are copied back in place.
+    flat: a buffer the gradients already live in as views (runtime.GraphedStep(flat_grads=True)) -- reduced in
+    place, no gather / scatter copies."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return None
+    if flat is not None:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        if average:
+            flat /= dist.get_world_size(group)
+        return flat
     ps: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
     for p in ps:
         if p.grad is None:  # a rank whose shard produced no gradient still has to take part

@@ -248,13 +248,14 @@ def recavg_pool_fwd(Vp, r: RaggedNotes, t_hat, log_sigma, gamma, beta, T, d, thr
 def recavg_pool_bwd(dE_drop, E_raw, mean, rstd, wsum, Vp, r: RaggedNotes, t_hat, log_sigma, gamma, T, d, thr, seed):
     dev = Vp.device
     dVp = torch.empty(r.M_alloc, d, dtype=torch.float32, device=dev)
+    dS = torch.empty(r.B * T, d, dtype=torch.float32, device=dev)
     dgamma = torch.zeros(d, dtype=torch.float32, device=dev)
     dbeta = torch.zeros(d, dtype=torch.float32, device=dev)
     dls = torch.zeros((), dtype=torch.float32, device=dev)
     bstride = 0 if t_hat.dim() == 1 else t_hat.stride(0)
     _lib.call("immtsf_recavg_pool_bwd", _p(dE_drop), _p(E_raw), _p(mean), _p(rstd), _p(wsum), _p(Vp), Vp.stride(0),
-              _p(r.tau_flat), _p(r.offsets), _p(t_hat), bstride, _p(log_sigma), _p(gamma), r.B, T, d, thr, seed,
-              _p(dVp), d, _p(dgamma), _p(dbeta), _p(dls), _stream())
+              _p(r.tau_flat), _p(r.offsets), _p(t_hat), bstride, _p(log_sigma), _p(gamma), r.B, T, d, max(r.N, 1), thr, seed,
+              _p(dS), _p(dVp), d, _p(dgamma), _p(dbeta), _p(dls), _stream())
     zero_pad_rows(dVp, d, r.m_dev, r.M_alloc)
     return dVp, dgamma, dbeta, dls
 

@@ -79,7 +79,7 @@ class GraphedStep:
     The reference's NaN ValueErrors need a device->host read, which a graph cannot contain: call check_nan() after a
     step when that guard is wanted (one sync)."""
 
-    def __init__(self, fusion, example, loss_fn=None, extras=(), warmup: int = 3):
+    def __init__(self, fusion, example, loss_fn=None, extras=(), warmup: int = 3, flat_grads: bool = False):
         from . import _lib
 
         if not torch.cuda.is_available():
@@ -101,12 +101,25 @@ class GraphedStep:
                 self._eager()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        for p in self.params:
-            p.grad = None
+        # flat_grads: every parameter gradient is a view into ONE buffer, zeroed inside the graph and accumulated
+        # in place by autograd, so the data-parallel all-reduce (dp.allreduce_grads(flat=...)) needs no gather copy
+        self.flat_grads = None
+        if flat_grads:
+            total = sum(p.numel() for p in self.params)
+            self.flat_grads = torch.zeros(total, dtype=torch.float32, device=dev)
+            off = 0
+            for p in self.params:
+                p.grad = self.flat_grads[off:off + p.numel()].view_as(p)
+                off += p.numel()
+        else:
+            for p in self.params:
+                p.grad = None
         self.static_in[3].grad = None
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             _lib.call("immtsf_seed_advance", self.seed_offset.data_ptr(), 1, ops._stream())
+            if self.flat_grads is not None:
+                self.flat_grads.zero_()
             out, loss = self._eager()
         self.Y_out, self.loss = out.detach(), loss.detach()
         self.flags = getattr(fusion, "_last_flags", None)

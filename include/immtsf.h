@@ -127,11 +127,13 @@ int immtsf_recavg_pool_fwd(const float* Vp, int ldv, const float* tau_flat, cons
                            const float* gamma, const float* beta, int B, int T, int d, float eps,
                            uint32_t drop_thr, uint64_t seed, float* E_drop, float* E_raw,
                            float* mean, float* rstd, float* wsum, void* stream);
+/* dS [B*T, d] is caller-owned scratch (the LayerNorm-backward rows, written by the first of the two kernels
+ * and read by the second); N_max bounds the notes per sample (grid size only). */
 int immtsf_recavg_pool_bwd(const float* dE_drop, const float* E_raw, const float* mean, const float* rstd,
                            const float* wsum, const float* Vp, int ldv, const float* tau_flat,
                            const int32_t* offsets, const float* t_hat, int t_hat_bstride,
-                           const float* log_sigma, const float* gamma, int B, int T, int d,
-                           uint32_t drop_thr, uint64_t seed, float* dVp, int lddv, float* dgamma,
+                           const float* log_sigma, const float* gamma, int B, int T, int d, int N_max,
+                           uint32_t drop_thr, uint64_t seed, float* dS, float* dVp, int lddv, float* dgamma,
                            float* dbeta, float* dlog_sigma, void* stream);
 
 /* ---- Time2Vec (TTF_T2V_XAttn.py:20-24,136) written straight into the

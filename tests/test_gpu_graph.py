@@ -69,3 +69,32 @@ def test_graph_replay_draws_fresh_dropout_masks():
         assert torch.equal(a, b)
     finally:
         runtime.SEEDS.fixed = None
+
+
+def test_graph_flat_gradient_bucket():
+    """flat_grads=True: every p.grad is a view into one buffer that the graph zeroes and autograd accumulates into;
+    the bucket must equal the eager gradients (it is what the data-parallel all-reduce sends)."""
+    from immtsf import runtime
+
+    cfg = dict(ttf="TTF_T2V_XAttn", mmf="MMF_GR_Add", d_txt=64, C=4, H=1, kappa=0.5)
+    fm = G.build_model(cfg, 96, dropout=0.0, seed=1)
+    G.randomise_(fm, 2)
+    fm.train()
+    notes, tau, t_hat, Y, _ = G.synth_batch(12, 6, 10, 96, 4, 21)
+    ex = [t.cuda() for t in (notes, tau, t_hat, Y)]
+    Gw = torch.randn(12, 10, 4, generator=torch.Generator().manual_seed(5)).cuda()
+    step = runtime.GraphedStep(fm, example=ex, loss_fn=lambda out, g: (out * g).sum(), extras=(Gw,), flat_grads=True)
+    try:
+        for _ in range(2):  # the second replay must not accumulate on top of the first
+            step(*ex, Gw)
+        flat = step.flat_grads.clone()
+        views = {k: p.grad.clone() for k, p in fm.named_parameters()}
+        assert flat.numel() == sum(p.numel() for p in fm.parameters())
+        ref = G.gpu_run(fm, notes, tau, t_hat, Y, Gw.cpu(), train=True)
+        off = 0
+        for k, p in fm.named_parameters():
+            G.assert_close(k, views[k].cpu(), ref["grads"][k], 1e-5, floor=1e-3)
+            assert torch.equal(flat[off:off + p.numel()].view_as(p), views[k])
+            off += p.numel()
+    finally:
+        step.close()
