@@ -51,6 +51,13 @@ WORKLOADS = {
     "cfg3": dict(ttf="TTF_T2V_XAttn", mmf="MMF_GR_Add", B=256, N=64, T=28, d_model=4096, d_txt=768, C=5, H=1, kappa=0.5,
                  history=14.0, pred=14.0, cpu_sample_B=16,
                  name="cfg3: T2V_XAttn+GR_Add, B256 N<=64 T28 d_model4096->768 C5 (BASELINE.json configs[2])"),
+    # configs[4]: MIMIC-shaped (many variables, long irregular histories), per-GPU batch of the 8-GPU run
+    "cfg5": dict(ttf="TTF_T2V_XAttn", mmf="MMF_XAttn_Add", B=256, N=32, T=192, d_model=768, d_txt=768, C=96, H=1, kappa=0.5,
+                 history=24.0, pred=24.0, cpu_sample_B=4,
+                 name="cfg5: T2V_XAttn+XAttn_Add, B256 N<=32 T192 d768 C96 (BASELINE.json configs[4], per-GPU shard)"),
+    "cfg5g": dict(ttf="TTF_T2V_XAttn", mmf="MMF_GR_Add", B=256, N=32, T=192, d_model=768, d_txt=768, C=96, H=1, kappa=0.5,
+                  history=24.0, pred=24.0, cpu_sample_B=4,
+                  name="cfg5g: T2V_XAttn+GR_Add, B256 N<=32 T192 d768 C96 (MIMIC-shaped, GRU fusion)"),
 }
 DROPOUT = 0.1
 # dram__bytes_read.sum + dram__bytes_write.sum of one gemm_tc_kernel launch (M6144 N768 K768) from the ncu --set full

@@ -92,6 +92,16 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+               ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+// 2-D tile of a plain matrix, or of batch (b1, b2) of a 4-D [batch1][batch2][rows][cols] view
+__device__ __forceinline__ void tma_tile(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int batched, int b2,
+                                         int b1) {
+  if (batched) tma_load_4d(dst, map, bar, c0, c1, b2, b1);
+  else tma_load_2d(dst, map, bar, c0, c1);
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -142,6 +152,10 @@ struct TcArgs {
   int ragged_dim;
   float* partial;  // split-K partial tiles [splitk][M][ldp]
   int ldp;
+  // batched mode (attention contractions): blockIdx.z = b1 * batch2 + b2, operands are 4-D tensor maps,
+  // C(b1, b2) = C + b1 * c_s1 + b2 * c_s2; no split-K, no ragged bounds
+  int batched, batch2;
+  long c_s1, c_s2;
 };
 
 template <bool A_MN, bool B_MN, int BN>
@@ -162,9 +176,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
   const uint32_t bars = base + STAGES * STAGE_BYTES;  // full[STAGES], empty[STAGES], tfull[2], tempty[2], tmem_ptr
   const uint32_t bar_full = bars, bar_empty = bars + 8 * STAGES, bar_tfull = bars + 16 * STAGES;
   const uint32_t bar_tempty = bar_tfull + 16, tmem_slot = bar_tempty + 16;
-  // split-K: blockIdx.z owns a contiguous range of k-blocks; partial tiles are combined with fp32 atomics
-  const int kb_per = (nkb + (int)gridDim.z - 1) / (int)gridDim.z;
-  const int z_kb0 = min(nkb, (int)blockIdx.z * kb_per), z_kb1 = min(nkb, z_kb0 + kb_per);
+  // split-K: blockIdx.z owns a contiguous range of k-blocks (partial tiles are summed by splitk_reduce_kernel);
+  // batched: blockIdx.z is the batch index and every CTA runs the whole contraction
+  const int nsplit = g.batched ? 1 : (int)gridDim.z, zsplit = g.batched ? 0 : (int)blockIdx.z;
+  const int bz1 = g.batched ? (int)blockIdx.z / g.batch2 : 0, bz2 = g.batched ? (int)blockIdx.z % g.batch2 : 0;
+  const int kb_per = (nkb + nsplit - 1) / nsplit;
+  const int z_kb0 = min(nkb, zsplit * kb_per), z_kb1 = min(nkb, z_kb0 + kb_per);
   const int nchunks = (z_kb1 - z_kb0 + KC - 1) / KC;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -204,23 +221,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
       mbar_expect_tx(fb, STAGE_BYTES);
       const int k0 = kb * BKT;
       if (!A_MN) {
-        tma_load_2d(sa_h, &mapAh, fb, k0, m0);
-        tma_load_2d(sa_l, &mapAl, fb, k0, m0);
+        tma_tile(sa_h, &mapAh, fb, k0, m0, g.batched, bz2, bz1);
+        tma_tile(sa_l, &mapAl, fb, k0, m0, g.batched, bz2, bz1);
       } else {
 #pragma unroll
         for (int j = 0; j < BM / 32; ++j) {
-          tma_load_2d(sa_h + j * 4096, &mapAh, fb, m0 + 32 * j, k0);
-          tma_load_2d(sa_l + j * 4096, &mapAl, fb, m0 + 32 * j, k0);
+          tma_tile(sa_h + j * 4096, &mapAh, fb, m0 + 32 * j, k0, g.batched, bz2, bz1);
+          tma_tile(sa_l + j * 4096, &mapAl, fb, m0 + 32 * j, k0, g.batched, bz2, bz1);
         }
       }
       if (!B_MN) {
-        tma_load_2d(sb_h, &mapBh, fb, k0, n0);
-        tma_load_2d(sb_l, &mapBl, fb, k0, n0);
+        tma_tile(sb_h, &mapBh, fb, k0, n0, g.batched, bz2, bz1);
+        tma_tile(sb_l, &mapBl, fb, k0, n0, g.batched, bz2, bz1);
       } else {
 #pragma unroll
         for (int j = 0; j < BN / 32; ++j) {
-          tma_load_2d(sb_h + j * 4096, &mapBh, fb, n0 + 32 * j, k0);
-          tma_load_2d(sb_l + j * 4096, &mapBl, fb, n0 + 32 * j, k0);
+          tma_tile(sb_h + j * 4096, &mapBh, fb, n0 + 32 * j, k0, g.batched, bz2, bz1);
+          tma_tile(sb_l + j * 4096, &mapBl, fb, n0 + 32 * j, k0, g.batched, bz2, bz1);
         }
       }
     }
@@ -292,18 +309,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
     }
     const int row = m0 + q * 32 + lane;
     const bool live = row < M;
-    if (gridDim.z > 1) {
+    if (nsplit > 1) {
       // split-K: this split's partial tile goes to the workspace [z][M][ldp]; splitk_reduce_kernel sums the
       // splits in a fixed order (deterministic, unlike atomics) and applies alpha / beta / bias
       if (row < g.M) {
-        float* prow = g.partial + ((size_t)blockIdx.z * g.M + row) * g.ldp + n0 + ch;
+        float* prow = g.partial + ((size_t)zsplit * g.M + row) * g.ldp + n0 + ch;
 #pragma unroll
         for (int j4 = 0; j4 < 128 / 4; ++j4)
           if (n0 + ch + j4 * 4 < g.ldp)
             *reinterpret_cast<float4*>(prow + j4 * 4) = make_float4(acc[j4 * 4], acc[j4 * 4 + 1], acc[j4 * 4 + 2], acc[j4 * 4 + 3]);
       }
     } else if (row < g.M) {
-      float* crow = g.C + (size_t)row * g.ldc + n0 + ch;
+      float* crow = g.C + bz1 * g.c_s1 + bz2 * g.c_s2 + (size_t)row * g.ldc + n0 + ch;
 #pragma unroll
       for (int j4 = 0; j4 < 128 / 4; ++j4) {
         const int n = n0 + ch + j4 * 4;
@@ -437,6 +454,21 @@ int make_map(CUtensorMap* m, const float* ptr, int rows, int cols, int ld, int b
   cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1u, 1u};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -2;
+}
+
+// 4-D fp32 view [batch1][batch2][rows][cols] with element strides (s1, s2, ld, 1); box = {32 cols, box_rows, 1, 1}
+int make_map4(CUtensorMap* m, const float* ptr, int rows, int cols, long ld, long s2, long s1, int batch2, int batch1, int box_rows,
+              bool mn_major) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return -1;
+  cuuint64_t dims[4] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batch2, (cuuint64_t)batch1};
+  cuuint64_t strides[3] = {(cuuint64_t)ld * 4, (cuuint64_t)s2 * 4, (cuuint64_t)s1 * 4};
+  cuuint32_t box[4] = {32u, (cuuint32_t)box_rows, 1u, 1u};
+  cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : -2;
@@ -606,6 +638,7 @@ int immtsf_gemm_tc(int transA, int transB, int M, int N, int K, float alpha, con
   TcArgs g;
   g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K; g.alpha = alpha; g.beta = beta; g.bias = bias;
   g.ragged = ragged; g.ragged_dim = ragged_dim;
+  g.batched = 0; g.batch2 = 1; g.c_s1 = 0; g.c_s2 = 0;
   dim3 grid(ceil_div(N, bn), ceil_div(M, BM));
   const int splitk = choose_splitk(M, N, K, bn);
   g.partial = nullptr; g.ldp = 0;
@@ -644,5 +677,84 @@ int immtsf_gemm_tc(int transA, int transB, int M, int N, int K, float alpha, con
     splitk_reduce_kernel<<<rg, 256, 0, st>>>(C, ldc, M, N, alpha, beta, bias, g.partial, g.ldp, splitk, ragged, ragged_dim);
     IMMTSF_CHECK_LAUNCH("splitk_reduce");
   }
+  return IMMTSF_OK;
+}
+
+
+// ---------------------------------------------------------------- batched products (attention contractions)
+// C(b1,b2)[M,N] = alpha * op(A(b1,b2)) op(B(b1,b2)) + beta * C(b1,b2), X(b1,b2) = X + b1*x_s1 + b2*x_s2 (element strides).
+// Operands are read through 4-D tensor maps, so tiles that overhang a batch's rows / columns are zero-filled by TMA
+// and the contraction never bleeds into the neighbouring batch.  The lo parts are split over each operand's whole
+// flat extent into the workspace.
+static size_t flat_extent(int rows, int cols, long ld, long s1, long s2, int batch1, int batch2) {
+  return (size_t)((long)(batch1 - 1) * s1 + (long)(batch2 - 1) * s2 + (long)(rows - 1) * ld + cols);
+}
+
+extern "C" size_t immtsf_gemm_batched_workspace_bytes(int transA, int transB, int M, int N, int K, int lda, long a_s1, long a_s2,
+                                                      int ldb, long b_s1, long b_s2, int batch1, int batch2) {
+  const int ra = transA ? K : M, ca = transA ? M : K, rb = transB ? N : K, cb = transB ? K : N;
+  return align_up(flat_extent(ra, ca, lda, a_s1, a_s2, batch1, batch2) * 4 + 16, 256) +
+         align_up(flat_extent(rb, cb, ldb, b_s1, b_s2, batch1, batch2) * 4 + 16, 256) + 256;
+}
+
+extern "C" int immtsf_gemm_batched(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda, long a_s1,
+                                   long a_s2, const float* B, int ldb, long b_s1, long b_s2, float beta, float* C, int ldc,
+                                   long c_s1, long c_s2, int batch1, int batch2, void* workspace, size_t workspace_bytes,
+                                   void* stream) {
+  if (M <= 0 || N <= 0 || batch1 <= 0 || batch2 <= 0) return IMMTSF_OK;
+  IMMTSF_REQUIRE(A && B && C && K >= 1, "gemm_batched: null operand or K < 1");
+  IMMTSF_REQUIRE((long)batch1 * batch2 <= 65535, "gemm_batched: at most 65535 batches");
+  auto ok16 = [](const void* p, long ld, long s1, long s2) { return ((uintptr_t)p & 15) == 0 && (ld & 3) == 0 && (s1 & 3) == 0 && (s2 & 3) == 0; };
+  IMMTSF_REQUIRE(ok16(A, lda, a_s1, a_s2) && ok16(B, ldb, b_s1, b_s2) && ok16(C, ldc, c_s1, c_s2),
+                 "gemm_batched: operands must be 16B aligned with every stride a multiple of 4 floats");
+  IMMTSF_REQUIRE(get_encode() != nullptr, "gemm_batched: cuTensorMapEncodeTiled unavailable");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t need = immtsf_gemm_batched_workspace_bytes(transA, transB, M, N, K, lda, a_s1, a_s2, ldb, b_s1, b_s2, batch1, batch2);
+  IMMTSF_REQUIRE(workspace != nullptr && workspace_bytes >= need, "gemm_batched: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
+  const int ra = transA ? K : M, ca = transA ? M : K, rb = transB ? N : K, cb = transB ? K : N;
+  const size_t ea = flat_extent(ra, ca, lda, a_s1, a_s2, batch1, batch2), eb = flat_extent(rb, cb, ldb, b_s1, b_s2, batch1, batch2);
+  uint8_t* w = (uint8_t*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+  float* Al = (float*)w;
+  float* Bl = (float*)(w + align_up(ea * 4 + 16, 256));
+  // lo over the flat extents (1 x extent "matrices"; the tail beyond a multiple of 4 is handled by the kernel)
+  int rc = launch_split_lo(A, (int)align_up(ea, 4), 1, (int)ea, Al, (int)align_up(ea, 4), nullptr, 0, st);
+  if (rc) return rc;
+  rc = launch_split_lo(B, (int)align_up(eb, 4), 1, (int)eb, Bl, (int)align_up(eb, 4), nullptr, 0, st);
+  if (rc) return rc;
+  const int bn = (N > 128 && ceil_div(N, 256) * ceil_div(M, BM) * batch1 * batch2 >= 148) ? 256 : 128;
+  const int boxA = transA ? 32 : BM, boxB = transB ? bn : 32;
+  CUtensorMap mAh, mAl, mBh, mBl;
+  if (make_map4(&mAh, A, ra, ca, lda, a_s2, a_s1, batch2, batch1, boxA, transA != 0) ||
+      make_map4(&mAl, Al, ra, ca, lda, a_s2, a_s1, batch2, batch1, boxA, transA != 0) ||
+      make_map4(&mBh, B, rb, cb, ldb, b_s2, b_s1, batch2, batch1, boxB, transB == 0) ||
+      make_map4(&mBl, Bl, rb, cb, ldb, b_s2, b_s1, batch2, batch1, boxB, transB == 0)) {
+    immtsf_set_error("gemm_batched: cuTensorMapEncodeTiled failed");
+    return IMMTSF_ERR_LAUNCH;
+  }
+  TcArgs g;
+  g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K; g.alpha = alpha; g.beta = beta; g.bias = nullptr;
+  g.ragged = nullptr; g.ragged_dim = 0; g.partial = nullptr; g.ldp = 0;
+  g.batched = 1; g.batch2 = batch2; g.c_s1 = c_s1; g.c_s2 = c_s2;
+  dim3 grid(ceil_div(N, bn), ceil_div(M, BM), batch1 * batch2);
+  static bool attr_done = false;
+  if (!attr_done) {
+#define TC_ATTR(a, b)                                                                                                      \
+  cudaFuncSetAttribute(gemm_tc_kernel<a, b, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128>::SMEM_BYTES);     \
+  cudaFuncSetAttribute(gemm_tc_kernel<a, b, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<256>::SMEM_BYTES)
+    TC_ATTR(false, false); TC_ATTR(false, true); TC_ATTR(true, false); TC_ATTR(true, true);
+#undef TC_ATTR
+    attr_done = true;
+  }
+#define TC_LAUNCH(a, b)                                                                                                   \
+  do {                                                                                                                    \
+    if (bn == 128) gemm_tc_kernel<a, b, 128><<<grid, Cfg<128>::THREADS, Cfg<128>::SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, g); \
+    else gemm_tc_kernel<a, b, 256><<<grid, Cfg<256>::THREADS, Cfg<256>::SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, g);          \
+  } while (0)
+  if (!transA && transB) TC_LAUNCH(false, false);
+  else if (!transA && !transB) TC_LAUNCH(false, true);
+  else if (transA && !transB) TC_LAUNCH(true, true);
+  else TC_LAUNCH(true, false);
+#undef TC_LAUNCH
+  IMMTSF_CHECK_LAUNCH("gemm_tc_batched");
   return IMMTSF_OK;
 }

@@ -162,26 +162,20 @@ __global__ void __launch_bounds__(256, NCH == 1 ? 4 : 2) recavg_pool_fwd_kernel(
   }
 }
 
-// Backward, phase 1: one CTA per (sample, tile of TT query rows) -- the same decomposition as forward.
-// LayerNorm backward of the tile's rows gives dS_t = dE_raw_t / den_t (written to the dS workspace), then the
-// sample's notes are streamed once to form P2_t = sum_n c_nt V'_n for the dlog_sigma term.
+// Backward, phase 1: one CTA per (sample, tile of TT query rows): LayerNorm backward of the tile's rows gives
+// dS_t = dE_raw_t / den_t (written to the dS scratch) and the scalar d(den_t) (written behind it).  No note is
+// touched here: every term that contracts over notes is formed in phase 2.
 template <int NCH>
-__global__ void __launch_bounds__(256) recavg_bwd_rows_kernel(const PoolArgs a) {
+__global__ void __launch_bounds__(256, NCH == 1 ? 3 : 2) recavg_bwd_rows_kernel(const PoolArgs a) {
   constexpr int TT = 8 / NCH;
-  __shared__ float s_c[POOL_NB][TT];
   __shared__ float s_red[32 * TT];
-  __shared__ float s_th[TT];
   const int b = blockIdx.y, t0 = blockIdx.x * TT;
-  const int nb = a.offsets[b], ne = a.offsets[b + 1];
-  const float sigma = expf(__ldg(a.log_sigma));
   const int d4 = a.d >> 2;
   const float inv_keep = inv_keep_from_thr(a.thr);
   const float inv_d = 1.f / (float)a.d;
   const uint64_t seed = resolve_seed(a.seed);
-  if (threadIdx.x < TT)
-    s_th[threadIdx.x] = (t0 + threadIdx.x < a.T) ? a.t_hat[(size_t)b * a.t_bstride + t0 + threadIdx.x] : 0.f;
+  float* dwsum_out = a.dS + (size_t)a.B * a.T * a.d;  // [B*T] scalars behind the dS rows
 
-  // ---- LayerNorm backward for TT rows -> dS (kept in g)
   float4 g[TT][NCH], xh[TT][NCH], dgam[NCH], dbet[NCH];
   float s1[TT], s2[TT], rs[TT], den[TT], dwsum[TT];
 #pragma unroll
@@ -228,84 +222,25 @@ __global__ void __launch_bounds__(256) recavg_bwd_rows_kernel(const PoolArgs a) 
   block_sum_multi<TT>(s2, s_red);
 #pragma unroll
   for (int t = 0; t < TT; ++t) {
+    if (t0 + t >= a.T) continue;
     const float m1 = s1[t] * inv_d, m2 = s2[t] * inv_d;
     const float sc = rs[t] / den[t];
     const size_t rowi = (size_t)b * a.T + t0 + t;
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
+      const int col4 = threadIdx.x + c * blockDim.x;
+      if (col4 >= d4) continue;
       // dE_raw = rstd * (g - mean(g) - xhat * mean(g*xhat));  dS = dE_raw / den
       float4 o;
       o.x = sc * (g[t][c].x - m1 - xh[t][c].x * m2);
       o.y = sc * (g[t][c].y - m1 - xh[t][c].y * m2);
       o.z = sc * (g[t][c].z - m1 - xh[t][c].z * m2);
       o.w = sc * (g[t][c].w - m1 - xh[t][c].w * m2);
-      const int col4 = threadIdx.x + c * blockDim.x;
-      const bool live = col4 < d4 && t0 + t < a.T;
-      g[t][c] = live ? o : f4_zero();
-      if (live) reinterpret_cast<float4*>(a.dS + rowi * a.d)[col4] = o;
+      reinterpret_cast<float4*>(a.dS + rowi * a.d)[col4] = o;
     }
     // d(den) = -sum_j dE_raw_j E_raw_j / den = -(s2 * eps * rstd^2) / den
-    dwsum[t] *= -(s2[t] * a.eps * rs[t] * rs[t]) / den[t];
+    if (threadIdx.x == 0) dwsum_out[rowi] = dwsum[t] * (-(s2[t] * a.eps * rs[t] * rs[t]) / den[t]);
   }
-  // ---- stream the segment: P2_t = sum_n c_nt V'_n, csum_t  (dlog_sigma)
-  float4 p2acc[TT][NCH];
-  float csum[TT];
-#pragma unroll
-  for (int t = 0; t < TT; ++t) {
-    csum[t] = 0.f;
-#pragma unroll
-    for (int c = 0; c < NCH; ++c) p2acc[t][c] = f4_zero();
-  }
-  for (int n0 = nb; n0 < ne; n0 += POOL_NB) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < POOL_NB * TT; i += blockDim.x) {
-      const int nn = i / TT, t = i % TT, n = n0 + nn;
-      float cc = 0.f;
-      if (n < ne && t0 + t < a.T) {
-        const float delta = fmaxf(s_th[t] - __ldg(a.tau + n), 0.f);
-        const float r = delta / sigma;
-        cc = expf(-(r * r)) * 2.f * r * r;  // dw/dlog_sigma
-      }
-      s_c[nn][t] = cc;
-    }
-    __syncthreads();
-    const int cnt = min(POOL_NB, ne - n0);
-    for (int nq = 0; nq < cnt; nq += 4) {  // 4 rows in flight per thread
-      float4 v[4][NCH];
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-          const int col4 = threadIdx.x + c * blockDim.x;
-          v[u][c] = (nq + u < cnt && col4 < d4)
-                        ? __ldg(reinterpret_cast<const float4*>(a.Vp + (size_t)(n0 + nq + u) * a.ldv) + col4) : f4_zero();
-        }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (nq + u < cnt) {
-#pragma unroll
-          for (int t = 0; t < TT; ++t) {
-            const float cc = s_c[nq + u][t];
-            csum[t] += cc;
-#pragma unroll
-            for (int c = 0; c < NCH; ++c) f4_fma(p2acc[t][c], cc, v[u][c]);
-          }
-        }
-      }
-    }
-  }
-  float part[TT];
-#pragma unroll
-  for (int t = 0; t < TT; ++t) {
-    float s = 0.f;
-#pragma unroll
-    for (int c = 0; c < NCH; ++c) s += f4_dot(g[t][c], p2acc[t][c]);
-    part[t] = s;
-  }
-  block_sum_multi<TT>(part, s_red);
-  float dls = 0.f;
-#pragma unroll
-  for (int t = 0; t < TT; ++t) dls += part[t] + dwsum[t] * csum[t];
 #pragma unroll
   for (int c = 0; c < NCH; ++c) {
     const int col4 = threadIdx.x + c * blockDim.x;
@@ -316,42 +251,54 @@ __global__ void __launch_bounds__(256) recavg_bwd_rows_kernel(const PoolArgs a) 
       atomicAdd(pb + 0, dbet[c].x); atomicAdd(pb + 1, dbet[c].y); atomicAdd(pb + 2, dbet[c].z); atomicAdd(pb + 3, dbet[c].w);
     }
   }
-  if (threadIdx.x == 0) atomicAdd(a.dlog_sigma, dls);
 }
 
-// Backward, phase 2: one CTA per (sample, tile of 8 notes): dV'_n = sum_t w_nt dS_t with register accumulators,
-// dS rows streamed 4 at a time -- every dV' row is written exactly once (no read-modify-write).
+// Backward, phase 2: one CTA per (sample, tile of NT notes).  With w_nt the recency weight and
+// c_nt = dw_nt/dlog_sigma = w_nt * 2 (delta/sigma)^2, both contractions over the query rows have the same shape:
+//   dV'_n = sum_t w_nt dS_t                      (written once, no read-modify-write)
+//   Q_n   = sum_t c_nt dS_t,  dlog_sigma += Q_n . V'_n + sum_t c_nt d(den_t)
+// so dS rows are streamed once (4 in flight) into two register accumulators per note.
 constexpr int POOL_TB = 32;  // query rows per shared-memory weight block
 template <int NCH>
-__global__ void __launch_bounds__(256) recavg_bwd_notes_kernel(const PoolArgs a) {
-  constexpr int POOL_NT = 8 / NCH;  // notes per CTA
-  __shared__ float s_w[POOL_TB][POOL_NT];
+__global__ void __launch_bounds__(256, NCH == 1 ? 2 : 1) recavg_bwd_notes_kernel(const PoolArgs a) {
+  constexpr int NT = 8 / NCH;  // notes per CTA
+  __shared__ float s_w[POOL_TB][NT];
+  __shared__ float s_c[POOL_TB][NT];
+  __shared__ float s_dw[POOL_TB];
+  __shared__ float s_red[32];
   const int b = blockIdx.y;
   const int nb = a.offsets[b], ne = a.offsets[b + 1];
-  const int n0 = nb + blockIdx.x * POOL_NT;
+  const int n0 = nb + blockIdx.x * NT;
   if (n0 >= ne) return;
-  const int ncnt = min(POOL_NT, ne - n0);
+  const int ncnt = min(NT, ne - n0);
   const float sigma = expf(__ldg(a.log_sigma));
   const int d4 = a.d >> 2;
-  float4 acc[POOL_NT][NCH];
+  const float* dwsum_in = a.dS + (size_t)a.B * a.T * a.d;
+  float4 accw[NT][NCH], accc[NT][NCH];
 #pragma unroll
-  for (int u = 0; u < POOL_NT; ++u)
+  for (int u = 0; u < NT; ++u)
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) acc[u][c] = f4_zero();
+    for (int c = 0; c < NCH; ++c) { accw[u][c] = f4_zero(); accc[u][c] = f4_zero(); }
+  float sc_term = 0.f;  // sum_t c_nt d(den_t), lane u < NT of warp 0 owns note u
   for (int t0 = 0; t0 < a.T; t0 += POOL_TB) {
     __syncthreads();
-    for (int i = threadIdx.x; i < POOL_TB * POOL_NT; i += blockDim.x) {
-      const int tt = i / POOL_NT, u = i % POOL_NT;
-      float w = 0.f;
+    for (int i = threadIdx.x; i < POOL_TB * NT; i += blockDim.x) {
+      const int tt = i / NT, u = i % NT;
+      float w = 0.f, cc = 0.f;
       if (t0 + tt < a.T && u < ncnt) {
         const float delta = fmaxf(a.t_hat[(size_t)b * a.t_bstride + t0 + tt] - __ldg(a.tau + n0 + u), 0.f);
         const float r = delta / sigma;
         w = expf(-(r * r));
+        cc = w * 2.f * r * r;
       }
       s_w[tt][u] = w;
+      s_c[tt][u] = cc;
     }
+    if (threadIdx.x < POOL_TB) s_dw[threadIdx.x] = t0 + threadIdx.x < a.T ? dwsum_in[(size_t)b * a.T + t0 + threadIdx.x] : 0.f;
     __syncthreads();
     const int tcnt = min(POOL_TB, a.T - t0);
+    if (threadIdx.x < NT)
+      for (int tt = 0; tt < tcnt; ++tt) sc_term = fmaf(s_c[tt][threadIdx.x], s_dw[tt], sc_term);
     for (int tq = 0; tq < tcnt; tq += 4) {
       float4 g[4][NCH];
 #pragma unroll
@@ -366,25 +313,33 @@ __global__ void __launch_bounds__(256) recavg_bwd_notes_kernel(const PoolArgs a)
       for (int v = 0; v < 4; ++v) {
         if (tq + v < tcnt) {
 #pragma unroll
-          for (int u = 0; u < POOL_NT; ++u) {
-            const float w = s_w[tq + v][u];
+          for (int u = 0; u < NT; ++u) {
+            const float w = s_w[tq + v][u], cc = s_c[tq + v][u];
 #pragma unroll
-            for (int c = 0; c < NCH; ++c) f4_fma(acc[u][c], w, g[v][c]);
+            for (int c = 0; c < NCH; ++c) { f4_fma(accw[u][c], w, g[v][c]); f4_fma(accc[u][c], cc, g[v][c]); }
           }
         }
       }
     }
   }
+  float dls = 0.f;
 #pragma unroll
-  for (int u = 0; u < POOL_NT; ++u) {
+  for (int u = 0; u < NT; ++u) {
     if (u < ncnt) {
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
         const int col4 = threadIdx.x + c * blockDim.x;
-        if (col4 < d4) reinterpret_cast<float4*>(a.dVp + (size_t)(n0 + u) * a.lddv)[col4] = acc[u][c];
+        if (col4 < d4) {
+          reinterpret_cast<float4*>(a.dVp + (size_t)(n0 + u) * a.lddv)[col4] = accw[u][c];
+          const float4 v = __ldg(reinterpret_cast<const float4*>(a.Vp + (size_t)(n0 + u) * a.ldv) + col4);
+          dls += f4_dot(accc[u][c], v);
+        }
       }
     }
   }
+  if (threadIdx.x < NT) dls += sc_term;
+  dls = block_sum(dls, s_red);
+  if (threadIdx.x == 0) atomicAdd(a.dlog_sigma, dls);
 }
 
 static int pool_geometry(int d, int& nch, int& threads) {

@@ -354,3 +354,101 @@ extern "C" int immtsf_xattn_tail_bwd(const float* dY_out, const float* delta_y, 
   IMMTSF_CHECK_LAUNCH("xattn_tail_bwd");
   return IMMTSF_OK;
 }
+
+
+// ------------------------------------------------------------------ large-T path: softmax rows around batched GEMMs
+// For T > 32 the T x T contractions run on the tensor cores (immtsf_gemm_batched: S = Q K^T, O = P~ V, and the
+// four backward products); what is left are these two row kernels over the [B, H, T, Tp] score buffers
+// (Tp = T rounded up to 4 floats; dropout indices ignore the padding: same masks as the small-T kernels).
+//   fwd: P = softmax(scale * S) written in place (saved for backward), P~ = P * keep / (1-p) -> Pt
+//   bwd: dP~ = dO V^T comes in through dS; dS <- scale * P * (dP~ * ks - D), D = sum_j P dP~ ks; Pt <- P * ks
+__global__ void __launch_bounds__(256) softmax_rows_fwd_kernel(float* __restrict__ S, float* __restrict__ Pt,
+                                                               const uint8_t* __restrict__ m_txt, int B, int H, int T, int Tp,
+                                                               float scale, uint32_t thr, SeedArg seed_) {
+  const uint64_t seed = resolve_seed(seed_);
+  const float inv_keep = inv_keep_from_thr(thr);
+  const int lane = threadIdx.x & 31;
+  const long rows = (long)B * H * T;
+  for (long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < rows; row += ((long)gridDim.x * blockDim.x) >> 5) {
+    const int b = (int)(row / ((long)H * T));
+    float* srow = S + row * Tp;
+    float* prow = Pt + row * Tp;
+    if (m_txt[b] == 0) {
+      for (int j = lane; j < Tp; j += 32) { srow[j] = 0.f; prow[j] = 0.f; }
+      continue;
+    }
+    float mx = -INFINITY;
+    for (int j = lane; j < T; j += 32) mx = fmaxf(mx, scale * srow[j]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < T; j += 32) sum += expf(scale * srow[j] - mx);
+    sum = warp_sum(sum);
+    for (int j = lane; j < Tp; j += 32) {
+      float p = 0.f, pt = 0.f;
+      if (j < T) {
+        p = expf(scale * srow[j] - mx) / sum;
+        pt = p * dropout_scale(seed, IMMTSF_SITE_MMF_ATTN, (uint64_t)row * T + j, thr, inv_keep);
+      }
+      srow[j] = p;
+      prow[j] = pt;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) softmax_rows_bwd_kernel(float* __restrict__ dS, const float* __restrict__ P,
+                                                               float* __restrict__ Pt, const uint8_t* __restrict__ m_txt, int B,
+                                                               int H, int T, int Tp, float scale, uint32_t thr, SeedArg seed_) {
+  const uint64_t seed = resolve_seed(seed_);
+  const float inv_keep = inv_keep_from_thr(thr);
+  const int lane = threadIdx.x & 31;
+  const long rows = (long)B * H * T;
+  for (long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < rows; row += ((long)gridDim.x * blockDim.x) >> 5) {
+    const int b = (int)(row / ((long)H * T));
+    float* drow = dS + row * Tp;
+    float* trow = Pt + row * Tp;
+    const float* prow = P + row * Tp;
+    if (m_txt[b] == 0) {
+      for (int j = lane; j < Tp; j += 32) { drow[j] = 0.f; trow[j] = 0.f; }
+      continue;
+    }
+    float D = 0.f;
+    for (int j = lane; j < T; j += 32) {
+      const float ks = dropout_scale(seed, IMMTSF_SITE_MMF_ATTN, (uint64_t)row * T + j, thr, inv_keep);
+      D = fmaf(prow[j], drow[j] * ks, D);
+    }
+    D = warp_sum(D);
+    for (int j = lane; j < Tp; j += 32) {
+      float ds = 0.f, pt = 0.f;
+      if (j < T) {
+        const float ks = dropout_scale(seed, IMMTSF_SITE_MMF_ATTN, (uint64_t)row * T + j, thr, inv_keep);
+        const float p = prow[j];
+        ds = scale * p * (drow[j] * ks - D);
+        pt = p * ks;
+      }
+      drow[j] = ds;
+      trow[j] = pt;
+    }
+  }
+}
+
+extern "C" int immtsf_softmax_rows_fwd(float* S, float* Pt, const uint8_t* m_txt, int B, int H, int T, int Tp, float scale,
+                                       uint32_t drop_thr, uint64_t seed, void* stream) {
+  if (B == 0 || T == 0) return IMMTSF_OK;
+  IMMTSF_REQUIRE(S && Pt && m_txt && H >= 1 && Tp >= T, "softmax_rows_fwd: bad args");
+  const long rows = (long)B * H * T;
+  int grid = (int)((rows + 7) / 8 < 148 * 16 ? (rows + 7) / 8 : 148 * 16);
+  softmax_rows_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(S, Pt, m_txt, B, H, T, Tp, scale, drop_thr, make_seed(seed));
+  IMMTSF_CHECK_LAUNCH("softmax_rows_fwd");
+  return IMMTSF_OK;
+}
+
+extern "C" int immtsf_softmax_rows_bwd(float* dS, const float* P, float* Pt, const uint8_t* m_txt, int B, int H, int T, int Tp,
+                                       float scale, uint32_t drop_thr, uint64_t seed, void* stream) {
+  if (B == 0 || T == 0) return IMMTSF_OK;
+  IMMTSF_REQUIRE(dS && P && Pt && m_txt && H >= 1 && Tp >= T, "softmax_rows_bwd: bad args");
+  const long rows = (long)B * H * T;
+  int grid = (int)((rows + 7) / 8 < 148 * 16 ? (rows + 7) / 8 : 148 * 16);
+  softmax_rows_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dS, P, Pt, m_txt, B, H, T, Tp, scale, drop_thr, make_seed(seed));
+  IMMTSF_CHECK_LAUNCH("softmax_rows_bwd");
+  return IMMTSF_OK;
+}

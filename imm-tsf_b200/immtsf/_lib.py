@@ -19,6 +19,7 @@ F = C.c_float
 U32 = C.c_uint32
 U64 = C.c_uint64
 SZ = C.c_size_t
+L = C.c_long
 
 # name -> argtypes, in the order of include/immtsf.h
 SIGNATURES = {
@@ -50,6 +51,9 @@ SIGNATURES = {
     "immtsf_gru_scan_bwd": [P, P, P, P, P, I, I, I, P, P, P],
     "immtsf_xattn_core_fwd": [P, I, P, I, P, I, P, I, I, I, I, U32, U64, P, I, P, P],
     "immtsf_xattn_core_bwd": [P, I, P, I, P, I, P, I, P, P, I, I, I, I, U32, U64, P, I, P, I, P, I, P],
+    "immtsf_gemm_batched": [I, I, I, I, I, F, P, I, L, L, P, I, L, L, F, P, I, L, L, I, I, P, SZ, P],
+    "immtsf_softmax_rows_fwd": [P, P, P, I, I, I, I, F, U32, U64, P],
+    "immtsf_softmax_rows_bwd": [P, P, P, P, I, I, I, I, F, U32, U64, P],
     "immtsf_xattn_tail_fwd": [P, P, P, P, P, I, I, I, F, F, U32, U64, P, P, P],
     "immtsf_xattn_tail_bwd": [P, P, P, P, I, I, I, F, F, U32, U64, P, P, P, P],
     "immtsf_axpby": [P, F, P, I, SZ, P],
@@ -84,6 +88,8 @@ def load():
     lib.immtsf_launch_count.restype = C.c_ulonglong
     lib.immtsf_gemm_workspace_bytes.argtypes = [I, I, I, I, I]
     lib.immtsf_gemm_workspace_bytes.restype = SZ
+    lib.immtsf_gemm_batched_workspace_bytes.argtypes = [I, I, I, I, I, I, L, L, I, L, L, I, I]
+    lib.immtsf_gemm_batched_workspace_bytes.restype = SZ
     _lib = lib
     return lib
 

@@ -127,8 +127,9 @@ int immtsf_recavg_pool_fwd(const float* Vp, int ldv, const float* tau_flat, cons
                            const float* gamma, const float* beta, int B, int T, int d, float eps,
                            uint32_t drop_thr, uint64_t seed, float* E_drop, float* E_raw,
                            float* mean, float* rstd, float* wsum, void* stream);
-/* dS [B*T, d] is caller-owned scratch (the LayerNorm-backward rows, written by the first of the two kernels
- * and read by the second); N_max bounds the notes per sample (grid size only). */
+/* dS: caller-owned scratch of B*T*(d+1) floats (the LayerNorm-backward rows [B*T, d] followed by one scalar per
+ * row, written by the first of the two kernels and read by the second); N_max bounds the notes per sample
+ * (grid size only). */
 int immtsf_recavg_pool_bwd(const float* dE_drop, const float* E_raw, const float* mean, const float* rstd,
                            const float* wsum, const float* Vp, int ldv, const float* tau_flat,
                            const int32_t* offsets, const float* t_hat, int t_hat_bstride,
@@ -200,6 +201,23 @@ int immtsf_xattn_core_bwd(const float* d_o, int lddo, const float* q, int ldq, c
                           const float* v, int ldv, const float* probs, const uint8_t* m_txt, int B, int T,
                           int H, int d, uint32_t drop_thr, uint64_t seed, float* dq, int lddq, float* dk,
                           int lddk, float* dv, int lddv, void* stream);
+/* Large-T form of the same core (T > 32: the T x T contractions are dense products and run on tcgen05):
+ *   S = Q K^T (immtsf_gemm_batched) -> immtsf_softmax_rows_fwd -> O = P~ V (immtsf_gemm_batched), and in backward
+ *   dP~ = dO V^T -> immtsf_softmax_rows_bwd -> dQ = dS K, dK = dS^T Q, dV = P~^T dO.
+ * Batched product: C(b1,b2)[M,N] = alpha * op(A(b1,b2)) op(B(b1,b2)) + beta * C(b1,b2) with X(b1,b2) = X + b1*x_s1 +
+ * b2*x_s2 (element strides, multiples of 4).  3xTF32 like immtsf_gemm; tiles that overhang a batch are zero-filled. */
+int immtsf_gemm_batched(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda, long a_s1,
+                        long a_s2, const float* B, int ldb, long b_s1, long b_s2, float beta, float* C, int ldc,
+                        long c_s1, long c_s2, int batch1, int batch2, void* workspace, size_t workspace_bytes,
+                        void* stream);
+size_t immtsf_gemm_batched_workspace_bytes(int transA, int transB, int M, int N, int K, int lda, long a_s1, long a_s2,
+                                           int ldb, long b_s1, long b_s2, int batch1, int batch2);
+/* S, Pt, dS: [B, H, T, Tp] score buffers (Tp >= T, a multiple of 4).  fwd: S <- P = softmax(scale*S) in place,
+ * Pt <- P * dropout keep-scale.  bwd: dS holds dP~ on entry and scale * P * (dP~ ks - D) on exit, Pt <- P ks. */
+int immtsf_softmax_rows_fwd(float* S, float* Pt, const uint8_t* m_txt, int B, int H, int T, int Tp, float scale,
+                            uint32_t drop_thr, uint64_t seed, void* stream);
+int immtsf_softmax_rows_bwd(float* dS, const float* P, float* Pt, const uint8_t* m_txt, int B, int H, int T, int Tp,
+                            float scale, uint32_t drop_thr, uint64_t seed, void* stream);
 /* tail (MMF_XAttn_Add.py:84-102): Y_out = (Y + kappa * m * dropout(LN_C(delta_y))) / (1+kappa) */
 int immtsf_xattn_tail_fwd(const float* Y, const float* delta_y, const float* gamma, const float* beta,
                           const uint8_t* m_txt, int B, int T, int C, float eps, float kappa,

@@ -14,7 +14,7 @@ from helpers import golden_names, load_golden
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HEADER = os.path.join(ROOT, "include", "immtsf.h")
-C2CT = {"int": "c_int", "float": "c_float", "uint32_t": "c_uint", "uint64_t": "c_ulong", "size_t": "c_ulong"}
+C2CT = {"int": "c_int", "float": "c_float", "uint32_t": "c_uint", "uint64_t": "c_ulong", "size_t": "c_ulong", "long": "c_long"}
 
 
 def _header_decls():
@@ -54,7 +54,8 @@ def test_binding_signatures_match_header():
             else:
                 base = carg.split()[-2] if len(carg.split()) >= 2 else carg
                 assert ct.__name__ == C2CT[base], (name, carg, ct.__name__)
-    assert set(decls) - set(_lib.SIGNATURES) == {"immtsf_last_error_string", "immtsf_launch_count", "immtsf_gemm_workspace_bytes"}
+    assert set(decls) - set(_lib.SIGNATURES) == {"immtsf_last_error_string", "immtsf_launch_count", "immtsf_gemm_workspace_bytes",
+                                                   "immtsf_gemm_batched_workspace_bytes"}
 
 
 def test_library_contains_sm100a_code_only():

@@ -233,6 +233,17 @@ def test_many_channels_vs_oracle():
         _vs_oracle(cfg, 64, B=4, N=8, T=20, p=0.1, train=True, seed=51)
 
 
+@pytest.mark.parametrize("ttf", ["TTF_RecAvg", "TTF_T2V_XAttn"])
+@pytest.mark.parametrize("T,H,p", [(40, 2, 0.1), (70, 1, 0.0), (193, 4, 0.2)])
+def test_long_prediction_window_xattn_vs_oracle(ttf, T, H, p):
+    """T > 32 (MIMIC-shaped windows): MMF_XAttn_Add's T x T contractions run as batched tcgen05 products around the
+    row-softmax kernels; T not a multiple of 4 or 32 exercises the padded score buffers and TMA zero fill, a
+    no-text sample exercises the all-masked rows."""
+    cfg = dict(ttf=ttf, mmf="MMF_XAttn_Add", d_txt=64, C=6, H=H, kappa=0.5)
+    _vs_oracle(cfg, 48, B=5, N=6, T=T, p=p, train=True, seed=61 + T)
+    _vs_oracle(cfg, 48, B=3, N=4, T=T, p=p, train=False, seed=71 + T, no_note=True)
+
+
 # ------------------------------------------------------------------ size-independent properties at full size
 def test_cfg2_properties_full_size():
     """BASELINE cfg2 (B 256, N_max 16, T_f 24, d 768, C 4, T2V_XAttn + XAttn_Add):
