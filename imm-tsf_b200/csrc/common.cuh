@@ -83,18 +83,37 @@ __host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t 
   }
   return Philox4{c0, c1, c2, c3};
 }
-// Random word for flat element index `idx` at dropout site `site`:
-// word (idx & 3) of philox(counter = (idx>>2 lo, idx>>2 hi, site, 0), key = seed).
-__device__ __forceinline__ uint32_t dropout_word(uint64_t seed, uint32_t site, uint64_t idx) {
-  const uint64_t c = idx >> 2;
+// Dropout decision for flat element index `idx` at dropout site `site`: one Philox call serves EIGHT elements
+// (16 random bits each): call counter = (idx>>3 lo, idx>>3 hi, site, 0), key = seed; element idx uses the 16-bit
+// field (idx & 1) of word (idx>>1) & 3.  An element is dropped iff field < thr, thr = floor(p * 2^16); the
+// realised rate thr / 2^16 differs from p by < 1.6e-5 and inv_keep uses the realised rate, so E[mask] = 1 exactly.
+__device__ __forceinline__ uint32_t dropout_field(uint64_t seed, uint32_t site, uint64_t idx) {
+  const uint64_t c = idx >> 3;
   const Philox4 r = philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), site, 0u, (uint32_t)seed, (uint32_t)(seed >> 32));
-  const uint32_t k = (uint32_t)(idx & 3);
-  return k == 0 ? r.x : (k == 1 ? r.y : (k == 2 ? r.z : r.w));
+  const uint32_t k = (uint32_t)(idx >> 1) & 3u;
+  const uint32_t w = k == 0 ? r.x : (k == 1 ? r.y : (k == 2 ? r.z : r.w));
+  return (idx & 1) ? (w >> 16) : (w & 0xFFFFu);
 }
-// keep-scale for one element: 0 if dropped else 1/(1-p).  thr = floor(p * 2^32).
+// keep-scale for one element: 0 if dropped else 1/(1-p).
 __device__ __forceinline__ float dropout_scale(uint64_t seed, uint32_t site, uint64_t idx, uint32_t thr, float inv_keep) {
   if (thr == 0u) return 1.f;
-  return dropout_word(seed, site, idx) >= thr ? inv_keep : 0.f;
+  return dropout_field(seed, site, idx) >= thr ? inv_keep : 0.f;
+}
+// keep-scales of the 8 consecutive elements idx8*8 .. idx8*8+7 (one Philox call)
+__device__ __forceinline__ void dropout_scale8(uint64_t seed, uint32_t site, uint64_t idx8, uint32_t thr, float inv_keep,
+                                               float (&o)[8]) {
+  if (thr == 0u) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = 1.f;
+    return;
+  }
+  const Philox4 r = philox4x32_10((uint32_t)idx8, (uint32_t)(idx8 >> 32), site, 0u, (uint32_t)seed, (uint32_t)(seed >> 32));
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    o[2 * k] = (w[k] & 0xFFFFu) >= thr ? inv_keep : 0.f;
+    o[2 * k + 1] = (w[k] >> 16) >= thr ? inv_keep : 0.f;
+  }
 }
 
 // Dropout seed as the kernels see it: a host value plus an optional device-resident offset.  The offset lets a

@@ -164,6 +164,118 @@ __global__ void __launch_bounds__(GR_WARPS * 32) gru_scan_bwd_kernel(const float
   }
 }
 
+// ------------------------------------------------------------------ wide recurrence (C > 32)
+// One warp per sample is a serial chain of 3C*C/32 FMAs per lane per step (8.6 us per step at C = 96).  For many
+// channels the recurrence gets a whole CTA per sample: 3C threads, thread j keeps row j of W_hh in REGISTERS, the
+// hidden state lives in shared memory (broadcast float4 reads), two barriers per step.  Forward also stores the
+// gate activations (r, z, n, W_hn h + b_hn) so that backward needs only the transposed product, for which thread
+// (g, k) keeps column k of gate block g in registers.
+template <int CMAX>
+__global__ void __launch_bounds__(3 * CMAX) gru_scan_fwd_wide_kernel(const float* __restrict__ G4, const float* __restrict__ w_hh,
+                                                                      const float* __restrict__ b_hh, int B, int T, int C,
+                                                                      float* __restrict__ h_all, float* __restrict__ h_prev,
+                                                                      float* __restrict__ gates) {
+  __shared__ __align__(16) float s_h[CMAX];
+  __shared__ float s_gh[3 * CMAX];
+  const int b = blockIdx.x, j = threadIdx.x;
+  const bool act = j < 3 * C;
+  float w[CMAX];
+#pragma unroll
+  for (int k = 0; k < CMAX; ++k) w[k] = (act && k < C) ? __ldg(w_hh + (size_t)j * C + k) : 0.f;
+  const float bj = act ? __ldg(b_hh + j) : 0.f;
+  if (j < CMAX) s_h[j] = 0.f;
+  __syncthreads();
+  const int ldg = 4 * C;
+  float h = 0.f;
+  for (int t = 0; t < T; ++t) {
+    const size_t row = (size_t)b * T + t;
+    float gi_r = 0.f, gi_z = 0.f, gi_n = 0.f;
+    if (j < C) {  // issued before the product so that their latency hides behind it
+      gi_r = __ldg(G4 + row * ldg + j);
+      gi_z = __ldg(G4 + row * ldg + C + j);
+      gi_n = __ldg(G4 + row * ldg + 2 * C + j);
+    }
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+    for (int k = 0; k < CMAX; k += 4) {
+      const float4 hv = *reinterpret_cast<const float4*>(&s_h[k]);
+      a0 = fmaf(w[k], hv.x, a0); a1 = fmaf(w[k + 1], hv.y, a1); a2 = fmaf(w[k + 2], hv.z, a2); a3 = fmaf(w[k + 3], hv.w, a3);
+    }
+    if (act) s_gh[j] = bj + ((a0 + a1) + (a2 + a3));
+    __syncthreads();
+    if (j < C) {
+      const float gn = s_gh[2 * C + j];
+      const float r = sigmoidf_(gi_r + s_gh[j]);
+      const float z = sigmoidf_(gi_z + s_gh[C + j]);
+      const float n = tanhf(gi_n + r * gn);
+      h_prev[row * C + j] = h;
+      h = (1.f - z) * n + z * h;
+      h_all[row * C + j] = h;
+      s_h[j] = h;
+      float* gp = gates + row * ldg;
+      gp[j] = r; gp[C + j] = z; gp[2 * C + j] = n; gp[3 * C + j] = gn;
+    }
+    __syncthreads();
+  }
+}
+
+template <int CMAX>
+__global__ void __launch_bounds__(3 * CMAX) gru_scan_bwd_wide_kernel(const float* __restrict__ gates, const float* __restrict__ h_prev,
+                                                                      const float* __restrict__ w_hh, const float* __restrict__ dh_out,
+                                                                      int B, int T, int C, float* __restrict__ dG4,
+                                                                      float* __restrict__ dGh) {
+  __shared__ float s_g[3 * CMAX];     // da_r, da_z, da_n * r of this step
+  __shared__ float s_part[3 * CMAX];  // per gate block: (W_g^T dgate_g)[k]
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const bool act = tid < 3 * C;
+  const int g = act ? tid / C : 0, k = act ? tid % C : 0;
+  float wt[CMAX];  // column k of gate block g
+#pragma unroll
+  for (int jj = 0; jj < CMAX; ++jj) wt[jj] = (act && jj < C) ? __ldg(w_hh + ((size_t)g * C + jj) * C + k) : 0.f;
+  const int ldg = 4 * C;
+  float dh = 0.f;
+  for (int t = T - 1; t >= 0; --t) {
+    const size_t row = (size_t)b * T + t;
+    float dh_direct = 0.f;
+    if (tid < C) {
+      const int j = tid;
+      const float* gp = gates + row * ldg;
+      const float r = gp[j], z = gp[C + j], n = gp[2 * C + j], gn = gp[3 * C + j];
+      const float hp = h_prev[row * C + j];
+      const float dht = dh + dh_out[row * C + j];
+      const float dn = dht * (1.f - z);
+      const float dz = dht * (hp - n);
+      const float da_n = dn * (1.f - n * n);
+      const float da_r = da_n * gn * r * (1.f - r);
+      const float da_z = dz * z * (1.f - z);
+      const float dhn = da_n * r;
+      dh_direct = dht * z;
+      dG4[row * ldg + j] = da_r;
+      dG4[row * ldg + C + j] = da_z;
+      dG4[row * ldg + 2 * C + j] = da_n;
+      dGh[row * 3 * C + j] = da_r;
+      dGh[row * 3 * C + C + j] = da_z;
+      dGh[row * 3 * C + 2 * C + j] = dhn;
+      s_g[j] = da_r;
+      s_g[C + j] = da_z;
+      s_g[2 * C + j] = dhn;
+    }
+    __syncthreads();
+    if (act) {
+      const float* sg = s_g + g * C;
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+      for (int jj = 0; jj < CMAX; jj += 2) {
+        a0 = fmaf(wt[jj], jj < C ? sg[jj] : 0.f, a0);
+        a1 = fmaf(wt[jj + 1], jj + 1 < C ? sg[jj + 1] : 0.f, a1);
+      }
+      s_part[tid] = a0 + a1;
+    }
+    __syncthreads();
+    if (tid < C) dh = dh_direct + s_part[tid] + s_part[C + tid] + s_part[2 * C + tid];
+  }
+}
+
 // ------------------------------------------------------------------ tail
 // one warp per (b,t) row, grid-stride over rows
 template <int UN>
@@ -182,7 +294,7 @@ __global__ void __launch_bounds__(GR_WARPS * 32) gr_tail_fwd_kernel(const float*
   __syncthreads();
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   float* hs = s_h + w * C;
-  const float inv_keep = thr == 0u ? 1.f : (float)(1.0 / (1.0 - (double)thr / 4294967296.0));
+  const float inv_keep = thr == 0u ? 1.f : (float)(1.0 / (1.0 - (double)thr / 65536.0));
   const int rows = B * T;
   bool bad = false;
   for (int row = blockIdx.x * GR_WARPS + w; row < rows; row += gridDim.x * GR_WARPS) {
@@ -250,7 +362,7 @@ __global__ void __launch_bounds__(GR_WARPS * 32) gr_tail_bwd_kernel(const float*
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   float* hs = s_h + w * C;
   float* ds = s_d + w * C;
-  const float inv_keep = thr == 0u ? 1.f : (float)(1.0 / (1.0 - (double)thr / 4294967296.0));
+  const float inv_keep = thr == 0u ? 1.f : (float)(1.0 / (1.0 - (double)thr / 65536.0));
   const int rows = B * T;
   float dgam[UN], dbet[UN];
 #pragma unroll
@@ -365,10 +477,18 @@ static int set_smem(K kernel, size_t bytes, const char* name) {
 }
 
 extern "C" int immtsf_gru_scan_fwd(const float* G4, const float* w_hh, const float* b_hh, int B, int T, int C,
-                                   float* h_all, float* h_prev, void* stream) {
+                                   float* h_all, float* h_prev, float* gates, void* stream) {
   if (B == 0 || T == 0) return IMMTSF_OK;
   IMMTSF_REQUIRE(G4 && w_hh && b_hh && h_all && h_prev, "gru_scan_fwd: null pointer");
   IMMTSF_REQUIRE(C >= 1 && C <= 128, "gru_scan_fwd: C=%d must be in [1,128]", C);
+  if (gates != nullptr && C > 32) {  // wide recurrence: one CTA per sample
+    cudaStream_t stw = (cudaStream_t)stream;
+    if (C <= 64) gru_scan_fwd_wide_kernel<64><<<B, 192, 0, stw>>>(G4, w_hh, b_hh, B, T, C, h_all, h_prev, gates);
+    else if (C <= 96) gru_scan_fwd_wide_kernel<96><<<B, 288, 0, stw>>>(G4, w_hh, b_hh, B, T, C, h_all, h_prev, gates);
+    else gru_scan_fwd_wide_kernel<128><<<B, 384, 0, stw>>>(G4, w_hh, b_hh, B, T, C, h_all, h_prev, gates);
+    IMMTSF_CHECK_LAUNCH("gru_scan_fwd_wide");
+    return IMMTSF_OK;
+  }
   const size_t smem = sizeof(float) * ((size_t)3 * C * (C + 1) + 3 * C + (size_t)GR_WARPS * C);
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = ceil_div(B, GR_WARPS);
@@ -382,10 +502,19 @@ extern "C" int immtsf_gru_scan_fwd(const float* G4, const float* w_hh, const flo
 }
 
 extern "C" int immtsf_gru_scan_bwd(const float* G4, const float* h_prev, const float* w_hh, const float* b_hh,
-                                   const float* dh_out, int B, int T, int C, float* dG4, float* dGh, void* stream) {
+                                   const float* dh_out, const float* gates, int B, int T, int C, float* dG4, float* dGh,
+                                   void* stream) {
   if (B == 0 || T == 0) return IMMTSF_OK;
   IMMTSF_REQUIRE(G4 && h_prev && w_hh && b_hh && dh_out && dG4 && dGh, "gru_scan_bwd: null pointer");
   IMMTSF_REQUIRE(C >= 1 && C <= 128, "gru_scan_bwd: C=%d must be in [1,128]", C);
+  if (gates != nullptr && C > 32) {
+    cudaStream_t stw = (cudaStream_t)stream;
+    if (C <= 64) gru_scan_bwd_wide_kernel<64><<<B, 192, 0, stw>>>(gates, h_prev, w_hh, dh_out, B, T, C, dG4, dGh);
+    else if (C <= 96) gru_scan_bwd_wide_kernel<96><<<B, 288, 0, stw>>>(gates, h_prev, w_hh, dh_out, B, T, C, dG4, dGh);
+    else gru_scan_bwd_wide_kernel<128><<<B, 384, 0, stw>>>(gates, h_prev, w_hh, dh_out, B, T, C, dG4, dGh);
+    IMMTSF_CHECK_LAUNCH("gru_scan_bwd_wide");
+    return IMMTSF_OK;
+  }
   const size_t smem = sizeof(float) * ((size_t)3 * C * (C + 1) + 3 * C + (size_t)GR_WARPS * C + (size_t)GR_WARPS * 3 * C);
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = ceil_div(B, GR_WARPS);

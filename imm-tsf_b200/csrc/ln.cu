@@ -6,7 +6,7 @@
 // column groups, statistics are block reductions over the register tile.
 // Backward accumulates dgamma / dbeta / dres per CTA in registers across its
 // row tiles and issues one atomicAdd per owned column at the end.
-#include "rowtile.cuh"
+#include "rowwarp.cuh"
 #include "../../include/immtsf.h"
 
 struct LnArgs {
@@ -186,6 +186,150 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnArgs a) {
   }
 }
 
+// ------------------------------------------------------------------ warp-per-row variants (d % 8 == 0, d <= 1024)
+template <int NC>
+__global__ void __launch_bounds__(256) ln_fwd_w_kernel(const LnArgs a) {
+  const int d8 = a.d >> 3, lane = threadIdx.x & 31;
+  const float inv_keep = inv_keep_from_thr(a.thr), inv_d = 1.f / (float)a.d;
+  const uint64_t seed = resolve_seed(a.seed);
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  for (int r = gw; r < a.R; r += nw) {
+    const bool v = a.valid == nullptr || a.valid[r / a.rps] != 0;
+    float z[NC][8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+      const int k = lane + 32 * i;
+      zero8(z[i]);
+      if (k < d8) {
+        if (v) {
+          load8(a.x + (size_t)r * a.ldx, k, z[i]);
+          if (a.xbias) { float t[8]; load8(a.xbias, k, t);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) z[i][e] += t[e]; }
+        }
+        if (a.res) { float t[8]; load8(a.res, k, t);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) z[i][e] += t[e]; }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s += z[i][e];
+      }
+    }
+    const float mu = warp_sum(s) * inv_d;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NC; ++i)
+      if (lane + 32 * i < d8)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) q = fmaf(z[i][e] - mu, z[i][e] - mu, q);
+    const float rs = 1.f / sqrtf(warp_sum(q) * inv_d + a.eps);
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+      const int k = lane + 32 * i;
+      if (k < d8) {
+        float g[8], be[8], ks[8], y[8];
+        load8(a.gamma, k, g);
+        load8(a.beta, k, be);
+        dropout_scale8(seed, a.site, (uint64_t)r * d8 + k, a.thr, inv_keep, ks);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) y[e] = ((z[i][e] - mu) * rs * g[e] + be[e]) * ks[e];
+        store8(a.y + (size_t)r * a.d, k, y);
+      }
+    }
+    if (lane == 0) {
+      if (a.mean) a.mean[r] = mu;
+      if (a.rstd) a.rstd[r] = rs;
+    }
+  }
+}
+
+template <int NC>
+__global__ void __launch_bounds__(128) ln_bwd_w_kernel(const LnArgs a) {
+  __shared__ float s_acc[3 * 1024];  // dgamma | dbeta | dres of this CTA
+  const int d8 = a.d >> 3, lane = threadIdx.x & 31;
+  const float inv_keep = inv_keep_from_thr(a.thr), inv_d = 1.f / (float)a.d;
+  const uint64_t seed = resolve_seed(a.seed);
+  for (int i = threadIdx.x; i < 3 * a.d; i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
+  float ga[NC][8], dgam[NC][8], dbet[NC][8], dres[NC][8];
+#pragma unroll
+  for (int i = 0; i < NC; ++i) {
+    zero8(ga[i]); zero8(dgam[i]); zero8(dbet[i]); zero8(dres[i]);
+    if (lane + 32 * i < d8) load8(a.gamma, lane + 32 * i, ga[i]);
+  }
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  for (int r = gw; r < a.R; r += nw) {
+    const bool v = a.valid == nullptr || a.valid[r / a.rps] != 0;
+    const float mu = a.mean[r], rs = a.rstd[r];
+    float g[NC][8], h[NC][8];
+    float p1 = 0.f, p2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+      const int k = lane + 32 * i;
+      zero8(g[i]); zero8(h[i]);
+      if (k < d8) {
+        float dy[8], ks[8], q[8];
+        load8(a.dy + (size_t)r * a.d, k, dy);
+        dropout_scale8(seed, a.site, (uint64_t)r * d8 + k, a.thr, inv_keep, ks);
+        zero8(q);
+        if (v) {
+          load8(a.x + (size_t)r * a.ldx, k, q);
+          if (a.xbias) { float t[8]; load8(a.xbias, k, t);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) q[e] += t[e]; }
+        }
+        if (a.res) { float t[8]; load8(a.res, k, t);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) q[e] += t[e]; }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float dye = dy[e] * ks[e];
+          const float he = (q[e] - mu) * rs;
+          dgam[i][e] = fmaf(dye, he, dgam[i][e]);
+          dbet[i][e] += dye;
+          const float gg = dye * ga[i][e];
+          g[i][e] = gg;
+          h[i][e] = he;
+          p1 += gg;
+          p2 = fmaf(gg, he, p2);
+        }
+      }
+    }
+    const float m1 = warp_sum(p1) * inv_d, m2 = warp_sum(p2) * inv_d;
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+      const int k = lane + 32 * i;
+      if (k < d8) {
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          o[e] = rs * (g[i][e] - m1 - h[i][e] * m2);
+          dres[i][e] += o[e];  // dz flows to the residual for every row
+          if (!v) o[e] = 0.f;
+        }
+        store8(a.dx + (size_t)r * a.d, k, o);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NC; ++i) {
+    const int k = lane + 32 * i;
+    if (k < d8)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        atomicAdd(&s_acc[8 * k + e], dgam[i][e]);
+        atomicAdd(&s_acc[a.d + 8 * k + e], dbet[i][e]);
+        atomicAdd(&s_acc[2 * a.d + 8 * k + e], dres[i][e]);
+      }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < a.d; i += blockDim.x) {
+    atomicAdd(a.dgamma + i, s_acc[i]);
+    atomicAdd(a.dbeta + i, s_acc[a.d + i]);
+    if (a.dres) atomicAdd(a.dres + i, s_acc[2 * a.d + i]);
+  }
+}
+
 static int ln_geometry(int d, int& nch, int& threads) {
   if (d <= 0 || (d & 3)) return -1;
   const int d4 = d >> 2;
@@ -210,10 +354,22 @@ extern "C" int immtsf_ln_fwd(const float* x, int ldx, const float* xbias, const 
   a.x = x; a.ldx = ldx; a.xbias = xbias; a.res = res; a.valid = valid; a.rps = rows_per_sample > 0 ? rows_per_sample : 1;
   a.gamma = gamma; a.beta = beta; a.R = R; a.d = d; a.eps = eps; a.thr = drop_thr; a.seed = make_seed(seed); a.site = site;
   a.y = y; a.mean = mean; a.rstd = rstd;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nc = rowwarp_nc(d);
+  if (nc > 0 && (res == nullptr || ((uintptr_t)res & 15) == 0) && (xbias == nullptr || ((uintptr_t)xbias & 15) == 0) &&
+      ((uintptr_t)gamma & 15) == 0 && ((uintptr_t)beta & 15) == 0 && ((uintptr_t)y & 15) == 0) {
+    int gridw = ceil_div(R, 8);
+    if (gridw > 148 * 8) gridw = 148 * 8;
+    if (nc == 1) ln_fwd_w_kernel<1><<<gridw, 256, 0, st>>>(a);
+    else if (nc == 2) ln_fwd_w_kernel<2><<<gridw, 256, 0, st>>>(a);
+    else if (nc == 3) ln_fwd_w_kernel<3><<<gridw, 256, 0, st>>>(a);
+    else ln_fwd_w_kernel<4><<<gridw, 256, 0, st>>>(a);
+    IMMTSF_CHECK_LAUNCH("ln_fwd_w");
+    return IMMTSF_OK;
+  }
   const int TT = 8 / nch;
   int grid = ceil_div(R, TT);
   if (grid > 148 * 8) grid = 148 * 8;
-  cudaStream_t st = (cudaStream_t)stream;
   if (nch == 1) ln_fwd_kernel<1><<<grid, threads, 0, st>>>(a);
   else if (nch == 2) ln_fwd_kernel<2><<<grid, threads, 0, st>>>(a);
   else ln_fwd_kernel<4><<<grid, threads, 0, st>>>(a);
@@ -235,10 +391,22 @@ extern "C" int immtsf_ln_bwd(const float* dy, const float* x, int ldx, const flo
   a.gamma = gamma; a.R = R; a.d = d; a.thr = drop_thr; a.seed = make_seed(seed); a.site = site;
   a.mean = const_cast<float*>(mean); a.rstd = const_cast<float*>(rstd);
   a.dy = dy; a.dx = dx; a.dres = dres; a.dgamma = dgamma; a.dbeta = dbeta;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nc = rowwarp_nc(d);
+  if (nc > 0 && (res == nullptr || ((uintptr_t)res & 15) == 0) && (xbias == nullptr || ((uintptr_t)xbias & 15) == 0) &&
+      ((uintptr_t)gamma & 15) == 0 && ((uintptr_t)dy & 15) == 0 && ((uintptr_t)dx & 15) == 0) {
+    int gridw = ceil_div(R, 4);
+    if (gridw > 148 * 4) gridw = 148 * 4;
+    if (nc == 1) ln_bwd_w_kernel<1><<<gridw, 128, 0, st>>>(a);
+    else if (nc == 2) ln_bwd_w_kernel<2><<<gridw, 128, 0, st>>>(a);
+    else if (nc == 3) ln_bwd_w_kernel<3><<<gridw, 128, 0, st>>>(a);
+    else ln_bwd_w_kernel<4><<<gridw, 128, 0, st>>>(a);
+    IMMTSF_CHECK_LAUNCH("ln_bwd_w");
+    return IMMTSF_OK;
+  }
   const int TT = 8 / nch;
   int grid = ceil_div(R, TT);
   if (grid > 148 * 3) grid = 148 * 3;
-  cudaStream_t st = (cudaStream_t)stream;
   if (nch == 1) ln_bwd_kernel<1><<<grid, threads, 0, st>>>(a);
   else if (nch == 2) ln_bwd_kernel<2><<<grid, threads, 0, st>>>(a);
   else ln_bwd_kernel<4><<<grid, threads, 0, st>>>(a);

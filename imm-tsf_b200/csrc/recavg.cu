@@ -22,7 +22,7 @@
 // dS_t . (sum_n c_nt V'_n), a second pooled vector accumulated in the same
 // pass.  d(den) uses the closed form sum_j dE_raw_j E_raw_j = s2*eps*rstd^2
 // (LayerNorm is scale invariant up to eps).
-#include "rowtile.cuh"
+#include "rowwarp.cuh"
 #include "../../include/immtsf.h"
 
 struct PoolArgs {
@@ -33,7 +33,7 @@ struct PoolArgs {
   int B, T, d; float eps; uint32_t thr; SeedArg seed;
   float* E_drop; float* E_raw; float* mean; float* rstd; float* wsum;
   // backward only
-  const float* dE_drop; float* dVp; int lddv; float* dgamma; float* dbeta; float* dlog_sigma; float* dS; int N_max;
+  const float* dE_drop; float* dVp; int lddv; float* dgamma; float* dbeta; double* dlog_sigma; float* dS; int N_max;
 };
 
 constexpr int POOL_NB = 32;  // notes per shared-memory weight block
@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(256, NCH == 1 ? 2 : 1) recavg_bwd_notes_kernel
   __shared__ float s_w[POOL_TB][NT];
   __shared__ float s_c[POOL_TB][NT];
   __shared__ float s_dw[POOL_TB];
-  __shared__ float s_red[32];
+  __shared__ double s_redd[8];
   const int b = blockIdx.y;
   const int nb = a.offsets[b], ne = a.offsets[b + 1];
   const int n0 = nb + blockIdx.x * NT;
@@ -322,7 +322,9 @@ __global__ void __launch_bounds__(256, NCH == 1 ? 2 : 1) recavg_bwd_notes_kernel
       }
     }
   }
-  float dls = 0.f;
+  // The terms Q_n . V'_n cancel almost completely across notes and columns (dS_t is orthogonal to the pooled row),
+  // so this one scalar is summed in double from the thread level up to the global accumulator.
+  double dls = 0.0;
 #pragma unroll
   for (int u = 0; u < NT; ++u) {
     if (u < ncnt) {
@@ -332,14 +334,182 @@ __global__ void __launch_bounds__(256, NCH == 1 ? 2 : 1) recavg_bwd_notes_kernel
         if (col4 < d4) {
           reinterpret_cast<float4*>(a.dVp + (size_t)(n0 + u) * a.lddv)[col4] = accw[u][c];
           const float4 v = __ldg(reinterpret_cast<const float4*>(a.Vp + (size_t)(n0 + u) * a.ldv) + col4);
-          dls += f4_dot(accc[u][c], v);
+          const float4 q = accc[u][c];
+          dls += (double)q.x * v.x + (double)q.y * v.y + (double)q.z * v.z + (double)q.w * v.w;
         }
       }
     }
   }
-  if (threadIdx.x < NT) dls += sc_term;
-  dls = block_sum(dls, s_red);
-  if (threadIdx.x == 0) atomicAdd(a.dlog_sigma, dls);
+  if (threadIdx.x < NT) dls += (double)sc_term;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) dls += __shfl_xor_sync(0xffffffffu, dls, o);
+  if ((threadIdx.x & 31) == 0) s_redd[threadIdx.x >> 5] = dls;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)((blockDim.x + 31) >> 5); ++w) t += s_redd[w];
+    atomicAdd(a.dlog_sigma, t);
+  }
+}
+
+// ------------------------------------------------------------------ warp-per-row variants (d % 8 == 0, d <= 1024)
+// Forward: a CTA is 8 warps = 8 consecutive query times of one sample; each warp pools the sample's notes for its own
+// query time (the 8 warps read the same V' rows back to back, so 7 of 8 reads hit L1), weights are computed by the
+// lanes (one note per lane) and broadcast with shuffles.  No shared memory, no block barrier.
+template <int NC>
+__global__ void __launch_bounds__(256) recavg_pool_fwd_w_kernel(const PoolArgs a) {
+  const int b = blockIdx.y, t = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (t >= a.T) return;
+  const int lane = threadIdx.x & 31, d8 = a.d >> 3;
+  const int nb = a.offsets[b], ne = a.offsets[b + 1];
+  const float inv_sigma = 1.f / expf(__ldg(a.log_sigma));
+  const float th = a.t_hat[(size_t)b * a.t_bstride + t];
+  float acc[NC][8];
+#pragma unroll
+  for (int i = 0; i < NC; ++i) zero8(acc[i]);
+  float wsum_l = 0.f;
+  for (int n0 = nb; n0 < ne; n0 += 32) {
+    float wl = 0.f;
+    if (n0 + lane < ne) {
+      const float r = fmaxf(th - __ldg(a.tau + n0 + lane), 0.f) * inv_sigma;
+      wl = expf(-(r * r));
+    }
+    wsum_l += wl;
+    const int cnt = min(32, ne - n0);
+    for (int j = 0; j < cnt; j += 2) {  // two rows of V' in flight
+      const float w0 = __shfl_sync(0xffffffffu, wl, j), w1 = __shfl_sync(0xffffffffu, wl, (j + 1) & 31);
+      const bool two = j + 1 < cnt;
+      const float* r0 = a.Vp + (size_t)(n0 + j) * a.ldv;
+      const float* r1 = a.Vp + (size_t)(n0 + j + (two ? 1 : 0)) * a.ldv;
+      float v0[NC][8], v1[NC][8];
+#pragma unroll
+      for (int i = 0; i < NC; ++i) {
+        const int k = lane + 32 * i;
+        if (k < d8) { load8(r0, k, v0[i]); load8(r1, k, v1[i]); }
+        else { zero8(v0[i]); zero8(v1[i]); }
+      }
+      const float w1e = two ? w1 : 0.f;
+#pragma unroll
+      for (int i = 0; i < NC; ++i)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[i][e] = fmaf(w1e, v1[i][e], fmaf(w0, v0[i][e], acc[i][e]));
+    }
+  }
+  const float wsum = warp_sum(wsum_l);
+  const float inv_den = 1.f / fmaxf(wsum, 1e-6f);  // E_raw = E_wsum / clamp_min(denom, 1e-6)
+  const float inv_d = 1.f / (float)a.d;
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NC; ++i)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { acc[i][e] *= inv_den; s += acc[i][e]; }  // chunks beyond d are exactly 0
+  const float mu = warp_sum(s) * inv_d;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NC; ++i)
+    if (lane + 32 * i < d8)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) q = fmaf(acc[i][e] - mu, acc[i][e] - mu, q);
+  const float rs = 1.f / sqrtf(warp_sum(q) * inv_d + a.eps);
+  const float inv_keep = inv_keep_from_thr(a.thr);
+  const uint64_t seed = resolve_seed(a.seed);
+  const size_t rowi = (size_t)b * a.T + t;
+#pragma unroll
+  for (int i = 0; i < NC; ++i) {
+    const int k = lane + 32 * i;
+    if (k < d8) {
+      float g[8], be[8], ks[8], y[8];
+      load8(a.gamma, k, g);
+      load8(a.beta, k, be);
+      dropout_scale8(seed, IMMTSF_SITE_TTF_DROPOUT, rowi * d8 + k, a.thr, inv_keep, ks);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) y[e] = ((acc[i][e] - mu) * rs * g[e] + be[e]) * ks[e];
+      store8(a.E_drop + rowi * a.d, k, y);
+      if (a.E_raw) store8(a.E_raw + rowi * a.d, k, acc[i]);
+    }
+  }
+  if (lane == 0) {
+    if (a.mean) a.mean[rowi] = mu;
+    if (a.rstd) a.rstd[rowi] = rs;
+    if (a.wsum) a.wsum[rowi] = wsum;
+  }
+}
+
+// Backward phase 1 (LayerNorm backward of the pooled rows -> dS, d(den)), one warp per (sample, query time) row.
+template <int NC>
+__global__ void __launch_bounds__(128) recavg_bwd_rows_w_kernel(const PoolArgs a) {
+  __shared__ float s_acc[2 * 1024];  // dgamma | dbeta of this CTA
+  const int d8 = a.d >> 3, lane = threadIdx.x & 31;
+  const float inv_keep = inv_keep_from_thr(a.thr), inv_d = 1.f / (float)a.d;
+  const uint64_t seed = resolve_seed(a.seed);
+  float* dwsum_out = a.dS + (size_t)a.B * a.T * a.d;
+  for (int i = threadIdx.x; i < 2 * a.d; i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
+  float dgam[NC][8], dbet[NC][8];
+#pragma unroll
+  for (int i = 0; i < NC; ++i) { zero8(dgam[i]); zero8(dbet[i]); }
+  const int R = a.B * a.T;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  for (int r = gw; r < R; r += nw) {
+    const float mu = a.mean[r], rs = a.rstd[r], ws = a.wsum[r];
+    const float den = fmaxf(ws, 1e-6f);
+    float g[NC][8], h[NC][8];
+    float p1 = 0.f, p2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+      const int k = lane + 32 * i;
+      zero8(g[i]); zero8(h[i]);
+      if (k < d8) {
+        float dy[8], ks[8], x[8], ga[8];
+        load8(a.dE_drop + (size_t)r * a.d, k, dy);
+        load8(a.E_raw + (size_t)r * a.d, k, x);
+        load8(a.gamma, k, ga);
+        dropout_scale8(seed, IMMTSF_SITE_TTF_DROPOUT, (uint64_t)r * d8 + k, a.thr, inv_keep, ks);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float dye = dy[e] * ks[e];
+          const float he = (x[e] - mu) * rs;
+          dgam[i][e] = fmaf(dye, he, dgam[i][e]);
+          dbet[i][e] += dye;
+          const float gg = dye * ga[e];
+          g[i][e] = gg;
+          h[i][e] = he;
+          p1 += gg;
+          p2 = fmaf(gg, he, p2);
+        }
+      }
+    }
+    const float s2 = warp_sum(p2);
+    const float m1 = warp_sum(p1) * inv_d, m2 = s2 * inv_d;
+    const float sc = rs / den;
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+      const int k = lane + 32 * i;
+      if (k < d8) {
+        float o[8];  // dE_raw = rstd * (g - mean(g) - xhat * mean(g*xhat));  dS = dE_raw / den
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = sc * (g[i][e] - m1 - h[i][e] * m2);
+        store8(a.dS + (size_t)r * a.d, k, o);
+      }
+    }
+    // d(den) = -sum_j dE_raw_j E_raw_j / den = -(s2 * eps * rstd^2) / den ; clamp_min passes gradient where wsum >= 1e-6
+    if (lane == 0) dwsum_out[r] = ws >= 1e-6f ? -(s2 * a.eps * rs * rs) / den : 0.f;
+  }
+#pragma unroll
+  for (int i = 0; i < NC; ++i) {
+    const int k = lane + 32 * i;
+    if (k < d8)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        atomicAdd(&s_acc[8 * k + e], dgam[i][e]);
+        atomicAdd(&s_acc[a.d + 8 * k + e], dbet[i][e]);
+      }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < a.d; i += blockDim.x) {
+    atomicAdd(a.dgamma + i, s_acc[i]);
+    atomicAdd(a.dbeta + i, s_acc[a.d + i]);
+  }
 }
 
 static int pool_geometry(int d, int& nch, int& threads) {
@@ -355,7 +525,7 @@ static int pool_geometry(int d, int& nch, int& threads) {
 
 extern "C" int immtsf_recavg_pool_fwd(const float* Vp, int ldv, const float* tau_flat, const int32_t* offsets,
                                       const float* t_hat, int t_hat_bstride, const float* log_sigma,
-                                      const float* gamma, const float* beta, int B, int T, int d, float eps,
+                                      const float* gamma, const float* beta, int B, int T, int d, int N_max, float eps,
                                       uint32_t drop_thr, uint64_t seed, float* E_drop, float* E_raw, float* mean,
                                       float* rstd, float* wsum, void* stream) {
   if (B == 0 || T == 0) return IMMTSF_OK;
@@ -368,6 +538,19 @@ extern "C" int immtsf_recavg_pool_fwd(const float* Vp, int ldv, const float* tau
   a.log_sigma = log_sigma; a.gamma = gamma; a.beta = beta; a.B = B; a.T = T; a.d = d; a.eps = eps;
   a.thr = drop_thr; a.seed = make_seed(seed); a.E_drop = E_drop; a.E_raw = E_raw; a.mean = mean; a.rstd = rstd; a.wsum = wsum;
   cudaStream_t st = (cudaStream_t)stream;
+  // Short segments (Time-IMM: a handful of notes per window): one warp per query time, the 8 warps of a CTA share
+  // the segment through L1.  Long segments: the CTA-tile kernel streams each V' row once per 8 query times.
+  const int nc = N_max <= 32 ? rowwarp_nc(d) : 0;
+  if (nc > 0 && ((uintptr_t)gamma & 15) == 0 && ((uintptr_t)beta & 15) == 0 && ((uintptr_t)E_drop & 15) == 0 &&
+      (E_raw == nullptr || ((uintptr_t)E_raw & 15) == 0)) {
+    dim3 gridw(ceil_div(T, 8), B);
+    if (nc == 1) recavg_pool_fwd_w_kernel<1><<<gridw, 256, 0, st>>>(a);
+    else if (nc == 2) recavg_pool_fwd_w_kernel<2><<<gridw, 256, 0, st>>>(a);
+    else if (nc == 3) recavg_pool_fwd_w_kernel<3><<<gridw, 256, 0, st>>>(a);
+    else recavg_pool_fwd_w_kernel<4><<<gridw, 256, 0, st>>>(a);
+    IMMTSF_CHECK_LAUNCH("recavg_pool_fwd_w");
+    return IMMTSF_OK;
+  }
   const int TT = 8 / nch;
   dim3 grid(ceil_div(T, TT), B);
   if (nch == 1) recavg_pool_fwd_kernel<1><<<grid, threads, 0, st>>>(a);
@@ -382,7 +565,7 @@ extern "C" int immtsf_recavg_pool_bwd(const float* dE_drop, const float* E_raw, 
                                       const int32_t* offsets, const float* t_hat, int t_hat_bstride,
                                       const float* log_sigma, const float* gamma, int B, int T, int d, int N_max,
                                       uint32_t drop_thr, uint64_t seed, float* dS, float* dVp, int lddv, float* dgamma,
-                                      float* dbeta, float* dlog_sigma, void* stream) {
+                                      float* dbeta, double* dlog_sigma, void* stream) {
   if (B == 0 || T == 0) return IMMTSF_OK;
   IMMTSF_REQUIRE(dE_drop && E_raw && mean && rstd && wsum && Vp && tau_flat && offsets && t_hat && log_sigma && gamma &&
                      dS && dVp && dgamma && dbeta && dlog_sigma, "recavg_pool_bwd: null pointer");
@@ -399,12 +582,23 @@ extern "C" int immtsf_recavg_pool_bwd(const float* dE_drop, const float* E_raw, 
   a.dE_drop = dE_drop; a.dVp = dVp; a.lddv = lddv; a.dgamma = dgamma; a.dbeta = dbeta; a.dlog_sigma = dlog_sigma;
   a.dS = dS; a.N_max = N_max;
   cudaStream_t st = (cudaStream_t)stream;
-  const int TT = 8 / nch;
-  dim3 grid1(ceil_div(T, TT), B);
-  if (nch == 1) recavg_bwd_rows_kernel<1><<<grid1, threads, 0, st>>>(a);
-  else if (nch == 2) recavg_bwd_rows_kernel<2><<<grid1, threads, 0, st>>>(a);
-  else recavg_bwd_rows_kernel<4><<<grid1, threads, 0, st>>>(a);
-  IMMTSF_CHECK_LAUNCH("recavg_bwd_rows");
+  const int nc = rowwarp_nc(d);
+  if (nc > 0 && ((uintptr_t)gamma & 15) == 0 && ((uintptr_t)dE_drop & 15) == 0 && ((uintptr_t)E_raw & 15) == 0) {
+    int gridw = ceil_div(B * T, 4);
+    if (gridw > 148 * 4) gridw = 148 * 4;
+    if (nc == 1) recavg_bwd_rows_w_kernel<1><<<gridw, 128, 0, st>>>(a);
+    else if (nc == 2) recavg_bwd_rows_w_kernel<2><<<gridw, 128, 0, st>>>(a);
+    else if (nc == 3) recavg_bwd_rows_w_kernel<3><<<gridw, 128, 0, st>>>(a);
+    else recavg_bwd_rows_w_kernel<4><<<gridw, 128, 0, st>>>(a);
+    IMMTSF_CHECK_LAUNCH("recavg_bwd_rows_w");
+  } else {
+    const int TT = 8 / nch;
+    dim3 grid1(ceil_div(T, TT), B);
+    if (nch == 1) recavg_bwd_rows_kernel<1><<<grid1, threads, 0, st>>>(a);
+    else if (nch == 2) recavg_bwd_rows_kernel<2><<<grid1, threads, 0, st>>>(a);
+    else recavg_bwd_rows_kernel<4><<<grid1, threads, 0, st>>>(a);
+    IMMTSF_CHECK_LAUNCH("recavg_bwd_rows");
+  }
   dim3 grid2(ceil_div(N_max, 8 / nch), B);
   if (nch == 1) recavg_bwd_notes_kernel<1><<<grid2, threads, 0, st>>>(a);
   else if (nch == 2) recavg_bwd_notes_kernel<2><<<grid2, threads, 0, st>>>(a);

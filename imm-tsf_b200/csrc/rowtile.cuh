@@ -37,14 +37,16 @@ __device__ __forceinline__ void f4_add(float4& acc, const float4& v) {
   acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
 }
 
-// dropout keep-scales for the 4 consecutive elements whose flat index / 4 == idx4
+// dropout keep-scales for the 4 consecutive elements whose flat index / 4 == idx4 (half of a Philox call, common.cuh)
 __device__ __forceinline__ float4 dropout_scale4(uint64_t seed, uint32_t site, uint64_t idx4, uint32_t thr, float inv_keep) {
   if (thr == 0u) return make_float4(1.f, 1.f, 1.f, 1.f);
-  const Philox4 r = philox4x32_10((uint32_t)idx4, (uint32_t)(idx4 >> 32), site, 0u, (uint32_t)seed, (uint32_t)(seed >> 32));
-  return make_float4(r.x >= thr ? inv_keep : 0.f, r.y >= thr ? inv_keep : 0.f, r.z >= thr ? inv_keep : 0.f,
-                     r.w >= thr ? inv_keep : 0.f);
+  const uint64_t c = idx4 >> 1;
+  const Philox4 r = philox4x32_10((uint32_t)c, (uint32_t)(c >> 32), site, 0u, (uint32_t)seed, (uint32_t)(seed >> 32));
+  const uint32_t w0 = (idx4 & 1) ? r.z : r.x, w1 = (idx4 & 1) ? r.w : r.y;
+  return make_float4((w0 & 0xFFFFu) >= thr ? inv_keep : 0.f, (w0 >> 16) >= thr ? inv_keep : 0.f,
+                     (w1 & 0xFFFFu) >= thr ? inv_keep : 0.f, (w1 >> 16) >= thr ? inv_keep : 0.f);
 }
 __host__ __device__ __forceinline__ float inv_keep_from_thr(uint32_t thr) {
-  // p = thr / 2^32 ; 1/(1-p)
-  return thr == 0u ? 1.f : (float)(1.0 / (1.0 - (double)thr / 4294967296.0));
+  // realised drop rate = thr / 2^16 ; 1/(1-rate)
+  return thr == 0u ? 1.f : (float)(1.0 / (1.0 - (double)thr / 65536.0));
 }

@@ -37,7 +37,7 @@ SIGNATURES = {
     "immtsf_split_lo": [P, I, I, I, P, I, P, P],
     "immtsf_gemm_plan": [I, I, I, I, I, P, I, P, I, P, I, I],
     "immtsf_colsum": [P, I, I, I, P, F, P, P, SZ, P],
-    "immtsf_recavg_pool_fwd": [P, I, P, P, P, I, P, P, P, I, I, I, F, U32, U64, P, P, P, P, P, P],
+    "immtsf_recavg_pool_fwd": [P, I, P, P, P, I, P, P, P, I, I, I, I, F, U32, U64, P, P, P, P, P, P],
     "immtsf_recavg_pool_bwd": [P, P, P, P, P, P, I, P, P, P, I, P, P, I, I, I, I, U32, U64, P, P, I, P, P, P, P],
     "immtsf_time2vec_fwd": [P, P, P, P, P, I, P, I, P, I, P],
     "immtsf_time2vec_bwd": [P, I, P, P, P, I, P, P, P, P, P, I, P],
@@ -45,10 +45,10 @@ SIGNATURES = {
     "immtsf_segattn_bwd": [P, P, P, P, P, I, I, I, I, I, I, U32, U64, P, P, P],
     "immtsf_ln_fwd": [P, I, P, P, P, I, P, P, I, I, F, U32, U64, U32, P, P, P, P],
     "immtsf_ln_bwd": [P, P, I, P, P, P, I, P, P, P, I, I, U32, U64, U32, P, P, P, P, P],
-    "immtsf_gru_scan_fwd": [P, P, P, I, I, I, P, P, P],
+    "immtsf_gru_scan_fwd": [P, P, P, I, I, I, P, P, P, P],
     "immtsf_gr_tail_fwd": [P, P, P, P, P, P, P, P, I, I, I, F, U32, U64, P, P, P],
     "immtsf_gr_tail_bwd": [P, P, P, P, P, P, P, P, I, I, I, F, U32, U64, P, P, P, P, P, P],
-    "immtsf_gru_scan_bwd": [P, P, P, P, P, I, I, I, P, P, P],
+    "immtsf_gru_scan_bwd": [P, P, P, P, P, P, I, I, I, P, P, P],
     "immtsf_xattn_core_fwd": [P, I, P, I, P, I, P, I, I, I, I, U32, U64, P, I, P, P],
     "immtsf_xattn_core_bwd": [P, I, P, I, P, I, P, I, P, P, I, I, I, I, U32, U64, P, I, P, I, P, I, P],
     "immtsf_gemm_batched": [I, I, I, I, I, F, P, I, L, L, P, I, L, L, F, P, I, L, L, I, I, P, SZ, P],

@@ -193,22 +193,22 @@ class GRAddFn(torch.autograd.Function):
         bcat = torch.cat([b_ih, b_g], dim=0)
         G4 = ops.linear_fwd(X, Wcat, bcat)
         W_hh_c, b_hh_c, W_r_c = W_hh.contiguous(), b_hh.contiguous(), W_r.contiguous()
-        h_all, h_prev = ops.gru_scan_fwd(G4, W_hh_c, b_hh_c, B, T, C)
+        h_all, h_prev, gates = ops.gru_scan_fwd(G4, W_hh_c, b_hh_c, B, T, C)
         Y_out = ops.gr_tail_fwd(Yc, G4, h_all, W_r_c, b_r, gamma, beta, m_txt, B, T, C, thr, seed, flags)
         if save:
             ctx.thr, ctx.seed, ctx.dims = thr, seed, (B, T, C, d)
-            ctx.save_for_backward(m_txt, X, Wcat, G4, h_all, h_prev, W_hh_c, b_hh_c, W_r_c, b_r, gamma, beta)
+            ctx.save_for_backward(m_txt, X, Wcat, G4, h_all, h_prev, W_hh_c, b_hh_c, W_r_c, b_r, gamma, beta, gates)
         return Y_out
 
     @staticmethod
     def backward(ctx, dY_out):
-        m_txt, X, Wcat, G4, h_all, h_prev, W_hh, b_hh, W_r, b_r, gamma, beta = ctx.saved_tensors
+        m_txt, X, Wcat, G4, h_all, h_prev, W_hh, b_hh, W_r, b_r, gamma, beta, gates = ctx.saved_tensors
         B, T, C, d = ctx.dims
         dY_out = dY_out.contiguous()
         dG4 = torch.empty_like(G4)
         d_delta, dh_out, dgamma, dbeta = ops.gr_tail_bwd(dY_out, G4, h_all, W_r, b_r, gamma, beta, m_txt, B, T, C, ctx.thr,
                                                          ctx.seed, dG4)
-        dGh = ops.gru_scan_bwd(G4, h_prev, W_hh, b_hh, dh_out, B, T, C, dG4)
+        dGh = ops.gru_scan_bwd(G4, h_prev, W_hh, b_hh, dh_out, B, T, C, dG4, gates)
         dW_r = ops.linear_wgrad(d_delta, h_all)
         db_r = ops.colsum(d_delta)
         dW_hh = ops.linear_wgrad(dGh, h_prev)

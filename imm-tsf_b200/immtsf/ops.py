@@ -42,10 +42,10 @@ def _chk(t: torch.Tensor, name: str, dtype=torch.float32):
 
 
 def drop_thr(p: float) -> int:
-    """floor(p * 2^32) clamped to uint32; 0 disables dropout."""
+    """floor(p * 2^16) clamped to 16 bits (csrc/common.cuh: 16 random bits per element); 0 disables dropout."""
     if p <= 0.0:
         return 0
-    return min(int(p * 4294967296.0), 4294967295)
+    return min(int(p * 65536.0), 65535)
 
 
 def new_seed() -> int:
@@ -241,7 +241,7 @@ def recavg_pool_fwd(Vp, r: RaggedNotes, t_hat, log_sigma, gamma, beta, T, d, thr
     wsum = torch.empty(B, T, dtype=torch.float32, device=dev) if save else None
     bstride = 0 if t_hat.dim() == 1 else t_hat.stride(0)
     _lib.call("immtsf_recavg_pool_fwd", _p(Vp), Vp.stride(0), _p(r.tau_flat), _p(r.offsets), _p(t_hat), bstride,
-              _p(log_sigma), _p(gamma), _p(beta), B, T, d, LN_EPS, thr, seed, _p(E_drop), _p(E_raw), _p(mean), _p(rstd),
+              _p(log_sigma), _p(gamma), _p(beta), B, T, d, max(r.N, 1), LN_EPS, thr, seed, _p(E_drop), _p(E_raw), _p(mean), _p(rstd),
               _p(wsum), _stream())
     return E_drop, E_raw, mean, rstd, wsum
 
@@ -252,13 +252,13 @@ def recavg_pool_bwd(dE_drop, E_raw, mean, rstd, wsum, Vp, r: RaggedNotes, t_hat,
     dS = torch.empty(r.B * T * (d + 1), dtype=torch.float32, device=dev)  # rows [B*T, d] + one scalar per row
     dgamma = torch.zeros(d, dtype=torch.float32, device=dev)
     dbeta = torch.zeros(d, dtype=torch.float32, device=dev)
-    dls = torch.zeros((), dtype=torch.float32, device=dev)
+    dls = torch.zeros((), dtype=torch.float64, device=dev)  # summed in double by the kernel
     bstride = 0 if t_hat.dim() == 1 else t_hat.stride(0)
     _lib.call("immtsf_recavg_pool_bwd", _p(dE_drop), _p(E_raw), _p(mean), _p(rstd), _p(wsum), _p(Vp), Vp.stride(0),
               _p(r.tau_flat), _p(r.offsets), _p(t_hat), bstride, _p(log_sigma), _p(gamma), r.B, T, d, max(r.N, 1), thr, seed,
               _p(dS), _p(dVp), d, _p(dgamma), _p(dbeta), _p(dls), _stream())
     zero_pad_rows(dVp, d, r.m_dev, r.M_alloc)
-    return dVp, dgamma, dbeta, dls
+    return dVp, dgamma, dbeta, dls.float()
 
 
 # ------------------------------------------------------------------ Time2Vec / segment attention / LN
@@ -323,8 +323,10 @@ def ln_bwd(dy, x, res, valid, rows_per_sample, gamma, mean, rstd, thr, seed, sit
 def gru_scan_fwd(G4, w_hh, b_hh, B, T, C):
     h_all = torch.empty(B * T, C, dtype=torch.float32, device=G4.device)
     h_prev = torch.empty(B * T, C, dtype=torch.float32, device=G4.device)
-    _lib.call("immtsf_gru_scan_fwd", _p(G4), _p(w_hh), _p(b_hh), B, T, C, _p(h_all), _p(h_prev), _stream())
-    return h_all, h_prev
+    # many channels: wide recurrence (one CTA per sample), which stores the gate activations for backward
+    gates = torch.empty(B * T, 4 * C, dtype=torch.float32, device=G4.device) if C > 32 else None
+    _lib.call("immtsf_gru_scan_fwd", _p(G4), _p(w_hh), _p(b_hh), B, T, C, _p(h_all), _p(h_prev), _p(gates), _stream())
+    return h_all, h_prev, gates
 
 
 def gr_tail_fwd(Y, G4, h_all, w_r, b_r, gamma, beta, m_txt, B, T, C, thr, seed, flags):
@@ -345,9 +347,10 @@ def gr_tail_bwd(dY_out, G4, h_all, w_r, b_r, gamma, beta, m_txt, B, T, C, thr, s
     return d_delta, dh_out, dgamma, dbeta
 
 
-def gru_scan_bwd(G4, h_prev, w_hh, b_hh, dh_out, B, T, C, dG4):
+def gru_scan_bwd(G4, h_prev, w_hh, b_hh, dh_out, B, T, C, dG4, gates=None):
     dGh = torch.empty(B * T, 3 * C, dtype=torch.float32, device=G4.device)
-    _lib.call("immtsf_gru_scan_bwd", _p(G4), _p(h_prev), _p(w_hh), _p(b_hh), _p(dh_out), B, T, C, _p(dG4), _p(dGh), _stream())
+    _lib.call("immtsf_gru_scan_bwd", _p(G4), _p(h_prev), _p(w_hh), _p(b_hh), _p(dh_out), _p(gates), B, T, C, _p(dG4), _p(dGh),
+              _stream())
     return dGh
 
 

@@ -23,8 +23,8 @@
  *     m_dev` so no host sync is needed.  Producers zero rows
  *     [sumN, roundup(sumN,128)) so that reductions over rows stay clean.
  *   - dropout masks are Philox4x32-10 functions of (seed, site, element index)
- *     (csrc/common.cuh), regenerated in backward; `drop_thr = floor(p*2^32)`,
- *     0 disables dropout.
+ *     (csrc/common.cuh: 16 random bits per element, one call per 8 elements),
+ *     regenerated in backward; `drop_thr = floor(p*2^16)`, 0 disables dropout.
  */
 #ifndef IMMTSF_H_
 #define IMMTSF_H_
@@ -124,18 +124,19 @@ int immtsf_colsum(const float* X, int M, int N, int ldx, float* out, float beta,
  * weighted mean over each ragged segment, LayerNorm, dropout ------------- */
 int immtsf_recavg_pool_fwd(const float* Vp, int ldv, const float* tau_flat, const int32_t* offsets,
                            const float* t_hat, int t_hat_bstride, const float* log_sigma,
-                           const float* gamma, const float* beta, int B, int T, int d, float eps,
+                           const float* gamma, const float* beta, int B, int T, int d, int N_max, float eps,
                            uint32_t drop_thr, uint64_t seed, float* E_drop, float* E_raw,
                            float* mean, float* rstd, float* wsum, void* stream);
 /* dS: caller-owned scratch of B*T*(d+1) floats (the LayerNorm-backward rows [B*T, d] followed by one scalar per
  * row, written by the first of the two kernels and read by the second); N_max bounds the notes per sample
- * (grid size only). */
+ * (grid size only).  dlog_sigma is a DOUBLE accumulator (zeroed by the caller): its terms cancel almost completely,
+ * so they are summed in double from the thread level up. */
 int immtsf_recavg_pool_bwd(const float* dE_drop, const float* E_raw, const float* mean, const float* rstd,
                            const float* wsum, const float* Vp, int ldv, const float* tau_flat,
                            const int32_t* offsets, const float* t_hat, int t_hat_bstride,
                            const float* log_sigma, const float* gamma, int B, int T, int d, int N_max,
                            uint32_t drop_thr, uint64_t seed, float* dS, float* dVp, int lddv, float* dgamma,
-                           float* dbeta, float* dlog_sigma, void* stream);
+                           float* dbeta, double* dlog_sigma, void* stream);
 
 /* ---- Time2Vec (TTF_T2V_XAttn.py:20-24,136) written straight into the
  * [V' ; phi] concat buffer (:139) ---------------------------------------- */
@@ -173,8 +174,10 @@ int immtsf_ln_bwd(const float* dy, const float* x, int ldx, const float* xbias, 
 /* ---- K5: MMF_GR_Add (MMF_GR_Add.py:43-60).  G4 [B*T, 4C] = [Y;E] [W_ih;W_g]^T
  * + [b_ih;b_g] comes from immtsf_gemm; the scan consumes columns [0,3C) and
  * the tail columns [3C,4C). ----------------------------------------------- */
+/* gates (nullable): [B*T, 4C] scratch for (r, z, n, W_hn h + b_hn).  When given and C > 32 the wide recurrence is
+ * used (one CTA per sample, W_hh rows in registers) and backward must be handed the same buffer. */
 int immtsf_gru_scan_fwd(const float* G4, const float* w_hh, const float* b_hh, int B, int T, int C,
-                        float* h_all, float* h_prev, void* stream);
+                        float* h_all, float* h_prev, float* gates, void* stream);
 int immtsf_gr_tail_fwd(const float* Y, const float* G4, const float* h_all, const float* w_r,
                        const float* b_r, const float* gamma, const float* beta, const uint8_t* m_txt,
                        int B, int T, int C, float eps, uint32_t drop_thr, uint64_t seed, float* Y_out,
@@ -190,7 +193,8 @@ int immtsf_gr_tail_bwd(const float* dY_out, const float* G4, const float* h_all,
 /*   dG4[:, 0:3C] = [da_r,da_z,da_n], dGh [B*T,3C] = [da_r,da_z,da_n*r]
  *   (-> dW_hh = dGh^T h_prev, db_hh = colsum dGh) */
 int immtsf_gru_scan_bwd(const float* G4, const float* h_prev, const float* w_hh, const float* b_hh,
-                        const float* dh_out, int B, int T, int C, float* dG4, float* dGh, void* stream);
+                        const float* dh_out, const float* gates, int B, int T, int C, float* dG4, float* dGh,
+                        void* stream);
 
 /* ---- K6: MMF_XAttn_Add core (MMF_XAttn_Add.py:73-80 + MHA internals):
  * per (sample, head) T x T attention; q,k,v are [B*T, d] with leading dims. */

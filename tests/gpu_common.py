@@ -98,6 +98,7 @@ def oracle_masks(cfg, notes, T, C, d, p, seed):
 
 
 def oracle_run(cfg, params, notes, tau, t_hat, Y, G, dtype=torch.float64, p=0.0, masks=None, grads=True):
+    p = philox_ref.realised_p(p)  # the kernels quantise the drop rate to 16 bits and rescale by the realised rate
     P = {k: v.detach().cpu().to(dtype).clone().requires_grad_(grads) for k, v in params.items()}
     Yr = Y.to(dtype).clone().requires_grad_(grads)
     mk = None if masks is None else {k: v.to(dtype) for k, v in masks.items()}

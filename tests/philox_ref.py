@@ -1,6 +1,7 @@
 """Host mirror of the kernels' dropout RNG (csrc/common.cuh): Philox4x32-10 keyed
-by the seed, counter = (idx>>2 lo, idx>>2 hi, site, 0), element idx uses word
-idx&3; keep iff word >= floor(p * 2^32).  Test infrastructure."""
+by the seed, counter = (idx>>3 lo, idx>>3 hi, site, 0); element idx uses the 16-bit
+field (idx & 1) of word (idx>>1) & 3; keep iff field >= floor(p * 2^16).  Test
+infrastructure."""
 import numpy as np
 
 M0, M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
@@ -29,12 +30,18 @@ def keep_mask(seed: int, site: int, idx: np.ndarray, p: float) -> np.ndarray:
     idx = np.asarray(idx, dtype=np.uint64)
     if p <= 0:
         return np.ones(idx.shape, dtype=np.float32)
-    thr = min(int(p * 4294967296.0), 4294967295)
-    c = idx >> np.uint64(2)
+    thr = min(int(p * 65536.0), 65535)
+    c = idx >> np.uint64(3)
     c0 = (c & MASK32).astype(np.uint32)
     c1 = (c >> np.uint64(32)).astype(np.uint32)
     z = np.zeros_like(c0)
     w = philox4x32_10(c0, c1, np.full_like(c0, site), z, seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
-    sel = (idx & np.uint64(3)).astype(np.int64)
+    sel = ((idx >> np.uint64(1)) & np.uint64(3)).astype(np.int64)
     word = np.choose(sel, w)
-    return (word >= np.uint32(thr)).astype(np.float32)
+    field = np.where((idx & np.uint64(1)) == 1, word >> np.uint32(16), word & np.uint32(0xFFFF))
+    return (field >= np.uint32(thr)).astype(np.float32)
+
+
+def realised_p(p: float) -> float:
+    """The drop rate the kernels realise for a nominal p: floor(p * 2^16) / 2^16 (what 1/(1-p) must use)."""
+    return min(int(p * 65536.0), 65535) / 65536.0 if p > 0 else 0.0

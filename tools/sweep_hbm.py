@@ -99,7 +99,7 @@ def main():
     for (B, T, C) in [(256, 24, 4), (2048, 24, 4), (256, 192, 96)]:
         G4 = torch.randn(B * T, 4 * C, device=dev)
         w_hh, b_hh = torch.randn(3 * C, C, device=dev) * 0.1, torch.zeros(3 * C, device=dev)
-        ms = timeit(lambda: ops.gru_scan_fwd(G4, w_hh, b_hh, B, T, C), flush)
+        ms = timeit(lambda: ops.gru_scan_fwd(G4, w_hh, b_hh, B, T, C), flush)  # C > 32: wide recurrence
         byt = 4.0 * B * T * (3 * C + 2 * C)
         rows.append(dict(kernel="gru_scan_fwd", B=B, T=T, C=C, ms=ms, alg_bytes=byt, GBps=byt / ms / 1e6, frac=byt / ms / 1e6 / peak,
                          us_per_scan_step=ms * 1e3 / T))
