@@ -697,10 +697,10 @@ extern "C" size_t immtsf_gemm_batched_workspace_bytes(int transA, int transB, in
          align_up(flat_extent(rb, cb, ldb, b_s1, b_s2, batch1, batch2) * 4 + 16, 256) + 256;
 }
 
-extern "C" int immtsf_gemm_batched(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda, long a_s1,
-                                   long a_s2, const float* B, int ldb, long b_s1, long b_s2, float beta, float* C, int ldc,
-                                   long c_s1, long c_s2, int batch1, int batch2, void* workspace, size_t workspace_bytes,
-                                   void* stream) {
+extern "C" int immtsf_gemm_batched(int transA, int transB, int M, int N, int K, float alpha, const float* A, const float* A_lo,
+                                   int lda, long a_s1, long a_s2, const float* B, const float* B_lo, int ldb, long b_s1,
+                                   long b_s2, float beta, float* C, int ldc, long c_s1, long c_s2, int batch1, int batch2,
+                                   void* workspace, size_t workspace_bytes, void* stream) {
   if (M <= 0 || N <= 0 || batch1 <= 0 || batch2 <= 0) return IMMTSF_OK;
   IMMTSF_REQUIRE(A && B && C && K >= 1, "gemm_batched: null operand or K < 1");
   IMMTSF_REQUIRE((long)batch1 * batch2 <= 65535, "gemm_batched: at most 65535 batches");
@@ -714,13 +714,21 @@ extern "C" int immtsf_gemm_batched(int transA, int transB, int M, int N, int K, 
   const int ra = transA ? K : M, ca = transA ? M : K, rb = transB ? N : K, cb = transB ? K : N;
   const size_t ea = flat_extent(ra, ca, lda, a_s1, a_s2, batch1, batch2), eb = flat_extent(rb, cb, ldb, b_s1, b_s2, batch1, batch2);
   uint8_t* w = (uint8_t*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
-  float* Al = (float*)w;
-  float* Bl = (float*)(w + align_up(ea * 4 + 16, 256));
-  // lo over the flat extents (1 x extent "matrices"; the tail beyond a multiple of 4 is handled by the kernel)
-  int rc = launch_split_lo(A, (int)align_up(ea, 4), 1, (int)ea, Al, (int)align_up(ea, 4), nullptr, 0, st);
-  if (rc) return rc;
-  rc = launch_split_lo(B, (int)align_up(eb, 4), 1, (int)eb, Bl, (int)align_up(eb, 4), nullptr, 0, st);
-  if (rc) return rc;
+  // lo over the flat extents (1 x extent "matrices"; the tail beyond a multiple of 4 is handled by the kernel),
+  // unless the caller hands in lo buffers it made earlier with immtsf_split_lo(src, ., 1, extent, ...)
+  const float* Al = A_lo;
+  const float* Bl = B_lo;
+  if (Al == nullptr) {
+    int rc = launch_split_lo(A, (int)align_up(ea, 4), 1, (int)ea, (float*)w, (int)align_up(ea, 4), nullptr, 0, st);
+    if (rc) return rc;
+    Al = (const float*)w;
+  }
+  if (Bl == nullptr) {
+    float* dst = (float*)(w + align_up(ea * 4 + 16, 256));
+    int rc = launch_split_lo(B, (int)align_up(eb, 4), 1, (int)eb, dst, (int)align_up(eb, 4), nullptr, 0, st);
+    if (rc) return rc;
+    Bl = dst;
+  }
   const int bn = (N > 128 && ceil_div(N, 256) * ceil_div(M, BM) * batch1 * batch2 >= 148) ? 256 : 128;
   const int boxA = transA ? 32 : BM, boxB = transB ? bn : 32;
   CUtensorMap mAh, mAl, mBh, mBl;

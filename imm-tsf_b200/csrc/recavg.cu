@@ -309,14 +309,28 @@ __global__ void __launch_bounds__(256, NCH == 1 ? 2 : 1) recavg_bwd_notes_kernel
           g[v][c] = (tq + v < tcnt && col4 < d4)
                         ? __ldg(reinterpret_cast<const float4*>(a.dS + ((size_t)b * a.T + t0 + tq + v) * a.d) + col4) : f4_zero();
         }
+      if (NT == 8 && ncnt <= 4) {  // half-empty tile (CTA-uniform): skip the empty note slots
 #pragma unroll
-      for (int v = 0; v < 4; ++v) {
-        if (tq + v < tcnt) {
+        for (int v = 0; v < 4; ++v) {
+          if (tq + v < tcnt) {
 #pragma unroll
-          for (int u = 0; u < NT; ++u) {
-            const float w = s_w[tq + v][u], cc = s_c[tq + v][u];
+            for (int u = 0; u < NT / 2; ++u) {
+              const float w = s_w[tq + v][u], cc = s_c[tq + v][u];
 #pragma unroll
-            for (int c = 0; c < NCH; ++c) { f4_fma(accw[u][c], w, g[v][c]); f4_fma(accc[u][c], cc, g[v][c]); }
+              for (int c = 0; c < NCH; ++c) { f4_fma(accw[u][c], w, g[v][c]); f4_fma(accc[u][c], cc, g[v][c]); }
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          if (tq + v < tcnt) {
+#pragma unroll
+            for (int u = 0; u < NT; ++u) {
+              const float w = s_w[tq + v][u], cc = s_c[tq + v][u];
+#pragma unroll
+              for (int c = 0; c < NCH; ++c) { f4_fma(accw[u][c], w, g[v][c]); f4_fma(accc[u][c], cc, g[v][c]); }
+            }
           }
         }
       }
@@ -356,82 +370,96 @@ __global__ void __launch_bounds__(256, NCH == 1 ? 2 : 1) recavg_bwd_notes_kernel
 // Forward: a CTA is 8 warps = 8 consecutive query times of one sample; each warp pools the sample's notes for its own
 // query time (the 8 warps read the same V' rows back to back, so 7 of 8 reads hit L1), weights are computed by the
 // lanes (one note per lane) and broadcast with shuffles.  No shared memory, no block barrier.
-template <int NC>
+template <int NC, int TPW>
 __global__ void __launch_bounds__(256) recavg_pool_fwd_w_kernel(const PoolArgs a) {
-  const int b = blockIdx.y, t = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (t >= a.T) return;
+  // warp w of the CTA owns the TPW query times t0 + w, t0 + w + 8, ...: every V' chunk it loads feeds TPW
+  // accumulators (the first version, one query time per warp, was bound by L1 bandwidth: 74 % l1tex throughput)
+  const int b = blockIdx.y, tb = blockIdx.x * (8 * TPW) + (threadIdx.x >> 5);
+  if (tb >= a.T) return;
   const int lane = threadIdx.x & 31, d8 = a.d >> 3;
   const int nb = a.offsets[b], ne = a.offsets[b + 1];
   const float inv_sigma = 1.f / expf(__ldg(a.log_sigma));
-  const float th = a.t_hat[(size_t)b * a.t_bstride + t];
-  float acc[NC][8];
+  float th[TPW];
 #pragma unroll
-  for (int i = 0; i < NC; ++i) zero8(acc[i]);
-  float wsum_l = 0.f;
+  for (int q = 0; q < TPW; ++q) th[q] = tb + 8 * q < a.T ? a.t_hat[(size_t)b * a.t_bstride + tb + 8 * q] : 0.f;
+  float acc[TPW][NC][8];
+  float wsum_l[TPW];
+#pragma unroll
+  for (int q = 0; q < TPW; ++q) {
+    wsum_l[q] = 0.f;
+#pragma unroll
+    for (int i = 0; i < NC; ++i) zero8(acc[q][i]);
+  }
   for (int n0 = nb; n0 < ne; n0 += 32) {
-    float wl = 0.f;
-    if (n0 + lane < ne) {
-      const float r = fmaxf(th - __ldg(a.tau + n0 + lane), 0.f) * inv_sigma;
-      wl = expf(-(r * r));
+    float wl[TPW];
+    const float tn = n0 + lane < ne ? __ldg(a.tau + n0 + lane) : 0.f;
+#pragma unroll
+    for (int q = 0; q < TPW; ++q) {
+      const float r = fmaxf(th[q] - tn, 0.f) * inv_sigma;
+      wl[q] = n0 + lane < ne ? expf(-(r * r)) : 0.f;
+      wsum_l[q] += wl[q];
     }
-    wsum_l += wl;
     const int cnt = min(32, ne - n0);
-    for (int j = 0; j < cnt; j += 2) {  // two rows of V' in flight
-      const float w0 = __shfl_sync(0xffffffffu, wl, j), w1 = __shfl_sync(0xffffffffu, wl, (j + 1) & 31);
-      const bool two = j + 1 < cnt;
+    for (int j = 0; j < cnt; ++j) {
       const float* r0 = a.Vp + (size_t)(n0 + j) * a.ldv;
-      const float* r1 = a.Vp + (size_t)(n0 + j + (two ? 1 : 0)) * a.ldv;
-      float v0[NC][8], v1[NC][8];
+      float v0[NC][8];
 #pragma unroll
       for (int i = 0; i < NC; ++i) {
-        const int k = lane + 32 * i;
-        if (k < d8) { load8(r0, k, v0[i]); load8(r1, k, v1[i]); }
-        else { zero8(v0[i]); zero8(v1[i]); }
+        if (lane + 32 * i < d8) load8(r0, lane + 32 * i, v0[i]);
+        else zero8(v0[i]);
       }
-      const float w1e = two ? w1 : 0.f;
 #pragma unroll
-      for (int i = 0; i < NC; ++i)
+      for (int q = 0; q < TPW; ++q) {
+        const float w0 = __shfl_sync(0xffffffffu, wl[q], j);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[i][e] = fmaf(w1e, v1[i][e], fmaf(w0, v0[i][e], acc[i][e]));
+        for (int i = 0; i < NC; ++i)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[q][i][e] = fmaf(w0, v0[i][e], acc[q][i][e]);
+      }
     }
   }
-  const float wsum = warp_sum(wsum_l);
-  const float inv_den = 1.f / fmaxf(wsum, 1e-6f);  // E_raw = E_wsum / clamp_min(denom, 1e-6)
-  const float inv_d = 1.f / (float)a.d;
-  float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < NC; ++i)
-#pragma unroll
-    for (int e = 0; e < 8; ++e) { acc[i][e] *= inv_den; s += acc[i][e]; }  // chunks beyond d are exactly 0
-  const float mu = warp_sum(s) * inv_d;
-  float q = 0.f;
-#pragma unroll
-  for (int i = 0; i < NC; ++i)
-    if (lane + 32 * i < d8)
-#pragma unroll
-      for (int e = 0; e < 8; ++e) q = fmaf(acc[i][e] - mu, acc[i][e] - mu, q);
-  const float rs = 1.f / sqrtf(warp_sum(q) * inv_d + a.eps);
   const float inv_keep = inv_keep_from_thr(a.thr);
   const uint64_t seed = resolve_seed(a.seed);
-  const size_t rowi = (size_t)b * a.T + t;
+  const float inv_d = 1.f / (float)a.d;
 #pragma unroll
-  for (int i = 0; i < NC; ++i) {
-    const int k = lane + 32 * i;
-    if (k < d8) {
-      float g[8], be[8], ks[8], y[8];
-      load8(a.gamma, k, g);
-      load8(a.beta, k, be);
-      dropout_scale8(seed, IMMTSF_SITE_TTF_DROPOUT, rowi * d8 + k, a.thr, inv_keep, ks);
+  for (int q = 0; q < TPW; ++q) {
+    const int t = tb + 8 * q;
+    if (t >= a.T) break;
+    const float wsum = warp_sum(wsum_l[q]);
+    const float inv_den = 1.f / fmaxf(wsum, 1e-6f);  // E_raw = E_wsum / clamp_min(denom, 1e-6)
+    float s = 0.f;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) y[e] = ((acc[i][e] - mu) * rs * g[e] + be[e]) * ks[e];
-      store8(a.E_drop + rowi * a.d, k, y);
-      if (a.E_raw) store8(a.E_raw + rowi * a.d, k, acc[i]);
+    for (int i = 0; i < NC; ++i)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { acc[q][i][e] *= inv_den; s += acc[q][i][e]; }  // chunks beyond d are exactly 0
+    const float mu = warp_sum(s) * inv_d;
+    float qq = 0.f;
+#pragma unroll
+    for (int i = 0; i < NC; ++i)
+      if (lane + 32 * i < d8)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) qq = fmaf(acc[q][i][e] - mu, acc[q][i][e] - mu, qq);
+    const float rs = 1.f / sqrtf(warp_sum(qq) * inv_d + a.eps);
+    const size_t rowi = (size_t)b * a.T + t;
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+      const int k = lane + 32 * i;
+      if (k < d8) {
+        float g[8], be[8], ks[8], y[8];
+        load8(a.gamma, k, g);
+        load8(a.beta, k, be);
+        dropout_scale8(seed, IMMTSF_SITE_TTF_DROPOUT, rowi * d8 + k, a.thr, inv_keep, ks);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) y[e] = ((acc[q][i][e] - mu) * rs * g[e] + be[e]) * ks[e];
+        store8(a.E_drop + rowi * a.d, k, y);
+        if (a.E_raw) store8(a.E_raw + rowi * a.d, k, acc[q][i]);
+      }
     }
-  }
-  if (lane == 0) {
-    if (a.mean) a.mean[rowi] = mu;
-    if (a.rstd) a.rstd[rowi] = rs;
-    if (a.wsum) a.wsum[rowi] = wsum;
+    if (lane == 0) {
+      if (a.mean) a.mean[rowi] = mu;
+      if (a.rstd) a.rstd[rowi] = rs;
+      if (a.wsum) a.wsum[rowi] = wsum;
+    }
   }
 }
 
@@ -543,11 +571,20 @@ extern "C" int immtsf_recavg_pool_fwd(const float* Vp, int ldv, const float* tau
   const int nc = N_max <= 32 ? rowwarp_nc(d) : 0;
   if (nc > 0 && ((uintptr_t)gamma & 15) == 0 && ((uintptr_t)beta & 15) == 0 && ((uintptr_t)E_drop & 15) == 0 &&
       (E_raw == nullptr || ((uintptr_t)E_raw & 15) == 0)) {
-    dim3 gridw(ceil_div(T, 8), B);
-    if (nc == 1) recavg_pool_fwd_w_kernel<1><<<gridw, 256, 0, st>>>(a);
-    else if (nc == 2) recavg_pool_fwd_w_kernel<2><<<gridw, 256, 0, st>>>(a);
-    else if (nc == 3) recavg_pool_fwd_w_kernel<3><<<gridw, 256, 0, st>>>(a);
-    else recavg_pool_fwd_w_kernel<4><<<gridw, 256, 0, st>>>(a);
+    // query times per warp: 3 when the row fits comfortably in registers (d <= 768) and T is long enough
+    const int tpw = (nc <= 3 && T > 16) ? 3 : (T > 8 && nc <= 3 ? 2 : 1);
+    dim3 gridw(ceil_div(T, 8 * tpw), B);
+#define FWD_W(NCV)                                                                    \
+  do {                                                                                \
+    if (tpw == 3) recavg_pool_fwd_w_kernel<NCV, 3><<<gridw, 256, 0, st>>>(a);         \
+    else if (tpw == 2) recavg_pool_fwd_w_kernel<NCV, 2><<<gridw, 256, 0, st>>>(a);    \
+    else recavg_pool_fwd_w_kernel<NCV, 1><<<gridw, 256, 0, st>>>(a);                  \
+  } while (0)
+    if (nc == 1) FWD_W(1);
+    else if (nc == 2) FWD_W(2);
+    else if (nc == 3) FWD_W(3);
+    else recavg_pool_fwd_w_kernel<4, 1><<<gridw, 256, 0, st>>>(a);
+#undef FWD_W
     IMMTSF_CHECK_LAUNCH("recavg_pool_fwd_w");
     return IMMTSF_OK;
   }

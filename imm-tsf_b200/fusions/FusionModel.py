@@ -58,12 +58,18 @@ class FusionModel(nn.Module):
                 raise ValueError("Y_out contains NaN values.")
             return Y_out
         flags = runtime.new_flags(Y_ts.device)
+        r = ops.csr_build(cm.as_f32(notes_input), cm.as_f32(tau), flags)
+        return self.forward_csr(r, t_hat, Y_ts)
+
+    def forward_csr(self, r, t_hat, Y_ts):
+        """Same as forward() for callers that already hold the ragged layout (immtsf.collate.ragged_collate):
+        no padded tensor, no content-mask pass, no compaction copy."""
+        flags = r.flags
         self._last_flags = flags  # read by runtime.GraphedStep.check_nan()
         check = runtime.nan_flags_enabled()
         Y32 = cm.as_f32(Y_ts)
         if check:
             ops.nan_check(Y32, flags, ops.FLAG_Y)
-        r = ops.csr_build(cm.as_f32(notes_input), cm.as_f32(tau), flags)
         E_txt, M_txt = self.ttf.forward_ragged(r, t_hat)
         if check:
             # the broadcast view of T2V eval mode has B distinct rows: check those only

@@ -251,7 +251,7 @@ class XAttnAddFn(torch.autograd.Function):
         # ---- per-row work
         q = ops.linear_fwd(Y2, Wq_f, in_b[:d])  # :68 + in_proj_q
         kv = ops.linear_fwd(E2, Wkv_f, in_b[d:], lo=lo)  # :69-70 + in_proj_k / in_proj_v, E read once
-        o, probs = ops.xattn_core_fwd(q, kv[:, :d], kv[:, d:], m_txt, B, T, H, d, thr, seed, save)
+        o, probs = ops.xattn_core_fwd(q, kv[:, :d], kv[:, d:], m_txt, B, T, H, d, thr, seed, save, lo=lo)
         delta_y = ops.linear_fwd(o, Wo_f, bo_f)  # out_proj + residual_head (:83)
         Y_out = ops.xattn_tail_fwd(Y2, delta_y, gamma, beta, m_txt, B, T, C, kappa, thr, seed, flags)
         if save:
@@ -276,7 +276,7 @@ class XAttnAddFn(torch.autograd.Function):
         db_r = ops.colsum(d_delta)  # d(bo_f) = d(b_r)
         do = ops.linear_dgrad(d_delta, Wo_f)
         dq, dkv = new(B * T, d), new(B * T, 2 * d)
-        ops.xattn_core_bwd(do, q, kv[:, :d], kv[:, d:], probs, m_txt, B, T, H, d, thr, seed, dq, dkv[:, :d], dkv[:, d:])
+        ops.xattn_core_bwd(do, q, kv[:, :d], kv[:, d:], probs, m_txt, B, T, H, d, thr, seed, dq, dkv[:, :d], dkv[:, d:], lo=lo)
         # ---- folded projections
         d_in_w, d_in_b = torch.empty_like(in_w), new(3 * d)
         dWq_f = ops.linear_wgrad(dq, Y2)  # [d, C]

@@ -358,16 +358,36 @@ def gru_scan_bwd(G4, h_prev, w_hh, b_hh, dh_out, B, T, C, dG4, gates=None):
 XATTN_SMALL_T = 32  # up to here one CTA holds the whole T x T problem of a (sample, head) (csrc/xattn_small.cu)
 
 
+def _flat_lo(lo: "LoCache", t: torch.Tensor, rows: int, cols: int, strides, batch1: int, batch2: int):
+    """lo over the flat extent of a batched operand (same layout as the operand), cached per (pointer, extent)."""
+    ld, s1, s2 = strides
+    extent = (batch1 - 1) * s1 + (batch2 - 1) * s2 + (rows - 1) * ld + cols
+    key = (t.data_ptr(), extent, "flat")
+    e = lo.get(key)
+    if e is None:
+        buf = torch.empty(round_up(extent, 4), dtype=torch.float32, device=t.device)
+        _lib.call("immtsf_split_lo", _p(t), round_up(extent, 4), 1, extent, _p(buf), round_up(extent, 4), None, _stream())
+        e = (t, buf)
+        lo[key] = e
+    return e[1]
+
+
 def gemm_batched(A, B, C, M, N, K, a_strides, b_strides, c_strides, batch1, batch2, transA=False, transB=False,
-                 alpha=1.0, beta=0.0):
+                 alpha=1.0, beta=0.0, lo: Optional["LoCache"] = None):
     """C(b1,b2)[M,N] = alpha*op(A(b1,b2)) op(B(b1,b2)) + beta*C(b1,b2); *_strides = (ld, s1, s2) in elements, A/B/C are
     the base tensors (only their data pointers are used).  tcgen05 3xTF32 (include/immtsf.h)."""
     lib = _lib.load()
     (lda, a1, a2), (ldb, b1, b2), (ldc, c1, c2) = a_strides, b_strides, c_strides
     need = lib.immtsf_gemm_batched_workspace_bytes(int(transA), int(transB), M, N, K, lda, a1, a2, ldb, b1, b2, batch1, batch2)
     ws = _workspace(C.device, need)
-    _lib.call("immtsf_gemm_batched", int(transA), int(transB), M, N, K, float(alpha), _p(A), lda, a1, a2, _p(B), ldb, b1, b2,
-              float(beta), _p(C), ldc, c1, c2, batch1, batch2, _p(ws), ws.numel(), _stream())
+    A_lo = B_lo = None
+    if lo is not None:
+        ra, ca = (K, M) if transA else (M, K)
+        rb, cb = (N, K) if transB else (K, N)
+        A_lo = _flat_lo(lo, A, ra, ca, a_strides, batch1, batch2)
+        B_lo = _flat_lo(lo, B, rb, cb, b_strides, batch1, batch2)
+    _lib.call("immtsf_gemm_batched", int(transA), int(transB), M, N, K, float(alpha), _p(A), _p(A_lo), lda, a1, a2, _p(B),
+              _p(B_lo), ldb, b1, b2, float(beta), _p(C), ldc, c1, c2, batch1, batch2, _p(ws), ws.numel(), _stream())
     return C
 
 
@@ -381,7 +401,7 @@ def B_H_ok(B, H):
     return B * H <= 65535
 
 
-def xattn_core_fwd(q, k, v, m_txt, B, T, H, d, thr, seed, save):
+def xattn_core_fwd(q, k, v, m_txt, B, T, H, d, thr, seed, save, lo=None):
     """MHA core of MMF_XAttn_Add.  T <= 32: one fused kernel per direction.  T > 32: batched tcgen05 products around a
     row-softmax kernel.  Returns (o [B*T, d], saved) where saved is what xattn_core_bwd needs."""
     o = torch.empty(B * T, d, dtype=torch.float32, device=q.device)
@@ -393,9 +413,9 @@ def xattn_core_fwd(q, k, v, m_txt, B, T, H, d, thr, seed, save):
         sP = (Tp, H * T * Tp, T * Tp)
         sq, sk, sv, so = (q.stride(0), T * q.stride(0), hd), (k.stride(0), T * k.stride(0), hd), (v.stride(0), T * v.stride(0), hd), \
             (o.stride(0), T * o.stride(0), hd)
-        gemm_batched(q, k, P, T, T, hd, sq, sk, sP, B, H, transB=True)  # S = Q K^T
+        gemm_batched(q, k, P, T, T, hd, sq, sk, sP, B, H, transB=True, lo=lo)  # S = Q K^T
         _lib.call("immtsf_softmax_rows_fwd", _p(P), _p(Pt), _p(m_txt), B, H, T, Tp, scale, thr, seed, _stream())
-        gemm_batched(Pt, v, o, T, hd, T, sP, sv, so, B, H)  # O = P~ V
+        gemm_batched(Pt, v, o, T, hd, T, sP, sv, so, B, H, lo=lo)  # O = P~ V
         return o, (P if save else None)
     probs = torch.empty(B, H, T, T, dtype=torch.float32, device=q.device) if save else None
     _lib.call("immtsf_xattn_core_fwd", _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(m_txt), B, T, H, d,
@@ -403,7 +423,7 @@ def xattn_core_fwd(q, k, v, m_txt, B, T, H, d, thr, seed, save):
     return o, probs
 
 
-def xattn_core_bwd(d_o, q, k, v, probs, m_txt, B, T, H, d, thr, seed, dq, dk, dv):
+def xattn_core_bwd(d_o, q, k, v, probs, m_txt, B, T, H, d, thr, seed, dq, dk, dv, lo=None):
     if _xattn_large_ok(q, k, v, T, H, d) and probs.shape[-1] == round_up(T, 4) and d_o.stride(0) % 4 == 0:
         hd, Tp = d // H, round_up(T, 4)
         scale = math.sqrt(1.0 / float(hd))
@@ -411,11 +431,12 @@ def xattn_core_bwd(d_o, q, k, v, probs, m_txt, B, T, H, d, thr, seed, dq, dk, dv
         Pt = torch.empty(B, H, T, Tp, dtype=torch.float32, device=q.device)
         sP = (Tp, H * T * Tp, T * Tp)
         st = lambda t: (t.stride(0), T * t.stride(0), hd)
-        gemm_batched(d_o, v, dS, T, T, hd, st(d_o), st(v), sP, B, H, transB=True)  # dP~ = dO V^T
+        gemm_batched(d_o, v, dS, T, T, hd, st(d_o), st(v), sP, B, H, transB=True, lo=lo)  # dP~ = dO V^T
         _lib.call("immtsf_softmax_rows_bwd", _p(dS), _p(probs), _p(Pt), _p(m_txt), B, H, T, Tp, scale, thr, seed, _stream())
-        gemm_batched(dS, k, dq, T, hd, T, sP, st(k), st(dq), B, H)  # dQ = dS K
-        gemm_batched(dS, q, dk, T, hd, T, sP, st(q), st(dk), B, H, transA=True)  # dK = dS^T Q
-        gemm_batched(Pt, d_o, dv, T, hd, T, sP, st(d_o), st(dv), B, H, transA=True)  # dV = P~^T dO
+        # dS was rewritten in place by the softmax kernel after its use as an output: its lo is made now and shared
+        gemm_batched(dS, k, dq, T, hd, T, sP, st(k), st(dq), B, H, lo=lo)  # dQ = dS K
+        gemm_batched(dS, q, dk, T, hd, T, sP, st(q), st(dk), B, H, transA=True, lo=lo)  # dK = dS^T Q
+        gemm_batched(Pt, d_o, dv, T, hd, T, sP, st(d_o), st(dv), B, H, transA=True, lo=lo)  # dV = P~^T dO
         return
     _lib.call("immtsf_xattn_core_bwd", _p(d_o), d_o.stride(0), _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0),
               _p(probs), _p(m_txt), B, T, H, d, thr, seed, _p(dq), dq.stride(0), _p(dk), dk.stride(0), _p(dv), dv.stride(0),

@@ -209,11 +209,13 @@ int immtsf_xattn_core_bwd(const float* d_o, int lddo, const float* q, int ldq, c
  *   S = Q K^T (immtsf_gemm_batched) -> immtsf_softmax_rows_fwd -> O = P~ V (immtsf_gemm_batched), and in backward
  *   dP~ = dO V^T -> immtsf_softmax_rows_bwd -> dQ = dS K, dK = dS^T Q, dV = P~^T dO.
  * Batched product: C(b1,b2)[M,N] = alpha * op(A(b1,b2)) op(B(b1,b2)) + beta * C(b1,b2) with X(b1,b2) = X + b1*x_s1 +
- * b2*x_s2 (element strides, multiples of 4).  3xTF32 like immtsf_gemm; tiles that overhang a batch are zero-filled. */
-int immtsf_gemm_batched(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda, long a_s1,
-                        long a_s2, const float* B, int ldb, long b_s1, long b_s2, float beta, float* C, int ldc,
-                        long c_s1, long c_s2, int batch1, int batch2, void* workspace, size_t workspace_bytes,
-                        void* stream);
+ * b2*x_s2 (element strides, multiples of 4).  3xTF32 like immtsf_gemm; tiles that overhang a batch are zero-filled.
+ * A_lo / B_lo (nullable): lo = x - trunc_tf32(x) over the operand's flat extent, same layout as the operand
+ * (immtsf_split_lo with rows = 1), for operands used by several products. */
+int immtsf_gemm_batched(int transA, int transB, int M, int N, int K, float alpha, const float* A, const float* A_lo,
+                        int lda, long a_s1, long a_s2, const float* B, const float* B_lo, int ldb, long b_s1,
+                        long b_s2, float beta, float* C, int ldc, long c_s1, long c_s2, int batch1, int batch2,
+                        void* workspace, size_t workspace_bytes, void* stream);
 size_t immtsf_gemm_batched_workspace_bytes(int transA, int transB, int M, int N, int K, int lda, long a_s1, long a_s2,
                                            int ldb, long b_s1, long b_s2, int batch1, int batch2);
 /* S, Pt, dS: [B, H, T, Tp] score buffers (Tp >= T, a multiple of 4).  fwd: S <- P = softmax(scale*S) in place,

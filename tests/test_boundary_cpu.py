@@ -75,7 +75,7 @@ def test_arg_validation_without_a_gpu():
     lib = _lib.load()
     rc = lib.immtsf_gemm(0, 1, 4, 4, 4, 1.0, None, 4, None, 4, 0.0, None, 4, None, None, 0, 0, None, 0, None)
     assert rc == -1 and b"null operand" in lib.immtsf_last_error_string()
-    rc = lib.immtsf_recavg_pool_fwd(1, 6, 1, 1, 1, 0, 1, 1, 1, 2, 2, 6, 1e-5, 0, 0, 1, None, None, None, None, None)
+    rc = lib.immtsf_recavg_pool_fwd(1, 6, 1, 1, 1, 0, 1, 1, 1, 2, 2, 6, 4, 1e-5, 0, 0, 1, None, None, None, None, None)
     assert rc == -1 and b"multiple of 4" in lib.immtsf_last_error_string()
 
 
