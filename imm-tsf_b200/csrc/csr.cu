@@ -88,51 +88,57 @@ __global__ void csr_scan_kernel(const uint8_t* __restrict__ note_mask, const flo
     if (threadIdx.x == blockDim.x - 1) s_carry = carry + warp_excl + incl;
     __syncthreads();
   }
-  // phase 2: one warp per sample fills rows / seg / tau_flat in note order
-  for (int b = w; b < B; b += nw) {
-    int pos = offsets[b];
-    const uint8_t* mrow = note_mask + (size_t)b * N;
-    for (int n0 = 0; n0 < N; n0 += 32) {
-      const int n = n0 + lane;
-      const bool v = n < N && mrow[n];
-      const unsigned bal = __ballot_sync(0xffffffffu, v);
-      if (v) {
-        const int p = pos + __popc(bal & ((1u << lane) - 1u));
-        rows[p] = b * N + n;
-        seg[p] = b;
-        tau_flat[p] = tau[(size_t)b * N + n];
-      }
-      pos += __popc(bal);
-    }
-  }
+  // rows / seg / tau_flat / emb_flat are filled by csr_gather_kernel (whole grid); here only the pad of tau_flat
   __syncthreads();
-  // zero the pad of tau_flat
   const int total = s_carry;
   int end = (total + 127) / 128 * 128;
   if (end > M_alloc) end = M_alloc;
   for (int i = total + threadIdx.x; i < end; i += blockDim.x) tau_flat[i] = 0.f;
 }
 
-// one CTA per destination row: copy the valid note row, or zero a pad row
-__global__ void csr_gather_kernel(const float* __restrict__ notes, const int32_t* __restrict__ rows,
-                                  const int32_t* __restrict__ offsets, int B, int d_m, float* __restrict__ emb_flat,
-                                  int M_alloc) {
+// Source-driven compaction, one warp per padded row (b, n): a valid row finds its destination
+// p = offsets[b] + #valid rows before it in its sample (ballot/popcount over the sample's mask bytes), copies its
+// embedding with 128-bit accesses and writes rows[p], seg[p], tau_flat[p].  Warps beyond B*N zero the pad rows
+// [sumN, roundup(sumN, 128)) of emb_flat.
+__global__ void __launch_bounds__(256) csr_gather_kernel(const float* __restrict__ notes, const float* __restrict__ tau,
+                                                         const uint8_t* __restrict__ note_mask,
+                                                         const int32_t* __restrict__ offsets, int B, int N, int d_m,
+                                                         int32_t* __restrict__ rows, int32_t* __restrict__ seg,
+                                                         float* __restrict__ tau_flat, float* __restrict__ emb_flat,
+                                                         int M_alloc) {
+  const int lane = threadIdx.x & 31;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  const int total_src = B * N;
   const int total = offsets[B];
   int end = (total + 127) / 128 * 128;
   if (end > M_alloc) end = M_alloc;
-  for (int r = blockIdx.x; r < end; r += gridDim.x) {
-    float* dst = emb_flat + (size_t)r * d_m;
-    if (r < total) {
-      const float* src = notes + (size_t)rows[r] * d_m;
-      if ((d_m & 3) == 0 && ((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0) {
-        const float4* s4 = reinterpret_cast<const float4*>(src);
-        float4* d4 = reinterpret_cast<float4*>(dst);
-        for (int i = threadIdx.x; i < (d_m >> 2); i += blockDim.x) d4[i] = __ldg(s4 + i);
-      } else {
-        for (int i = threadIdx.x; i < d_m; i += blockDim.x) dst[i] = __ldg(src + i);
+  const int npad = end - total;
+  for (int i = gw; i < total_src + npad; i += nw) {
+    float* dst;
+    const float* src = nullptr;
+    if (i < total_src) {
+      if (!note_mask[i]) continue;
+      const int b = i / N, n = i - b * N;
+      const uint8_t* mrow = note_mask + (size_t)b * N;
+      int before = 0;
+      for (int n0 = 0; n0 < n; n0 += 32) {
+        const bool v = n0 + lane < n && mrow[n0 + lane];
+        before += __popc(__ballot_sync(0xffffffffu, v));
       }
+      const int p = offsets[b] + before;
+      if (lane == 0) { rows[p] = i; seg[p] = b; tau_flat[p] = tau[i]; }
+      dst = emb_flat + (size_t)p * d_m;
+      src = notes + (size_t)i * d_m;
     } else {
-      for (int i = threadIdx.x; i < d_m; i += blockDim.x) dst[i] = 0.f;
+      dst = emb_flat + (size_t)(total + (i - total_src)) * d_m;
+    }
+    if (emb_flat == nullptr) continue;
+    if ((d_m & 3) == 0 && ((uintptr_t)dst & 15) == 0 && (src == nullptr || ((uintptr_t)src & 15) == 0)) {
+      float4* d4 = reinterpret_cast<float4*>(dst);
+      const float4* s4 = reinterpret_cast<const float4*>(src);
+      for (int k = lane; k < (d_m >> 2); k += 32) d4[k] = src ? __ldg(s4 + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+      for (int k = lane; k < d_m; k += 32) dst[k] = src ? __ldg(src + k) : 0.f;
     }
   }
 }
@@ -154,10 +160,11 @@ extern "C" int immtsf_csr_build(const float* notes, const float* tau, int B, int
   }
   csr_scan_kernel<<<1, 1024, 0, st>>>(note_mask, tau, B, N, offsets, rows, seg, tau_flat, m_txt, M_alloc);
   IMMTSF_CHECK_LAUNCH("csr_scan");
-  if (emb_flat && total_rows > 0 && d_m > 0) {
-    int grid = total_rows < 148 * 16 ? total_rows : 148 * 16;
-    const int threads = d_m >= 1024 ? 256 : 128;
-    csr_gather_kernel<<<grid, threads, 0, st>>>(notes, rows, offsets, B, d_m, emb_flat, M_alloc);
+  if (total_rows > 0) {
+    int grid = ceil_div(total_rows + 128, 8);
+    if (grid > 148 * 16) grid = 148 * 16;
+    csr_gather_kernel<<<grid, 256, 0, st>>>(notes, tau, note_mask, offsets, B, N, d_m, rows, seg, tau_flat,
+                                            d_m > 0 ? emb_flat : nullptr, M_alloc);
     IMMTSF_CHECK_LAUNCH("csr_gather");
   }
   return IMMTSF_OK;

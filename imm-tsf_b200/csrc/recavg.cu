@@ -299,10 +299,11 @@ __global__ void __launch_bounds__(256, NCH == 1 ? 2 : 1) recavg_bwd_notes_kernel
     const int tcnt = min(POOL_TB, a.T - t0);
     if (threadIdx.x < NT)
       for (int tt = 0; tt < tcnt; ++tt) sc_term = fmaf(s_c[tt][threadIdx.x], s_dw[tt], sc_term);
-    for (int tq = 0; tq < tcnt; tq += 4) {
-      float4 g[4][NCH];
+    constexpr int PF = NCH == 1 ? 8 : 4;  // dS rows in flight per thread: the loop is bound by L2 latency otherwise
+    for (int tq = 0; tq < tcnt; tq += PF) {
+      float4 g[PF][NCH];
 #pragma unroll
-      for (int v = 0; v < 4; ++v)
+      for (int v = 0; v < PF; ++v)
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
           const int col4 = threadIdx.x + c * blockDim.x;
@@ -311,7 +312,7 @@ __global__ void __launch_bounds__(256, NCH == 1 ? 2 : 1) recavg_bwd_notes_kernel
         }
       if (NT == 8 && ncnt <= 4) {  // half-empty tile (CTA-uniform): skip the empty note slots
 #pragma unroll
-        for (int v = 0; v < 4; ++v) {
+        for (int v = 0; v < PF; ++v) {
           if (tq + v < tcnt) {
 #pragma unroll
             for (int u = 0; u < NT / 2; ++u) {
@@ -323,7 +324,7 @@ __global__ void __launch_bounds__(256, NCH == 1 ? 2 : 1) recavg_bwd_notes_kernel
         }
       } else {
 #pragma unroll
-        for (int v = 0; v < 4; ++v) {
+        for (int v = 0; v < PF; ++v) {
           if (tq + v < tcnt) {
 #pragma unroll
             for (int u = 0; u < NT; ++u) {
