@@ -60,11 +60,11 @@ WORKLOADS = {
                   name="cfg5g: T2V_XAttn+GR_Add, B256 N<=32 T192 d768 C96 (MIMIC-shaped, GRU fusion)"),
 }
 DROPOUT = 0.1
-# dram__bytes_read.sum + dram__bytes_write.sum of one gemm_tc_kernel launch (M6144 N768 K768) from the ncu --set full
-# capture in profiles/r1_ncu_gemm_tc_full_summary.csv; algorithmic operand bytes of that launch: 42.5 MB (the
-# 18.9 MB output stays in the 126 MB L2)
-TRAFFIC_NCU = 43.4e6
-TRAFFIC_NOTE = "bytes per launch, M6144 N768 K768, profiles/r1_ncu_gemm_tc_full_summary.csv (algorithmic operand bytes 42.5e6)"
+# dram__bytes_read.sum + dram__bytes_write.sum of one gemm_tc_kernel<.,.,256> launch (M6144 N768 K768) from the
+# ncu --set full capture in profiles/r1_ncu_gemm_tc_bn256_summary.txt; algorithmic operand bytes of that launch:
+# 42.5 MB (A, A_lo, B, B_lo; the 18.9 MB output stays in the 126 MB L2)
+TRAFFIC_NCU = 42.9e6
+TRAFFIC_NOTE = "bytes per launch, M6144 N768 K768, profiles/r1_ncu_gemm_tc_bn256_summary.txt (algorithmic operand bytes 42.5e6)"
 METRIC = "fused TTF+MMF fwd+bwd throughput"
 UNIT = "samples/s"
 
