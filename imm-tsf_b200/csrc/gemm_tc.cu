@@ -102,6 +102,9 @@ __device__ __forceinline__ void tma_tile(uint32_t dst, const CUtensorMap* map, u
   if (batched) tma_load_4d(dst, map, bar, c0, c1, b2, b1);
   else tma_load_2d(dst, map, bar, c0, c1);
 }
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -156,7 +159,75 @@ struct TcArgs {
   // C(b1, b2) = C + b1 * c_s1 + b2 * c_s2; no split-K, no ragged bounds
   int batched, batch2;
   long c_s1, c_s2;
+  // diagnostics (immtsf_gemm_trace): per-CTA clock64 stamps of the pair kernel's phases, 8 slots per CTA
+  long long* trace;
 };
+#define TC_STAMP(slot)                                                                                             \
+  do {                                                                                                             \
+    if (g.trace != nullptr)                                                                                        \
+      g.trace[((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 + (slot)] = clock64(); \
+  } while (0)
+
+
+// Epilogue write-out.  After tcgen05.ld a thread owns one output ROW (128 consecutive columns of it), so direct stores
+// would touch 32 different 128 B lines per instruction (measured: 16 k cycles to store a 128 x 256 tile, a quarter of
+// the CTA's lifetime at K = 768).  Each epilogue warp therefore stages its 32 rows x 128 columns in shared memory
+// (the operand ring is idle once the last accumulator chunk is complete; row stride 132 floats keeps both the
+// row-per-lane writes and the row-per-instruction reads conflict-free) and then writes whole 512 B row segments.
+constexpr int EPI_LD = 132;
+constexpr int EPI_WARP_BYTES = 32 * EPI_LD * 4;  // 16.5 KiB per epilogue warp
+
+// rows [row0, row0+32) x columns [ncol0, ncol0+128) of this warp; `out` points at (row0, ncol0) of C or of the
+// split-K partial tile.  partial: raw sums, rows < Mfull, columns < ncols (ld of the partial).  Otherwise
+// alpha / bias / beta, zeros for ragged pad rows (row >= Mlive), columns < ncols.
+__device__ __forceinline__ void epilogue_store(const float (&acc)[128], uint32_t stage, int lane, float* out, size_t ld,
+                                               int row0, int ncol0, int Mfull, int Mlive, int ncols, bool partial, float alpha,
+                                               float beta, const float* __restrict__ bias) {
+  const uint32_t mine = stage + (uint32_t)(lane * EPI_LD * 4);
+#pragma unroll
+  for (int j4 = 0; j4 < 32; ++j4)
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(mine + j4 * 16), "f"(acc[j4 * 4]), "f"(acc[j4 * 4 + 1]),
+                 "f"(acc[j4 * 4 + 2]), "f"(acc[j4 * 4 + 3]) : "memory");
+  __syncwarp();
+  const int n = ncol0 + lane * 4;
+  if (n >= ncols) return;
+  float b[4] = {0.f, 0.f, 0.f, 0.f};
+  if (!partial && bias != nullptr) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      if (n + e < ncols) b[e] = __ldg(bias + n + e);
+  }
+  const bool full4 = n + 3 < ncols;
+  const int nrows = min(32, Mfull - row0);
+  for (int rr = 0; rr < nrows; ++rr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "r"(stage + (uint32_t)((rr * EPI_LD + lane * 4) * 4)));
+    float* p = out + (size_t)rr * ld + lane * 4;
+    if (!partial) {
+      const bool live = row0 + rr < Mlive;
+      v.x = live ? fmaf(alpha, v.x, b[0]) : 0.f; v.y = live ? fmaf(alpha, v.y, b[1]) : 0.f;
+      v.z = live ? fmaf(alpha, v.z, b[2]) : 0.f; v.w = live ? fmaf(alpha, v.w, b[3]) : 0.f;
+      if (beta != 0.f && live) {
+        if (full4) {
+          const float4 cc = *reinterpret_cast<const float4*>(p);
+          v.x = fmaf(beta, cc.x, v.x); v.y = fmaf(beta, cc.y, v.y); v.z = fmaf(beta, cc.z, v.z); v.w = fmaf(beta, cc.w, v.w);
+        } else {
+          v.x = fmaf(beta, p[0], v.x);
+          if (n + 1 < ncols) v.y = fmaf(beta, p[1], v.y);
+          if (n + 2 < ncols) v.z = fmaf(beta, p[2], v.z);
+        }
+      }
+    }
+    if (full4) {
+      *reinterpret_cast<float4*>(p) = v;
+    } else {
+      p[0] = v.x;
+      if (n + 1 < ncols) p[1] = v.y;
+      if (n + 2 < ncols) p[2] = v.z;
+    }
+  }
+}
 
 template <bool A_MN, bool B_MN, int BN>
 __global__ void __launch_bounds__(Cfg<BN>::THREADS, 1)
@@ -185,6 +256,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
   const int nchunks = (z_kb1 - z_kb0 + KC - 1) / KC;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+  if (warp == 0 && lane == 0) {  // hide the descriptor fetch behind the barrier / TMEM set-up
+    prefetch_tmap(&mapAh); prefetch_tmap(&mapAl); prefetch_tmap(&mapBh); prefetch_tmap(&mapBl);
+  }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(bar_full + 8 * s, 1);
@@ -307,57 +381,253 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
     }
-    const int row = m0 + q * 32 + lane;
-    const bool live = row < M;
+    // the operand ring is idle now (every load was consumed by an MMA that has completed): stage + coalesced stores
+    const uint32_t stage = base + (uint32_t)((warp - 4) * EPI_WARP_BYTES);
+    const int row0 = m0 + q * 32;
     if (nsplit > 1) {
       // split-K: this split's partial tile goes to the workspace [z][M][ldp]; splitk_reduce_kernel sums the
       // splits in a fixed order (deterministic, unlike atomics) and applies alpha / beta / bias
-      if (row < g.M) {
-        float* prow = g.partial + ((size_t)zsplit * g.M + row) * g.ldp + n0 + ch;
-#pragma unroll
-        for (int j4 = 0; j4 < 128 / 4; ++j4)
-          if (n0 + ch + j4 * 4 < g.ldp)
-            *reinterpret_cast<float4*>(prow + j4 * 4) = make_float4(acc[j4 * 4], acc[j4 * 4 + 1], acc[j4 * 4 + 2], acc[j4 * 4 + 3]);
-      }
-    } else if (row < g.M) {
-      float* crow = g.C + bz1 * g.c_s1 + bz2 * g.c_s2 + (size_t)row * g.ldc + n0 + ch;
-#pragma unroll
-      for (int j4 = 0; j4 < 128 / 4; ++j4) {
-        const int n = n0 + ch + j4 * 4;
-        if (n < g.N) {
-          float o[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float x = g.alpha * acc[j4 * 4 + e];
-            if (g.bias != nullptr && n + e < g.N) x += __ldg(g.bias + n + e);
-            o[e] = live ? x : 0.f;
-          }
-          if (n + 3 < g.N) {
-            float4 ov = make_float4(o[0], o[1], o[2], o[3]);
-            if (g.beta != 0.f && live) {
-              const float4 cc = *reinterpret_cast<const float4*>(crow + j4 * 4);
-              ov.x = fmaf(g.beta, cc.x, ov.x); ov.y = fmaf(g.beta, cc.y, ov.y);
-              ov.z = fmaf(g.beta, cc.z, ov.z); ov.w = fmaf(g.beta, cc.w, ov.w);
-            }
-            *reinterpret_cast<float4*>(crow + j4 * 4) = ov;
-          } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              if (n + e < g.N) {
-                float x = o[e];
-                if (g.beta != 0.f && live) x = fmaf(g.beta, crow[j4 * 4 + e], x);
-                crow[j4 * 4 + e] = x;
-              }
-            }
-          }
-        }
-      }
+      epilogue_store(acc, stage, lane, g.partial + ((size_t)zsplit * g.M + row0) * g.ldp + n0 + ch, (size_t)g.ldp, row0, n0 + ch,
+                     g.M, g.M, g.ldp, true, 1.f, 0.f, nullptr);
+    } else {
+      epilogue_store(acc, stage, lane, g.C + bz1 * g.c_s1 + bz2 * g.c_s2 + (size_t)row0 * g.ldc + n0 + ch, (size_t)g.ldc, row0,
+                     n0 + ch, g.M, M, g.N, false, g.alpha, g.beta, g.bias);
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 2) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS));
+  }
+}
+
+// ---------------------------------------------------------------- CTA-pair variant (cta_group::2)
+// Two CTAs of a cluster (one TPC) compute one 256 x 256 output tile: each CTA stages ITS 128 rows of A and ITS 128
+// columns of B (64 KiB per k-block instead of 96 KiB for the same 128 x 256 per-CTA output -> 3 stages fit), the
+// leader CTA (cluster rank 0) issues tcgen05.mma.cta_group::2 with M = 256, N = 256, and the tensor cores of both SMs
+// read both B halves.  Each CTA's TMEM holds its own 128 rows x 256 columns, so the epilogue is the 128 x 256 one.
+//   full[s]   lives in the leader; both producers' TMA loads complete_tx on it (expect_tx = 2 x 64 KiB)
+//   empty[s]  one per CTA, arrived by the leader's tcgen05.commit multicast to both CTAs
+//   tfull[b]  one per CTA (multicast commit), tempty[b] in the leader, 16 arrivals (8 epilogue warps x 2 CTAs)
+struct Cfg2 {
+  static constexpr int BN = 256, BNH = 128;
+  static constexpr int STAGES = 3;
+  static constexpr int TILE_B = BNH * BKT * 4;
+  static constexpr int STAGE_BYTES = 2 * TILE_A + 2 * TILE_B;  // 64 KiB per CTA
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int EPI_WARPS = 8;
+  static constexpr int THREADS = 128 + 32 * EPI_WARPS;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// shared::cluster address of the same smem offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load of a CTA pair: data into the executing CTA's smem, completion bytes onto `bar` (a shared::cluster address,
+// here always the leader's full barrier)
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+
+template <bool A_MN, bool B_MN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg2::THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
+                const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl, const TcArgs g) {
+  using C_ = Cfg2;
+  constexpr int STAGES = C_::STAGES, STAGE_BYTES = C_::STAGE_BYTES, TILE_B = C_::TILE_B, BN = C_::BN, BNH = C_::BNH;
+  extern __shared__ uint8_t smem_raw[];
+  if (threadIdx.x == 0) {
+    TC_STAMP(0);
+    if (g.trace != nullptr) {
+      long long gt;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+      g.trace[((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 + 7] = gt;
+    }
+  }
+  int M = g.M, K = g.K;
+  if (g.ragged_dim == 1) M = ragged_rows(M, g.ragged);
+  if (g.ragged_dim == 2) K = ragged_rows(K, g.ragged);
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int m_pair = (int)(blockIdx.x >> 1) * (2 * BM);
+  const int m0 = m_pair + (int)rank * BM, n0 = blockIdx.y * BN;
+  if (g.ragged_dim == 1 && m_pair >= M) return;  // whole pair tile beyond the ragged end (uniform per cluster)
+  const int nkb = (K + BKT - 1) / BKT;
+
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = base + STAGES * STAGE_BYTES;
+  const uint32_t bar_full = bars, bar_empty = bars + 8 * STAGES, bar_tfull = bars + 16 * STAGES;
+  const uint32_t bar_tempty = bar_tfull + 16, tmem_slot = bar_tempty + 16;
+  const int nsplit = (int)gridDim.z, zsplit = (int)blockIdx.z;
+  const int kb_per = (nkb + nsplit - 1) / nsplit;
+  const int z_kb0 = min(nkb, zsplit * kb_per), z_kb1 = min(nkb, z_kb0 + kb_per);
+  const int nchunks = (z_kb1 - z_kb0 + KC - 1) / KC;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {  // hide the descriptor fetch behind the barrier / TMEM set-up
+    prefetch_tmap(&mapAh); prefetch_tmap(&mapAl); prefetch_tmap(&mapBh); prefetch_tmap(&mapBl);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_tfull + 8 * b, 1);
+      mbar_init(bar_tempty + 8 * b, 2 * C_::EPI_WARPS);  // epilogue warps of both CTAs
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  cluster_sync_all();  // barrier inits and the TMEM allocation of BOTH CTAs are visible before any remote arrive / MMA
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  if (threadIdx.x == 0) TC_STAMP(1);
+
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+  if (warp == 0 && lane == 0) {
+    // ===== TMA producer (both CTAs; completion on the leader's full barrier) =====
+    const uint32_t nb0 = n0 + (int)rank * BNH;
+    for (int kb = z_kb0; kb < z_kb1; ++kb) {
+      const int it = kb - z_kb0;
+      const int s = it % STAGES, ph = (it / STAGES) & 1;
+      mbar_wait(bar_empty + 8 * s, ph ^ 1);
+      const uint32_t sa_h = base + s * STAGE_BYTES, sa_l = sa_h + TILE_A, sb_h = sa_l + TILE_A, sb_l = sb_h + TILE_B;
+      if (leader) mbar_expect_tx(bar_full + 8 * s, 2 * STAGE_BYTES);
+      const uint32_t fb = mapa_shared(bar_full + 8 * s, 0);
+      const int k0 = kb * BKT;
+      if (!A_MN) {
+        tma_load_2d_pair(sa_h, &mapAh, fb, k0, m0);
+        tma_load_2d_pair(sa_l, &mapAl, fb, k0, m0);
+      } else {
+#pragma unroll
+        for (int j = 0; j < BM / 32; ++j) {
+          tma_load_2d_pair(sa_h + j * 4096, &mapAh, fb, m0 + 32 * j, k0);
+          tma_load_2d_pair(sa_l + j * 4096, &mapAl, fb, m0 + 32 * j, k0);
+        }
+      }
+      if (!B_MN) {
+        tma_load_2d_pair(sb_h, &mapBh, fb, k0, nb0);
+        tma_load_2d_pair(sb_l, &mapBl, fb, k0, nb0);
+      } else {
+#pragma unroll
+        for (int j = 0; j < BNH / 32; ++j) {
+          tma_load_2d_pair(sb_h + j * 4096, &mapBh, fb, nb0 + 32 * j, k0);
+          tma_load_2d_pair(sb_l + j * 4096, &mapBl, fb, nb0 + 32 * j, k0);
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0 && leader) {
+    // ===== MMA issuer (leader CTA only) =====
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                           ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+    for (int c = 0; c < nchunks; ++c) {
+      const int buf = c & 1;
+      mbar_wait(bar_tempty + 8 * buf, ((c >> 1) & 1) ^ 1);  // both CTAs' epilogues have drained this TMEM buffer
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tacc = tmem_base + (uint32_t)(buf * BN);
+      const int kb0 = z_kb0 + c * KC;
+      const int kb_end = min(z_kb1, kb0 + KC);
+      for (int kb = kb0; kb < kb_end; ++kb) {
+        const int it = kb - z_kb0;
+        const int s = it % STAGES, ph = (it / STAGES) & 1;
+        mbar_wait(bar_full + 8 * s, ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (kb == z_kb0) TC_STAMP(2);
+        const uint32_t sa_h = base + s * STAGE_BYTES, sa_l = sa_h + TILE_A, sb_h = sa_l + TILE_A, sb_l = sb_h + TILE_B;
+#pragma unroll
+        for (int prod = 0; prod < 3; ++prod) {
+          const uint32_t sa = prod == 0 ? sa_l : sa_h;  // lo*hi, hi*lo, hi*hi
+          const uint32_t sb = prod == 1 ? sb_l : sb_h;
+#pragma unroll
+          for (int ks = 0; ks < BKT / 8; ++ks) {
+            const uint64_t ad = make_desc(sa + (A_MN ? ks * 1024 : ks * 32), A_MN);
+            const uint64_t bd = make_desc(sb + (B_MN ? ks * 1024 : ks * 32), B_MN);
+            const bool first = (kb == kb0) && ks == 0 && prod == 0;
+            umma_tf32_pair(tacc, ad, bd, idesc, first ? 0u : 1u);
+          }
+        }
+        umma_commit_pair(bar_empty + 8 * s);  // frees this stage in BOTH CTAs
+      }
+      umma_commit_pair(bar_tfull + 8 * buf);
+    }
+    TC_STAMP(3);
+  }
+  } else {
+    // ===== epilogue (both CTAs; each drains its own 128 rows) =====
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    const int q = warp & 3;
+    const int ch = ((warp - 4) >> 2) * 128;
+    const uint32_t tempty_leader = mapa_shared(bar_tempty, 0);
+    float acc[128];
+#pragma unroll
+    for (int j = 0; j < 128; ++j) acc[j] = 0.f;
+    for (int c = 0; c < nchunks; ++c) {
+      const int buf = c & 1;
+      mbar_wait(bar_tfull + 8 * buf, (c >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (c == nchunks - 1 && threadIdx.x == 128) TC_STAMP(4);
+#pragma unroll
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + ch + c0), v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(v[j]);
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tempty_leader + 8 * buf);
+    }
+    const uint32_t stage = base + (uint32_t)((warp - 4) * EPI_WARP_BYTES);
+    const int row0 = m0 + q * 32;
+    if (nsplit > 1) {
+      epilogue_store(acc, stage, lane, g.partial + ((size_t)zsplit * g.M + row0) * g.ldp + n0 + ch, (size_t)g.ldp, row0, n0 + ch,
+                     g.M, g.M, g.ldp, true, 1.f, 0.f, nullptr);
+    } else {
+      epilogue_store(acc, stage, lane, g.C + (size_t)row0 * g.ldc + n0 + ch, (size_t)g.ldc, row0, n0 + ch, g.M, M, g.N, false,
+                     g.alpha, g.beta, g.bias);
+    }
+  }
+  if (threadIdx.x == 128) TC_STAMP(5);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  cluster_sync_all();  // the peer may still be reading this CTA's smem / arriving on its barriers until here
+  if (threadIdx.x == 0) TC_STAMP(6);
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS));
   }
 }
 
@@ -476,12 +746,22 @@ int make_map4(CUtensorMap* m, const float* ptr, int rows, int cols, long ld, lon
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// Kernel variants: 0 = 128x128 tiles, 1 = 128x256 tiles, 2 = CTA pairs (256x256 per cluster of two).
+constexpr int V128 = 0, V256 = 1, VPAIR = 2;
+inline int variant_bn(int v) { return v == V128 ? 128 : 256; }
+// CTAs that cover the output once
+inline long tile_ctas(int M, int N, int v) {
+  if (v == VPAIR) return (long)ceil_div(N, 256) * 2 * ceil_div(M, 2 * BM);
+  return (long)ceil_div(N, variant_bn(v)) * ceil_div(M, BM);
+}
+
 // split-K when the output has too few tiles to occupy the 148 SMs (weight gradients: M, N = d; K = rows)
-inline int choose_splitk(int M, int N, int K, int bn) {
-  const int tiles = ceil_div(N, bn) * ceil_div(M, BM), nkb = ceil_div(K, BKT);
+inline int choose_splitk(int M, int N, int K, int v) {
+  const long tiles = tile_ctas(M, N, v);
+  const int nkb = ceil_div(K, BKT);
   int splitk = 1;
   if (tiles * 2 <= 148 && nkb >= 16) {
-    splitk = 148 / tiles;
+    splitk = (int)(148 / tiles);
     if (splitk > nkb / 8) splitk = nkb / 8;
     if (splitk > 16) splitk = 16;
     if (splitk < 1) splitk = 1;
@@ -489,37 +769,50 @@ inline int choose_splitk(int M, int N, int K, int bn) {
   return splitk;
 }
 
-// Tile width: estimated time = waves x k-blocks per CTA x bytes per k-block (the kernel is operand-bandwidth bound).
-// IMMTSF_TC_BN=128|256 forces one variant (tests, experiments).
-inline int choose_bn(int M, int N, int K) {
+// Variant: estimated time = waves x k-blocks per CTA x operand bytes per k-block per CTA (the kernel is bound by
+// L2->SM operand bandwidth): 64 KiB for a 128x128 tile, 96 KiB for 128x256, 64 KiB for the 128x256 half of a pair.
+// IMMTSF_TC_BN=128|256|512 forces one variant (512 = pairs; tests, experiments).
+inline int choose_variant(int M, int N, int K) {
   static int forced = -1;
   if (forced < 0) {
     const char* e = getenv("IMMTSF_TC_BN");
     forced = e ? atoi(e) : 0;
   }
-  if (forced == 128 || forced == 256) return forced;
-  if (N <= 128) return 128;
-  double cost[2];
-  const int bns[2] = {128, 256};
-  for (int i = 0; i < 2; ++i) {
-    const int bn = bns[i], sk = choose_splitk(M, N, K, bn);
-    const long ctas = (long)ceil_div(N, bn) * ceil_div(M, BM) * sk;
+  if (forced == 128) return V128;
+  if (forced == 256) return V256;
+  if (forced == 512) return VPAIR;
+  if (N <= 128) return V128;
+  double best = 0.0;
+  int best_v = V128;
+  for (int v = 0; v < 3; ++v) {
+    if (v == VPAIR && M <= BM) continue;
+    const int sk = choose_splitk(M, N, K, v);
+    const long ctas = tile_ctas(M, N, v) * sk;
     const double waves = (double)((ctas + 147) / 148);
     // + fixed prologue/epilogue cost per tile, + the partial-tile round trip and reduce launch of split-K
-    const double kb = (double)ceil_div(ceil_div(K, BKT), sk) + 6.0 + (sk > 1 ? 8.0 : 0.0);
-    cost[i] = waves * kb * (bn == 128 ? 64.0 : 96.0);
+    const double kb = (double)ceil_div(ceil_div(K, BKT), sk) + (v == VPAIR ? 7.0 : 6.0) + (sk > 1 ? 8.0 : 0.0);
+    const double cost = waves * kb * (v == V256 ? 96.0 : 64.0);
+    if (v == 0 || cost < best) { best = cost; best_v = v; }
   }
-  return cost[1] < cost[0] ? 256 : 128;
+  return best_v;
 }
 
 }  // namespace
 
 // ---------------------------------------------------------------- per-launch timing (bench.py's roofline)
 namespace {
+long long* g_trace = nullptr;
 struct ProfRec { cudaEvent_t e0, e1; int M, N, K, ragged_dim; };
 ProfRec* g_prof = nullptr;
 int g_prof_cap = 0, g_prof_n = 0, g_prof_on = 0;
 }  // namespace
+
+// Diagnostics: when set, every CTA of the CTA-pair kernel writes 8 clock64 stamps (entry, prologue done, first operands
+// landed, MMAs issued, accumulator complete, stores done, exit, -) to buf[cta * 8 + slot]; NULL switches it off.
+extern "C" int immtsf_gemm_trace(long long* buf) {
+  g_trace = buf;
+  return IMMTSF_OK;
+}
 
 // Start recording a CUDA-event pair around every gemm_tc_kernel launch (on the launch stream).
 extern "C" int immtsf_profile_begin(int max_records) {
@@ -556,7 +849,7 @@ extern "C" int immtsf_profile_end(int* M, int* N, int* K, int* ragged_dim, float
 size_t immtsf_gemm_tc_workspace(int transA, int transB, int M, int N, int K) {
   const size_t ra = transA ? K : M, ca = transA ? M : K, rb = transB ? N : K, cb = transB ? K : N;
   const size_t a = align_up(ra * align_up(ca, 4) * 4, 256), b = align_up(rb * align_up(cb, 4) * 4, 256);
-  const int sk = choose_splitk(M, N, K, choose_bn(M, N, K));
+  const int sk = choose_splitk(M, N, K, choose_variant(M, N, K));
   const size_t p = sk > 1 ? align_up((size_t)sk * M * align_up(N, 4) * 4, 256) : 0;
   return a + b + p + 256;
 }
@@ -628,8 +921,10 @@ int immtsf_gemm_tc(int transA, int transB, int M, int N, int K, float alpha, con
   }
   CUtensorMap mAh, mAl, mBh, mBl;
   // K-major operand [rows=MN][cols=K]: box 32 x 128 (or 256) ; MN-major operand [rows=K][cols=MN]: box 32 x 32
-  const int bn = choose_bn(M, N, K);
-  const int boxA = transA ? 32 : BM, boxB = transB ? bn : 32;
+  const int variant = choose_variant(M, N, K);
+  const int bn = variant_bn(variant);
+  // pairs: every CTA fetches its own 128-column half of B
+  const int boxA = transA ? 32 : BM, boxB = transB ? (variant == VPAIR ? Cfg2::BNH : bn) : 32;
   if (make_map(&mAh, A, ra, ca, lda, boxA, transA != 0) || make_map(&mAl, Al, ra, ca, lda2, boxA, transA != 0) ||
       make_map(&mBh, B, rb, cb, ldb, boxB, transB == 0) || make_map(&mBl, Bl, rb, cb, ldb2, boxB, transB == 0)) {
     immtsf_set_error("gemm_tc: cuTensorMapEncodeTiled failed");
@@ -638,9 +933,10 @@ int immtsf_gemm_tc(int transA, int transB, int M, int N, int K, float alpha, con
   TcArgs g;
   g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K; g.alpha = alpha; g.beta = beta; g.bias = bias;
   g.ragged = ragged; g.ragged_dim = ragged_dim;
-  g.batched = 0; g.batch2 = 1; g.c_s1 = 0; g.c_s2 = 0;
+  g.batched = 0; g.batch2 = 1; g.c_s1 = 0; g.c_s2 = 0; g.trace = g_trace;
   dim3 grid(ceil_div(N, bn), ceil_div(M, BM));
-  const int splitk = choose_splitk(M, N, K, bn);
+  if (variant == VPAIR) grid = dim3(2 * ceil_div(M, 2 * BM), ceil_div(N, 256));  // x: CTA pairs along M (cluster 2x1x1)
+  const int splitk = choose_splitk(M, N, K, variant);
   g.partial = nullptr; g.ldp = 0;
   if (splitk > 1) {
     grid.z = splitk;
@@ -654,6 +950,10 @@ int immtsf_gemm_tc(int transA, int transB, int M, int N, int K, float alpha, con
   cudaFuncSetAttribute(gemm_tc_kernel<a, b, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<256>::SMEM_BYTES)
     TC_ATTR(false, false); TC_ATTR(false, true); TC_ATTR(true, false); TC_ATTR(true, true);
 #undef TC_ATTR
+    cudaFuncSetAttribute(gemm_tc2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2::SMEM_BYTES);
+    cudaFuncSetAttribute(gemm_tc2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2::SMEM_BYTES);
+    cudaFuncSetAttribute(gemm_tc2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2::SMEM_BYTES);
+    cudaFuncSetAttribute(gemm_tc2_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2::SMEM_BYTES);
     attr_done = true;
   }
   ProfRec* rec = (g_prof_on && g_prof_n < g_prof_cap) ? &g_prof[g_prof_n++] : nullptr;
@@ -661,7 +961,8 @@ int immtsf_gemm_tc(int transA, int transB, int M, int N, int K, float alpha, con
   // UMMA "B is K-major" means stored [N][K], i.e. transB=1
 #define TC_LAUNCH(a, b)                                                                                                   \
   do {                                                                                                                    \
-    if (bn == 128) gemm_tc_kernel<a, b, 128><<<grid, Cfg<128>::THREADS, Cfg<128>::SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, g); \
+    if (variant == VPAIR) gemm_tc2_kernel<a, b><<<grid, Cfg2::THREADS, Cfg2::SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, g);      \
+    else if (bn == 128) gemm_tc_kernel<a, b, 128><<<grid, Cfg<128>::THREADS, Cfg<128>::SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, g); \
     else gemm_tc_kernel<a, b, 256><<<grid, Cfg<256>::THREADS, Cfg<256>::SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, g);          \
   } while (0)
   if (!transA && transB) TC_LAUNCH(false, false);
@@ -742,7 +1043,7 @@ extern "C" int immtsf_gemm_batched(int transA, int transB, int M, int N, int K, 
   TcArgs g;
   g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K; g.alpha = alpha; g.beta = beta; g.bias = nullptr;
   g.ragged = nullptr; g.ragged_dim = 0; g.partial = nullptr; g.ldp = 0;
-  g.batched = 1; g.batch2 = batch2; g.c_s1 = c_s1; g.c_s2 = c_s2;
+  g.batched = 1; g.batch2 = batch2; g.c_s1 = c_s1; g.c_s2 = c_s2; g.trace = nullptr;
   dim3 grid(ceil_div(N, bn), ceil_div(M, BM), batch1 * batch2);
   static bool attr_done = false;
   if (!attr_done) {

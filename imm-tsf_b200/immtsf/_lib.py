@@ -29,6 +29,7 @@ SIGNATURES = {
     "immtsf_seed_advance": [P, U64, P],
     "immtsf_profile_begin": [I],
     "immtsf_profile_end": [P, P, P, P, P, I],
+    "immtsf_gemm_trace": [P],
     "immtsf_csr_build": [P, P, I, I, I, P, P, P, P, P, P, P, P, I, P],
     "immtsf_nan_check": [P, SZ, P, I, P],
     "immtsf_zero_pad_rows": [P, I, I, P, I, P],

@@ -58,6 +58,10 @@ int immtsf_seed_advance(uint64_t* dev_ptr, uint64_t inc, void* stream);
  * the number of records copied (shape, ragged_dim and milliseconds each). */
 int immtsf_profile_begin(int max_records);
 int immtsf_profile_end(int* M, int* N, int* K, int* ragged_dim, float* ms, int cap);
+/* Diagnostics of the CTA-pair tcgen05 kernel: while buf != NULL every CTA writes clock64 stamps of its phases to
+ * buf[cta * 8 + slot]: 0 entry, 1 prologue done, 2 first operands landed (leader), 3 MMAs issued (leader),
+ * 4 accumulator complete, 5 stores done, 6 exit; slot 7 = globaltimer (ns) at entry.  NULL switches it off. */
+int immtsf_gemm_trace(long long* buf);
 
 /* ---- K1: padded -> ragged CSR (replaces the content mask of
  * fusions/TTF_RecAvg.py:69 / fusions/TTF_T2V_XAttn.py:107, the NaN guard of

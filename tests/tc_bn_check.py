@@ -1,4 +1,4 @@
-"""Helper run as a subprocess by test_gpu_gemm_tc.py with IMMTSF_TC_BN=128|256: the tile-width override is read
+"""Helper run as a subprocess by test_gpu_gemm_tc.py with IMMTSF_TC_BN=128|256|512 (512 = CTA pairs): the tile-width override is read
 once per process.  Checks the forced variant against fp64 on shapes that exercise N tails, split-K, ragged
 bounds, all transpositions and the epilogue (alpha/beta/bias)."""
 import os
@@ -12,7 +12,7 @@ from immtsf import ops  # noqa: E402
 
 TOL = 4e-6
 worst = 0.0
-for (M, N, K) in [(128, 256, 64), (300, 200, 136), (256, 520, 768), (768, 768, 6144), (2200, 1152, 768), (6144, 768, 768)]:
+for (M, N, K) in [(128, 256, 64), (300, 200, 136), (384, 300, 40), (256, 520, 768), (768, 768, 6144), (2200, 1152, 768), (6144, 768, 768)]:
     for tA in (0, 1):
         for tB in (0, 1):
             g = torch.Generator().manual_seed(M + 3 * N + 7 * K + 2 * tA + tB)
@@ -37,7 +37,9 @@ out = torch.full((M, N), 7.0, device="cuda")
 ops.gemm(A, W, out, transB=True, ragged=m_dev, ragged_dim=1, backend=ops.BACKEND_TC)
 ref = A.double() @ W.double().T
 assert ((out[:m].double() - ref[:m]).abs().max() / ref.abs().max()).item() <= TOL
-assert (out[m:384] == 0).all() and (out[384:] == 7.0).all()
+tile = 256 if os.environ.get("IMMTSF_TC_BN") == "512" else 128  # pad rows are zeroed up to the end of the last touched tile
+edge = (m + tile - 1) // tile * tile
+assert (out[m:edge] == 0).all() and (out[edge:] == 7.0).all()
 dy = torch.randn(M, N, generator=g).cuda()
 dy[m:] = 0.0
 dw = torch.empty(N, K, device="cuda")

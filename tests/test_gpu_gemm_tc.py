@@ -62,7 +62,9 @@ def test_gemm_tc_ragged():
     ops.gemm(A, W, out, transB=True, ragged=m_dev, ragged_dim=1, backend=ops.BACKEND_TC)
     ref = A.double().cpu() @ W.double().cpu().T
     G.assert_close("rows<m", out[:m].cpu(), ref[:m], TOL)
-    assert (out[m:384] == 0).all() and (out[384:] == 7.0).all()
+    # pad rows are zeroed up to the end of the last touched tile (128 rows, or 256 for the CTA-pair variant)
+    assert (out[m:384] == 0).all() and (out[512:] == 7.0).all()
+    assert (out[384:512] == 0).all() or (out[384:512] == 7.0).all()
     dy = torch.randn(M, N, generator=g).cuda()
     dy[m:] = 0.0
     dw = torch.empty(N, K, device="cuda")
@@ -90,9 +92,10 @@ def test_auto_backend_uses_tc_for_big_and_ffma_for_skinny():
 
 
 @pytest.mark.timeout(300)
-@pytest.mark.parametrize("bn", ["128", "256"])
+@pytest.mark.parametrize("bn", ["128", "256", "512"])
 def test_gemm_tc_both_tile_widths(bn):
-    """The 128x128 (dual TMEM accumulator) and 128x256 (setmaxnreg, 8 epilogue warps) variants, each forced."""
+    """The 128x128 (dual TMEM accumulator), 128x256 (setmaxnreg, 8 epilogue warps) and CTA-pair (cta_group::2,
+    256x256 per cluster; IMMTSF_TC_BN=512) variants, each forced."""
     import os
     import subprocess
     import sys
