@@ -268,8 +268,8 @@ def run_gpu_arm(args, w):
             src = d_in if resident else h_in
             if graphed is not None:
                 loss = graphed(*src)  # copies into the static buffers (H2D when src is pinned host memory) + one replay
-                if world > 1:
-                    dp.allreduce_grads(params, flat=graphed.flat_grads)
+                if world > 1 and graphed.group is None:
+                    dp.allreduce_grads(params, flat=graphed.flat_grads)  # (in-graph mode: the replay already reduced)
             else:
                 inp = src if resident else [t.to(dev, non_blocking=True) for t in src]
                 loss = step(inp)
@@ -306,7 +306,21 @@ def run_gpu_arm(args, w):
     if not args.eager:
         for p in params:
             p.grad = None
-        graphed = runtime.GraphedStep(fm, example=d_in, warmup=2, flat_grads=world > 1)
+        dp_mode = "none"
+        if world > 1 and args.dp_mode == "ingraph":
+            try:
+                graphed = runtime.GraphedStep(fm, example=d_in, warmup=2, allreduce_group=True)
+                dp_mode = "two NCCL all-reduces captured in the step graph (MMF bucket overlaps the TTF backward)"
+            except Exception as e:  # capture of NCCL refused: fall back to one all-reduce after the replay
+                print(f"[bench] in-graph all-reduce unavailable ({type(e).__name__}: {e}); reducing after the replay", file=sys.stderr)
+                torch.cuda.synchronize()
+                graphed = None
+        if graphed is None:
+            for p in params:
+                p.grad = None
+            graphed = runtime.GraphedStep(fm, example=d_in, warmup=2, flat_grads=world > 1)
+            if world > 1:
+                dp_mode = "one NCCL all-reduce of the flat gradient bucket after the graph replay"
     timed(W, True, graphed)
     barrier()
     clocks = ClockSampler(local)
@@ -341,6 +355,8 @@ def run_gpu_arm(args, w):
 
     if rank != 0:
         if world > 1:
+            graphed = None
+            torch.cuda.synchronize()
             dist.destroy_process_group()
         return
     peaks = load_peaks()
@@ -363,7 +379,7 @@ def run_gpu_arm(args, w):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": w["name"], "step": "FusionModel forward+backward (all param grads + dY_ts), train mode, dropout 0.1",
                    "per_gpu_batch": w["B"], "global_batch": w["B"] * world, "sum_notes_rank0": sumN,
-                   "parallelism": f"dp{world}" if world > 1 else "single",
+                   "parallelism": f"dp{world}" if world > 1 else "single", "dp_allreduce": dp_mode if not args.eager else "after backward",
                    "l2": "256 MiB flush write before every timed step", "gemm_backend": os.environ.get("IMMTSF_GEMM", "auto"),
                    "launch": "eager (one host call per kernel)" if args.eager else "runtime.GraphedStep (whole step replayed as one CUDA graph)",
                    "eager_samples_per_s": samples / (ms_eager / 1e3), "kernels_per_step": launches_per_step,
@@ -385,6 +401,8 @@ def run_gpu_arm(args, w):
     }
     print(json.dumps(line), flush=True)
     if world > 1:
+        graphed = None  # graphs that captured NCCL work must go before the communicator
+        torch.cuda.synchronize()
         dist.destroy_process_group()
 
 
@@ -397,6 +415,9 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="time the eager path only (no CUDA-graph replay)")
+    ap.add_argument("--dp-mode", default="post", choices=["ingraph", "post"],
+                    help="N > 1: gradient all-reduce issued after the graph replay (default), or captured inside the step "
+                         "graph in two buckets (experimental: measured no gain at N=2, see DESIGN.md 6)")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     if args.impl == "reference":

@@ -71,6 +71,11 @@ class FusionModel(nn.Module):
         if check:
             ops.nan_check(Y32, flags, ops.FLAG_Y)
         E_txt, M_txt = self.ttf.forward_ragged(r, t_hat)
+        hook = getattr(self, "_e_txt_grad_hook", None)
+        if hook is not None and E_txt.requires_grad:
+            # data-parallel overlap (immtsf/runtime.py GraphedStep): called when backward crosses the MMF -> TTF
+            # boundary, i.e. when every MMF parameter gradient is final
+            E_txt.register_hook(hook)
         if check:
             # the broadcast view of T2V eval mode has B distinct rows: check those only
             ops.nan_check(E_txt[:, :1] if E_txt.stride(1) == 0 else E_txt, flags, ops.FLAG_E)

@@ -79,7 +79,12 @@ class GraphedStep:
     The reference's NaN ValueErrors need a device->host read, which a graph cannot contain: call check_nan() after a
     step when that guard is wanted (one sync)."""
 
-    def __init__(self, fusion, example, loss_fn=None, extras=(), warmup: int = 3, flat_grads: bool = False):
+    def __init__(self, fusion, example, loss_fn=None, extras=(), warmup: int = 3, flat_grads: bool = False,
+                 allreduce_group=None):
+        """allreduce_group: a torch.distributed process group (or True for the default group).  The data-parallel
+        gradient all-reduce is then captured INSIDE the graph, in two buckets: the MMF gradients are
+        reduced on NCCL's stream as soon as the MMF backward has produced them -- overlapping the TTF backward -- and
+        the TTF bucket follows at the end.  Implies flat_grads (the buckets are slices of one flat buffer)."""
         from . import _lib
 
         if not torch.cuda.is_available():
@@ -91,6 +96,19 @@ class GraphedStep:
         self.static_in[3].requires_grad_(True)
         self.static_extra = [t.detach().to(dev, copy=True) for t in extras]
         self.params = [p for p in fusion.parameters() if p.requires_grad]
+        self.group = None
+        if allreduce_group is not None and allreduce_group is not False:
+            import torch.distributed as dist
+
+            if dist.is_available() and dist.is_initialized():
+                self.group = dist.group.WORLD if allreduce_group is True else allreduce_group
+                if dist.get_world_size(self.group) == 1:
+                    self.group = None
+        flat_grads = flat_grads or self.group is not None
+        # bucket order = the order in which backward completes the gradients: MMF first, then TTF
+        mmf_ids = {id(p) for p in fusion.mmf.parameters()} if hasattr(fusion, "mmf") else set()
+        self.params.sort(key=lambda p: 0 if id(p) in mmf_ids else 1)
+        self.n_first = sum(p.numel() for p in self.params if id(p) in mmf_ids)
         self.seed_offset = torch.zeros(1, dtype=torch.int64, device=dev)
         self._lib = _lib
         _lib.call("immtsf_set_seed_offset_ptr", self.seed_offset.data_ptr())
@@ -116,13 +134,42 @@ class GraphedStep:
                 p.grad = None
         self.static_in[3].grad = None
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            _lib.call("immtsf_seed_advance", self.seed_offset.data_ptr(), 1, ops._stream())
-            if self.flat_grads is not None:
-                self.flat_grads.zero_()
-            out, loss = self._eager()
+        self._works = []
+        if self.group is not None:
+            fusion._e_txt_grad_hook = self._reduce_first_bucket  # fires between the MMF and the TTF backward
+        try:
+            # NCCL's watchdog thread may touch CUDA while we capture: thread-local capture mode tolerates that
+            mode = dict(capture_error_mode="thread_local") if self.group is not None else {}
+            with torch.cuda.graph(self.graph, **mode):
+                _lib.call("immtsf_seed_advance", self.seed_offset.data_ptr(), 1, ops._stream())
+                if self.flat_grads is not None:
+                    self.flat_grads.zero_()
+                out, loss = self._eager()
+                if self.group is not None:
+                    self._reduce_rest()
+        finally:
+            if self.group is not None:
+                fusion._e_txt_grad_hook = None
         self.Y_out, self.loss = out.detach(), loss.detach()
         self.flags = getattr(fusion, "_last_flags", None)
+
+    def _reduce_first_bucket(self, grad):
+        import torch.distributed as dist
+
+        if self.n_first > 0:
+            self._works.append(dist.all_reduce(self.flat_grads[: self.n_first], op=dist.ReduceOp.SUM, group=self.group,
+                                               async_op=True))
+        return None
+
+    def _reduce_rest(self):
+        import torch.distributed as dist
+
+        if self.n_first < self.flat_grads.numel():
+            self._works.append(dist.all_reduce(self.flat_grads[self.n_first:], op=dist.ReduceOp.SUM, group=self.group,
+                                               async_op=True))
+        for w in self._works:
+            w.wait()  # the capture stream joins NCCL's stream
+        self._works = []
 
     def _eager(self):
         out = self.fusion(self.static_in[0], self.static_in[1], self.static_in[2], self.static_in[3])
