@@ -15,8 +15,8 @@
 
 int immtsf_gemm_tc(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda, const float* A_lo,
                    int lda_lo, const float* B, int ldb, const float* B_lo, int ldb_lo, float beta, float* C, int ldc,
-                   const float* bias, const int32_t* ragged, int ragged_dim, void* workspace, size_t workspace_bytes,
-                   cudaStream_t st);
+                   float* C_lo, int ldc_lo, const float* bias, const int32_t* ragged, int ragged_dim, void* workspace,
+                   size_t workspace_bytes, cudaStream_t st);
 size_t immtsf_gemm_tc_workspace(int transA, int transB, int M, int N, int K);
 int immtsf_gemm_tc_eligible(int forced, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
                             const float* C, int ldc);
@@ -264,8 +264,9 @@ extern "C" int immtsf_gemm_plan(int transA, int transB, int M, int N, int K, con
 
 extern "C" int immtsf_gemm_ex(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda,
                               const float* A_lo, int lda_lo, const float* B, int ldb, const float* B_lo, int ldb_lo,
-                              float beta, float* C, int ldc, const float* bias, const int32_t* ragged, int ragged_dim,
-                              int backend, void* workspace, size_t workspace_bytes, void* stream) {
+                              float beta, float* C, int ldc, float* C_lo, int ldc_lo, const float* bias,
+                              const int32_t* ragged, int ragged_dim, int backend, void* workspace, size_t workspace_bytes,
+                              void* stream) {
   IMMTSF_REQUIRE(M >= 0 && N >= 0 && K >= 0, "gemm: negative dimension");
   if (M == 0 || N == 0) return IMMTSF_OK;
   IMMTSF_REQUIRE(A && B && C, "gemm: null operand");
@@ -279,11 +280,12 @@ extern "C" int immtsf_gemm_ex(int transA, int transB, int M, int N, int K, float
   if (plan == 3) {  // skinny shapes (a dimension <= 32): dedicated streaming kernels
     const int rc = immtsf_gemm_skinny(transA, transB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, ragged, ragged_dim,
                                       workspace, workspace_bytes, st);
-    if (rc <= 0) return rc;
+    if (rc < 0) return rc;
+    if (rc == 0) return C_lo != nullptr ? immtsf_split_lo(C, ldc, M, N, C_lo, ldc_lo, ragged_dim == 1 ? ragged : nullptr, stream) : rc;
   }
   if (plan == 2)
-    return immtsf_gemm_tc(transA, transB, M, N, K, alpha, A, lda, A_lo, lda_lo, B, ldb, B_lo, ldb_lo, beta, C, ldc, bias, ragged,
-                          ragged_dim, workspace, workspace_bytes, st);
+    return immtsf_gemm_tc(transA, transB, M, N, K, alpha, A, lda, A_lo, lda_lo, B, ldb, B_lo, ldb_lo, beta, C, ldc, C_lo, ldc_lo,
+                          bias, ragged, ragged_dim, workspace, workspace_bytes, st);
   if (plan < 0) {
     immtsf_set_error("gemm: tcgen05 backend requested but shape/alignment is not eligible");
     return IMMTSF_ERR_UNSUPPORTED;
@@ -301,6 +303,7 @@ extern "C" int immtsf_gemm_ex(int transA, int transB, int M, int N, int K, float
   if (tiles128 >= 148 && N >= 96) launch_ffma<128, 128, 8, 8>(g, transA, transB, st);
   else launch_ffma<64, 64, 4, 4>(g, transA, transB, st);
   IMMTSF_CHECK_LAUNCH("gemm_ffma");
+  if (C_lo != nullptr) return immtsf_split_lo(C, ldc, M, N, C_lo, ldc_lo, ragged_dim == 1 ? ragged : nullptr, stream);
   return IMMTSF_OK;
 }
 
@@ -308,8 +311,8 @@ extern "C" int immtsf_gemm(int transA, int transB, int M, int N, int K, float al
                            const float* B, int ldb, float beta, float* C, int ldc, const float* bias,
                            const int32_t* ragged, int ragged_dim, int backend, void* workspace,
                            size_t workspace_bytes, void* stream) {
-  return immtsf_gemm_ex(transA, transB, M, N, K, alpha, A, lda, nullptr, 0, B, ldb, nullptr, 0, beta, C, ldc, bias, ragged,
-                        ragged_dim, backend, workspace, workspace_bytes, stream);
+  return immtsf_gemm_ex(transA, transB, M, N, K, alpha, A, lda, nullptr, 0, B, ldb, nullptr, 0, beta, C, ldc, nullptr, 0, bias,
+                        ragged, ragged_dim, backend, workspace, workspace_bytes, stream);
 }
 
 extern "C" size_t immtsf_gemm_workspace_bytes(int transA, int transB, int M, int N, int K) {

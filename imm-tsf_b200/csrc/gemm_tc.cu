@@ -159,6 +159,9 @@ struct TcArgs {
   // C(b1, b2) = C + b1 * c_s1 + b2 * c_s2; no split-K, no ragged bounds
   int batched, batch2;
   long c_s1, c_s2;
+  // optional second output: lo = C - trunc_tf32(C), so that a consumer product does not need a split pass over C
+  float* C_lo;
+  int ldc_lo;
   // diagnostics (immtsf_gemm_trace): per-CTA clock64 stamps of the pair kernel's phases, 8 slots per CTA
   long long* trace;
 };
@@ -182,7 +185,8 @@ constexpr int EPI_WARP_BYTES = 32 * EPI_LD * 4;  // 16.5 KiB per epilogue warp
 // alpha / bias / beta, zeros for ragged pad rows (row >= Mlive), columns < ncols.
 __device__ __forceinline__ void epilogue_store(const float (&acc)[128], uint32_t stage, int lane, float* out, size_t ld,
                                                int row0, int ncol0, int Mfull, int Mlive, int ncols, bool partial, float alpha,
-                                               float beta, const float* __restrict__ bias) {
+                                               float beta, const float* __restrict__ bias, float* out_lo = nullptr,
+                                               size_t ld_lo = 0) {
   const uint32_t mine = stage + (uint32_t)(lane * EPI_LD * 4);
 #pragma unroll
   for (int j4 = 0; j4 < 32; ++j4)
@@ -225,6 +229,14 @@ __device__ __forceinline__ void epilogue_store(const float (&acc)[128], uint32_t
       p[0] = v.x;
       if (n + 1 < ncols) p[1] = v.y;
       if (n + 2 < ncols) p[2] = v.z;
+    }
+    if (out_lo != nullptr) {  // ld_lo is a multiple of 4 and >= roundup(ncols, 4): the whole float4 is in bounds
+      float4 l;
+      l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+      l.y = n + 1 < ncols ? v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u) : 0.f;
+      l.z = n + 2 < ncols ? v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u) : 0.f;
+      l.w = n + 3 < ncols ? v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u) : 0.f;
+      *reinterpret_cast<float4*>(out_lo + (size_t)rr * ld_lo + lane * 4) = l;
     }
   }
 }
@@ -391,7 +403,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
                      g.M, g.M, g.ldp, true, 1.f, 0.f, nullptr);
     } else {
       epilogue_store(acc, stage, lane, g.C + bz1 * g.c_s1 + bz2 * g.c_s2 + (size_t)row0 * g.ldc + n0 + ch, (size_t)g.ldc, row0,
-                     n0 + ch, g.M, M, g.N, false, g.alpha, g.beta, g.bias);
+                     n0 + ch, g.M, M, g.N, false, g.alpha, g.beta, g.bias,
+                     g.C_lo != nullptr ? g.C_lo + (size_t)row0 * g.ldc_lo + n0 + ch : nullptr, (size_t)g.ldc_lo);
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -619,7 +632,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant
                      g.M, g.M, g.ldp, true, 1.f, 0.f, nullptr);
     } else {
       epilogue_store(acc, stage, lane, g.C + (size_t)row0 * g.ldc + n0 + ch, (size_t)g.ldc, row0, n0 + ch, g.M, M, g.N, false,
-                     g.alpha, g.beta, g.bias);
+                     g.alpha, g.beta, g.bias, g.C_lo != nullptr ? g.C_lo + (size_t)row0 * g.ldc_lo + n0 + ch : nullptr,
+                     (size_t)g.ldc_lo);
     }
   }
   if (threadIdx.x == 128) TC_STAMP(5);
@@ -634,7 +648,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant
 // C = alpha * sum_z partial[z] + beta*C + bias for rows < M_eff; zeros for ragged pad rows inside touched tiles
 __global__ void splitk_reduce_kernel(float* __restrict__ C, int ldc, int M, int N, float alpha, float beta,
                                      const float* __restrict__ bias, const float* __restrict__ partial, int ldp, int splitk,
-                                     const int32_t* __restrict__ ragged, int ragged_dim) {
+                                     const int32_t* __restrict__ ragged, int ragged_dim, float* __restrict__ C_lo, int ldc_lo) {
   int Meff = M;
   if (ragged_dim == 1) Meff = ragged_rows(M, ragged);
   int Mtouch = (Meff + BM - 1) / BM * BM;
@@ -659,6 +673,7 @@ __global__ void splitk_reduce_kernel(float* __restrict__ C, int ldc, int M, int 
         if (bias != nullptr) x += bias[c + e];
       }
       out[e] = x;
+      if (C_lo != nullptr) C_lo[(size_t)r * ldc_lo + c + e] = x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
     }
   }
 }
@@ -692,6 +707,43 @@ __global__ void split_lo_kernel(const float* __restrict__ src, int ld_src, int r
     l.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
     l.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
     *reinterpret_cast<float4*>(lo + (size_t)r * ld_dst + c) = l;
+  }
+}
+
+// Several small tensors (the weight matrices of a module) in ONE launch: optional plain copy (hi_dst: the packed
+// operand of a fused projection) and / or the lo split.  blockIdx.y = task.
+constexpr int MS_MAX = 16;
+struct MultiSplitArgs {
+  const float* src[MS_MAX];
+  float* hi[MS_MAX];
+  float* lo[MS_MAX];
+  int rows[MS_MAX], cols[MS_MAX], ld_src[MS_MAX], ld_hi[MS_MAX], ld_lo[MS_MAX];
+};
+__global__ void multi_split_kernel(const __grid_constant__ MultiSplitArgs a) {
+  const int t = blockIdx.y;
+  const float* __restrict__ src = a.src[t];
+  float* __restrict__ hi = a.hi[t];
+  float* __restrict__ lo = a.lo[t];
+  const int cols = a.cols[t], c4n = (cols + 3) >> 2;
+  const size_t total = (size_t)a.rows[t] * c4n;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / c4n), c = (int)(i % c4n) * 4;
+    const float* p = src + (size_t)r * a.ld_src[t] + c;
+    float x[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) x[e] = c + e < cols ? __ldg(p + e) : 0.f;
+    if (hi != nullptr) {
+      float* h = hi + (size_t)r * a.ld_hi[t] + c;
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (c + e < cols) h[e] = x[e];
+    }
+    if (lo != nullptr) {
+      float* l = lo + (size_t)r * a.ld_lo[t] + c;
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (c + e < cols) l[e] = x[e] - __uint_as_float(__float_as_uint(x[e]) & 0xFFFFE000u);
+    }
   }
 }
 
@@ -888,10 +940,41 @@ extern "C" int immtsf_split_lo(const float* src, int ld, int rows, int cols, flo
   return launch_split_lo(src, ld, rows, cols, lo, ld_lo, ragged, ragged != nullptr, (cudaStream_t)stream);
 }
 
+// n <= 16 tasks: task i reads src[i] (rows[i] x cols[i], ld_src[i]) and writes a copy to hi[i] (nullable, ld_hi[i])
+// and src - trunc_tf32(src) to lo[i] (nullable, ld_lo[i]).  One launch for all of them.
+extern "C" int immtsf_multi_split(int n, const float* const* src, const int* ld_src, const int* rows, const int* cols,
+                                  float* const* hi, const int* ld_hi, float* const* lo, const int* ld_lo, void* stream) {
+  if (n == 0) return IMMTSF_OK;
+  IMMTSF_REQUIRE(n > 0 && n <= MS_MAX, "multi_split: 1..16 tasks per call");
+  IMMTSF_REQUIRE(src && ld_src && rows && cols && hi && ld_hi && lo && ld_lo, "multi_split: null array");
+  MultiSplitArgs a;
+  size_t most = 0;
+  for (int i = 0; i < MS_MAX; ++i) {
+    const int j = i < n ? i : 0;
+    IMMTSF_REQUIRE(src[j] != nullptr && rows[j] >= 0 && cols[j] >= 0 && ld_src[j] >= cols[j], "multi_split: bad task %d", j);
+    IMMTSF_REQUIRE((hi[j] == nullptr || ld_hi[j] >= cols[j]) && (lo[j] == nullptr || ld_lo[j] >= cols[j]),
+                   "multi_split: destination leading dimension too small (task %d)", j);
+    a.src[i] = src[j]; a.hi[i] = hi[j]; a.lo[i] = lo[j];
+    a.rows[i] = rows[j]; a.cols[i] = cols[j]; a.ld_src[i] = ld_src[j]; a.ld_hi[i] = ld_hi[j]; a.ld_lo[i] = ld_lo[j];
+    const size_t tot = (size_t)rows[j] * ((cols[j] + 3) / 4);
+    if (i < n && tot > most) most = tot;
+  }
+  int gx = (int)((most + 255) / 256);
+  if (gx > 148 * 2) gx = 148 * 2;
+  if (gx < 1) gx = 1;
+  multi_split_kernel<<<dim3(gx, n), 256, 0, (cudaStream_t)stream>>>(a);
+  IMMTSF_CHECK_LAUNCH("multi_split");
+  return IMMTSF_OK;
+}
+
 int immtsf_gemm_tc(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda, const float* A_lo,
                    int lda_lo, const float* B, int ldb, const float* B_lo, int ldb_lo, float beta, float* C, int ldc,
-                   const float* bias, const int32_t* ragged, int ragged_dim, void* workspace, size_t workspace_bytes,
-                   cudaStream_t st) {
+                   float* C_lo, int ldc_lo, const float* bias, const int32_t* ragged, int ragged_dim, void* workspace,
+                   size_t workspace_bytes, cudaStream_t st) {
+  if (C_lo != nullptr && (((uintptr_t)C_lo & 15) != 0 || (ldc_lo & 3) != 0 || ldc_lo < (int)align_up(N, 4))) {
+    immtsf_set_error("gemm_tc: C_lo must be 16B aligned with ldc_lo %% 4 == 0 and ldc_lo >= roundup(N, 4)");
+    return IMMTSF_ERR_ARG;
+  }
   const size_t need = immtsf_gemm_tc_workspace(transA, transB, M, N, K);
   if (workspace == nullptr || workspace_bytes < need) {
     immtsf_set_error("gemm_tc: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
@@ -933,7 +1016,7 @@ int immtsf_gemm_tc(int transA, int transB, int M, int N, int K, float alpha, con
   TcArgs g;
   g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K; g.alpha = alpha; g.beta = beta; g.bias = bias;
   g.ragged = ragged; g.ragged_dim = ragged_dim;
-  g.batched = 0; g.batch2 = 1; g.c_s1 = 0; g.c_s2 = 0; g.trace = g_trace;
+  g.batched = 0; g.batch2 = 1; g.c_s1 = 0; g.c_s2 = 0; g.trace = g_trace; g.C_lo = C_lo; g.ldc_lo = ldc_lo;
   dim3 grid(ceil_div(N, bn), ceil_div(M, BM));
   if (variant == VPAIR) grid = dim3(2 * ceil_div(M, 2 * BM), ceil_div(N, 256));  // x: CTA pairs along M (cluster 2x1x1)
   const int splitk = choose_splitk(M, N, K, variant);
@@ -975,7 +1058,8 @@ int immtsf_gemm_tc(int transA, int transB, int M, int N, int K, float alpha, con
   if (splitk > 1) {
     const size_t tot = (size_t)M * (g.ldp / 4);
     int rg = (int)((tot + 255) / 256); if (rg > 148 * 8) rg = 148 * 8;
-    splitk_reduce_kernel<<<rg, 256, 0, st>>>(C, ldc, M, N, alpha, beta, bias, g.partial, g.ldp, splitk, ragged, ragged_dim);
+    splitk_reduce_kernel<<<rg, 256, 0, st>>>(C, ldc, M, N, alpha, beta, bias, g.partial, g.ldp, splitk, ragged, ragged_dim, C_lo,
+                                             ldc_lo);
     IMMTSF_CHECK_LAUNCH("splitk_reduce");
   }
   return IMMTSF_OK;
@@ -1043,7 +1127,7 @@ extern "C" int immtsf_gemm_batched(int transA, int transB, int M, int N, int K, 
   TcArgs g;
   g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K; g.alpha = alpha; g.beta = beta; g.bias = nullptr;
   g.ragged = nullptr; g.ragged_dim = 0; g.partial = nullptr; g.ldp = 0;
-  g.batched = 1; g.batch2 = batch2; g.c_s1 = c_s1; g.c_s2 = c_s2; g.trace = nullptr;
+  g.batched = 1; g.batch2 = batch2; g.c_s1 = c_s1; g.c_s2 = c_s2; g.trace = nullptr; g.C_lo = nullptr; g.ldc_lo = 0;
   dim3 grid(ceil_div(N, bn), ceil_div(M, BM), batch1 * batch2);
   static bool attr_done = false;
   if (!attr_done) {

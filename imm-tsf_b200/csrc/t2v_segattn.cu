@@ -17,18 +17,25 @@
 __global__ void time2vec_fwd_kernel(const float* __restrict__ tau, const float* __restrict__ w_lin,
                                     const float* __restrict__ b_lin, const float* __restrict__ w_per,
                                     const float* __restrict__ b_per, int d_tau, float* __restrict__ out, int ld,
-                                    const int32_t* __restrict__ m_dev, int M_alloc) {
+                                    float* __restrict__ out_lo, int ld_lo, const int32_t* __restrict__ m_dev, int M_alloc) {
   const int m = ragged_rows(M_alloc, m_dev);
   int end = (m + 127) / 128 * 128;
   if (end > M_alloc) end = M_alloc;
   for (int n = blockIdx.x; n < end; n += gridDim.x) {
     float* o = out + (size_t)n * ld;
+    float* l = out_lo != nullptr ? out_lo + (size_t)n * ld_lo : nullptr;
     if (n < m) {
       const float t = tau[n];
-      for (int k = threadIdx.x; k < d_tau; k += blockDim.x)
-        o[k] = (k == 0) ? fmaf(w_lin[0], t, b_lin[0]) : sinf(fmaf(w_per[k - 1], t, b_per[k - 1]));
+      for (int k = threadIdx.x; k < d_tau; k += blockDim.x) {
+        const float v = (k == 0) ? fmaf(w_lin[0], t, b_lin[0]) : sinf(fmaf(w_per[k - 1], t, b_per[k - 1]));
+        o[k] = v;
+        if (l != nullptr) l[k] = v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);  // tcgen05 operand split
+      }
     } else {
-      for (int k = threadIdx.x; k < d_tau; k += blockDim.x) o[k] = 0.f;
+      for (int k = threadIdx.x; k < d_tau; k += blockDim.x) {
+        o[k] = 0.f;
+        if (l != nullptr) l[k] = 0.f;
+      }
     }
   }
 }
@@ -65,13 +72,15 @@ __global__ void time2vec_bwd_kernel(const float* __restrict__ dphi, int ld, cons
 }
 
 extern "C" int immtsf_time2vec_fwd(const float* tau_flat, const float* w_lin, const float* b_lin, const float* w_per,
-                                   const float* b_per, int d_tau, float* out, int ld, const int32_t* m_dev,
-                                   int M_alloc, void* stream) {
+                                   const float* b_per, int d_tau, float* out, int ld, float* out_lo, int ld_lo,
+                                   const int32_t* m_dev, int M_alloc, void* stream) {
   if (M_alloc == 0) return IMMTSF_OK;
   IMMTSF_REQUIRE(tau_flat && w_lin && b_lin && w_per && b_per && out && m_dev, "time2vec_fwd: null pointer");
   IMMTSF_REQUIRE(d_tau > 1 && ld >= d_tau, "time2vec_fwd: d_tau must be > 1 (TTF_T2V_XAttn.py:14) and ld >= d_tau");
+  IMMTSF_REQUIRE(out_lo == nullptr || ld_lo >= d_tau, "time2vec_fwd: ld_lo < d_tau");
   int grid = M_alloc < 148 * 8 ? M_alloc : 148 * 8;
-  time2vec_fwd_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(tau_flat, w_lin, b_lin, w_per, b_per, d_tau, out, ld, m_dev, M_alloc);
+  time2vec_fwd_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(tau_flat, w_lin, b_lin, w_per, b_per, d_tau, out, ld, out_lo, ld_lo,
+                                                              m_dev, M_alloc);
   IMMTSF_CHECK_LAUNCH("time2vec_fwd");
   return IMMTSF_OK;
 }

@@ -70,6 +70,15 @@ class FusionModel(nn.Module):
         Y32 = cm.as_f32(Y_ts)
         if check:
             ops.nan_check(Y32, flags, ops.FLAG_Y)
+        # one operand-split cache for the whole step: E_txt (and dE_txt in backward) are handed from one module's GEMM
+        # epilogue to the other module's product together with their tcgen05 lo operand
+        ops.begin_step(e_txt_feeds_tc=isinstance(self.mmf, MMF_XAttn_Add))
+        try:
+            return self._forward_step(r, t_hat, Y32, flags, check)
+        finally:
+            ops.end_step()
+
+    def _forward_step(self, r, t_hat, Y32, flags, check):
         E_txt, M_txt = self.ttf.forward_ragged(r, t_hat)
         hook = getattr(self, "_e_txt_grad_hook", None)
         if hook is not None and E_txt.requires_grad:

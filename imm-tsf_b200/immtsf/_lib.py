@@ -34,13 +34,14 @@ SIGNATURES = {
     "immtsf_nan_check": [P, SZ, P, I, P],
     "immtsf_zero_pad_rows": [P, I, I, P, I, P],
     "immtsf_gemm": [I, I, I, I, I, F, P, I, P, I, F, P, I, P, P, I, I, P, SZ, P],
-    "immtsf_gemm_ex": [I, I, I, I, I, F, P, I, P, I, P, I, P, I, F, P, I, P, P, I, I, P, SZ, P],
+    "immtsf_gemm_ex": [I, I, I, I, I, F, P, I, P, I, P, I, P, I, F, P, I, P, I, P, P, I, I, P, SZ, P],
     "immtsf_split_lo": [P, I, I, I, P, I, P, P],
+    "immtsf_multi_split": [I, P, P, P, P, P, P, P, P, P],
     "immtsf_gemm_plan": [I, I, I, I, I, P, I, P, I, P, I, I],
     "immtsf_colsum": [P, I, I, I, P, F, P, P, SZ, P],
     "immtsf_recavg_pool_fwd": [P, I, P, P, P, I, P, P, P, I, I, I, I, F, U32, U64, P, P, P, P, P, P],
     "immtsf_recavg_pool_bwd": [P, P, P, P, P, P, I, P, P, P, I, P, P, I, I, I, I, U32, U64, P, P, I, P, P, P, P],
-    "immtsf_time2vec_fwd": [P, P, P, P, P, I, P, I, P, I, P],
+    "immtsf_time2vec_fwd": [P, P, P, P, P, I, P, I, P, I, P, I, P],
     "immtsf_time2vec_bwd": [P, I, P, P, P, I, P, P, P, P, P, I, P],
     "immtsf_segattn_fwd": [P, P, P, I, I, I, I, I, I, U32, U64, P, P, P],
     "immtsf_segattn_bwd": [P, P, P, P, P, I, I, I, I, I, I, U32, U64, P, P, P],

@@ -30,10 +30,12 @@ class RecAvgFn(torch.autograd.Function):
     def forward(ctx, r: RaggedNotes, t_hat, T, thr, seed, save, log_sigma, W_in, b_in, gamma, beta, W_p, b_p):
         B = r.B
         d = W_p.shape[0]
-        lo = ops.LoCache()
+        step = ops.step_ctx()
+        lo = step.lo
+        ops.weight_los(lo, [(w, []) for w in (W_in, W_p) if w is not None])
         Vp = ops.linear_fwd(r.emb_flat, W_in, b_in, ragged=r.m_dev, lo=lo) if W_in is not None else r.emb_flat
         E_drop, E_raw, mean, rstd, wsum = ops.recavg_pool_fwd(Vp, r, t_hat, log_sigma, gamma, beta, T, d, thr, seed, save)
-        E_txt = ops.linear_fwd(E_drop.view(B * T, d), W_p, b_p, lo=lo).view(B, T, d)
+        E_txt = ops.linear_fwd(E_drop.view(B * T, d), W_p, b_p, lo=lo, emit_lo=step.e_txt_feeds_tc).view(B, T, d)
         if save:
             ctx.r, ctx.T, ctx.thr, ctx.seed, ctx.has_in, ctx.lo = r, T, thr, seed, W_in is not None, lo
             ctx.save_for_backward(t_hat, log_sigma, W_in, gamma, W_p, Vp, E_drop, E_raw, mean, rstd, wsum)
@@ -73,23 +75,33 @@ class T2VXAttnFn(torch.autograd.Function):
         dt = d // 2
         dev = Qp.device
         new = lambda *s: torch.empty(*s, dtype=_f32, device=dev)
-        lo = ops.LoCache()
+        step = ops.step_ctx()
+        lo = step.lo
         per_query = thr != 0  # attention dropout makes every (sample, query) row distinct
         fold = per_query and H == 1
-        # [V' ; phi] concat buffer (TTF_T2V_XAttn.py:139), written in place by the two producers
-        Xcat = new(r.M_alloc, d + dt)
-        if W_in is not None:
-            ops.gemm(r.emb_flat, W_in, Xcat[:, :d], transB=True, bias=b_in, ragged=r.m_dev, ragged_dim=1, lo=lo)
-        else:
-            Xcat[:, :d].copy_(r.emb_flat)
-        ops.time2vec_fwd(r, w_lin, b_lin, w_per, b_per, dt, Xcat[:, d:])
-        X = ops.linear_fwd(Xcat, W_kv, b_kv, ragged=r.m_dev, lo=lo)  # :140
+        # [V' ; phi] concat buffer (TTF_T2V_XAttn.py:139) and its tcgen05 lo operand, both written in place by the
+        # two producers (input_proj epilogue / Time2Vec kernel): no separate split pass
+        Xcat, Xcat_lo = new(r.M_alloc, d + dt), new(r.M_alloc, ops.round_up(d + dt, 4))
+        # every weight matrix's lo, and the packed [W_k ; W_o W_v] operand's first half, in one launch
+        extra = []
         if fold:
-            Wkv, bkv = new(2 * d, d), new(2 * d)
-            Wkv[:d].copy_(in_w[d:2 * d])
-            bkv[:d].copy_(in_b[d:2 * d])
-            ops.gemm(out_w, in_w[2 * d:], Wkv[d:], lo=lo)  # W_o W_v
+            Wkv, bkv, Wkv_lo = new(2 * d, d), new(2 * d), new(2 * d, d)
+            extra = [(in_w[d:2 * d], Wkv[:d], Wkv_lo[:d]), (in_b[d:2 * d], bkv[:d], None)]
+        if W_in is None:
+            extra.append((r.emb_flat, Xcat[:, :d], Xcat_lo[:, :d]))
+        ws = [(W_in, [])] if W_in is not None else []
+        ws += [(W_kv, []), (in_w, [slice(d, None), slice(2 * d, None)]), (out_w, []), (W_po, [])]
+        ops.weight_los(lo, ws, extra)
+        if W_in is not None:
+            ops.gemm(r.emb_flat, W_in, Xcat[:, :d], transB=True, bias=b_in, ragged=r.m_dev, ragged_dim=1, lo=lo,
+                     emit_lo=Xcat_lo[:, :d])
+        ops.time2vec_fwd(r, w_lin, b_lin, w_per, b_per, dt, Xcat[:, d:], Xcat_lo[:, d:])
+        lo.put(Xcat, Xcat_lo)
+        X = ops.linear_fwd(Xcat, W_kv, b_kv, ragged=r.m_dev, lo=lo, emit_lo=True)  # :140
+        if fold:
+            ops.gemm(out_w, in_w[2 * d:], Wkv[d:], lo=lo, emit_lo=Wkv_lo[d:])  # W_o W_v
             ops.gemm(in_b[2 * d:].view(1, d), out_w, bkv[d:].view(1, d), transB=True)  # W_o b_v
+            lo.put(Wkv, Wkv_lo)
         else:
             Wkv, bkv = in_w[d:], in_b[d:]
         KVp = ops.linear_fwd(X, Wkv, bkv, ragged=r.m_dev, lo=lo)  # MHA k/v in-projection, once per note
@@ -101,7 +113,7 @@ class T2VXAttnFn(torch.autograd.Function):
         rps = T if per_query else 1
         y, mean, rstd = ops.ln_fwd(attn_out, Qp.view(d), r.m_txt, rps, gamma, beta, thr, seed, ops.SITE_TTF_DROPOUT, save,
                                    xbias=out_b if fold else None)
-        E = ops.linear_fwd(y, W_po, b_po, lo=lo)
+        E = ops.linear_fwd(y, W_po, b_po, lo=lo, emit_lo=step.e_txt_feeds_tc)
         if save:
             ctx.r, ctx.T, ctx.H, ctx.thr, ctx.seed, ctx.lo = r, T, H, thr, seed, lo
             ctx.has_in, ctx.per_query, ctx.scale, ctx.fold = W_in is not None, per_query, scale, fold
@@ -146,7 +158,9 @@ class T2VXAttnFn(torch.autograd.Function):
         ops.axpby(dres, 1.0, dQp.view(d), True)
         # key/value path, once per note
         if fold:
-            dWkv = ops.linear_wgrad(dKVp, X, ragged=r.m_dev, lo=lo)  # [2d, d]: rows [d,2d) are d(W_o W_v)
+            dWkv, dWkv_lo = new(2 * d, d), new(2 * d, d)
+            ops.linear_wgrad(dKVp, X, out=dWkv, ragged=r.m_dev, lo=lo, emit_lo=dWkv_lo)  # rows [d,2d) are d(W_o W_v)
+            lo.put(dWkv[d:], dWkv_lo[d:])
             dbkv = ops.colsum(dKVp, ragged=r.m_dev)
             d_in_w[d:2 * d].copy_(dWkv[:d])
             d_in_b[d:2 * d].copy_(dbkv[:d])
@@ -158,10 +172,13 @@ class T2VXAttnFn(torch.autograd.Function):
         else:
             ops.linear_wgrad(dKVp, X, out=d_in_w[d:], ragged=r.m_dev, lo=lo)
             ops.colsum(dKVp, out=d_in_b[d:], ragged=r.m_dev)
-        dX = ops.linear_dgrad(dKVp, Wkv, ragged=r.m_dev, lo=lo)
+        dX = ops.linear_dgrad(dKVp, Wkv, ragged=r.m_dev, lo=lo, emit_lo=True)
         dW_kv = ops.linear_wgrad(dX, Xcat, ragged=r.m_dev, lo=lo)
         db_kv = ops.colsum(dX, ragged=r.m_dev)
-        dXcat = ops.linear_dgrad(dX, W_kv, ragged=r.m_dev, lo=lo)
+        dXcat_lo = new(r.M_alloc, ops.round_up(d + dt, 4)) if ctx.has_in else False
+        dXcat = ops.linear_dgrad(dX, W_kv, ragged=r.m_dev, lo=lo, emit_lo=dXcat_lo)
+        if ctx.has_in:
+            lo.put(dXcat[:, :d], dXcat_lo[:, :d])
         dwl, dbl, dwp, dbp = ops.time2vec_bwd(dXcat[:, d:], r, w_per, b_per, dt)
         dW_in = db_in = None
         if ctx.has_in:
@@ -240,12 +257,15 @@ class XAttnAddFn(torch.autograd.Function):
         dev = Y.device
         Y2 = Y.contiguous().view(B * T, C)
         E2 = E.contiguous().view(B * T, de)
-        lo = ops.LoCache()
-        # ---- weight-space folds
+        lo = ops.step_ctx().lo
+        ops.weight_los(lo, [(W_K, []), (W_V, []), (in_w, [slice(d, 2 * d), slice(2 * d, None)])])
+        # ---- weight-space folds (their epilogues also write the folded operand's lo)
         Wq_f = ops.gemm(in_w[:d], W_Q, torch.empty(d, C, dtype=_f32, device=dev))  # [d, C]
         Wkv_f = torch.empty(2 * d, de, dtype=_f32, device=dev)
-        ops.gemm(in_w[d:2 * d], W_K, Wkv_f[:d], lo=lo)
-        ops.gemm(in_w[2 * d:], W_V, Wkv_f[d:], lo=lo)
+        Wkv_f_lo = torch.empty(2 * d, ops.round_up(de, 4), dtype=_f32, device=dev)
+        ops.gemm(in_w[d:2 * d], W_K, Wkv_f[:d], lo=lo, emit_lo=Wkv_f_lo[:d])
+        ops.gemm(in_w[2 * d:], W_V, Wkv_f[d:], lo=lo, emit_lo=Wkv_f_lo[d:])
+        lo.put(Wkv_f, Wkv_f_lo)
         Wo_f = ops.gemm(W_r, out_w, torch.empty(C, d, dtype=_f32, device=dev))  # [C, d]
         bo_f = ops.gemm(out_b.view(1, d), W_r, torch.empty(1, C, dtype=_f32, device=dev), transB=True, bias=b_r).view(C)
         # ---- per-row work
@@ -283,9 +303,12 @@ class XAttnAddFn(torch.autograd.Function):
         ops.colsum(dq, out=d_in_b[:d])
         dY = ops.axpby(dY_out.view(B * T, C), 1.0 / (1.0 + kappa), new(B * T, C), False)
         ops.linear_dgrad(dq, Wq_f, out=dY, beta=1.0)
-        dWkv_f = ops.linear_wgrad(dkv, E2, lo=lo)  # [2d, de]
+        dWkv_f, dWkv_f_lo = new(2 * d, de), new(2 * d, ops.round_up(de, 4))
+        ops.linear_wgrad(dkv, E2, out=dWkv_f, lo=lo, emit_lo=dWkv_f_lo)  # [2d, de]; its halves feed the un-fold products
+        lo.put(dWkv_f[:d], dWkv_f_lo[:d])
+        lo.put(dWkv_f[d:], dWkv_f_lo[d:])
         ops.colsum(dkv, out=d_in_b[d:])
-        dE = ops.linear_dgrad(dkv, Wkv_f, lo=lo)
+        dE = ops.linear_dgrad(dkv, Wkv_f, lo=lo, emit_lo=True)  # handed to the TTF backward with its lo
         # ---- un-fold the weight gradients: W_f = W_a W_b  =>  dW_a = dW_f W_b^T, dW_b = W_a^T dW_f
         ops.gemm(dWq_f, W_Q, d_in_w[:d], transB=True)
         dW_Q = ops.gemm(in_w[:d], dWq_f, new(d, C), transA=True)

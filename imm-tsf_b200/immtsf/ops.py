@@ -147,10 +147,82 @@ class LoCache(dict):
             self[key] = e
         return e[1]
 
+    def put(self, t: torch.Tensor, lo: torch.Tensor):
+        """Register a lo that a producer kernel wrote together with t (GEMM epilogue, immtsf_gemm_ex C_lo).  Valid
+        for ragged and non-ragged consumers alike: rows past the ragged bound are never live in a product."""
+        for rg in (False, True):
+            self[(t.data_ptr(), tuple(t.shape), t.stride(0), rg)] = (t, lo)
+
+
+class StepCtx:
+    """What TTF and MMF share within one FusionModel step: the operand-split cache (so that E_txt / dE_txt, produced by
+    one module's GEMM epilogue together with their lo, are not split again by the other) and whether the MMF module
+    consumes E_txt with a tcgen05 product at all."""
+
+    def __init__(self, lo=None, e_txt_feeds_tc=False):
+        self.lo = lo if lo is not None else LoCache()
+        self.e_txt_feeds_tc = e_txt_feeds_tc
+
+
+_STEP: Optional[StepCtx] = None
+
+
+def begin_step(e_txt_feeds_tc: bool) -> StepCtx:
+    global _STEP
+    _STEP = StepCtx(e_txt_feeds_tc=e_txt_feeds_tc)
+    return _STEP
+
+
+def end_step():
+    global _STEP
+    _STEP = None
+
+
+def step_ctx() -> StepCtx:
+    """The step context opened by FusionModel.forward, or a private one for a module called on its own."""
+    return _STEP if _STEP is not None else StepCtx()
+
+
+def weight_los(lo: "LoCache", weights, extra_tasks=()):
+    """lo operands of a module's weight matrices in ONE launch (immtsf_multi_split) instead of one split per matrix.
+    weights: list of (W, [row slices that are used as operands on their own]).  extra_tasks: (src, hi, lo) copies that
+    ride along.  Returns the lo buffers in order."""
+    tasks, out = list(extra_tasks), []
+    for w, slices in weights:
+        buf = torch.empty(w.shape[0], round_up(w.shape[1], 4), dtype=torch.float32, device=w.device)
+        tasks.append((w, None, buf))
+        lo.put(w, buf)
+        for sl in slices:
+            lo.put(w[sl], buf[sl])
+        out.append(buf)
+    multi_split(tasks)
+    return out
+
+
+def multi_split(tasks):
+    """tasks: list of (src, hi_dst or None, lo_dst or None), 2-D row-major views (1-D = one row).  One launch per 16
+    tasks: hi_dst gets a copy of src, lo_dst gets src - trunc_tf32(src)."""
+    import ctypes as C
+
+    as2d = lambda t: t if t is None or t.dim() == 2 else t.view(1, -1)
+    for i0 in range(0, len(tasks), 16):
+        chunk = [(as2d(s), as2d(h), as2d(l)) for s, h, l in tasks[i0:i0 + 16]]
+        n = len(chunk)
+        for s, h, l in chunk:
+            _mat(s, "multi_split src")
+            assert (h is None or (h.stride(1) == 1 and h.shape == s.shape)) and (l is None or (l.stride(1) == 1 and l.shape[0] == s.shape[0]))
+        PA, IA = C.c_void_p * n, C.c_int * n
+        _lib.call("immtsf_multi_split", n, PA(*[s.data_ptr() for s, _, _ in chunk]), IA(*[s.stride(0) for s, _, _ in chunk]),
+                  IA(*[s.shape[0] for s, _, _ in chunk]), IA(*[s.shape[1] for s, _, _ in chunk]),
+                  PA(*[_p(h) for _, h, _ in chunk]), IA(*[h.stride(0) if h is not None else 0 for _, h, _ in chunk]),
+                  PA(*[_p(l) for _, _, l in chunk]), IA(*[l.stride(0) if l is not None else 0 for _, _, l in chunk]), _stream())
+
 
 def gemm(A, B, C, transA=False, transB=False, bias=None, alpha=1.0, beta=0.0, ragged=None, ragged_dim=0, backend=None,
-         lo: Optional[LoCache] = None):
-    """C[M,N] = alpha*op(A)*op(B) + beta*C + bias (shapes per include/immtsf.h)."""
+         lo: Optional[LoCache] = None, emit_lo=False):
+    """C[M,N] = alpha*op(A)*op(B) + beta*C + bias (shapes per include/immtsf.h).
+    emit_lo (needs lo): the epilogue also writes C - trunc_tf32(C) and registers it in the cache, for a C that is an
+    operand of a later tcgen05 product."""
     _mat(A, "A"), _mat(B, "B"), _mat(C, "C")
     M, N = C.shape
     K = A.shape[0] if transA else A.shape[1]
@@ -179,34 +251,43 @@ def gemm(A, B, C, transA=False, transB=False, bias=None, alpha=1.0, beta=0.0, ra
         b_ragged = ragged is not None and (ragged_dim == 2 and not transB)
         A_lo = lo.lo_for(A, ragged if a_ragged else None)
         B_lo = lo.lo_for(B, ragged if b_ragged else None)
+    C_lo = None
+    if isinstance(emit_lo, torch.Tensor):
+        C_lo = emit_lo  # caller-owned destination (a slice of a packed operand's lo); written by any backend
+    elif emit_lo and lo is not None and plan == 2:
+        # (ragged rows: pad rows inside touched tiles get lo = 0 like C; rows past them are never live in a product)
+        C_lo = torch.empty(M, round_up(N, 4), dtype=torch.float32, device=C.device)
     _lib.call("immtsf_gemm_ex", int(transA), int(transB), M, N, K, float(alpha), _p(A), A.stride(0), _p(A_lo),
               A_lo.stride(0) if A_lo is not None else 0, _p(B), B.stride(0), _p(B_lo), B_lo.stride(0) if B_lo is not None else 0,
-              float(beta), _p(C), C.stride(0), _p(bias), _p(ragged), ragged_dim, be, _p(ws), ws_bytes, _stream())
+              float(beta), _p(C), C.stride(0), _p(C_lo), C_lo.stride(0) if C_lo is not None else 0, _p(bias), _p(ragged),
+              ragged_dim, be, _p(ws), ws_bytes, _stream())
+    if C_lo is not None and lo is not None:
+        lo.put(C, C_lo)
     if prof is not None:
         ev1.record()
         prof.append(("gemm", (M, N, K, ragged_dim), ev0, ev1, plan))
     return C
 
 
-def linear_fwd(x, w, b, out=None, ragged=None, lo=None):
+def linear_fwd(x, w, b, out=None, ragged=None, lo=None, emit_lo=False):
     """out[M,N] = x[M,K] w[N,K]^T + b."""
     if out is None:
         out = torch.empty(x.shape[0], w.shape[0], dtype=torch.float32, device=x.device)
-    return gemm(x, w, out, transB=True, bias=b, ragged=ragged, ragged_dim=1 if ragged is not None else 0, lo=lo)
+    return gemm(x, w, out, transB=True, bias=b, ragged=ragged, ragged_dim=1 if ragged is not None else 0, lo=lo, emit_lo=emit_lo)
 
 
-def linear_dgrad(dy, w, out=None, ragged=None, beta=0.0, lo=None):
+def linear_dgrad(dy, w, out=None, ragged=None, beta=0.0, lo=None, emit_lo=False):
     """dx[M,K] = dy[M,N] w[N,K]."""
     if out is None:
         out = torch.empty(dy.shape[0], w.shape[1], dtype=torch.float32, device=dy.device)
-    return gemm(dy, w, out, beta=beta, ragged=ragged, ragged_dim=1 if ragged is not None else 0, lo=lo)
+    return gemm(dy, w, out, beta=beta, ragged=ragged, ragged_dim=1 if ragged is not None else 0, lo=lo, emit_lo=emit_lo)
 
 
-def linear_wgrad(dy, x, out=None, ragged=None, beta=0.0, lo=None):
+def linear_wgrad(dy, x, out=None, ragged=None, beta=0.0, lo=None, emit_lo=False):
     """dw[N,K] = dy[M,N]^T x[M,K]."""
     if out is None:
         out = torch.empty(dy.shape[1], x.shape[1], dtype=torch.float32, device=dy.device)
-    return gemm(dy, x, out, transA=True, beta=beta, ragged=ragged, ragged_dim=2 if ragged is not None else 0, lo=lo)
+    return gemm(dy, x, out, transA=True, beta=beta, ragged=ragged, ragged_dim=2 if ragged is not None else 0, lo=lo, emit_lo=emit_lo)
 
 
 def colsum(X, out=None, ragged=None, beta=0.0):
@@ -262,10 +343,10 @@ def recavg_pool_bwd(dE_drop, E_raw, mean, rstd, wsum, Vp, r: RaggedNotes, t_hat,
 
 
 # ------------------------------------------------------------------ Time2Vec / segment attention / LN
-def time2vec_fwd(r: RaggedNotes, w_lin, b_lin, w_per, b_per, d_tau, out_view):
-    """out_view: [M_alloc, d_tau] column slice of the concat buffer."""
+def time2vec_fwd(r: RaggedNotes, w_lin, b_lin, w_per, b_per, d_tau, out_view, lo_view=None):
+    """out_view: [M_alloc, d_tau] column slice of the concat buffer; lo_view: the same slice of its lo operand."""
     _lib.call("immtsf_time2vec_fwd", _p(r.tau_flat), _p(w_lin), _p(b_lin), _p(w_per), _p(b_per), d_tau, _p(out_view),
-              out_view.stride(0), _p(r.m_dev), r.M_alloc, _stream())
+              out_view.stride(0), _p(lo_view), lo_view.stride(0) if lo_view is not None else 0, _p(r.m_dev), r.M_alloc, _stream())
 
 
 def time2vec_bwd(dphi_view, r: RaggedNotes, w_per, b_per, d_tau):

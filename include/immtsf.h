@@ -104,16 +104,23 @@ size_t immtsf_gemm_workspace_bytes(int transA, int transB, int M, int N, int K);
 /* Same, with optional pre-split operands for the tcgen05 backend.  kind::tf32 reads fp32 containers and ignores
  * the low 13 mantissa bits, so the "hi" operand is the tensor itself; A_lo / B_lo = x - trunc_tf32(x) (from
  * immtsf_split_lo, same shape as the operand, leading dimension lda_lo / ldb_lo) let a caller that uses a tensor
- * in several products (forward, dgrad, wgrad) split it once.  NULL => split internally into the workspace. */
+ * in several products (forward, dgrad, wgrad) split it once.  NULL => split internally into the workspace.
+ * C_lo (nullable, leading dimension ldc_lo >= roundup(N,4), multiple of 4): second output, C - trunc_tf32(C),
+ * written by the epilogue that writes C, so that a product consuming C needs no split pass over it. */
 int immtsf_gemm_ex(int transA, int transB, int M, int N, int K, float alpha,
                    const float* A, int lda, const float* A_lo, int lda_lo,
                    const float* B, int ldb, const float* B_lo, int ldb_lo, float beta,
-                   float* C, int ldc, const float* bias, const int32_t* ragged,
-                   int ragged_dim, int backend, void* workspace, size_t workspace_bytes,
-                   void* stream);
+                   float* C, int ldc, float* C_lo, int ldc_lo, const float* bias,
+                   const int32_t* ragged, int ragged_dim, int backend, void* workspace,
+                   size_t workspace_bytes, void* stream);
 /* lo[rows][ld_lo] = src - trunc_tf32(src); rows bounded by roundup(*ragged,128) when ragged != NULL */
 int immtsf_split_lo(const float* src, int ld, int rows, int cols, float* lo, int ld_lo,
                     const int32_t* ragged, void* stream);
+/* One launch for up to 16 small tensors (a module's weight matrices): task i reads src[i] (rows[i] x cols[i],
+ * leading dimension ld_src[i]) and writes a plain copy to hi[i] (nullable: e.g. a slice of a packed operand) and
+ * src - trunc_tf32(src) to lo[i] (nullable).  The arrays are host arrays of length n. */
+int immtsf_multi_split(int n, const float* const* src, const int* ld_src, const int* rows, const int* cols,
+                       float* const* hi, const int* ld_hi, float* const* lo, const int* ld_lo, void* stream);
 /* kernel family immtsf_gemm would pick for this call: 1 FFMA, 2 tcgen05, 3 skinny streaming kernels */
 int immtsf_gemm_plan(int transA, int transB, int M, int N, int K, const float* A, int lda,
                      const float* B, int ldb, const float* C, int ldc, int backend);
@@ -143,10 +150,11 @@ int immtsf_recavg_pool_bwd(const float* dE_drop, const float* E_raw, const float
                            float* dbeta, double* dlog_sigma, void* stream);
 
 /* ---- Time2Vec (TTF_T2V_XAttn.py:20-24,136) written straight into the
- * [V' ; phi] concat buffer (:139) ---------------------------------------- */
+ * [V' ; phi] concat buffer (:139); out_lo (nullable): phi - trunc_tf32(phi) into the
+ * matching columns of that buffer's tcgen05 lo operand ------------------- */
 int immtsf_time2vec_fwd(const float* tau_flat, const float* w_lin, const float* b_lin, const float* w_per,
-                        const float* b_per, int d_tau, float* out, int ld, const int32_t* m_dev,
-                        int M_alloc, void* stream);
+                        const float* b_per, int d_tau, float* out, int ld, float* out_lo, int ld_lo,
+                        const int32_t* m_dev, int M_alloc, void* stream);
 int immtsf_time2vec_bwd(const float* dphi, int ld, const float* tau_flat, const float* w_per,
                         const float* b_per, int d_tau, float* dw_lin, float* db_lin, float* dw_per,
                         float* db_per, const int32_t* m_dev, int M_alloc, void* stream);
