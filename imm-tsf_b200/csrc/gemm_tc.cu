@@ -241,17 +241,20 @@ __device__ __forceinline__ void epilogue_store(const float (&acc)[128], uint32_t
   }
 }
 
-template <bool A_MN, bool B_MN, int BN>
-__global__ void __launch_bounds__(Cfg<BN>::THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
-               const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl, const TcArgs g) {
+// One CTA = one BM x BN output tile (tile_m, tile_n).  A_MN / B_MN are compile-time constants in gemm_tc_kernel and
+// run-time values in the grouped kernel (they only select descriptor bits and TMA box coordinates).
+template <int BN>
+__device__ __forceinline__ void tc_cta(const CUtensorMap* pAh, const CUtensorMap* pAl, const CUtensorMap* pBh,
+                                       const CUtensorMap* pBl, const TcArgs& g, const bool A_MN, const bool B_MN,
+                                       const int tile_m, const int tile_n, const int nsplit, const int zsplit, const int bz1,
+                                       const int bz2) {
   using C_ = Cfg<BN>;
   constexpr int STAGES = C_::STAGES, STAGE_BYTES = C_::STAGE_BYTES, TILE_B = C_::TILE_B, NACC = C_::NACC;
   extern __shared__ uint8_t smem_raw[];
   int M = g.M, K = g.K;
   if (g.ragged_dim == 1) M = ragged_rows(M, g.ragged);
   if (g.ragged_dim == 2) K = ragged_rows(K, g.ragged);
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int m0 = tile_m * BM, n0 = tile_n * BN;
   if (g.ragged_dim == 1 && m0 >= M) return;  // whole tile beyond the ragged end (uniform per CTA)
   const int nkb = (K + BKT - 1) / BKT;
 
@@ -259,17 +262,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
   const uint32_t bars = base + STAGES * STAGE_BYTES;  // full[STAGES], empty[STAGES], tfull[2], tempty[2], tmem_ptr
   const uint32_t bar_full = bars, bar_empty = bars + 8 * STAGES, bar_tfull = bars + 16 * STAGES;
   const uint32_t bar_tempty = bar_tfull + 16, tmem_slot = bar_tempty + 16;
-  // split-K: blockIdx.z owns a contiguous range of k-blocks (partial tiles are summed by splitk_reduce_kernel);
-  // batched: blockIdx.z is the batch index and every CTA runs the whole contraction
-  const int nsplit = g.batched ? 1 : (int)gridDim.z, zsplit = g.batched ? 0 : (int)blockIdx.z;
-  const int bz1 = g.batched ? (int)blockIdx.z / g.batch2 : 0, bz2 = g.batched ? (int)blockIdx.z % g.batch2 : 0;
   const int kb_per = (nkb + nsplit - 1) / nsplit;
   const int z_kb0 = min(nkb, zsplit * kb_per), z_kb1 = min(nkb, z_kb0 + kb_per);
   const int nchunks = (z_kb1 - z_kb0 + KC - 1) / KC;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {  // hide the descriptor fetch behind the barrier / TMEM set-up
-    prefetch_tmap(&mapAh); prefetch_tmap(&mapAl); prefetch_tmap(&mapBh); prefetch_tmap(&mapBl);
+    prefetch_tmap(pAh); prefetch_tmap(pAl); prefetch_tmap(pBh); prefetch_tmap(pBl);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -307,23 +306,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
       mbar_expect_tx(fb, STAGE_BYTES);
       const int k0 = kb * BKT;
       if (!A_MN) {
-        tma_tile(sa_h, &mapAh, fb, k0, m0, g.batched, bz2, bz1);
-        tma_tile(sa_l, &mapAl, fb, k0, m0, g.batched, bz2, bz1);
+        tma_tile(sa_h, pAh, fb, k0, m0, g.batched, bz2, bz1);
+        tma_tile(sa_l, pAl, fb, k0, m0, g.batched, bz2, bz1);
       } else {
 #pragma unroll
         for (int j = 0; j < BM / 32; ++j) {
-          tma_tile(sa_h + j * 4096, &mapAh, fb, m0 + 32 * j, k0, g.batched, bz2, bz1);
-          tma_tile(sa_l + j * 4096, &mapAl, fb, m0 + 32 * j, k0, g.batched, bz2, bz1);
+          tma_tile(sa_h + j * 4096, pAh, fb, m0 + 32 * j, k0, g.batched, bz2, bz1);
+          tma_tile(sa_l + j * 4096, pAl, fb, m0 + 32 * j, k0, g.batched, bz2, bz1);
         }
       }
       if (!B_MN) {
-        tma_tile(sb_h, &mapBh, fb, k0, n0, g.batched, bz2, bz1);
-        tma_tile(sb_l, &mapBl, fb, k0, n0, g.batched, bz2, bz1);
+        tma_tile(sb_h, pBh, fb, k0, n0, g.batched, bz2, bz1);
+        tma_tile(sb_l, pBl, fb, k0, n0, g.batched, bz2, bz1);
       } else {
 #pragma unroll
         for (int j = 0; j < BN / 32; ++j) {
-          tma_tile(sb_h + j * 4096, &mapBh, fb, n0 + 32 * j, k0, g.batched, bz2, bz1);
-          tma_tile(sb_l + j * 4096, &mapBl, fb, n0 + 32 * j, k0, g.batched, bz2, bz1);
+          tma_tile(sb_h + j * 4096, pBh, fb, n0 + 32 * j, k0, g.batched, bz2, bz1);
+          tma_tile(sb_l + j * 4096, pBl, fb, n0 + 32 * j, k0, g.batched, bz2, bz1);
         }
       }
     }
@@ -412,6 +411,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant_
   if (warp == 2) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS));
   }
+}
+
+
+template <bool A_MN, bool B_MN, int BN>
+__global__ void __launch_bounds__(Cfg<BN>::THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
+               const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl, const TcArgs g) {
+  // split-K: blockIdx.z owns a contiguous range of k-blocks (partial tiles are summed by splitk_reduce_kernel);
+  // batched: blockIdx.z is the batch index and every CTA runs the whole contraction
+  const int nsplit = g.batched ? 1 : (int)gridDim.z, zsplit = g.batched ? 0 : (int)blockIdx.z;
+  const int bz1 = g.batched ? (int)blockIdx.z / g.batch2 : 0, bz2 = g.batched ? (int)blockIdx.z % g.batch2 : 0;
+  tc_cta<BN>(&mapAh, &mapAl, &mapBh, &mapBl, g, A_MN, B_MN, (int)blockIdx.y, (int)blockIdx.x, nsplit, zsplit, bz1, bz2);
+}
+
+// Grouped launch: up to GRP_MAX independent small products (the d x d x d weight-space folds and un-folds, which are
+// too small to fill the GPU one at a time) as ONE grid; blockIdx.z = problem, 128 x 128 tiles, no split-K.
+constexpr int GRP_MAX = 4;
+struct GroupArgs {
+  CUtensorMap maps[GRP_MAX][4];  // A, A_lo, B, B_lo
+  TcArgs g[GRP_MAX];
+  int a_mn[GRP_MAX], b_mn[GRP_MAX];
+};
+__global__ void __launch_bounds__(Cfg<128>::THREADS, 1) gemm_tc_group_kernel(const __grid_constant__ GroupArgs grp) {
+  const int p = blockIdx.z;
+  const TcArgs& g = grp.g[p];
+  if ((int)blockIdx.y * BM >= g.M || (int)blockIdx.x * 128 >= g.N) return;  // this problem has fewer tiles (uniform per CTA)
+  tc_cta<128>(&grp.maps[p][0], &grp.maps[p][1], &grp.maps[p][2], &grp.maps[p][3], g, grp.a_mn[p] != 0, grp.b_mn[p] != 0,
+              (int)blockIdx.y, (int)blockIdx.x, 1, 0, 0, 0);
 }
 
 // ---------------------------------------------------------------- CTA-pair variant (cta_group::2)
@@ -821,10 +848,24 @@ inline int choose_splitk(int M, int N, int K, int v) {
   return splitk;
 }
 
-// Variant: estimated time = waves x k-blocks per CTA x operand bytes per k-block per CTA (the kernel is bound by
-// L2->SM operand bandwidth): 64 KiB for a 128x128 tile, 96 KiB for 128x256, 64 KiB for the 128x256 half of a pair.
-// IMMTSF_TC_BN=128|256|512 forces one variant (512 = pairs; tests, experiments).
-inline int choose_variant(int M, int N, int K) {
+// Expected fraction of live rows of a ragged operand (the true count lives on the device and is never read back):
+// Time-IMM-like batches hold U{1..N_max} notes per sample.  IMMTSF_RAGGED_FILL overrides it.
+inline double ragged_fill() {
+  static double f = -1.0;
+  if (f < 0.0) {
+    const char* e = getenv("IMMTSF_RAGGED_FILL");
+    f = e ? atof(e) : 0.6;
+    if (!(f > 0.0 && f <= 1.0)) f = 0.6;
+  }
+  return f;
+}
+
+// Variant: estimated clocks = waves x (k-blocks per CTA x clocks per k-block + fixed prologue/epilogue), where a
+// k-block costs the larger of its tensor time (768 clk for a 128x128 tile, 1536 for 128x256) and the time the L2
+// needs to feed every co-resident CTA (64 / 96 / 64 KiB per k-block; ~6300 B/clk chip-wide).  Measured with
+// immtsf_gemm_trace: ~15 k clocks of prologue + epilogue per CTA.  IMMTSF_TC_BN=128|256|512 forces one variant
+// (512 = pairs; tests, experiments).  ragged_dim: the bound is device-resident, so the estimate uses ragged_fill().
+inline int choose_variant(int M, int N, int K, int ragged_dim = 0) {
   static int forced = -1;
   if (forced < 0) {
     const char* e = getenv("IMMTSF_TC_BN");
@@ -834,16 +875,21 @@ inline int choose_variant(int M, int N, int K) {
   if (forced == 256) return V256;
   if (forced == 512) return VPAIR;
   if (N <= 128) return V128;
+  const int Me = ragged_dim == 1 ? max(BM, (int)(M * ragged_fill())) : M;
+  const int Ke = ragged_dim == 2 ? max(BKT, (int)(K * ragged_fill())) : K;
   double best = 0.0;
   int best_v = V128;
   for (int v = 0; v < 3; ++v) {
     if (v == VPAIR && M <= BM) continue;
-    const int sk = choose_splitk(M, N, K, v);
-    const long ctas = tile_ctas(M, N, v) * sk;
+    const int sk = choose_splitk(M, N, K, v);  // (the launch uses the allocated extent)
+    const long ctas = tile_ctas(Me, N, v) * sk;
     const double waves = (double)((ctas + 147) / 148);
-    // + fixed prologue/epilogue cost per tile, + the partial-tile round trip and reduce launch of split-K
-    const double kb = (double)ceil_div(ceil_div(K, BKT), sk) + (v == VPAIR ? 7.0 : 6.0) + (sk > 1 ? 8.0 : 0.0);
-    const double cost = waves * kb * (v == V256 ? 96.0 : 64.0);
+    const double resident = (double)(ctas < 148 ? ctas : 148);
+    const double tens = v == V128 ? 768.0 : 1536.0, kib = v == V256 ? 96.0 : 64.0;
+    const double feed = resident * kib * 1024.0 / 6300.0;
+    const double t_kb = tens > feed ? tens : feed;
+    const double cost = waves * ((double)ceil_div(ceil_div(Ke, BKT), sk) * t_kb + (v == VPAIR ? 16000.0 : 15000.0)) +
+                        (sk > 1 ? 9000.0 : 0.0);  // + the partial-tile round trip and reduce launch of split-K
     if (v == 0 || cost < best) { best = cost; best_v = v; }
   }
   return best_v;
@@ -901,7 +947,8 @@ extern "C" int immtsf_profile_end(int* M, int* N, int* K, int* ragged_dim, float
 size_t immtsf_gemm_tc_workspace(int transA, int transB, int M, int N, int K) {
   const size_t ra = transA ? K : M, ca = transA ? M : K, rb = transB ? N : K, cb = transB ? K : N;
   const size_t a = align_up(ra * align_up(ca, 4) * 4, 256), b = align_up(rb * align_up(cb, 4) * 4, 256);
-  const int sk = choose_splitk(M, N, K, choose_variant(M, N, K));
+  int sk = 1;  // the variant depends on ragged_dim, which this query does not know: size for the largest split
+  for (int v = 0; v < 3; ++v) sk = max(sk, choose_splitk(M, N, K, v));
   const size_t p = sk > 1 ? align_up((size_t)sk * M * align_up(N, 4) * 4, 256) : 0;
   return a + b + p + 256;
 }
@@ -976,7 +1023,7 @@ int immtsf_gemm_tc(int transA, int transB, int M, int N, int K, float alpha, con
     return IMMTSF_ERR_ARG;
   }
   const size_t need = immtsf_gemm_tc_workspace(transA, transB, M, N, K);
-  if (workspace == nullptr || workspace_bytes < need) {
+  if (workspace == nullptr || workspace_bytes < need) {  // (an upper bound over the variants)
     immtsf_set_error("gemm_tc: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
     return IMMTSF_ERR_ARG;
   }
@@ -1004,7 +1051,7 @@ int immtsf_gemm_tc(int transA, int transB, int M, int N, int K, float alpha, con
   }
   CUtensorMap mAh, mAl, mBh, mBl;
   // K-major operand [rows=MN][cols=K]: box 32 x 128 (or 256) ; MN-major operand [rows=K][cols=MN]: box 32 x 32
-  const int variant = choose_variant(M, N, K);
+  const int variant = choose_variant(M, N, K, ragged_dim);
   const int bn = variant_bn(variant);
   // pairs: every CTA fetches its own 128-column half of B
   const int boxA = transA ? 32 : BM, boxB = transB ? (variant == VPAIR ? Cfg2::BNH : bn) : 32;
@@ -1065,6 +1112,57 @@ int immtsf_gemm_tc(int transA, int transB, int M, int N, int K, float alpha, con
   return IMMTSF_OK;
 }
 
+
+// ---------------------------------------------------------------- grouped products
+// n <= 4 independent products C_i = alpha_i op(A_i) op(B_i) + beta_i C_i in one launch (see gemm_tc_group_kernel).
+// Every operand comes with its lo part (immtsf_split_lo / a producer's C_lo); C_lo[i] (nullable) as in immtsf_gemm_ex.
+extern "C" int immtsf_gemm_group(int n, const int* transA, const int* transB, const int* M, const int* N, const int* K,
+                                 const float* alpha, const float* const* A, const float* const* A_lo, const int* lda,
+                                 const int* lda_lo, const float* const* B, const float* const* B_lo, const int* ldb,
+                                 const int* ldb_lo, const float* beta, float* const* C, const int* ldc, float* const* C_lo,
+                                 const int* ldc_lo, void* stream) {
+  if (n == 0) return IMMTSF_OK;
+  IMMTSF_REQUIRE(n > 0 && n <= GRP_MAX, "gemm_group: 1..4 problems per call");
+  IMMTSF_REQUIRE(get_encode() != nullptr, "gemm_group: cuTensorMapEncodeTiled unavailable");
+  GroupArgs grp;
+  int gx = 1, gy = 1;
+  for (int i = 0; i < n; ++i) {
+    IMMTSF_REQUIRE(M[i] > 0 && N[i] > 0 && K[i] > 0 && A[i] && A_lo[i] && B[i] && B_lo[i] && C[i], "gemm_group: bad problem %d", i);
+    IMMTSF_REQUIRE(immtsf_gemm_tc_eligible(1, M[i], N[i], K[i], A[i], lda[i], B[i], ldb[i], C[i], ldc[i]) &&
+                       ((uintptr_t)A_lo[i] & 15) == 0 && (lda_lo[i] & 3) == 0 && ((uintptr_t)B_lo[i] & 15) == 0 && (ldb_lo[i] & 3) == 0,
+                   "gemm_group: problem %d: operands must be 16B aligned with leading dimensions %% 4 == 0", i);
+    IMMTSF_REQUIRE(C_lo[i] == nullptr || (((uintptr_t)C_lo[i] & 15) == 0 && (ldc_lo[i] & 3) == 0 && ldc_lo[i] >= (int)align_up(N[i], 4)),
+                   "gemm_group: problem %d: bad C_lo", i);
+    const int tA = transA[i], tB = transB[i];
+    const int ra = tA ? K[i] : M[i], ca = tA ? M[i] : K[i], rb = tB ? N[i] : K[i], cb = tB ? K[i] : N[i];
+    const int boxA = tA ? 32 : BM, boxB = tB ? 128 : 32;
+    if (make_map(&grp.maps[i][0], A[i], ra, ca, lda[i], boxA, tA != 0) || make_map(&grp.maps[i][1], A_lo[i], ra, ca, lda_lo[i], boxA, tA != 0) ||
+        make_map(&grp.maps[i][2], B[i], rb, cb, ldb[i], boxB, tB == 0) || make_map(&grp.maps[i][3], B_lo[i], rb, cb, ldb_lo[i], boxB, tB == 0)) {
+      immtsf_set_error("gemm_group: cuTensorMapEncodeTiled failed (problem %d)", i);
+      return IMMTSF_ERR_LAUNCH;
+    }
+    TcArgs& g = grp.g[i];
+    g.C = C[i]; g.ldc = ldc[i]; g.M = M[i]; g.N = N[i]; g.K = K[i]; g.alpha = alpha[i]; g.beta = beta[i]; g.bias = nullptr;
+    g.ragged = nullptr; g.ragged_dim = 0; g.partial = nullptr; g.ldp = 0;
+    g.batched = 0; g.batch2 = 1; g.c_s1 = 0; g.c_s2 = 0; g.trace = nullptr; g.C_lo = C_lo[i]; g.ldc_lo = ldc_lo[i];
+    grp.a_mn[i] = tA ? 1 : 0;   // UMMA "A is MN-major" = stored [K][M]
+    grp.b_mn[i] = tB ? 0 : 1;   // UMMA "B is K-major" = stored [N][K] = transB
+    gx = max(gx, ceil_div(N[i], 128));
+    gy = max(gy, ceil_div(M[i], BM));
+  }
+  for (int i = n; i < GRP_MAX; ++i) {
+    for (int j = 0; j < 4; ++j) grp.maps[i][j] = grp.maps[0][j];
+    grp.g[i] = grp.g[0]; grp.a_mn[i] = grp.a_mn[0]; grp.b_mn[i] = grp.b_mn[0];
+  }
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(gemm_tc_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128>::SMEM_BYTES);
+    attr_done = true;
+  }
+  gemm_tc_group_kernel<<<dim3(gx, gy, n), Cfg<128>::THREADS, Cfg<128>::SMEM_BYTES, (cudaStream_t)stream>>>(grp);
+  IMMTSF_CHECK_LAUNCH("gemm_tc_group");
+  return IMMTSF_OK;
+}
 
 // ---------------------------------------------------------------- batched products (attention contractions)
 // C(b1,b2)[M,N] = alpha * op(A(b1,b2)) op(B(b1,b2)) + beta * C(b1,b2), X(b1,b2) = X + b1*x_s1 + b2*x_s2 (element strides).

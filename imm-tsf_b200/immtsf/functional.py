@@ -165,9 +165,10 @@ class T2VXAttnFn(torch.autograd.Function):
             d_in_w[d:2 * d].copy_(dWkv[:d])
             d_in_b[d:2 * d].copy_(dbkv[:d])
             # un-fold W_f = W_o W_v, b_f = W_o b_v
-            dW_o = ops.gemm(dWkv[d:], in_w[2 * d:], new(d, d), transB=True, lo=lo)
+            dW_o = new(d, d)
+            ops.gemm_group([dict(A=dWkv[d:], B=in_w[2 * d:], C=dW_o, transB=True),
+                            dict(A=out_w, B=dWkv[d:], C=d_in_w[2 * d:], transA=True)], lo)
             ops.gemm(dbkv[d:].view(d, 1), in_b[2 * d:].view(1, d), dW_o, beta=1.0)
-            ops.gemm(out_w, dWkv[d:], d_in_w[2 * d:], transA=True, lo=lo)
             ops.gemm(dbkv[d:].view(1, d), out_w, d_in_b[2 * d:].view(1, d))
         else:
             ops.linear_wgrad(dKVp, X, out=d_in_w[d:], ragged=r.m_dev, lo=lo)
@@ -263,8 +264,8 @@ class XAttnAddFn(torch.autograd.Function):
         Wq_f = ops.gemm(in_w[:d], W_Q, torch.empty(d, C, dtype=_f32, device=dev))  # [d, C]
         Wkv_f = torch.empty(2 * d, de, dtype=_f32, device=dev)
         Wkv_f_lo = torch.empty(2 * d, ops.round_up(de, 4), dtype=_f32, device=dev)
-        ops.gemm(in_w[d:2 * d], W_K, Wkv_f[:d], lo=lo, emit_lo=Wkv_f_lo[:d])
-        ops.gemm(in_w[2 * d:], W_V, Wkv_f[d:], lo=lo, emit_lo=Wkv_f_lo[d:])
+        ops.gemm_group([dict(A=in_w[d:2 * d], B=W_K, C=Wkv_f[:d], emit_lo=Wkv_f_lo[:d]),
+                        dict(A=in_w[2 * d:], B=W_V, C=Wkv_f[d:], emit_lo=Wkv_f_lo[d:])], lo)  # one launch
         lo.put(Wkv_f, Wkv_f_lo)
         Wo_f = ops.gemm(W_r, out_w, torch.empty(C, d, dtype=_f32, device=dev))  # [C, d]
         bo_f = ops.gemm(out_b.view(1, d), W_r, torch.empty(1, C, dtype=_f32, device=dev), transB=True, bias=b_r).view(C)
@@ -312,10 +313,11 @@ class XAttnAddFn(torch.autograd.Function):
         # ---- un-fold the weight gradients: W_f = W_a W_b  =>  dW_a = dW_f W_b^T, dW_b = W_a^T dW_f
         ops.gemm(dWq_f, W_Q, d_in_w[:d], transB=True)
         dW_Q = ops.gemm(in_w[:d], dWq_f, new(d, C), transA=True)
-        ops.gemm(dWkv_f[:d], W_K, d_in_w[d:2 * d], transB=True, lo=lo)
-        dW_K = ops.gemm(in_w[d:2 * d], dWkv_f[:d], new(d, de), transA=True, lo=lo)
-        ops.gemm(dWkv_f[d:], W_V, d_in_w[2 * d:], transB=True, lo=lo)
-        dW_V = ops.gemm(in_w[2 * d:], dWkv_f[d:], new(d, de), transA=True, lo=lo)
+        dW_K, dW_V = new(d, de), new(d, de)
+        ops.gemm_group([dict(A=dWkv_f[:d], B=W_K, C=d_in_w[d:2 * d], transB=True),
+                        dict(A=in_w[d:2 * d], B=dWkv_f[:d], C=dW_K, transA=True),
+                        dict(A=dWkv_f[d:], B=W_V, C=d_in_w[2 * d:], transB=True),
+                        dict(A=in_w[2 * d:], B=dWkv_f[d:], C=dW_V, transA=True)], lo)  # the four un-folds, one launch
         dW_r = ops.gemm(dWo_f, out_w, new(C, d), transB=True)
         ops.gemm(db_r.view(C, 1), out_b.view(1, d), dW_r, beta=1.0)  # bo_f = W_r b_o + b_r also depends on W_r
         dW_o = ops.gemm(W_r, dWo_f, new(d, d), transA=True)

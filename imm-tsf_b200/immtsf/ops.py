@@ -269,6 +269,45 @@ def gemm(A, B, C, transA=False, transB=False, bias=None, alpha=1.0, beta=0.0, ra
     return C
 
 
+def gemm_group(problems, lo: LoCache):
+    """Independent products in one launch (immtsf_gemm_group).  problems: dicts with A, B, C and optional transA,
+    transB, alpha, beta, emit_lo (a tensor: destination of C's lo).  Falls back to one immtsf_gemm_ex per product when
+    a shape is not eligible for the tcgen05 kernel (tiny test sizes)."""
+    import ctypes as C_
+
+    lib = _lib.load()
+    norm = []
+    for pr in problems:
+        A, B, C = _mat(pr["A"], "A"), _mat(pr["B"], "B"), _mat(pr["C"], "C")
+        tA, tB = bool(pr.get("transA", False)), bool(pr.get("transB", False))
+        M, N = C.shape
+        K = A.shape[0] if tA else A.shape[1]
+        assert tuple(A.shape) == ((K, M) if tA else (M, K)) and tuple(B.shape) == ((N, K) if tB else (K, N)), "gemm_group: shape mismatch"
+        norm.append((A, B, C, tA, tB, M, N, K, float(pr.get("alpha", 1.0)), float(pr.get("beta", 0.0)), pr.get("emit_lo")))
+    ok = all(lib.immtsf_gemm_plan(int(tA), int(tB), M, N, K, _p(A), A.stride(0), _p(B), B.stride(0), _p(C), C.stride(0),
+                                  gemm_backend()) == 2 for (A, B, C, tA, tB, M, N, K, _, _, _) in norm)
+    if not ok or gemm_backend() == BACKEND_FFMA:
+        for (A, B, C, tA, tB, M, N, K, al, be, el) in norm:
+            gemm(A, B, C, transA=tA, transB=tB, alpha=al, beta=be, lo=lo, emit_lo=el if el is not None else False)
+        return
+    for i0 in range(0, len(norm), 4):
+        ch = norm[i0:i0 + 4]
+        n = len(ch)
+        Alo = [lo.lo_for(c[0], None) for c in ch]
+        Blo = [lo.lo_for(c[1], None) for c in ch]
+        IA, FA, PA = C_.c_int * n, C_.c_float * n, C_.c_void_p * n
+        _lib.call("immtsf_gemm_group", n, IA(*[int(c[3]) for c in ch]), IA(*[int(c[4]) for c in ch]), IA(*[c[5] for c in ch]),
+                  IA(*[c[6] for c in ch]), IA(*[c[7] for c in ch]), FA(*[c[8] for c in ch]),
+                  PA(*[c[0].data_ptr() for c in ch]), PA(*[t.data_ptr() for t in Alo]), IA(*[c[0].stride(0) for c in ch]),
+                  IA(*[t.stride(0) for t in Alo]), PA(*[c[1].data_ptr() for c in ch]), PA(*[t.data_ptr() for t in Blo]),
+                  IA(*[c[1].stride(0) for c in ch]), IA(*[t.stride(0) for t in Blo]), FA(*[c[9] for c in ch]),
+                  PA(*[c[2].data_ptr() for c in ch]), IA(*[c[2].stride(0) for c in ch]),
+                  PA(*[_p(c[10]) for c in ch]), IA(*[c[10].stride(0) if c[10] is not None else 0 for c in ch]), _stream())
+        for c in ch:
+            if c[10] is not None:
+                lo.put(c[2], c[10])
+
+
 def linear_fwd(x, w, b, out=None, ragged=None, lo=None, emit_lo=False):
     """out[M,N] = x[M,K] w[N,K]^T + b."""
     if out is None:

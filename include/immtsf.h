@@ -116,6 +116,15 @@ int immtsf_gemm_ex(int transA, int transB, int M, int N, int K, float alpha,
 /* lo[rows][ld_lo] = src - trunc_tf32(src); rows bounded by roundup(*ragged,128) when ragged != NULL */
 int immtsf_split_lo(const float* src, int ld, int rows, int cols, float* lo, int ld_lo,
                     const int32_t* ragged, void* stream);
+/* Up to 4 independent products C_i = alpha_i * op(A_i) op(B_i) + beta_i * C_i in ONE launch (the d x d x d
+ * weight-space folds / un-folds of MMF_XAttn_Add and TTF_T2V_XAttn, each too small to fill the GPU).  tcgen05 3xTF32,
+ * 128 x 128 tiles, no bias / ragged bounds / split-K.  Every operand comes with its lo part; C_lo[i] (nullable) is the
+ * second output of immtsf_gemm_ex.  All arrays are host arrays of length n. */
+int immtsf_gemm_group(int n, const int* transA, const int* transB, const int* M, const int* N, const int* K,
+                      const float* alpha, const float* const* A, const float* const* A_lo, const int* lda,
+                      const int* lda_lo, const float* const* B, const float* const* B_lo, const int* ldb,
+                      const int* ldb_lo, const float* beta, float* const* C, const int* ldc, float* const* C_lo,
+                      const int* ldc_lo, void* stream);
 /* One launch for up to 16 small tensors (a module's weight matrices): task i reads src[i] (rows[i] x cols[i],
  * leading dimension ld_src[i]) and writes a plain copy to hi[i] (nullable: e.g. a slice of a packed operand) and
  * src - trunc_tf32(src) to lo[i] (nullable).  The arrays are host arrays of length n. */

@@ -105,3 +105,48 @@ def test_gemm_tc_both_tile_widths(bn):
                        capture_output=True, text=True, timeout=280)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     assert f"OK IMMTSF_TC_BN={bn}" in r.stdout
+
+
+@pytest.mark.timeout(120)
+def test_gemm_group_mixed_transpositions_and_shapes():
+    """immtsf_gemm_group: four products of different shapes / transpositions in one launch, with beta and C_lo."""
+    from immtsf import ops
+
+    g = torch.Generator().manual_seed(31)
+    lo = ops.LoCache()
+    specs = [(768, 768, 768, 0, 0), (768, 640, 256, 0, 1), (384, 768, 512, 1, 0), (256, 384, 768, 1, 1)]
+    probs, refs, los = [], [], []
+    for (M, N, K, tA, tB) in specs:
+        A = torch.randn((K, M) if tA else (M, K), generator=g).cuda()
+        B = (torch.randn((N, K) if tB else (K, N), generator=g) * 0.3).cuda()
+        C = torch.randn(M, N, generator=g).cuda()
+        C_lo = torch.empty(M, N, device="cuda")
+        refs.append(0.5 * _ref(A.cpu(), B.cpu(), tA, tB) + 2.0 * C.double().cpu())
+        probs.append(dict(A=A, B=B, C=C, transA=bool(tA), transB=bool(tB), alpha=0.5, beta=2.0, emit_lo=C_lo))
+        los.append(C_lo)
+    ops.gemm_group(probs, lo)
+    torch.cuda.synchronize()
+    for pr, ref, C_lo in zip(probs, refs, los):
+        G.assert_close("gemm_group", pr["C"].cpu(), ref, TOL)
+        hi = (pr["C"].view(torch.int32) & -8192).view(torch.float32)
+        assert torch.equal(C_lo, pr["C"] - hi)
+
+
+@pytest.mark.timeout(120)
+def test_gemm_emits_lo_of_its_output():
+    """immtsf_gemm_ex C_lo (plain, split-K and ragged launches): exactly C - trunc_tf32(C)."""
+    from immtsf import ops
+
+    g = torch.Generator().manual_seed(32)
+    for (M, N, K, tA, tB, ragged) in [(6144, 768, 768, 0, 1, None), (768, 768, 6144, 1, 0, None), (640, 256, 128, 0, 1, 300)]:
+        lo = ops.LoCache()
+        A = torch.randn((K, M) if tA else (M, K), generator=g).cuda()
+        B = torch.randn((N, K) if tB else (K, N), generator=g).cuda()
+        C = torch.empty(M, N, device="cuda")
+        rg = None if ragged is None else torch.tensor([ragged], dtype=torch.int32, device="cuda")
+        ops.gemm(A, B, C, transA=bool(tA), transB=bool(tB), ragged=rg, ragged_dim=1 if rg is not None else 0, backend=ops.BACKEND_TC,
+                 lo=lo, emit_lo=True)
+        C_lo = lo.lo_for(C, None)
+        rows = M if ragged is None else 384
+        hi = (C[:rows].view(torch.int32) & -8192).view(torch.float32)
+        assert torch.equal(C_lo[:rows], C[:rows] - hi)
