@@ -63,8 +63,9 @@ DROPOUT = 0.1
 # dram__bytes_read.sum + dram__bytes_write.sum of one gemm_tc_kernel<.,.,256> launch (M6144 N768 K768) from the
 # ncu --set full capture in profiles/r1_ncu_gemm_tc_bn256_summary.txt; algorithmic operand bytes of that launch:
 # 42.5 MB (A, A_lo, B, B_lo; the 18.9 MB output stays in the 126 MB L2)
-TRAFFIC_NCU = 42.9e6
-TRAFFIC_NOTE = "bytes per launch, M6144 N768 K768, profiles/r1_ncu_gemm_tc_bn256_summary.txt (algorithmic operand bytes 42.5e6)"
+TRAFFIC_NCU = 43.5e6
+TRAFFIC_NOTE = ("bytes per launch of gemm_tc2_kernel, M6144 N768 K768, cold L2: dram read 42.63 MB + write 0.85 MB, "
+                "profiles/r1_ncu_gemm_tc2_pair_summary.txt (algorithmic operand bytes 42.5e6; the 18.9 MB output stays in L2)")
 METRIC = "fused TTF+MMF fwd+bwd throughput"
 UNIT = "samples/s"
 
@@ -188,7 +189,7 @@ class ClockSampler:
     def start(self):
         try:
             self.f = open(self.path, "w")
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "25",
                                           "-i", str(self.dev)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -280,6 +281,29 @@ def run_gpu_arm(args, w):
             total_ms += e0.elapsed_time(e1)
         return total_ms
 
+    def timed_prefetched(n, graphed):
+        """e2e with the double-buffered input pipeline (GraphedStep.prefetch): inside step i's timed region the H2D of
+        step i+1's inputs runs on the copy stream next to step i's kernels, and step i waits for its own inputs, copied
+        during step i-1.  Every timed region thus contains one full H2D and the D2H of its loss.  `hidden` counts
+        the regions whose H2D had NOT landed when the region closed (it would then have run in the untimed flush gap)."""
+        total_ms, hidden = 0.0, 0
+        graphed.prefetch(*h_in)
+        torch.cuda.synchronize()
+        for _ in range(n):
+            flush.fill_(1.0)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            loss = graphed.step_prefetched()
+            graphed.prefetch(*h_in)  # next step's inputs, overlapping this step
+            if world > 1 and graphed.group is None:
+                dp.allreduce_grads(params, flat=graphed.flat_grads)
+            loss_host.copy_(loss.detach(), non_blocking=True)
+            e1.record()
+            e1.synchronize()
+            hidden += 0 if graphed.prefetch_done() else 1
+            total_ms += e0.elapsed_time(e1)
+        return total_ms, hidden
+
     def barrier():
         torch.cuda.synchronize()
         if world > 1:
@@ -332,8 +356,15 @@ def run_gpu_arm(args, w):
     ms_res = max_over_ranks(ms_res)
     timed(2, False, graphed)
     barrier()
-    ms_e2e = max_over_ranks(timed(K, False, graphed))
+    ms_e2e_serial = max_over_ranks(timed(K, False, graphed))
     barrier()
+    ms_e2e, h2d_hidden = ms_e2e_serial, None
+    if graphed is not None:
+        timed_prefetched(2, graphed)
+        barrier()
+        ms_pf, h2d_hidden = timed_prefetched(K, graphed)
+        ms_e2e = max_over_ranks(ms_pf)
+        barrier()
     clk = clocks.stop() if rank == 0 else None
 
     # instrumented pass: a CUDA-event pair around every gemm_tc_kernel launch, recorded inside the library on the
@@ -385,10 +416,15 @@ def run_gpu_arm(args, w):
                    "eager_samples_per_s": samples / (ms_eager / 1e3), "kernels_per_step": launches_per_step,
                    "algorithmic_gflop_fwd_bwd": fb_f / 1e9},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                "ms_per_step": ms_e2e / K},
+                "ms_per_step": ms_e2e / K,
+                "input_pipeline": "eager: H2D then step" if graphed is None else
+                                  "double-buffered (GraphedStep.prefetch): the H2D of step i+1 runs inside step i's timed region",
+                "h2d_not_landed_at_region_end": h2d_hidden,
+                "serial_value": samples / (ms_e2e_serial / 1e3)},
         "gpu_launches": launches,
         "clocks": clk,
-        "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 3xTF32 dense projections, %d launches/step)" % (n_gemm // max(nprof, 1)),
+        "roofline": {"bound": "tensor", "kernel": "gemm_tc2_kernel / gemm_tc_kernel / gemm_tc_group_kernel (tcgen05 3xTF32 dense projections: CTA pairs, "
+                               "single-CTA tiles, grouped folds; %d launches/step)" % (n_gemm // max(nprof, 1)),
                      "achieved": achieved, "peak": peaks["tensor"], "unit": "TFLOP/s", "frac": achieved / peaks["tensor"],
                      "traffic": TRAFFIC_NCU, "traffic_note": TRAFFIC_NOTE, "peak_source": peaks["src"],
                      "note": "achieved = fp32-exact (algorithmic) FLOPs of the live rows / summed per-launch CUDA-event time; every "

@@ -1159,7 +1159,16 @@ extern "C" int immtsf_gemm_group(int n, const int* transA, const int* transB, co
     cudaFuncSetAttribute(gemm_tc_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128>::SMEM_BYTES);
     attr_done = true;
   }
+  // per-launch timing (bench.py): one record for the group, M scaled so that 2*M*N*K equals the group's FLOPs
+  ProfRec* rec = (g_prof_on && g_prof_n < g_prof_cap) ? &g_prof[g_prof_n++] : nullptr;
+  if (rec) {
+    double f = 0.0;
+    for (int i = 0; i < n; ++i) f += (double)M[i] * N[i] * K[i];
+    rec->M = (int)(f / ((double)N[0] * K[0]) + 0.5); rec->N = N[0]; rec->K = K[0]; rec->ragged_dim = 0;
+    cudaEventRecord(rec->e0, (cudaStream_t)stream);
+  }
   gemm_tc_group_kernel<<<dim3(gx, gy, n), Cfg<128>::THREADS, Cfg<128>::SMEM_BYTES, (cudaStream_t)stream>>>(grp);
+  if (rec) cudaEventRecord(rec->e1, (cudaStream_t)stream);
   IMMTSF_CHECK_LAUNCH("gemm_tc_group");
   return IMMTSF_OK;
 }

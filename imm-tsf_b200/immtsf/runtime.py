@@ -135,6 +135,7 @@ class GraphedStep:
         self.static_in[3].grad = None
         self.graph = torch.cuda.CUDAGraph()
         self._works = []
+        self._stage = self._copy_stream = self._staged = self._consumed = None
         if self.group is not None:
             fusion._e_txt_grad_hook = self._reduce_first_bucket  # fires between the MMF and the TTF backward
         try:
@@ -180,6 +181,39 @@ class GraphedStep:
     @property
     def dY_ts(self):
         return self.static_in[3].grad
+
+    def prefetch(self, notes, tau, t_hat, Y_ts, *extras):
+        """Start the host->device copy of the NEXT step's inputs (pinned host tensors) on a copy stream into staging
+        buffers, so that it overlaps the step that is running now; step_prefetched() then consumes them.  This is the
+        double-buffered input pipeline of a training loop: the graph's static inputs cannot be overwritten while a
+        replay may still read them, so the DMA targets a second set of buffers."""
+        if self._stage is None:
+            self._stage = [torch.empty_like(t) for t in self.static_in + self.static_extra]
+            self._copy_stream = torch.cuda.Stream()
+            self._staged = torch.cuda.Event()
+            self._consumed = torch.cuda.Event()
+            self._consumed.record()
+        cs = self._copy_stream
+        cs.wait_event(self._consumed)  # the previous staged batch has been moved into the static inputs
+        with torch.cuda.stream(cs), torch.no_grad():
+            for s, t in zip(self._stage, (notes, tau, t_hat, Y_ts) + tuple(extras)):
+                s.copy_(t, non_blocking=True)
+            self._staged.record(cs)
+
+    def prefetch_done(self) -> bool:
+        """True when the last prefetch() has fully landed on the device (no host wait)."""
+        return self._staged is not None and self._staged.query()
+
+    def step_prefetched(self):
+        """One step on the inputs of the last prefetch(): device-to-device move into the static inputs + one replay."""
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self._staged)
+        with torch.no_grad():
+            for s, t in zip(self.static_in + self.static_extra, self._stage):
+                s.copy_(t, non_blocking=True)
+        self._consumed.record(cur)
+        self.graph.replay()
+        return self.loss
 
     def __call__(self, notes, tau, t_hat, Y_ts, *extras):
         with torch.no_grad():
