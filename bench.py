@@ -216,6 +216,17 @@ class ClockSampler:
             for nm, v in zip(names, c[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
+        if not sm:  # the timed region was shorter than one sampling period: one synchronous reading right after it
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.dev)],
+                                     capture_output=True, text=True, timeout=20).stdout
+                c = [x.strip() for x in out.strip().splitlines()[0].split(",")]
+                sm.append(float(c[1])); mx.append(float(c[2]))
+                for nm, v in zip(names, c[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
 
