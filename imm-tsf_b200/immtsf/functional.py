@@ -248,62 +248,94 @@ class XAttnAddFn(torch.autograd.Function):
     (proj_q -> in_proj_q, proj_k -> in_proj_k, proj_v -> in_proj_v, :68-76) and the MHA out-projection into
     residual_head (:76,:83).  Consecutive linear maps are folded in WEIGHT space -- (E W_K^T) W_k^T = E (W_k W_K)^T --
     so the per-row work is one [B*T, d_txt] x [d_txt, 2d] projection instead of six d x d ones; the folds are d^3
-    (or rank-C) products, and backward un-folds the weight gradients the same way (the chain rule of the fold)."""
+    (or rank-C) products, and backward un-folds the weight gradients the same way (the chain rule of the fold).
+
+    Rank-(C+1) query path (T <= 32, the Time-IMM windows): q_i = Wq_f y_i + b_q is a projection of the C-channel
+    series, so q_i . k_j = [y_i ; 1] . kq_j with kq_j = [Wq_f^T k_j ; b_q . k_j].  kq [B*T, H*(C+1)] is one skinny product
+    per head; q and dq ([B*T, d] each) are never formed (csrc/xattn_small.cu, include/immtsf.h)."""
 
     @staticmethod
     def forward(ctx, Y, E, m_txt, H, kappa, thr, seed, save, flags, W_Q, W_K, W_V, in_w, in_b, out_w, out_b, W_r, b_r,
                 gamma, beta):
         B, T, C = Y.shape
         d, de = W_Q.shape[0], E.shape[2]
+        hd, C1 = d // H, C + 1
         dev = Y.device
+        new = lambda *s: torch.empty(*s, dtype=_f32, device=dev)
         Y2 = Y.contiguous().view(B * T, C)
         E2 = E.contiguous().view(B * T, de)
         lo = ops.step_ctx().lo
-        ops.weight_los(lo, [(W_K, []), (W_V, []), (in_w, [slice(d, 2 * d), slice(2 * d, None)])])
+        kv = new(B * T, 2 * d)
+        lowrank = ops.xattn_lowrank_ok(T, H, d, C, kv[:, d:])
         # ---- weight-space folds (their epilogues also write the folded operand's lo)
-        Wq_f = ops.gemm(in_w[:d], W_Q, torch.empty(d, C, dtype=_f32, device=dev))  # [d, C]
-        Wkv_f = torch.empty(2 * d, de, dtype=_f32, device=dev)
-        Wkv_f_lo = torch.empty(2 * d, ops.round_up(de, 4), dtype=_f32, device=dev)
+        Wq_aug = new(d, C1)  # [Wq_f | b_q]
+        extra = [(in_b[:d].view(d, 1), Wq_aug[:, C:], None)] if lowrank else []
+        ops.weight_los(lo, [(W_K, []), (W_V, []), (in_w, [slice(d, 2 * d), slice(2 * d, None)])], extra)
+        Wq_f = ops.gemm(in_w[:d], W_Q, Wq_aug[:, :C])  # [d, C]
+        Wkv_f = new(2 * d, de)
+        Wkv_f_lo = new(2 * d, ops.round_up(de, 4))
         ops.gemm_group([dict(A=in_w[d:2 * d], B=W_K, C=Wkv_f[:d], emit_lo=Wkv_f_lo[:d]),
                         dict(A=in_w[2 * d:], B=W_V, C=Wkv_f[d:], emit_lo=Wkv_f_lo[d:])], lo)  # one launch
         lo.put(Wkv_f, Wkv_f_lo)
-        Wo_f = ops.gemm(W_r, out_w, torch.empty(C, d, dtype=_f32, device=dev))  # [C, d]
-        bo_f = ops.gemm(out_b.view(1, d), W_r, torch.empty(1, C, dtype=_f32, device=dev), transB=True, bias=b_r).view(C)
+        Wo_f = ops.gemm(W_r, out_w, new(C, d))  # [C, d]
+        bo_f = ops.gemm(out_b.view(1, d), W_r, new(1, C), transB=True, bias=b_r).view(C)
         # ---- per-row work
-        q = ops.linear_fwd(Y2, Wq_f, in_b[:d])  # :68 + in_proj_q
-        kv = ops.linear_fwd(E2, Wkv_f, in_b[d:], lo=lo)  # :69-70 + in_proj_k / in_proj_v, E read once
-        o, probs = ops.xattn_core_fwd(q, kv[:, :d], kv[:, d:], m_txt, B, T, H, d, thr, seed, save, lo=lo)
+        ops.linear_fwd(E2, Wkv_f, in_b[d:], out=kv, lo=lo)  # :69-70 + in_proj_k / in_proj_v, E read once
+        if lowrank:
+            q = None
+            kq = new(B * T, H * C1)
+            for h in range(H):
+                ops.gemm(kv[:, h * hd:(h + 1) * hd], Wq_aug[h * hd:(h + 1) * hd], kq[:, h * C1:(h + 1) * C1])
+            o, probs = ops.xattn_lowrank_fwd(Y2, kq, kv[:, d:], m_txt, B, T, H, d, C, thr, seed, save)
+        else:
+            kq = None
+            q = ops.linear_fwd(Y2, Wq_f, in_b[:d])  # :68 + in_proj_q
+            o, probs = ops.xattn_core_fwd(q, kv[:, :d], kv[:, d:], m_txt, B, T, H, d, thr, seed, save, lo=lo)
         delta_y = ops.linear_fwd(o, Wo_f, bo_f)  # out_proj + residual_head (:83)
         Y_out = ops.xattn_tail_fwd(Y2, delta_y, gamma, beta, m_txt, B, T, C, kappa, thr, seed, flags)
         if save:
-            ctx.H, ctx.kappa, ctx.thr, ctx.seed, ctx.dims, ctx.lo = H, kappa, thr, seed, (B, T, C, d, de), lo
-            ctx.save_for_backward(m_txt, Y2, E2, W_Q, W_K, W_V, in_w, out_w, out_b, W_r, gamma, Wq_f, Wkv_f, Wo_f, q, kv, o, probs,
-                                  delta_y)
+            ctx.H, ctx.kappa, ctx.thr, ctx.seed, ctx.dims, ctx.lo, ctx.lowrank = H, kappa, thr, seed, (B, T, C, d, de), lo, lowrank
+            ctx.save_for_backward(m_txt, Y2, E2, W_Q, W_K, W_V, in_w, out_w, out_b, W_r, gamma, Wq_aug, Wkv_f, Wo_f, q, kq, kv, o,
+                                  probs, delta_y)
         return Y_out
 
     @staticmethod
     def backward(ctx, dY_out):
-        (m_txt, Y2, E2, W_Q, W_K, W_V, in_w, out_w, out_b, W_r, gamma, Wq_f, Wkv_f, Wo_f, q, kv, o, probs,
+        (m_txt, Y2, E2, W_Q, W_K, W_V, in_w, out_w, out_b, W_r, gamma, Wq_aug, Wkv_f, Wo_f, q, kq, kv, o, probs,
          delta_y) = ctx.saved_tensors
         B, T, C, d, de = ctx.dims
-        H, kappa, thr, seed, lo = ctx.H, ctx.kappa, ctx.thr, ctx.seed, ctx.lo
+        H, kappa, thr, seed, lo, lowrank = ctx.H, ctx.kappa, ctx.thr, ctx.seed, ctx.lo, ctx.lowrank
         ctx.lo = None
+        hd, C1 = d // H, C + 1
         dev = Y2.device
         new = lambda *s: torch.empty(*s, dtype=_f32, device=dev)
+        Wq_f = Wq_aug[:, :C]
         dY_out = dY_out.contiguous()
         d_delta, dgamma, dbeta = ops.xattn_tail_bwd(dY_out, delta_y, gamma, m_txt, B, T, C, kappa, thr, seed)
         # ---- folded out_proj + residual_head
         dWo_f = ops.linear_wgrad(d_delta, o)  # [C, d]
         db_r = ops.colsum(d_delta)  # d(bo_f) = d(b_r)
         do = ops.linear_dgrad(d_delta, Wo_f)
-        dq, dkv = new(B * T, d), new(B * T, 2 * d)
-        ops.xattn_core_bwd(do, q, kv[:, :d], kv[:, d:], probs, m_txt, B, T, H, d, thr, seed, dq, dkv[:, :d], dkv[:, d:], lo=lo)
-        # ---- folded projections
+        dkv = new(B * T, 2 * d)
         d_in_w, d_in_b = torch.empty_like(in_w), new(3 * d)
-        dWq_f = ops.linear_wgrad(dq, Y2)  # [d, C]
-        ops.colsum(dq, out=d_in_b[:d])
         dY = ops.axpby(dY_out.view(B * T, C), 1.0 / (1.0 + kappa), new(B * T, C), False)
-        ops.linear_dgrad(dq, Wq_f, out=dY, beta=1.0)
+        if lowrank:
+            z, dyh = ops.xattn_lowrank_bwd(do, Y2, kq, kv[:, d:], probs, m_txt, B, T, H, d, C, thr, seed, dkv[:, d:])
+            dWq_aug = new(d, C1)
+            for h in range(H):
+                zh, ks = z[:, h * C1:(h + 1) * C1], slice(h * hd, (h + 1) * hd)
+                ops.gemm(zh, Wq_aug[ks], dkv[:, ks], transB=True)  # dk = Z [Wq_f | b_q]^T
+                ops.gemm(kv[:, ks], zh, dWq_aug[ks], transA=True)  # d[Wq_f | b_q] = k^T Z
+                ops.axpby(dyh[h], 1.0, dY, True)
+            dWq_f = dWq_aug[:, :C]
+            d_in_b[:d].copy_(dWq_aug[:, C])
+        else:
+            dq = new(B * T, d)
+            ops.xattn_core_bwd(do, q, kv[:, :d], kv[:, d:], probs, m_txt, B, T, H, d, thr, seed, dq, dkv[:, :d], dkv[:, d:], lo=lo)
+            dWq_f = ops.linear_wgrad(dq, Y2)  # [d, C]
+            ops.colsum(dq, out=d_in_b[:d])
+            ops.linear_dgrad(dq, Wq_f, out=dY, beta=1.0)
+        # ---- folded projections
         dWkv_f, dWkv_f_lo = new(2 * d, de), new(2 * d, ops.round_up(de, 4))
         ops.linear_wgrad(dkv, E2, out=dWkv_f, lo=lo, emit_lo=dWkv_f_lo)  # [2d, de]; its halves feed the un-fold products
         lo.put(dWkv_f[:d], dWkv_f_lo[:d])

@@ -563,6 +563,28 @@ def xattn_core_bwd(d_o, q, k, v, probs, m_txt, B, T, H, d, thr, seed, dq, dk, dv
               _stream())
 
 
+def xattn_lowrank_ok(T, H, d, C, *tensors) -> bool:
+    """Rank-(C+1) query path applies (T <= 32, C + 1 <= 32) and the wide operands are 16B aligned."""
+    al = all(t.data_ptr() % 16 == 0 and t.stride(0) % 4 == 0 for t in tensors)
+    return al and bool(_lib.load().immtsf_xattn_lowrank_ok(T, H, d, C))
+
+
+def xattn_lowrank_fwd(Y2, kq, v, m_txt, B, T, H, d, C, thr, seed, save):
+    o = torch.empty(B * T, d, dtype=torch.float32, device=v.device)
+    probs = torch.empty(B, H, T, T, dtype=torch.float32, device=v.device) if save else None
+    _lib.call("immtsf_xattn_lowrank_fwd", _p(Y2), Y2.stride(0), _p(kq), kq.stride(0), _p(v), v.stride(0), _p(m_txt), B, T, H, d, C,
+              thr, seed, _p(o), o.stride(0), _p(probs), _stream())
+    return o, probs
+
+
+def xattn_lowrank_bwd(d_o, Y2, kq, v, probs, m_txt, B, T, H, d, C, thr, seed, dv):
+    z = torch.empty(B * T, H * (C + 1), dtype=torch.float32, device=v.device)
+    dyh = torch.empty(H, B * T, C, dtype=torch.float32, device=v.device)
+    _lib.call("immtsf_xattn_lowrank_bwd", _p(d_o), d_o.stride(0), _p(Y2), Y2.stride(0), _p(kq), kq.stride(0), _p(v), v.stride(0),
+              _p(probs), _p(m_txt), B, T, H, d, C, thr, seed, _p(dv), dv.stride(0), _p(z), z.stride(0), _p(dyh), _stream())
+    return z, dyh
+
+
 def xattn_tail_fwd(Y, delta_y, gamma, beta, m_txt, B, T, C, kappa, thr, seed, flags):
     Y_out = torch.empty(B, T, C, dtype=torch.float32, device=Y.device)
     _lib.call("immtsf_xattn_tail_fwd", _p(Y), _p(delta_y), _p(gamma), _p(beta), _p(m_txt), B, T, C, LN_EPS, float(kappa), thr,

@@ -226,6 +226,19 @@ int immtsf_xattn_core_bwd(const float* d_o, int lddo, const float* q, int ldq, c
                           const float* v, int ldv, const float* probs, const uint8_t* m_txt, int B, int T,
                           int H, int d, uint32_t drop_thr, uint64_t seed, float* dq, int lddq, float* dk,
                           int lddk, float* dv, int lddv, void* stream);
+/* Rank-(C+1) query path for T <= 32 (csrc/xattn_small.cu).  In MMF_XAttn_Add the queries are a projection of the
+ * C-channel series (q_i = W y_i + b, MMF_XAttn_Add.py:68 + in_proj_q), so q_i . k_j = [y_i ; 1] . kq_j with
+ * kq_j = [W^T k_j ; b . k_j]: the caller makes kq [B*T, H*(C+1)] with one skinny product per head and q is never
+ * formed.  Backward returns dv, Z [B*T, H*(C+1)] (Z_j = sum_i dS_ij [y_i ; 1]: dk = Z [W | b]^T and
+ * d[W | b] = k^T Z are two skinny products) and dyh [H][B*T][C] (per-head query-side gradient into Y_ts). */
+int immtsf_xattn_lowrank_ok(int T, int H, int d, int C);
+int immtsf_xattn_lowrank_fwd(const float* y, int ldy, const float* kq, int ldkq, const float* v, int ldv,
+                             const uint8_t* m_txt, int B, int T, int H, int d, int C, uint32_t drop_thr,
+                             uint64_t seed, float* o, int ldo, float* probs, void* stream);
+int immtsf_xattn_lowrank_bwd(const float* d_o, int lddo, const float* y, int ldy, const float* kq, int ldkq,
+                             const float* v, int ldv, const float* probs, const uint8_t* m_txt, int B, int T,
+                             int H, int d, int C, uint32_t drop_thr, uint64_t seed, float* dv, int lddv,
+                             float* z, int ldz, float* dyh, void* stream);
 /* Large-T form of the same core (T > 32: the T x T contractions are dense products and run on tcgen05):
  *   S = Q K^T (immtsf_gemm_batched) -> immtsf_softmax_rows_fwd -> O = P~ V (immtsf_gemm_batched), and in backward
  *   dP~ = dO V^T -> immtsf_softmax_rows_bwd -> dQ = dS K, dK = dS^T Q, dV = P~^T dO.

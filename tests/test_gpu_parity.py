@@ -348,3 +348,42 @@ def test_dropout_is_statistically_right():
     frac = (E1 == 0).float().mean().item()
     assert abs(frac - 0.25) < 0.02, frac
     assert not torch.equal(E1, E2)
+
+
+@pytest.mark.parametrize("T,H,d,C", [(24, 1, 768, 4), (32, 2, 64, 31), (7, 4, 96, 1), (17, 1, 128, 12)])
+def test_xattn_lowrank_query_path_equals_dense_core(T, H, d, C):
+    """Rank-(C+1) query path (csrc/xattn_small.cu, MMF_XAttn_Add.py:68-76) against the dense T<=32 core on the same
+    q = W y + b: forward output and probabilities, and in backward dv, dk (= Z [W|b]^T), d[W|b] (= k^T Z) and the
+    query-side gradient into Y_ts, incl. a sample without text (m_txt = 0) and attention dropout."""
+    from immtsf import ops
+
+    B, hd, C1 = 5, d // H, C + 1
+    g = torch.Generator().manual_seed(T * 131 + H * 17 + C)
+    rn = lambda *s: torch.randn(*s, generator=g).cuda()
+    Y2, k, v, d_o = rn(B * T, C), rn(B * T, d), rn(B * T, d), rn(B * T, d)
+    W, b = rn(d, C) * 0.3, rn(d) * 0.1
+    m_txt = torch.ones(B, dtype=torch.uint8, device="cuda")
+    m_txt[2] = 0
+    thr, seed = ops.drop_thr(0.25), 1234567
+    q = (Y2.double() @ W.double().T + b.double()).float()
+    o_ref, p_ref = ops.xattn_core_fwd(q, k, v, m_txt, B, T, H, d, thr, seed, True)
+    dq, dk_ref, dv_ref = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+    ops.xattn_core_bwd(d_o, q, k, v, p_ref, m_txt, B, T, H, d, thr, seed, dq, dk_ref, dv_ref)
+    W_aug = torch.cat([W, b.view(d, 1)], dim=1).contiguous()
+    kq = torch.empty(B * T, H * C1, device="cuda")
+    for h in range(H):
+        kq[:, h * C1:(h + 1) * C1] = (k[:, h * hd:(h + 1) * hd].double() @ W_aug[h * hd:(h + 1) * hd].double()).float()
+    assert ops.xattn_lowrank_ok(T, H, d, C, v)
+    o, p = ops.xattn_lowrank_fwd(Y2, kq, v, m_txt, B, T, H, d, C, thr, seed, True)
+    G.assert_close("o", o.cpu(), o_ref.cpu(), 2e-6)
+    G.assert_close("probs", p.cpu(), p_ref.cpu(), 2e-6)
+    dv = torch.empty_like(v)
+    z, dyh = ops.xattn_lowrank_bwd(d_o, Y2, kq, v, p_ref, m_txt, B, T, H, d, C, thr, seed, dv)
+    G.assert_close("dv", dv.cpu(), dv_ref.cpu(), 2e-6)
+    dk = torch.cat([z[:, h * C1:(h + 1) * C1].double() @ W_aug[h * hd:(h + 1) * hd].double().T for h in range(H)], dim=1)
+    G.assert_close("dk", dk.cpu(), dk_ref.cpu(), 5e-6)
+    dW_aug = torch.cat([k[:, h * hd:(h + 1) * hd].double().T @ z[:, h * C1:(h + 1) * C1].double() for h in range(H)], dim=0)
+    G.assert_close("dW", dW_aug[:, :C].cpu(), (dq.double().T @ Y2.double()).cpu(), 5e-6)
+    G.assert_close("db", dW_aug[:, C].cpu(), dq.double().sum(0).cpu(), 5e-6, floor=1e-3)
+    G.assert_close("dY", dyh.double().sum(0).cpu(), (dq.double() @ W.double()).cpu(), 5e-6)
+    assert (dv[2 * T:3 * T] == 0).all() and (z[2 * T:3 * T] == 0).all() and (dyh[:, 2 * T:3 * T] == 0).all() and (o[2 * T:3 * T] == 0).all()
