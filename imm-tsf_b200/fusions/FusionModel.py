@@ -72,7 +72,8 @@ class FusionModel(nn.Module):
             ops.nan_check(Y32, flags, ops.FLAG_Y)
         # one operand-split cache for the whole step: E_txt (and dE_txt in backward) are handed from one module's GEMM
         # epilogue to the other module's product together with their tcgen05 lo operand
-        ops.begin_step(e_txt_feeds_tc=isinstance(self.mmf, MMF_XAttn_Add))
+        T = t_hat.shape[-1]
+        ops.begin_step(e_txt_feeds_tc=isinstance(self.mmf, MMF_XAttn_Add) and not self.mmf.rank_path(T))
         try:
             return self._forward_step(r, t_hat, Y32, flags, check)
         finally:

@@ -38,12 +38,18 @@ class MMF_XAttn_Add(nn.Module):
                   self.layer_norm.weight, self.layer_norm.bias)
         save = F_._need_save(Y_ts, E_txt, *params)
         own_flags = flags if flags is not None else runtime.new_flags(Y_ts.device)
-        out = F_.XAttnAddFn.apply(cm.as_f32(Y_ts), cm.as_f32(E_txt), cm.m_txt_u8(M_txt, B), self.n_heads, float(self.kappa),
+        # Time-IMM shapes (T <= 32, few channels): the rank-(2C+1) form -- one skinny pass over E_txt, no tensor of width d
+        fn = F_.XAttnAddRankFn if self.rank_path(T) else F_.XAttnAddFn
+        out = fn.apply(cm.as_f32(Y_ts), cm.as_f32(E_txt), cm.m_txt_u8(M_txt, B), self.n_heads, float(self.kappa),
                                   thr, seed, save, own_flags, *params)
         if flags is None:  # standalone call: keep the reference's "delta_y contains NaN" ValueError (:84-91)
             if runtime.nan_check_enabled() and own_flags.tolist()[ops.FLAG_OUT]:
                 raise ValueError("delta_y contains NaN values.")
         return out
+
+    def rank_path(self, T: int) -> bool:
+        """Whether forward will use the rank-(2C+1) form (csrc/xattn_rank.cu) for T query times."""
+        return ops.xattn_rank_ok(T, self.n_heads, self.d_attn, self.C)
 
     def forward(self, Y_ts, E_txt, M_txt):
         return self.forward_flags(Y_ts, E_txt, M_txt, None)

@@ -57,6 +57,9 @@ SIGNATURES = {
     "immtsf_xattn_lowrank_ok": [I, I, I, I],
     "immtsf_xattn_lowrank_fwd": [P, I, P, I, P, I, P, I, I, I, I, I, U32, U64, P, I, P, P],
     "immtsf_xattn_lowrank_bwd": [P, I, P, I, P, I, P, I, P, P, I, I, I, I, I, U32, U64, P, I, P, I, P, P],
+    "immtsf_xattn_rank_ok": [I, I, I, I],
+    "immtsf_xattn_rank_fwd": [P, I, P, I, P, P, I, I, I, I, I, U32, U64, P, P, P],
+    "immtsf_xattn_rank_bwd": [P, P, I, P, I, P, P, I, I, I, I, I, U32, U64, P, I, P, P],
     "immtsf_gemm_batched": [I, I, I, I, I, F, P, P, I, L, L, P, P, I, L, L, F, P, I, L, L, I, I, P, SZ, P],
     "immtsf_softmax_rows_fwd": [P, P, P, I, I, I, I, F, U32, U64, P],
     "immtsf_softmax_rows_bwd": [P, P, P, P, I, I, I, I, F, U32, U64, P],

@@ -356,3 +356,105 @@ class XAttnAddFn(torch.autograd.Function):
         db_o = ops.gemm(db_r.view(1, C), W_r, new(1, d)).view(d)
         return (dY.view(B, T, C), dE.view(B, T, de), None, None, None, None, None, None, None, dW_Q, dW_K, dW_V,
                 d_in_w, d_in_b, dW_o, db_o, dW_r, db_r, dgamma, dbeta)
+
+
+class XAttnAddRankFn(torch.autograd.Function):
+    """MMF_XAttn_Add.py:56-103 for the Time-IMM case (T <= 32, few channels): the rank-(2C+1) form of csrc/xattn_rank.cu.
+
+    Queries are projections of the C-channel series and the output goes through residual_head back to C channels, so
+        score_ij = [y_i ; 1] . kq_j / sqrt(hd),  kq_j = A e_j + a0,   A = Wq_aug^T in_k W_K,  Wq_aug = [in_q W_Q | b_q]
+        delta_i  = sum_h sum_j P~_ij vo_j + bo,  vo_j = G e_j + g0,   G = Wo_f in_v W_V,      Wo_f = W_r W_o
+    (per head: the rows of in_k / in_v and the columns of Wo_f that belong to the head).  The only pass over the wide
+    data is R = E_txt [A ; G]^T + [a0 ; g0]; q, k, v, o and their gradients never exist, and the d x d weight matrices
+    only meet in skinny weight-space products (each is one immtsf_gemm call below, with its two backward products)."""
+
+    @staticmethod
+    def forward(ctx, Y, E, m_txt, H, kappa, thr, seed, save, flags, W_Q, W_K, W_V, in_w, in_b, out_w, out_b, W_r, b_r,
+                gamma, beta):
+        B, T, C = Y.shape
+        d, de = W_Q.shape[0], E.shape[2]
+        hd, C1 = d // H, C + 1
+        n1, nr = H * C1, H * (2 * C + 1)
+        dev = Y.device
+        new = lambda *s: torch.empty(*s, dtype=_f32, device=dev)
+        Y2 = Y.contiguous().view(B * T, C)
+        E2 = E.contiguous().view(B * T, de)
+        in_k, in_v, b_k, b_v = in_w[d:2 * d], in_w[2 * d:], in_b[d:2 * d], in_b[2 * d:]
+        # ---- weight space
+        Wq_aug = new(d, C1)
+        ops.multi_split([(in_b[:d].view(d, 1), Wq_aug[:, C:], None)])
+        ops.gemm(in_w[:d], W_Q, Wq_aug[:, :C])
+        Wo_f = ops.gemm(W_r, out_w, new(C, d))
+        bo_f = ops.gemm(out_b.view(1, d), W_r, new(1, C), transB=True, bias=b_r).view(C)
+        Wr, br = new(nr, de), new(nr)
+        P1, P2 = new(H, C1, d), new(H, C, d)
+        for h in range(H):
+            hs, ra, rg = slice(h * hd, (h + 1) * hd), slice(h * C1, (h + 1) * C1), slice(n1 + h * C, n1 + (h + 1) * C)
+            ops.gemm(Wq_aug[hs], in_k[hs], P1[h], transA=True)  # Wq_aug_h^T in_k_h            [C1, d]
+            ops.gemm(P1[h], W_K, Wr[ra])  # A_h                                                  [C1, de]
+            ops.gemm(Wq_aug[hs], b_k[hs].view(hd, 1), br[ra].view(C1, 1), transA=True)  # a0_h
+            ops.gemm(Wo_f[:, hs], in_v[hs], P2[h])  # Wo_f_h in_v_h                              [C, d]
+            ops.gemm(P2[h], W_V, Wr[rg])  # G_h                                                  [C, de]
+            ops.gemm(Wo_f[:, hs], b_v[hs].view(hd, 1), br[rg].view(C, 1))  # g0_h
+        # ---- the one pass over E_txt, then the T x (2C+1) attention and the tail
+        R = ops.gemm(E2, Wr, new(B * T, nr), transB=True, bias=br)
+        delta_y, probs = ops.xattn_rank_fwd(Y2, R, bo_f, m_txt, B, T, H, d, C, thr, seed, save)
+        Y_out = ops.xattn_tail_fwd(Y2, delta_y, gamma, beta, m_txt, B, T, C, kappa, thr, seed, flags)
+        if save:
+            ctx.H, ctx.kappa, ctx.thr, ctx.seed, ctx.dims = H, kappa, thr, seed, (B, T, C, d, de)
+            ctx.save_for_backward(m_txt, Y2, E2, W_Q, W_K, W_V, in_w, in_b, out_w, out_b, W_r, gamma, Wq_aug, Wo_f, P1, P2, Wr, R,
+                                  probs, delta_y)
+        return Y_out
+
+    @staticmethod
+    def backward(ctx, dY_out):
+        (m_txt, Y2, E2, W_Q, W_K, W_V, in_w, in_b, out_w, out_b, W_r, gamma, Wq_aug, Wo_f, P1, P2, Wr, R, probs,
+         delta_y) = ctx.saved_tensors
+        B, T, C, d, de = ctx.dims
+        H, kappa, thr, seed = ctx.H, ctx.kappa, ctx.thr, ctx.seed
+        hd, C1 = d // H, C + 1
+        n1, nr = H * C1, H * (2 * C + 1)
+        dev = Y2.device
+        new = lambda *s: torch.empty(*s, dtype=_f32, device=dev)
+        in_k, in_v, b_k, b_v = in_w[d:2 * d], in_w[2 * d:], in_b[d:2 * d], in_b[2 * d:]
+        dY_out = dY_out.contiguous()
+        d_delta, dgamma, dbeta = ops.xattn_tail_bwd(dY_out, delta_y, gamma, m_txt, B, T, C, kappa, thr, seed)
+        dbo_f = ops.colsum(d_delta)  # = d(b_r)
+        dR, dY = ops.xattn_rank_bwd(d_delta, Y2, R, probs, m_txt, B, T, H, d, C, thr, seed)
+        ops.axpby(dY_out.view(B * T, C), 1.0 / (1.0 + kappa), dY, True)  # the blend passes Y straight through
+        dWr = ops.gemm(dR, E2, new(nr, de), transA=True)
+        dbr = ops.colsum(dR)
+        dE = ops.gemm(dR, Wr, new(B * T, de))
+        # ---- weight space: every product C = A B gives dA = dC B^T, dB = A^T dC
+        d_in_w, d_in_b = torch.empty_like(in_w), new(3 * d)
+        d_in_k, d_in_v, db_k, db_v = d_in_w[d:2 * d], d_in_w[2 * d:], d_in_b[d:2 * d], d_in_b[2 * d:]
+        dWq_aug, dWo_f, dW_K, dW_V = new(d, C1), new(C, d), new(d, de), new(d, de)
+        for h in range(H):
+            hs, ra, rg = slice(h * hd, (h + 1) * hd), slice(h * C1, (h + 1) * C1), slice(n1 + h * C, n1 + (h + 1) * C)
+            acc = 1.0 if h > 0 else 0.0
+            # G_h = P2_h W_V ; P2_h = Wo_f_h in_v_h ; g0_h = Wo_f_h b_v_h
+            dP2 = ops.gemm(dWr[rg], W_V, new(C, d), transB=True)
+            ops.gemm(P2[h], dWr[rg], dW_V, transA=True, beta=acc)
+            ops.gemm(dP2, in_v[hs], dWo_f[:, hs], transB=True)
+            ops.gemm(Wo_f[:, hs], dP2, d_in_v[hs], transA=True)
+            ops.gemm(dbr[rg].view(C, 1), b_v[hs].view(1, hd), dWo_f[:, hs], beta=1.0)
+            ops.gemm(Wo_f[:, hs], dbr[rg].view(C, 1), db_v[hs].view(hd, 1), transA=True)
+            # A_h = P1_h W_K ; P1_h = Wq_aug_h^T in_k_h ; a0_h = Wq_aug_h^T b_k_h
+            dP1 = ops.gemm(dWr[ra], W_K, new(C1, d), transB=True)
+            ops.gemm(P1[h], dWr[ra], dW_K, transA=True, beta=acc)
+            ops.gemm(in_k[hs], dP1, dWq_aug[hs], transB=True)
+            ops.gemm(Wq_aug[hs], dP1, d_in_k[hs])
+            ops.gemm(b_k[hs].view(hd, 1), dbr[ra].view(1, C1), dWq_aug[hs], beta=1.0)
+            ops.gemm(Wq_aug[hs], dbr[ra].view(C1, 1), db_k[hs].view(hd, 1))
+        # Wo_f = W_r W_o ; bo_f = W_r b_o + b_r
+        dW_r = ops.gemm(dWo_f, out_w, new(C, d), transB=True)
+        ops.gemm(dbo_f.view(C, 1), out_b.view(1, d), dW_r, beta=1.0)
+        dW_o = ops.gemm(W_r, dWo_f, new(d, d), transA=True)
+        db_o = ops.gemm(dbo_f.view(1, C), W_r, new(1, d)).view(d)
+        # Wq_aug = [in_q W_Q | b_q]
+        dWq_f = dWq_aug[:, :C]
+        ops.gemm(dWq_f, W_Q, d_in_w[:d], transB=True)
+        dW_Q = ops.gemm(in_w[:d], dWq_f, new(d, C), transA=True)
+        ops.multi_split([(dWq_aug[:, C:], d_in_b[:d].view(d, 1), None)])
+        return (dY.view(B, T, C), dE.view(B, T, de), None, None, None, None, None, None, None, dW_Q, dW_K, dW_V,
+                d_in_w, d_in_b, dW_o, db_o, dW_r, dbo_f, dgamma, dbeta)

@@ -585,6 +585,28 @@ def xattn_lowrank_bwd(d_o, Y2, kq, v, probs, m_txt, B, T, H, d, C, thr, seed, dv
     return z, dyh
 
 
+def xattn_rank_ok(T, H, d, C) -> bool:
+    if os.environ.get("IMMTSF_XATTN_RANK", "1") == "0":
+        return False
+    return bool(_lib.load().immtsf_xattn_rank_ok(T, H, d, C))
+
+
+def xattn_rank_fwd(Y2, R, bo, m_txt, B, T, H, d, C, thr, seed, save):
+    delta_y = torch.empty(B * T, C, dtype=torch.float32, device=R.device)
+    probs = torch.empty(B, H, T, T, dtype=torch.float32, device=R.device) if save else None
+    _lib.call("immtsf_xattn_rank_fwd", _p(Y2), Y2.stride(0), _p(R), R.stride(0), _p(bo), _p(m_txt), B, T, H, d, C, thr, seed,
+              _p(delta_y), _p(probs), _stream())
+    return delta_y, probs
+
+
+def xattn_rank_bwd(d_delta, Y2, R, probs, m_txt, B, T, H, d, C, thr, seed):
+    dR = torch.empty_like(R)
+    dY = torch.empty(B * T, C, dtype=torch.float32, device=R.device)
+    _lib.call("immtsf_xattn_rank_bwd", _p(d_delta), _p(Y2), Y2.stride(0), _p(R), R.stride(0), _p(probs), _p(m_txt), B, T, H, d, C,
+              thr, seed, _p(dR), dR.stride(0), _p(dY), _stream())
+    return dR, dY
+
+
 def xattn_tail_fwd(Y, delta_y, gamma, beta, m_txt, B, T, C, kappa, thr, seed, flags):
     Y_out = torch.empty(B, T, C, dtype=torch.float32, device=Y.device)
     _lib.call("immtsf_xattn_tail_fwd", _p(Y), _p(delta_y), _p(gamma), _p(beta), _p(m_txt), B, T, C, LN_EPS, float(kappa), thr,

@@ -239,6 +239,19 @@ int immtsf_xattn_lowrank_bwd(const float* d_o, int lddo, const float* y, int ldy
                              const float* v, int ldv, const float* probs, const uint8_t* m_txt, int B, int T,
                              int H, int d, int C, uint32_t drop_thr, uint64_t seed, float* dv, int lddv,
                              float* z, int ldz, float* dyh, void* stream);
+/* MMF_XAttn_Add as a rank-(2C+1) form in E_txt (csrc/xattn_rank.cu; T <= 32, C <= 31, H*(C+1) <= 64).  Both ends of
+ * the attention are C-dimensional (queries = projections of the C-channel series, output = residual_head of the
+ * MHA output), so with R = [kq | vo] = E_txt [A ; G]^T + [a0 ; g0]  ([B*T, H*(C+1) + H*C], one skinny product;
+ * A = Wq_aug^T in_k W_K, G = (W_r W_o) in_v W_V per head, formed by skinny weight-space products)
+ *   score_ij = [y_i ; 1] . kq_j / sqrt(hd),   delta_i = sum_h sum_j P~_ij vo_j + bo
+ * and no tensor of width d (q, k, v, o or their gradients) exists.  Backward returns dR = [Z | U] and dY. */
+int immtsf_xattn_rank_ok(int T, int H, int d, int C);
+int immtsf_xattn_rank_fwd(const float* y, int ldy, const float* r, int ldr, const float* bo, const uint8_t* m_txt,
+                          int B, int T, int H, int d, int C, uint32_t drop_thr, uint64_t seed, float* delta_y,
+                          float* probs, void* stream);
+int immtsf_xattn_rank_bwd(const float* d_delta, const float* y, int ldy, const float* r, int ldr, const float* probs,
+                          const uint8_t* m_txt, int B, int T, int H, int d, int C, uint32_t drop_thr, uint64_t seed,
+                          float* dr, int lddr, float* dy, void* stream);
 /* Large-T form of the same core (T > 32: the T x T contractions are dense products and run on tcgen05):
  *   S = Q K^T (immtsf_gemm_batched) -> immtsf_softmax_rows_fwd -> O = P~ V (immtsf_gemm_batched), and in backward
  *   dP~ = dO V^T -> immtsf_softmax_rows_bwd -> dQ = dS K, dK = dS^T Q, dV = P~^T dO.

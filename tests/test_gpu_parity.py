@@ -387,3 +387,20 @@ def test_xattn_lowrank_query_path_equals_dense_core(T, H, d, C):
     G.assert_close("db", dW_aug[:, C].cpu(), dq.double().sum(0).cpu(), 5e-6, floor=1e-3)
     G.assert_close("dY", dyh.double().sum(0).cpu(), (dq.double() @ W.double()).cpu(), 5e-6)
     assert (dv[2 * T:3 * T] == 0).all() and (z[2 * T:3 * T] == 0).all() and (dyh[:, 2 * T:3 * T] == 0).all() and (o[2 * T:3 * T] == 0).all()
+
+
+@pytest.mark.parametrize("ttf", ["TTF_RecAvg", "TTF_T2V_XAttn"])
+@pytest.mark.parametrize("H,p", [(1, 0.1), (2, 0.0)])
+def test_mmf_xattn_dense_path_still_matches_oracle(ttf, H, p, monkeypatch):
+    """MMF_XAttn_Add at T <= 32 normally runs the rank-(2C+1) form (csrc/xattn_rank.cu); IMMTSF_XATTN_RANK=0 keeps it on the
+    dense folded projections + rank-(C+1) query path (XAttnAddFn), which large C*H configurations still use."""
+    monkeypatch.setenv("IMMTSF_XATTN_RANK", "0")
+    cfg = dict(ttf=ttf, mmf="MMF_XAttn_Add", d_txt=768 if H == 1 else 64, C=4, H=H, kappa=0.5)
+    _vs_oracle(cfg, 768 if H == 1 else 96, B=16, N=8, T=24, p=p, train=True, seed=41)
+
+
+def test_mmf_xattn_rank_path_is_selected_for_time_imm_shapes():
+    from immtsf import ops
+
+    assert ops.xattn_rank_ok(24, 1, 768, 4) and ops.xattn_rank_ok(32, 2, 64, 31)
+    assert not ops.xattn_rank_ok(33, 1, 768, 4) and not ops.xattn_rank_ok(24, 4, 768, 31)
