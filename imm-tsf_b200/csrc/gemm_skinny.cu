@@ -56,17 +56,33 @@ __global__ void __launch_bounds__(256) gemm_smallk_kernel(const SkArgs g) {
 #pragma unroll
     for (int e = 0; e < 4; ++e)
       if (e < nv) bs[e] = __ldg(g.bias + n + e);
+  // whole float4 groups of the A row may be read when the row (incl. its padding up to a multiple of 4) is in bounds
+  const bool avec = KMAX >= 4 && g.a_cs == 1 && (g.a_rs & 3) == 0 && (((uintptr_t)g.A) & 15) == 0 && g.a_rs >= ((g.K + 3) & ~3);
   for (int m = blockIdx.y; m < Mtouch; m += gridDim.y) {
     float o[4] = {0.f, 0.f, 0.f, 0.f};
     const bool live = m < Meff;
     if (live) {
       float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      if (avec) {  // A rows are contiguous and 16B aligned: KMAX/4 broadcast float4 loads instead of KMAX scalar ones
 #pragma unroll
-      for (int k = 0; k < KMAX; ++k) {
-        if (k < g.K) {
-          const float a = __ldg(g.A + (long)m * g.a_rs + k * g.a_cs);
+        for (int k4 = 0; k4 < KMAX / 4; ++k4) {
+          if (k4 * 4 < g.K) {
+            const float4 av = __ldg(reinterpret_cast<const float4*>(g.A + (long)m * g.a_rs) + k4);
+            const float a4[4] = {av.x, av.y, av.z, av.w};
 #pragma unroll
-          for (int e = 0; e < 4; ++e) acc[e] = fmaf(a, b[k][e], acc[e]);
+            for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+              for (int e = 0; e < 4; ++e) acc[e] = fmaf(a4[kk], b[k4 * 4 + kk][e], acc[e]);  // b[k] = 0 for k >= K
+          }
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+          if (k < g.K) {
+            const float a = __ldg(g.A + (long)m * g.a_rs + k * g.a_cs);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[e] = fmaf(a, b[k][e], acc[e]);
+          }
         }
       }
 #pragma unroll
@@ -90,8 +106,18 @@ __global__ void __launch_bounds__(256) gemm_smallk_kernel(const SkArgs g) {
 // ------------------------------------------------------------------ small-N
 // A rows are k-contiguous (a_cs == 1), 16B aligned (a_rs % 4 == 0, K % 4 == 0).
 // One warp owns SN_R consecutive rows; lanes stride float4 chunks of k.
-template <int NMAX, int SN_R>
+// SMEMB: B' is staged once per CTA as s_b[n][K] (k contiguous), so a lane fetches its four k's of column n with ONE
+// conflict-free LDS.128 instead of four scalar global loads (NMAX = 16: 64 -> 16 load instructions per 128 FMA).
+template <int NMAX, int SN_R, bool SMEMB = false>
 __global__ void __launch_bounds__(256) gemm_smalln_kernel(const SkArgs g) {
+  extern __shared__ __align__(16) float s_b[];
+  if (SMEMB) {
+    for (int i = threadIdx.x; i < g.N * g.K; i += blockDim.x) {
+      const int n = i / g.K, k = i % g.K;
+      s_b[i] = __ldg(g.B + (long)k * g.b_rs + (long)n * g.b_cs);
+    }
+    __syncthreads();
+  }
   int Meff = g.M;
   if (g.ragged_dim == 1) Meff = ragged_rows(g.M, g.ragged);
   int Mtouch = (Meff + 127) / 128 * 128;
@@ -115,8 +141,14 @@ __global__ void __launch_bounds__(256) gemm_smalln_kernel(const SkArgs g) {
 #pragma unroll
         for (int n = 0; n < NMAX; ++n) {
           if (n < g.N) {
-            const float b0 = __ldg(bp + n * g.b_cs), b1 = __ldg(bp + g.b_rs + n * g.b_cs);
-            const float b2 = __ldg(bp + 2 * g.b_rs + n * g.b_cs), b3 = __ldg(bp + 3 * g.b_rs + n * g.b_cs);
+            float b0, b1, b2, b3;
+            if (SMEMB) {
+              const float4 bv = *reinterpret_cast<const float4*>(s_b + n * g.K + k4 * 4);
+              b0 = bv.x; b1 = bv.y; b2 = bv.z; b3 = bv.w;
+            } else {
+              b0 = __ldg(bp + n * g.b_cs); b1 = __ldg(bp + g.b_rs + n * g.b_cs);
+              b2 = __ldg(bp + 2 * g.b_rs + n * g.b_cs); b3 = __ldg(bp + 3 * g.b_rs + n * g.b_cs);
+            }
 #pragma unroll
             for (int r = 0; r < SN_R; ++r)
               acc[r][n] = fmaf(a[r].x, b0, fmaf(a[r].y, b1, fmaf(a[r].z, b2, fmaf(a[r].w, b3, acc[r][n]))));
@@ -167,6 +199,7 @@ __global__ void __launch_bounds__(256) gemm_tallt_partial_kernel(const float* __
   float4 acc[SMAX];
 #pragma unroll
   for (int s = 0; s < SMAX; ++s) acc[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const bool svec = S != nullptr && s_ss == 1 && (s_ks & 3) == 0 && (((uintptr_t)S) & 15) == 0 && s_ks >= ((Sn + 3) & ~3);
   if (n < N) {
     const bool full = n + 3 < N;
     for (int kb = k0 + w; kb < k1; kb += 4 * TT_WARPS) {
@@ -187,12 +220,28 @@ __global__ void __launch_bounds__(256) gemm_tallt_partial_kernel(const float* __
       for (int u = 0; u < 4; ++u) {
         const int k = kb + u * TT_WARPS;
         if (k < k1) {
+          if (SMAX >= 4 && svec) {  // S' rows contiguous, 16B aligned and padded: SMAX/4 float4 loads per row
 #pragma unroll
-          for (int s = 0; s < SMAX; ++s) {
-            if (s < Sn) {
-              const float c = S != nullptr ? __ldg(S + (long)k * s_ks + s * s_ss) : 1.f;
-              acc[s].x = fmaf(c, v[u].x, acc[s].x); acc[s].y = fmaf(c, v[u].y, acc[s].y);
-              acc[s].z = fmaf(c, v[u].z, acc[s].z); acc[s].w = fmaf(c, v[u].w, acc[s].w);
+            for (int s4 = 0; s4 < SMAX / 4; ++s4) {
+              if (s4 * 4 < Sn) {
+                const float4 cv = __ldg(reinterpret_cast<const float4*>(S + (long)k * s_ks) + s4);
+                const float c4[4] = {cv.x, cv.y, cv.z, cv.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const int s = s4 * 4 + e;  // rows s >= Sn accumulate padding values that are never written out
+                  acc[s].x = fmaf(c4[e], v[u].x, acc[s].x); acc[s].y = fmaf(c4[e], v[u].y, acc[s].y);
+                  acc[s].z = fmaf(c4[e], v[u].z, acc[s].z); acc[s].w = fmaf(c4[e], v[u].w, acc[s].w);
+                }
+              }
+            }
+          } else {
+#pragma unroll
+            for (int s = 0; s < SMAX; ++s) {
+              if (s < Sn) {
+                const float c = S != nullptr ? __ldg(S + (long)k * s_ks + s * s_ss) : 1.f;
+                acc[s].x = fmaf(c, v[u].x, acc[s].x); acc[s].y = fmaf(c, v[u].y, acc[s].y);
+                acc[s].z = fmaf(c, v[u].z, acc[s].z); acc[s].w = fmaf(c, v[u].w, acc[s].w);
+              }
             }
           }
         }
@@ -243,6 +292,26 @@ __global__ void __launch_bounds__(256) gemm_tallt_reduce_kernel(const float* __r
 inline bool al16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
 int launch_smalln(const SkArgs& g, cudaStream_t st) {
+  // many rows and a B' that fits shared memory: stage it (persistent-style grid, every CTA stages B' once)
+  const size_t bbytes = (size_t)g.N * g.K * sizeof(float);
+  if (g.M >= 1024 && g.N > 4 && bbytes <= 96 * 1024) {
+    static bool attr = false;
+    if (!attr) {
+      cudaFuncSetAttribute(gemm_smalln_kernel<8, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      cudaFuncSetAttribute(gemm_smalln_kernel<16, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      cudaFuncSetAttribute(gemm_smalln_kernel<32, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      attr = true;
+    }
+    const int R = g.N <= 16 ? 2 : 1;
+    int grid = ceil_div(ceil_div(g.M, R), 8);
+    const int cap = 148 * (bbytes <= 32 * 1024 ? 4 : 2);
+    if (grid > cap) grid = cap;
+    if (g.N <= 8) gemm_smalln_kernel<8, 2, true><<<grid, 256, bbytes, st>>>(g);
+    else if (g.N <= 16) gemm_smalln_kernel<16, 2, true><<<grid, 256, bbytes, st>>>(g);
+    else gemm_smalln_kernel<32, 1, true><<<grid, 256, bbytes, st>>>(g);
+    IMMTSF_CHECK_LAUNCH("gemm_smalln");
+    return IMMTSF_OK;
+  }
   const bool few = g.M < 148 * 16 * 4;  // few rows: one or two rows per warp so that every SM has warps to hide latency
   const int R = g.N <= 8 ? (few ? (g.M < 148 * 16 * 2 ? 1 : 2) : 4) : (g.N <= 16 ? 2 : 1);
   const int warps = ceil_div(g.M, R);

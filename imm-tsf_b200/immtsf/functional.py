@@ -375,6 +375,7 @@ class XAttnAddRankFn(torch.autograd.Function):
         d, de = W_Q.shape[0], E.shape[2]
         hd, C1 = d // H, C + 1
         n1, nr = H * C1, H * (2 * C + 1)
+        nrp = ops.round_up(nr, 4)  # rows of R / dR are padded to 16 bytes (vector loads in the skinny kernels); pads unused
         dev = Y.device
         new = lambda *s: torch.empty(*s, dtype=_f32, device=dev)
         Y2 = Y.contiguous().view(B * T, C)
@@ -392,12 +393,12 @@ class XAttnAddRankFn(torch.autograd.Function):
             hs, ra, rg = slice(h * hd, (h + 1) * hd), slice(h * C1, (h + 1) * C1), slice(n1 + h * C, n1 + (h + 1) * C)
             ops.gemm(Wq_aug[hs], in_k[hs], P1[h], transA=True)  # Wq_aug_h^T in_k_h            [C1, d]
             ops.gemm(P1[h], W_K, Wr[ra])  # A_h                                                  [C1, de]
-            ops.gemm(Wq_aug[hs], b_k[hs].view(hd, 1), br[ra].view(C1, 1), transA=True)  # a0_h
+            ops.gemm(b_k[hs].view(1, hd), Wq_aug[hs], br[ra].view(1, C1))  # a0_h^T = b_k_h^T Wq_aug_h
             ops.gemm(Wo_f[:, hs], in_v[hs], P2[h])  # Wo_f_h in_v_h                              [C, d]
             ops.gemm(P2[h], W_V, Wr[rg])  # G_h                                                  [C, de]
             ops.gemm(Wo_f[:, hs], b_v[hs].view(hd, 1), br[rg].view(C, 1))  # g0_h
         # ---- the one pass over E_txt, then the T x (2C+1) attention and the tail
-        R = ops.gemm(E2, Wr, new(B * T, nr), transB=True, bias=br)
+        R = ops.gemm(E2, Wr, new(B * T, nrp)[:, :nr], transB=True, bias=br)
         delta_y, probs = ops.xattn_rank_fwd(Y2, R, bo_f, m_txt, B, T, H, d, C, thr, seed, save)
         Y_out = ops.xattn_tail_fwd(Y2, delta_y, gamma, beta, m_txt, B, T, C, kappa, thr, seed, flags)
         if save:

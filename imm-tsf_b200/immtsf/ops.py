@@ -600,7 +600,7 @@ def xattn_rank_fwd(Y2, R, bo, m_txt, B, T, H, d, C, thr, seed, save):
 
 
 def xattn_rank_bwd(d_delta, Y2, R, probs, m_txt, B, T, H, d, C, thr, seed):
-    dR = torch.empty_like(R)
+    dR = torch.empty(R.shape[0], R.stride(0), dtype=torch.float32, device=R.device)[:, : R.shape[1]]  # same padding as R
     dY = torch.empty(B * T, C, dtype=torch.float32, device=R.device)
     _lib.call("immtsf_xattn_rank_bwd", _p(d_delta), _p(Y2), Y2.stride(0), _p(R), R.stride(0), _p(probs), _p(m_txt), B, T, H, d, C,
               thr, seed, _p(dR), dR.stride(0), _p(dY), _stream())
