@@ -294,7 +294,7 @@ inline bool al16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 int launch_smalln(const SkArgs& g, cudaStream_t st) {
   // many rows and a B' that fits shared memory: stage it (persistent-style grid, every CTA stages B' once)
   const size_t bbytes = (size_t)g.N * g.K * sizeof(float);
-  if (g.M >= 1024 && g.N > 4 && bbytes <= 96 * 1024) {
+  if (g.M >= 256 && g.N > 4 && bbytes <= 96 * 1024) {
     static bool attr = false;
     if (!attr) {
       cudaFuncSetAttribute(gemm_smalln_kernel<8, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);

@@ -9,6 +9,8 @@ host syncs (:103-112) plus the ones inside the TTF/MMF modules are folded into
 device flags read once at the end of forward (still raising ValueError)."""
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -73,13 +75,29 @@ class FusionModel(nn.Module):
         # one operand-split cache for the whole step: E_txt (and dE_txt in backward) are handed from one module's GEMM
         # epilogue to the other module's product together with their tcgen05 lo operand
         T = t_hat.shape[-1]
-        ops.begin_step(e_txt_feeds_tc=isinstance(self.mmf, MMF_XAttn_Add) and not self.mmf.rank_path(T))
+        rank = isinstance(self.mmf, MMF_XAttn_Add) and self.mmf.rank_path(T)
+        # rank form of MMF_XAttn_Add: E_txt only enters through one skinny product, so the TTF's final projection is folded
+        # into that operand in weight space and E_txt [B, T, d] is never materialised (IMMTSF_FUSE_PROJ=0 keeps it)
+        defer = rank and self.ttf.can_defer() and os.environ.get("IMMTSF_FUSE_PROJ", "1") != "0"
+        ops.begin_step(e_txt_feeds_tc=isinstance(self.mmf, MMF_XAttn_Add) and not rank)
         try:
-            return self._forward_step(r, t_hat, Y32, flags, check)
+            return self._forward_step(r, t_hat, Y32, flags, check, defer)
         finally:
             ops.end_step()
 
-    def _forward_step(self, r, t_hat, Y32, flags, check):
+    def _forward_step(self, r, t_hat, Y32, flags, check, defer):
+        if defer:
+            E_txt, M_txt = self.ttf.forward_ragged(r, t_hat, defer=True)
+            W_p, b_p = self.ttf.final_proj()
+            if check:  # E_txt_true has a NaN iff one of its three factors has one
+                for t in (E_txt, W_p, b_p):
+                    ops.nan_check(t, flags, ops.FLAG_E)
+            hook = getattr(self, "_e_txt_grad_hook", None)
+            if hook is not None and E_txt.requires_grad:
+                E_txt.register_hook(hook)
+            Y_out = self.mmf.forward_flags(Y32, E_txt, M_txt, flags, final_proj=(W_p, b_p))
+            runtime.raise_on_flags(flags)
+            return Y_out
         E_txt, M_txt = self.ttf.forward_ragged(r, t_hat)
         hook = getattr(self, "_e_txt_grad_hook", None)
         if hook is not None and E_txt.requires_grad:

@@ -28,7 +28,9 @@ class MMF_XAttn_Add(nn.Module):
         self.layer_norm = nn.LayerNorm(C)
         self.dropout = nn.Dropout(dropout)
 
-    def forward_flags(self, Y_ts, E_txt, M_txt, flags):
+    def forward_flags(self, Y_ts, E_txt, M_txt, flags, final_proj=None):
+        """final_proj = (W_p, b_p): E_txt is handed in WITHOUT the producer's last projection (E_txt_true = E_txt W_p^T +
+        b_p); only valid on the rank path, which folds it into its skinny operand."""
         cm.require_cuda(Y_ts, "MMF_XAttn_Add")
         B, T, C = Y_ts.shape
         thr, seed = cm.dropout_args(self.dropout.p, self.training)
@@ -40,8 +42,13 @@ class MMF_XAttn_Add(nn.Module):
         own_flags = flags if flags is not None else runtime.new_flags(Y_ts.device)
         # Time-IMM shapes (T <= 32, few channels): the rank-(2C+1) form -- one skinny pass over E_txt, no tensor of width d
         fn = F_.XAttnAddRankFn if self.rank_path(T) else F_.XAttnAddFn
+        extra = ()
+        if fn is F_.XAttnAddRankFn:
+            extra = tuple(final_proj) if final_proj is not None else (None, None)
+        elif final_proj is not None:
+            raise RuntimeError("MMF_XAttn_Add: a deferred projection needs the rank path")
         out = fn.apply(cm.as_f32(Y_ts), cm.as_f32(E_txt), cm.m_txt_u8(M_txt, B), self.n_heads, float(self.kappa),
-                                  thr, seed, save, own_flags, *params)
+                       thr, seed, save, own_flags, *params, *extra)
         if flags is None:  # standalone call: keep the reference's "delta_y contains NaN" ValueError (:84-91)
             if runtime.nan_check_enabled() and own_flags.tolist()[ops.FLAG_OUT]:
                 raise ValueError("delta_y contains NaN values.")

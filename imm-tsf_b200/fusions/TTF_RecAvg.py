@@ -38,14 +38,23 @@ class TTF_RecAvg(nn.Module):
         self.dropout = nn.Dropout(dropout)
 
     # -- ragged entry point (shared CSR + NaN flags when called from FusionModel)
-    def forward_ragged(self, r: ops.RaggedNotes, t_hat: torch.Tensor):
+    def final_proj(self):
+        """The last linear map of forward (TTF_RecAvg.py:109), which a consumer may fold into its own operand."""
+        return self.proj.weight, self.proj.bias
+
+    def can_defer(self) -> bool:
+        return True
+
+    def forward_ragged(self, r: ops.RaggedNotes, t_hat: torch.Tensor, defer: bool = False):
+        """defer=True: return dropout(LN(E_raw)) without `proj`; the caller applies final_proj() (FusionModel fuses it
+        into the rank form of MMF_XAttn_Add)."""
         t_hat, T = cm.fix_t_hat(t_hat, r.B)
         thr, seed = cm.dropout_args(self.dropout.p, self.training)
         ip = self.input_proj
         params = (self.log_recency_sigma, ip.weight if ip is not None else None, ip.bias if ip is not None else None,
                   self.layer_norm.weight, self.layer_norm.bias, self.proj.weight, self.proj.bias)
         save = F_._need_save(*params)
-        E_txt = F_.RecAvgFn.apply(r, t_hat, T, thr, seed, save, *params)
+        E_txt = F_.RecAvgFn.apply(r, t_hat, T, thr, seed, save, bool(defer), *params)
         return E_txt, cm.m_txt_bool(r)
 
     def forward(self, notes_input, tau: torch.Tensor, t_hat: torch.Tensor):

@@ -59,7 +59,17 @@ class TTF_T2V_XAttn(nn.Module):
         self.proj_out = nn.Linear(self.d_txt, self.d_txt)
         self.Q_param = nn.Parameter(torch.randn(1, 1, self.d_txt))
 
-    def forward_ragged(self, r: ops.RaggedNotes, t_hat: torch.Tensor):
+    def final_proj(self):
+        """The last linear map of forward (TTF_T2V_XAttn.py:182), which a consumer may fold into its own operand."""
+        return self.proj_out.weight, self.proj_out.bias
+
+    def can_defer(self) -> bool:
+        """Only when every (sample, query time) row is distinct (train mode with attention dropout); in eval the T_f rows
+        of a sample are one broadcast row."""
+        return self.training and ops.drop_thr(self.dropout.p) != 0
+
+    def forward_ragged(self, r: ops.RaggedNotes, t_hat: torch.Tensor, defer: bool = False):
+        """defer=True: return dropout(LN(attn + Q)) without proj_out; the caller applies final_proj()."""
         _, T = cm.fix_t_hat(t_hat, r.B)  # only the length of t_hat matters (reference :143,150)
         thr, seed = cm.dropout_args(self.dropout.p, self.training)
         ip, t2v, at = self.input_proj, self.time2vec, self.attn
@@ -69,7 +79,7 @@ class TTF_T2V_XAttn(nn.Module):
                   at.out_proj.weight, at.out_proj.bias, self.layer_norm.weight, self.layer_norm.bias,
                   self.proj_out.weight, self.proj_out.bias)
         save = F_._need_save(*params)
-        E_txt = F_.T2VXAttnFn.apply(r, T, self.n_heads, thr, seed, save, *params)
+        E_txt = F_.T2VXAttnFn.apply(r, T, self.n_heads, thr, seed, save, bool(defer), *params)
         return E_txt, cm.m_txt_bool(r)
 
     def forward(self, notes_input, tau: torch.Tensor, t_hat: torch.Tensor):

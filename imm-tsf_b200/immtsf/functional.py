@@ -27,17 +27,22 @@ def _need_save(*params) -> bool:
 # ============================================================== TTF_RecAvg
 class RecAvgFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, r: RaggedNotes, t_hat, T, thr, seed, save, log_sigma, W_in, b_in, gamma, beta, W_p, b_p):
+    def forward(ctx, r: RaggedNotes, t_hat, T, thr, seed, save, defer, log_sigma, W_in, b_in, gamma, beta, W_p, b_p):
+        """defer: return dropout(LN(E_raw)) WITHOUT the final `proj` (TTF_RecAvg.py:109) -- the consumer (the rank form of
+        MMF_XAttn_Add) folds W_p into its own skinny operand, and E_txt is never materialised."""
         B = r.B
         d = W_p.shape[0]
         step = ops.step_ctx()
         lo = step.lo
-        ops.weight_los(lo, [(w, []) for w in (W_in, W_p) if w is not None])
+        ops.weight_los(lo, [(w, []) for w in ((W_in,) if defer else (W_in, W_p)) if w is not None])
         Vp = ops.linear_fwd(r.emb_flat, W_in, b_in, ragged=r.m_dev, lo=lo) if W_in is not None else r.emb_flat
         E_drop, E_raw, mean, rstd, wsum = ops.recavg_pool_fwd(Vp, r, t_hat, log_sigma, gamma, beta, T, d, thr, seed, save)
-        E_txt = ops.linear_fwd(E_drop.view(B * T, d), W_p, b_p, lo=lo, emit_lo=step.e_txt_feeds_tc).view(B, T, d)
+        if defer:
+            E_txt = E_drop.view(B, T, d)
+        else:
+            E_txt = ops.linear_fwd(E_drop.view(B * T, d), W_p, b_p, lo=lo, emit_lo=step.e_txt_feeds_tc).view(B, T, d)
         if save:
-            ctx.r, ctx.T, ctx.thr, ctx.seed, ctx.has_in, ctx.lo = r, T, thr, seed, W_in is not None, lo
+            ctx.r, ctx.T, ctx.thr, ctx.seed, ctx.has_in, ctx.lo, ctx.defer = r, T, thr, seed, W_in is not None, lo, defer
             ctx.save_for_backward(t_hat, log_sigma, W_in, gamma, W_p, Vp, E_drop, E_raw, mean, rstd, wsum)
         return E_txt
 
@@ -48,16 +53,20 @@ class RecAvgFn(torch.autograd.Function):
         ctx.lo = None
         B, d = r.B, W_p.shape[0]
         dE = dE_txt.contiguous().view(B * T, d)
-        dW_p = ops.linear_wgrad(dE, E_drop.view(B * T, d), lo=lo)
-        db_p = ops.colsum(dE)
-        dE_drop = ops.linear_dgrad(dE, W_p, lo=lo)
+        if ctx.defer:
+            dW_p = db_p = None  # the consumer returns these
+            dE_drop = dE
+        else:
+            dW_p = ops.linear_wgrad(dE, E_drop.view(B * T, d), lo=lo)
+            db_p = ops.colsum(dE)
+            dE_drop = ops.linear_dgrad(dE, W_p, lo=lo)
         dVp, dgamma, dbeta, dls = ops.recavg_pool_bwd(dE_drop, E_raw, mean, rstd, wsum, Vp, r, t_hat, log_sigma, gamma, T, d,
                                                       ctx.thr, ctx.seed)
         dW_in = db_in = None
         if ctx.has_in:
             dW_in = ops.linear_wgrad(dVp, r.emb_flat, ragged=r.m_dev, lo=lo)
             db_in = ops.colsum(dVp, ragged=r.m_dev)
-        return None, None, None, None, None, None, dls, dW_in, db_in, dgamma, dbeta, dW_p, db_p
+        return None, None, None, None, None, None, None, dls, dW_in, db_in, dgamma, dbeta, dW_p, db_p
 
 
 # ============================================================== TTF_T2V_XAttn
@@ -68,8 +77,10 @@ class T2VXAttnFn(torch.autograd.Function):
     (sample, query) row; its bias is added inside the LayerNorm kernel (xbias)."""
 
     @staticmethod
-    def forward(ctx, r: RaggedNotes, T, H, thr, seed, save, Qp, W_in, b_in, w_lin, b_lin, w_per, b_per, W_kv, b_kv,
+    def forward(ctx, r: RaggedNotes, T, H, thr, seed, save, defer, Qp, W_in, b_in, w_lin, b_lin, w_per, b_per, W_kv, b_kv,
                 in_w, in_b, out_w, out_b, gamma, beta, W_po, b_po):
+        """defer (train mode with attention dropout only): return dropout(LN(attn + Q)) WITHOUT proj_out (:182); the rank
+        form of MMF_XAttn_Add folds W_po into its skinny operand and returns its gradient."""
         B = r.B
         d = W_po.shape[0]
         dt = d // 2
@@ -90,7 +101,7 @@ class T2VXAttnFn(torch.autograd.Function):
         if W_in is None:
             extra.append((r.emb_flat, Xcat[:, :d], Xcat_lo[:, :d]))
         ws = [(W_in, [])] if W_in is not None else []
-        ws += [(W_kv, []), (in_w, [slice(d, None), slice(2 * d, None)]), (out_w, []), (W_po, [])]
+        ws += [(W_kv, []), (in_w, [slice(d, None), slice(2 * d, None)]), (out_w, [])] + ([] if defer else [(W_po, [])])
         ops.weight_los(lo, ws, extra)
         if W_in is not None:
             ops.gemm(r.emb_flat, W_in, Xcat[:, :d], transB=True, bias=b_in, ragged=r.m_dev, ragged_dim=1, lo=lo,
@@ -113,9 +124,10 @@ class T2VXAttnFn(torch.autograd.Function):
         rps = T if per_query else 1
         y, mean, rstd = ops.ln_fwd(attn_out, Qp.view(d), r.m_txt, rps, gamma, beta, thr, seed, ops.SITE_TTF_DROPOUT, save,
                                    xbias=out_b if fold else None)
-        E = ops.linear_fwd(y, W_po, b_po, lo=lo, emit_lo=step.e_txt_feeds_tc)
+        assert not defer or per_query, "defer needs per-(sample, query) rows"
+        E = y if defer else ops.linear_fwd(y, W_po, b_po, lo=lo, emit_lo=step.e_txt_feeds_tc)
         if save:
-            ctx.r, ctx.T, ctx.H, ctx.thr, ctx.seed, ctx.lo = r, T, H, thr, seed, lo
+            ctx.r, ctx.T, ctx.H, ctx.thr, ctx.seed, ctx.lo, ctx.defer = r, T, H, thr, seed, lo, defer
             ctx.has_in, ctx.per_query, ctx.scale, ctx.fold = W_in is not None, per_query, scale, fold
             ctx.save_for_backward(Qp, w_per, b_per, W_kv, in_w, in_b, out_w, out_b, gamma, W_po, Xcat, X, Wkv, KVp, q, attn_cat,
                                   probs, attn_out, y, mean, rstd)
@@ -134,9 +146,13 @@ class T2VXAttnFn(torch.autograd.Function):
         per_query = ctx.per_query
         dEc = dE_txt.contiguous()
         dE = dEc.view(B * T, d) if per_query else ops.group_sum_rows(dEc.view(B * T, d), B, T, d)
-        dW_po = ops.linear_wgrad(dE, y, lo=lo)
-        db_po = ops.colsum(dE)
-        dy = ops.linear_dgrad(dE, W_po, lo=lo)
+        if ctx.defer:
+            dW_po = db_po = None  # the consumer returns these
+            dy = dE
+        else:
+            dW_po = ops.linear_wgrad(dE, y, lo=lo)
+            db_po = ops.colsum(dE)
+            dy = ops.linear_dgrad(dE, W_po, lo=lo)
         rps = T if per_query else 1
         dx, dres, dgamma, dbeta = ops.ln_bwd(dy, attn_out, Qp.view(d), r.m_txt, rps, gamma, mean, rstd, thr, seed,
                                              ops.SITE_TTF_DROPOUT, xbias=out_b if fold else None)
@@ -185,7 +201,7 @@ class T2VXAttnFn(torch.autograd.Function):
         if ctx.has_in:
             dW_in = ops.linear_wgrad(dXcat[:, :d], r.emb_flat, ragged=r.m_dev, lo=lo)
             db_in = ops.colsum(dXcat[:, :d], ragged=r.m_dev)
-        return (None, None, None, None, None, None, dQp.view(1, 1, d), dW_in, db_in, dwl, dbl, dwp, dbp, dW_kv, db_kv,
+        return (None, None, None, None, None, None, None, dQp.view(1, 1, d), dW_in, db_in, dwl, dbl, dwp, dbp, dW_kv, db_kv,
                 d_in_w, d_in_b, dW_o, db_o, dgamma, dbeta, dW_po, db_po)
 
 
@@ -370,16 +386,19 @@ class XAttnAddRankFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, Y, E, m_txt, H, kappa, thr, seed, save, flags, W_Q, W_K, W_V, in_w, in_b, out_w, out_b, W_r, b_r,
-                gamma, beta):
+                gamma, beta, W_p=None, b_p=None):
+        """W_p, b_p (optional): the producer's final projection, E_txt = E W_p^T + b_p with E the tensor handed in
+        (TTF `proj` / `proj_out`, deferred).  It is folded into the skinny operand -- R = E (Wr W_p)^T + (Wr b_p + br) --
+        so E_txt [B, T, d] is never formed; this Function then also returns the gradients of W_p and b_p."""
         B, T, C = Y.shape
-        d, de = W_Q.shape[0], E.shape[2]
+        d, de = W_Q.shape[0], W_K.shape[1]
         hd, C1 = d // H, C + 1
         n1, nr = H * C1, H * (2 * C + 1)
         nrp = ops.round_up(nr, 4)  # rows of R / dR are padded to 16 bytes (vector loads in the skinny kernels); pads unused
         dev = Y.device
         new = lambda *s: torch.empty(*s, dtype=_f32, device=dev)
         Y2 = Y.contiguous().view(B * T, C)
-        E2 = E.contiguous().view(B * T, de)
+        E2 = E.contiguous().view(B * T, E.shape[2])
         in_k, in_v, b_k, b_v = in_w[d:2 * d], in_w[2 * d:], in_b[d:2 * d], in_b[2 * d:]
         # ---- weight space
         Wq_aug = new(d, C1)
@@ -397,20 +416,26 @@ class XAttnAddRankFn(torch.autograd.Function):
             ops.gemm(Wo_f[:, hs], in_v[hs], P2[h])  # Wo_f_h in_v_h                              [C, d]
             ops.gemm(P2[h], W_V, Wr[rg])  # G_h                                                  [C, de]
             ops.gemm(Wo_f[:, hs], b_v[hs].view(hd, 1), br[rg].view(C, 1))  # g0_h
+        if W_p is not None:  # fold the producer's last projection: Wr_eff = Wr W_p, br_eff = Wr b_p + br
+            Wr_eff = ops.gemm(Wr, W_p, new(nr, W_p.shape[1]))
+            br_eff = ops.gemm(Wr, b_p.view(de, 1), new(nr, 1)).view(nr)  # one warp per row of Wr
+            ops.axpby(br, 1.0, br_eff, True)
+        else:
+            Wr_eff, br_eff = Wr, br
         # ---- the one pass over E_txt, then the T x (2C+1) attention and the tail
-        R = ops.gemm(E2, Wr, new(B * T, nrp)[:, :nr], transB=True, bias=br)
+        R = ops.gemm(E2, Wr_eff, new(B * T, nrp)[:, :nr], transB=True, bias=br_eff)
         delta_y, probs = ops.xattn_rank_fwd(Y2, R, bo_f, m_txt, B, T, H, d, C, thr, seed, save)
         Y_out = ops.xattn_tail_fwd(Y2, delta_y, gamma, beta, m_txt, B, T, C, kappa, thr, seed, flags)
         if save:
             ctx.H, ctx.kappa, ctx.thr, ctx.seed, ctx.dims = H, kappa, thr, seed, (B, T, C, d, de)
             ctx.save_for_backward(m_txt, Y2, E2, W_Q, W_K, W_V, in_w, in_b, out_w, out_b, W_r, gamma, Wq_aug, Wo_f, P1, P2, Wr, R,
-                                  probs, delta_y)
+                                  probs, delta_y, W_p, b_p, Wr_eff if W_p is not None else None)
         return Y_out
 
     @staticmethod
     def backward(ctx, dY_out):
         (m_txt, Y2, E2, W_Q, W_K, W_V, in_w, in_b, out_w, out_b, W_r, gamma, Wq_aug, Wo_f, P1, P2, Wr, R, probs,
-         delta_y) = ctx.saved_tensors
+         delta_y, W_p, b_p, Wr_eff) = ctx.saved_tensors
         B, T, C, d, de = ctx.dims
         H, kappa, thr, seed = ctx.H, ctx.kappa, ctx.thr, ctx.seed
         hd, C1 = d // H, C + 1
@@ -423,9 +448,20 @@ class XAttnAddRankFn(torch.autograd.Function):
         dbo_f = ops.colsum(d_delta)  # = d(b_r)
         dR, dY = ops.xattn_rank_bwd(d_delta, Y2, R, probs, m_txt, B, T, H, d, C, thr, seed)
         ops.axpby(dY_out.view(B * T, C), 1.0 / (1.0 + kappa), dY, True)  # the blend passes Y straight through
-        dWr = ops.gemm(dR, E2, new(nr, de), transA=True)
-        dbr = ops.colsum(dR)
-        dE = ops.gemm(dR, Wr, new(B * T, de))
+        dW_p = db_p = None
+        if W_p is None:
+            dWr = ops.gemm(dR, E2, new(nr, de), transA=True)
+            dbr = ops.colsum(dR)
+            dE = ops.gemm(dR, Wr, new(B * T, de))
+        else:  # un-fold Wr_eff = Wr W_p, br_eff = Wr b_p + br
+            dk = W_p.shape[1]
+            dWr_eff = ops.gemm(dR, E2, new(nr, dk), transA=True)
+            dbr = ops.colsum(dR)
+            dE = ops.gemm(dR, Wr_eff, new(B * T, dk))
+            dWr = ops.gemm(dWr_eff, W_p, new(nr, de), transB=True)
+            ops.gemm(dbr.view(nr, 1), b_p.view(1, de), dWr, beta=1.0)
+            dW_p = ops.gemm(Wr, dWr_eff, new(de, dk), transA=True)
+            db_p = ops.gemm(Wr, dbr.view(nr, 1), new(de, 1), transA=True).view(de)
         # ---- weight space: every product C = A B gives dA = dC B^T, dB = A^T dC
         d_in_w, d_in_b = torch.empty_like(in_w), new(3 * d)
         d_in_k, d_in_v, db_k, db_v = d_in_w[d:2 * d], d_in_w[2 * d:], d_in_b[d:2 * d], d_in_b[2 * d:]
@@ -457,5 +493,5 @@ class XAttnAddRankFn(torch.autograd.Function):
         ops.gemm(dWq_f, W_Q, d_in_w[:d], transB=True)
         dW_Q = ops.gemm(in_w[:d], dWq_f, new(d, C), transA=True)
         ops.multi_split([(dWq_aug[:, C:], d_in_b[:d].view(d, 1), None)])
-        return (dY.view(B, T, C), dE.view(B, T, de), None, None, None, None, None, None, None, dW_Q, dW_K, dW_V,
-                d_in_w, d_in_b, dW_o, db_o, dW_r, dbo_f, dgamma, dbeta)
+        return (dY.view(B, T, C), dE.view(B, T, dE.shape[1]), None, None, None, None, None, None, None, dW_Q, dW_K, dW_V,
+                d_in_w, d_in_b, dW_o, db_o, dW_r, dbo_f, dgamma, dbeta, dW_p, db_p)

@@ -404,3 +404,23 @@ def test_mmf_xattn_rank_path_is_selected_for_time_imm_shapes():
 
     assert ops.xattn_rank_ok(24, 1, 768, 4) and ops.xattn_rank_ok(32, 2, 64, 31)
     assert not ops.xattn_rank_ok(33, 1, 768, 4) and not ops.xattn_rank_ok(24, 4, 768, 31)
+
+
+@pytest.mark.parametrize("ttf", ["TTF_RecAvg", "TTF_T2V_XAttn"])
+def test_folded_final_projection_equals_materialised_e_txt(ttf, monkeypatch):
+    """FusionModel folds the TTF's final projection (proj / proj_out) into the rank operand of MMF_XAttn_Add, so E_txt is
+    never formed; IMMTSF_FUSE_PROJ=0 materialises it.  Same dropout masks, same results: outputs and every gradient
+    (W_p / b_p gradients come from the MMF Function in the folded schedule)."""
+    cfg = dict(ttf=ttf, mmf="MMF_XAttn_Add", d_txt=64, C=4, H=2, kappa=0.5)
+    fm = G.build_model(cfg, 96, dropout=0.2, seed=5)
+    G.randomise_(fm, 6)
+    notes, tau, t_hat, Y, Gw = G.synth_batch(12, 7, 13, 96, 4, 7)
+    assert fm.mmf.rank_path(13)
+    fused = G.gpu_run(fm, notes, tau, t_hat, Y, Gw, train=True)
+    monkeypatch.setenv("IMMTSF_FUSE_PROJ", "0")
+    plain = G.gpu_run(fm, notes, tau, t_hat, Y, Gw, train=True)
+    G.assert_close("Y_out", fused["Y_out"], plain["Y_out"], 2e-6)
+    G.assert_close("dY", fused["dY"], plain["dY"], 1e-5)
+    gmax = max(float(v.abs().max()) for v in plain["grads"].values())
+    for k, g in plain["grads"].items():
+        G.assert_close(k, fused["grads"][k], g, 2e-5, floor=1e-3 * gmax)
