@@ -81,24 +81,33 @@ class FusionModel(nn.Module):
         defer = rank and self.ttf.can_defer() and os.environ.get("IMMTSF_FUSE_PROJ", "1") != "0"
         ops.begin_step(e_txt_feeds_tc=isinstance(self.mmf, MMF_XAttn_Add) and not rank)
         try:
-            return self._forward_step(r, t_hat, Y32, flags, check, defer)
+            return self._forward_step(r, t_hat, Y32, flags, check, defer, rank)
         finally:
             ops.end_step()
 
-    def _forward_step(self, r, t_hat, Y32, flags, check, defer):
+    def _forward_step(self, r, t_hat, Y32, flags, check, defer, rank):
+        # the weight-space half of the rank form depends on parameters only: it runs on a side stream beside the TTF
+        # forward (and, through autograd, its backward beside the TTF backward).  IMMTSF_SIDE_STREAM=0 keeps one stream.
+        side = os.environ.get("IMMTSF_SIDE_STREAM", "1") != "0"
         if defer:
-            E_txt, M_txt = self.ttf.forward_ragged(r, t_hat, defer=True)
             W_p, b_p = self.ttf.final_proj()
+            wts = self.mmf.rank_weights((W_p, b_p), side=side)
+            E_txt, M_txt = self.ttf.forward_ragged(r, t_hat, defer=True)
+            if side:
+                self.mmf.wait_rank_weights(wts)
             if check:  # E_txt_true has a NaN iff one of its three factors has one
                 for t in (E_txt, W_p, b_p):
                     ops.nan_check(t, flags, ops.FLAG_E)
             hook = getattr(self, "_e_txt_grad_hook", None)
             if hook is not None and E_txt.requires_grad:
                 E_txt.register_hook(hook)
-            Y_out = self.mmf.forward_flags(Y32, E_txt, M_txt, flags, final_proj=(W_p, b_p))
+            Y_out = self.mmf.forward_flags(Y32, E_txt, M_txt, flags, final_proj=(W_p, b_p), rank_weights=wts)
             runtime.raise_on_flags(flags)
             return Y_out
+        wts = self.mmf.rank_weights(None, side=side) if rank else None
         E_txt, M_txt = self.ttf.forward_ragged(r, t_hat)
+        if rank and side:
+            self.mmf.wait_rank_weights(wts)
         hook = getattr(self, "_e_txt_grad_hook", None)
         if hook is not None and E_txt.requires_grad:
             # data-parallel overlap (immtsf/runtime.py GraphedStep): called when backward crosses the MMF -> TTF
@@ -107,6 +116,9 @@ class FusionModel(nn.Module):
         if check:
             # the broadcast view of T2V eval mode has B distinct rows: check those only
             ops.nan_check(E_txt[:, :1] if E_txt.stride(1) == 0 else E_txt, flags, ops.FLAG_E)
-        Y_out = self.mmf.forward_flags(Y32, E_txt, M_txt, flags)
+        if rank:
+            Y_out = self.mmf.forward_flags(Y32, E_txt, M_txt, flags, rank_weights=wts)
+        else:
+            Y_out = self.mmf.forward_flags(Y32, E_txt, M_txt, flags)
         runtime.raise_on_flags(flags)
         return Y_out

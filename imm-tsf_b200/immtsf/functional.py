@@ -374,33 +374,23 @@ class XAttnAddFn(torch.autograd.Function):
                 d_in_w, d_in_b, dW_o, db_o, dW_r, db_r, dgamma, dbeta)
 
 
-class XAttnAddRankFn(torch.autograd.Function):
-    """MMF_XAttn_Add.py:56-103 for the Time-IMM case (T <= 32, few channels): the rank-(2C+1) form of csrc/xattn_rank.cu.
-
-    Queries are projections of the C-channel series and the output goes through residual_head back to C channels, so
-        score_ij = [y_i ; 1] . kq_j / sqrt(hd),  kq_j = A e_j + a0,   A = Wq_aug^T in_k W_K,  Wq_aug = [in_q W_Q | b_q]
-        delta_i  = sum_h sum_j P~_ij vo_j + bo,  vo_j = G e_j + g0,   G = Wo_f in_v W_V,      Wo_f = W_r W_o
-    (per head: the rows of in_k / in_v and the columns of Wo_f that belong to the head).  The only pass over the wide
-    data is R = E_txt [A ; G]^T + [a0 ; g0]; q, k, v, o and their gradients never exist, and the d x d weight matrices
-    only meet in skinny weight-space products (each is one immtsf_gemm call below, with its two backward products)."""
+class XAttnRankWeightsFn(torch.autograd.Function):
+    """Weight-space half of the rank-(2C+1) form of MMF_XAttn_Add (csrc/xattn_rank.cu): from the module's parameters to
+    the skinny operand of the data pass,
+        Wr = [A ; G] per head,  A_h = Wq_aug_h^T in_k_h W_K,  G_h = Wo_f_h in_v_h W_V,   br = [a0 ; g0],   bo_f = W_r b_o + b_r
+    with Wq_aug = [in_q W_Q | b_q] and Wo_f = W_r W_o, optionally composed with the producer's deferred final projection
+    (Wr_eff = Wr W_p, br_eff = Wr b_p + br).  Every product is one skinny immtsf_gemm; backward is the chain rule of each
+    (C = A B  =>  dA = dC B^T, dB = A^T dC).  It depends on parameters only, so FusionModel runs it on a side stream next
+    to the TTF forward, and autograd runs its backward on that stream next to the TTF backward."""
 
     @staticmethod
-    def forward(ctx, Y, E, m_txt, H, kappa, thr, seed, save, flags, W_Q, W_K, W_V, in_w, in_b, out_w, out_b, W_r, b_r,
-                gamma, beta, W_p=None, b_p=None):
-        """W_p, b_p (optional): the producer's final projection, E_txt = E W_p^T + b_p with E the tensor handed in
-        (TTF `proj` / `proj_out`, deferred).  It is folded into the skinny operand -- R = E (Wr W_p)^T + (Wr b_p + br) --
-        so E_txt [B, T, d] is never formed; this Function then also returns the gradients of W_p and b_p."""
-        B, T, C = Y.shape
+    def forward(ctx, H, C, W_Q, W_K, W_V, in_w, in_b, out_w, out_b, W_r, b_r, W_p, b_p):
         d, de = W_Q.shape[0], W_K.shape[1]
         hd, C1 = d // H, C + 1
         n1, nr = H * C1, H * (2 * C + 1)
-        nrp = ops.round_up(nr, 4)  # rows of R / dR are padded to 16 bytes (vector loads in the skinny kernels); pads unused
-        dev = Y.device
+        dev = W_Q.device
         new = lambda *s: torch.empty(*s, dtype=_f32, device=dev)
-        Y2 = Y.contiguous().view(B * T, C)
-        E2 = E.contiguous().view(B * T, E.shape[2])
         in_k, in_v, b_k, b_v = in_w[d:2 * d], in_w[2 * d:], in_b[d:2 * d], in_b[2 * d:]
-        # ---- weight space
         Wq_aug = new(d, C1)
         ops.multi_split([(in_b[:d].view(d, 1), Wq_aug[:, C:], None)])
         ops.gemm(in_w[:d], W_Q, Wq_aug[:, :C])
@@ -422,47 +412,30 @@ class XAttnAddRankFn(torch.autograd.Function):
             ops.axpby(br, 1.0, br_eff, True)
         else:
             Wr_eff, br_eff = Wr, br
-        # ---- the one pass over E_txt, then the T x (2C+1) attention and the tail
-        R = ops.gemm(E2, Wr_eff, new(B * T, nrp)[:, :nr], transB=True, bias=br_eff)
-        delta_y, probs = ops.xattn_rank_fwd(Y2, R, bo_f, m_txt, B, T, H, d, C, thr, seed, save)
-        Y_out = ops.xattn_tail_fwd(Y2, delta_y, gamma, beta, m_txt, B, T, C, kappa, thr, seed, flags)
-        if save:
-            ctx.H, ctx.kappa, ctx.thr, ctx.seed, ctx.dims = H, kappa, thr, seed, (B, T, C, d, de)
-            ctx.save_for_backward(m_txt, Y2, E2, W_Q, W_K, W_V, in_w, in_b, out_w, out_b, W_r, gamma, Wq_aug, Wo_f, P1, P2, Wr, R,
-                                  probs, delta_y, W_p, b_p, Wr_eff if W_p is not None else None)
-        return Y_out
+        ctx.H, ctx.C, ctx.dims = H, C, (d, de)
+        ctx.save_for_backward(W_Q, W_K, W_V, in_w, in_b, out_w, out_b, W_r, Wq_aug, Wo_f, P1, P2, Wr, W_p, b_p)
+        return Wr_eff, br_eff, bo_f
 
     @staticmethod
-    def backward(ctx, dY_out):
-        (m_txt, Y2, E2, W_Q, W_K, W_V, in_w, in_b, out_w, out_b, W_r, gamma, Wq_aug, Wo_f, P1, P2, Wr, R, probs,
-         delta_y, W_p, b_p, Wr_eff) = ctx.saved_tensors
-        B, T, C, d, de = ctx.dims
-        H, kappa, thr, seed = ctx.H, ctx.kappa, ctx.thr, ctx.seed
+    def backward(ctx, dWr_eff, dbr_eff, dbo_f):
+        W_Q, W_K, W_V, in_w, in_b, out_w, out_b, W_r, Wq_aug, Wo_f, P1, P2, Wr, W_p, b_p = ctx.saved_tensors
+        H, C = ctx.H, ctx.C
+        d, de = ctx.dims
         hd, C1 = d // H, C + 1
         n1, nr = H * C1, H * (2 * C + 1)
-        dev = Y2.device
+        dev = W_Q.device
         new = lambda *s: torch.empty(*s, dtype=_f32, device=dev)
         in_k, in_v, b_k, b_v = in_w[d:2 * d], in_w[2 * d:], in_b[d:2 * d], in_b[2 * d:]
-        dY_out = dY_out.contiguous()
-        d_delta, dgamma, dbeta = ops.xattn_tail_bwd(dY_out, delta_y, gamma, m_txt, B, T, C, kappa, thr, seed)
-        dbo_f = ops.colsum(d_delta)  # = d(b_r)
-        dR, dY = ops.xattn_rank_bwd(d_delta, Y2, R, probs, m_txt, B, T, H, d, C, thr, seed)
-        ops.axpby(dY_out.view(B * T, C), 1.0 / (1.0 + kappa), dY, True)  # the blend passes Y straight through
+        dWr_eff, dbr, dbo_f = dWr_eff.contiguous(), dbr_eff.contiguous(), dbo_f.contiguous()
         dW_p = db_p = None
         if W_p is None:
-            dWr = ops.gemm(dR, E2, new(nr, de), transA=True)
-            dbr = ops.colsum(dR)
-            dE = ops.gemm(dR, Wr, new(B * T, de))
+            dWr = dWr_eff
         else:  # un-fold Wr_eff = Wr W_p, br_eff = Wr b_p + br
             dk = W_p.shape[1]
-            dWr_eff = ops.gemm(dR, E2, new(nr, dk), transA=True)
-            dbr = ops.colsum(dR)
-            dE = ops.gemm(dR, Wr_eff, new(B * T, dk))
             dWr = ops.gemm(dWr_eff, W_p, new(nr, de), transB=True)
             ops.gemm(dbr.view(nr, 1), b_p.view(1, de), dWr, beta=1.0)
             dW_p = ops.gemm(Wr, dWr_eff, new(de, dk), transA=True)
             db_p = ops.gemm(Wr, dbr.view(nr, 1), new(de, 1), transA=True).view(de)
-        # ---- weight space: every product C = A B gives dA = dC B^T, dB = A^T dC
         d_in_w, d_in_b = torch.empty_like(in_w), new(3 * d)
         d_in_k, d_in_v, db_k, db_v = d_in_w[d:2 * d], d_in_w[2 * d:], d_in_b[d:2 * d], d_in_b[2 * d:]
         dWq_aug, dWo_f, dW_K, dW_V = new(d, C1), new(C, d), new(d, de), new(d, de)
@@ -493,5 +466,40 @@ class XAttnAddRankFn(torch.autograd.Function):
         ops.gemm(dWq_f, W_Q, d_in_w[:d], transB=True)
         dW_Q = ops.gemm(in_w[:d], dWq_f, new(d, C), transA=True)
         ops.multi_split([(dWq_aug[:, C:], d_in_b[:d].view(d, 1), None)])
-        return (dY.view(B, T, C), dE.view(B, T, dE.shape[1]), None, None, None, None, None, None, None, dW_Q, dW_K, dW_V,
-                d_in_w, d_in_b, dW_o, db_o, dW_r, dbo_f, dgamma, dbeta, dW_p, db_p)
+        return None, None, dW_Q, dW_K, dW_V, d_in_w, d_in_b, dW_o, db_o, dW_r, dbo_f, dW_p, db_p
+
+
+class XAttnRankDataFn(torch.autograd.Function):
+    """Data half of the rank form: R = E Wr^T + br (the one skinny pass over the text-side tensor), the T x (2C+1)
+    attention (immtsf_xattn_rank_*) and the LayerNorm / dropout / kappa-blend tail (MMF_XAttn_Add.py:83-102)."""
+
+    @staticmethod
+    def forward(ctx, Y, E, m_txt, H, kappa, thr, seed, save, flags, d, Wr, br, bo_f, gamma, beta):
+        B, T, C = Y.shape
+        nr = H * (2 * C + 1)
+        nrp = ops.round_up(nr, 4)  # rows of R / dR are padded to 16 bytes (vector loads in the skinny kernels); pads unused
+        Y2 = Y.contiguous().view(B * T, C)
+        E2 = E.contiguous().view(B * T, E.shape[2])
+        R = ops.gemm(E2, Wr, torch.empty(B * T, nrp, dtype=_f32, device=Y.device)[:, :nr], transB=True, bias=br)
+        delta_y, probs = ops.xattn_rank_fwd(Y2, R, bo_f, m_txt, B, T, H, d, C, thr, seed, save)
+        Y_out = ops.xattn_tail_fwd(Y2, delta_y, gamma, beta, m_txt, B, T, C, kappa, thr, seed, flags)
+        if save:
+            ctx.H, ctx.kappa, ctx.thr, ctx.seed, ctx.dims = H, kappa, thr, seed, (B, T, C, d)
+            ctx.save_for_backward(m_txt, Y2, E2, Wr, gamma, R, probs, delta_y)
+        return Y_out
+
+    @staticmethod
+    def backward(ctx, dY_out):
+        m_txt, Y2, E2, Wr, gamma, R, probs, delta_y = ctx.saved_tensors
+        B, T, C, d = ctx.dims
+        H, kappa, thr, seed = ctx.H, ctx.kappa, ctx.thr, ctx.seed
+        nr, dk = Wr.shape
+        dY_out = dY_out.contiguous()
+        d_delta, dgamma, dbeta = ops.xattn_tail_bwd(dY_out, delta_y, gamma, m_txt, B, T, C, kappa, thr, seed)
+        dbo_f = ops.colsum(d_delta)  # = d(b_r)
+        dR, dY = ops.xattn_rank_bwd(d_delta, Y2, R, probs, m_txt, B, T, H, d, C, thr, seed)
+        ops.axpby(dY_out.view(B * T, C), 1.0 / (1.0 + kappa), dY, True)  # the blend passes Y straight through
+        dWr = ops.gemm(dR, E2, torch.empty(nr, dk, dtype=_f32, device=dR.device), transA=True)
+        dbr = ops.colsum(dR)
+        dE = ops.gemm(dR, Wr, torch.empty(B * T, dk, dtype=_f32, device=dR.device))
+        return dY.view(B, T, C), dE.view(B, T, dk), None, None, None, None, None, None, None, None, dWr, dbr, dbo_f, dgamma, dbeta

@@ -117,10 +117,11 @@ _WS = {}
 def _workspace(dev, nbytes: int) -> torch.Tensor:
     """Per-device scratch for the tcgen05 backend's operand split.  Grows on demand; reuse across GEMMs is
     safe because every launch is ordered on the current stream."""
-    w = _WS.get(dev)
+    key = (dev, torch.cuda.current_stream().cuda_stream)  # kernels on different streams may run concurrently
+    w = _WS.get(key)
     if w is None or w.numel() < nbytes:
-        w = torch.empty(max(nbytes, 64 << 20), dtype=torch.uint8, device=dev)
-        _WS[dev] = w
+        w = torch.empty(max(nbytes, (64 << 20) if len(_WS) == 0 else (16 << 20)), dtype=torch.uint8, device=dev)
+        _WS[key] = w
     return w
 
 
@@ -176,6 +177,19 @@ def begin_step(e_txt_feeds_tc: bool) -> StepCtx:
 def end_step():
     global _STEP
     _STEP = None
+
+
+_SIDE = {}
+
+
+def side_stream(dev) -> "torch.cuda.Stream":
+    """Side stream for work that depends on parameters only (the weight-space half of the rank form of MMF_XAttn_Add):
+    it runs beside the TTF forward, and autograd runs its backward there beside the TTF backward."""
+    st = _SIDE.get(dev)
+    if st is None:
+        st = torch.cuda.Stream(device=dev)
+        _SIDE[dev] = st
+    return st
 
 
 def step_ctx() -> StepCtx:

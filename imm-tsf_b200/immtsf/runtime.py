@@ -136,7 +136,13 @@ class GraphedStep:
         self.graph = torch.cuda.CUDAGraph()
         self._works = []
         self._stage = self._copy_stream = self._staged = self._consumed = None
-        if self.group is not None:
+        # (bucketed overlap: the hook fires when backward crosses the MMF -> TTF boundary; only meaningful when every MMF
+        # gradient is final there, i.e. with the dense MMF path on one stream -- IMMTSF_XATTN_RANK=0 IMMTSF_SIDE_STREAM=0)
+        bucketed = self.group is not None and os.environ.get("IMMTSF_SIDE_STREAM", "1") == "0" and \
+            os.environ.get("IMMTSF_XATTN_RANK", "1") == "0"
+        if self.group is not None and not bucketed:
+            self.n_first = 0
+        if bucketed:
             fusion._e_txt_grad_hook = self._reduce_first_bucket  # fires between the MMF and the TTF backward
         try:
             # NCCL's watchdog thread may touch CUDA while we capture: thread-local capture mode tolerates that
