@@ -156,51 +156,76 @@ class T2VXAttnFn(torch.autograd.Function):
         rps = T if per_query else 1
         dx, dres, dgamma, dbeta = ops.ln_bwd(dy, attn_out, Qp.view(d), r.m_txt, rps, gamma, mean, rstd, thr, seed,
                                              ops.SITE_TTF_DROPOUT, xbias=out_b if fold else None)
-        db_o = ops.colsum(dx)
         if fold:
             d_attn_cat = dx
         else:
             dW_o = ops.linear_wgrad(dx, attn_cat, lo=lo)
             d_attn_cat = ops.linear_dgrad(dx, out_w, lo=lo)
         dKVp, dq_partial = ops.segattn_bwd(d_attn_cat, q, KVp, probs, r, T, H, d, per_query, thr, seed)
-        # query path: q = (Qp W_q^T + b_q) * scale
-        dq = ops.colsum(dq_partial)
-        dq_pre = ops.axpby(dq, ctx.scale, torch.empty_like(dq), False).view(1, d)
+        # Everything that only feeds parameter gradients goes to the wgrad stream (ops.Fork); the current stream keeps the
+        # data-gradient chain dKVp -> dX -> dXcat.  dKVp is read by both: its lo is split before the fork.
+        fk = ops.Fork(dev, enabled=fold)
+        if fold and ops.gemm_backend() != ops.BACKEND_FFMA:
+            lo.lo_for(dKVp, r.m_dev)
         d_in_w = torch.empty_like(in_w)
         d_in_b = new(3 * d)
-        ops.linear_wgrad(dq_pre, Qp.view(1, d), out=d_in_w[:d])
-        d_in_b[:d].copy_(dq_pre.view(d))
-        dQp = ops.linear_dgrad(dq_pre, in_w[:d])  # [1,d]
-        ops.axpby(dres, 1.0, dQp.view(d), True)
-        # key/value path, once per note
-        if fold:
-            dWkv, dWkv_lo = new(2 * d, d), new(2 * d, d)
-            ops.linear_wgrad(dKVp, X, out=dWkv, ragged=r.m_dev, lo=lo, emit_lo=dWkv_lo)  # rows [d,2d) are d(W_o W_v)
-            lo.put(dWkv[d:], dWkv_lo[d:])
-            dbkv = ops.colsum(dKVp, ragged=r.m_dev)
-            d_in_w[d:2 * d].copy_(dWkv[:d])
-            d_in_b[d:2 * d].copy_(dbkv[:d])
-            # un-fold W_f = W_o W_v, b_f = W_o b_v
-            dW_o = new(d, d)
-            ops.gemm_group([dict(A=dWkv[d:], B=in_w[2 * d:], C=dW_o, transB=True),
-                            dict(A=out_w, B=dWkv[d:], C=d_in_w[2 * d:], transA=True)], lo)
-            ops.gemm(dbkv[d:].view(d, 1), in_b[2 * d:].view(1, d), dW_o, beta=1.0)
-            ops.gemm(dbkv[d:].view(1, d), out_w, d_in_b[2 * d:].view(1, d))
-        else:
-            ops.linear_wgrad(dKVp, X, out=d_in_w[d:], ragged=r.m_dev, lo=lo)
-            ops.colsum(dKVp, out=d_in_b[d:], ragged=r.m_dev)
+        res = {}
+
+        def params_from_attention():
+            res["db_o"] = ops.colsum(dx)
+            # query path: q = (Qp W_q^T + b_q) * scale
+            dq = ops.colsum(dq_partial)
+            dq_pre = ops.axpby(dq, ctx.scale, torch.empty_like(dq), False).view(1, d)
+            ops.linear_wgrad(dq_pre, Qp.view(1, d), out=d_in_w[:d])
+            d_in_b[:d].copy_(dq_pre.view(d))
+            dQp = ops.linear_dgrad(dq_pre, in_w[:d])  # [1,d]
+            ops.axpby(dres, 1.0, dQp.view(d), True)
+            res["dQp"] = dQp
+            # key/value path, once per note
+            if fold:
+                dWkv, dWkv_lo = new(2 * d, d), new(2 * d, d)
+                ops.linear_wgrad(dKVp, X, out=dWkv, ragged=r.m_dev, lo=lo, emit_lo=dWkv_lo)  # rows [d,2d) are d(W_o W_v)
+                lo.put(dWkv[d:], dWkv_lo[d:])
+                dbkv = ops.colsum(dKVp, ragged=r.m_dev)
+                d_in_w[d:2 * d].copy_(dWkv[:d])
+                d_in_b[d:2 * d].copy_(dbkv[:d])
+                # un-fold W_f = W_o W_v, b_f = W_o b_v
+                dW_o = new(d, d)
+                ops.gemm_group([dict(A=dWkv[d:], B=in_w[2 * d:], C=dW_o, transB=True),
+                                dict(A=out_w, B=dWkv[d:], C=d_in_w[2 * d:], transA=True)], lo)
+                ops.gemm(dbkv[d:].view(d, 1), in_b[2 * d:].view(1, d), dW_o, beta=1.0)
+                ops.gemm(dbkv[d:].view(1, d), out_w, d_in_b[2 * d:].view(1, d))
+                res["dW_o"] = dW_o
+            else:
+                ops.linear_wgrad(dKVp, X, out=d_in_w[d:], ragged=r.m_dev, lo=lo)
+                ops.colsum(dKVp, out=d_in_b[d:], ragged=r.m_dev)
+
+        fk.run(params_from_attention, dx, dq_partial, dres, dKVp, d_in_w, d_in_b)
         dX = ops.linear_dgrad(dKVp, Wkv, ragged=r.m_dev, lo=lo, emit_lo=True)
-        dW_kv = ops.linear_wgrad(dX, Xcat, ragged=r.m_dev, lo=lo)
-        db_kv = ops.colsum(dX, ragged=r.m_dev)
+
+        def params_from_dX():
+            res["dW_kv"] = ops.linear_wgrad(dX, Xcat, ragged=r.m_dev, lo=lo)
+            res["db_kv"] = ops.colsum(dX, ragged=r.m_dev)
+
+        fk.run(params_from_dX, dX, *([lo.lo_for(dX, r.m_dev)] if fk.side is not None and ops.gemm_backend() != ops.BACKEND_FFMA else []))
         dXcat_lo = new(r.M_alloc, ops.round_up(d + dt, 4)) if ctx.has_in else False
         dXcat = ops.linear_dgrad(dX, W_kv, ragged=r.m_dev, lo=lo, emit_lo=dXcat_lo)
         if ctx.has_in:
             lo.put(dXcat[:, :d], dXcat_lo[:, :d])
-        dwl, dbl, dwp, dbp = ops.time2vec_bwd(dXcat[:, d:], r, w_per, b_per, dt)
-        dW_in = db_in = None
-        if ctx.has_in:
-            dW_in = ops.linear_wgrad(dXcat[:, :d], r.emb_flat, ragged=r.m_dev, lo=lo)
-            db_in = ops.colsum(dXcat[:, :d], ragged=r.m_dev)
+
+        def params_from_dXcat():
+            res["t2v"] = ops.time2vec_bwd(dXcat[:, d:], r, w_per, b_per, dt)
+            res["dW_in"] = res["db_in"] = None
+            if ctx.has_in:
+                res["dW_in"] = ops.linear_wgrad(dXcat[:, :d], r.emb_flat, ragged=r.m_dev, lo=lo)
+                res["db_in"] = ops.colsum(dXcat[:, :d], ragged=r.m_dev)
+
+        fk.run(params_from_dXcat, dXcat, *([dXcat_lo] if ctx.has_in else []))
+        dwl, dbl, dwp, dbp = res["t2v"]
+        dQp, dW_kv, db_kv, dW_in, db_in, db_o = res["dQp"], res["dW_kv"], res["db_kv"], res["dW_in"], res["db_in"], res["db_o"]
+        if fold:
+            dW_o = res["dW_o"]
+        fk.join(dQp, dW_in, db_in, dwl, dbl, dwp, dbp, dW_kv, db_kv, d_in_w, d_in_b, dW_o, db_o)
         return (None, None, None, None, None, None, None, dQp.view(1, 1, d), dW_in, db_in, dwl, dbl, dwp, dbp, dW_kv, db_kv,
                 d_in_w, d_in_b, dW_o, db_o, dgamma, dbeta, dW_po, db_po)
 

@@ -192,6 +192,44 @@ def side_stream(dev) -> "torch.cuda.Stream":
     return st
 
 
+def side_streams_enabled() -> bool:
+    return os.environ.get("IMMTSF_SIDE_STREAM", "1") != "0"
+
+
+class Fork:
+    """Parameter-gradient work of a backward pass on a second stream.  Weight and bias gradients are not needed until
+    the end of the step, while the data-gradient chain (dgrad products, attention / LayerNorm backward) is the critical
+    path and its ragged products leave a third of the SMs idle: `run` enqueues a closure on the wgrad stream after
+    everything issued so far on the current stream, `join` makes the current stream wait for all of it.  Captured in a
+    CUDA graph these are parallel branches.  Operands read on both streams must have their lo split BEFORE the fork."""
+
+    def __init__(self, device, enabled: bool = True):
+        self.cur = torch.cuda.current_stream(device)
+        self.side = None
+        if enabled and side_streams_enabled():
+            key = (device, "wgrad")
+            self.side = _SIDE.get(key)
+            if self.side is None:
+                self.side = _SIDE[key] = torch.cuda.Stream(device=device)
+
+    def run(self, fn, *reads):
+        if self.side is None:
+            return fn()
+        self.side.wait_stream(self.cur)
+        for t in reads:
+            t.record_stream(self.side)
+        with torch.cuda.stream(self.side):
+            return fn()
+
+    def join(self, *tensors):
+        if self.side is None:
+            return
+        self.cur.wait_stream(self.side)
+        for t in tensors:
+            if t is not None:
+                t.record_stream(self.cur)
+
+
 def step_ctx() -> StepCtx:
     """The step context opened by FusionModel.forward, or a private one for a module called on its own."""
     return _STEP if _STEP is not None else StepCtx()
