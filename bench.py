@@ -185,8 +185,54 @@ class ClockSampler:
 
     def __init__(self, dev):
         self.dev, self.proc, self.path = dev, None, f"/tmp/immtsf_clocks_{os.getpid()}.csv"
+        self.nv = None
+
+    def _start_nvml(self):
+        """NVML in a sampling thread (same counters nvidia-smi prints, but a 5 ms period: the timed region of a
+        sub-millisecond step is shorter than nvidia-smi's start-up)."""
+        import threading
+
+        import pynvml as N
+
+        N.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[self.dev]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else self.dev
+        h = N.nvmlDeviceGetHandleByIndex(idx)
+        bits = {"hw_slowdown": getattr(N, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(N, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(N, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(N, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        reasons_fn = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
+        st = {"sm": [], "mx": float(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)), "reasons": set(), "stop": False, "from": 0}
+
+        def loop():
+            while not st["stop"]:
+                try:
+                    st["sm"].append(float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)))
+                    r = reasons_fn(h)
+                    for nm, b in bits.items():
+                        if r & b:
+                            st["reasons"].add(nm)
+                except Exception:
+                    pass
+                time.sleep(0.005)
+
+        st["thread"] = threading.Thread(target=loop, daemon=True)
+        st["thread"].start()
+        self.nv = st
+
+    def mark(self):
+        """Forget what was sampled so far (warm-up)."""
+        if self.nv is not None:
+            self.nv["from"] = len(self.nv["sm"])
+            self.nv["reasons"].clear()
 
     def start(self):
+        try:
+            self._start_nvml()
+            return
+        except Exception:
+            self.nv = None
         try:
             self.f = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "25",
@@ -195,6 +241,12 @@ class ClockSampler:
             self.proc = None
 
     def stop(self):
+        if self.nv is not None:
+            self.nv["stop"] = True
+            self.nv["thread"].join(timeout=2)
+            sm = self.nv["sm"][self.nv["from"]:]
+            return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.nv["mx"],
+                    "reasons": sorted(self.nv["reasons"]), "samples": len(sm), "source": "NVML, 5 ms period"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -345,7 +397,8 @@ def run_gpu_arm(args, w):
         if world > 1 and args.dp_mode == "ingraph":
             try:
                 graphed = runtime.GraphedStep(fm, example=d_in, warmup=2, allreduce_group=True)
-                dp_mode = "two NCCL all-reduces captured in the step graph (MMF bucket overlaps the TTF backward)"
+                dp_mode = ("NCCL captured in the step graph: rank-form upstream gradients (KBs) reduced mid-backward on the side stream, "
+                           "one all-reduce of the remaining bucket at the end; %d of %d gradient floats are never communicated" % (graphed.n_first, graphed.flat_grads.numel()))
             except Exception as e:  # capture of NCCL refused: fall back to one all-reduce after the replay
                 print(f"[bench] in-graph all-reduce unavailable ({type(e).__name__}: {e}); reducing after the replay", file=sys.stderr)
                 torch.cuda.synchronize()
@@ -356,11 +409,13 @@ def run_gpu_arm(args, w):
             graphed = runtime.GraphedStep(fm, example=d_in, warmup=2, flat_grads=world > 1)
             if world > 1:
                 dp_mode = "one NCCL all-reduce of the flat gradient bucket after the graph replay"
-    timed(W, True, graphed)
-    barrier()
     clocks = ClockSampler(local)
     if rank == 0:
-        clocks.start()
+        clocks.start()  # before the warm-up: NVML's first queries are slow and would perturb the first timed steps
+    timed(W, True, graphed)
+    barrier()
+    if rank == 0:
+        clocks.mark()  # only samples from here on count
     ms_res = timed(K, True, graphed)
     launches = launches_per_step * K
     barrier()
@@ -462,9 +517,9 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="time the eager path only (no CUDA-graph replay)")
-    ap.add_argument("--dp-mode", default="post", choices=["ingraph", "post"],
-                    help="N > 1: gradient all-reduce issued after the graph replay (default), or captured inside the step "
-                         "graph in two buckets (experimental: measured no gain at N=2, see DESIGN.md 6)")
+    ap.add_argument("--dp-mode", default="ingraph", choices=["ingraph", "post"],
+                    help="N > 1: one gradient all-reduce after the graph replay (default), or NCCL captured inside the step "
+                         "graph with the rank-form gradients reduced through their small upstream tensors (DESIGN.md 6)")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     if args.impl == "reference":

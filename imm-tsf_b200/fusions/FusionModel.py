@@ -63,6 +63,23 @@ class FusionModel(nn.Module):
         r = ops.csr_build(cm.as_f32(notes_input), cm.as_f32(tau), flags)
         return self.forward_csr(r, t_hat, Y_ts)
 
+    def _schedule(self, T):
+        """(rank, defer): MMF_XAttn_Add in its rank form for T query times / TTF final projection folded into it."""
+        rank = isinstance(self.mmf, MMF_XAttn_Add) and self.mmf.rank_path(T)
+        defer = rank and self.ttf.can_defer() and os.environ.get("IMMTSF_FUSE_PROJ", "1") != "0"
+        return rank, defer
+
+    def dp_prereduced_params(self, T):
+        """Parameters whose gradients come out of the rank form's weight-space backward: under in-graph data parallelism
+        (runtime.GraphedStep(allreduce_group=...)) their three small upstream tensors are all-reduced instead of them."""
+        rank, defer = self._schedule(T)
+        ps = []
+        if rank:
+            ps += list(self.mmf._params()[:9])
+            if defer:
+                ps += list(self.ttf.final_proj())
+        return ps
+
     def forward_csr(self, r, t_hat, Y_ts):
         """Same as forward() for callers that already hold the ragged layout (immtsf.collate.ragged_collate):
         no padded tensor, no content-mask pass, no compaction copy."""
@@ -75,10 +92,9 @@ class FusionModel(nn.Module):
         # one operand-split cache for the whole step: E_txt (and dE_txt in backward) are handed from one module's GEMM
         # epilogue to the other module's product together with their tcgen05 lo operand
         T = t_hat.shape[-1]
-        rank = isinstance(self.mmf, MMF_XAttn_Add) and self.mmf.rank_path(T)
         # rank form of MMF_XAttn_Add: E_txt only enters through one skinny product, so the TTF's final projection is folded
         # into that operand in weight space and E_txt [B, T, d] is never materialised (IMMTSF_FUSE_PROJ=0 keeps it)
-        defer = rank and self.ttf.can_defer() and os.environ.get("IMMTSF_FUSE_PROJ", "1") != "0"
+        rank, defer = self._schedule(T)
         ops.begin_step(e_txt_feeds_tc=isinstance(self.mmf, MMF_XAttn_Add) and not rank)
         try:
             return self._forward_step(r, t_hat, Y32, flags, check, defer, rank)
@@ -98,9 +114,6 @@ class FusionModel(nn.Module):
             if check:  # E_txt_true has a NaN iff one of its three factors has one
                 for t in (E_txt, W_p, b_p):
                     ops.nan_check(t, flags, ops.FLAG_E)
-            hook = getattr(self, "_e_txt_grad_hook", None)
-            if hook is not None and E_txt.requires_grad:
-                E_txt.register_hook(hook)
             Y_out = self.mmf.forward_flags(Y32, E_txt, M_txt, flags, final_proj=(W_p, b_p), rank_weights=wts)
             runtime.raise_on_flags(flags)
             return Y_out
@@ -108,11 +121,6 @@ class FusionModel(nn.Module):
         E_txt, M_txt = self.ttf.forward_ragged(r, t_hat)
         if rank and side:
             self.mmf.wait_rank_weights(wts)
-        hook = getattr(self, "_e_txt_grad_hook", None)
-        if hook is not None and E_txt.requires_grad:
-            # data-parallel overlap (immtsf/runtime.py GraphedStep): called when backward crosses the MMF -> TTF
-            # boundary, i.e. when every MMF parameter gradient is final
-            E_txt.register_hook(hook)
         if check:
             # the broadcast view of T2V eval mode has B distinct rows: check those only
             ops.nan_check(E_txt[:, :1] if E_txt.stride(1) == 0 else E_txt, flags, ops.FLAG_E)

@@ -452,6 +452,15 @@ class XAttnRankWeightsFn(torch.autograd.Function):
         new = lambda *s: torch.empty(*s, dtype=_f32, device=dev)
         in_k, in_v, b_k, b_v = in_w[d:2 * d], in_w[2 * d:], in_b[d:2 * d], in_b[2 * d:]
         dWr_eff, dbr, dbo_f = dWr_eff.contiguous(), dbr_eff.contiguous(), dbo_f.contiguous()
+        if ops.DP_GROUP is not None:
+            # data parallel: every gradient below is linear in these three small tensors and the parameters are replicated,
+            # so reducing THEM (H(2C+1) x (d+1) + C floats) gives all-reduced parameter gradients with no further traffic
+            import torch.distributed as dist
+
+            pack = torch.cat([dWr_eff.reshape(-1), dbr.reshape(-1), dbo_f.reshape(-1)])
+            dist.all_reduce(pack, op=dist.ReduceOp.SUM, group=ops.DP_GROUP)
+            n0 = dWr_eff.numel()
+            dWr_eff, dbr, dbo_f = pack[:n0].view_as(dWr_eff), pack[n0:n0 + nr], pack[n0 + nr:]
         dW_p = db_p = None
         if W_p is None:
             dWr = dWr_eff

@@ -180,6 +180,9 @@ def end_step():
 
 
 _SIDE = {}
+# process group for in-graph data parallelism (runtime.GraphedStep(allreduce_group=...)): while set, the weight-space
+# backward of the rank form all-reduces its upstream gradients and so produces already-reduced parameter gradients
+DP_GROUP = None
 
 
 def side_stream(dev) -> "torch.cuda.Stream":

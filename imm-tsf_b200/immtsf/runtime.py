@@ -82,9 +82,10 @@ class GraphedStep:
     def __init__(self, fusion, example, loss_fn=None, extras=(), warmup: int = 3, flat_grads: bool = False,
                  allreduce_group=None):
         """allreduce_group: a torch.distributed process group (or True for the default group).  The data-parallel
-        gradient all-reduce is then captured INSIDE the graph, in two buckets: the MMF gradients are
-        reduced on NCCL's stream as soon as the MMF backward has produced them -- overlapping the TTF backward -- and
-        the TTF bucket follows at the end.  Implies flat_grads (the buckets are slices of one flat buffer)."""
+        gradient all-reduce is then captured INSIDE the graph.  With the rank form of MMF_XAttn_Add the
+        MMF weight gradients (and the folded TTF projection's) are not communicated at all: their three small upstream
+        tensors are all-reduced in the middle of backward and the weight-space backward runs on the reduced values.
+        Implies flat_grads."""
         from . import _lib
 
         if not torch.cuda.is_available():
@@ -105,15 +106,22 @@ class GraphedStep:
                 if dist.get_world_size(self.group) == 1:
                     self.group = None
         flat_grads = flat_grads or self.group is not None
-        # bucket order = the order in which backward completes the gradients: MMF first, then TTF
-        mmf_ids = {id(p) for p in fusion.mmf.parameters()} if hasattr(fusion, "mmf") else set()
-        self.params.sort(key=lambda p: 0 if id(p) in mmf_ids else 1)
-        self.n_first = sum(p.numel() for p in self.params if id(p) in mmf_ids)
+        # In-graph data parallelism: parameters whose gradients come out of the weight-space backward of the rank form
+        # (functional.XAttnRankWeightsFn) are functions of three small upstream tensors; those are all-reduced instead
+        # (28 KB instead of 14 MB at cfg2), so these parameters' gradients are born reduced and sit in front of the flat
+        # bucket, outside the all-reduce that closes the step.
+        pre = []
+        if self.group is not None and hasattr(fusion, "dp_prereduced_params"):
+            pre = fusion.dp_prereduced_params(self.static_in[2].shape[-1])
+        pre_ids = {id(p) for p in pre}
+        self.params.sort(key=lambda p: 0 if id(p) in pre_ids else 1)
+        self.n_first = sum(p.numel() for p in self.params if id(p) in pre_ids)
         self.seed_offset = torch.zeros(1, dtype=torch.int64, device=dev)
         self._lib = _lib
         _lib.call("immtsf_set_seed_offset_ptr", self.seed_offset.data_ptr())
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
+        ops.DP_GROUP = self.group if self.n_first > 0 else None
         with torch.cuda.stream(side):  # warm-up off the capture stream: lazy allocations (workspaces) happen here
             for _ in range(max(warmup, 1)):
                 self._eager()
@@ -136,14 +144,6 @@ class GraphedStep:
         self.graph = torch.cuda.CUDAGraph()
         self._works = []
         self._stage = self._copy_stream = self._staged = self._consumed = None
-        # (bucketed overlap: the hook fires when backward crosses the MMF -> TTF boundary; only meaningful when every MMF
-        # gradient is final there, i.e. with the dense MMF path on one stream -- IMMTSF_XATTN_RANK=0 IMMTSF_SIDE_STREAM=0)
-        bucketed = self.group is not None and os.environ.get("IMMTSF_SIDE_STREAM", "1") == "0" and \
-            os.environ.get("IMMTSF_XATTN_RANK", "1") == "0"
-        if self.group is not None and not bucketed:
-            self.n_first = 0
-        if bucketed:
-            fusion._e_txt_grad_hook = self._reduce_first_bucket  # fires between the MMF and the TTF backward
         try:
             # NCCL's watchdog thread may touch CUDA while we capture: thread-local capture mode tolerates that
             mode = dict(capture_error_mode="thread_local") if self.group is not None else {}
@@ -155,28 +155,16 @@ class GraphedStep:
                 if self.group is not None:
                     self._reduce_rest()
         finally:
-            if self.group is not None:
-                fusion._e_txt_grad_hook = None
+            ops.DP_GROUP = None
         self.Y_out, self.loss = out.detach(), loss.detach()
         self.flags = getattr(fusion, "_last_flags", None)
 
-    def _reduce_first_bucket(self, grad):
-        import torch.distributed as dist
-
-        if self.n_first > 0:
-            self._works.append(dist.all_reduce(self.flat_grads[: self.n_first], op=dist.ReduceOp.SUM, group=self.group,
-                                               async_op=True))
-        return None
-
     def _reduce_rest(self):
+        """The all-reduce that closes the step: everything behind the born-reduced prefix of the flat bucket."""
         import torch.distributed as dist
 
         if self.n_first < self.flat_grads.numel():
-            self._works.append(dist.all_reduce(self.flat_grads[self.n_first:], op=dist.ReduceOp.SUM, group=self.group,
-                                               async_op=True))
-        for w in self._works:
-            w.wait()  # the capture stream joins NCCL's stream
-        self._works = []
+            dist.all_reduce(self.flat_grads[self.n_first:], op=dist.ReduceOp.SUM, group=self.group)
 
     def _eager(self):
         out = self.fusion(self.static_in[0], self.static_in[1], self.static_in[2], self.static_in[3])
