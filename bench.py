@@ -323,8 +323,10 @@ def run_gpu_arm(args, w):
         return loss
 
     def timed(n, resident, graphed=None):
-        """n steps, each bracketed by its own CUDA-event pair (the 256 MiB L2 flush sits between the pairs)."""
-        total_ms = 0.0
+        """n steps, each bracketed by its own CUDA-event pair (the 256 MiB L2 flush sits between the pairs).  The host
+        enqueues all n steps and synchronises once at the end, as a training loop does: a host sync per step would add
+        the host's launch latency to every step and, on several GPUs, let the ranks drift apart between steps."""
+        pairs = []
         for _ in range(n):
             flush.fill_(1.0)  # L2 flush, outside the timed events
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -340,32 +342,33 @@ def run_gpu_arm(args, w):
             if not resident:
                 loss_host.copy_(loss.detach(), non_blocking=True)
             e1.record()
-            e1.synchronize()
-            total_ms += e0.elapsed_time(e1)
-        return total_ms
+            pairs.append((e0, e1))
+        torch.cuda.synchronize()
+        return sum(e0.elapsed_time(e1) for e0, e1 in pairs)
 
     def timed_prefetched(n, graphed):
         """e2e with the double-buffered input pipeline (GraphedStep.prefetch): inside step i's timed region the H2D of
         step i+1's inputs runs on the copy stream next to step i's kernels, and step i waits for its own inputs, copied
         during step i-1.  Every timed region thus contains one full H2D and the D2H of its loss.  `hidden` counts
         the regions whose H2D had NOT landed when the region closed (it would then have run in the untimed flush gap)."""
-        total_ms, hidden = 0.0, 0
         graphed.prefetch(*h_in)
         torch.cuda.synchronize()
+        pairs, staged = [], []
         for _ in range(n):
             flush.fill_(1.0)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             loss = graphed.step_prefetched()
             graphed.prefetch(*h_in)  # next step's inputs, overlapping this step
+            staged.append(graphed._staged)
             if world > 1 and graphed.group is None:
                 dp.allreduce_grads(params, flat=graphed.flat_grads)
             loss_host.copy_(loss.detach(), non_blocking=True)
             e1.record()
-            e1.synchronize()
-            hidden += 0 if graphed.prefetch_done() else 1
-            total_ms += e0.elapsed_time(e1)
-        return total_ms, hidden
+            pairs.append((e0, e1))
+        torch.cuda.synchronize()
+        hidden = sum(1 for (e0, e1), st in zip(pairs, staged) if st.elapsed_time(e1) < 0.0)
+        return sum(e0.elapsed_time(e1) for e0, e1 in pairs), hidden
 
     def barrier():
         torch.cuda.synchronize()
@@ -406,7 +409,7 @@ def run_gpu_arm(args, w):
         if graphed is None:
             for p in params:
                 p.grad = None
-            graphed = runtime.GraphedStep(fm, example=d_in, warmup=2, flat_grads=world > 1)
+            graphed = runtime.GraphedStep(fm, example=d_in, warmup=2, flat_grads=world > 1 or args.flat_grads)
             if world > 1:
                 dp_mode = "one NCCL all-reduce of the flat gradient bucket after the graph replay"
     clocks = ClockSampler(local)
@@ -517,6 +520,7 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="time the eager path only (no CUDA-graph replay)")
+    ap.add_argument("--flat-grads", action="store_true", help="N = 1: keep the gradients in the flat bucket of the N > 1 runs (diagnostic)")
     ap.add_argument("--dp-mode", default="ingraph", choices=["ingraph", "post"],
                     help="N > 1: one gradient all-reduce after the graph replay (default), or NCCL captured inside the step "
                          "graph with the rank-form gradients reduced through their small upstream tensors (DESIGN.md 6)")

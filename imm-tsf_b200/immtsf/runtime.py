@@ -184,7 +184,6 @@ class GraphedStep:
         if self._stage is None:
             self._stage = [torch.empty_like(t) for t in self.static_in + self.static_extra]
             self._copy_stream = torch.cuda.Stream()
-            self._staged = torch.cuda.Event()
             self._consumed = torch.cuda.Event()
             self._consumed.record()
         cs = self._copy_stream
@@ -192,6 +191,7 @@ class GraphedStep:
         with torch.cuda.stream(cs), torch.no_grad():
             for s, t in zip(self._stage, (notes, tau, t_hat, Y_ts) + tuple(extras)):
                 s.copy_(t, non_blocking=True)
+            self._staged = torch.cuda.Event(enable_timing=True)  # one per batch: callers may keep it to time the copy
             self._staged.record(cs)
 
     def prefetch_done(self) -> bool:
