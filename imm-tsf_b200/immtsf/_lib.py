@@ -65,6 +65,9 @@ SIGNATURES = {
     "immtsf_softmax_rows_bwd": [P, P, P, P, I, I, I, I, F, U32, U64, P],
     "immtsf_xattn_tail_fwd": [P, P, P, P, P, I, I, I, F, F, U32, U64, P, P, P],
     "immtsf_xattn_tail_bwd": [P, P, P, P, I, I, I, F, F, U32, U64, P, P, P, P],
+    "immtsf_masked_mse_partial": [P, P, P, L, I, I, P, P, P, P, SZ, P],
+    "immtsf_masked_mse_finalize": [P, P, I, P, P, P],
+    "immtsf_masked_mse_bwd": [P, P, P, L, I, P, P, P, P],
     "immtsf_axpby": [P, F, P, I, SZ, P],
     "immtsf_group_sum_rows": [P, I, I, I, I, P, P],
 }
@@ -97,6 +100,8 @@ def load():
     lib.immtsf_launch_count.restype = C.c_ulonglong
     lib.immtsf_gemm_workspace_bytes.argtypes = [I, I, I, I, I]
     lib.immtsf_gemm_workspace_bytes.restype = SZ
+    lib.immtsf_masked_mse_workspace_bytes.argtypes = [I]
+    lib.immtsf_masked_mse_workspace_bytes.restype = SZ
     lib.immtsf_gemm_batched_workspace_bytes.argtypes = [I, I, I, I, I, I, L, L, I, L, L, I, I]
     lib.immtsf_gemm_batched_workspace_bytes.restype = SZ
     _lib = lib

@@ -63,6 +63,10 @@ def masked_mse_exact(pred: torch.Tensor, truth: torch.Tensor, mask: torch.Tensor
     """Reference loss (lib/evaluation.py compute_error(..., 'MSE', 'mean')) made exact under batch sharding.
     pred/truth/mask: [B_local, T, C].  Returns this rank's SHARE of the global loss: summing the
     returned values over ranks gives the single-process loss, and so do the gradients after a SUM all-reduce."""
+    if pred.is_cuda:  # the fused kernels (immtsf/loss.py); same value up to the reference's 1e-8 in the denominator
+        from . import loss as _loss
+
+        return _loss.masked_mse(pred, truth, mask, group=group)
     C = pred.shape[-1]
     err = ((pred - truth) ** 2) * mask
     numer = err.reshape(-1, C).sum(0)  # differentiable, local

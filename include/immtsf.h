@@ -286,6 +286,22 @@ int immtsf_axpby(const float* x, float alpha, float* y, int accumulate, size_t n
 /* out[r, c] = sum_{t<T} x[r*T + t, c]   ([R*T, d] -> [R, d]) */
 int immtsf_group_sum_rows(const float* x, int ldx, int R, int T, int d, float* out, void* stream);
 
+/* ---- next to the path: the masked-MSE training loss, lib/evaluation.py:17-69 compute_error(...,
+ * "MSE", "mean") as called at :107-113, and the all-zero-mask check of :128-132 --------------------------------------
+ * partial: err_cnt[0..C) = sum (truth-pred)^2 mask, err_cnt[C..2C) = sum mask over the rows (= samples x T) of this
+ *   shard, deterministic (per-CTA partials added in CTA order by the last CTA; ticket: a zero-initialised device word
+ *   the kernel leaves at zero); *empty_flag (nullable) is set when a sample's mask is all zero.
+ * finalize: loss = sum_c err_c / (cnt_c + 1e-8) / count_nonzero(cnt); scale_c = 1 / ((cnt_c + 1e-8) count_nonzero(cnt)).
+ *   Under batch sharding pass the all-reduced counts: the loss is then this shard's share of the global loss.
+ * bwd: dpred = *gloss * 2 (pred - truth) mask * scale_c   (gloss NULL = 1). */
+size_t immtsf_masked_mse_workspace_bytes(int C);
+int immtsf_masked_mse_partial(const float* pred, const float* truth, const float* mask, long rows, int T, int C,
+                              float* err_cnt, int32_t* empty_flag, unsigned int* ticket, void* workspace,
+                              size_t workspace_bytes, void* stream);
+int immtsf_masked_mse_finalize(const float* err, const float* cnt, int C, float* loss, float* scale, void* stream);
+int immtsf_masked_mse_bwd(const float* pred, const float* truth, const float* mask, long rows, int C,
+                          const float* scale, const float* gloss, float* dpred, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

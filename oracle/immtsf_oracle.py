@@ -433,3 +433,22 @@ def param_shapes(ttf_name: str, mmf_name: str, d_model: int, d_txt: Optional[int
         s["mmf.layer_norm.weight"] = (C,)
         s["mmf.layer_norm.bias"] = (C,)
     return s
+
+
+# ------------------------------------------------------------------ masked MSE
+def masked_mse(truth: Tensor, pred: Tensor, mask: Tensor, reduce: str = "mean", count: Optional[Tensor] = None):
+    """lib/evaluation.py:17-69 `compute_error(truth, pred_y, mask, "MSE", reduce)` restated (n_traj_samples = 1).
+    error = (truth - pred)^2 * mask (:27-30); per-variable sums over every (sample, time) (:51-52);
+    'mean': sum_c [err_c / (count_c + 1e-8)] / count_nonzero(count) (:57-61); 'sum': (err, count) (:65-67).
+    count (optional): the GLOBAL per-variable counts of a batch-sharded run -- the returned value is then this shard's
+    share of the global loss (shares add up to the single-process loss; immtsf/dp.py)."""
+    C = pred.shape[-1]
+    err = ((truth - pred) ** 2) * mask
+    err_c = err.reshape(-1, C).sum(dim=0)
+    cnt_c = mask.reshape(-1, C).sum(dim=0)
+    if reduce == "sum":
+        return err_c, cnt_c
+    if count is None:
+        count = cnt_c
+    n_avail = torch.count_nonzero(count)
+    return (err_c / (count + 1e-8)).sum() / n_avail

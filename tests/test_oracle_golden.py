@@ -120,3 +120,33 @@ def test_fixtures_regenerate_identically(tmp_path):
             if k == "meta":
                 continue
             assert np.allclose(a[k], b[k], rtol=1e-6, atol=1e-7), (name, k)
+
+
+def test_masked_mse_oracle_matches_reference_golden():
+    """oracle.masked_mse (lib/evaluation.py:17-69 restated) against vectors produced by the reference's compute_error
+    (oracle/make_golden_loss.py): loss, d loss / d pred, the 'sum' reduction, and a variable without observations."""
+    import os
+
+    import numpy as np
+    import torch
+
+    from oracle import immtsf_oracle as O
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "loss_mse.npz"))
+    for name in ("dense", "ragged", "novar", "one"):
+        pred, truth, mask = (torch.from_numpy(g[f"{name}:{k}"]) for k in ("pred", "truth", "mask"))
+        for dt, tag, tol in ((torch.float32, "32", 2e-6), (torch.float64, "64", 1e-12)):
+            p = pred.to(dt).clone().requires_grad_(True)
+            loss = O.masked_mse(truth.to(dt), p, mask.to(dt))
+            loss.backward()
+            ref = torch.from_numpy(g[f"{name}:loss{tag}"])
+            assert abs(float(loss) - float(ref)) <= tol * max(abs(float(ref)), 1e-30), (name, tag)
+            rg = torch.from_numpy(g[f"{name}:dpred{tag}"])
+            assert (p.grad - rg).abs().max() <= tol * max(float(rg.abs().max()), 1e-30), (name, tag)
+        s, c = O.masked_mse(truth.double(), pred.double(), mask.double(), reduce="sum")
+        assert torch.allclose(s, torch.from_numpy(g[f"{name}:sum"]), rtol=1e-12) and torch.equal(c, torch.from_numpy(g[f"{name}:count"]))
+    # shares of a sharded batch add up to the single-process loss
+    pred, truth, mask = (torch.from_numpy(g[f"ragged:{k}"]).double() for k in ("pred", "truth", "mask"))
+    _, cnt = O.masked_mse(truth, pred, mask, reduce="sum")
+    shares = sum(O.masked_mse(truth[a:b], pred[a:b], mask[a:b], count=cnt) for a, b in ((0, 3), (3, 8)))
+    assert abs(float(shares) - float(g["ragged:loss64"])) < 1e-12
