@@ -63,9 +63,10 @@ DROPOUT = 0.1
 # dram__bytes_read.sum + dram__bytes_write.sum of one gemm_tc_kernel<.,.,256> launch (M6144 N768 K768) from the
 # ncu --set full capture in profiles/r1_ncu_gemm_tc_bn256_summary.txt; algorithmic operand bytes of that launch:
 # 42.5 MB (A, A_lo, B, B_lo; the 18.9 MB output stays in the 126 MB L2)
-TRAFFIC_NCU = 43.5e6
-TRAFFIC_NOTE = ("bytes per launch of gemm_tc2_kernel, M6144 N768 K768, cold L2: dram read 42.63 MB + write 0.85 MB, "
-                "profiles/r1_ncu_gemm_tc2_pair_summary.txt (algorithmic operand bytes 42.5e6; the 18.9 MB output stays in L2)")
+TRAFFIC_NCU = 36.26e6
+TRAFFIC_NOTE = ("bytes per launch of the longest GEMM of the cfg2 step, dX = dKVp Wkv (gemm_tc_kernel<0,1,128>, 2134 live of "
+                "4096 rows, N768, K1536), cold L2: dram read 36.23 MB + write 0.03 MB, profiles/r1_ncu_step_gemms_summary.txt "
+                "(algorithmic operand bytes 35.6e6: A and A_lo 26.2 MB, B and B_lo 9.4 MB; the output stays in L2)")
 METRIC = "fused TTF+MMF fwd+bwd throughput"
 UNIT = "samples/s"
 
