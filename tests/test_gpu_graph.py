@@ -103,3 +103,36 @@ def test_graph_flat_gradient_bucket():
         assert step.n_first == 0 and step.group is None
     finally:
         step.close()
+
+
+def test_prefetch_pipeline_equals_direct_calls():
+    """GraphedStep.prefetch / step_prefetched (double-buffered H2D on a copy stream) must give the results of calling
+    the step with the same batches directly, batch after batch, from pinned host memory."""
+    from immtsf import runtime
+
+    cfg = dict(ttf="TTF_T2V_XAttn", mmf="MMF_XAttn_Add", d_txt=64, C=4, H=1, kappa=0.5)
+    fm = G.build_model(cfg, 96, dropout=0.0, seed=1)
+    G.randomise_(fm, 2)
+    fm.train()
+    batches = [[t.pin_memory() for t in G.synth_batch(10, 6, 9, 96, 4, s)[:4]] for s in (3, 4, 5)]
+    step = runtime.GraphedStep(fm, example=[t.cuda() for t in batches[0]])
+    try:
+        direct = []
+        for b in batches:
+            step(*b)
+            torch.cuda.synchronize()
+            direct.append((step.Y_out.clone(), step.dY_ts.clone(), [p.grad.clone() for p in step.params]))
+        step.prefetch(*batches[0])
+        for i in range(len(batches)):
+            step.step_prefetched()
+            if i + 1 < len(batches):
+                step.prefetch(*batches[i + 1])  # overlaps the running step
+            torch.cuda.synchronize()
+            y, dy, gs = direct[i]
+            assert torch.equal(step.Y_out, y)
+            G.assert_close("dY", step.dY_ts.cpu(), dy.cpu(), 1e-6)
+            for p, g in zip(step.params, gs):  # (some reductions over rows use atomics: equal to rounding, not bitwise)
+                G.assert_close("grad", p.grad.cpu(), g.cpu(), 1e-5, floor=1e-3)
+        assert step.prefetch_done()
+    finally:
+        step.close()
