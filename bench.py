@@ -402,7 +402,8 @@ def run_gpu_arm(args, w):
             try:
                 graphed = runtime.GraphedStep(fm, example=d_in, warmup=2, allreduce_group=True)
                 dp_mode = ("NCCL captured in the step graph: rank-form upstream gradients (KBs) reduced mid-backward on the side stream, "
-                           "one all-reduce of the remaining bucket at the end; %d of %d gradient floats are never communicated" % (graphed.n_first, graphed.flat_grads.numel()))
+                           "one %s of the remaining gradients at the end; %d of %d gradient floats are never communicated"
+                           % ("coalesced all-reduce (no flat bucket)" if graphed.coalesced else "all-reduce of the flat bucket", graphed.n_first, graphed.n_total))
             except Exception as e:  # capture of NCCL refused: fall back to one all-reduce after the replay
                 print(f"[bench] in-graph all-reduce unavailable ({type(e).__name__}: {e}); reducing after the replay", file=sys.stderr)
                 torch.cuda.synchronize()

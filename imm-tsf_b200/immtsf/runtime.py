@@ -105,7 +105,11 @@ class GraphedStep:
                 self.group = dist.group.WORLD if allreduce_group is True else allreduce_group
                 if dist.get_world_size(self.group) == 1:
                     self.group = None
-        flat_grads = flat_grads or self.group is not None
+        # in-graph data parallelism reduces the gradient tensors where autograd put them, as ONE coalesced NCCL launch
+        # (no flat bucket: its zeroing and its accumulate kernel per parameter cost 31 us per cfg2 step); IMMTSF_DP_FLAT=1
+        # brings the bucket back
+        self.coalesced = self.group is not None and not flat_grads and os.environ.get("IMMTSF_DP_FLAT", "0") != "1"
+        flat_grads = flat_grads or (self.group is not None and not self.coalesced)
         # In-graph data parallelism: parameters whose gradients come out of the weight-space backward of the rank form
         # (functional.XAttnRankWeightsFn) are functions of three small upstream tensors; those are all-reduced instead
         # (28 KB instead of 14 MB at cfg2), so these parameters' gradients are born reduced and sit in front of the flat
@@ -113,7 +117,8 @@ class GraphedStep:
         pre = []
         if self.group is not None and hasattr(fusion, "dp_prereduced_params"):
             pre = fusion.dp_prereduced_params(self.static_in[2].shape[-1])
-        pre_ids = {id(p) for p in pre}
+        pre_ids = self._pre_ids = {id(p) for p in pre}
+        self.n_total = sum(p.numel() for p in self.params)
         self.params.sort(key=lambda p: 0 if id(p) in pre_ids else 1)
         self.n_first = sum(p.numel() for p in self.params if id(p) in pre_ids)
         self.seed_offset = torch.zeros(1, dtype=torch.int64, device=dev)
@@ -160,10 +165,16 @@ class GraphedStep:
         self.flags = getattr(fusion, "_last_flags", None)
 
     def _reduce_rest(self):
-        """The all-reduce that closes the step: everything behind the born-reduced prefix of the flat bucket."""
+        """The all-reduce that closes the step: every gradient that was not born reduced."""
         import torch.distributed as dist
 
-        if self.n_first < self.flat_grads.numel():
+        if self.coalesced:
+            todo = [p.grad for p in self.params if id(p) not in self._pre_ids and p.grad is not None]
+            if todo:
+                with dist._coalescing_manager(group=self.group, device=todo[0].device):
+                    for g in todo:
+                        dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group)
+        elif self.n_first < self.flat_grads.numel():
             dist.all_reduce(self.flat_grads[self.n_first:], op=dist.ReduceOp.SUM, group=self.group)
 
     def _eager(self):

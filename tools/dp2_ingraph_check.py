@@ -33,7 +33,7 @@ def main():
         # rank form: the MMF weight gradients (and RecAvg's folded `proj`) are born reduced and not communicated
         assert step.group is not None and (step.n_first > 0) == (mmf == "MMF_XAttn_Add"), step.n_first
         if rank == 0:
-            print(f"{ttf}+{mmf}: {step.n_first} of {step.flat_grads.numel()} gradient floats never communicated", flush=True)
+            print(f"{ttf}+{mmf}: {step.n_first} of {step.n_total} gradient floats never communicated", flush=True)
         try:
             for _ in range(2):  # replays re-zero the flat bucket and reduce again
                 step(*mine)
@@ -63,7 +63,7 @@ def main():
         if mode == "post":
             dp.allreduce_grads(step.params, flat=step.flat_grads)
         else:
-            assert step.n_first > 0.4 * step.flat_grads.numel(), (step.n_first, step.flat_grads.numel())
+            assert step.n_first > 0.4 * step.n_total and step.coalesced, (step.n_first, step.n_total)
         torch.cuda.synchronize()
         grads[mode] = {k: p.grad.clone() for k, p in fm.named_parameters()}
         step.close()
