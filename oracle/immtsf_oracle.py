@@ -452,3 +452,59 @@ def masked_mse(truth: Tensor, pred: Tensor, mask: Tensor, reduce: str = "mean", 
         count = cnt_c
     n_avail = torch.count_nonzero(count)
     return (err_c / (count + 1e-8)).sum() / n_avail
+
+
+# ------------------------------------------------------------------ per-(note, query) Time2Vec attention
+def ttf_t2v_xattn_perquery(
+    P: Params,
+    notes: Tensor,
+    tau: Tensor,
+    t_hat: Tensor,
+    n_heads: int = 1,
+    p: float = 0.0,
+    masks: Optional[Dict[str, Tensor]] = None,
+    prefix: str = "ttf.",
+) -> Tuple[Tensor, Tensor]:
+    """fusions/TTF_T2V_XAttn_old.py:82-161: the variant in which the query time matters.  Time2Vec encodes the
+    clamped lag max(t_hat - tau, 0) of every (note, query) pair (:120-121), so keys/values differ per query time and
+    the attention is a dense [T_f x N] problem per sample.  `input_proj` (absent from the _old file, present in the
+    active module fusions/TTF_T2V_XAttn.py:120-121) is applied when the parameter exists, so the variant plugs into FusionModel(d_txt=...).
+
+    masks: ``ttf.attn_dropout`` [B,T,H,N], ``ttf.dropout`` [B,T,d]."""
+    masks = masks or {}
+    V = notes
+    note_mask = note_mask_from_content(V)  # :95
+    if torch.isnan(V).any():  # :104
+        raise ValueError("Input embeddings V contain NaN values.")
+    if prefix + "input_proj.weight" in P:
+        V = linear(V, P[prefix + "input_proj.weight"], P[prefix + "input_proj.bias"])
+    M_txt = note_mask.any(dim=1, keepdim=True)  # :108
+    B, N, d = V.shape
+    t_hat = _fix_t_hat(t_hat, B)  # :112-117
+    T = t_hat.shape[1]
+    delta = (t_hat[:, None, :] - tau[:, :, None]).clamp_min(0)  # :120  [B,N,T]
+    phi = time2vec(P, delta.unsqueeze(-1), prefix + "time2vec.")  # :121  [B,N,T,d_tau]
+    V_exp = V.unsqueeze(2).expand(-1, -1, T, -1)  # :126
+    KV = torch.cat([V_exp, phi], dim=-1)  # :127
+    KV = KV.permute(0, 2, 1, 3).reshape(B * T, N, KV.shape[-1])  # :128
+    KVp = linear(KV, P[prefix + "KV_proj.weight"], P[prefix + "KV_proj.bias"])  # :129
+    Qp = P[prefix + "Q_param"]
+    Q = Qp.expand(B, T, d).reshape(B * T, 1, d)  # :132
+    mp_flat = (~note_mask).repeat_interleave(T, dim=0)  # :135
+    keep = masks.get(prefix + "attn_dropout")
+    kflat = None if keep is None else keep.reshape(B * T, n_heads, 1, N)
+    attn_out = mha(  # :138-143
+        Q, KVp, KVp,
+        P[prefix + "attn.in_proj_weight"], P[prefix + "attn.in_proj_bias"],
+        P[prefix + "attn.out_proj.weight"], P[prefix + "attn.out_proj.bias"],
+        n_heads, mp_flat, p, kflat,
+    )
+    E_attn = attn_out.reshape(B, T, d)  # :144
+    mask = M_txt.view(B, 1, 1).expand(B, T, d)  # :148
+    E_attn = torch.where(mask, E_attn, torch.zeros_like(E_attn))  # :150
+    E_resid = layer_norm(  # :154-155
+        E_attn + Qp.expand(B, T, d), P[prefix + "layer_norm.weight"], P[prefix + "layer_norm.bias"]
+    )
+    E_drop = apply_dropout(E_resid, p, masks.get(prefix + "dropout"))  # :156
+    E_txt = linear(E_drop, P[prefix + "proj_out.weight"], P[prefix + "proj_out.bias"])  # :159
+    return E_txt, M_txt
