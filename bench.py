@@ -55,6 +55,10 @@ WORKLOADS = {
     "cfg5": dict(ttf="TTF_T2V_XAttn", mmf="MMF_XAttn_Add", B=256, N=32, T=192, d_model=768, d_txt=768, C=96, H=1, kappa=0.5,
                  history=24.0, pred=24.0, cpu_sample_B=4,
                  name="cfg5: T2V_XAttn+XAttn_Add, B256 N<=32 T192 d768 C96 (BASELINE.json configs[4], per-GPU shard)"),
+    # the per-(note, query) Time2Vec attention (fusions/TTF_T2V_XAttn_old.py semantics) on the cfg2 shape
+    "cfg2q": dict(ttf="TTF_T2V_XAttn_old", mmf="MMF_XAttn_Add", B=256, N=16, T=24, d_model=768, d_txt=768, C=4, H=1, kappa=0.5,
+                  history=7.0, pred=7.0, cpu_sample_B=8,
+                  name="cfg2q: per-(note,query) T2V_XAttn(_old)+XAttn_Add, B256 N<=16 T24 d768 C4 H1 (SURVEY 8f row f3)"),
     "cfg5g": dict(ttf="TTF_T2V_XAttn", mmf="MMF_GR_Add", B=256, N=32, T=192, d_model=768, d_txt=768, C=96, H=1, kappa=0.5,
                   history=24.0, pred=24.0, cpu_sample_B=4,
                   name="cfg5g: T2V_XAttn+GR_Add, B256 N<=32 T192 d768 C96 (MIMIC-shaped, GRU fusion)"),
@@ -94,6 +98,9 @@ def algorithmic_flops(w, sumN, per_query=True):
     f_in = 2 * sumN * d_m * d
     if w["ttf"] == "TTF_RecAvg":
         ttf = 2 * sumN * T * d + 2 * ST * d * d  # pool (upper bound sum_i T_i N_i d) + proj
+    elif w["ttf"] == "TTF_T2V_XAttn_old":
+        # once per note: W_a; per (note, query): score (d_tau) + pooling of A and phi; per (sample, query) row: W_phi, W_v, W_o, proj_out
+        ttf = 2 * sumN * d * d + 2 * sumN * T * (d // 2) + 2 * sumN * T * (d + d // 2) + ST * (2 * (d // 2) * d + 3 * 2 * d * d)
     else:
         R = ST if per_query else B
         ttf = 2 * sumN * (d + d // 2) * d + 2 * sumN * d * 2 * d + 2 * d * d + 2 * sumN * d + 2 * sumN * T * d + 2 * R * d * d * 2
@@ -129,7 +136,7 @@ def cpu_oracle_step_fn(w, sample_B, threads):
     B, N, T, C, H, d = sample_B, w["N"], w["T"], w["C"], w["H"], w["d_txt"]
     keep = lambda *s: (torch.rand(*s, generator=g) >= DROPOUT).float()
     masks = {"ttf.dropout": keep(B, T, d), "mmf.dropout": keep(B, T, C)}
-    if w["ttf"] == "TTF_T2V_XAttn":
+    if w["ttf"].startswith("TTF_T2V_XAttn"):
         masks["ttf.attn_dropout"] = keep(B, T, H, N)
     if w["mmf"] == "MMF_XAttn_Add":
         masks["mmf.attn_dropout"] = keep(B, H, T, T)

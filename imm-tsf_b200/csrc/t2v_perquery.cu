@@ -1,0 +1,383 @@
+// Per-(note, query) Time2Vec attention over each ragged note segment -- SURVEY.md 8f row f3, the semantics of
+// fusions/TTF_T2V_XAttn_old.py:119-143 (Time2Vec of the clamped lag max(t_hat - tau, 0) of EVERY (note, query) pair
+// enters the keys and values, so the attention is a dense [T_f x N_i] problem per sample).
+//
+// The reference builds [V ; phi] for B*T*N pairs, runs KV_proj on all of them and lets nn.MultiheadAttention project
+// K and V again.  With X_nt = A_n + W_phi phi_nt (A_n = W_a V'_n + b_kv, once per note):
+//   score_{h,n,t} = a_{n,h} + g_h . phi_nt          a = A U^T, u_h = W_k[h]^T q_h, g_h = W_phi^T u_h
+//   Z_{t,h} = sum_n P~ A_n,  Phi_{t,h} = sum_n P~ phi_nt,  sp_{t,h} = sum_n P~     (P~ = dropout(softmax_n(score)))
+// and the head output is W_v[h] (Z + W_phi Phi) + sp b_v[h] -- GEMMs on B*T rows done by the caller.  No vector of
+// width d exists per (note, query) pair; sin() is evaluated on the fly (twice in forward, once in backward).
+//
+// Layout: A [M_alloc, d] (lda), a_sc / da [M_alloc, H], g [H, d_tau]; output rows r = (b*T + t)*H + h:
+// Z [B*T*H, d], Phi [B*T*H, d_tau], sp [B*T*H]; probs[(h*T + t) * M_alloc + row] (softmax before dropout).
+// Forward: grid (ceil(T/TQ), B); backward: one CTA per sample walking its query tiles (dA / da / the Time2Vec partials
+// are owned by that CTA: no atomics, deterministic).
+#include "rowtile.cuh"
+#include "../../include/immtsf.h"
+
+constexpr int PQ_MAXH = 8;
+
+struct PQArgs {
+  const float* A; int lda; const float* a_sc; const float* g; const float* tau; const int32_t* offsets;
+  const float* t_hat; int t_bstride;
+  const float* w_lin; const float* b_lin; const float* w_per; const float* b_per;
+  int B, T, H, d, dt, NM, TQ; size_t M_alloc; uint32_t thr; SeedArg seed;
+  float* Z; float* Phi; float* sp; float* probs;
+  const float* dZ; const float* dPhi; const float* dsp; const float* probs_in;
+  float* dA; int lddA; float* da; float* dpart;
+};
+
+__device__ __forceinline__ float pq_phi(int k, float dl, float wl, float bl, const float* __restrict__ w_per,
+                                        const float* __restrict__ b_per) {
+  return k == 0 ? fmaf(wl, dl, bl) : sinf(fmaf(__ldg(w_per + k - 1), dl, __ldg(b_per + k - 1)));
+}
+
+// smem: s_dl [TQ][NM] | s_p [TQ*H][NM]
+__global__ void __launch_bounds__(256) t2vq_fwd_kernel(const PQArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const int H = a.H, d = a.d, dt = a.dt, NM = a.NM, TQ = a.TQ, T = a.T;
+  float* s_dl = smem;
+  float* s_p = smem + (size_t)TQ * NM;
+  const int b = blockIdx.y, t0 = blockIdx.x * TQ;
+  const int tcnt = min(TQ, T - t0), rows = tcnt * H;
+  const int nb = a.offsets[b], nn = a.offsets[b + 1] - nb;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const size_t row0 = ((size_t)b * T + t0) * H;
+  if (nn == 0) {  // no notes: the pooled quantities are 0 (the caller's LayerNorm masks the sample, reference :146-150)
+    for (int i = threadIdx.x; i < rows * d; i += blockDim.x) a.Z[row0 * d + i] = 0.f;
+    for (int i = threadIdx.x; i < rows * dt; i += blockDim.x) a.Phi[row0 * dt + i] = 0.f;
+    for (int i = threadIdx.x; i < rows; i += blockDim.x) a.sp[row0 + i] = 0.f;
+    return;
+  }
+  const float wl = a.w_lin[0], bl = a.b_lin[0];
+  const float inv_keep = inv_keep_from_thr(a.thr);
+  const uint64_t seed = resolve_seed(a.seed);
+  // 0) lags
+  for (int i = threadIdx.x; i < tcnt * nn; i += blockDim.x) {
+    const int tt = i / nn, n = i % nn;
+    s_dl[tt * NM + n] = fmaxf(a.t_hat[(size_t)b * a.t_bstride + t0 + tt] - a.tau[nb + n], 0.f);
+  }
+  __syncthreads();
+  // 1) scores: one warp per (query time, note), lanes over the Time2Vec units, all heads at once
+  for (int i = w; i < tcnt * nn; i += nw) {
+    const int tt = i / nn, n = i % nn;
+    const float dl = s_dl[tt * NM + n];
+    float acc[PQ_MAXH];
+#pragma unroll
+    for (int h = 0; h < PQ_MAXH; ++h) acc[h] = 0.f;
+    for (int k = lane; k < dt; k += 32) {
+      const float ph = pq_phi(k, dl, wl, bl, a.w_per, a.b_per);
+#pragma unroll
+      for (int h = 0; h < PQ_MAXH; ++h)
+        if (h < H) acc[h] = fmaf(__ldg(a.g + (size_t)h * dt + k), ph, acc[h]);
+    }
+#pragma unroll
+    for (int h = 0; h < PQ_MAXH; ++h) {
+      if (h < H) {
+        const float s = warp_sum(acc[h]);
+        if (lane == 0) s_p[(tt * H + h) * NM + n] = s + a.a_sc[(size_t)(nb + n) * H + h];
+      }
+    }
+  }
+  __syncthreads();
+  // 2) softmax over the segment + dropout, one warp per (query time, head) row
+  for (int r = w; r < rows; r += nw) {
+    const int tt = r / H, h = r % H, t = t0 + tt;
+    float* pr = s_p + (size_t)r * NM;
+    float mx = -INFINITY;
+    for (int n = lane; n < nn; n += 32) mx = fmaxf(mx, pr[n]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int n = lane; n < nn; n += 32) {
+      const float e = expf(pr[n] - mx);
+      pr[n] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    float spt = 0.f;
+    for (int n = lane; n < nn; n += 32) {
+      const float p = pr[n] / sum;
+      if (a.probs) a.probs[((size_t)h * T + t) * a.M_alloc + nb + n] = p;
+      const float pt = p * dropout_scale(seed, IMMTSF_SITE_TTF_ATTN, (((uint64_t)b * T + t) * H + h) * NM + n, a.thr, inv_keep);
+      pr[n] = pt;
+      spt += pt;
+    }
+    spt = warp_sum(spt);
+    if (lane == 0) a.sp[row0 + r] = spt;
+  }
+  __syncthreads();
+  // 3) Z rows: thread per float4 column, 8 rows of the tile at a time
+  const int d4 = d >> 2;
+  for (int col4 = threadIdx.x; col4 < d4; col4 += blockDim.x) {
+    for (int r0 = 0; r0 < rows; r0 += 8) {
+      float4 acc[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc[u] = f4_zero();
+      for (int n = 0; n < nn; ++n) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(a.A + (size_t)(nb + n) * a.lda) + col4);
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (r0 + u < rows) f4_fma(acc[u], s_p[(size_t)(r0 + u) * NM + n], v);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (r0 + u < rows) reinterpret_cast<float4*>(a.Z + (row0 + r0 + u) * d)[col4] = acc[u];
+    }
+  }
+  // 4) Phi rows: thread per (query time, unit), all heads
+  for (int i = threadIdx.x; i < tcnt * dt; i += blockDim.x) {
+    const int tt = i / dt, k = i % dt;
+    float acc[PQ_MAXH];
+#pragma unroll
+    for (int h = 0; h < PQ_MAXH; ++h) acc[h] = 0.f;
+    for (int n = 0; n < nn; ++n) {
+      const float ph = pq_phi(k, s_dl[tt * NM + n], wl, bl, a.w_per, a.b_per);
+#pragma unroll
+      for (int h = 0; h < PQ_MAXH; ++h)
+        if (h < H) acc[h] = fmaf(s_p[(size_t)(tt * H + h) * NM + n], ph, acc[h]);
+    }
+#pragma unroll
+    for (int h = 0; h < PQ_MAXH; ++h)
+      if (h < H) a.Phi[(row0 + tt * H + h) * dt + k] = acc[h];
+  }
+}
+
+// smem: s_dl [TQ][NM] | s_pt [TQ*H][NM] | s_ds [TQ*H][NM] | s_da [H][NM]
+__global__ void __launch_bounds__(256) t2vq_bwd_kernel(const PQArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const int H = a.H, d = a.d, dt = a.dt, NM = a.NM, TQ = a.TQ, T = a.T;
+  float* s_dl = smem;
+  float* s_pt = s_dl + (size_t)TQ * NM;
+  float* s_ds = s_pt + (size_t)TQ * H * NM;
+  float* s_da = s_ds + (size_t)TQ * H * NM;
+  const int b = blockIdx.x;
+  const int nb = a.offsets[b], nn = a.offsets[b + 1] - nb;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  float* part = a.dpart + (size_t)b * (2 + H) * dt;
+  if (nn == 0) {
+    for (int i = threadIdx.x; i < (2 + H) * dt; i += blockDim.x) part[i] = 0.f;
+    return;
+  }
+  const float wl = a.w_lin[0], bl = a.b_lin[0];
+  const float inv_keep = inv_keep_from_thr(a.thr);
+  const uint64_t seed = resolve_seed(a.seed);
+  const int d4 = d >> 2;
+  for (int t0 = 0; t0 < T; t0 += TQ) {
+    const int tcnt = min(TQ, T - t0), rows = tcnt * H;
+    const size_t row0 = ((size_t)b * T + t0) * H;
+    // 0) lags
+    for (int i = threadIdx.x; i < tcnt * nn; i += blockDim.x) {
+      const int tt = i / nn, n = i % nn;
+      s_dl[tt * NM + n] = fmaxf(a.t_hat[(size_t)b * a.t_bstride + t0 + tt] - a.tau[nb + n], 0.f);
+    }
+    __syncthreads();
+    // a) dP~[t,h,n] = dZ[t,h] . A[n] + dPhi[t,h] . phi[n,t] + dsp[t,h]: one warp per (query time, note)
+    for (int i = w; i < tcnt * nn; i += nw) {
+      const int tt = i / nn, n = i % nn;
+      const float dl = s_dl[tt * NM + n];
+      float acc[PQ_MAXH];
+#pragma unroll
+      for (int h = 0; h < PQ_MAXH; ++h) acc[h] = 0.f;
+      const float4* ar = reinterpret_cast<const float4*>(a.A + (size_t)(nb + n) * a.lda);
+      for (int c4 = lane; c4 < d4; c4 += 32) {
+        const float4 av = __ldg(ar + c4);
+#pragma unroll
+        for (int h = 0; h < PQ_MAXH; ++h)
+          if (h < H) acc[h] += f4_dot(av, __ldg(reinterpret_cast<const float4*>(a.dZ + (row0 + tt * H + h) * d) + c4));
+      }
+      for (int k = lane; k < dt; k += 32) {
+        const float ph = pq_phi(k, dl, wl, bl, a.w_per, a.b_per);
+#pragma unroll
+        for (int h = 0; h < PQ_MAXH; ++h)
+          if (h < H) acc[h] = fmaf(__ldg(a.dPhi + (row0 + tt * H + h) * dt + k), ph, acc[h]);
+      }
+#pragma unroll
+      for (int h = 0; h < PQ_MAXH; ++h) {
+        if (h < H) {
+          const float s = warp_sum(acc[h]);
+          if (lane == 0) s_ds[(size_t)(tt * H + h) * NM + n] = s + a.dsp[row0 + tt * H + h];
+        }
+      }
+    }
+    __syncthreads();
+    // b) dropout + softmax backward per row: s_ds <- dS, s_pt <- P~
+    for (int r = w; r < rows; r += nw) {
+      const int tt = r / H, h = r % H, t = t0 + tt;
+      float* dsr = s_ds + (size_t)r * NM;
+      float* ptr = s_pt + (size_t)r * NM;
+      const float* pg = a.probs_in + ((size_t)h * T + t) * a.M_alloc + nb;
+      float D = 0.f;
+      for (int n = lane; n < nn; n += 32) {
+        const float ks = dropout_scale(seed, IMMTSF_SITE_TTF_ATTN, (((uint64_t)b * T + t) * H + h) * NM + n, a.thr, inv_keep);
+        const float p = pg[n];
+        const float dp = dsr[n] * ks;
+        dsr[n] = dp;
+        ptr[n] = p * ks;
+        D = fmaf(p, dp, D);
+      }
+      D = warp_sum(D);
+      for (int n = lane; n < nn; n += 32) dsr[n] = pg[n] * (dsr[n] - D);
+    }
+    __syncthreads();
+    // b2) da[n,h] += sum over the tile's query times of dS, in query order (deterministic)
+    for (int i = threadIdx.x; i < H * nn; i += blockDim.x) {
+      const int h = i / nn, n = i % nn;
+      float acc = t0 == 0 ? 0.f : s_da[h * NM + n];
+      for (int tt = 0; tt < tcnt; ++tt) acc += s_ds[(size_t)(tt * H + h) * NM + n];
+      s_da[h * NM + n] = acc;
+    }
+    // c) dA[n] (+)= sum_r P~[r,n] dZ[r]: thread per float4 column, 8 notes at a time
+    for (int col4 = threadIdx.x; col4 < d4; col4 += blockDim.x) {
+      const float4* gz = reinterpret_cast<const float4*>(a.dZ + row0 * d) + col4;
+      for (int n0 = 0; n0 < nn; n0 += 8) {
+        float4 acc[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc[u] = f4_zero();
+        for (int r = 0; r < rows; ++r) {
+          const float4 go = __ldg(gz + (size_t)r * d4);
+          const float* pr = s_pt + (size_t)r * NM + n0;
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            if (n0 + u < nn) f4_fma(acc[u], pr[u], go);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          if (n0 + u < nn) {
+            float4* dst = reinterpret_cast<float4*>(a.dA + (size_t)(nb + n0 + u) * a.lddA) + col4;
+            if (t0 == 0) *dst = acc[u];
+            else { float4 o = *dst; f4_add(o, acc[u]); *dst = o; }
+          }
+        }
+      }
+    }
+    // d) Time2Vec parameter partials and dg: thread per unit k; every partial of sample b is owned by one thread
+    for (int k = threadIdx.x; k < dt; k += blockDim.x) {
+      const float wk = k == 0 ? wl : __ldg(a.w_per + k - 1), bk = k == 0 ? bl : __ldg(a.b_per + k - 1);
+      float sw = 0.f, sb = 0.f, sg[PQ_MAXH], gk[PQ_MAXH];
+#pragma unroll
+      for (int h = 0; h < PQ_MAXH; ++h) {
+        sg[h] = 0.f;
+        gk[h] = h < H ? __ldg(a.g + (size_t)h * dt + k) : 0.f;
+      }
+      for (int tt = 0; tt < tcnt; ++tt) {
+        float dph[PQ_MAXH];
+#pragma unroll
+        for (int h = 0; h < PQ_MAXH; ++h) dph[h] = h < H ? __ldg(a.dPhi + (row0 + tt * H + h) * dt + k) : 0.f;
+        for (int n = 0; n < nn; ++n) {
+          const float dl = s_dl[tt * NM + n];
+          const float arg = fmaf(wk, dl, bk);
+          float ph = arg, cs = 1.f;
+          if (k != 0) sincosf(arg, &ph, &cs);
+          float dphi = 0.f;
+#pragma unroll
+          for (int h = 0; h < PQ_MAXH; ++h) {
+            if (h < H) {
+              const float ds = s_ds[(size_t)(tt * H + h) * NM + n];
+              dphi = fmaf(s_pt[(size_t)(tt * H + h) * NM + n], dph[h], dphi);
+              dphi = fmaf(ds, gk[h], dphi);
+              sg[h] = fmaf(ds, ph, sg[h]);
+            }
+          }
+          const float dpre = dphi * cs;
+          sw = fmaf(dpre, dl, sw);
+          sb += dpre;
+        }
+      }
+      if (t0 == 0) {
+        part[k] = sw;
+        part[dt + k] = sb;
+#pragma unroll
+        for (int h = 0; h < PQ_MAXH; ++h)
+          if (h < H) part[(size_t)(2 + h) * dt + k] = sg[h];
+      } else {
+        part[k] += sw;
+        part[dt + k] += sb;
+#pragma unroll
+        for (int h = 0; h < PQ_MAXH; ++h)
+          if (h < H) part[(size_t)(2 + h) * dt + k] += sg[h];
+      }
+    }
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < H * nn; i += blockDim.x) {
+    const int h = i / nn, n = i % nn;
+    a.da[(size_t)(nb + n) * H + h] = s_da[h * NM + n];
+  }
+}
+
+static int pq_common(PQArgs& a, const char* who, const float* A, int lda, const float* g, const float* tau_flat,
+                     const int32_t* offsets, const float* t_hat, int t_bstride, const float* w_lin, const float* b_lin,
+                     const float* w_per, const float* b_per, int B, int T, int H, int d, int d_tau, int N_max, int M_alloc,
+                     uint32_t drop_thr, uint64_t seed) {
+  IMMTSF_REQUIRE(A && g && tau_flat && offsets && t_hat && w_lin && b_lin && w_per && b_per, "%s: null pointer", who);
+  IMMTSF_REQUIRE(H >= 1 && H <= PQ_MAXH, "%s: 1 <= n_heads <= %d supported (got %d)", who, PQ_MAXH, H);
+  IMMTSF_REQUIRE(d >= 4 && (d & 3) == 0 && (lda & 3) == 0 && lda >= d, "%s: d and lda must be multiples of 4 (d=%d lda=%d)", who, d, lda);
+  IMMTSF_REQUIRE(d_tau > 1, "%s: d_tau must be > 1 (TTF_T2V_XAttn_old.py:14)", who);
+  IMMTSF_REQUIRE(((uintptr_t)A & 15) == 0, "%s: A must be 16B aligned", who);
+  IMMTSF_REQUIRE(N_max >= 1 && T >= 1 && M_alloc >= 1 && t_bstride >= 0, "%s: N_max, T, M_alloc must be >= 1", who);
+  a.A = A; a.lda = lda; a.g = g; a.tau = tau_flat; a.offsets = offsets; a.t_hat = t_hat; a.t_bstride = t_bstride;
+  a.w_lin = w_lin; a.b_lin = b_lin; a.w_per = w_per; a.b_per = b_per;
+  a.B = B; a.T = T; a.H = H; a.d = d; a.dt = d_tau; a.NM = N_max; a.M_alloc = (size_t)M_alloc; a.thr = drop_thr; a.seed = make_seed(seed);
+  return IMMTSF_OK;
+}
+
+extern "C" int immtsf_t2vq_attn_fwd(const float* A, int lda, const float* a_sc, const float* g, const float* tau_flat,
+                                    const int32_t* offsets, const float* t_hat, int t_hat_bstride, const float* w_lin,
+                                    const float* b_lin, const float* w_per, const float* b_per, int B, int T, int H, int d,
+                                    int d_tau, int N_max, int M_alloc, uint32_t drop_thr, uint64_t seed, float* Z, float* Phi,
+                                    float* sp, float* probs, void* stream) {
+  if (B == 0) return IMMTSF_OK;
+  PQArgs a = {};
+  const int rc = pq_common(a, "t2vq_attn_fwd", A, lda, g, tau_flat, offsets, t_hat, t_hat_bstride, w_lin, b_lin, w_per, b_per, B, T, H, d,
+                           d_tau, N_max, M_alloc, drop_thr, seed);
+  if (rc != IMMTSF_OK) return rc;
+  IMMTSF_REQUIRE(a_sc && Z && Phi && sp, "t2vq_attn_fwd: null pointer");
+  IMMTSF_REQUIRE(((uintptr_t)Z & 15) == 0, "t2vq_attn_fwd: Z must be 16B aligned");
+  IMMTSF_REQUIRE(B <= 65535, "t2vq_attn_fwd: B <= 65535");
+  a.a_sc = a_sc; a.Z = Z; a.Phi = Phi; a.sp = sp; a.probs = probs;
+  int TQ = 8;
+  const size_t plane = (size_t)N_max * sizeof(float);
+  while (TQ > 1 && (size_t)TQ * (1 + H) * plane > 160 * 1024) TQ >>= 1;
+  const size_t smem = (size_t)TQ * (1 + H) * plane;
+  if (smem > 200 * 1024) { immtsf_set_error("t2vq_attn_fwd: H*N_max=%d too large for shared memory", H * N_max); return IMMTSF_ERR_UNSUPPORTED; }
+  a.TQ = TQ;
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    cudaFuncSetAttribute(t2vq_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    smem_set = smem;
+  }
+  t2vq_fwd_kernel<<<dim3(ceil_div(T, TQ), B), 256, smem, (cudaStream_t)stream>>>(a);
+  IMMTSF_CHECK_LAUNCH("t2vq_attn_fwd");
+  return IMMTSF_OK;
+}
+
+extern "C" int immtsf_t2vq_attn_bwd(const float* dZ, const float* dPhi, const float* dsp, const float* A, int lda, const float* g,
+                                    const float* probs, const float* tau_flat, const int32_t* offsets, const float* t_hat,
+                                    int t_hat_bstride, const float* w_lin, const float* b_lin, const float* w_per,
+                                    const float* b_per, int B, int T, int H, int d, int d_tau, int N_max, int M_alloc,
+                                    uint32_t drop_thr, uint64_t seed, float* dA, int lddA, float* da, float* dpart, void* stream) {
+  if (B == 0) return IMMTSF_OK;
+  PQArgs a = {};
+  const int rc = pq_common(a, "t2vq_attn_bwd", A, lda, g, tau_flat, offsets, t_hat, t_hat_bstride, w_lin, b_lin, w_per, b_per, B, T, H, d,
+                           d_tau, N_max, M_alloc, drop_thr, seed);
+  if (rc != IMMTSF_OK) return rc;
+  IMMTSF_REQUIRE(dZ && dPhi && dsp && probs && dA && da && dpart, "t2vq_attn_bwd: null pointer");
+  IMMTSF_REQUIRE(((uintptr_t)dZ & 15) == 0 && ((uintptr_t)dA & 15) == 0 && (lddA & 3) == 0 && lddA >= d,
+                 "t2vq_attn_bwd: dZ / dA must be 16B aligned, lddA a multiple of 4");
+  a.dZ = dZ; a.dPhi = dPhi; a.dsp = dsp; a.probs_in = probs; a.dA = dA; a.lddA = lddA; a.da = da; a.dpart = dpart;
+  int TQ = 8;
+  const size_t plane = (size_t)N_max * sizeof(float);
+  while (TQ > 1 && ((size_t)TQ * (1 + 2 * H) + H) * plane > 160 * 1024) TQ >>= 1;
+  const size_t smem = ((size_t)TQ * (1 + 2 * H) + H) * plane;
+  if (smem > 200 * 1024) { immtsf_set_error("t2vq_attn_bwd: H*N_max=%d too large for shared memory", H * N_max); return IMMTSF_ERR_UNSUPPORTED; }
+  a.TQ = TQ;
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    cudaFuncSetAttribute(t2vq_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    smem_set = smem;
+  }
+  t2vq_bwd_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(a);
+  IMMTSF_CHECK_LAUNCH("t2vq_attn_bwd");
+  return IMMTSF_OK;
+}

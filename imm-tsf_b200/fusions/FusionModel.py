@@ -18,10 +18,13 @@ from immtsf import ops, runtime
 from fusions import _common as cm
 from fusions.TTF_RecAvg import TTF_RecAvg
 from fusions.TTF_T2V_XAttn import TTF_T2V_XAttn
+from fusions.TTF_T2V_XAttn_old import TTF_T2V_XAttn as TTF_T2V_XAttn_old
 from fusions.MMF_GR_Add import MMF_GR_Add
 from fusions.MMF_XAttn_Add import MMF_XAttn_Add
 
-_TTF_CLASSES = {"TTF_RecAvg": TTF_RecAvg, "TTF_T2V_XAttn": TTF_T2V_XAttn}
+# "TTF_T2V_XAttn_old": the per-(note, query) variant (reference file of that name; not in main.py's argparse choices --
+# pass the class or this name through args.TTF_module)
+_TTF_CLASSES = {"TTF_RecAvg": TTF_RecAvg, "TTF_T2V_XAttn": TTF_T2V_XAttn, "TTF_T2V_XAttn_old": TTF_T2V_XAttn_old}
 _MMF_CLASSES = {"MMF_GR_Add": MMF_GR_Add, "MMF_XAttn_Add": MMF_XAttn_Add}
 
 

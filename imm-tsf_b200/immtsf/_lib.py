@@ -46,6 +46,8 @@ SIGNATURES = {
     "immtsf_time2vec_bwd": [P, I, P, P, P, I, P, P, P, P, P, I, P],
     "immtsf_segattn_fwd": [P, P, P, I, I, I, I, I, I, U32, U64, P, P, P],
     "immtsf_segattn_bwd": [P, P, P, P, P, I, I, I, I, I, I, U32, U64, P, P, P],
+    "immtsf_t2vq_attn_fwd": [P, I, P, P, P, P, P, I, P, P, P, P, I, I, I, I, I, I, I, U32, U64, P, P, P, P, P],
+    "immtsf_t2vq_attn_bwd": [P, P, P, P, I, P, P, P, P, P, I, P, P, P, P, I, I, I, I, I, I, I, U32, U64, P, I, P, P, P],
     "immtsf_ln_fwd": [P, I, P, P, P, I, P, P, I, I, F, U32, U64, U32, P, P, P, P],
     "immtsf_ln_bwd": [P, P, I, P, P, P, I, P, P, P, I, I, U32, U64, U32, P, P, P, P, P],
     "immtsf_gru_scan_fwd": [P, P, P, I, I, I, P, P, P, P],

@@ -5,6 +5,7 @@ sits on the compute path; torch provides memory, views and the autograd tape.
 Reference semantics (file:line):
   RecAvgFn     fusions/TTF_RecAvg.py:54-112
   T2VXAttnFn   fusions/TTF_T2V_XAttn.py:93-184 (+ nn.MultiheadAttention internals)
+  T2VPerQueryFn fusions/TTF_T2V_XAttn_old.py:82-161 (per-(note, query) Time2Vec)
   GRAddFn      fusions/MMF_GR_Add.py:31-61
   XAttnAddFn   fusions/MMF_XAttn_Add.py:56-103
 """
@@ -226,6 +227,123 @@ class T2VXAttnFn(torch.autograd.Function):
         if fold:
             dW_o = res["dW_o"]
         fk.join(dQp, dW_in, db_in, dwl, dbl, dwp, dbp, dW_kv, db_kv, d_in_w, d_in_b, dW_o, db_o)
+        return (None, None, None, None, None, None, None, dQp.view(1, 1, d), dW_in, db_in, dwl, dbl, dwp, dbp, dW_kv, db_kv,
+                d_in_w, d_in_b, dW_o, db_o, dgamma, dbeta, dW_po, db_po)
+
+
+# ============================================================== TTF_T2V_XAttn, per-(note, query) variant
+class T2VPerQueryFn(torch.autograd.Function):
+    """fusions/TTF_T2V_XAttn_old.py:82-161: Time2Vec of the clamped lag of every (note, query) pair enters keys and
+    values.  The reference projects B*T*N concatenated rows twice (KV_proj, then the MHA in-projection); here, with
+    X_nt = A_n + W_phi phi_nt, the projections run once per note (A) and once per (sample, query, head) row (Z, Phi), and
+    the fused kernel between them never forms a per-pair vector of width d (csrc/t2v_perquery.cu).  The composition is
+    stated in plain torch in oracle/perquery_schedule.py and checked there against the reference semantics."""
+
+    @staticmethod
+    def forward(ctx, r: RaggedNotes, t_hat, T, H, thr, seed, save, Qp, W_in, b_in, w_lin, b_lin, w_per, b_per, W_kv, b_kv,
+                in_w, in_b, out_w, out_b, gamma, beta, W_po, b_po):
+        B = r.B
+        d = W_po.shape[0]
+        dt, hd = d // 2, d // H
+        dev = Qp.device
+        new = lambda *s: torch.empty(*s, dtype=_f32, device=dev)
+        step = ops.step_ctx()
+        lo = step.lo
+        W_a, W_phi = W_kv[:, :d], W_kv[:, d:]
+        W_q, W_k, W_v, b_v = in_w[:d], in_w[d:2 * d], in_w[2 * d:], in_b[2 * d:]
+        Vp = ops.linear_fwd(r.emb_flat, W_in, b_in, ragged=r.m_dev, lo=lo) if W_in is not None else r.emb_flat
+        A = ops.linear_fwd(Vp, W_a, b_kv, ragged=r.m_dev, lo=lo)  # the note part of KV_proj (:129), once per note
+        # query side: u_h = W_k[h]^T q_h (block-diagonal q), g_h = W_phi^T u_h
+        scale = math.sqrt(1.0 / float(hd))
+        q0 = ops.linear_fwd(Qp.view(1, d), W_q, in_b[:d])
+        q = ops.axpby(q0, scale, torch.empty_like(q0), False)
+        Qblk = torch.zeros(H, d, dtype=_f32, device=dev)
+        for h in range(H):
+            Qblk[h, h * hd:(h + 1) * hd].copy_(q[0, h * hd:(h + 1) * hd])
+        U = ops.gemm(Qblk, W_k, new(H, d))
+        a_sc = ops.linear_fwd(A, U, None, ragged=r.m_dev)  # [M_alloc, H]
+        g = ops.gemm(U, W_phi, new(H, dt))
+        t2v = (w_lin, b_lin, w_per, b_per)
+        Z, Phi, sp, probs = ops.t2vq_attn_fwd(A, a_sc, g, r, t_hat, t2v, T, H, d, dt, thr, seed, save)
+        XZ = ops.gemm(Phi, W_phi, Z, transB=True, beta=1.0, lo=lo)  # Z + Phi W_phi^T, in place
+        XZv, spv = XZ.view(B * T, H * d), sp.view(B * T, H)
+        O = new(B * T, d)
+        for h in range(H):
+            hs = slice(h * hd, (h + 1) * hd)
+            ops.gemm(XZv[:, h * d:(h + 1) * d], W_v[hs], O[:, hs], transB=True, lo=lo)
+            ops.gemm(spv[:, h:h + 1], b_v[hs].view(1, hd), O[:, hs], beta=1.0)  # sum_n P~ b_v (P~ does not sum to 1 under dropout)
+        attn_out = ops.linear_fwd(O, out_w, out_b, lo=lo)
+        y, mean, rstd = ops.ln_fwd(attn_out, Qp.view(d), r.m_txt, T, gamma, beta, thr, seed, ops.SITE_TTF_DROPOUT, save)
+        E = ops.linear_fwd(y, W_po, b_po, lo=lo, emit_lo=step.e_txt_feeds_tc)
+        if save:
+            ctx.r, ctx.T, ctx.H, ctx.thr, ctx.seed, ctx.lo, ctx.scale = r, T, H, thr, seed, lo, scale
+            ctx.has_in = W_in is not None
+            ctx.save_for_backward(Qp, w_lin, b_lin, w_per, b_per, W_kv, in_w, in_b, out_w, gamma, W_po, t_hat, Vp, A, Qblk, U, g, Phi, sp, probs,
+                                  XZ, O, attn_out, y, mean, rstd)
+        return E.view(B, T, d)
+
+    @staticmethod
+    def backward(ctx, dE_txt):
+        (Qp, w_lin, b_lin, w_per, b_per, W_kv, in_w, in_b, out_w, gamma, W_po, t_hat, Vp, A, Qblk, U, g, Phi, sp, probs, XZ, O,
+         attn_out, y, mean, rstd) = ctx.saved_tensors
+        r, T, H, thr, seed, lo, scale = ctx.r, ctx.T, ctx.H, ctx.thr, ctx.seed, ctx.lo, ctx.scale
+        ctx.lo = None
+        B, d = r.B, W_po.shape[0]
+        dt, hd = d // 2, d // H
+        dev = Qp.device
+        new = lambda *s: torch.empty(*s, dtype=_f32, device=dev)
+        W_a, W_phi = W_kv[:, :d], W_kv[:, d:]
+        W_q, W_k, W_v, b_v = in_w[:d], in_w[d:2 * d], in_w[2 * d:], in_b[2 * d:]
+        dE = dE_txt.contiguous().view(B * T, d)
+        dW_po = ops.linear_wgrad(dE, y, lo=lo)
+        db_po = ops.colsum(dE)
+        dy = ops.linear_dgrad(dE, W_po, lo=lo)
+        dx, dres, dgamma, dbeta = ops.ln_bwd(dy, attn_out, Qp.view(d), r.m_txt, T, gamma, mean, rstd, thr, seed, ops.SITE_TTF_DROPOUT)
+        dW_o = ops.linear_wgrad(dx, O, lo=lo)
+        db_o = ops.colsum(dx)
+        dO = ops.linear_dgrad(dx, out_w, lo=lo)
+        d_in_w, d_in_b = new(3 * d, d), new(3 * d)
+        dXZ, dsp = new(B * T * H, d), new(B * T * H)
+        XZv, spv, dXZv, dspv = XZ.view(B * T, H * d), sp.view(B * T, H), dXZ.view(B * T, H * d), dsp.view(B * T, H)
+        for h in range(H):
+            hs = slice(h * hd, (h + 1) * hd)
+            vs = slice(2 * d + h * hd, 2 * d + (h + 1) * hd)
+            dO_h = dO[:, hs]
+            ops.gemm(dO_h, W_v[hs], dXZv[:, h * d:(h + 1) * d], lo=lo)  # [BT,hd] x [hd,d]
+            ops.gemm(dO_h, XZv[:, h * d:(h + 1) * d], d_in_w[vs], transA=True, lo=lo)  # dW_v[h]
+            ops.gemm(dO_h, spv[:, h:h + 1], d_in_b[vs].view(hd, 1), transA=True)  # db_v[h] = dO_h^T sp_h
+            ops.gemm(dO_h, b_v[hs].view(hd, 1), dspv[:, h:h + 1])  # dsp_h = dO_h b_v[h]
+        dPhi = ops.gemm(dXZ, W_phi, new(B * T * H, dt), lo=lo)
+        dW_kv = new(d, d + dt)
+        ops.gemm(dXZ, Phi, dW_kv[:, d:], transA=True, lo=lo)  # dW_phi = dXZ^T Phi
+        t2v = (w_lin, b_lin, w_per, b_per)
+        dA, da, dpart = ops.t2vq_attn_bwd(dXZ, dPhi, dsp, A, g, probs, r, t_hat, t2v, T, H, d, dt, thr, seed)
+        tg = ops.colsum(dpart)  # [(2+H)*dt]: d w, d b, dg
+        dg = tg[2 * dt:].view(H, dt)
+        dU = ops.linear_wgrad(da, A, ragged=r.m_dev)  # [H,d] = da^T A
+        ops.gemm(dg, W_phi, dU, transB=True, beta=1.0)  # + dg W_phi^T
+        ops.gemm(da, U, dA, beta=1.0, ragged=r.m_dev, ragged_dim=1)  # dA += da U
+        ops.gemm(U, dg, dW_kv[:, d:], transA=True, beta=1.0)  # dW_phi += U^T dg
+        ops.gemm(Qblk, dU, d_in_w[d:2 * d], transA=True)  # dW_k: row j of head h is q_j dU_h
+        d_in_b[d:2 * d].zero_()  # q_h . b_k[h] is constant over the notes of a segment: it cancels in the softmax
+        dQblk = ops.gemm(dU, W_k, new(H, d), transB=True)
+        dq = new(1, d)
+        for h in range(H):
+            dq[0, h * hd:(h + 1) * hd].copy_(dQblk[h, h * hd:(h + 1) * hd])
+        dq_pre = ops.axpby(dq, scale, torch.empty_like(dq), False)
+        ops.linear_wgrad(dq_pre, Qp.view(1, d), out=d_in_w[:d])
+        d_in_b[:d].copy_(dq_pre.view(d))
+        dQp = ops.linear_dgrad(dq_pre, W_q)
+        ops.axpby(dres, 1.0, dQp.view(d), True)
+        ops.linear_wgrad(dA, Vp, out=dW_kv[:, :d], ragged=r.m_dev, lo=lo)
+        db_kv = ops.colsum(dA, ragged=r.m_dev)
+        dW_in = db_in = None
+        if ctx.has_in:
+            dVp = ops.linear_dgrad(dA, W_a, ragged=r.m_dev, lo=lo)
+            dW_in = ops.linear_wgrad(dVp, r.emb_flat, ragged=r.m_dev, lo=lo)
+            db_in = ops.colsum(dVp, ragged=r.m_dev)
+        dwl, dbl = tg[:1].view(1, 1), tg[dt:dt + 1]
+        dwp, dbp = tg[1:dt].view(dt - 1, 1), tg[dt + 1:2 * dt]
         return (None, None, None, None, None, None, None, dQp.view(1, 1, d), dW_in, db_in, dwl, dbl, dwp, dbp, dW_kv, db_kv,
                 d_in_w, d_in_b, dW_o, db_o, dgamma, dbeta, dW_po, db_po)
 

@@ -472,6 +472,39 @@ def segattn_bwd(d_attn_cat, q, KVp, probs, r: RaggedNotes, T, H, d, per_query, t
     return dKVp, dq_partial
 
 
+def t2vq_attn_fwd(A, a_sc, g, r: RaggedNotes, t_hat, t2v_params, T, H, d, d_tau, thr, seed, save):
+    """Per-(note, query) Time2Vec attention over each ragged segment (csrc/t2v_perquery.cu).  Returns Z [B*T*H, d],
+    Phi [B*T*H, d_tau], sp [B*T*H] and the saved softmax [H*T*M_alloc] (None unless save)."""
+    R = r.B * T * H
+    dev = A.device
+    Z = torch.empty(R, d, dtype=torch.float32, device=dev)
+    Phi = torch.empty(R, d_tau, dtype=torch.float32, device=dev)
+    sp = torch.empty(R, dtype=torch.float32, device=dev)
+    probs = torch.empty(H * T * r.M_alloc, dtype=torch.float32, device=dev) if save else None
+    w_lin, b_lin, w_per, b_per = t2v_params
+    bstride = 0 if t_hat.dim() == 1 else t_hat.stride(0)
+    _lib.call("immtsf_t2vq_attn_fwd", _p(A), A.stride(0), _p(a_sc), _p(g), _p(r.tau_flat), _p(r.offsets), _p(t_hat), bstride,
+              _p(w_lin), _p(b_lin), _p(w_per), _p(b_per), r.B, T, H, d, d_tau, max(r.N, 1), r.M_alloc, thr, seed, _p(Z), _p(Phi),
+              _p(sp), _p(probs), _stream())
+    return Z, Phi, sp, probs
+
+
+def t2vq_attn_bwd(dZ, dPhi, dsp, A, g, probs, r: RaggedNotes, t_hat, t2v_params, T, H, d, d_tau, thr, seed):
+    """Returns dA [M_alloc, d] (pooling part), da [M_alloc, H] and the per-sample partials [B, 2+H, d_tau]."""
+    dev = A.device
+    dA = torch.empty(r.M_alloc, d, dtype=torch.float32, device=dev)
+    da = torch.empty(r.M_alloc, H, dtype=torch.float32, device=dev)
+    dpart = torch.empty(max(r.B, 1), (2 + H) * d_tau, dtype=torch.float32, device=dev)
+    w_lin, b_lin, w_per, b_per = t2v_params
+    bstride = 0 if t_hat.dim() == 1 else t_hat.stride(0)
+    _lib.call("immtsf_t2vq_attn_bwd", _p(dZ), _p(dPhi), _p(dsp), _p(A), A.stride(0), _p(g), _p(probs), _p(r.tau_flat), _p(r.offsets),
+              _p(t_hat), bstride, _p(w_lin), _p(b_lin), _p(w_per), _p(b_per), r.B, T, H, d, d_tau, max(r.N, 1), r.M_alloc, thr, seed,
+              _p(dA), dA.stride(0), _p(da), _p(dpart), _stream())
+    zero_pad_rows(dA, d, r.m_dev, r.M_alloc)
+    zero_pad_rows(da, H, r.m_dev, r.M_alloc)
+    return dA, da, dpart
+
+
 def ln_fwd(x, res, valid, rows_per_sample, gamma, beta, thr, seed, site, save, xbias=None):
     R, d = x.shape
     y = torch.empty(R, d, dtype=torch.float32, device=x.device)

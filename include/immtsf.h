@@ -181,6 +181,29 @@ int immtsf_segattn_bwd(const float* d_attn_cat, const float* q, const float* KVp
                        const int32_t* offsets, int B, int T, int H, int d, int N_max, int per_query,
                        uint32_t drop_thr, uint64_t seed, float* dKVp, float* dq_partial, void* stream);
 
+/* ---- K3b: per-(note, query) Time2Vec attention (fusions/TTF_T2V_XAttn_old.py:119-143 -- Time2Vec
+ * of the clamped lag max(t_hat - tau, 0) of every (note, query) pair enters keys and values).  With
+ * X_nt = A_n + W_phi phi_nt (A = V' W_a^T + b_kv once per note, KV_proj.weight = [W_a | W_phi]) the caller supplies
+ * A [M_alloc, d], the per-note score base a_sc = A U^T [M_alloc, H] (u_h = W_k[h]^T q_h, q scaled by hd^-1/2) and
+ * g = U W_phi [H, d_tau]; the kernel evaluates sin() on the fly, takes softmax_n(a_sc + g_h . phi_nt) over each ragged
+ * segment, applies attention dropout and returns, for output row r = (b*T + t)*H + h,
+ *   Z [B*T*H, d] = sum_n P~ A_n,  Phi [B*T*H, d_tau] = sum_n P~ phi_nt,  sp [B*T*H] = sum_n P~
+ * (head output = W_v[h] (Z + W_phi Phi) + sp b_v[h]: GEMMs of the caller).  probs (nullable) [H*T*M_alloc]:
+ * softmax before dropout at (h*T + t)*M_alloc + row.  H <= 8.  t_hat_bstride = 0 for a shared 1-D t_hat. */
+int immtsf_t2vq_attn_fwd(const float* A, int lda, const float* a_sc, const float* g, const float* tau_flat,
+                         const int32_t* offsets, const float* t_hat, int t_hat_bstride, const float* w_lin,
+                         const float* b_lin, const float* w_per, const float* b_per, int B, int T, int H, int d,
+                         int d_tau, int N_max, int M_alloc, uint32_t drop_thr, uint64_t seed, float* Z, float* Phi,
+                         float* sp, float* probs, void* stream);
+/* Backward: dA [M_alloc, d] (rows of the pooling only; the caller adds da U), da [M_alloc, H], and per-sample
+ * partials dpart [B, 2+H, d_tau]: row 0 = d w (unit 0: time2vec.linear, units k >= 1: periodic k-1), row 1 = d b,
+ * rows 2.. = dg[h]; the caller sums them over samples (immtsf_colsum).  One CTA owns a sample: no atomics. */
+int immtsf_t2vq_attn_bwd(const float* dZ, const float* dPhi, const float* dsp, const float* A, int lda, const float* g,
+                         const float* probs, const float* tau_flat, const int32_t* offsets, const float* t_hat,
+                         int t_hat_bstride, const float* w_lin, const float* b_lin, const float* w_per,
+                         const float* b_per, int B, int T, int H, int d, int d_tau, int N_max, int M_alloc,
+                         uint32_t drop_thr, uint64_t seed, float* dA, int lddA, float* da, float* dpart, void* stream);
+
 /* ---- residual + LayerNorm + dropout over d (TTF_T2V_XAttn.py:171-179) ---
  * z = (valid[row / rows_per_sample] ? x + xbias : 0) + res;  y = dropout(LN(z))
  * xbias [d] (nullable): a bias that belongs to x (the MHA out_proj bias when out_proj is folded into V). */

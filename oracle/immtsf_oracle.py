@@ -337,6 +337,8 @@ def fusion_forward(
         E_txt, M_txt = ttf_recavg(P, notes, tau, t_hat, p, masks)
     elif ttf_name == "TTF_T2V_XAttn":
         E_txt, M_txt = ttf_t2v_xattn(P, notes, tau, t_hat, n_heads, p, masks, faithful_expand=faithful_expand)
+    elif ttf_name == "TTF_T2V_XAttn_old":
+        E_txt, M_txt = ttf_t2v_xattn_perquery(P, notes, tau, t_hat, n_heads, p, masks)
     else:
         raise KeyError(ttf_name)
     if torch.isnan(E_txt).any():  # :107

@@ -81,7 +81,7 @@ def oracle_masks(cfg, notes, T, C, d, p, seed):
         return m
     m["ttf.dropout"] = torch.from_numpy(
         philox_ref.keep_mask(seed, SITE_TTF_DROPOUT, np.arange(B * T * d, dtype=np.uint64), p).reshape(B, T, d))
-    if cfg["ttf"] == "TTF_T2V_XAttn":
+    if cfg["ttf"].startswith("TTF_T2V_XAttn"):
         mask = O.note_mask_from_content(notes)
         rank = (torch.cumsum(mask.to(torch.int64), dim=1) - 1).clamp_min(0).numpy().astype(np.uint64)  # [B,N]
         b_ = np.arange(B, dtype=np.uint64)[:, None, None, None]

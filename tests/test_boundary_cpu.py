@@ -86,11 +86,28 @@ def test_registries_and_identity_dispatch():
     from fusions.MMF_GR_Add import MMF_GR_Add
     from fusions.MMF_XAttn_Add import MMF_XAttn_Add
 
-    assert FM._TTF_CLASSES == {"TTF_RecAvg": TTF_RecAvg, "TTF_T2V_XAttn": TTF_T2V_XAttn}
+    from fusions.TTF_T2V_XAttn_old import TTF_T2V_XAttn as PerQuery
+
+    # the reference's two names (fusions/FusionModel.py:14-17) plus the per-(note, query) variant
+    assert FM._TTF_CLASSES == {"TTF_RecAvg": TTF_RecAvg, "TTF_T2V_XAttn": TTF_T2V_XAttn, "TTF_T2V_XAttn_old": PerQuery}
     assert FM._MMF_CLASSES == {"MMF_GR_Add": MMF_GR_Add, "MMF_XAttn_Add": MMF_XAttn_Add}
     from fusions.load_llm import get_context_window_size, get_d_model  # main.py:40 imports this name
 
     assert get_d_model("GPT2") == 768 and get_d_model("Llama") == 4096 and get_context_window_size("BERT") == 512
+
+
+def test_perquery_state_dict_contract():
+    """The per-(note, query) module loads the state_dict of the reference's TTF_T2V_XAttn_old class strictly."""
+    import fusions.load_llm as L
+    from fusions.TTF_T2V_XAttn_old import TTF_T2V_XAttn
+    from test_perquery_cpu import load_pq
+
+    cfg, params, inp, _ = load_pq("pq_h4")
+    L.register_d_model("TINY", inp["notes"].shape[2])
+    m = TTF_T2V_XAttn("TINY", 1, n_heads_fusion=cfg["H"])
+    m.load_state_dict({k[len("ttf."):]: v for k, v in params.items()}, strict=True)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(inp["notes"], inp["tau"], inp["t_hat"])  # no CPU fallback
 
 
 @pytest.mark.parametrize("name", golden_names())
@@ -193,4 +210,4 @@ def test_launcher_swaps_fusions_under_an_unmodified_script(tmp_path):
     assert r.returncode == 0, r.stderr[-2000:]
     assert os.path.join("imm-tsf_b200", "fusions", "FusionModel.py") in r.stdout
     assert "CTX 1024" in r.stdout and "ARGS ['--x', '1']" in r.stdout
-    assert "['TTF_RecAvg', 'TTF_T2V_XAttn'] ['MMF_GR_Add', 'MMF_XAttn_Add']" in r.stdout
+    assert "['TTF_RecAvg', 'TTF_T2V_XAttn', 'TTF_T2V_XAttn_old'] ['MMF_GR_Add', 'MMF_XAttn_Add']" in r.stdout

@@ -10,7 +10,8 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("ttf,mmf", [("TTF_RecAvg", "MMF_GR_Add"), ("TTF_T2V_XAttn", "MMF_XAttn_Add"),
-                                     ("TTF_T2V_XAttn", "MMF_GR_Add"), ("TTF_RecAvg", "MMF_XAttn_Add")])
+                                     ("TTF_T2V_XAttn", "MMF_GR_Add"), ("TTF_RecAvg", "MMF_XAttn_Add"),
+                                     ("TTF_T2V_XAttn_old", "MMF_GR_Add"), ("TTF_T2V_XAttn_old", "MMF_XAttn_Add")])
 def test_graph_replay_equals_eager_on_new_inputs(ttf, mmf):
     from immtsf import runtime
 
