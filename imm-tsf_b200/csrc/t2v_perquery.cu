@@ -33,10 +33,12 @@ __device__ __forceinline__ float pq_phi(int k, float dl, float wl, float bl, con
   return k == 0 ? fmaf(wl, dl, bl) : sinf(fmaf(__ldg(w_per + k - 1), dl, __ldg(b_per + k - 1)));
 }
 
-// smem: s_dl [TQ][NM] | s_p [TQ*H][NM]
+// smem: s_dl [TQ][NM] | s_p [TQ*H][NM].  H is a template parameter: with a run-time head count the guarded 8-way
+// unrolled head loops were 2/3 of the executed instructions (ncu source page, profiles/r1_ncu_t2vq_v1_summary.txt).
+template <int H>
 __global__ void __launch_bounds__(256) t2vq_fwd_kernel(const PQArgs a) {
   extern __shared__ __align__(16) float smem[];
-  const int H = a.H, d = a.d, dt = a.dt, NM = a.NM, TQ = a.TQ, T = a.T;
+  const int d = a.d, dt = a.dt, NM = a.NM, TQ = a.TQ, T = a.T;
   float* s_dl = smem;
   float* s_p = smem + (size_t)TQ * NM;
   const int b = blockIdx.y, t0 = blockIdx.x * TQ;
@@ -63,17 +65,17 @@ __global__ void __launch_bounds__(256) t2vq_fwd_kernel(const PQArgs a) {
   for (int i = w; i < tcnt * nn; i += nw) {
     const int tt = i / nn, n = i % nn;
     const float dl = s_dl[tt * NM + n];
-    float acc[PQ_MAXH];
+    float acc[H];
 #pragma unroll
-    for (int h = 0; h < PQ_MAXH; ++h) acc[h] = 0.f;
+    for (int h = 0; h < H; ++h) acc[h] = 0.f;
     for (int k = lane; k < dt; k += 32) {
       const float ph = pq_phi(k, dl, wl, bl, a.w_per, a.b_per);
 #pragma unroll
-      for (int h = 0; h < PQ_MAXH; ++h)
-        if (h < H) acc[h] = fmaf(__ldg(a.g + (size_t)h * dt + k), ph, acc[h]);
+      for (int h = 0; h < H; ++h)
+        acc[h] = fmaf(__ldg(a.g + (size_t)h * dt + k), ph, acc[h]);
     }
 #pragma unroll
-    for (int h = 0; h < PQ_MAXH; ++h) {
+    for (int h = 0; h < H; ++h) {
       if (h < H) {
         const float s = warp_sum(acc[h]);
         if (lane == 0) s_p[(tt * H + h) * NM + n] = s + a.a_sc[(size_t)(nb + n) * H + h];
@@ -128,25 +130,26 @@ __global__ void __launch_bounds__(256) t2vq_fwd_kernel(const PQArgs a) {
   // 4) Phi rows: thread per (query time, unit), all heads
   for (int i = threadIdx.x; i < tcnt * dt; i += blockDim.x) {
     const int tt = i / dt, k = i % dt;
-    float acc[PQ_MAXH];
+    float acc[H];
 #pragma unroll
-    for (int h = 0; h < PQ_MAXH; ++h) acc[h] = 0.f;
+    for (int h = 0; h < H; ++h) acc[h] = 0.f;
     for (int n = 0; n < nn; ++n) {
       const float ph = pq_phi(k, s_dl[tt * NM + n], wl, bl, a.w_per, a.b_per);
 #pragma unroll
-      for (int h = 0; h < PQ_MAXH; ++h)
-        if (h < H) acc[h] = fmaf(s_p[(size_t)(tt * H + h) * NM + n], ph, acc[h]);
+      for (int h = 0; h < H; ++h)
+        acc[h] = fmaf(s_p[(size_t)(tt * H + h) * NM + n], ph, acc[h]);
     }
 #pragma unroll
-    for (int h = 0; h < PQ_MAXH; ++h)
-      if (h < H) a.Phi[(row0 + tt * H + h) * dt + k] = acc[h];
+    for (int h = 0; h < H; ++h)
+      a.Phi[(row0 + tt * H + h) * dt + k] = acc[h];
   }
 }
 
 // smem: s_dl [TQ][NM] | s_pt [TQ*H][NM] | s_ds [TQ*H][NM] | s_da [H][NM]
-__global__ void __launch_bounds__(256) t2vq_bwd_kernel(const PQArgs a) {
+template <int H>
+__global__ void __launch_bounds__(512) t2vq_bwd_kernel(const PQArgs a) {
   extern __shared__ __align__(16) float smem[];
-  const int H = a.H, d = a.d, dt = a.dt, NM = a.NM, TQ = a.TQ, T = a.T;
+  const int d = a.d, dt = a.dt, NM = a.NM, TQ = a.TQ, T = a.T;
   float* s_dl = smem;
   float* s_pt = s_dl + (size_t)TQ * NM;
   float* s_ds = s_pt + (size_t)TQ * H * NM;
@@ -176,24 +179,24 @@ __global__ void __launch_bounds__(256) t2vq_bwd_kernel(const PQArgs a) {
     for (int i = w; i < tcnt * nn; i += nw) {
       const int tt = i / nn, n = i % nn;
       const float dl = s_dl[tt * NM + n];
-      float acc[PQ_MAXH];
+      float acc[H];
 #pragma unroll
-      for (int h = 0; h < PQ_MAXH; ++h) acc[h] = 0.f;
+      for (int h = 0; h < H; ++h) acc[h] = 0.f;
       const float4* ar = reinterpret_cast<const float4*>(a.A + (size_t)(nb + n) * a.lda);
       for (int c4 = lane; c4 < d4; c4 += 32) {
         const float4 av = __ldg(ar + c4);
 #pragma unroll
-        for (int h = 0; h < PQ_MAXH; ++h)
-          if (h < H) acc[h] += f4_dot(av, __ldg(reinterpret_cast<const float4*>(a.dZ + (row0 + tt * H + h) * d) + c4));
+        for (int h = 0; h < H; ++h)
+          acc[h] += f4_dot(av, __ldg(reinterpret_cast<const float4*>(a.dZ + (row0 + tt * H + h) * d) + c4));
       }
       for (int k = lane; k < dt; k += 32) {
         const float ph = pq_phi(k, dl, wl, bl, a.w_per, a.b_per);
 #pragma unroll
-        for (int h = 0; h < PQ_MAXH; ++h)
-          if (h < H) acc[h] = fmaf(__ldg(a.dPhi + (row0 + tt * H + h) * dt + k), ph, acc[h]);
+        for (int h = 0; h < H; ++h)
+          acc[h] = fmaf(__ldg(a.dPhi + (row0 + tt * H + h) * dt + k), ph, acc[h]);
       }
 #pragma unroll
-      for (int h = 0; h < PQ_MAXH; ++h) {
+      for (int h = 0; h < H; ++h) {
         if (h < H) {
           const float s = warp_sum(acc[h]);
           if (lane == 0) s_ds[(size_t)(tt * H + h) * NM + n] = s + a.dsp[row0 + tt * H + h];
@@ -227,43 +230,43 @@ __global__ void __launch_bounds__(256) t2vq_bwd_kernel(const PQArgs a) {
       for (int tt = 0; tt < tcnt; ++tt) acc += s_ds[(size_t)(tt * H + h) * NM + n];
       s_da[h * NM + n] = acc;
     }
-    // c) dA[n] (+)= sum_r P~[r,n] dZ[r]: thread per float4 column, 8 notes at a time
-    for (int col4 = threadIdx.x; col4 < d4; col4 += blockDim.x) {
+    // c) dA[n] (+)= sum_r P~[r,n] dZ[r]: one work item per (float4 column, 4 notes)
+    const int nch = (nn + 3) >> 2;
+    for (int it = threadIdx.x; it < d4 * nch; it += blockDim.x) {
+      const int col4 = it % d4, n0 = (it / d4) * 4;
       const float4* gz = reinterpret_cast<const float4*>(a.dZ + row0 * d) + col4;
-      for (int n0 = 0; n0 < nn; n0 += 8) {
-        float4 acc[8];
+      float4 acc[4];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) acc[u] = f4_zero();
-        for (int r = 0; r < rows; ++r) {
-          const float4 go = __ldg(gz + (size_t)r * d4);
-          const float* pr = s_pt + (size_t)r * NM + n0;
+      for (int u = 0; u < 4; ++u) acc[u] = f4_zero();
+      for (int r = 0; r < rows; ++r) {
+        const float4 go = __ldg(gz + (size_t)r * d4);
+        const float* pr = s_pt + (size_t)r * NM + n0;
 #pragma unroll
-          for (int u = 0; u < 8; ++u)
-            if (n0 + u < nn) f4_fma(acc[u], pr[u], go);
-        }
+        for (int u = 0; u < 4; ++u)
+          if (n0 + u < nn) f4_fma(acc[u], pr[u], go);
+      }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          if (n0 + u < nn) {
-            float4* dst = reinterpret_cast<float4*>(a.dA + (size_t)(nb + n0 + u) * a.lddA) + col4;
-            if (t0 == 0) *dst = acc[u];
-            else { float4 o = *dst; f4_add(o, acc[u]); *dst = o; }
-          }
+      for (int u = 0; u < 4; ++u) {
+        if (n0 + u < nn) {
+          float4* dst = reinterpret_cast<float4*>(a.dA + (size_t)(nb + n0 + u) * a.lddA) + col4;
+          if (t0 == 0) *dst = acc[u];
+          else { float4 o = *dst; f4_add(o, acc[u]); *dst = o; }
         }
       }
     }
     // d) Time2Vec parameter partials and dg: thread per unit k; every partial of sample b is owned by one thread
     for (int k = threadIdx.x; k < dt; k += blockDim.x) {
       const float wk = k == 0 ? wl : __ldg(a.w_per + k - 1), bk = k == 0 ? bl : __ldg(a.b_per + k - 1);
-      float sw = 0.f, sb = 0.f, sg[PQ_MAXH], gk[PQ_MAXH];
+      float sw = 0.f, sb = 0.f, sg[H], gk[H];
 #pragma unroll
-      for (int h = 0; h < PQ_MAXH; ++h) {
+      for (int h = 0; h < H; ++h) {
         sg[h] = 0.f;
-        gk[h] = h < H ? __ldg(a.g + (size_t)h * dt + k) : 0.f;
+        gk[h] = __ldg(a.g + (size_t)h * dt + k);
       }
       for (int tt = 0; tt < tcnt; ++tt) {
-        float dph[PQ_MAXH];
+        float dph[H];
 #pragma unroll
-        for (int h = 0; h < PQ_MAXH; ++h) dph[h] = h < H ? __ldg(a.dPhi + (row0 + tt * H + h) * dt + k) : 0.f;
+        for (int h = 0; h < H; ++h) dph[h] = __ldg(a.dPhi + (row0 + tt * H + h) * dt + k);
         for (int n = 0; n < nn; ++n) {
           const float dl = s_dl[tt * NM + n];
           const float arg = fmaf(wk, dl, bk);
@@ -271,7 +274,7 @@ __global__ void __launch_bounds__(256) t2vq_bwd_kernel(const PQArgs a) {
           if (k != 0) sincosf(arg, &ph, &cs);
           float dphi = 0.f;
 #pragma unroll
-          for (int h = 0; h < PQ_MAXH; ++h) {
+          for (int h = 0; h < H; ++h) {
             if (h < H) {
               const float ds = s_ds[(size_t)(tt * H + h) * NM + n];
               dphi = fmaf(s_pt[(size_t)(tt * H + h) * NM + n], dph[h], dphi);
@@ -288,14 +291,14 @@ __global__ void __launch_bounds__(256) t2vq_bwd_kernel(const PQArgs a) {
         part[k] = sw;
         part[dt + k] = sb;
 #pragma unroll
-        for (int h = 0; h < PQ_MAXH; ++h)
-          if (h < H) part[(size_t)(2 + h) * dt + k] = sg[h];
+        for (int h = 0; h < H; ++h)
+          part[(size_t)(2 + h) * dt + k] = sg[h];
       } else {
         part[k] += sw;
         part[dt + k] += sb;
 #pragma unroll
-        for (int h = 0; h < PQ_MAXH; ++h)
-          if (h < H) part[(size_t)(2 + h) * dt + k] += sg[h];
+        for (int h = 0; h < H; ++h)
+          part[(size_t)(2 + h) * dt + k] += sg[h];
       }
     }
     __syncthreads();
@@ -304,6 +307,25 @@ __global__ void __launch_bounds__(256) t2vq_bwd_kernel(const PQArgs a) {
     const int h = i / nn, n = i % nn;
     a.da[(size_t)(nb + n) * H + h] = s_da[h * NM + n];
   }
+}
+
+template <int H>
+static void pq_launch_fwd(const PQArgs& a, size_t smem, cudaStream_t st) {
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    cudaFuncSetAttribute(t2vq_fwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    smem_set = smem;
+  }
+  t2vq_fwd_kernel<H><<<dim3(ceil_div(a.T, a.TQ), a.B), 256, smem, st>>>(a);
+}
+template <int H>
+static void pq_launch_bwd(const PQArgs& a, size_t smem, cudaStream_t st) {
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    cudaFuncSetAttribute(t2vq_bwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    smem_set = smem;
+  }
+  t2vq_bwd_kernel<H><<<a.B, 512, smem, st>>>(a);
 }
 
 static int pq_common(PQArgs& a, const char* who, const float* A, int lda, const float* g, const float* tau_flat,
@@ -342,12 +364,16 @@ extern "C" int immtsf_t2vq_attn_fwd(const float* A, int lda, const float* a_sc, 
   const size_t smem = (size_t)TQ * (1 + H) * plane;
   if (smem > 200 * 1024) { immtsf_set_error("t2vq_attn_fwd: H*N_max=%d too large for shared memory", H * N_max); return IMMTSF_ERR_UNSUPPORTED; }
   a.TQ = TQ;
-  static size_t smem_set = 0;
-  if (smem > 48 * 1024 && smem > smem_set) {
-    cudaFuncSetAttribute(t2vq_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    smem_set = smem;
+  switch (H) {
+    case 1: pq_launch_fwd<1>(a, smem, (cudaStream_t)stream); break;
+    case 2: pq_launch_fwd<2>(a, smem, (cudaStream_t)stream); break;
+    case 3: pq_launch_fwd<3>(a, smem, (cudaStream_t)stream); break;
+    case 4: pq_launch_fwd<4>(a, smem, (cudaStream_t)stream); break;
+    case 5: pq_launch_fwd<5>(a, smem, (cudaStream_t)stream); break;
+    case 6: pq_launch_fwd<6>(a, smem, (cudaStream_t)stream); break;
+    case 7: pq_launch_fwd<7>(a, smem, (cudaStream_t)stream); break;
+    default: pq_launch_fwd<8>(a, smem, (cudaStream_t)stream); break;
   }
-  t2vq_fwd_kernel<<<dim3(ceil_div(T, TQ), B), 256, smem, (cudaStream_t)stream>>>(a);
   IMMTSF_CHECK_LAUNCH("t2vq_attn_fwd");
   return IMMTSF_OK;
 }
@@ -372,12 +398,16 @@ extern "C" int immtsf_t2vq_attn_bwd(const float* dZ, const float* dPhi, const fl
   const size_t smem = ((size_t)TQ * (1 + 2 * H) + H) * plane;
   if (smem > 200 * 1024) { immtsf_set_error("t2vq_attn_bwd: H*N_max=%d too large for shared memory", H * N_max); return IMMTSF_ERR_UNSUPPORTED; }
   a.TQ = TQ;
-  static size_t smem_set = 0;
-  if (smem > 48 * 1024 && smem > smem_set) {
-    cudaFuncSetAttribute(t2vq_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    smem_set = smem;
+  switch (H) {
+    case 1: pq_launch_bwd<1>(a, smem, (cudaStream_t)stream); break;
+    case 2: pq_launch_bwd<2>(a, smem, (cudaStream_t)stream); break;
+    case 3: pq_launch_bwd<3>(a, smem, (cudaStream_t)stream); break;
+    case 4: pq_launch_bwd<4>(a, smem, (cudaStream_t)stream); break;
+    case 5: pq_launch_bwd<5>(a, smem, (cudaStream_t)stream); break;
+    case 6: pq_launch_bwd<6>(a, smem, (cudaStream_t)stream); break;
+    case 7: pq_launch_bwd<7>(a, smem, (cudaStream_t)stream); break;
+    default: pq_launch_bwd<8>(a, smem, (cudaStream_t)stream); break;
   }
-  t2vq_bwd_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(a);
   IMMTSF_CHECK_LAUNCH("t2vq_attn_bwd");
   return IMMTSF_OK;
 }

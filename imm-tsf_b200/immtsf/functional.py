@@ -251,6 +251,12 @@ class T2VPerQueryFn(torch.autograd.Function):
         lo = step.lo
         W_a, W_phi = W_kv[:, :d], W_kv[:, d:]
         W_q, W_k, W_v, b_v = in_w[:d], in_w[d:2 * d], in_w[2 * d:], in_b[2 * d:]
+        # tcgen05 lo operands of every weight matrix (and of the views used as operands on their own) in one launch
+        heads = [slice(2 * d + h * hd, 2 * d + (h + 1) * hd) for h in range(H)] if H > 1 else []
+        ws = ([(W_in, [])] if W_in is not None else []) + [
+            (W_kv, [(slice(None), slice(0, d)), (slice(None), slice(d, None))]),
+            (in_w, [slice(d, 2 * d), slice(2 * d, None)] + heads), (out_w, []), (W_po, [])]
+        ops.weight_los(lo, ws)
         Vp = ops.linear_fwd(r.emb_flat, W_in, b_in, ragged=r.m_dev, lo=lo) if W_in is not None else r.emb_flat
         A = ops.linear_fwd(Vp, W_a, b_kv, ragged=r.m_dev, lo=lo)  # the note part of KV_proj (:129), once per note
         # query side: u_h = W_k[h]^T q_h (block-diagonal q), g_h = W_phi^T u_h

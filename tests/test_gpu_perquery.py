@@ -206,6 +206,6 @@ def test_properties_cfg2_shape():
         E3, _ = fm.ttf(notes.cuda(), tau.cuda(), t_hat[0].cuda())
         E4, _ = fm.ttf(notes.cuda(), tau.cuda(), t_hat[0][None].repeat(B, 1).cuda())
     G.assert_close("permutation", E1.cpu(), E0.cpu(), 2e-6)
-    assert torch.equal(E2, E0)
+    G.assert_close("padding width", E2.cpu(), E0.cpu(), 2e-6)  # (M_alloc changes the GEMM tiling of the ragged rows)
     assert torch.equal(E3, E4)
     assert (E0[:, 0] - E0[:, -1]).abs().max().item() > 1e-3 * E0.abs().max().item()
