@@ -70,6 +70,10 @@ SIGNATURES = {
     "immtsf_masked_mse_partial": [P, P, P, L, I, I, P, P, P, P, SZ, P],
     "immtsf_masked_mse_finalize": [P, P, I, P, P, P],
     "immtsf_masked_mse_bwd": [P, P, P, L, I, P, P, P, P],
+    "immtsf_window_count": [P, P, P, P, P, I, P, P],
+    "immtsf_exclusive_scan_i32": [P, I, P, P, P],
+    "immtsf_window_fill": [P, P, P, P, P, I, P, P, P, P],
+    "immtsf_batch_gather": [P, I, I, P, P, P, P, P, I, I, P, I, P, P],
     "immtsf_axpby": [P, F, P, I, SZ, P],
     "immtsf_group_sum_rows": [P, I, I, I, I, P, P],
 }

@@ -325,6 +325,26 @@ int immtsf_masked_mse_finalize(const float* err, const float* cnt, int C, float*
 int immtsf_masked_mse_bwd(const float* pred, const float* truth, const float* mask, long rows, int C,
                           const float* scale, const float* gloss, float* dpred, void* stream);
 
+/* ---- next to the path: the text-embedding store.  The reference keeps a Python list of (rel_time,
+ * embedding row) per record (lib/parse_datasets.py:132-147), filters it per chunk window with a list comprehension
+ * (:204-209) and pads / stacks the selected rows per batch (multimodal_collate :786-819).  Here every embedding row of every
+ * record is resident once: emb_all [sumN, d_m] (ld), rel_all [sumN], entity_offsets [E+1].
+ * window_count: counts[i] = #{j in record ent[i] : st[i] <= (double)rel_all[j] < hist_end[i]}   (one warp per chunk)
+ * exclusive_scan_i32: offsets[0] = 0, offsets[i+1] = counts[0] + ... + counts[i]; *overflow_flag = 1 if a sum exceeds int32
+ * window_fill: chunk_rows[chunk_offsets[i] + k] = row of the k-th selected note of chunk i IN FILE ORDER (the order of the
+ *   reference's comprehension), chunk_tau[...] = (float)((double)rel - st[i])
+ * batch_gather: sample b of a batch is chunk chunk_ids[b]; its selected rows are copied to emb_flat[offsets[b] + k] and
+ *   their tau to tau_flat (offsets [B+1]: exclusive scan of the chunk sizes, made by the caller); N_max >= every size. */
+int immtsf_window_count(const float* rel_all, const int32_t* entity_offsets, const int32_t* ent, const double* st,
+                        const double* hist_end, int n, int32_t* counts, void* stream);
+int immtsf_exclusive_scan_i32(const int32_t* counts, int n, int32_t* offsets, int32_t* overflow_flag, void* stream);
+int immtsf_window_fill(const float* rel_all, const int32_t* entity_offsets, const int32_t* ent, const double* st,
+                       const double* hist_end, int n, const int32_t* chunk_offsets, int32_t* chunk_rows,
+                       float* chunk_tau, void* stream);
+int immtsf_batch_gather(const float* emb_all, int ld, int d_m, const int32_t* chunk_offsets, const int32_t* chunk_rows,
+                        const float* chunk_tau, const int32_t* chunk_ids, const int32_t* offsets, int B, int N_max,
+                        float* emb_flat, int ld_out, float* tau_flat, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

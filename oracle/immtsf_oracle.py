@@ -510,3 +510,52 @@ def ttf_t2v_xattn_perquery(
     E_drop = apply_dropout(E_resid, p, masks.get(prefix + "dropout"))  # :156
     E_txt = linear(E_drop, P[prefix + "proj_out.weight"], P[prefix + "proj_out.bias"])  # :159
     return E_txt, M_txt
+
+
+# ------------------------------------------------------------------ text store / chunk windows
+def chunk_windows(tt: Tensor, mask: Tensor, history: float, pred_window: float, stride: float):
+    """lib/parse_datasets.py:176-227 restated for ONE record, numeric side only: the window starts `st` for which the
+    reference forms a chunk BEFORE looking at the texts (>= 2 observations in [st, st+total), at least one observed
+    value in the history part and one in the prediction part).  Python floats throughout, as in the reference."""
+    total = history + pred_window
+    t_max = tt.max().item()
+    st = tt.min().item()
+    out = []
+    while st + total <= t_max:  # :183
+        idx = ((tt >= st) & (tt < st + total)).nonzero(as_tuple=False).squeeze(1)  # :184-186
+        if idx.numel() >= 2:  # :187
+            sub_tt = tt[idx] - st
+            sub_mask = mask[idx]
+            hist_mask = sub_mask[sub_tt < history]  # :197
+            pred_mask = sub_mask[sub_tt >= history]  # :198
+            if hist_mask.sum() == 0 or pred_mask.sum() == 0:  # :201-203
+                st += stride
+                continue
+            out.append(st)
+        st += stride  # :227
+    return out
+
+
+def select_window_notes(record_texts, st: float, history: float):
+    """lib/parse_datasets.py:203-209: notes of the history window only, in the order of the record's list (= file
+    order), times made relative to the window start.  record_texts: list of (t, payload)."""
+    hist_end = st + history
+    return [(t - st, payload) for (t, payload) in record_texts if st <= t < hist_end]
+
+
+def collate_text(raws):
+    """The text part of multimodal_collate, lib/parse_datasets.py:781-819: raws[b] = list of (t, embedding row).
+    Returns tau [B, N_max] and notes_embeddings [B, N_max, d] (zero tail padding)."""
+    from torch.nn.utils.rnn import pad_sequence
+
+    time_seqs = [torch.tensor([t for (t, _) in seq], dtype=torch.float32) for seq in raws]  # :786-790
+    tau = pad_sequence(time_seqs, batch_first=True, padding_value=0.0)  # :792
+    d_txt = None
+    for seq in raws:  # :802-806
+        if seq:
+            d_txt = seq[0][1].size(-1)
+            break
+    if d_txt is None:
+        return tau, torch.zeros((len(raws), 0, 0))  # :809
+    emb_seqs = [torch.stack([e for (_, e) in seq], dim=0) if seq else torch.zeros((0, d_txt)) for seq in raws]  # :811-816
+    return tau, pad_sequence(emb_seqs, batch_first=True, padding_value=0.0)  # :817-819
