@@ -47,7 +47,8 @@ SIGNATURES = {
     "immtsf_segattn_fwd": [P, P, P, I, I, I, I, I, I, U32, U64, P, P, P],
     "immtsf_segattn_bwd": [P, P, P, P, P, I, I, I, I, I, I, U32, U64, P, P, P],
     "immtsf_t2vq_attn_fwd": [P, I, P, P, P, P, P, I, P, P, P, P, I, I, I, I, I, I, I, U32, U64, P, P, P, P, P],
-    "immtsf_t2vq_attn_bwd": [P, P, P, P, I, P, P, P, P, P, I, P, P, P, P, I, I, I, I, I, I, I, U32, U64, P, I, P, P, P],
+    "immtsf_t2vq_bwd_tiles": [I, I, I],
+    "immtsf_t2vq_attn_bwd": [P, P, P, P, I, P, P, P, P, P, I, P, P, P, P, I, I, I, I, I, I, I, U32, U64, P, I, P, P, P, SZ, P],
     "immtsf_ln_fwd": [P, I, P, P, P, I, P, P, I, I, F, U32, U64, U32, P, P, P, P],
     "immtsf_ln_bwd": [P, P, I, P, P, P, I, P, P, P, I, I, U32, U64, U32, P, P, P, P, P],
     "immtsf_gru_scan_fwd": [P, P, P, I, I, I, P, P, P, P],
@@ -106,6 +107,8 @@ def load():
     lib.immtsf_launch_count.restype = C.c_ulonglong
     lib.immtsf_gemm_workspace_bytes.argtypes = [I, I, I, I, I]
     lib.immtsf_gemm_workspace_bytes.restype = SZ
+    lib.immtsf_t2vq_bwd_workspace_bytes.argtypes = [I, I, I]
+    lib.immtsf_t2vq_bwd_workspace_bytes.restype = SZ
     lib.immtsf_masked_mse_workspace_bytes.argtypes = [I]
     lib.immtsf_masked_mse_workspace_bytes.restype = SZ
     lib.immtsf_gemm_batched_workspace_bytes.argtypes = [I, I, I, I, I, I, L, L, I, L, L, I, I]

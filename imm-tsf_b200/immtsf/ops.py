@@ -490,16 +490,20 @@ def t2vq_attn_fwd(A, a_sc, g, r: RaggedNotes, t_hat, t2v_params, T, H, d, d_tau,
 
 
 def t2vq_attn_bwd(dZ, dPhi, dsp, A, g, probs, r: RaggedNotes, t_hat, t2v_params, T, H, d, d_tau, thr, seed):
-    """Returns dA [M_alloc, d] (pooling part), da [M_alloc, H] and the per-sample partials [B, 2+H, d_tau]."""
+    """Returns dA [M_alloc, d] (pooling part), da [M_alloc, H] and the per-(sample, query tile) partials [B*tiles, (2+H)*d_tau]."""
     dev = A.device
     dA = torch.empty(r.M_alloc, d, dtype=torch.float32, device=dev)
     da = torch.empty(r.M_alloc, H, dtype=torch.float32, device=dev)
-    dpart = torch.empty(max(r.B, 1), (2 + H) * d_tau, dtype=torch.float32, device=dev)
+    lib = _lib.load()
+    tiles = lib.immtsf_t2vq_bwd_tiles(T, H, max(r.N, 1))
+    dpart = torch.empty(max(r.B, 1) * tiles, (2 + H) * d_tau, dtype=torch.float32, device=dev)
+    ws_bytes = lib.immtsf_t2vq_bwd_workspace_bytes(T, H, r.M_alloc)
+    ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dev)  # P~ and dS between the two launches
     w_lin, b_lin, w_per, b_per = t2v_params
     bstride = 0 if t_hat.dim() == 1 else t_hat.stride(0)
     _lib.call("immtsf_t2vq_attn_bwd", _p(dZ), _p(dPhi), _p(dsp), _p(A), A.stride(0), _p(g), _p(probs), _p(r.tau_flat), _p(r.offsets),
               _p(t_hat), bstride, _p(w_lin), _p(b_lin), _p(w_per), _p(b_per), r.B, T, H, d, d_tau, max(r.N, 1), r.M_alloc, thr, seed,
-              _p(dA), dA.stride(0), _p(da), _p(dpart), _stream())
+              _p(dA), dA.stride(0), _p(da), _p(dpart), _p(ws), ws_bytes, _stream())
     zero_pad_rows(dA, d, r.m_dev, r.M_alloc)
     zero_pad_rows(da, H, r.m_dev, r.M_alloc)
     return dA, da, dpart

@@ -195,14 +195,20 @@ int immtsf_t2vq_attn_fwd(const float* A, int lda, const float* a_sc, const float
                          const float* b_lin, const float* w_per, const float* b_per, int B, int T, int H, int d,
                          int d_tau, int N_max, int M_alloc, uint32_t drop_thr, uint64_t seed, float* Z, float* Phi,
                          float* sp, float* probs, void* stream);
-/* Backward: dA [M_alloc, d] (rows of the pooling only; the caller adds da U), da [M_alloc, H], and per-sample
- * partials dpart [B, 2+H, d_tau]: row 0 = d w (unit 0: time2vec.linear, units k >= 1: periodic k-1), row 1 = d b,
- * rows 2.. = dg[h]; the caller sums them over samples (immtsf_colsum).  One CTA owns a sample: no atomics. */
+/* Backward, two launches: (1) per (query tile, sample) CTA: dP~, dropout + softmax backward, the Time2Vec parameter
+ * partials of the tile; (2) per (column block, sample) CTA: dA [M_alloc, d] = sum over the sample's (t, h) rows of P~ dZ
+ * (the pooling part only; the caller adds da U) and da [M_alloc, H] = sum_t dS.  dpart [B * tiles, 2+H, d_tau]
+ * (tiles = immtsf_t2vq_bwd_tiles): row 0 = d w (unit 0: time2vec.linear, units k >= 1: periodic k-1), row 1 = d b,
+ * rows 2.. = dg[h]; the caller sums the rows (immtsf_colsum).  workspace: >= immtsf_t2vq_bwd_workspace_bytes (P~ and dS of
+ * every (h, t, note) between the two launches).  Every output element is owned by one thread: no atomics. */
+int immtsf_t2vq_bwd_tiles(int T, int H, int N_max);
+size_t immtsf_t2vq_bwd_workspace_bytes(int T, int H, int M_alloc);
 int immtsf_t2vq_attn_bwd(const float* dZ, const float* dPhi, const float* dsp, const float* A, int lda, const float* g,
                          const float* probs, const float* tau_flat, const int32_t* offsets, const float* t_hat,
                          int t_hat_bstride, const float* w_lin, const float* b_lin, const float* w_per,
                          const float* b_per, int B, int T, int H, int d, int d_tau, int N_max, int M_alloc,
-                         uint32_t drop_thr, uint64_t seed, float* dA, int lddA, float* da, float* dpart, void* stream);
+                         uint32_t drop_thr, uint64_t seed, float* dA, int lddA, float* da, float* dpart,
+                         void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- residual + LayerNorm + dropout over d (TTF_T2V_XAttn.py:171-179) ---
  * z = (valid[row / rows_per_sample] ? x + xbias : 0) + res;  y = dropout(LN(z))
