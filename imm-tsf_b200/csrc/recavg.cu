@@ -22,6 +22,7 @@
 // dS_t . (sum_n c_nt V'_n), a second pooled vector accumulated in the same
 // pass.  d(den) uses the closed form sum_j dE_raw_j E_raw_j = s2*eps*rstd^2
 // (LayerNorm is scale invariant up to eps).
+#include <stdlib.h>
 #include "rowwarp.cuh"
 #include "../../include/immtsf.h"
 
@@ -464,6 +465,184 @@ __global__ void __launch_bounds__(256) recavg_pool_fwd_w_kernel(const PoolArgs a
   }
 }
 
+// ------------------------------------------------------------------ forward with TMA-staged segments
+// Same warp-per-query-time arithmetic as recavg_pool_fwd_w_kernel, but the sample's V' rows reach the SM ONCE, as a bulk
+// asynchronous copy (cp.async.bulk, completion on an mbarrier) into shared memory, instead of one dependent L1/L2 round trip
+// per note inside the pooling loop (ncu on the register version: long-scoreboard stalls 11.6 per issue at 41 % issue
+// utilisation -- latency-bound on exactly those loads).  The recency weights are computed while the copy is in flight.
+// Bank conflicts: a lane owns float8 chunks (one Philox call per chunk), i.e. 32-byte strides between lanes, which would be
+// 2-way conflicts for LDS.128.  Lanes 4-7 of every quarter warp therefore read the SECOND float4 of their chunk first
+// (p = 1) and keep their halves swapped in registers until the epilogue; every LDS.128 wavefront then covers 8 distinct
+// 16-byte bank groups.
+__device__ __forceinline__ uint32_t rs_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void rs_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void rs_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void rs_mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "RS_WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra RS_WAIT_DONE;\n\t"
+      "bra RS_WAIT_LOOP;\n\t"
+      "RS_WAIT_DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void rs_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void f4_fma_s(float4& acc, float s, const float4& v) {
+  acc.x = fmaf(s, v.x, acc.x); acc.y = fmaf(s, v.y, acc.y); acc.z = fmaf(s, v.z, acc.z); acc.w = fmaf(s, v.w, acc.w);
+}
+
+// smem: s_v [RS][d] (RS <= 32 rows per stage).  grid (ceil(T / (8*TPW)), B), 256 threads.
+template <int NC, int TPW>
+__global__ void __launch_bounds__(256) recavg_pool_fwd_s_kernel(const PoolArgs a, int RS) {
+  extern __shared__ __align__(128) float s_v[];
+  __shared__ __align__(8) unsigned long long s_bar;
+  const int b = blockIdx.y, lane = threadIdx.x & 31;
+  const int tb = blockIdx.x * (8 * TPW) + (threadIdx.x >> 5);
+  const bool active = tb < a.T;  // inactive warps still take part in the barriers
+  const int d = a.d, d8 = d >> 3;
+  const int nb = a.offsets[b], ne = a.offsets[b + 1];
+  const uint32_t bar = rs_smem_u32(&s_bar), sv = rs_smem_u32(s_v);
+  if (threadIdx.x == 0) rs_mbar_init(bar, 1);
+  __syncthreads();
+  const float inv_sigma = 1.f / expf(__ldg(a.log_sigma));
+  const int p = (lane >> 2) & 1;
+  float th[TPW], wsum_l[TPW];
+  float4 accA[TPW][NC], accB[TPW][NC];
+#pragma unroll
+  for (int q = 0; q < TPW; ++q) {
+    th[q] = tb + 8 * q < a.T ? a.t_hat[(size_t)b * a.t_bstride + tb + 8 * q] : 0.f;
+    wsum_l[q] = 0.f;
+#pragma unroll
+    for (int i = 0; i < NC; ++i) { accA[q][i] = f4_zero(); accB[q][i] = f4_zero(); }
+  }
+  uint32_t phase = 0;
+  for (int n0 = nb; n0 < ne; n0 += RS) {
+    const int cnt = min(RS, ne - n0);
+    if (n0 != nb) __syncthreads();  // every warp is done reading the previous stage
+    if (threadIdx.x == 0) {
+      const uint32_t row_bytes = (uint32_t)d * 4u;
+      rs_mbar_expect_tx(bar, (uint32_t)cnt * row_bytes);
+      if (a.ldv == d) {
+        rs_bulk_g2s(sv, a.Vp + (size_t)n0 * a.ldv, (uint32_t)cnt * row_bytes, bar);
+      } else {
+        for (int j = 0; j < cnt; ++j) rs_bulk_g2s(sv + (uint32_t)j * row_bytes, a.Vp + (size_t)(n0 + j) * a.ldv, row_bytes, bar);
+      }
+    }
+    // recency weights of the stage's notes (lane j <-> note n0 + j) while the copy is in flight
+    float wl[TPW];
+    const float tn = lane < cnt ? __ldg(a.tau + n0 + lane) : 0.f;
+#pragma unroll
+    for (int q = 0; q < TPW; ++q) {
+      const float r = fmaxf(th[q] - tn, 0.f) * inv_sigma;
+      wl[q] = lane < cnt ? expf(-(r * r)) : 0.f;
+      wsum_l[q] += wl[q];
+    }
+    rs_mbar_wait(bar, phase);
+    phase ^= 1u;
+    if (active) {
+      for (int j = 0; j < cnt; ++j) {
+        const float4* row = reinterpret_cast<const float4*>(s_v + (size_t)j * d);
+        float4 vA[NC], vB[NC];
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+          const int k = lane + 32 * i;
+          if (k < d8) { vA[i] = row[2 * k + p]; vB[i] = row[2 * k + 1 - p]; }
+          else { vA[i] = f4_zero(); vB[i] = f4_zero(); }
+        }
+#pragma unroll
+        for (int q = 0; q < TPW; ++q) {
+          const float w0 = __shfl_sync(0xffffffffu, wl[q], j);
+#pragma unroll
+          for (int i = 0; i < NC; ++i) { f4_fma_s(accA[q][i], w0, vA[i]); f4_fma_s(accB[q][i], w0, vB[i]); }
+        }
+      }
+    }
+  }
+  if (!active) return;
+  const float inv_keep = inv_keep_from_thr(a.thr);
+  const uint64_t seed = resolve_seed(a.seed);
+  const float inv_d = 1.f / (float)a.d;
+#pragma unroll
+  for (int q = 0; q < TPW; ++q) {
+    const int t = tb + 8 * q;
+    if (t >= a.T) break;
+    const float wsum = warp_sum(wsum_l[q]);
+    const float inv_den = 1.f / fmaxf(wsum, 1e-6f);  // E_raw = E_wsum / clamp_min(denom, 1e-6)
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {  // chunks beyond d are exactly 0
+      float4& A = accA[q][i];
+      float4& Bv = accB[q][i];
+      A.x *= inv_den; A.y *= inv_den; A.z *= inv_den; A.w *= inv_den;
+      Bv.x *= inv_den; Bv.y *= inv_den; Bv.z *= inv_den; Bv.w *= inv_den;
+      s += (A.x + A.y) + (A.z + A.w) + (Bv.x + Bv.y) + (Bv.z + Bv.w);
+    }
+    const float mu = warp_sum(s) * inv_d;
+    float qq = 0.f;
+#pragma unroll
+    for (int i = 0; i < NC; ++i)
+      if (lane + 32 * i < d8) {
+        const float4 A = accA[q][i], Bv = accB[q][i];
+        qq = fmaf(A.x - mu, A.x - mu, qq); qq = fmaf(A.y - mu, A.y - mu, qq); qq = fmaf(A.z - mu, A.z - mu, qq); qq = fmaf(A.w - mu, A.w - mu, qq);
+        qq = fmaf(Bv.x - mu, Bv.x - mu, qq); qq = fmaf(Bv.y - mu, Bv.y - mu, qq); qq = fmaf(Bv.z - mu, Bv.z - mu, qq); qq = fmaf(Bv.w - mu, Bv.w - mu, qq);
+      }
+    const float rs = 1.f / sqrtf(warp_sum(qq) * inv_d + a.eps);
+    const size_t rowi = (size_t)b * a.T + t;
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+      const int k = lane + 32 * i;
+      if (k < d8) {
+        float ks[8];
+        dropout_scale8(seed, IMMTSF_SITE_TTF_DROPOUT, rowi * d8 + k, a.thr, inv_keep, ks);
+        const int oA = 2 * k + p, oB = 2 * k + 1 - p;  // float4 index of each half within the row
+        const float4 gA = __ldg(reinterpret_cast<const float4*>(a.gamma) + oA), gB = __ldg(reinterpret_cast<const float4*>(a.gamma) + oB);
+        const float4 bA = __ldg(reinterpret_cast<const float4*>(a.beta) + oA), bB = __ldg(reinterpret_cast<const float4*>(a.beta) + oB);
+        const float4 A = accA[q][i], Bv = accB[q][i];
+        float4 kA, kB, yA, yB;
+        kA.x = p ? ks[4] : ks[0]; kA.y = p ? ks[5] : ks[1]; kA.z = p ? ks[6] : ks[2]; kA.w = p ? ks[7] : ks[3];
+        kB.x = p ? ks[0] : ks[4]; kB.y = p ? ks[1] : ks[5]; kB.z = p ? ks[2] : ks[6]; kB.w = p ? ks[3] : ks[7];
+        yA.x = ((A.x - mu) * rs * gA.x + bA.x) * kA.x; yA.y = ((A.y - mu) * rs * gA.y + bA.y) * kA.y;
+        yA.z = ((A.z - mu) * rs * gA.z + bA.z) * kA.z; yA.w = ((A.w - mu) * rs * gA.w + bA.w) * kA.w;
+        yB.x = ((Bv.x - mu) * rs * gB.x + bB.x) * kB.x; yB.y = ((Bv.y - mu) * rs * gB.y + bB.y) * kB.y;
+        yB.z = ((Bv.z - mu) * rs * gB.z + bB.z) * kB.z; yB.w = ((Bv.w - mu) * rs * gB.w + bB.w) * kB.w;
+        float4* eo = reinterpret_cast<float4*>(a.E_drop + rowi * a.d);
+        eo[oA] = yA;
+        eo[oB] = yB;
+        if (a.E_raw) {
+          float4* er = reinterpret_cast<float4*>(a.E_raw + rowi * a.d);
+          er[oA] = A;
+          er[oB] = Bv;
+        }
+      }
+    }
+    if (lane == 0) {
+      if (a.mean) a.mean[rowi] = mu;
+      if (a.rstd) a.rstd[rowi] = rs;
+      if (a.wsum) a.wsum[rowi] = wsum;
+    }
+  }
+}
+
+template <int NC, int TPW>
+static void launch_fwd_s(const PoolArgs& a, dim3 grid, int RS, size_t smem, cudaStream_t st) {
+  static size_t smem_set = 0;
+  if (smem + 1024 > 48 * 1024 && smem > smem_set) {  // (the kernel also has 128 B of static shared memory)
+    cudaFuncSetAttribute(recavg_pool_fwd_s_kernel<NC, TPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    smem_set = smem;
+  }
+  recavg_pool_fwd_s_kernel<NC, TPW><<<grid, 256, smem, st>>>(a, RS);
+}
+
 // Backward phase 1 (LayerNorm backward of the pooled rows -> dS, d(den)), one warp per (sample, query time) row.
 template <int NC>
 __global__ void __launch_bounds__(128) recavg_bwd_rows_w_kernel(const PoolArgs a) {
@@ -575,6 +754,25 @@ extern "C" int immtsf_recavg_pool_fwd(const float* Vp, int ldv, const float* tau
     // query times per warp: 3 when the row fits comfortably in registers (d <= 768) and T is long enough
     const int tpw = (nc <= 3 && T > 16) ? 3 : (T > 8 && nc <= 3 ? 2 : 1);
     dim3 gridw(ceil_div(T, 8 * tpw), B);
+    // default: the TMA-staged kernel (IMMTSF_RECAVG_TMA=0 keeps the register version for A/B runs)
+    static const int use_tma = []() { const char* e = getenv("IMMTSF_RECAVG_TMA"); return !(e && e[0] == '0'); }();
+    const int RS = N_max < 16 ? N_max : 16;
+    const size_t smem_s = (size_t)RS * d * sizeof(float);
+    if (use_tma && ((uintptr_t)Vp & 15) == 0 && (ldv & 3) == 0 && (d & 7) == 0) {
+#define FWD_S(NCV)                                                        \
+  do {                                                                    \
+    if (tpw == 3) launch_fwd_s<NCV, 3>(a, gridw, RS, smem_s, st);         \
+    else if (tpw == 2) launch_fwd_s<NCV, 2>(a, gridw, RS, smem_s, st);    \
+    else launch_fwd_s<NCV, 1>(a, gridw, RS, smem_s, st);                  \
+  } while (0)
+      if (nc == 1) FWD_S(1);
+      else if (nc == 2) FWD_S(2);
+      else if (nc == 3) FWD_S(3);
+      else launch_fwd_s<4, 1>(a, gridw, RS, smem_s, st);
+#undef FWD_S
+      IMMTSF_CHECK_LAUNCH("recavg_pool_fwd_s");
+      return IMMTSF_OK;
+    }
 #define FWD_W(NCV)                                                                    \
   do {                                                                                \
     if (tpw == 3) recavg_pool_fwd_w_kernel<NCV, 3><<<gridw, 256, 0, st>>>(a);         \
