@@ -34,6 +34,25 @@ void immtsf_count_launch();  // host-side counter of kernel launches (bench.py's
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// Grid size of a persistent (grid-stride) kernel: never more CTAs than can be resident at once -- a partial second wave
+// makes the launch take two full CTA lifetimes (recavg_bwd_rows_w<3>: 159 registers = 3 CTAs/SM resident, but 4 per SM
+// were launched: 1.33 waves in ncu).  The occupancy query is cached per kernel.
+static inline int resident_grid(const void* kernel, int threads, size_t smem, int want, int max_per_sm) {
+  static const void* keys[64];
+  static int vals[64];
+  static int n = 0;
+  int per_sm = 0;
+  for (int i = 0; i < n; ++i)
+    if (keys[i] == kernel) per_sm = vals[i];
+  if (per_sm == 0) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    if (n < 64) { keys[n] = kernel; vals[n] = per_sm; ++n; }
+  }
+  if (per_sm > max_per_sm) per_sm = max_per_sm;
+  const int cap = 148 * per_sm;
+  return want < cap ? want : cap;
+}
+
 // ---------------------------------------------------------------- reductions
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

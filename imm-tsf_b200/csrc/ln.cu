@@ -395,12 +395,13 @@ extern "C" int immtsf_ln_bwd(const float* dy, const float* x, int ldx, const flo
   const int nc = rowwarp_nc(d);
   if (nc > 0 && (res == nullptr || ((uintptr_t)res & 15) == 0) && (xbias == nullptr || ((uintptr_t)xbias & 15) == 0) &&
       ((uintptr_t)gamma & 15) == 0 && ((uintptr_t)dy & 15) == 0 && ((uintptr_t)dx & 15) == 0) {
-    int gridw = ceil_div(R, 4);
-    if (gridw > 148 * 4) gridw = 148 * 4;
-    if (nc == 1) ln_bwd_w_kernel<1><<<gridw, 128, 0, st>>>(a);
-    else if (nc == 2) ln_bwd_w_kernel<2><<<gridw, 128, 0, st>>>(a);
-    else if (nc == 3) ln_bwd_w_kernel<3><<<gridw, 128, 0, st>>>(a);
-    else ln_bwd_w_kernel<4><<<gridw, 128, 0, st>>>(a);
+    const int want = ceil_div(R, 4);
+#define LNB_W(NCV) ln_bwd_w_kernel<NCV><<<resident_grid((const void*)ln_bwd_w_kernel<NCV>, 128, 0, want, 4), 128, 0, st>>>(a)
+    if (nc == 1) LNB_W(1);
+    else if (nc == 2) LNB_W(2);
+    else if (nc == 3) LNB_W(3);
+    else LNB_W(4);
+#undef LNB_W
     IMMTSF_CHECK_LAUNCH("ln_bwd_w");
     return IMMTSF_OK;
   }

@@ -502,8 +502,8 @@ __device__ __forceinline__ void f4_fma_s(float4& acc, float s, const float4& v) 
 }
 
 // smem: s_v [RS][d] (RS <= 32 rows per stage).  grid (ceil(T / (8*TPW)), B), 256 threads.
-template <int NC, int TPW>
-__global__ void __launch_bounds__(256) recavg_pool_fwd_s_kernel(const PoolArgs a, int RS) {
+template <int NC, int TPW, int MINB, bool FULL>
+__global__ void __launch_bounds__(256, MINB) recavg_pool_fwd_s_kernel(const PoolArgs a, int RS) {
   extern __shared__ __align__(128) float s_v[];
   __shared__ __align__(8) unsigned long long s_bar;
   const int b = blockIdx.y, lane = threadIdx.x & 31;
@@ -556,7 +556,7 @@ __global__ void __launch_bounds__(256) recavg_pool_fwd_s_kernel(const PoolArgs a
 #pragma unroll
         for (int i = 0; i < NC; ++i) {
           const int k = lane + 32 * i;
-          if (k < d8) { vA[i] = row[2 * k + p]; vB[i] = row[2 * k + 1 - p]; }
+          if (FULL || k < d8) { vA[i] = row[2 * k + p]; vB[i] = row[2 * k + 1 - p]; }
           else { vA[i] = f4_zero(); vB[i] = f4_zero(); }
         }
 #pragma unroll
@@ -591,7 +591,7 @@ __global__ void __launch_bounds__(256) recavg_pool_fwd_s_kernel(const PoolArgs a
     float qq = 0.f;
 #pragma unroll
     for (int i = 0; i < NC; ++i)
-      if (lane + 32 * i < d8) {
+      if (FULL || lane + 32 * i < d8) {
         const float4 A = accA[q][i], Bv = accB[q][i];
         qq = fmaf(A.x - mu, A.x - mu, qq); qq = fmaf(A.y - mu, A.y - mu, qq); qq = fmaf(A.z - mu, A.z - mu, qq); qq = fmaf(A.w - mu, A.w - mu, qq);
         qq = fmaf(Bv.x - mu, Bv.x - mu, qq); qq = fmaf(Bv.y - mu, Bv.y - mu, qq); qq = fmaf(Bv.z - mu, Bv.z - mu, qq); qq = fmaf(Bv.w - mu, Bv.w - mu, qq);
@@ -601,7 +601,7 @@ __global__ void __launch_bounds__(256) recavg_pool_fwd_s_kernel(const PoolArgs a
 #pragma unroll
     for (int i = 0; i < NC; ++i) {
       const int k = lane + 32 * i;
-      if (k < d8) {
+      if (FULL || k < d8) {
         float ks[8];
         dropout_scale8(seed, IMMTSF_SITE_TTF_DROPOUT, rowi * d8 + k, a.thr, inv_keep, ks);
         const int oA = 2 * k + p, oB = 2 * k + 1 - p;  // float4 index of each half within the row
@@ -633,14 +633,23 @@ __global__ void __launch_bounds__(256) recavg_pool_fwd_s_kernel(const PoolArgs a
   }
 }
 
-template <int NC, int TPW>
-static void launch_fwd_s(const PoolArgs& a, dim3 grid, int RS, size_t smem, cudaStream_t st) {
+template <int NC, int TPW, int MINB, bool FULL>
+static void launch_fwd_s2(const PoolArgs& a, dim3 grid, int RS, size_t smem, cudaStream_t st) {
   static size_t smem_set = 0;
   if (smem + 1024 > 48 * 1024 && smem > smem_set) {  // (the kernel also has 128 B of static shared memory)
-    cudaFuncSetAttribute(recavg_pool_fwd_s_kernel<NC, TPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(recavg_pool_fwd_s_kernel<NC, TPW, MINB, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     smem_set = smem;
   }
-  recavg_pool_fwd_s_kernel<NC, TPW><<<grid, 256, smem, st>>>(a, RS);
+  recavg_pool_fwd_s_kernel<NC, TPW, MINB, FULL><<<grid, 256, smem, st>>>(a, RS);
+}
+// tpw: query times per warp.  3: capped at 128 registers, 2 CTAs per SM (MINB = 2); 2: capped at 80 registers, 3 CTAs per SM (MINB = 3).
+template <int NC>
+static void launch_fwd_s(const PoolArgs& a, int tpw, int T, int B, int RS, size_t smem, cudaStream_t st) {
+  const bool full = (a.d >> 3) == 32 * NC;
+  dim3 grid(ceil_div(T, 8 * tpw), B);
+  if (tpw == 3) { if (full) launch_fwd_s2<NC, 3, 2, true>(a, grid, RS, smem, st); else launch_fwd_s2<NC, 3, 2, false>(a, grid, RS, smem, st); }
+  else if (tpw == 2) { if (full) launch_fwd_s2<NC, 2, 3, true>(a, grid, RS, smem, st); else launch_fwd_s2<NC, 2, 3, false>(a, grid, RS, smem, st); }
+  else { if (full) launch_fwd_s2<NC, 1, 3, true>(a, grid, RS, smem, st); else launch_fwd_s2<NC, 1, 3, false>(a, grid, RS, smem, st); }
 }
 
 // Backward phase 1 (LayerNorm backward of the pooled rows -> dS, d(den)), one warp per (sample, query time) row.
@@ -759,17 +768,13 @@ extern "C" int immtsf_recavg_pool_fwd(const float* Vp, int ldv, const float* tau
     const int RS = N_max < 16 ? N_max : 16;
     const size_t smem_s = (size_t)RS * d * sizeof(float);
     if (use_tma && ((uintptr_t)Vp & 15) == 0 && (ldv & 3) == 0 && (d & 7) == 0) {
-#define FWD_S(NCV)                                                        \
-  do {                                                                    \
-    if (tpw == 3) launch_fwd_s<NCV, 3>(a, gridw, RS, smem_s, st);         \
-    else if (tpw == 2) launch_fwd_s<NCV, 2>(a, gridw, RS, smem_s, st);    \
-    else launch_fwd_s<NCV, 1>(a, gridw, RS, smem_s, st);                  \
-  } while (0)
-      if (nc == 1) FWD_S(1);
-      else if (nc == 2) FWD_S(2);
-      else if (nc == 3) FWD_S(3);
-      else launch_fwd_s<4, 1>(a, gridw, RS, smem_s, st);
-#undef FWD_S
+      int tpw_s = (nc <= 3 && T > 16) ? 3 : 1;  // measured (profiles/r1_sweep_hbm_v4.json): T 24: 3 > 1 > 2; T 16: 1 > 2 > 3
+      static const int tpw_env = []() { const char* e = getenv("IMMTSF_RECAVG_TPW"); return e ? atoi(e) : 0; }();
+      if (tpw_env >= 1 && tpw_env <= 3 && nc <= 3) tpw_s = tpw_env;
+      if (nc == 1) launch_fwd_s<1>(a, tpw_s, T, B, RS, smem_s, st);
+      else if (nc == 2) launch_fwd_s<2>(a, tpw_s, T, B, RS, smem_s, st);
+      else if (nc == 3) launch_fwd_s<3>(a, tpw_s, T, B, RS, smem_s, st);
+      else launch_fwd_s<4>(a, 1, T, B, RS, smem_s, st);
       IMMTSF_CHECK_LAUNCH("recavg_pool_fwd_s");
       return IMMTSF_OK;
     }
@@ -820,12 +825,13 @@ extern "C" int immtsf_recavg_pool_bwd(const float* dE_drop, const float* E_raw, 
   cudaStream_t st = (cudaStream_t)stream;
   const int nc = rowwarp_nc(d);
   if (nc > 0 && ((uintptr_t)gamma & 15) == 0 && ((uintptr_t)dE_drop & 15) == 0 && ((uintptr_t)E_raw & 15) == 0) {
-    int gridw = ceil_div(B * T, 4);
-    if (gridw > 148 * 4) gridw = 148 * 4;
-    if (nc == 1) recavg_bwd_rows_w_kernel<1><<<gridw, 128, 0, st>>>(a);
-    else if (nc == 2) recavg_bwd_rows_w_kernel<2><<<gridw, 128, 0, st>>>(a);
-    else if (nc == 3) recavg_bwd_rows_w_kernel<3><<<gridw, 128, 0, st>>>(a);
-    else recavg_bwd_rows_w_kernel<4><<<gridw, 128, 0, st>>>(a);
+    const int want = ceil_div(B * T, 4);
+#define ROWS_W(NCV) recavg_bwd_rows_w_kernel<NCV><<<resident_grid((const void*)recavg_bwd_rows_w_kernel<NCV>, 128, 0, want, 4), 128, 0, st>>>(a)
+    if (nc == 1) ROWS_W(1);
+    else if (nc == 2) ROWS_W(2);
+    else if (nc == 3) ROWS_W(3);
+    else ROWS_W(4);
+#undef ROWS_W
     IMMTSF_CHECK_LAUNCH("recavg_bwd_rows_w");
   } else {
     const int TT = 8 / nch;
