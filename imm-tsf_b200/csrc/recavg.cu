@@ -259,6 +259,34 @@ __global__ void __launch_bounds__(256, NCH == 1 ? 3 : 2) recavg_bwd_rows_kernel(
 //   dV'_n = sum_t w_nt dS_t                      (written once, no read-modify-write)
 //   Q_n   = sum_t c_nt dS_t,  dlog_sigma += Q_n . V'_n + sum_t c_nt d(den_t)
 // so dS rows are streamed once (4 in flight) into two register accumulators per note.
+// mbarrier + 1-D bulk asynchronous copy (TMA) helpers shared by the staged kernels below
+__device__ __forceinline__ uint32_t rs_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void rs_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void rs_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void rs_mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "RS_WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra RS_WAIT_DONE;\n\t"
+      "bra RS_WAIT_LOOP;\n\t"
+      "RS_WAIT_DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void rs_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void f4_fma_s(float4& acc, float s, const float4& v) {
+  acc.x = fmaf(s, v.x, acc.x); acc.y = fmaf(s, v.y, acc.y); acc.z = fmaf(s, v.z, acc.z); acc.w = fmaf(s, v.w, acc.w);
+}
+
 constexpr int POOL_TB = 32;  // query rows per shared-memory weight block
 template <int NCH>
 __global__ void __launch_bounds__(256, NCH == 1 ? 2 : 1) recavg_bwd_notes_kernel(const PoolArgs a) {
@@ -353,6 +381,104 @@ __global__ void __launch_bounds__(256, NCH == 1 ? 2 : 1) recavg_bwd_notes_kernel
           const float4 q = accc[u][c];
           dls += (double)q.x * v.x + (double)q.y * v.y + (double)q.z * v.z + (double)q.w * v.w;
         }
+      }
+    }
+  }
+  if (threadIdx.x < NT) dls += (double)sc_term;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) dls += __shfl_xor_sync(0xffffffffu, dls, o);
+  if ((threadIdx.x & 31) == 0) s_redd[threadIdx.x >> 5] = dls;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)((blockDim.x + 31) >> 5); ++w) t += s_redd[w];
+    atomicAdd(a.dlog_sigma, t);
+  }
+}
+
+// Notes kernel with the sample's dS rows staged by one bulk asynchronous copy per tile of TB query rows (they are
+// contiguous: [T][d] per sample) instead of PF-deep dependent loads through L1/L2 -- the register version was latency-bound
+// (long-scoreboard 4.0 per issue at 18 % warps active, profiles/r1_ncu_recavg_v4_summary.txt).  d <= 1024 (one float4
+// column per thread), 8 notes per CTA.  The weights of the tile are computed while the copy is in flight.
+__global__ void __launch_bounds__(256, 2) recavg_bwd_notes_s_kernel(const PoolArgs a, int TB) {
+  constexpr int NT = 8;
+  extern __shared__ __align__(128) float s_g[];  // [TB][d]
+  __shared__ __align__(16) float s_w[POOL_TB][NT];
+  __shared__ __align__(16) float s_c[POOL_TB][NT];
+  __shared__ float s_dw[POOL_TB];
+  __shared__ double s_redd[8];
+  __shared__ __align__(8) unsigned long long s_bar;
+  const int b = blockIdx.y;
+  const int nb = a.offsets[b], ne = a.offsets[b + 1];
+  const int n0 = nb + blockIdx.x * NT;
+  if (n0 >= ne) return;
+  const int ncnt = min(NT, ne - n0);
+  const float sigma = expf(__ldg(a.log_sigma));
+  const int d4 = a.d >> 2;
+  const float* dwsum_in = a.dS + (size_t)a.B * a.T * a.d;
+  const uint32_t bar = rs_smem_u32(&s_bar), sg = rs_smem_u32(s_g);
+  if (threadIdx.x == 0) rs_mbar_init(bar, 1);
+  float4 accw[NT], accc[NT];
+#pragma unroll
+  for (int u = 0; u < NT; ++u) { accw[u] = f4_zero(); accc[u] = f4_zero(); }
+  float sc_term = 0.f;  // sum_t c_nt d(den_t), thread u < NT owns note u
+  uint32_t phase = 0;
+  const bool half = ncnt <= 4;  // half-empty tile (CTA-uniform): skip the empty note slots
+  for (int t0 = 0; t0 < a.T; t0 += TB) {
+    const int tcnt = min(TB, a.T - t0);
+    __syncthreads();  // the previous tile is consumed (and the barrier initialised, first time round)
+    if (threadIdx.x == 0) {
+      const uint32_t bytes = (uint32_t)tcnt * (uint32_t)a.d * 4u;
+      rs_mbar_expect_tx(bar, bytes);
+      rs_bulk_g2s(sg, a.dS + ((size_t)b * a.T + t0) * a.d, bytes, bar);
+    }
+    for (int i = threadIdx.x; i < TB * NT; i += blockDim.x) {
+      const int tt = i / NT, u = i % NT;
+      float w = 0.f, cc = 0.f;
+      if (tt < tcnt && u < ncnt) {
+        const float delta = fmaxf(a.t_hat[(size_t)b * a.t_bstride + t0 + tt] - __ldg(a.tau + n0 + u), 0.f);
+        const float r = delta / sigma;
+        w = expf(-(r * r));
+        cc = w * 2.f * r * r;
+      }
+      s_w[tt][u] = w;
+      s_c[tt][u] = cc;
+    }
+    if (threadIdx.x < TB) s_dw[threadIdx.x] = threadIdx.x < tcnt ? dwsum_in[(size_t)b * a.T + t0 + threadIdx.x] : 0.f;
+    __syncthreads();
+    if (threadIdx.x < NT)
+      for (int tt = 0; tt < tcnt; ++tt) sc_term = fmaf(s_c[tt][threadIdx.x], s_dw[tt], sc_term);
+    rs_mbar_wait(bar, phase);
+    phase ^= 1u;
+    if ((int)threadIdx.x < d4) {
+      const float4* gp = reinterpret_cast<const float4*>(s_g) + threadIdx.x;
+      for (int tt = 0; tt < tcnt; ++tt) {
+        const float4 g = gp[(size_t)tt * d4];
+        const float4 w0 = *reinterpret_cast<const float4*>(&s_w[tt][0]), c0 = *reinterpret_cast<const float4*>(&s_c[tt][0]);
+        f4_fma(accw[0], w0.x, g); f4_fma(accc[0], c0.x, g);
+        f4_fma(accw[1], w0.y, g); f4_fma(accc[1], c0.y, g);
+        f4_fma(accw[2], w0.z, g); f4_fma(accc[2], c0.z, g);
+        f4_fma(accw[3], w0.w, g); f4_fma(accc[3], c0.w, g);
+        if (!half) {
+          const float4 w1 = *reinterpret_cast<const float4*>(&s_w[tt][4]), c1 = *reinterpret_cast<const float4*>(&s_c[tt][4]);
+          f4_fma(accw[4], w1.x, g); f4_fma(accc[4], c1.x, g);
+          f4_fma(accw[5], w1.y, g); f4_fma(accc[5], c1.y, g);
+          f4_fma(accw[6], w1.z, g); f4_fma(accc[6], c1.z, g);
+          f4_fma(accw[7], w1.w, g); f4_fma(accc[7], c1.w, g);
+        }
+      }
+    }
+  }
+  // (same epilogue as recavg_bwd_notes_kernel: dV' rows out, the scalar d log sigma summed in double)
+  double dls = 0.0;
+  if ((int)threadIdx.x < d4) {
+#pragma unroll
+    for (int u = 0; u < NT; ++u) {
+      if (u < ncnt) {
+        reinterpret_cast<float4*>(a.dVp + (size_t)(n0 + u) * a.lddv)[threadIdx.x] = accw[u];
+        const float4 v = __ldg(reinterpret_cast<const float4*>(a.Vp + (size_t)(n0 + u) * a.ldv) + threadIdx.x);
+        const float4 q = accc[u];
+        dls += (double)q.x * v.x + (double)q.y * v.y + (double)q.z * v.z + (double)q.w * v.w;
       }
     }
   }
@@ -474,33 +600,6 @@ __global__ void __launch_bounds__(256) recavg_pool_fwd_w_kernel(const PoolArgs a
 // 2-way conflicts for LDS.128.  Lanes 4-7 of every quarter warp therefore read the SECOND float4 of their chunk first
 // (p = 1) and keep their halves swapped in registers until the epilogue; every LDS.128 wavefront then covers 8 distinct
 // 16-byte bank groups.
-__device__ __forceinline__ uint32_t rs_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void rs_mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void rs_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void rs_mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P1;\n\t"
-      "RS_WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-      "@P1 bra RS_WAIT_DONE;\n\t"
-      "bra RS_WAIT_LOOP;\n\t"
-      "RS_WAIT_DONE:\n\t"
-      "}" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void rs_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
-               "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void f4_fma_s(float4& acc, float s, const float4& v) {
-  acc.x = fmaf(s, v.x, acc.x); acc.y = fmaf(s, v.y, acc.y); acc.z = fmaf(s, v.z, acc.z); acc.w = fmaf(s, v.w, acc.w);
-}
-
 // smem: s_v [RS][d] (RS <= 32 rows per stage).  grid (ceil(T / (8*TPW)), B), 256 threads.
 template <int NC, int TPW, int MINB, bool FULL>
 __global__ void __launch_bounds__(256, MINB) recavg_pool_fwd_s_kernel(const PoolArgs a, int RS) {
@@ -729,6 +828,126 @@ __global__ void __launch_bounds__(128) recavg_bwd_rows_w_kernel(const PoolArgs a
   }
 }
 
+// The same rows kernel with a two-stage shared-memory ring per WARP: lane 0 posts the bulk asynchronous copies of the NEXT
+// row's dE_drop and E_raw (2 x d x 4 bytes, completion on the warp's mbarrier of that stage) before the warp works on the
+// current row, so two rows per warp are in flight instead of one (the register version: 3.06 TB/s of DRAM traffic at 12
+// resident warps/SM, long-scoreboard 4.0 per issue -- memory-level parallelism, not bandwidth, was the limit).
+// smem (dynamic): [4 warps][2 stages][2 rows][d].
+__device__ __forceinline__ void lds8(const float* row, int k, float (&o)[8]) {
+  const float4 a = reinterpret_cast<const float4*>(row)[2 * k];
+  const float4 b = reinterpret_cast<const float4*>(row)[2 * k + 1];
+  o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+}
+template <int NC>
+__global__ void __launch_bounds__(128) recavg_bwd_rows_s_kernel(const PoolArgs a) {
+  extern __shared__ __align__(128) float s_ring[];
+  __shared__ float s_acc[2 * 1024];  // dgamma | dbeta of this CTA
+  __shared__ __align__(8) unsigned long long s_bar[4][2];
+  const int d = a.d, d8 = d >> 3, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const float inv_keep = inv_keep_from_thr(a.thr), inv_d = 1.f / (float)d;
+  const uint64_t seed = resolve_seed(a.seed);
+  float* dwsum_out = a.dS + (size_t)a.B * a.T * d;
+  for (int i = threadIdx.x; i < 2 * d; i += blockDim.x) s_acc[i] = 0.f;
+  if (lane == 0) { rs_mbar_init(rs_smem_u32(&s_bar[w][0]), 1); rs_mbar_init(rs_smem_u32(&s_bar[w][1]), 1); }
+  __syncthreads();
+  float dgam[NC][8], dbet[NC][8];
+#pragma unroll
+  for (int i = 0; i < NC; ++i) { zero8(dgam[i]); zero8(dbet[i]); }
+  const int R = a.B * a.T;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  float* ring = s_ring + (size_t)w * 4 * d;  // stage s: dy at ring + s*2*d, x at ring + s*2*d + d
+  const uint32_t row_bytes = (uint32_t)d * 4u;
+  if (lane == 0 && gw < R) {
+    const uint32_t bar = rs_smem_u32(&s_bar[w][0]);
+    rs_mbar_expect_tx(bar, 2u * row_bytes);
+    rs_bulk_g2s(rs_smem_u32(ring), a.dE_drop + (size_t)gw * d, row_bytes, bar);
+    rs_bulk_g2s(rs_smem_u32(ring + d), a.E_raw + (size_t)gw * d, row_bytes, bar);
+  }
+  int it = 0;
+  for (int r = gw; r < R; r += nw, ++it) {
+    const int st = it & 1;
+    __syncwarp();  // every lane is done reading stage st^1 (the previous row)
+    if (lane == 0 && r + nw < R) {
+      const uint32_t bar = rs_smem_u32(&s_bar[w][st ^ 1]);
+      float* nxt = ring + (size_t)(st ^ 1) * 2 * d;
+      rs_mbar_expect_tx(bar, 2u * row_bytes);
+      rs_bulk_g2s(rs_smem_u32(nxt), a.dE_drop + (size_t)(r + nw) * d, row_bytes, bar);
+      rs_bulk_g2s(rs_smem_u32(nxt + d), a.E_raw + (size_t)(r + nw) * d, row_bytes, bar);
+    }
+    const float mu = a.mean[r], rs = a.rstd[r], ws = a.wsum[r];
+    const float den = fmaxf(ws, 1e-6f);
+    rs_mbar_wait(rs_smem_u32(&s_bar[w][st]), (uint32_t)((it >> 1) & 1));
+    const float* sdy = ring + (size_t)st * 2 * d;
+    const float* sx = sdy + d;
+    float g[NC][8], h[NC][8];
+    float p1 = 0.f, p2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+      const int k = lane + 32 * i;
+      zero8(g[i]); zero8(h[i]);
+      if (k < d8) {
+        float dy[8], ks[8], x[8], ga[8];
+        lds8(sdy, k, dy);
+        lds8(sx, k, x);
+        load8(a.gamma, k, ga);
+        dropout_scale8(seed, IMMTSF_SITE_TTF_DROPOUT, (uint64_t)r * d8 + k, a.thr, inv_keep, ks);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float dye = dy[e] * ks[e];
+          const float he = (x[e] - mu) * rs;
+          dgam[i][e] = fmaf(dye, he, dgam[i][e]);
+          dbet[i][e] += dye;
+          const float gg = dye * ga[e];
+          g[i][e] = gg;
+          h[i][e] = he;
+          p1 += gg;
+          p2 = fmaf(gg, he, p2);
+        }
+      }
+    }
+    const float s2 = warp_sum(p2);
+    const float m1 = warp_sum(p1) * inv_d, m2 = s2 * inv_d;
+    const float sc = rs / den;
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+      const int k = lane + 32 * i;
+      if (k < d8) {
+        float o[8];  // dE_raw = rstd * (g - mean(g) - xhat * mean(g*xhat));  dS = dE_raw / den
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = sc * (g[i][e] - m1 - h[i][e] * m2);
+        store8(a.dS + (size_t)r * d, k, o);
+      }
+    }
+    if (lane == 0) dwsum_out[r] = ws >= 1e-6f ? -(s2 * a.eps * rs * rs) / den : 0.f;
+  }
+#pragma unroll
+  for (int i = 0; i < NC; ++i) {
+    const int k = lane + 32 * i;
+    if (k < d8)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        atomicAdd(&s_acc[8 * k + e], dgam[i][e]);
+        atomicAdd(&s_acc[d + 8 * k + e], dbet[i][e]);
+      }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < d; i += blockDim.x) {
+    atomicAdd(a.dgamma + i, s_acc[i]);
+    atomicAdd(a.dbeta + i, s_acc[d + i]);
+  }
+}
+
+template <int NC>
+static void launch_rows_s(const PoolArgs& a, int want, cudaStream_t st) {
+  const size_t smem = (size_t)4 * 4 * a.d * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(recavg_bwd_rows_s_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 4 * 1024 * (int)sizeof(float));
+    attr = true;
+  }
+  recavg_bwd_rows_s_kernel<NC><<<resident_grid((const void*)recavg_bwd_rows_s_kernel<NC>, 128, smem, want, 4), 128, smem, st>>>(a);
+}
+
 static int pool_geometry(int d, int& nch, int& threads) {
   if (d <= 0 || (d & 3)) return -1;
   const int d4 = d >> 2;
@@ -826,12 +1045,20 @@ extern "C" int immtsf_recavg_pool_bwd(const float* dE_drop, const float* E_raw, 
   const int nc = rowwarp_nc(d);
   if (nc > 0 && ((uintptr_t)gamma & 15) == 0 && ((uintptr_t)dE_drop & 15) == 0 && ((uintptr_t)E_raw & 15) == 0) {
     const int want = ceil_div(B * T, 4);
+    static const int rows_tma = []() { const char* e = getenv("IMMTSF_RECAVG_TMA"); return !(e && e[0] == '0'); }();
+    if (rows_tma) {
+      if (nc == 1) launch_rows_s<1>(a, want, st);
+      else if (nc == 2) launch_rows_s<2>(a, want, st);
+      else if (nc == 3) launch_rows_s<3>(a, want, st);
+      else launch_rows_s<4>(a, want, st);
+    } else {
 #define ROWS_W(NCV) recavg_bwd_rows_w_kernel<NCV><<<resident_grid((const void*)recavg_bwd_rows_w_kernel<NCV>, 128, 0, want, 4), 128, 0, st>>>(a)
     if (nc == 1) ROWS_W(1);
     else if (nc == 2) ROWS_W(2);
     else if (nc == 3) ROWS_W(3);
     else ROWS_W(4);
 #undef ROWS_W
+    }
     IMMTSF_CHECK_LAUNCH("recavg_bwd_rows_w");
   } else {
     const int TT = 8 / nch;
@@ -842,6 +1069,20 @@ extern "C" int immtsf_recavg_pool_bwd(const float* dE_drop, const float* E_raw, 
     IMMTSF_CHECK_LAUNCH("recavg_bwd_rows");
   }
   dim3 grid2(ceil_div(N_max, 8 / nch), B);
+  static const int notes_tma = []() { const char* e = getenv("IMMTSF_RECAVG_TMA"); return !(e && e[0] == '0'); }();
+  if (nch == 1 && notes_tma) {
+    int TB = T < POOL_TB ? T : POOL_TB;
+    while (TB > 1 && (size_t)TB * d * sizeof(float) > 96 * 1024) --TB;
+    const size_t smem = (size_t)TB * d * sizeof(float);
+    static size_t smem_set = 0;
+    if (smem + 4096 > 48 * 1024 && smem > smem_set) {
+      cudaFuncSetAttribute(recavg_bwd_notes_s_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      smem_set = smem;
+    }
+    recavg_bwd_notes_s_kernel<<<grid2, threads, smem, st>>>(a, TB);
+    IMMTSF_CHECK_LAUNCH("recavg_bwd_notes_s");
+    return IMMTSF_OK;
+  }
   if (nch == 1) recavg_bwd_notes_kernel<1><<<grid2, threads, 0, st>>>(a);
   else if (nch == 2) recavg_bwd_notes_kernel<2><<<grid2, threads, 0, st>>>(a);
   else recavg_bwd_notes_kernel<4><<<grid2, threads, 0, st>>>(a);
