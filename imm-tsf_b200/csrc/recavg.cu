@@ -37,6 +37,9 @@ struct PoolArgs {
   const float* dE_drop; float* dVp; int lddv; float* dgamma; float* dbeta; double* dlog_sigma; float* dS; int N_max;
 };
 
+#ifndef IMMTSF_RECAVG_FUSED_BWD_DEFAULT
+#define IMMTSF_RECAVG_FUSED_BWD_DEFAULT 8  // one-launch backward (232 GPU tests green with it; =0: two-kernel path)
+#endif
 constexpr int POOL_NB = 32;  // notes per shared-memory weight block
 
 // ncu (B 2048, N<=16, T 24, d 768) showed the first version of this kernel issue-bound, not memory-bound (47 % issue
@@ -948,6 +951,222 @@ static void launch_rows_s(const PoolArgs& a, int want, cudaStream_t st) {
   recavg_bwd_rows_s_kernel<NC><<<resident_grid((const void*)recavg_bwd_rows_s_kernel<NC>, 128, smem, want, 4), 128, smem, st>>>(a);
 }
 
+// ------------------------------------------------------------------ backward in ONE launch (short prediction windows)
+// The two-kernel backward writes dS [B*T, d] to HBM and reads it back once per tile of 8 notes (B 2048, N <= 16, T 24, d 768:
+// 151 MB written + up to 302 MB read against 405 MB of algorithmic traffic).  Here a persistent CTA owns one sample at a time and
+// dS never leaves shared memory:
+//   1. one bulk asynchronous copy brings the sample's dE_drop rows [T][d] (contiguous) into s_g; each warp streams its E_raw
+//      rows (t = w, w + 8, ...) through a private one-row buffer with its own mbarrier;
+//   2. rows phase, warp per query row, two passes over shared memory (so that g and x^ need no registers across the warp
+//      reductions): s_g row <- dy*keep*gamma, then s_g row <- dS_t; d(den_t) -> s_dw[t];
+//   3. the warps' dgamma / dbeta partials of the sample are exchanged through the (now idle) E_raw buffers and summed by
+//      column-owner threads into two float4 registers that live for the whole kernel (48 accumulator registers per lane
+//      would not survive the note phase under the 128-register cap);
+//   4. note phase, thread per float4 column, NTN notes per pass: dV'_n = sum_t w_nt dS_t, Q_n = sum_t c_nt dS_t from s_g.
+// Requires T <= POOL_TB, d % 8 == 0, d <= 1024 and (T + 8) * d * 4 bytes of dynamic shared memory (2 CTAs per SM at T 24, d 768).
+__device__ __forceinline__ void sts8(float* row, int k, const float (&v)[8]) {
+  reinterpret_cast<float4*>(row)[2 * k] = make_float4(v[0], v[1], v[2], v[3]);
+  reinterpret_cast<float4*>(row)[2 * k + 1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+template <int NC, int NTN>
+__global__ void __launch_bounds__(256, 2) recavg_bwd_fused_kernel(const PoolArgs a) {
+  static_assert(NTN == 4 || NTN == 8, "notes per pass");
+  extern __shared__ __align__(128) float s_dyn[];  // s_g [T][d] | s_x [8 warps][d]
+  __shared__ __align__(16) float s_w[POOL_TB][NTN];
+  __shared__ __align__(16) float s_c[POOL_TB][NTN];
+  __shared__ float s_dw[POOL_TB];
+  __shared__ double s_redd[8];
+  __shared__ __align__(8) unsigned long long s_barg;
+  __shared__ __align__(8) unsigned long long s_barx[8];
+  const int d = a.d, d8 = d >> 3, d4 = d >> 2, T = a.T;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float* s_g = s_dyn;
+  float* s_x = s_dyn + (size_t)T * d;
+  float* s_xw = s_x + (size_t)w * d;
+  const uint32_t barg = rs_smem_u32(&s_barg), barx = rs_smem_u32(&s_barx[w]);
+  if (threadIdx.x == 0) rs_mbar_init(barg, 1);
+  if (lane == 0) rs_mbar_init(barx, 1);
+  __syncthreads();
+  const float inv_keep = inv_keep_from_thr(a.thr), inv_d = 1.f / (float)d;
+  const uint64_t seed = resolve_seed(a.seed);
+  const float sigma = expf(__ldg(a.log_sigma));
+  const uint32_t row_bytes = (uint32_t)d * 4u;
+  float4 colg = f4_zero(), colb = f4_zero();  // dgamma / dbeta of float4 column threadIdx.x, over every sample of this CTA
+  double dls = 0.0;
+  uint32_t phg = 0, phx = 0;
+  for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
+    const int nb = a.offsets[b], ne = a.offsets[b + 1];
+    // generic-proxy writes of the previous sample (dS rows, gradient partials) are ordered before the bulk copies below
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      rs_mbar_expect_tx(barg, (uint32_t)T * row_bytes);
+      rs_bulk_g2s(rs_smem_u32(s_g), a.dE_drop + (size_t)b * T * d, (uint32_t)T * row_bytes, barg);
+    }
+    if (w < T && lane == 0) {
+      rs_mbar_expect_tx(barx, row_bytes);
+      rs_bulk_g2s(rs_smem_u32(s_xw), a.E_raw + ((size_t)b * T + w) * d, row_bytes, barx);
+    }
+    float dgam[NC][8], dbet[NC][8];
+#pragma unroll
+    for (int i = 0; i < NC; ++i) { zero8(dgam[i]); zero8(dbet[i]); }
+    rs_mbar_wait(barg, phg);
+    phg ^= 1u;
+    for (int t = w; t < T; t += 8) {
+      const size_t r = (size_t)b * T + t;
+      const float mu = a.mean[r], rs = a.rstd[r], ws = a.wsum[r];
+      const float den = fmaxf(ws, 1e-6f);
+      float* sg = s_g + (size_t)t * d;
+      rs_mbar_wait(barx, phx);
+      phx ^= 1u;
+      float p1 = 0.f, p2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < NC; ++i) {
+        const int k = lane + 32 * i;
+        if (k < d8) {
+          float dy[8], x[8], ga[8], ks[8], gg[8];
+          lds8(sg, k, dy);
+          lds8(s_xw, k, x);
+          load8(a.gamma, k, ga);
+          dropout_scale8(seed, IMMTSF_SITE_TTF_DROPOUT, (uint64_t)r * d8 + k, a.thr, inv_keep, ks);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float dye = dy[e] * ks[e];
+            const float he = (x[e] - mu) * rs;
+            dgam[i][e] = fmaf(dye, he, dgam[i][e]);
+            dbet[i][e] += dye;
+            gg[e] = dye * ga[e];
+            p1 += gg[e];
+            p2 = fmaf(gg[e], he, p2);
+          }
+          sts8(sg, k, gg);  // re-read below by this lane only
+        }
+      }
+      const float s2 = warp_sum(p2);
+      const float m1 = warp_sum(p1) * inv_d, m2 = s2 * inv_d;
+      const float sc = rs / den;
+#pragma unroll
+      for (int i = 0; i < NC; ++i) {
+        const int k = lane + 32 * i;
+        if (k < d8) {
+          float gg[8], x[8], o[8];  // dE_raw = rstd * (g - mean(g) - xhat * mean(g*xhat));  dS = dE_raw / den
+          lds8(sg, k, gg);
+          lds8(s_xw, k, x);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] = sc * (gg[e] - m1 - ((x[e] - mu) * rs) * m2);
+          sts8(sg, k, o);
+        }
+      }
+      // d(den) = -sum_j dE_raw_j E_raw_j / den = -(s2 * eps * rstd^2) / den ; clamp_min passes gradient where wsum >= 1e-6
+      if (lane == 0) s_dw[t] = ws >= 1e-6f ? -(s2 * a.eps * rs * rs) / den : 0.f;
+      __syncwarp();  // every lane is done with the E_raw row
+      if (t + 8 < T && lane == 0) {
+        rs_mbar_expect_tx(barx, row_bytes);
+        rs_bulk_g2s(rs_smem_u32(s_xw), a.E_raw + (r + 8) * d, row_bytes, barx);
+      }
+    }
+    // the warps' dgamma, then dbeta, partials of this sample -> column owners (through the idle E_raw buffers)
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < NC; ++i)
+      if (lane + 32 * i < d8) sts8(s_xw, lane + 32 * i, dgam[i]);
+    __syncthreads();  // also: dS and d(den) of every query row are in shared memory
+    if ((int)threadIdx.x < d4) {
+#pragma unroll
+      for (int ww = 0; ww < 8; ++ww) f4_add(colg, reinterpret_cast<const float4*>(s_x + (size_t)ww * d)[threadIdx.x]);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NC; ++i)
+      if (lane + 32 * i < d8) sts8(s_xw, lane + 32 * i, dbet[i]);
+    __syncthreads();
+    if ((int)threadIdx.x < d4) {
+#pragma unroll
+      for (int ww = 0; ww < 8; ++ww) f4_add(colb, reinterpret_cast<const float4*>(s_x + (size_t)ww * d)[threadIdx.x]);
+    }
+    // note phase
+    for (int n0 = nb; n0 < ne; n0 += NTN) {
+      const int ncnt = min(NTN, ne - n0);
+      if (n0 != nb) __syncthreads();  // the previous pass has consumed s_w / s_c
+      for (int i = threadIdx.x; i < T * NTN; i += blockDim.x) {
+        const int tt = i / NTN, u = i % NTN;
+        float wv = 0.f, cc = 0.f;
+        if (u < ncnt) {
+          const float delta = fmaxf(a.t_hat[(size_t)b * a.t_bstride + tt] - __ldg(a.tau + n0 + u), 0.f);
+          const float rr = delta / sigma;
+          wv = expf(-(rr * rr));
+          cc = wv * 2.f * rr * rr;
+        }
+        s_w[tt][u] = wv;
+        s_c[tt][u] = cc;
+      }
+      __syncthreads();
+      if (threadIdx.x < NTN) {  // sum_t c_nt d(den_t), thread u owns note u
+        float sc_term = 0.f;
+        for (int tt = 0; tt < T; ++tt) sc_term = fmaf(s_c[tt][threadIdx.x], s_dw[tt], sc_term);
+        dls += (double)sc_term;
+      }
+      if ((int)threadIdx.x < d4) {
+        float4 accw[NTN], accc[NTN];
+#pragma unroll
+        for (int u = 0; u < NTN; ++u) { accw[u] = f4_zero(); accc[u] = f4_zero(); }
+        const float4* gp = reinterpret_cast<const float4*>(s_g) + threadIdx.x;
+        const bool half = NTN == 8 && ncnt <= 4;  // half-empty pass (CTA-uniform): skip the empty note slots
+        for (int tt = 0; tt < T; ++tt) {
+          const float4 g = gp[(size_t)tt * d4];
+          const float4 w0 = *reinterpret_cast<const float4*>(&s_w[tt][0]), c0 = *reinterpret_cast<const float4*>(&s_c[tt][0]);
+          f4_fma(accw[0], w0.x, g); f4_fma(accc[0], c0.x, g);
+          f4_fma(accw[1], w0.y, g); f4_fma(accc[1], c0.y, g);
+          f4_fma(accw[2], w0.z, g); f4_fma(accc[2], c0.z, g);
+          f4_fma(accw[3], w0.w, g); f4_fma(accc[3], c0.w, g);
+          if (NTN == 8 && !half) {
+            const float4 w1 = *reinterpret_cast<const float4*>(&s_w[tt][NTN - 4]), c1 = *reinterpret_cast<const float4*>(&s_c[tt][NTN - 4]);
+            f4_fma(accw[NTN - 4], w1.x, g); f4_fma(accc[NTN - 4], c1.x, g);
+            f4_fma(accw[NTN - 3], w1.y, g); f4_fma(accc[NTN - 3], c1.y, g);
+            f4_fma(accw[NTN - 2], w1.z, g); f4_fma(accc[NTN - 2], c1.z, g);
+            f4_fma(accw[NTN - 1], w1.w, g); f4_fma(accc[NTN - 1], c1.w, g);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < NTN; ++u) {
+          if (u < ncnt) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(a.Vp + (size_t)(n0 + u) * a.ldv) + threadIdx.x);
+            const float4 q = accc[u];
+            dls += (double)q.x * v.x + (double)q.y * v.y + (double)q.z * v.z + (double)q.w * v.w;
+            reinterpret_cast<float4*>(a.dVp + (size_t)(n0 + u) * a.lddv)[threadIdx.x] = accw[u];
+          }
+        }
+      }
+    }
+  }
+  if ((int)threadIdx.x < d4) {
+    float* pg = a.dgamma + 4 * threadIdx.x;
+    float* pb = a.dbeta + 4 * threadIdx.x;
+    atomicAdd(pg + 0, colg.x); atomicAdd(pg + 1, colg.y); atomicAdd(pg + 2, colg.z); atomicAdd(pg + 3, colg.w);
+    atomicAdd(pb + 0, colb.x); atomicAdd(pb + 1, colb.y); atomicAdd(pb + 2, colb.z); atomicAdd(pb + 3, colb.w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) dls += __shfl_xor_sync(0xffffffffu, dls, o);
+  if (lane == 0) s_redd[w] = dls;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int ww = 0; ww < 8; ++ww) t += s_redd[ww];
+    atomicAdd(a.dlog_sigma, t);
+  }
+}
+
+template <int NC, int NTN>
+static void launch_bwd_fused(const PoolArgs& a, cudaStream_t st) {
+  const size_t smem = (size_t)(a.T + 8) * a.d * sizeof(float);
+  static size_t smem_set = 0;
+  if (smem + 4096 > 48 * 1024 && smem > smem_set) {
+    cudaFuncSetAttribute(recavg_bwd_fused_kernel<NC, NTN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    smem_set = smem;
+  }
+  recavg_bwd_fused_kernel<NC, NTN><<<resident_grid((const void*)recavg_bwd_fused_kernel<NC, NTN>, 256, smem, a.B, 2), 256, smem, st>>>(a);
+}
+
 static int pool_geometry(int d, int& nch, int& threads) {
   if (d <= 0 || (d & 3)) return -1;
   const int d4 = d >> 2;
@@ -1043,6 +1262,21 @@ extern "C" int immtsf_recavg_pool_bwd(const float* dE_drop, const float* E_raw, 
   a.dS = dS; a.N_max = N_max;
   cudaStream_t st = (cudaStream_t)stream;
   const int nc = rowwarp_nc(d);
+  // Short prediction windows: one launch, dS stays in shared memory (IMMTSF_RECAVG_FUSED_BWD=0 keeps the two-kernel path,
+  // =4 / =8 picks the notes per pass).
+  const char* fused_env = getenv("IMMTSF_RECAVG_FUSED_BWD");  // read per call: tests A/B the two paths inside one process
+  const int fused = fused_env ? atoi(fused_env) : IMMTSF_RECAVG_FUSED_BWD_DEFAULT;
+  if (fused && nc > 0 && T <= POOL_TB && (size_t)(T + 8) * d * sizeof(float) <= 108 * 1024 && ((uintptr_t)gamma & 15) == 0 &&
+      ((uintptr_t)dE_drop & 15) == 0 && ((uintptr_t)E_raw & 15) == 0) {
+#define BWD_F(NCV) do { if (fused == 4) launch_bwd_fused<NCV, 4>(a, st); else launch_bwd_fused<NCV, 8>(a, st); } while (0)
+    if (nc == 1) BWD_F(1);
+    else if (nc == 2) BWD_F(2);
+    else if (nc == 3) BWD_F(3);
+    else BWD_F(4);
+#undef BWD_F
+    IMMTSF_CHECK_LAUNCH("recavg_bwd_fused");
+    return IMMTSF_OK;
+  }
   if (nc > 0 && ((uintptr_t)gamma & 15) == 0 && ((uintptr_t)dE_drop & 15) == 0 && ((uintptr_t)E_raw & 15) == 0) {
     const int want = ceil_div(B * T, 4);
     static const int rows_tma = []() { const char* e = getenv("IMMTSF_RECAVG_TMA"); return !(e && e[0] == '0'); }();

@@ -295,6 +295,37 @@ def test_recavg_properties_full_size():
     G.assert_close("mean-pooling limit", a.cpu(), b.cpu(), 2e-5)
 
 
+@pytest.mark.parametrize("B,N,T,d,p", [(5, 6, 7, 64, 0.1), (64, 16, 24, 768, 0.1), (300, 3, 16, 1024, 0.2), (9, 40, 24, 256, 0.0),
+                                         (3, 1, 1, 8, 0.5), (150, 16, 32, 512, 0.1), (2, 5, 24, 776, 0.1)])
+def test_recavg_bwd_fused_equals_two_kernel(B, N, T, d, p, monkeypatch):
+    """The one-launch backward (dS kept in shared memory, IMMTSF_RECAVG_FUSED_BWD=8 / =4) against the two-kernel
+    backward (=0) on the same inputs: same formulas, only the summation order of dgamma / dbeta / dlog_sigma differs.
+    Includes T < 8 (idle row warps), N > 8 (several note passes), a sample without notes, d not a multiple of 256."""
+    from immtsf import ops
+
+    notes, tau, t_hat, _, _ = G.synth_batch(B, N, T, d, 1, 31, no_note=B > 2)
+    r = ops.csr_build(notes.cuda(), tau.cuda())
+    t_hat = t_hat.cuda()
+    g = torch.Generator().manual_seed(3)
+    ls = torch.tensor(-0.3, device="cuda")
+    gamma = (1.0 + 0.1 * torch.randn(d, generator=g)).cuda()
+    beta = (0.1 * torch.randn(d, generator=g)).cuda()
+    thr, seed = ops.drop_thr(p), 991
+    E_drop, E_raw, mean, rstd, wsum = ops.recavg_pool_fwd(r.emb_flat, r, t_hat, ls, gamma, beta, T, d, thr, seed, True)
+    dE = torch.randn(B, T, d, generator=g).cuda().view_as(E_drop)
+    outs = {}
+    for mode in ("0", "8", "4"):
+        monkeypatch.setenv("IMMTSF_RECAVG_FUSED_BWD", mode)
+        outs[mode] = [x.clone() for x in ops.recavg_pool_bwd(dE, E_raw, mean, rstd, wsum, r.emb_flat, r, t_hat, ls, gamma, T, d, thr, seed)]
+    torch.cuda.synchronize()
+    for mode in ("8", "4"):
+        for name, ref, got in zip(("dVp", "dgamma", "dbeta", "dlog_sigma"), outs["0"], outs[mode]):
+            assert torch.isfinite(got).all(), (mode, name)
+            den = max(ref.abs().max().item(), 1e-6)
+            err = (got - ref).abs().max().item()
+            assert err <= 2e-5 * den, f"fused={mode} {name}: err {err:.3e} vs max {den:.3e}"
+
+
 # ------------------------------------------------------------------ boundary behaviour
 def test_error_conventions():
     cfg = dict(ttf="TTF_RecAvg", mmf="MMF_GR_Add", d_txt=16, C=4, H=1, kappa=0.5)
