@@ -476,13 +476,19 @@ __global__ void __launch_bounds__(256, 2) recavg_bwd_notes_s_kernel(const PoolAr
   double dls = 0.0;
   if ((int)threadIdx.x < d4) {
 #pragma unroll
-    for (int u = 0; u < NT; ++u) {
-      if (u < ncnt) {
-        reinterpret_cast<float4*>(a.dVp + (size_t)(n0 + u) * a.lddv)[threadIdx.x] = accw[u];
-        const float4 v = __ldg(reinterpret_cast<const float4*>(a.Vp + (size_t)(n0 + u) * a.ldv) + threadIdx.x);
-        const float4 q = accc[u];
+    for (int h0 = 0; h0 < NT; h0 += 4) {  // four V' rows requested before the first store (which may alias, as far as the compiler knows)
+      float4 vv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        vv[u] = h0 + u < ncnt ? __ldg(reinterpret_cast<const float4*>(a.Vp + (size_t)(n0 + h0 + u) * a.ldv) + threadIdx.x) : f4_zero();
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float4 q = accc[h0 + u], v = vv[u];  // empty slots: q == v == 0
         dls += (double)q.x * v.x + (double)q.y * v.y + (double)q.z * v.z + (double)q.w * v.w;
       }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (h0 + u < ncnt) reinterpret_cast<float4*>(a.dVp + (size_t)(n0 + h0 + u) * a.lddv)[threadIdx.x] = accw[h0 + u];
     }
   }
   if (threadIdx.x < NT) dls += (double)sc_term;
@@ -1002,6 +1008,9 @@ __global__ void __launch_bounds__(256, 2) recavg_bwd_fused_kernel(const PoolArgs
     if (threadIdx.x == 0) {
       rs_mbar_expect_tx(barg, (uint32_t)T * row_bytes);
       rs_bulk_g2s(rs_smem_u32(s_g), a.dE_drop + (size_t)b * T * d, (uint32_t)T * row_bytes, barg);
+      // the sample's V' rows are only needed by the note phase's epilogue: start them towards L2 now
+      if (ne > nb && a.ldv == d)
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.Vp + (size_t)nb * a.ldv), "r"((uint32_t)(ne - nb) * row_bytes) : "memory");
     }
     if (w < T && lane == 0) {
       rs_mbar_expect_tx(barx, row_bytes);
@@ -1010,11 +1019,15 @@ __global__ void __launch_bounds__(256, 2) recavg_bwd_fused_kernel(const PoolArgs
     float dgam[NC][8], dbet[NC][8];
 #pragma unroll
     for (int i = 0; i < NC; ++i) { zero8(dgam[i]); zero8(dbet[i]); }
+    // LayerNorm statistics of the warp's first row are requested before the wait on the copy, the next row's one row ahead
+    float mu_n = 0.f, rs_n = 0.f, ws_n = 0.f;
+    if (w < T) { const size_t r0 = (size_t)b * T + w; mu_n = a.mean[r0]; rs_n = a.rstd[r0]; ws_n = a.wsum[r0]; }
     rs_mbar_wait(barg, phg);
     phg ^= 1u;
     for (int t = w; t < T; t += 8) {
       const size_t r = (size_t)b * T + t;
-      const float mu = a.mean[r], rs = a.rstd[r], ws = a.wsum[r];
+      const float mu = mu_n, rs = rs_n, ws = ws_n;
+      if (t + 8 < T) { mu_n = a.mean[r + 8]; rs_n = a.rstd[r + 8]; ws_n = a.wsum[r + 8]; }  // consumed one row later
       const float den = fmaxf(ws, 1e-6f);
       float* sg = s_g + (size_t)t * d;
       rs_mbar_wait(barx, phx);
@@ -1127,14 +1140,22 @@ __global__ void __launch_bounds__(256, 2) recavg_bwd_fused_kernel(const PoolArgs
             f4_fma(accw[NTN - 1], w1.w, g); f4_fma(accc[NTN - 1], c1.w, g);
           }
         }
+        // every V' row of the pass is requested before the first store (stores to dV' may alias as far as the compiler
+        // knows, which serialised one DRAM round trip per note: 15 % of the stall samples of the first version)
 #pragma unroll
-        for (int u = 0; u < NTN; ++u) {
-          if (u < ncnt) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(a.Vp + (size_t)(n0 + u) * a.ldv) + threadIdx.x);
-            const float4 q = accc[u];
+        for (int h0 = 0; h0 < NTN; h0 += 4) {  // four notes at a time (register budget)
+          float4 vv[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            vv[u] = h0 + u < ncnt ? __ldg(reinterpret_cast<const float4*>(a.Vp + (size_t)(n0 + h0 + u) * a.ldv) + threadIdx.x) : f4_zero();
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float4 q = accc[h0 + u], v = vv[u];  // empty slots: q == v == 0
             dls += (double)q.x * v.x + (double)q.y * v.y + (double)q.z * v.z + (double)q.w * v.w;
-            reinterpret_cast<float4*>(a.dVp + (size_t)(n0 + u) * a.lddv)[threadIdx.x] = accw[u];
           }
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (h0 + u < ncnt) reinterpret_cast<float4*>(a.dVp + (size_t)(n0 + h0 + u) * a.lddv)[threadIdx.x] = accw[h0 + u];
         }
       }
     }
@@ -1262,11 +1283,12 @@ extern "C" int immtsf_recavg_pool_bwd(const float* dE_drop, const float* E_raw, 
   a.dS = dS; a.N_max = N_max;
   cudaStream_t st = (cudaStream_t)stream;
   const int nc = rowwarp_nc(d);
-  // Short prediction windows: one launch, dS stays in shared memory (IMMTSF_RECAVG_FUSED_BWD=0 keeps the two-kernel path,
-  // =4 / =8 picks the notes per pass).
+  // Short prediction windows and segments (N_max <= 32: at N <= 64, T 28 the two-kernel path measured 272 us against 339 us,
+  // profiles/r1_sweep_hbm_v6_fused.json): one launch, dS stays in shared memory (IMMTSF_RECAVG_FUSED_BWD=0 keeps the
+  // two-kernel path, =4 / =8 picks the notes per pass).
   const char* fused_env = getenv("IMMTSF_RECAVG_FUSED_BWD");  // read per call: tests A/B the two paths inside one process
   const int fused = fused_env ? atoi(fused_env) : IMMTSF_RECAVG_FUSED_BWD_DEFAULT;
-  if (fused && nc > 0 && T <= POOL_TB && (size_t)(T + 8) * d * sizeof(float) <= 108 * 1024 && ((uintptr_t)gamma & 15) == 0 &&
+  if (fused && nc > 0 && T <= POOL_TB && N_max <= 32 && (size_t)(T + 8) * d * sizeof(float) <= 108 * 1024 && ((uintptr_t)gamma & 15) == 0 &&
       ((uintptr_t)dE_drop & 15) == 0 && ((uintptr_t)E_raw & 15) == 0) {
 #define BWD_F(NCV) do { if (fused == 4) launch_bwd_fused<NCV, 4>(a, st); else launch_bwd_fused<NCV, 8>(a, st); } while (0)
     if (nc == 1) BWD_F(1);

@@ -295,12 +295,13 @@ def test_recavg_properties_full_size():
     G.assert_close("mean-pooling limit", a.cpu(), b.cpu(), 2e-5)
 
 
-@pytest.mark.parametrize("B,N,T,d,p", [(5, 6, 7, 64, 0.1), (64, 16, 24, 768, 0.1), (300, 3, 16, 1024, 0.2), (9, 40, 24, 256, 0.0),
+@pytest.mark.parametrize("B,N,T,d,p", [(5, 6, 7, 64, 0.1), (64, 16, 24, 768, 0.1), (300, 3, 16, 1024, 0.2), (9, 30, 24, 256, 0.0), (9, 40, 24, 256, 0.0),
                                          (3, 1, 1, 8, 0.5), (150, 16, 32, 512, 0.1), (2, 5, 24, 776, 0.1)])
 def test_recavg_bwd_fused_equals_two_kernel(B, N, T, d, p, monkeypatch):
     """The one-launch backward (dS kept in shared memory, IMMTSF_RECAVG_FUSED_BWD=8 / =4) against the two-kernel
     backward (=0) on the same inputs: same formulas, only the summation order of dgamma / dbeta / dlog_sigma differs.
-    Includes T < 8 (idle row warps), N > 8 (several note passes), a sample without notes, d not a multiple of 256."""
+    Includes T < 8 (idle row warps), N > 8 (several note passes), N > 32 (both modes take the two-kernel path), a sample
+    without notes, d not a multiple of 256."""
     from immtsf import ops
 
     notes, tau, t_hat, _, _ = G.synth_batch(B, N, T, d, 1, 31, no_note=B > 2)
