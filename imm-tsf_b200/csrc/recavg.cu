@@ -35,12 +35,29 @@ struct PoolArgs {
   float* E_drop; float* E_raw; float* mean; float* rstd; float* wsum;
   // backward only
   const float* dE_drop; float* dVp; int lddv; float* dgamma; float* dbeta; double* dlog_sigma; float* dS; int N_max;
+  int maskbit;  // host-side dispatch only: 1 = the TAG instantiations (keep flags in the LSB of E_raw)
 };
 
 #ifndef IMMTSF_RECAVG_FUSED_BWD_DEFAULT
 #define IMMTSF_RECAVG_FUSED_BWD_DEFAULT 8  // one-launch backward (232 GPU tests green with it; =0: two-kernel path)
 #endif
 constexpr int POOL_NB = 32;  // notes per shared-memory weight block
+
+// Experimental (IMMTSF_RECAVG_MASKBIT=1, default off until measured; template parameter TAG of the kernels below, so the
+// default instantiations are untouched): E_raw is saved for the backward only, which needs x^ = (E_raw - mean) * rstd and
+// the dropout keep flag of the same element.  The forward stores the flag in the mantissa LSB of E_raw (<= 1 ulp = 6e-8
+// relative on x, far inside the 5e-5 gradient tolerance) and the backward reads it back instead of running Philox4x32-10
+// again (18 % of its executed instructions, profiles/r1_ncu_recavg_fused_bwd_summary.txt).  No extra bytes, no ABI change.
+__device__ __forceinline__ float tag_keep(float x, float ks) {
+  return __uint_as_float((__float_as_uint(x) & ~1u) | (ks != 0.f ? 1u : 0u));
+}
+__device__ __forceinline__ float4 tag_keep4(const float4& x, const float4& ks) {
+  return make_float4(tag_keep(x.x, ks.x), tag_keep(x.y, ks.y), tag_keep(x.z, ks.z), tag_keep(x.w, ks.w));
+}
+__device__ __forceinline__ void keep_of8(const float (&x)[8], float inv_keep, float (&ks)[8]) {
+#pragma unroll
+  for (int e = 0; e < 8; ++e) ks[e] = (__float_as_uint(x[e]) & 1u) ? inv_keep : 0.f;
+}
 
 // ncu (B 2048, N<=16, T 24, d 768) showed the first version of this kernel issue-bound, not memory-bound (47 % issue
 // utilisation with 18 warps/SM, long-scoreboard stalls ~1): hence the register cap (more resident warps), the
@@ -610,7 +627,7 @@ __global__ void __launch_bounds__(256) recavg_pool_fwd_w_kernel(const PoolArgs a
 // (p = 1) and keep their halves swapped in registers until the epilogue; every LDS.128 wavefront then covers 8 distinct
 // 16-byte bank groups.
 // smem: s_v [RS][d] (RS <= 32 rows per stage).  grid (ceil(T / (8*TPW)), B), 256 threads.
-template <int NC, int TPW, int MINB, bool FULL>
+template <int NC, int TPW, int MINB, bool FULL, bool TAG>
 __global__ void __launch_bounds__(256, MINB) recavg_pool_fwd_s_kernel(const PoolArgs a, int RS) {
   extern __shared__ __align__(128) float s_v[];
   __shared__ __align__(8) unsigned long long s_bar;
@@ -728,8 +745,8 @@ __global__ void __launch_bounds__(256, MINB) recavg_pool_fwd_s_kernel(const Pool
         eo[oB] = yB;
         if (a.E_raw) {
           float4* er = reinterpret_cast<float4*>(a.E_raw + rowi * a.d);
-          er[oA] = A;
-          er[oB] = Bv;
+          er[oA] = (TAG && a.thr) ? tag_keep4(A, kA) : A;
+          er[oB] = (TAG && a.thr) ? tag_keep4(Bv, kB) : Bv;
         }
       }
     }
@@ -741,14 +758,19 @@ __global__ void __launch_bounds__(256, MINB) recavg_pool_fwd_s_kernel(const Pool
   }
 }
 
-template <int NC, int TPW, int MINB, bool FULL>
-static void launch_fwd_s2(const PoolArgs& a, dim3 grid, int RS, size_t smem, cudaStream_t st) {
+template <int NC, int TPW, int MINB, bool FULL, bool TAG>
+static void launch_fwd_s3(const PoolArgs& a, dim3 grid, int RS, size_t smem, cudaStream_t st) {
   static size_t smem_set = 0;
   if (smem + 1024 > 48 * 1024 && smem > smem_set) {  // (the kernel also has 128 B of static shared memory)
-    cudaFuncSetAttribute(recavg_pool_fwd_s_kernel<NC, TPW, MINB, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(recavg_pool_fwd_s_kernel<NC, TPW, MINB, FULL, TAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     smem_set = smem;
   }
-  recavg_pool_fwd_s_kernel<NC, TPW, MINB, FULL><<<grid, 256, smem, st>>>(a, RS);
+  recavg_pool_fwd_s_kernel<NC, TPW, MINB, FULL, TAG><<<grid, 256, smem, st>>>(a, RS);
+}
+template <int NC, int TPW, int MINB, bool FULL>
+static void launch_fwd_s2(const PoolArgs& a, dim3 grid, int RS, size_t smem, cudaStream_t st) {
+  if (a.maskbit) launch_fwd_s3<NC, TPW, MINB, FULL, true>(a, grid, RS, smem, st);
+  else launch_fwd_s3<NC, TPW, MINB, FULL, false>(a, grid, RS, smem, st);
 }
 // tpw: query times per warp.  3: capped at 128 registers, 2 CTAs per SM (MINB = 2); 2: capped at 80 registers, 3 CTAs per SM (MINB = 3).
 template <int NC>
@@ -761,7 +783,7 @@ static void launch_fwd_s(const PoolArgs& a, int tpw, int T, int B, int RS, size_
 }
 
 // Backward phase 1 (LayerNorm backward of the pooled rows -> dS, d(den)), one warp per (sample, query time) row.
-template <int NC>
+template <int NC, bool TAG>
 __global__ void __launch_bounds__(128) recavg_bwd_rows_w_kernel(const PoolArgs a) {
   __shared__ float s_acc[2 * 1024];  // dgamma | dbeta of this CTA
   const int d8 = a.d >> 3, lane = threadIdx.x & 31;
@@ -789,7 +811,8 @@ __global__ void __launch_bounds__(128) recavg_bwd_rows_w_kernel(const PoolArgs a
         load8(a.dE_drop + (size_t)r * a.d, k, dy);
         load8(a.E_raw + (size_t)r * a.d, k, x);
         load8(a.gamma, k, ga);
-        dropout_scale8(seed, IMMTSF_SITE_TTF_DROPOUT, (uint64_t)r * d8 + k, a.thr, inv_keep, ks);
+        if (TAG && a.thr) keep_of8(x, inv_keep, ks);
+        else dropout_scale8(seed, IMMTSF_SITE_TTF_DROPOUT, (uint64_t)r * d8 + k, a.thr, inv_keep, ks);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const float dye = dy[e] * ks[e];
@@ -847,7 +870,7 @@ __device__ __forceinline__ void lds8(const float* row, int k, float (&o)[8]) {
   const float4 b = reinterpret_cast<const float4*>(row)[2 * k + 1];
   o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
 }
-template <int NC>
+template <int NC, bool TAG>
 __global__ void __launch_bounds__(128) recavg_bwd_rows_s_kernel(const PoolArgs a) {
   extern __shared__ __align__(128) float s_ring[];
   __shared__ float s_acc[2 * 1024];  // dgamma | dbeta of this CTA
@@ -899,7 +922,8 @@ __global__ void __launch_bounds__(128) recavg_bwd_rows_s_kernel(const PoolArgs a
         lds8(sdy, k, dy);
         lds8(sx, k, x);
         load8(a.gamma, k, ga);
-        dropout_scale8(seed, IMMTSF_SITE_TTF_DROPOUT, (uint64_t)r * d8 + k, a.thr, inv_keep, ks);
+        if (TAG && a.thr) keep_of8(x, inv_keep, ks);
+        else dropout_scale8(seed, IMMTSF_SITE_TTF_DROPOUT, (uint64_t)r * d8 + k, a.thr, inv_keep, ks);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const float dye = dy[e] * ks[e];
@@ -946,15 +970,20 @@ __global__ void __launch_bounds__(128) recavg_bwd_rows_s_kernel(const PoolArgs a
   }
 }
 
-template <int NC>
-static void launch_rows_s(const PoolArgs& a, int want, cudaStream_t st) {
+template <int NC, bool TAG>
+static void launch_rows_s2(const PoolArgs& a, int want, cudaStream_t st) {
   const size_t smem = (size_t)4 * 4 * a.d * sizeof(float);
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(recavg_bwd_rows_s_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 4 * 1024 * (int)sizeof(float));
+    cudaFuncSetAttribute(recavg_bwd_rows_s_kernel<NC, TAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 4 * 1024 * (int)sizeof(float));
     attr = true;
   }
-  recavg_bwd_rows_s_kernel<NC><<<resident_grid((const void*)recavg_bwd_rows_s_kernel<NC>, 128, smem, want, 4), 128, smem, st>>>(a);
+  recavg_bwd_rows_s_kernel<NC, TAG><<<resident_grid((const void*)recavg_bwd_rows_s_kernel<NC, TAG>, 128, smem, want, 4), 128, smem, st>>>(a);
+}
+template <int NC>
+static void launch_rows_s(const PoolArgs& a, int want, cudaStream_t st) {
+  if (a.maskbit) launch_rows_s2<NC, true>(a, want, st);
+  else launch_rows_s2<NC, false>(a, want, st);
 }
 
 // ------------------------------------------------------------------ backward in ONE launch (short prediction windows)
@@ -974,7 +1003,7 @@ __device__ __forceinline__ void sts8(float* row, int k, const float (&v)[8]) {
   reinterpret_cast<float4*>(row)[2 * k] = make_float4(v[0], v[1], v[2], v[3]);
   reinterpret_cast<float4*>(row)[2 * k + 1] = make_float4(v[4], v[5], v[6], v[7]);
 }
-template <int NC, int NTN>
+template <int NC, int NTN, bool TAG>
 __global__ void __launch_bounds__(256, 2) recavg_bwd_fused_kernel(const PoolArgs a) {
   static_assert(NTN == 4 || NTN == 8, "notes per pass");
   extern __shared__ __align__(128) float s_dyn[];  // s_g [T][d] | s_x [8 warps][d]
@@ -1041,7 +1070,8 @@ __global__ void __launch_bounds__(256, 2) recavg_bwd_fused_kernel(const PoolArgs
           lds8(sg, k, dy);
           lds8(s_xw, k, x);
           load8(a.gamma, k, ga);
-          dropout_scale8(seed, IMMTSF_SITE_TTF_DROPOUT, (uint64_t)r * d8 + k, a.thr, inv_keep, ks);
+          if (TAG && a.thr) keep_of8(x, inv_keep, ks);
+          else dropout_scale8(seed, IMMTSF_SITE_TTF_DROPOUT, (uint64_t)r * d8 + k, a.thr, inv_keep, ks);
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             const float dye = dy[e] * ks[e];
@@ -1177,15 +1207,29 @@ __global__ void __launch_bounds__(256, 2) recavg_bwd_fused_kernel(const PoolArgs
   }
 }
 
-template <int NC, int NTN>
-static void launch_bwd_fused(const PoolArgs& a, cudaStream_t st) {
+template <int NC, int NTN, bool TAG>
+static void launch_bwd_fused2(const PoolArgs& a, cudaStream_t st) {
   const size_t smem = (size_t)(a.T + 8) * a.d * sizeof(float);
   static size_t smem_set = 0;
   if (smem + 4096 > 48 * 1024 && smem > smem_set) {
-    cudaFuncSetAttribute(recavg_bwd_fused_kernel<NC, NTN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(recavg_bwd_fused_kernel<NC, NTN, TAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     smem_set = smem;
   }
-  recavg_bwd_fused_kernel<NC, NTN><<<resident_grid((const void*)recavg_bwd_fused_kernel<NC, NTN>, 256, smem, a.B, 2), 256, smem, st>>>(a);
+  recavg_bwd_fused_kernel<NC, NTN, TAG><<<resident_grid((const void*)recavg_bwd_fused_kernel<NC, NTN, TAG>, 256, smem, a.B, 2), 256, smem, st>>>(a);
+}
+template <int NC, int NTN>
+static void launch_bwd_fused(const PoolArgs& a, cudaStream_t st) {
+  if (a.maskbit) launch_bwd_fused2<NC, NTN, true>(a, st);
+  else launch_bwd_fused2<NC, NTN, false>(a, st);
+}
+
+// Keep flags in the LSB of E_raw (experimental, see tag_keep): decided from what BOTH entry points see, so that the forward
+// and the backward of one step agree; read per call (tests A/B the two conventions inside one process).
+static int recavg_maskbit(int d, int N_max) {
+  const char* e = getenv("IMMTSF_RECAVG_MASKBIT");
+  if (!e || atoi(e) == 0) return 0;
+  const char* t = getenv("IMMTSF_RECAVG_TMA");
+  return rowwarp_nc(d) > 0 && N_max <= 32 && !(t && t[0] == '0');
 }
 
 static int pool_geometry(int d, int& nch, int& threads) {
@@ -1213,6 +1257,7 @@ extern "C" int immtsf_recavg_pool_fwd(const float* Vp, int ldv, const float* tau
   a.Vp = Vp; a.ldv = ldv; a.tau = tau_flat; a.offsets = offsets; a.t_hat = t_hat; a.t_bstride = t_hat_bstride;
   a.log_sigma = log_sigma; a.gamma = gamma; a.beta = beta; a.B = B; a.T = T; a.d = d; a.eps = eps;
   a.thr = drop_thr; a.seed = make_seed(seed); a.E_drop = E_drop; a.E_raw = E_raw; a.mean = mean; a.rstd = rstd; a.wsum = wsum;
+  a.maskbit = recavg_maskbit(d, N_max);
   cudaStream_t st = (cudaStream_t)stream;
   // Short segments (Time-IMM: a handful of notes per window): one warp per query time, the 8 warps of a CTA share
   // the segment through L1.  Long segments: the CTA-tile kernel streams each V' row once per 8 query times.
@@ -1237,6 +1282,7 @@ extern "C" int immtsf_recavg_pool_fwd(const float* Vp, int ldv, const float* tau
       IMMTSF_CHECK_LAUNCH("recavg_pool_fwd_s");
       return IMMTSF_OK;
     }
+    IMMTSF_REQUIRE(!a.maskbit, "recavg_pool_fwd: IMMTSF_RECAVG_MASKBIT needs the staged kernel (16B-aligned V', ld %% 4 == 0)");
 #define FWD_W(NCV)                                                                    \
   do {                                                                                \
     if (tpw == 3) recavg_pool_fwd_w_kernel<NCV, 3><<<gridw, 256, 0, st>>>(a);         \
@@ -1251,6 +1297,7 @@ extern "C" int immtsf_recavg_pool_fwd(const float* Vp, int ldv, const float* tau
     IMMTSF_CHECK_LAUNCH("recavg_pool_fwd_w");
     return IMMTSF_OK;
   }
+  IMMTSF_REQUIRE(!a.maskbit, "recavg_pool_fwd: IMMTSF_RECAVG_MASKBIT needs 16B-aligned gamma / beta / E_drop / E_raw");
   const int TT = 8 / nch;
   dim3 grid(ceil_div(T, TT), B);
   if (nch == 1) recavg_pool_fwd_kernel<1><<<grid, threads, 0, st>>>(a);
@@ -1281,6 +1328,7 @@ extern "C" int immtsf_recavg_pool_bwd(const float* dE_drop, const float* E_raw, 
   a.rstd = const_cast<float*>(rstd); a.wsum = const_cast<float*>(wsum);
   a.dE_drop = dE_drop; a.dVp = dVp; a.lddv = lddv; a.dgamma = dgamma; a.dbeta = dbeta; a.dlog_sigma = dlog_sigma;
   a.dS = dS; a.N_max = N_max;
+  a.maskbit = recavg_maskbit(d, N_max);
   cudaStream_t st = (cudaStream_t)stream;
   const int nc = rowwarp_nc(d);
   // Short prediction windows and segments (N_max <= 32: at N <= 64, T 28 the two-kernel path measured 272 us against 339 us,
@@ -1308,15 +1356,18 @@ extern "C" int immtsf_recavg_pool_bwd(const float* dE_drop, const float* E_raw, 
       else if (nc == 3) launch_rows_s<3>(a, want, st);
       else launch_rows_s<4>(a, want, st);
     } else {
-#define ROWS_W(NCV) recavg_bwd_rows_w_kernel<NCV><<<resident_grid((const void*)recavg_bwd_rows_w_kernel<NCV>, 128, 0, want, 4), 128, 0, st>>>(a)
+#define ROWS_W2(NCV, TAGV) recavg_bwd_rows_w_kernel<NCV, TAGV><<<resident_grid((const void*)recavg_bwd_rows_w_kernel<NCV, TAGV>, 128, 0, want, 4), 128, 0, st>>>(a)
+#define ROWS_W(NCV) do { if (a.maskbit) ROWS_W2(NCV, true); else ROWS_W2(NCV, false); } while (0)
     if (nc == 1) ROWS_W(1);
     else if (nc == 2) ROWS_W(2);
     else if (nc == 3) ROWS_W(3);
     else ROWS_W(4);
 #undef ROWS_W
+#undef ROWS_W2
     }
     IMMTSF_CHECK_LAUNCH("recavg_bwd_rows_w");
   } else {
+    IMMTSF_REQUIRE(!a.maskbit, "recavg_pool_bwd: IMMTSF_RECAVG_MASKBIT needs 16B-aligned gamma / dE_drop / E_raw");
     const int TT = 8 / nch;
     dim3 grid1(ceil_div(T, TT), B);
     if (nch == 1) recavg_bwd_rows_kernel<1><<<grid1, threads, 0, st>>>(a);

@@ -1,0 +1,67 @@
+"""GPU checks of kernel variants that are compiled in but OFF by default because they have not been measured on a B200
+yet (written when the round's GPU budget was spent).  They run only with IMMTSF_EXPERIMENTAL=1, so an unmeasured variant
+can never turn the default suite red:
+
+    IMMTSF_EXPERIMENTAL=1 python -m pytest tests/test_gpu_experimental.py -m gpu -q
+
+Each test A/Bs a variant against the default path of the same library inside one process (the switches are read per call).
+"""
+import os
+
+import pytest
+import torch
+
+import gpu_common as G
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("IMMTSF_EXPERIMENTAL") != "1", reason="set IMMTSF_EXPERIMENTAL=1")]
+
+
+def _recavg_step(B, N, T, d, p, seed=31):
+    from immtsf import ops
+
+    notes, tau, t_hat, _, _ = G.synth_batch(B, N, T, d, 1, seed, no_note=B > 2)
+    r = ops.csr_build(notes.cuda(), tau.cuda())
+    t_hat = t_hat.cuda()
+    g = torch.Generator().manual_seed(3)
+    ls = torch.tensor(-0.3, device="cuda")
+    gamma = (1.0 + 0.1 * torch.randn(d, generator=g)).cuda()
+    beta = (0.1 * torch.randn(d, generator=g)).cuda()
+    thr, sd = ops.drop_thr(p), 991
+    dE = torch.randn(B, T, d, generator=g).cuda()
+
+    def run():
+        E_drop, E_raw, mean, rstd, wsum = ops.recavg_pool_fwd(r.emb_flat, r, t_hat, ls, gamma, beta, T, d, thr, sd, True)
+        grads = ops.recavg_pool_bwd(dE.view_as(E_drop), E_raw, mean, rstd, wsum, r.emb_flat, r, t_hat, ls, gamma, T, d, thr, sd)
+        torch.cuda.synchronize()
+        return E_drop.clone(), E_raw.clone(), [x.clone() for x in grads]
+
+    return run
+
+
+@pytest.mark.parametrize("fused", ["8", "0"])
+@pytest.mark.parametrize("B,N,T,d,p", [(5, 6, 7, 64, 0.1), (64, 16, 24, 768, 0.1), (300, 3, 16, 1024, 0.2), (9, 30, 40, 256, 0.3),
+                                         (3, 1, 1, 8, 0.5), (17, 16, 24, 768, 0.0)])
+def test_recavg_keep_flags_in_e_raw_lsb(B, N, T, d, p, fused, monkeypatch):
+    """IMMTSF_RECAVG_MASKBIT=1: the forward stores every element's dropout keep flag in the mantissa LSB of the saved
+    E_raw and the backward reads it back instead of regenerating the Philox mask.  E_drop must be bit-identical, E_raw within
+    one ulp, every gradient within 2e-5 of the default path (same mask, x perturbed by <= 1 ulp); with both backward
+    variants (one launch / two kernels; T 40 exercises the two-kernel path in both)."""
+    monkeypatch.setenv("IMMTSF_RECAVG_FUSED_BWD", fused)
+    run = _recavg_step(B, N, T, d, p)
+    monkeypatch.setenv("IMMTSF_RECAVG_MASKBIT", "0")
+    E0, X0, g0 = run()
+    monkeypatch.setenv("IMMTSF_RECAVG_MASKBIT", "1")
+    E1, X1, g1 = run()
+    assert torch.equal(E0, E1)
+    ulp = (X0.view(torch.int32) - X1.view(torch.int32)).abs().max().item()
+    assert ulp <= 1, ulp
+    if p > 0:
+        kept = (X1.view(torch.int32) & 1).bool()
+        # a kept element of E_drop is zero only if LayerNorm's output is exactly zero there
+        assert torch.equal(kept | (E1 == 0), torch.ones_like(kept)) and (kept & (E1 != 0)).sum() == (E1 != 0).sum()
+    for name, ref, got in zip(("dVp", "dgamma", "dbeta", "dlog_sigma"), g0, g1):
+        assert torch.isfinite(got).all(), name
+        den = max(ref.abs().max().item(), 1e-6)
+        err = (got - ref).abs().max().item()
+        assert err <= 2e-5 * den, f"{name}: err {err:.3e} vs max {den:.3e}"
