@@ -1003,7 +1003,10 @@ __device__ __forceinline__ void sts8(float* row, int k, const float (&v)[8]) {
   reinterpret_cast<float4*>(row)[2 * k] = make_float4(v[0], v[1], v[2], v[3]);
   reinterpret_cast<float4*>(row)[2 * k + 1] = make_float4(v[4], v[5], v[6], v[7]);
 }
-template <int NC, int NTN, bool TAG>
+// SKIPQ (experimental, IMMTSF_RECAVG_SKIPQ=1, default off until measured): c_nt = w_nt * 2 (delta/sigma)^2 is exactly 0 wherever
+// tau_n >= t_hat_t, i.e. for every note that is not older than the whole prediction window (Time-IMM: ~6/7 of the notes); a
+// half pass (4 notes) whose c_nt are ALL zero skips its Q_n accumulators -- half of its FFMAs -- and contributes exact zeros.
+template <int NC, int NTN, bool TAG, bool SKIPQ>
 __global__ void __launch_bounds__(256, 2) recavg_bwd_fused_kernel(const PoolArgs a) {
   static_assert(NTN == 4 || NTN == 8, "notes per pass");
   extern __shared__ __align__(128) float s_dyn[];  // s_g [T][d] | s_x [8 warps][d]
@@ -1149,6 +1152,15 @@ __global__ void __launch_bounds__(256, 2) recavg_bwd_fused_kernel(const PoolArgs
         for (int tt = 0; tt < T; ++tt) sc_term = fmaf(s_c[tt][threadIdx.x], s_dw[tt], sc_term);
         dls += (double)sc_term;
       }
+      bool need_lo = true, need_hi = true;  // warp-uniform: does any (t, note) of the half pass have c_nt != 0 ?
+      if (SKIPQ) {
+        const float4 z0 = lane < T ? *reinterpret_cast<const float4*>(&s_c[lane][0]) : f4_zero();
+        need_lo = __any_sync(0xffffffffu, z0.x != 0.f || z0.y != 0.f || z0.z != 0.f || z0.w != 0.f);
+        if (NTN == 8) {
+          const float4 z1 = lane < T ? *reinterpret_cast<const float4*>(&s_c[lane][NTN - 4]) : f4_zero();
+          need_hi = __any_sync(0xffffffffu, z1.x != 0.f || z1.y != 0.f || z1.z != 0.f || z1.w != 0.f);
+        }
+      }
       if ((int)threadIdx.x < d4) {
         float4 accw[NTN], accc[NTN];
 #pragma unroll
@@ -1157,17 +1169,34 @@ __global__ void __launch_bounds__(256, 2) recavg_bwd_fused_kernel(const PoolArgs
         const bool half = NTN == 8 && ncnt <= 4;  // half-empty pass (CTA-uniform): skip the empty note slots
         for (int tt = 0; tt < T; ++tt) {
           const float4 g = gp[(size_t)tt * d4];
-          const float4 w0 = *reinterpret_cast<const float4*>(&s_w[tt][0]), c0 = *reinterpret_cast<const float4*>(&s_c[tt][0]);
-          f4_fma(accw[0], w0.x, g); f4_fma(accc[0], c0.x, g);
-          f4_fma(accw[1], w0.y, g); f4_fma(accc[1], c0.y, g);
-          f4_fma(accw[2], w0.z, g); f4_fma(accc[2], c0.z, g);
-          f4_fma(accw[3], w0.w, g); f4_fma(accc[3], c0.w, g);
-          if (NTN == 8 && !half) {
-            const float4 w1 = *reinterpret_cast<const float4*>(&s_w[tt][NTN - 4]), c1 = *reinterpret_cast<const float4*>(&s_c[tt][NTN - 4]);
-            f4_fma(accw[NTN - 4], w1.x, g); f4_fma(accc[NTN - 4], c1.x, g);
-            f4_fma(accw[NTN - 3], w1.y, g); f4_fma(accc[NTN - 3], c1.y, g);
-            f4_fma(accw[NTN - 2], w1.z, g); f4_fma(accc[NTN - 2], c1.z, g);
-            f4_fma(accw[NTN - 1], w1.w, g); f4_fma(accc[NTN - 1], c1.w, g);
+          if (!SKIPQ) {
+            const float4 w0 = *reinterpret_cast<const float4*>(&s_w[tt][0]), c0 = *reinterpret_cast<const float4*>(&s_c[tt][0]);
+            f4_fma(accw[0], w0.x, g); f4_fma(accc[0], c0.x, g);
+            f4_fma(accw[1], w0.y, g); f4_fma(accc[1], c0.y, g);
+            f4_fma(accw[2], w0.z, g); f4_fma(accc[2], c0.z, g);
+            f4_fma(accw[3], w0.w, g); f4_fma(accc[3], c0.w, g);
+            if (NTN == 8 && !half) {
+              const float4 w1 = *reinterpret_cast<const float4*>(&s_w[tt][NTN - 4]), c1 = *reinterpret_cast<const float4*>(&s_c[tt][NTN - 4]);
+              f4_fma(accw[NTN - 4], w1.x, g); f4_fma(accc[NTN - 4], c1.x, g);
+              f4_fma(accw[NTN - 3], w1.y, g); f4_fma(accc[NTN - 3], c1.y, g);
+              f4_fma(accw[NTN - 2], w1.z, g); f4_fma(accc[NTN - 2], c1.z, g);
+              f4_fma(accw[NTN - 1], w1.w, g); f4_fma(accc[NTN - 1], c1.w, g);
+            }
+          } else {
+            const float4 w0 = *reinterpret_cast<const float4*>(&s_w[tt][0]);
+            f4_fma(accw[0], w0.x, g); f4_fma(accw[1], w0.y, g); f4_fma(accw[2], w0.z, g); f4_fma(accw[3], w0.w, g);
+            if (need_lo) {
+              const float4 c0 = *reinterpret_cast<const float4*>(&s_c[tt][0]);
+              f4_fma(accc[0], c0.x, g); f4_fma(accc[1], c0.y, g); f4_fma(accc[2], c0.z, g); f4_fma(accc[3], c0.w, g);
+            }
+            if (NTN == 8 && !half) {
+              const float4 w1 = *reinterpret_cast<const float4*>(&s_w[tt][NTN - 4]);
+              f4_fma(accw[NTN - 4], w1.x, g); f4_fma(accw[NTN - 3], w1.y, g); f4_fma(accw[NTN - 2], w1.z, g); f4_fma(accw[NTN - 1], w1.w, g);
+              if (need_hi) {
+                const float4 c1 = *reinterpret_cast<const float4*>(&s_c[tt][NTN - 4]);
+                f4_fma(accc[NTN - 4], c1.x, g); f4_fma(accc[NTN - 3], c1.y, g); f4_fma(accc[NTN - 2], c1.z, g); f4_fma(accc[NTN - 1], c1.w, g);
+              }
+            }
           }
         }
         // every V' row of the pass is requested before the first store (stores to dV' may alias as far as the compiler
@@ -1207,20 +1236,23 @@ __global__ void __launch_bounds__(256, 2) recavg_bwd_fused_kernel(const PoolArgs
   }
 }
 
-template <int NC, int NTN, bool TAG>
+template <int NC, int NTN, bool TAG, bool SKIPQ>
 static void launch_bwd_fused2(const PoolArgs& a, cudaStream_t st) {
   const size_t smem = (size_t)(a.T + 8) * a.d * sizeof(float);
   static size_t smem_set = 0;
   if (smem + 4096 > 48 * 1024 && smem > smem_set) {
-    cudaFuncSetAttribute(recavg_bwd_fused_kernel<NC, NTN, TAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(recavg_bwd_fused_kernel<NC, NTN, TAG, SKIPQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     smem_set = smem;
   }
-  recavg_bwd_fused_kernel<NC, NTN, TAG><<<resident_grid((const void*)recavg_bwd_fused_kernel<NC, NTN, TAG>, 256, smem, a.B, 2), 256, smem, st>>>(a);
+  recavg_bwd_fused_kernel<NC, NTN, TAG, SKIPQ>
+      <<<resident_grid((const void*)recavg_bwd_fused_kernel<NC, NTN, TAG, SKIPQ>, 256, smem, a.B, 2), 256, smem, st>>>(a);
 }
 template <int NC, int NTN>
 static void launch_bwd_fused(const PoolArgs& a, cudaStream_t st) {
-  if (a.maskbit) launch_bwd_fused2<NC, NTN, true>(a, st);
-  else launch_bwd_fused2<NC, NTN, false>(a, st);
+  const char* e = getenv("IMMTSF_RECAVG_SKIPQ");  // read per call (A/B inside one process)
+  const bool skipq = e && atoi(e) != 0;
+  if (a.maskbit) { if (skipq) launch_bwd_fused2<NC, NTN, true, true>(a, st); else launch_bwd_fused2<NC, NTN, true, false>(a, st); }
+  else { if (skipq) launch_bwd_fused2<NC, NTN, false, true>(a, st); else launch_bwd_fused2<NC, NTN, false, false>(a, st); }
 }
 
 // Keep flags in the LSB of E_raw (experimental, see tag_keep): decided from what BOTH entry points see, so that the forward

@@ -65,3 +65,38 @@ def test_recavg_keep_flags_in_e_raw_lsb(B, N, T, d, p, fused, monkeypatch):
         den = max(ref.abs().max().item(), 1e-6)
         err = (got - ref).abs().max().item()
         assert err <= 2e-5 * den, f"{name}: err {err:.3e} vs max {den:.3e}"
+
+
+@pytest.mark.parametrize("maskbit", ["0", "1"])
+@pytest.mark.parametrize("history", [7.0, 0.4, 1.2])
+@pytest.mark.parametrize("B,N,T,d,p", [(64, 16, 24, 768, 0.1), (5, 6, 7, 64, 0.1), (9, 30, 24, 256, 0.0), (3, 1, 1, 8, 0.5)])
+def test_recavg_fused_bwd_skips_zero_sensitivity_passes(B, N, T, d, p, history, maskbit, monkeypatch):
+    """IMMTSF_RECAVG_SKIPQ=1: half passes (4 notes) of the one-launch backward whose c_nt = dw_nt/dlog_sigma are all exactly
+    zero (tau_n >= every t_hat_t) skip the Q_n accumulators.  Only exact zeros are skipped, so dV' is bit-identical and
+    dlog_sigma differs at most in summation order.  history 7: most notes are newer than the window (c = 0); 0.4 and 1.2:
+    most or many notes are older than some query time (little or nothing skipped)."""
+    from immtsf import ops
+
+    monkeypatch.setenv("IMMTSF_RECAVG_MASKBIT", maskbit)
+    outs = {}
+    for notes_per_pass in ("8", "4"):
+        monkeypatch.setenv("IMMTSF_RECAVG_FUSED_BWD", notes_per_pass)
+        notes, tau, t_hat, _, _ = G.synth_batch(B, N, T, d, 1, 77, history=history, pred=1.0, no_note=B > 2)
+        r = ops.csr_build(notes.cuda(), tau.cuda())
+        t_hat = t_hat.cuda()
+        g = torch.Generator().manual_seed(5)
+        ls = torch.tensor(0.2, device="cuda")
+        gamma = (1.0 + 0.1 * torch.randn(d, generator=g)).cuda()
+        beta = torch.zeros(d, device="cuda")
+        thr, sd = ops.drop_thr(p), 17
+        E_drop, E_raw, mean, rstd, wsum = ops.recavg_pool_fwd(r.emb_flat, r, t_hat, ls, gamma, beta, T, d, thr, sd, True)
+        dE = torch.randn(B, T, d, generator=g).cuda().view_as(E_drop)
+        for skip in ("0", "1"):
+            monkeypatch.setenv("IMMTSF_RECAVG_SKIPQ", skip)
+            outs[skip] = [x.clone() for x in ops.recavg_pool_bwd(dE, E_raw, mean, rstd, wsum, r.emb_flat, r, t_hat, ls, gamma, T, d, thr, sd)]
+        torch.cuda.synchronize()
+        assert torch.equal(outs["0"][0], outs["1"][0]), (notes_per_pass, "dVp")
+        for name, ref, got in zip(("dgamma", "dbeta"), outs["0"][1:3], outs["1"][1:3]):  # float atomics across CTAs: order varies
+            assert (ref - got).abs().max().item() <= 1e-5 * max(ref.abs().max().item(), 1e-6), (notes_per_pass, name)
+        ref, got = outs["0"][3], outs["1"][3]
+        assert abs(float(ref) - float(got)) <= 1e-6 * max(abs(float(ref)), 1e-6), (notes_per_pass, float(ref), float(got))
