@@ -782,6 +782,172 @@ static void launch_fwd_s(const PoolArgs& a, int tpw, int T, int B, int RS, size_
   else { if (full) launch_fwd_s2<NC, 1, 3, true>(a, grid, RS, smem, st); else launch_fwd_s2<NC, 1, 3, false>(a, grid, RS, smem, st); }
 }
 
+// ------------------------------------------------------------------ persistent forward, segments double-buffered
+// Experimental (IMMTSF_RECAVG_FWD_PERSIST=1, default off until measured).  recavg_pool_fwd_s_kernel runs one CTA per (sample,
+// tile of 8*TPW query times): the bulk copy of the segment is issued, waited for and consumed by the same short-lived CTA, so
+// the copy latency is only hidden by the other CTA of the SM (ncu: long-scoreboard + barrier stalls, 60 % issue utilisation).
+// Here 2 CTAs per SM stay resident and walk the work items (sample, tile) with a two-stage ring: the copy of item i + grid is
+// posted before item i is touched and lands while item i is pooled and normalised.  Same arithmetic, lane ownership and
+// bank-conflict-free half swap as the staged kernel.  Requires every segment to fit one stage (N_max <= RS <= 16).
+// smem: s_v [2][RS][d].  grid = resident CTAs, 256 threads.
+template <int NC, int TPW, bool FULL, bool TAG>
+__global__ void __launch_bounds__(256, 2) recavg_pool_fwd_p_kernel(const PoolArgs a, int RS, int ntiles) {
+  extern __shared__ __align__(128) float s_v[];
+  __shared__ __align__(8) unsigned long long s_bar[2];
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  const int d = a.d, d8 = d >> 3;
+  const uint32_t bar0 = rs_smem_u32(&s_bar[0]), sv = rs_smem_u32(s_v);
+  const uint32_t row_bytes = (uint32_t)d * 4u, stage_bytes = (uint32_t)RS * row_bytes;
+  if (threadIdx.x == 0) { rs_mbar_init(bar0, 1); rs_mbar_init(bar0 + 8u, 1); }
+  __syncthreads();
+  const float inv_sigma = 1.f / expf(__ldg(a.log_sigma));
+  const float inv_keep = inv_keep_from_thr(a.thr);
+  const uint64_t seed = resolve_seed(a.seed);
+  const float inv_d = 1.f / (float)a.d;
+  const int p = (lane >> 2) & 1;
+  const int nitems = a.B * ntiles;
+  // thread 0 posts the copy of one item's segment into a stage (empty segments still complete the phase: expect_tx 0)
+  auto post = [&](int item, int stage) {
+    const int b = item / ntiles;
+    const int nb = a.offsets[b], cnt = a.offsets[b + 1] - nb;
+    const uint32_t bar = bar0 + 8u * (uint32_t)stage, dst = sv + (uint32_t)stage * stage_bytes;
+    rs_mbar_expect_tx(bar, (uint32_t)cnt * row_bytes);
+    if (a.ldv == d) {
+      if (cnt > 0) rs_bulk_g2s(dst, a.Vp + (size_t)nb * a.ldv, (uint32_t)cnt * row_bytes, bar);
+    } else {
+      for (int j = 0; j < cnt; ++j) rs_bulk_g2s(dst + (uint32_t)j * row_bytes, a.Vp + (size_t)(nb + j) * a.ldv, row_bytes, bar);
+    }
+  };
+  if (threadIdx.x == 0 && (int)blockIdx.x < nitems) post(blockIdx.x, 0);
+  int it = 0;
+  for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
+    const int st = it & 1;
+    const int b = item / ntiles, tile = item - b * ntiles;
+    const int tb = tile * (8 * TPW) + wrp;
+    const bool active = tb < a.T;
+    const int nb = a.offsets[b], cnt = a.offsets[b + 1] - nb;
+    // stage st ^ 1 was read by the previous item; every warp passed the barrier behind that item's pooling loop
+    if (threadIdx.x == 0 && item + (int)gridDim.x < nitems) post(item + gridDim.x, st ^ 1);
+    float th[TPW], wl[TPW];
+    float4 accA[TPW][NC], accB[TPW][NC];
+    const float tn = lane < cnt ? __ldg(a.tau + nb + lane) : 0.f;
+#pragma unroll
+    for (int q = 0; q < TPW; ++q) {
+      th[q] = tb + 8 * q < a.T ? a.t_hat[(size_t)b * a.t_bstride + tb + 8 * q] : 0.f;
+      const float r = fmaxf(th[q] - tn, 0.f) * inv_sigma;
+      wl[q] = lane < cnt ? expf(-(r * r)) : 0.f;
+#pragma unroll
+      for (int i = 0; i < NC; ++i) { accA[q][i] = f4_zero(); accB[q][i] = f4_zero(); }
+    }
+    rs_mbar_wait(bar0 + 8u * (uint32_t)st, (uint32_t)((it >> 1) & 1));
+    if (active) {
+      const float* base = s_v + (size_t)st * RS * d;
+      for (int j = 0; j < cnt; ++j) {
+        const float4* row = reinterpret_cast<const float4*>(base + (size_t)j * d);
+        float4 vA[NC], vB[NC];
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+          const int k = lane + 32 * i;
+          if (FULL || k < d8) { vA[i] = row[2 * k + p]; vB[i] = row[2 * k + 1 - p]; }
+          else { vA[i] = f4_zero(); vB[i] = f4_zero(); }
+        }
+#pragma unroll
+        for (int q = 0; q < TPW; ++q) {
+          const float w0 = __shfl_sync(0xffffffffu, wl[q], j);
+#pragma unroll
+          for (int i = 0; i < NC; ++i) { f4_fma_s(accA[q][i], w0, vA[i]); f4_fma_s(accB[q][i], w0, vB[i]); }
+        }
+      }
+    }
+    __syncthreads();  // stage st is free again (the copy of item + 2 * grid is posted one iteration from now)
+    if (!active) continue;
+#pragma unroll
+    for (int q = 0; q < TPW; ++q) {
+      const int t = tb + 8 * q;
+      if (t >= a.T) break;
+      const float wsum = warp_sum(wl[q]);
+      const float inv_den = 1.f / fmaxf(wsum, 1e-6f);  // E_raw = E_wsum / clamp_min(denom, 1e-6)
+      float sm = 0.f;
+#pragma unroll
+      for (int i = 0; i < NC; ++i) {  // chunks beyond d are exactly 0
+        float4& A = accA[q][i];
+        float4& Bv = accB[q][i];
+        A.x *= inv_den; A.y *= inv_den; A.z *= inv_den; A.w *= inv_den;
+        Bv.x *= inv_den; Bv.y *= inv_den; Bv.z *= inv_den; Bv.w *= inv_den;
+        sm += (A.x + A.y) + (A.z + A.w) + (Bv.x + Bv.y) + (Bv.z + Bv.w);
+      }
+      const float mu = warp_sum(sm) * inv_d;
+      float qq = 0.f;
+#pragma unroll
+      for (int i = 0; i < NC; ++i)
+        if (FULL || lane + 32 * i < d8) {
+          const float4 A = accA[q][i], Bv = accB[q][i];
+          qq = fmaf(A.x - mu, A.x - mu, qq); qq = fmaf(A.y - mu, A.y - mu, qq); qq = fmaf(A.z - mu, A.z - mu, qq); qq = fmaf(A.w - mu, A.w - mu, qq);
+          qq = fmaf(Bv.x - mu, Bv.x - mu, qq); qq = fmaf(Bv.y - mu, Bv.y - mu, qq); qq = fmaf(Bv.z - mu, Bv.z - mu, qq); qq = fmaf(Bv.w - mu, Bv.w - mu, qq);
+        }
+      const float rs = 1.f / sqrtf(warp_sum(qq) * inv_d + a.eps);
+      const size_t rowi = (size_t)b * a.T + t;
+#pragma unroll
+      for (int i = 0; i < NC; ++i) {
+        const int k = lane + 32 * i;
+        if (FULL || k < d8) {
+          float ks[8];
+          dropout_scale8(seed, IMMTSF_SITE_TTF_DROPOUT, rowi * d8 + k, a.thr, inv_keep, ks);
+          const int oA = 2 * k + p, oB = 2 * k + 1 - p;  // float4 index of each half within the row
+          const float4 gA = __ldg(reinterpret_cast<const float4*>(a.gamma) + oA), gB = __ldg(reinterpret_cast<const float4*>(a.gamma) + oB);
+          const float4 bA = __ldg(reinterpret_cast<const float4*>(a.beta) + oA), bB = __ldg(reinterpret_cast<const float4*>(a.beta) + oB);
+          const float4 A = accA[q][i], Bv = accB[q][i];
+          float4 kA, kB, yA, yB;
+          kA.x = p ? ks[4] : ks[0]; kA.y = p ? ks[5] : ks[1]; kA.z = p ? ks[6] : ks[2]; kA.w = p ? ks[7] : ks[3];
+          kB.x = p ? ks[0] : ks[4]; kB.y = p ? ks[1] : ks[5]; kB.z = p ? ks[2] : ks[6]; kB.w = p ? ks[3] : ks[7];
+          yA.x = ((A.x - mu) * rs * gA.x + bA.x) * kA.x; yA.y = ((A.y - mu) * rs * gA.y + bA.y) * kA.y;
+          yA.z = ((A.z - mu) * rs * gA.z + bA.z) * kA.z; yA.w = ((A.w - mu) * rs * gA.w + bA.w) * kA.w;
+          yB.x = ((Bv.x - mu) * rs * gB.x + bB.x) * kB.x; yB.y = ((Bv.y - mu) * rs * gB.y + bB.y) * kB.y;
+          yB.z = ((Bv.z - mu) * rs * gB.z + bB.z) * kB.z; yB.w = ((Bv.w - mu) * rs * gB.w + bB.w) * kB.w;
+          float4* eo = reinterpret_cast<float4*>(a.E_drop + rowi * a.d);
+          eo[oA] = yA;
+          eo[oB] = yB;
+          if (a.E_raw) {
+            float4* er = reinterpret_cast<float4*>(a.E_raw + rowi * a.d);
+            er[oA] = (TAG && a.thr) ? tag_keep4(A, kA) : A;
+            er[oB] = (TAG && a.thr) ? tag_keep4(Bv, kB) : Bv;
+          }
+        }
+      }
+      if (lane == 0) {
+        if (a.mean) a.mean[rowi] = mu;
+        if (a.rstd) a.rstd[rowi] = rs;
+        if (a.wsum) a.wsum[rowi] = wsum;
+      }
+    }
+  }
+}
+
+template <int NC, int TPW, bool FULL, bool TAG>
+static void launch_fwd_p2(const PoolArgs& a, int RS, int ntiles, cudaStream_t st) {
+  const size_t smem = (size_t)2 * RS * a.d * sizeof(float);
+  static size_t smem_set = 0;
+  if (smem + 1024 > 48 * 1024 && smem > smem_set) {
+    cudaFuncSetAttribute(recavg_pool_fwd_p_kernel<NC, TPW, FULL, TAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    smem_set = smem;
+  }
+  const int grid = resident_grid((const void*)recavg_pool_fwd_p_kernel<NC, TPW, FULL, TAG>, 256, smem, a.B * ntiles, 2);
+  recavg_pool_fwd_p_kernel<NC, TPW, FULL, TAG><<<grid, 256, smem, st>>>(a, RS, ntiles);
+}
+template <int NC>
+static void launch_fwd_p(const PoolArgs& a, int tpw, int RS, cudaStream_t st) {
+  const bool full = (a.d >> 3) == 32 * NC;
+  const int ntiles = ceil_div(a.T, 8 * tpw);
+#define FWD_P(TPWV)                                                                                                        \
+  do {                                                                                                                     \
+    if (full) { if (a.maskbit) launch_fwd_p2<NC, TPWV, true, true>(a, RS, ntiles, st); else launch_fwd_p2<NC, TPWV, true, false>(a, RS, ntiles, st); } \
+    else { if (a.maskbit) launch_fwd_p2<NC, TPWV, false, true>(a, RS, ntiles, st); else launch_fwd_p2<NC, TPWV, false, false>(a, RS, ntiles, st); }   \
+  } while (0)
+  if (tpw == 3) FWD_P(3);
+  else FWD_P(1);
+#undef FWD_P
+}
+
 // Backward phase 1 (LayerNorm backward of the pooled rows -> dS, d(den)), one warp per (sample, query time) row.
 template <int NC, bool TAG>
 __global__ void __launch_bounds__(128) recavg_bwd_rows_w_kernel(const PoolArgs a) {
@@ -1307,6 +1473,14 @@ extern "C" int immtsf_recavg_pool_fwd(const float* Vp, int ldv, const float* tau
       int tpw_s = (nc <= 3 && T > 16) ? 3 : 1;  // measured (profiles/r1_sweep_hbm_v4.json): T 24: 3 > 1 > 2; T 16: 1 > 2 > 3
       static const int tpw_env = []() { const char* e = getenv("IMMTSF_RECAVG_TPW"); return e ? atoi(e) : 0; }();
       if (tpw_env >= 1 && tpw_env <= 3 && nc <= 3) tpw_s = tpw_env;
+      const char* pe = getenv("IMMTSF_RECAVG_FWD_PERSIST");  // experimental, read per call (A/B inside one process)
+      if (pe && atoi(pe) != 0 && nc <= 3 && N_max <= RS && tpw_s != 2) {
+        if (nc == 1) launch_fwd_p<1>(a, tpw_s, RS, st);
+        else if (nc == 2) launch_fwd_p<2>(a, tpw_s, RS, st);
+        else launch_fwd_p<3>(a, tpw_s, RS, st);
+        IMMTSF_CHECK_LAUNCH("recavg_pool_fwd_p");
+        return IMMTSF_OK;
+      }
       if (nc == 1) launch_fwd_s<1>(a, tpw_s, T, B, RS, smem_s, st);
       else if (nc == 2) launch_fwd_s<2>(a, tpw_s, T, B, RS, smem_s, st);
       else if (nc == 3) launch_fwd_s<3>(a, tpw_s, T, B, RS, smem_s, st);

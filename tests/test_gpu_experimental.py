@@ -100,3 +100,36 @@ def test_recavg_fused_bwd_skips_zero_sensitivity_passes(B, N, T, d, p, history, 
             assert (ref - got).abs().max().item() <= 1e-5 * max(ref.abs().max().item(), 1e-6), (notes_per_pass, name)
         ref, got = outs["0"][3], outs["1"][3]
         assert abs(float(ref) - float(got)) <= 1e-6 * max(abs(float(ref)), 1e-6), (notes_per_pass, float(ref), float(got))
+
+
+@pytest.mark.parametrize("maskbit", ["0", "1"])
+@pytest.mark.parametrize("B,N,T,d,p", [(64, 16, 24, 768, 0.1), (5, 6, 7, 64, 0.1), (300, 3, 16, 1024, 0.2), (150, 16, 32, 512, 0.1),
+                                         (33, 12, 9, 256, 0.3), (700, 16, 24, 768, 0.0), (3, 1, 1, 8, 0.5)])
+def test_recavg_persistent_forward_is_bit_identical(B, N, T, d, p, maskbit, monkeypatch):
+    """IMMTSF_RECAVG_FWD_PERSIST=1: resident CTAs walk the (sample, query tile) items with a two-stage ring of bulk copies.
+    Same lane ownership and summation order as the staged kernel, so every output is bit-identical (B 700 x 1 tile and
+    B 150 x 2 tiles exceed the 296 resident CTAs: several items per CTA, both stages and both mbarrier parities in use;
+    d 1024 is outside the variant's range and must fall back)."""
+    from immtsf import ops
+
+    monkeypatch.setenv("IMMTSF_RECAVG_MASKBIT", maskbit)
+    notes, tau, t_hat, _, _ = G.synth_batch(B, N, T, d, 1, 123, no_note=B > 2)
+    r = ops.csr_build(notes.cuda(), tau.cuda())
+    t_hat = t_hat.cuda()
+    g = torch.Generator().manual_seed(9)
+    ls = torch.tensor(0.1, device="cuda")
+    gamma = (1.0 + 0.1 * torch.randn(d, generator=g)).cuda()
+    beta = (0.1 * torch.randn(d, generator=g)).cuda()
+    thr, sd = ops.drop_thr(p), 4242
+    outs = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("IMMTSF_RECAVG_FWD_PERSIST", mode)
+        for save in (True, False):
+            o = ops.recavg_pool_fwd(r.emb_flat, r, t_hat, ls, gamma, beta, T, d, thr, sd, save)
+            torch.cuda.synchronize()
+            outs[(mode, save)] = [None if x is None else x.clone() for x in o]
+    for save in (True, False):
+        for name, ref, got in zip(("E_drop", "E_raw", "mean", "rstd", "wsum"), outs[("0", save)], outs[("1", save)]):
+            assert (ref is None) == (got is None), (save, name)
+            if ref is not None:
+                assert torch.equal(ref, got), (save, name, (ref - got).abs().max().item())
