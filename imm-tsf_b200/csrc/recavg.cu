@@ -1541,7 +1541,8 @@ extern "C" int immtsf_recavg_pool_bwd(const float* dE_drop, const float* E_raw, 
   // profiles/r1_sweep_hbm_v6_fused.json): one launch, dS stays in shared memory (IMMTSF_RECAVG_FUSED_BWD=0 keeps the
   // two-kernel path, =4 / =8 picks the notes per pass).
   const char* fused_env = getenv("IMMTSF_RECAVG_FUSED_BWD");  // read per call: tests A/B the two paths inside one process
-  const int fused = fused_env ? atoi(fused_env) : IMMTSF_RECAVG_FUSED_BWD_DEFAULT;
+  const char* tma_env = getenv("IMMTSF_RECAVG_TMA");  // =0 means "no bulk-copy kernels at all": the fused kernel is one
+  const int fused = (tma_env && tma_env[0] == '0') ? 0 : (fused_env ? atoi(fused_env) : IMMTSF_RECAVG_FUSED_BWD_DEFAULT);
   if (fused && nc > 0 && T <= POOL_TB && N_max <= 32 && (size_t)(T + 8) * d * sizeof(float) <= 108 * 1024 && ((uintptr_t)gamma & 15) == 0 &&
       ((uintptr_t)dE_drop & 15) == 0 && ((uintptr_t)E_raw & 15) == 0) {
 #define BWD_F(NCV) do { if (fused == 4) launch_bwd_fused<NCV, 4>(a, st); else launch_bwd_fused<NCV, 8>(a, st); } while (0)
