@@ -1421,6 +1421,260 @@ static void launch_bwd_fused(const PoolArgs& a, cudaStream_t st) {
   else { if (skipq) launch_bwd_fused2<NC, NTN, false, true>(a, st); else launch_bwd_fused2<NC, NTN, false, false>(a, st); }
 }
 
+// ------------------------------------------------------------------ backward, warp-specialised pipeline (experimental)
+// IMMTSF_RECAVG_BWD_PIPE=1, default off, NOT YET RUN ON A B200.  recavg_bwd_fused_kernel runs its rows phase and its note phase
+// one after the other with CTA-wide barriers in between (ncu: 19 % of the stall samples on barriers, 43 % issue utilisation).
+// Here the two phases belong to different warps of one persistent CTA per SM and overlap across consecutive samples:
+//   * 8 ROW warps: warp w owns the query rows t = w, w + 8, ... of the current sample; lane 0 fetches the (dE_drop, E_raw) row
+//     pair with two bulk copies into the warp's private buffer (own mbarrier), the warp writes dS_t into stage st of a two-stage
+//     dS ring and d(den_t) into s_dw[st], and arrives on full[st].  dgamma / dbeta stay in the row warps' registers for the
+//     whole kernel (no per-sample exchange) and are combined once at the end.
+//   * 2*NC NOTE warps (thread per float4 column): wait for full[st], contract dS with the recency weights exactly like the
+//     fused kernel's note phase (8 notes per pass, barrier 1 among the note warps only), write dV', arrive on empty[st].
+// Row warps wait for empty[st] before they overwrite a stage (sample it - 2).  mbarrier arrive / try_wait carry release / acquire
+// semantics at CTA scope; the lanes of a warp are ordered before their lane 0's arrive by __syncwarp().
+// smem (dynamic): s_g [2][T][d] | s_xy [8 warps][2 rows][d].  blockDim = 256 + 64 * NC, 1 CTA per SM.
+__device__ __forceinline__ void rs_mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void rs_named_bar(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+template <int NC, bool TAG, bool SKIPQ>
+__global__ void __launch_bounds__(256 + 64 * NC, 1) recavg_bwd_pipe_kernel(const PoolArgs a) {
+  constexpr int NTN = 8, NWN = 2 * NC, NOTE_THREADS = 32 * NWN;
+  extern __shared__ __align__(128) float s_dyn[];
+  __shared__ __align__(16) float s_w[POOL_TB][NTN];
+  __shared__ __align__(16) float s_c[POOL_TB][NTN];
+  __shared__ float s_dw[2][POOL_TB];
+  __shared__ __align__(8) unsigned long long s_full[2];
+  __shared__ __align__(8) unsigned long long s_empty[2];
+  __shared__ __align__(8) unsigned long long s_barx[8];
+  const int d = a.d, d8 = d >> 3, d4 = d >> 2, T = a.T;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float* s_g = s_dyn;                                // [2][T][d]
+  float* s_xy = s_dyn + (size_t)2 * T * d;           // [8][2][d]
+  if (threadIdx.x == 0) {
+    rs_mbar_init(rs_smem_u32(&s_full[0]), 8); rs_mbar_init(rs_smem_u32(&s_full[1]), 8);
+    rs_mbar_init(rs_smem_u32(&s_empty[0]), NWN); rs_mbar_init(rs_smem_u32(&s_empty[1]), NWN);
+  }
+  if (w < 8 && lane == 0) rs_mbar_init(rs_smem_u32(&s_barx[w]), 1);
+  __syncthreads();
+  const uint32_t row_bytes = (uint32_t)d * 4u;
+  if (w < 8) {
+    // ================================================================ row warps
+    const float inv_keep = inv_keep_from_thr(a.thr), inv_d = 1.f / (float)d;
+    const uint64_t seed = resolve_seed(a.seed);
+    float* s_dy = s_xy + (size_t)w * 2 * d;
+    float* s_x = s_dy + d;
+    const uint32_t barx = rs_smem_u32(&s_barx[w]);
+    float dgam[NC][8], dbet[NC][8];
+#pragma unroll
+    for (int i = 0; i < NC; ++i) { zero8(dgam[i]); zero8(dbet[i]); }
+    uint32_t phx = 0;
+    auto fetch = [&](size_t r) {  // lane 0: the (dE_drop, E_raw) pair of row r into this warp's buffer
+      rs_mbar_expect_tx(barx, 2u * row_bytes);
+      rs_bulk_g2s(rs_smem_u32(s_dy), a.dE_drop + r * d, row_bytes, barx);
+      rs_bulk_g2s(rs_smem_u32(s_x), a.E_raw + r * d, row_bytes, barx);
+    };
+    if (lane == 0 && (int)blockIdx.x < a.B && w < T) fetch((size_t)blockIdx.x * T + w);
+    int it = 0;
+    for (int b = blockIdx.x; b < a.B; b += gridDim.x, ++it) {
+      const int st = it & 1;
+      float* sg_stage = s_g + (size_t)st * T * d;
+      if (it >= 2) rs_mbar_wait(rs_smem_u32(&s_empty[st]), (uint32_t)(((it >> 1) - 1) & 1));  // the note warps are done with sample it - 2
+      for (int t = w; t < T; t += 8) {
+        const size_t r = (size_t)b * T + t;
+        const float mu = a.mean[r], rs = a.rstd[r], ws = a.wsum[r];
+        const float den = fmaxf(ws, 1e-6f);
+        rs_mbar_wait(barx, phx);
+        phx ^= 1u;
+        float gg[NC][8];
+        float p1 = 0.f, p2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+          const int k = lane + 32 * i;
+          zero8(gg[i]);
+          if (k < d8) {
+            float dy[8], x[8], ga[8], ks[8];
+            lds8(s_dy, k, dy);
+            lds8(s_x, k, x);
+            load8(a.gamma, k, ga);
+            if (TAG && a.thr) keep_of8(x, inv_keep, ks);
+            else dropout_scale8(seed, IMMTSF_SITE_TTF_DROPOUT, (uint64_t)r * d8 + k, a.thr, inv_keep, ks);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float dye = dy[e] * ks[e];
+              const float he = (x[e] - mu) * rs;
+              dgam[i][e] = fmaf(dye, he, dgam[i][e]);
+              dbet[i][e] += dye;
+              gg[i][e] = dye * ga[e];
+              p1 += gg[i][e];
+              p2 = fmaf(gg[i][e], he, p2);
+            }
+          }
+        }
+        const float s2 = warp_sum(p2);
+        const float m1 = warp_sum(p1) * inv_d, m2 = s2 * inv_d;
+        const float sc = rs / den;
+        float* sg = sg_stage + (size_t)t * d;
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+          const int k = lane + 32 * i;
+          if (k < d8) {
+            float x[8], o[8];  // dE_raw = rstd * (g - mean(g) - xhat * mean(g*xhat));  dS = dE_raw / den
+            lds8(s_x, k, x);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = sc * (gg[i][e] - m1 - ((x[e] - mu) * rs) * m2);
+            sts8(sg, k, o);
+          }
+        }
+        if (lane == 0) s_dw[st][t] = ws >= 1e-6f ? -(s2 * a.eps * rs * rs) / den : 0.f;
+        __syncwarp();  // every lane is done with the row pair
+        if (lane == 0) {  // next row of this warp: same sample, or the warp's first row of its next sample
+          if (t + 8 < T) fetch(r + 8);
+          else if (b + (int)gridDim.x < a.B && w < T) fetch((size_t)(b + gridDim.x) * T + w);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) rs_mbar_arrive(rs_smem_u32(&s_full[st]));  // this warp's dS rows and d(den) of sample b are in stage st
+    }
+    // dgamma / dbeta of this CTA: the 8 row warps take turns on one [2][d] array (the row buffers are idle now)
+    rs_named_bar(2, 256);
+    float* s_acc = s_xy;
+    for (int i = threadIdx.x; i < 2 * d; i += 256) s_acc[i] = 0.f;
+    for (int turn = 0; turn < 8; ++turn) {
+      rs_named_bar(2, 256);
+      if (w == turn) {
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+          const int k = lane + 32 * i;
+          if (k < d8) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { s_acc[8 * k + e] += dgam[i][e]; s_acc[d + 8 * k + e] += dbet[i][e]; }
+          }
+        }
+      }
+    }
+    rs_named_bar(2, 256);
+    for (int i = threadIdx.x; i < d; i += 256) {
+      atomicAdd(a.dgamma + i, s_acc[i]);
+      atomicAdd(a.dbeta + i, s_acc[d + i]);
+    }
+  } else {
+    // ================================================================ note warps
+    const int nt = threadIdx.x - 256;  // float4 column owned in the contraction
+    const float sigma = expf(__ldg(a.log_sigma));
+    double dls = 0.0;
+    int it = 0;
+    for (int b = blockIdx.x; b < a.B; b += gridDim.x, ++it) {
+      const int st = it & 1;
+      const int nb = a.offsets[b], ne = a.offsets[b + 1];
+      const float* sg_stage = s_g + (size_t)st * T * d;
+      if (nt == 0 && ne > nb && a.ldv == d)  // V' rows are needed by the epilogues only: start them towards L2
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.Vp + (size_t)nb * a.ldv), "r"((uint32_t)(ne - nb) * row_bytes) : "memory");
+      bool waited = false;
+      for (int n0 = nb; n0 < ne; n0 += NTN) {
+        const int ncnt = min(NTN, ne - n0);
+        rs_named_bar(1, NOTE_THREADS);  // the previous pass (or sample) has consumed s_w / s_c
+        for (int i = nt; i < T * NTN; i += NOTE_THREADS) {
+          const int tt = i / NTN, u = i % NTN;
+          float wv = 0.f, cc = 0.f;
+          if (u < ncnt) {
+            const float delta = fmaxf(a.t_hat[(size_t)b * a.t_bstride + tt] - __ldg(a.tau + n0 + u), 0.f);
+            const float rr = delta / sigma;
+            wv = expf(-(rr * rr));
+            cc = wv * 2.f * rr * rr;
+          }
+          s_w[tt][u] = wv;
+          s_c[tt][u] = cc;
+        }
+        rs_named_bar(1, NOTE_THREADS);
+        if (!waited) {  // the weights of the first pass do not depend on dS: computed before the wait
+          rs_mbar_wait(rs_smem_u32(&s_full[st]), (uint32_t)((it >> 1) & 1));
+          waited = true;
+        }
+        if (nt < NTN) {  // sum_t c_nt d(den_t), thread u owns note u
+          float sc_term = 0.f;
+          for (int tt = 0; tt < T; ++tt) sc_term = fmaf(s_c[tt][nt], s_dw[st][tt], sc_term);
+          dls += (double)sc_term;
+        }
+        bool need_lo = true, need_hi = true;
+        if (SKIPQ) {
+          const float4 z0 = lane < T ? *reinterpret_cast<const float4*>(&s_c[lane][0]) : f4_zero();
+          const float4 z1 = lane < T ? *reinterpret_cast<const float4*>(&s_c[lane][4]) : f4_zero();
+          need_lo = __any_sync(0xffffffffu, z0.x != 0.f || z0.y != 0.f || z0.z != 0.f || z0.w != 0.f);
+          need_hi = __any_sync(0xffffffffu, z1.x != 0.f || z1.y != 0.f || z1.z != 0.f || z1.w != 0.f);
+        }
+        if (nt < d4) {
+          float4 accw[NTN], accc[NTN];
+#pragma unroll
+          for (int u = 0; u < NTN; ++u) { accw[u] = f4_zero(); accc[u] = f4_zero(); }
+          const float4* gp = reinterpret_cast<const float4*>(sg_stage) + nt;
+          const bool half = ncnt <= 4;  // half-empty pass: skip the empty note slots
+          for (int tt = 0; tt < T; ++tt) {
+            const float4 g = gp[(size_t)tt * d4];
+            const float4 w0 = *reinterpret_cast<const float4*>(&s_w[tt][0]);
+            f4_fma(accw[0], w0.x, g); f4_fma(accw[1], w0.y, g); f4_fma(accw[2], w0.z, g); f4_fma(accw[3], w0.w, g);
+            if (need_lo) {
+              const float4 c0 = *reinterpret_cast<const float4*>(&s_c[tt][0]);
+              f4_fma(accc[0], c0.x, g); f4_fma(accc[1], c0.y, g); f4_fma(accc[2], c0.z, g); f4_fma(accc[3], c0.w, g);
+            }
+            if (!half) {
+              const float4 w1 = *reinterpret_cast<const float4*>(&s_w[tt][4]);
+              f4_fma(accw[4], w1.x, g); f4_fma(accw[5], w1.y, g); f4_fma(accw[6], w1.z, g); f4_fma(accw[7], w1.w, g);
+              if (need_hi) {
+                const float4 c1 = *reinterpret_cast<const float4*>(&s_c[tt][4]);
+                f4_fma(accc[4], c1.x, g); f4_fma(accc[5], c1.y, g); f4_fma(accc[6], c1.z, g); f4_fma(accc[7], c1.w, g);
+              }
+            }
+          }
+#pragma unroll
+          for (int h0 = 0; h0 < NTN; h0 += 4) {  // four V' rows requested before the first store
+            float4 vv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              vv[u] = h0 + u < ncnt ? __ldg(reinterpret_cast<const float4*>(a.Vp + (size_t)(n0 + h0 + u) * a.ldv) + nt) : f4_zero();
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float4 q = accc[h0 + u], v = vv[u];  // empty slots: q == v == 0
+              dls += (double)q.x * v.x + (double)q.y * v.y + (double)q.z * v.z + (double)q.w * v.w;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (h0 + u < ncnt) reinterpret_cast<float4*>(a.dVp + (size_t)(n0 + h0 + u) * a.lddv)[nt] = accw[h0 + u];
+          }
+        }
+      }
+      if (!waited) rs_mbar_wait(rs_smem_u32(&s_full[st]), (uint32_t)((it >> 1) & 1));  // sample without notes: keep the phases in step
+      __syncwarp();
+      if (lane == 0) rs_mbar_arrive(rs_smem_u32(&s_empty[st]));  // this warp no longer reads stage st
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dls += __shfl_xor_sync(0xffffffffu, dls, o);
+    if (lane == 0) atomicAdd(a.dlog_sigma, dls);
+  }
+}
+
+template <int NC, bool TAG, bool SKIPQ>
+static void launch_bwd_pipe2(const PoolArgs& a, cudaStream_t st) {
+  const size_t smem = (size_t)(2 * a.T + 16) * a.d * sizeof(float);
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    cudaFuncSetAttribute(recavg_bwd_pipe_kernel<NC, TAG, SKIPQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    smem_set = smem;
+  }
+  const int grid = a.B < 148 ? a.B : 148;
+  recavg_bwd_pipe_kernel<NC, TAG, SKIPQ><<<grid, 256 + 64 * NC, smem, st>>>(a);
+}
+template <int NC>
+static void launch_bwd_pipe(const PoolArgs& a, cudaStream_t st) {
+  const char* e = getenv("IMMTSF_RECAVG_SKIPQ");
+  const bool skipq = e && atoi(e) != 0;
+  if (a.maskbit) { if (skipq) launch_bwd_pipe2<NC, true, true>(a, st); else launch_bwd_pipe2<NC, true, false>(a, st); }
+  else { if (skipq) launch_bwd_pipe2<NC, false, true>(a, st); else launch_bwd_pipe2<NC, false, false>(a, st); }
+}
+
 // Keep flags in the LSB of E_raw (experimental, see tag_keep): decided from what BOTH entry points see, so that the forward
 // and the backward of one step agree; read per call (tests A/B the two conventions inside one process).
 static int recavg_maskbit(int d, int N_max) {
@@ -1543,6 +1797,17 @@ extern "C" int immtsf_recavg_pool_bwd(const float* dE_drop, const float* E_raw, 
   const char* fused_env = getenv("IMMTSF_RECAVG_FUSED_BWD");  // read per call: tests A/B the two paths inside one process
   const char* tma_env = getenv("IMMTSF_RECAVG_TMA");  // =0 means "no bulk-copy kernels at all": the fused kernel is one
   const int fused = (tma_env && tma_env[0] == '0') ? 0 : (fused_env ? atoi(fused_env) : IMMTSF_RECAVG_FUSED_BWD_DEFAULT);
+  const char* pipe_env = getenv("IMMTSF_RECAVG_BWD_PIPE");  // experimental warp-specialised backward, read per call
+  if (pipe_env && atoi(pipe_env) != 0 && fused && nc > 0 && T <= POOL_TB && N_max <= 32 &&
+      (size_t)(2 * T + 16) * d * sizeof(float) <= 220 * 1024 && ((uintptr_t)gamma & 15) == 0 && ((uintptr_t)dE_drop & 15) == 0 &&
+      ((uintptr_t)E_raw & 15) == 0) {
+    if (nc == 1) launch_bwd_pipe<1>(a, st);
+    else if (nc == 2) launch_bwd_pipe<2>(a, st);
+    else if (nc == 3) launch_bwd_pipe<3>(a, st);
+    else launch_bwd_pipe<4>(a, st);
+    IMMTSF_CHECK_LAUNCH("recavg_bwd_pipe");
+    return IMMTSF_OK;
+  }
   if (fused && nc > 0 && T <= POOL_TB && N_max <= 32 && (size_t)(T + 8) * d * sizeof(float) <= 108 * 1024 && ((uintptr_t)gamma & 15) == 0 &&
       ((uintptr_t)dE_drop & 15) == 0 && ((uintptr_t)E_raw & 15) == 0) {
 #define BWD_F(NCV) do { if (fused == 4) launch_bwd_fused<NCV, 4>(a, st); else launch_bwd_fused<NCV, 8>(a, st); } while (0)

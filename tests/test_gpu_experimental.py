@@ -133,3 +133,36 @@ def test_recavg_persistent_forward_is_bit_identical(B, N, T, d, p, maskbit, monk
             assert (ref is None) == (got is None), (save, name)
             if ref is not None:
                 assert torch.equal(ref, got), (save, name, (ref - got).abs().max().item())
+
+
+@pytest.mark.parametrize("maskbit,skipq", [("0", "0"), ("1", "1")])
+@pytest.mark.parametrize("B,N,T,d,p", [(5, 6, 7, 64, 0.1), (64, 16, 24, 768, 0.1), (700, 16, 24, 768, 0.1), (300, 3, 16, 1024, 0.2),
+                                         (9, 30, 24, 256, 0.0), (3, 1, 1, 8, 0.5), (450, 16, 32, 512, 0.1), (2, 5, 24, 776, 0.1)])
+def test_recavg_bwd_pipe_equals_default(B, N, T, d, p, maskbit, skipq, monkeypatch):
+    """IMMTSF_RECAVG_BWD_PIPE=1: warp-specialised one-launch backward (8 row warps + 2*NC note warps, two-stage dS ring with
+    full / empty mbarriers, 1 CTA per SM) against the default backward on the same inputs.  B 700 and B 450 give every CTA
+    several samples (both ring stages, both parities of every mbarrier); T 7 leaves a row warp idle; one sample has no notes."""
+    monkeypatch.setenv("IMMTSF_RECAVG_MASKBIT", maskbit)
+    monkeypatch.setenv("IMMTSF_RECAVG_SKIPQ", skipq)
+    from immtsf import ops
+
+    notes, tau, t_hat, _, _ = G.synth_batch(B, N, T, d, 1, 55, no_note=B > 2)
+    r = ops.csr_build(notes.cuda(), tau.cuda())
+    t_hat = t_hat.cuda()
+    g = torch.Generator().manual_seed(13)
+    ls = torch.tensor(-0.2, device="cuda")
+    gamma = (1.0 + 0.1 * torch.randn(d, generator=g)).cuda()
+    beta = (0.1 * torch.randn(d, generator=g)).cuda()
+    thr, sd = ops.drop_thr(p), 808
+    E_drop, E_raw, mean, rstd, wsum = ops.recavg_pool_fwd(r.emb_flat, r, t_hat, ls, gamma, beta, T, d, thr, sd, True)
+    dE = torch.randn(B, T, d, generator=g).cuda().view_as(E_drop)
+    outs = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("IMMTSF_RECAVG_BWD_PIPE", mode)
+        outs[mode] = [x.clone() for x in ops.recavg_pool_bwd(dE, E_raw, mean, rstd, wsum, r.emb_flat, r, t_hat, ls, gamma, T, d, thr, sd)]
+        torch.cuda.synchronize()
+    for name, ref, got in zip(("dVp", "dgamma", "dbeta", "dlog_sigma"), outs["0"], outs["1"]):
+        assert torch.isfinite(got).all(), name
+        den = max(ref.abs().max().item(), 1e-6)
+        err = (got - ref).abs().max().item()
+        assert err <= 2e-5 * den, f"{name}: err {err:.3e} vs max {den:.3e}"
