@@ -31,7 +31,7 @@ class MMF_GR_Add(nn.Module):
     def forward_flags(self, Y_ts, E_txt, M_txt, flags):
         cm.require_cuda(Y_ts, "MMF_GR_Add")
         B, T, C = Y_ts.shape
-        thr, seed = cm.dropout_args(self.dropout.p, self.training)
+        thr, seed = cm.dropout_args(self.dropout.p, self.training, self)
         g = self.gru
         params = (g.weight_ih_l0, g.weight_hh_l0, g.bias_ih_l0, g.bias_hh_l0, self.residual_head.weight,
                   self.residual_head.bias, self.gate_net.weight, self.gate_net.bias, self.layer_norm.weight,

@@ -63,7 +63,7 @@ class MMF_XAttn_Add(nn.Module):
         rank_weights(...) when the caller already computed it (FusionModel, on the side stream)."""
         cm.require_cuda(Y_ts, "MMF_XAttn_Add")
         B, T, C = Y_ts.shape
-        thr, seed = cm.dropout_args(self.dropout.p, self.training)
+        thr, seed = cm.dropout_args(self.dropout.p, self.training, self)
         params = self._params()
         save = F_._need_save(Y_ts, E_txt, *params)
         own_flags = flags if flags is not None else runtime.new_flags(Y_ts.device)

@@ -49,7 +49,7 @@ class TTF_RecAvg(nn.Module):
         """defer=True: return dropout(LN(E_raw)) without `proj`; the caller applies final_proj() (FusionModel fuses it
         into the rank form of MMF_XAttn_Add)."""
         t_hat, T = cm.fix_t_hat(t_hat, r.B)
-        thr, seed = cm.dropout_args(self.dropout.p, self.training)
+        thr, seed = cm.dropout_args(self.dropout.p, self.training, self)
         ip = self.input_proj
         params = (self.log_recency_sigma, ip.weight if ip is not None else None, ip.bias if ip is not None else None,
                   self.layer_norm.weight, self.layer_norm.bias, self.proj.weight, self.proj.bias)

@@ -71,7 +71,7 @@ class TTF_T2V_XAttn(nn.Module):
     def forward_ragged(self, r: ops.RaggedNotes, t_hat: torch.Tensor, defer: bool = False):
         """defer=True: return dropout(LN(attn + Q)) without proj_out; the caller applies final_proj()."""
         _, T = cm.fix_t_hat(t_hat, r.B)  # only the length of t_hat matters (reference :143,150)
-        thr, seed = cm.dropout_args(self.dropout.p, self.training)
+        thr, seed = cm.dropout_args(self.dropout.p, self.training, self)
         ip, t2v, at = self.input_proj, self.time2vec, self.attn
         params = (self.Q_param, ip.weight if ip is not None else None, ip.bias if ip is not None else None,
                   t2v.linear.weight, t2v.linear.bias, t2v.periodic.weight, t2v.periodic.bias,

@@ -56,7 +56,7 @@ class TTF_T2V_XAttn(nn.Module):
     def forward_ragged(self, r: ops.RaggedNotes, t_hat: torch.Tensor, defer: bool = False):
         assert not defer
         t_hat, T = cm.fix_t_hat(t_hat, r.B)
-        thr, seed = cm.dropout_args(self.dropout.p, self.training)
+        thr, seed = cm.dropout_args(self.dropout.p, self.training, self)
         ip, t2v, at = self.input_proj, self.time2vec, self.attn
         params = (self.Q_param, ip.weight if ip is not None else None, ip.bias if ip is not None else None,
                   t2v.linear.weight, t2v.linear.bias, t2v.periodic.weight, t2v.periodic.bias,

@@ -23,6 +23,8 @@ def as_f32(t: torch.Tensor) -> torch.Tensor:
 def fix_t_hat(t_hat: torch.Tensor, B: int):
     """Reference: fusions/TTF_RecAvg.py:86-91 / fusions/TTF_T2V_XAttn.py:128-133.
     A 1-D t_hat is shared by all samples (no repeat: kernels take a batch stride of 0)."""
+    if not t_hat.is_cuda:  # a host pointer handed to a kernel is an asynchronous illegal address, not an exception
+        raise RuntimeError("t_hat must be a CUDA tensor on the device of the notes -- the immtsf path has no CPU fallback")
     if t_hat.dim() == 1:
         return as_f32(t_hat).contiguous(), t_hat.shape[0]
     if t_hat.shape[0] != B:
@@ -38,7 +40,17 @@ def m_txt_u8(M_txt: torch.Tensor, B: int) -> torch.Tensor:
     return M_txt.reshape(B).to(torch.uint8).contiguous()
 
 
-def dropout_args(module_p: float, training: bool):
+def dropout_args(module_p: float, training: bool, module=None):
+    """(thr, seed) of a module's dropout sites.  The kernels take ONE LayerNorm epsilon (ops.LN_EPS, the nn.LayerNorm
+    default the reference constructs with) and ONE drop rate per module (the reference passes the same `dropout` to
+    nn.Dropout and nn.MultiheadAttention): a module whose containers were edited to anything else would silently diverge
+    from the reference, so that is an error here."""
+    if module is not None:
+        ln, attn = getattr(module, "layer_norm", None), getattr(module, "attn", None)
+        if ln is not None and ln.eps != ops.LN_EPS:
+            raise ValueError(f"layer_norm.eps = {ln.eps}: the immtsf kernels are built for eps = {ops.LN_EPS}")
+        if attn is not None and float(attn.dropout) != float(module_p):
+            raise ValueError(f"attn.dropout = {attn.dropout} differs from dropout.p = {module_p}: one drop rate per module is supported")
     thr = ops.drop_thr(module_p) if training else 0
     seed = runtime.SEEDS.next() if thr else 0
     return thr, seed

@@ -29,6 +29,7 @@ class MaskedMSEFn(torch.autograd.Function):
     def forward(ctx, pred, truth, mask, group, empty_flag):
         for t, nm in ((pred, "pred"), (truth, "truth"), (mask, "mask")):
             ops._chk(t, nm)
+        ctx.in_shape = pred.shape  # the gradient goes back in the caller's layout ([1, B, T, C] included)
         if pred.dim() == 4 and pred.shape[0] == 1:  # [n_traj_samples = 1, B, T, C] (lib/evaluation.py:21-23)
             pred = pred[0]
         if pred.dim() != 3 or truth.shape != pred.shape or mask.shape != pred.shape:
@@ -62,7 +63,7 @@ class MaskedMSEFn(torch.autograd.Function):
         g = gloss.contiguous().to(torch.float32)
         dpred = torch.empty_like(p)
         _lib.call("immtsf_masked_mse_bwd", ops._p(p), ops._p(t), ops._p(m), B * T, C, ops._p(scale), ops._p(g), ops._p(dpred), ops._stream())
-        return dpred, None, None, None, None
+        return dpred.view(ctx.in_shape), None, None, None, None
 
 
 def masked_mse(pred: torch.Tensor, truth: torch.Tensor, mask: torch.Tensor, group=None, empty_flag: torch.Tensor = None):

@@ -408,6 +408,7 @@ def group_sum_rows(x, R, T, d):
 # ------------------------------------------------------------------ RecAvg pooling
 def recavg_pool_fwd(Vp, r: RaggedNotes, t_hat, log_sigma, gamma, beta, T, d, thr, seed, save):
     B = r.B
+    _chk(t_hat, "t_hat")
     dev = Vp.device
     E_drop = torch.empty(B, T, d, dtype=torch.float32, device=dev)
     E_raw = torch.empty(B, T, d, dtype=torch.float32, device=dev) if save else None
@@ -477,6 +478,7 @@ def t2vq_attn_fwd(A, a_sc, g, r: RaggedNotes, t_hat, t2v_params, T, H, d, d_tau,
     Phi [B*T*H, d_tau], sp [B*T*H] and the saved softmax [H*T*M_alloc] (None unless save)."""
     R = r.B * T * H
     dev = A.device
+    _chk(t_hat, "t_hat")
     Z = torch.empty(R, d, dtype=torch.float32, device=dev)
     Phi = torch.empty(R, d_tau, dtype=torch.float32, device=dev)
     sp = torch.empty(R, dtype=torch.float32, device=dev)

@@ -61,6 +61,18 @@ class SeedSource:
 SEEDS = SeedSource()
 
 
+_CAPTURE = {}
+
+
+def capture_stream(dev) -> "torch.cuda.Stream":
+    dev = torch.device(dev)
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    st = _CAPTURE.get(key)
+    if st is None:
+        st = _CAPTURE[key] = torch.cuda.Stream(device=dev)
+    return st
+
+
 class GraphedStep:
     """One training step of the fusion path -- FusionModel forward, loss, backward (every parameter gradient and
     dY_ts) -- captured ONCE in a CUDA graph and replayed with a single launch.
@@ -124,10 +136,12 @@ class GraphedStep:
         self.seed_offset = torch.zeros(1, dtype=torch.int64, device=dev)
         self._lib = _lib
         _lib.call("immtsf_set_seed_offset_ptr", self.seed_offset.data_ptr())
-        side = torch.cuda.Stream()
+        # ONE capture stream per device for every GraphedStep of the process: the warm-up runs on it, so the per-stream
+        # GEMM workspaces (ops._workspace is keyed by stream) exist before the capture begins and are shared by all graphs
+        side = capture_stream(dev)
         side.wait_stream(torch.cuda.current_stream())
         ops.DP_GROUP = self.group if self.n_first > 0 else None
-        with torch.cuda.stream(side):  # warm-up off the capture stream: lazy allocations (workspaces) happen here
+        with torch.cuda.stream(side):  # lazy allocations (workspaces, side streams) happen here, outside the graph's pool
             for _ in range(max(warmup, 1)):
                 self._eager()
         torch.cuda.current_stream().wait_stream(side)
@@ -152,7 +166,7 @@ class GraphedStep:
         try:
             # NCCL's watchdog thread may touch CUDA while we capture: thread-local capture mode tolerates that
             mode = dict(capture_error_mode="thread_local") if self.group is not None else {}
-            with torch.cuda.graph(self.graph, **mode):
+            with torch.cuda.graph(self.graph, stream=side, **mode):
                 _lib.call("immtsf_seed_advance", self.seed_offset.data_ptr(), 1, ops._stream())
                 if self.flat_grads is not None:
                     self.flat_grads.zero_()

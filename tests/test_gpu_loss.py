@@ -54,8 +54,11 @@ def test_masked_mse_vs_oracle_sizes_determinism_and_flags(B, T, C):
     assert vals[0][0] == vals[1][0] and torch.equal(vals[0][1], vals[1][1])  # deterministic reduction order
     assert int(flag.item()) == 1
     # 4-D prediction with one trajectory sample, as models return it (lib/evaluation.py:21-23)
-    v4 = L.masked_mse(pred.cuda().unsqueeze(0), truth.cuda(), mask.cuda())
+    p4 = pred.cuda().unsqueeze(0).requires_grad_(True)
+    v4 = L.masked_mse(p4, truth.cuda(), mask.cuda())
     assert float(v4) == vals[0][0]
+    (3.0 * v4).backward()  # the gradient comes back in the caller's 4-D layout
+    assert tuple(p4.grad.shape) == (1,) + tuple(pred.shape) and torch.equal(p4.grad[0], vals[0][1])
 
 
 def test_masked_mse_shares_add_up_under_sharding():
