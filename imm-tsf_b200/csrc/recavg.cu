@@ -35,29 +35,12 @@ struct PoolArgs {
   float* E_drop; float* E_raw; float* mean; float* rstd; float* wsum;
   // backward only
   const float* dE_drop; float* dVp; int lddv; float* dgamma; float* dbeta; double* dlog_sigma; float* dS; int N_max;
-  int maskbit;  // host-side dispatch only: 1 = the TAG instantiations (keep flags in the LSB of E_raw)
 };
 
 #ifndef IMMTSF_RECAVG_FUSED_BWD_DEFAULT
 #define IMMTSF_RECAVG_FUSED_BWD_DEFAULT 8  // one-launch backward (232 GPU tests green with it; =0: two-kernel path)
 #endif
 constexpr int POOL_NB = 32;  // notes per shared-memory weight block
-
-// Experimental (IMMTSF_RECAVG_MASKBIT=1, default off until measured; template parameter TAG of the kernels below, so the
-// default instantiations are untouched): E_raw is saved for the backward only, which needs x^ = (E_raw - mean) * rstd and
-// the dropout keep flag of the same element.  The forward stores the flag in the mantissa LSB of E_raw (<= 1 ulp = 6e-8
-// relative on x, far inside the 5e-5 gradient tolerance) and the backward reads it back instead of running Philox4x32-10
-// again (18 % of its executed instructions, profiles/r1_ncu_recavg_fused_bwd_summary.txt).  No extra bytes, no ABI change.
-__device__ __forceinline__ float tag_keep(float x, float ks) {
-  return __uint_as_float((__float_as_uint(x) & ~1u) | (ks != 0.f ? 1u : 0u));
-}
-__device__ __forceinline__ float4 tag_keep4(const float4& x, const float4& ks) {
-  return make_float4(tag_keep(x.x, ks.x), tag_keep(x.y, ks.y), tag_keep(x.z, ks.z), tag_keep(x.w, ks.w));
-}
-__device__ __forceinline__ void keep_of8(const float (&x)[8], float inv_keep, float (&ks)[8]) {
-#pragma unroll
-  for (int e = 0; e < 8; ++e) ks[e] = (__float_as_uint(x[e]) & 1u) ? inv_keep : 0.f;
-}
 
 // ncu (B 2048, N<=16, T 24, d 768) showed the first version of this kernel issue-bound, not memory-bound (47 % issue
 // utilisation with 18 warps/SM, long-scoreboard stalls ~1): hence the register cap (more resident warps), the
@@ -627,7 +610,7 @@ __global__ void __launch_bounds__(256) recavg_pool_fwd_w_kernel(const PoolArgs a
 // (p = 1) and keep their halves swapped in registers until the epilogue; every LDS.128 wavefront then covers 8 distinct
 // 16-byte bank groups.
 // smem: s_v [RS][d] (RS <= 32 rows per stage).  grid (ceil(T / (8*TPW)), B), 256 threads.
-template <int NC, int TPW, int MINB, bool FULL, bool TAG>
+template <int NC, int TPW, int MINB, bool FULL>
 __global__ void __launch_bounds__(256, MINB) recavg_pool_fwd_s_kernel(const PoolArgs a, int RS) {
   extern __shared__ __align__(128) float s_v[];
   __shared__ __align__(8) unsigned long long s_bar;
@@ -745,8 +728,8 @@ __global__ void __launch_bounds__(256, MINB) recavg_pool_fwd_s_kernel(const Pool
         eo[oB] = yB;
         if (a.E_raw) {
           float4* er = reinterpret_cast<float4*>(a.E_raw + rowi * a.d);
-          er[oA] = (TAG && a.thr) ? tag_keep4(A, kA) : A;
-          er[oB] = (TAG && a.thr) ? tag_keep4(Bv, kB) : Bv;
+          er[oA] = A;
+          er[oB] = Bv;
         }
       }
     }
@@ -758,19 +741,14 @@ __global__ void __launch_bounds__(256, MINB) recavg_pool_fwd_s_kernel(const Pool
   }
 }
 
-template <int NC, int TPW, int MINB, bool FULL, bool TAG>
-static void launch_fwd_s3(const PoolArgs& a, dim3 grid, int RS, size_t smem, cudaStream_t st) {
-  static size_t smem_set = 0;
-  if (smem + 1024 > 48 * 1024 && smem > smem_set) {  // (the kernel also has 128 B of static shared memory)
-    cudaFuncSetAttribute(recavg_pool_fwd_s_kernel<NC, TPW, MINB, FULL, TAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    smem_set = smem;
-  }
-  recavg_pool_fwd_s_kernel<NC, TPW, MINB, FULL, TAG><<<grid, 256, smem, st>>>(a, RS);
-}
 template <int NC, int TPW, int MINB, bool FULL>
 static void launch_fwd_s2(const PoolArgs& a, dim3 grid, int RS, size_t smem, cudaStream_t st) {
-  if (a.maskbit) launch_fwd_s3<NC, TPW, MINB, FULL, true>(a, grid, RS, smem, st);
-  else launch_fwd_s3<NC, TPW, MINB, FULL, false>(a, grid, RS, smem, st);
+  static size_t smem_set = 0;
+  if (smem + 1024 > 48 * 1024 && smem > smem_set) {  // (the kernel also has 128 B of static shared memory)
+    cudaFuncSetAttribute(recavg_pool_fwd_s_kernel<NC, TPW, MINB, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    smem_set = smem;
+  }
+  recavg_pool_fwd_s_kernel<NC, TPW, MINB, FULL><<<grid, 256, smem, st>>>(a, RS);
 }
 // tpw: query times per warp.  3: capped at 128 registers, 2 CTAs per SM (MINB = 2); 2: capped at 80 registers, 3 CTAs per SM (MINB = 3).
 template <int NC>
@@ -782,174 +760,8 @@ static void launch_fwd_s(const PoolArgs& a, int tpw, int T, int B, int RS, size_
   else { if (full) launch_fwd_s2<NC, 1, 3, true>(a, grid, RS, smem, st); else launch_fwd_s2<NC, 1, 3, false>(a, grid, RS, smem, st); }
 }
 
-// ------------------------------------------------------------------ persistent forward, segments double-buffered
-// Experimental (IMMTSF_RECAVG_FWD_PERSIST=1, default off until measured).  recavg_pool_fwd_s_kernel runs one CTA per (sample,
-// tile of 8*TPW query times): the bulk copy of the segment is issued, waited for and consumed by the same short-lived CTA, so
-// the copy latency is only hidden by the other CTA of the SM (ncu: long-scoreboard + barrier stalls, 60 % issue utilisation).
-// Here 2 CTAs per SM stay resident and walk the work items (sample, tile) with a two-stage ring: the copy of item i + grid is
-// posted before item i is touched and lands while item i is pooled and normalised.  Same arithmetic, lane ownership and
-// bank-conflict-free half swap as the staged kernel.  Requires every segment to fit one stage (N_max <= RS <= 16).
-// smem: s_v [2][RS][d].  grid = resident CTAs, 256 threads.
-template <int NC, int TPW, bool FULL, bool TAG>
-__global__ void __launch_bounds__(256, 2) recavg_pool_fwd_p_kernel(const PoolArgs a, int RS, int ntiles) {
-  extern __shared__ __align__(128) float s_v[];
-  __shared__ __align__(8) unsigned long long s_bar[2];
-  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-  const int d = a.d, d8 = d >> 3;
-  const uint32_t bar0 = rs_smem_u32(&s_bar[0]), sv = rs_smem_u32(s_v);
-  const uint32_t row_bytes = (uint32_t)d * 4u, stage_bytes = (uint32_t)RS * row_bytes;
-  if (threadIdx.x == 0) { rs_mbar_init(bar0, 1); rs_mbar_init(bar0 + 8u, 1); }
-  __syncthreads();
-  const float inv_sigma = 1.f / expf(__ldg(a.log_sigma));
-  const float inv_keep = inv_keep_from_thr(a.thr);
-  const uint64_t seed = resolve_seed(a.seed);
-  const float inv_d = 1.f / (float)a.d;
-  const int p = (lane >> 2) & 1;
-  const int nitems = a.B * ntiles;
-  // thread 0 posts the copy of one item's segment into a stage (empty segments still complete the phase: expect_tx 0)
-  auto post = [&](int item, int stage) {
-    const int b = item / ntiles;
-    const int nb = a.offsets[b], cnt = a.offsets[b + 1] - nb;
-    const uint32_t bar = bar0 + 8u * (uint32_t)stage, dst = sv + (uint32_t)stage * stage_bytes;
-    rs_mbar_expect_tx(bar, (uint32_t)cnt * row_bytes);
-    if (a.ldv == d) {
-      if (cnt > 0) rs_bulk_g2s(dst, a.Vp + (size_t)nb * a.ldv, (uint32_t)cnt * row_bytes, bar);
-    } else {
-      for (int j = 0; j < cnt; ++j) rs_bulk_g2s(dst + (uint32_t)j * row_bytes, a.Vp + (size_t)(nb + j) * a.ldv, row_bytes, bar);
-    }
-  };
-  if (threadIdx.x == 0 && (int)blockIdx.x < nitems) post(blockIdx.x, 0);
-  int it = 0;
-  for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
-    const int st = it & 1;
-    const int b = item / ntiles, tile = item - b * ntiles;
-    const int tb = tile * (8 * TPW) + wrp;
-    const bool active = tb < a.T;
-    const int nb = a.offsets[b], cnt = a.offsets[b + 1] - nb;
-    // stage st ^ 1 was read by the previous item; every warp passed the barrier behind that item's pooling loop
-    if (threadIdx.x == 0 && item + (int)gridDim.x < nitems) post(item + gridDim.x, st ^ 1);
-    float th[TPW], wl[TPW];
-    float4 accA[TPW][NC], accB[TPW][NC];
-    const float tn = lane < cnt ? __ldg(a.tau + nb + lane) : 0.f;
-#pragma unroll
-    for (int q = 0; q < TPW; ++q) {
-      th[q] = tb + 8 * q < a.T ? a.t_hat[(size_t)b * a.t_bstride + tb + 8 * q] : 0.f;
-      const float r = fmaxf(th[q] - tn, 0.f) * inv_sigma;
-      wl[q] = lane < cnt ? expf(-(r * r)) : 0.f;
-#pragma unroll
-      for (int i = 0; i < NC; ++i) { accA[q][i] = f4_zero(); accB[q][i] = f4_zero(); }
-    }
-    rs_mbar_wait(bar0 + 8u * (uint32_t)st, (uint32_t)((it >> 1) & 1));
-    if (active) {
-      const float* base = s_v + (size_t)st * RS * d;
-      for (int j = 0; j < cnt; ++j) {
-        const float4* row = reinterpret_cast<const float4*>(base + (size_t)j * d);
-        float4 vA[NC], vB[NC];
-#pragma unroll
-        for (int i = 0; i < NC; ++i) {
-          const int k = lane + 32 * i;
-          if (FULL || k < d8) { vA[i] = row[2 * k + p]; vB[i] = row[2 * k + 1 - p]; }
-          else { vA[i] = f4_zero(); vB[i] = f4_zero(); }
-        }
-#pragma unroll
-        for (int q = 0; q < TPW; ++q) {
-          const float w0 = __shfl_sync(0xffffffffu, wl[q], j);
-#pragma unroll
-          for (int i = 0; i < NC; ++i) { f4_fma_s(accA[q][i], w0, vA[i]); f4_fma_s(accB[q][i], w0, vB[i]); }
-        }
-      }
-    }
-    __syncthreads();  // stage st is free again (the copy of item + 2 * grid is posted one iteration from now)
-    if (!active) continue;
-#pragma unroll
-    for (int q = 0; q < TPW; ++q) {
-      const int t = tb + 8 * q;
-      if (t >= a.T) break;
-      const float wsum = warp_sum(wl[q]);
-      const float inv_den = 1.f / fmaxf(wsum, 1e-6f);  // E_raw = E_wsum / clamp_min(denom, 1e-6)
-      float sm = 0.f;
-#pragma unroll
-      for (int i = 0; i < NC; ++i) {  // chunks beyond d are exactly 0
-        float4& A = accA[q][i];
-        float4& Bv = accB[q][i];
-        A.x *= inv_den; A.y *= inv_den; A.z *= inv_den; A.w *= inv_den;
-        Bv.x *= inv_den; Bv.y *= inv_den; Bv.z *= inv_den; Bv.w *= inv_den;
-        sm += (A.x + A.y) + (A.z + A.w) + (Bv.x + Bv.y) + (Bv.z + Bv.w);
-      }
-      const float mu = warp_sum(sm) * inv_d;
-      float qq = 0.f;
-#pragma unroll
-      for (int i = 0; i < NC; ++i)
-        if (FULL || lane + 32 * i < d8) {
-          const float4 A = accA[q][i], Bv = accB[q][i];
-          qq = fmaf(A.x - mu, A.x - mu, qq); qq = fmaf(A.y - mu, A.y - mu, qq); qq = fmaf(A.z - mu, A.z - mu, qq); qq = fmaf(A.w - mu, A.w - mu, qq);
-          qq = fmaf(Bv.x - mu, Bv.x - mu, qq); qq = fmaf(Bv.y - mu, Bv.y - mu, qq); qq = fmaf(Bv.z - mu, Bv.z - mu, qq); qq = fmaf(Bv.w - mu, Bv.w - mu, qq);
-        }
-      const float rs = 1.f / sqrtf(warp_sum(qq) * inv_d + a.eps);
-      const size_t rowi = (size_t)b * a.T + t;
-#pragma unroll
-      for (int i = 0; i < NC; ++i) {
-        const int k = lane + 32 * i;
-        if (FULL || k < d8) {
-          float ks[8];
-          dropout_scale8(seed, IMMTSF_SITE_TTF_DROPOUT, rowi * d8 + k, a.thr, inv_keep, ks);
-          const int oA = 2 * k + p, oB = 2 * k + 1 - p;  // float4 index of each half within the row
-          const float4 gA = __ldg(reinterpret_cast<const float4*>(a.gamma) + oA), gB = __ldg(reinterpret_cast<const float4*>(a.gamma) + oB);
-          const float4 bA = __ldg(reinterpret_cast<const float4*>(a.beta) + oA), bB = __ldg(reinterpret_cast<const float4*>(a.beta) + oB);
-          const float4 A = accA[q][i], Bv = accB[q][i];
-          float4 kA, kB, yA, yB;
-          kA.x = p ? ks[4] : ks[0]; kA.y = p ? ks[5] : ks[1]; kA.z = p ? ks[6] : ks[2]; kA.w = p ? ks[7] : ks[3];
-          kB.x = p ? ks[0] : ks[4]; kB.y = p ? ks[1] : ks[5]; kB.z = p ? ks[2] : ks[6]; kB.w = p ? ks[3] : ks[7];
-          yA.x = ((A.x - mu) * rs * gA.x + bA.x) * kA.x; yA.y = ((A.y - mu) * rs * gA.y + bA.y) * kA.y;
-          yA.z = ((A.z - mu) * rs * gA.z + bA.z) * kA.z; yA.w = ((A.w - mu) * rs * gA.w + bA.w) * kA.w;
-          yB.x = ((Bv.x - mu) * rs * gB.x + bB.x) * kB.x; yB.y = ((Bv.y - mu) * rs * gB.y + bB.y) * kB.y;
-          yB.z = ((Bv.z - mu) * rs * gB.z + bB.z) * kB.z; yB.w = ((Bv.w - mu) * rs * gB.w + bB.w) * kB.w;
-          float4* eo = reinterpret_cast<float4*>(a.E_drop + rowi * a.d);
-          eo[oA] = yA;
-          eo[oB] = yB;
-          if (a.E_raw) {
-            float4* er = reinterpret_cast<float4*>(a.E_raw + rowi * a.d);
-            er[oA] = (TAG && a.thr) ? tag_keep4(A, kA) : A;
-            er[oB] = (TAG && a.thr) ? tag_keep4(Bv, kB) : Bv;
-          }
-        }
-      }
-      if (lane == 0) {
-        if (a.mean) a.mean[rowi] = mu;
-        if (a.rstd) a.rstd[rowi] = rs;
-        if (a.wsum) a.wsum[rowi] = wsum;
-      }
-    }
-  }
-}
-
-template <int NC, int TPW, bool FULL, bool TAG>
-static void launch_fwd_p2(const PoolArgs& a, int RS, int ntiles, cudaStream_t st) {
-  const size_t smem = (size_t)2 * RS * a.d * sizeof(float);
-  static size_t smem_set = 0;
-  if (smem + 1024 > 48 * 1024 && smem > smem_set) {
-    cudaFuncSetAttribute(recavg_pool_fwd_p_kernel<NC, TPW, FULL, TAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    smem_set = smem;
-  }
-  const int grid = resident_grid((const void*)recavg_pool_fwd_p_kernel<NC, TPW, FULL, TAG>, 256, smem, a.B * ntiles, 2);
-  recavg_pool_fwd_p_kernel<NC, TPW, FULL, TAG><<<grid, 256, smem, st>>>(a, RS, ntiles);
-}
-template <int NC>
-static void launch_fwd_p(const PoolArgs& a, int tpw, int RS, cudaStream_t st) {
-  const bool full = (a.d >> 3) == 32 * NC;
-  const int ntiles = ceil_div(a.T, 8 * tpw);
-#define FWD_P(TPWV)                                                                                                        \
-  do {                                                                                                                     \
-    if (full) { if (a.maskbit) launch_fwd_p2<NC, TPWV, true, true>(a, RS, ntiles, st); else launch_fwd_p2<NC, TPWV, true, false>(a, RS, ntiles, st); } \
-    else { if (a.maskbit) launch_fwd_p2<NC, TPWV, false, true>(a, RS, ntiles, st); else launch_fwd_p2<NC, TPWV, false, false>(a, RS, ntiles, st); }   \
-  } while (0)
-  if (tpw == 3) FWD_P(3);
-  else FWD_P(1);
-#undef FWD_P
-}
-
 // Backward phase 1 (LayerNorm backward of the pooled rows -> dS, d(den)), one warp per (sample, query time) row.
-template <int NC, bool TAG>
+template <int NC>
 __global__ void __launch_bounds__(128) recavg_bwd_rows_w_kernel(const PoolArgs a) {
   __shared__ float s_acc[2 * 1024];  // dgamma | dbeta of this CTA
   const int d8 = a.d >> 3, lane = threadIdx.x & 31;
@@ -977,8 +789,7 @@ __global__ void __launch_bounds__(128) recavg_bwd_rows_w_kernel(const PoolArgs a
         load8(a.dE_drop + (size_t)r * a.d, k, dy);
         load8(a.E_raw + (size_t)r * a.d, k, x);
         load8(a.gamma, k, ga);
-        if (TAG && a.thr) keep_of8(x, inv_keep, ks);
-        else dropout_scale8(seed, IMMTSF_SITE_TTF_DROPOUT, (uint64_t)r * d8 + k, a.thr, inv_keep, ks);
+        dropout_scale8(seed, IMMTSF_SITE_TTF_DROPOUT, (uint64_t)r * d8 + k, a.thr, inv_keep, ks);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const float dye = dy[e] * ks[e];
@@ -1036,7 +847,7 @@ __device__ __forceinline__ void lds8(const float* row, int k, float (&o)[8]) {
   const float4 b = reinterpret_cast<const float4*>(row)[2 * k + 1];
   o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
 }
-template <int NC, bool TAG>
+template <int NC>
 __global__ void __launch_bounds__(128) recavg_bwd_rows_s_kernel(const PoolArgs a) {
   extern __shared__ __align__(128) float s_ring[];
   __shared__ float s_acc[2 * 1024];  // dgamma | dbeta of this CTA
@@ -1088,8 +899,7 @@ __global__ void __launch_bounds__(128) recavg_bwd_rows_s_kernel(const PoolArgs a
         lds8(sdy, k, dy);
         lds8(sx, k, x);
         load8(a.gamma, k, ga);
-        if (TAG && a.thr) keep_of8(x, inv_keep, ks);
-        else dropout_scale8(seed, IMMTSF_SITE_TTF_DROPOUT, (uint64_t)r * d8 + k, a.thr, inv_keep, ks);
+        dropout_scale8(seed, IMMTSF_SITE_TTF_DROPOUT, (uint64_t)r * d8 + k, a.thr, inv_keep, ks);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const float dye = dy[e] * ks[e];
@@ -1136,20 +946,15 @@ __global__ void __launch_bounds__(128) recavg_bwd_rows_s_kernel(const PoolArgs a
   }
 }
 
-template <int NC, bool TAG>
-static void launch_rows_s2(const PoolArgs& a, int want, cudaStream_t st) {
+template <int NC>
+static void launch_rows_s(const PoolArgs& a, int want, cudaStream_t st) {
   const size_t smem = (size_t)4 * 4 * a.d * sizeof(float);
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(recavg_bwd_rows_s_kernel<NC, TAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 4 * 1024 * (int)sizeof(float));
+    cudaFuncSetAttribute(recavg_bwd_rows_s_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 4 * 1024 * (int)sizeof(float));
     attr = true;
   }
-  recavg_bwd_rows_s_kernel<NC, TAG><<<resident_grid((const void*)recavg_bwd_rows_s_kernel<NC, TAG>, 128, smem, want, 4), 128, smem, st>>>(a);
-}
-template <int NC>
-static void launch_rows_s(const PoolArgs& a, int want, cudaStream_t st) {
-  if (a.maskbit) launch_rows_s2<NC, true>(a, want, st);
-  else launch_rows_s2<NC, false>(a, want, st);
+  recavg_bwd_rows_s_kernel<NC><<<resident_grid((const void*)recavg_bwd_rows_s_kernel<NC>, 128, smem, want, 4), 128, smem, st>>>(a);
 }
 
 // ------------------------------------------------------------------ backward in ONE launch (short prediction windows)
@@ -1169,10 +974,7 @@ __device__ __forceinline__ void sts8(float* row, int k, const float (&v)[8]) {
   reinterpret_cast<float4*>(row)[2 * k] = make_float4(v[0], v[1], v[2], v[3]);
   reinterpret_cast<float4*>(row)[2 * k + 1] = make_float4(v[4], v[5], v[6], v[7]);
 }
-// SKIPQ (experimental, IMMTSF_RECAVG_SKIPQ=1, default off until measured): c_nt = w_nt * 2 (delta/sigma)^2 is exactly 0 wherever
-// tau_n >= t_hat_t, i.e. for every note that is not older than the whole prediction window (Time-IMM: ~6/7 of the notes); a
-// half pass (4 notes) whose c_nt are ALL zero skips its Q_n accumulators -- half of its FFMAs -- and contributes exact zeros.
-template <int NC, int NTN, bool TAG, bool SKIPQ>
+template <int NC, int NTN>
 __global__ void __launch_bounds__(256, 2) recavg_bwd_fused_kernel(const PoolArgs a) {
   static_assert(NTN == 4 || NTN == 8, "notes per pass");
   extern __shared__ __align__(128) float s_dyn[];  // s_g [T][d] | s_x [8 warps][d]
@@ -1239,8 +1041,7 @@ __global__ void __launch_bounds__(256, 2) recavg_bwd_fused_kernel(const PoolArgs
           lds8(sg, k, dy);
           lds8(s_xw, k, x);
           load8(a.gamma, k, ga);
-          if (TAG && a.thr) keep_of8(x, inv_keep, ks);
-          else dropout_scale8(seed, IMMTSF_SITE_TTF_DROPOUT, (uint64_t)r * d8 + k, a.thr, inv_keep, ks);
+          dropout_scale8(seed, IMMTSF_SITE_TTF_DROPOUT, (uint64_t)r * d8 + k, a.thr, inv_keep, ks);
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             const float dye = dy[e] * ks[e];
@@ -1318,15 +1119,6 @@ __global__ void __launch_bounds__(256, 2) recavg_bwd_fused_kernel(const PoolArgs
         for (int tt = 0; tt < T; ++tt) sc_term = fmaf(s_c[tt][threadIdx.x], s_dw[tt], sc_term);
         dls += (double)sc_term;
       }
-      bool need_lo = true, need_hi = true;  // warp-uniform: does any (t, note) of the half pass have c_nt != 0 ?
-      if (SKIPQ) {
-        const float4 z0 = lane < T ? *reinterpret_cast<const float4*>(&s_c[lane][0]) : f4_zero();
-        need_lo = __any_sync(0xffffffffu, z0.x != 0.f || z0.y != 0.f || z0.z != 0.f || z0.w != 0.f);
-        if (NTN == 8) {
-          const float4 z1 = lane < T ? *reinterpret_cast<const float4*>(&s_c[lane][NTN - 4]) : f4_zero();
-          need_hi = __any_sync(0xffffffffu, z1.x != 0.f || z1.y != 0.f || z1.z != 0.f || z1.w != 0.f);
-        }
-      }
       if ((int)threadIdx.x < d4) {
         float4 accw[NTN], accc[NTN];
 #pragma unroll
@@ -1335,34 +1127,17 @@ __global__ void __launch_bounds__(256, 2) recavg_bwd_fused_kernel(const PoolArgs
         const bool half = NTN == 8 && ncnt <= 4;  // half-empty pass (CTA-uniform): skip the empty note slots
         for (int tt = 0; tt < T; ++tt) {
           const float4 g = gp[(size_t)tt * d4];
-          if (!SKIPQ) {
-            const float4 w0 = *reinterpret_cast<const float4*>(&s_w[tt][0]), c0 = *reinterpret_cast<const float4*>(&s_c[tt][0]);
-            f4_fma(accw[0], w0.x, g); f4_fma(accc[0], c0.x, g);
-            f4_fma(accw[1], w0.y, g); f4_fma(accc[1], c0.y, g);
-            f4_fma(accw[2], w0.z, g); f4_fma(accc[2], c0.z, g);
-            f4_fma(accw[3], w0.w, g); f4_fma(accc[3], c0.w, g);
-            if (NTN == 8 && !half) {
-              const float4 w1 = *reinterpret_cast<const float4*>(&s_w[tt][NTN - 4]), c1 = *reinterpret_cast<const float4*>(&s_c[tt][NTN - 4]);
-              f4_fma(accw[NTN - 4], w1.x, g); f4_fma(accc[NTN - 4], c1.x, g);
-              f4_fma(accw[NTN - 3], w1.y, g); f4_fma(accc[NTN - 3], c1.y, g);
-              f4_fma(accw[NTN - 2], w1.z, g); f4_fma(accc[NTN - 2], c1.z, g);
-              f4_fma(accw[NTN - 1], w1.w, g); f4_fma(accc[NTN - 1], c1.w, g);
-            }
-          } else {
-            const float4 w0 = *reinterpret_cast<const float4*>(&s_w[tt][0]);
-            f4_fma(accw[0], w0.x, g); f4_fma(accw[1], w0.y, g); f4_fma(accw[2], w0.z, g); f4_fma(accw[3], w0.w, g);
-            if (need_lo) {
-              const float4 c0 = *reinterpret_cast<const float4*>(&s_c[tt][0]);
-              f4_fma(accc[0], c0.x, g); f4_fma(accc[1], c0.y, g); f4_fma(accc[2], c0.z, g); f4_fma(accc[3], c0.w, g);
-            }
-            if (NTN == 8 && !half) {
-              const float4 w1 = *reinterpret_cast<const float4*>(&s_w[tt][NTN - 4]);
-              f4_fma(accw[NTN - 4], w1.x, g); f4_fma(accw[NTN - 3], w1.y, g); f4_fma(accw[NTN - 2], w1.z, g); f4_fma(accw[NTN - 1], w1.w, g);
-              if (need_hi) {
-                const float4 c1 = *reinterpret_cast<const float4*>(&s_c[tt][NTN - 4]);
-                f4_fma(accc[NTN - 4], c1.x, g); f4_fma(accc[NTN - 3], c1.y, g); f4_fma(accc[NTN - 2], c1.z, g); f4_fma(accc[NTN - 1], c1.w, g);
-              }
-            }
+          const float4 w0 = *reinterpret_cast<const float4*>(&s_w[tt][0]), c0 = *reinterpret_cast<const float4*>(&s_c[tt][0]);
+          f4_fma(accw[0], w0.x, g); f4_fma(accc[0], c0.x, g);
+          f4_fma(accw[1], w0.y, g); f4_fma(accc[1], c0.y, g);
+          f4_fma(accw[2], w0.z, g); f4_fma(accc[2], c0.z, g);
+          f4_fma(accw[3], w0.w, g); f4_fma(accc[3], c0.w, g);
+          if (NTN == 8 && !half) {
+            const float4 w1 = *reinterpret_cast<const float4*>(&s_w[tt][NTN - 4]), c1 = *reinterpret_cast<const float4*>(&s_c[tt][NTN - 4]);
+            f4_fma(accw[NTN - 4], w1.x, g); f4_fma(accc[NTN - 4], c1.x, g);
+            f4_fma(accw[NTN - 3], w1.y, g); f4_fma(accc[NTN - 3], c1.y, g);
+            f4_fma(accw[NTN - 2], w1.z, g); f4_fma(accc[NTN - 2], c1.z, g);
+            f4_fma(accw[NTN - 1], w1.w, g); f4_fma(accc[NTN - 1], c1.w, g);
           }
         }
         // every V' row of the pass is requested before the first store (stores to dV' may alias as far as the compiler
@@ -1402,286 +1177,16 @@ __global__ void __launch_bounds__(256, 2) recavg_bwd_fused_kernel(const PoolArgs
   }
 }
 
-template <int NC, int NTN, bool TAG, bool SKIPQ>
-static void launch_bwd_fused2(const PoolArgs& a, cudaStream_t st) {
+template <int NC, int NTN>
+static void launch_bwd_fused(const PoolArgs& a, cudaStream_t st) {
   const size_t smem = (size_t)(a.T + 8) * a.d * sizeof(float);
   static size_t smem_set = 0;
   if (smem + 4096 > 48 * 1024 && smem > smem_set) {
-    cudaFuncSetAttribute(recavg_bwd_fused_kernel<NC, NTN, TAG, SKIPQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(recavg_bwd_fused_kernel<NC, NTN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     smem_set = smem;
   }
-  recavg_bwd_fused_kernel<NC, NTN, TAG, SKIPQ>
-      <<<resident_grid((const void*)recavg_bwd_fused_kernel<NC, NTN, TAG, SKIPQ>, 256, smem, a.B, 2), 256, smem, st>>>(a);
-}
-template <int NC, int NTN>
-static void launch_bwd_fused(const PoolArgs& a, cudaStream_t st) {
-  const char* e = getenv("IMMTSF_RECAVG_SKIPQ");  // read per call (A/B inside one process)
-  const bool skipq = e && atoi(e) != 0;
-  if (a.maskbit) { if (skipq) launch_bwd_fused2<NC, NTN, true, true>(a, st); else launch_bwd_fused2<NC, NTN, true, false>(a, st); }
-  else { if (skipq) launch_bwd_fused2<NC, NTN, false, true>(a, st); else launch_bwd_fused2<NC, NTN, false, false>(a, st); }
-}
-
-// ------------------------------------------------------------------ backward, warp-specialised pipeline (experimental)
-// IMMTSF_RECAVG_BWD_PIPE=1, default off, NOT YET RUN ON A B200.  recavg_bwd_fused_kernel runs its rows phase and its note phase
-// one after the other with CTA-wide barriers in between (ncu: 19 % of the stall samples on barriers, 43 % issue utilisation).
-// Here the two phases belong to different warps of one persistent CTA per SM and overlap across consecutive samples:
-//   * 8 ROW warps: warp w owns the query rows t = w, w + 8, ... of the current sample; lane 0 fetches the (dE_drop, E_raw) row
-//     pair with two bulk copies into the warp's private buffer (own mbarrier), the warp writes dS_t into stage st of a two-stage
-//     dS ring and d(den_t) into s_dw[st], and arrives on full[st].  dgamma / dbeta stay in the row warps' registers for the
-//     whole kernel (no per-sample exchange) and are combined once at the end.
-//   * 2*NC NOTE warps (thread per float4 column): wait for full[st], contract dS with the recency weights exactly like the
-//     fused kernel's note phase (8 notes per pass, barrier 1 among the note warps only), write dV', arrive on empty[st].
-// Row warps wait for empty[st] before they overwrite a stage (sample it - 2).  mbarrier arrive / try_wait carry release / acquire
-// semantics at CTA scope; the lanes of a warp are ordered before their lane 0's arrive by __syncwarp().
-// smem (dynamic): s_g [2][T][d] | s_xy [8 warps][2 rows][d].  blockDim = 256 + 64 * NC, 1 CTA per SM.
-__device__ __forceinline__ void rs_mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void rs_named_bar(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-template <int NC, bool TAG, bool SKIPQ>
-__global__ void __launch_bounds__(256 + 64 * NC, 1) recavg_bwd_pipe_kernel(const PoolArgs a) {
-  constexpr int NTN = 8, NWN = 2 * NC, NOTE_THREADS = 32 * NWN;
-  extern __shared__ __align__(128) float s_dyn[];
-  __shared__ __align__(16) float s_w[POOL_TB][NTN];
-  __shared__ __align__(16) float s_c[POOL_TB][NTN];
-  __shared__ float s_dw[2][POOL_TB];
-  __shared__ __align__(8) unsigned long long s_full[2];
-  __shared__ __align__(8) unsigned long long s_empty[2];
-  __shared__ __align__(8) unsigned long long s_barx[8];
-  const int d = a.d, d8 = d >> 3, d4 = d >> 2, T = a.T;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  float* s_g = s_dyn;                                // [2][T][d]
-  float* s_xy = s_dyn + (size_t)2 * T * d;           // [8][2][d]
-  if (threadIdx.x == 0) {
-    rs_mbar_init(rs_smem_u32(&s_full[0]), 8); rs_mbar_init(rs_smem_u32(&s_full[1]), 8);
-    rs_mbar_init(rs_smem_u32(&s_empty[0]), NWN); rs_mbar_init(rs_smem_u32(&s_empty[1]), NWN);
-  }
-  if (w < 8 && lane == 0) rs_mbar_init(rs_smem_u32(&s_barx[w]), 1);
-  __syncthreads();
-  const uint32_t row_bytes = (uint32_t)d * 4u;
-  if (w < 8) {
-    // ================================================================ row warps
-    const float inv_keep = inv_keep_from_thr(a.thr), inv_d = 1.f / (float)d;
-    const uint64_t seed = resolve_seed(a.seed);
-    float* s_dy = s_xy + (size_t)w * 2 * d;
-    float* s_x = s_dy + d;
-    const uint32_t barx = rs_smem_u32(&s_barx[w]);
-    float dgam[NC][8], dbet[NC][8];
-#pragma unroll
-    for (int i = 0; i < NC; ++i) { zero8(dgam[i]); zero8(dbet[i]); }
-    uint32_t phx = 0;
-    auto fetch = [&](size_t r) {  // lane 0: the (dE_drop, E_raw) pair of row r into this warp's buffer
-      rs_mbar_expect_tx(barx, 2u * row_bytes);
-      rs_bulk_g2s(rs_smem_u32(s_dy), a.dE_drop + r * d, row_bytes, barx);
-      rs_bulk_g2s(rs_smem_u32(s_x), a.E_raw + r * d, row_bytes, barx);
-    };
-    if (lane == 0 && (int)blockIdx.x < a.B && w < T) fetch((size_t)blockIdx.x * T + w);
-    int it = 0;
-    for (int b = blockIdx.x; b < a.B; b += gridDim.x, ++it) {
-      const int st = it & 1;
-      float* sg_stage = s_g + (size_t)st * T * d;
-      if (it >= 2) rs_mbar_wait(rs_smem_u32(&s_empty[st]), (uint32_t)(((it >> 1) - 1) & 1));  // the note warps are done with sample it - 2
-      for (int t = w; t < T; t += 8) {
-        const size_t r = (size_t)b * T + t;
-        const float mu = a.mean[r], rs = a.rstd[r], ws = a.wsum[r];
-        const float den = fmaxf(ws, 1e-6f);
-        rs_mbar_wait(barx, phx);
-        phx ^= 1u;
-        float gg[NC][8];
-        float p1 = 0.f, p2 = 0.f;
-#pragma unroll
-        for (int i = 0; i < NC; ++i) {
-          const int k = lane + 32 * i;
-          zero8(gg[i]);
-          if (k < d8) {
-            float dy[8], x[8], ga[8], ks[8];
-            lds8(s_dy, k, dy);
-            lds8(s_x, k, x);
-            load8(a.gamma, k, ga);
-            if (TAG && a.thr) keep_of8(x, inv_keep, ks);
-            else dropout_scale8(seed, IMMTSF_SITE_TTF_DROPOUT, (uint64_t)r * d8 + k, a.thr, inv_keep, ks);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const float dye = dy[e] * ks[e];
-              const float he = (x[e] - mu) * rs;
-              dgam[i][e] = fmaf(dye, he, dgam[i][e]);
-              dbet[i][e] += dye;
-              gg[i][e] = dye * ga[e];
-              p1 += gg[i][e];
-              p2 = fmaf(gg[i][e], he, p2);
-            }
-          }
-        }
-        const float s2 = warp_sum(p2);
-        const float m1 = warp_sum(p1) * inv_d, m2 = s2 * inv_d;
-        const float sc = rs / den;
-        float* sg = sg_stage + (size_t)t * d;
-#pragma unroll
-        for (int i = 0; i < NC; ++i) {
-          const int k = lane + 32 * i;
-          if (k < d8) {
-            float x[8], o[8];  // dE_raw = rstd * (g - mean(g) - xhat * mean(g*xhat));  dS = dE_raw / den
-            lds8(s_x, k, x);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) o[e] = sc * (gg[i][e] - m1 - ((x[e] - mu) * rs) * m2);
-            sts8(sg, k, o);
-          }
-        }
-        if (lane == 0) s_dw[st][t] = ws >= 1e-6f ? -(s2 * a.eps * rs * rs) / den : 0.f;
-        __syncwarp();  // every lane is done with the row pair
-        if (lane == 0) {  // next row of this warp: same sample, or the warp's first row of its next sample
-          if (t + 8 < T) fetch(r + 8);
-          else if (b + (int)gridDim.x < a.B && w < T) fetch((size_t)(b + gridDim.x) * T + w);
-        }
-      }
-      __syncwarp();
-      if (lane == 0) rs_mbar_arrive(rs_smem_u32(&s_full[st]));  // this warp's dS rows and d(den) of sample b are in stage st
-    }
-    // dgamma / dbeta of this CTA: the 8 row warps take turns on one [2][d] array (the row buffers are idle now)
-    rs_named_bar(2, 256);
-    float* s_acc = s_xy;
-    for (int i = threadIdx.x; i < 2 * d; i += 256) s_acc[i] = 0.f;
-    for (int turn = 0; turn < 8; ++turn) {
-      rs_named_bar(2, 256);
-      if (w == turn) {
-#pragma unroll
-        for (int i = 0; i < NC; ++i) {
-          const int k = lane + 32 * i;
-          if (k < d8) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) { s_acc[8 * k + e] += dgam[i][e]; s_acc[d + 8 * k + e] += dbet[i][e]; }
-          }
-        }
-      }
-    }
-    rs_named_bar(2, 256);
-    for (int i = threadIdx.x; i < d; i += 256) {
-      atomicAdd(a.dgamma + i, s_acc[i]);
-      atomicAdd(a.dbeta + i, s_acc[d + i]);
-    }
-  } else {
-    // ================================================================ note warps
-    const int nt = threadIdx.x - 256;  // float4 column owned in the contraction
-    const float sigma = expf(__ldg(a.log_sigma));
-    double dls = 0.0;
-    int it = 0;
-    for (int b = blockIdx.x; b < a.B; b += gridDim.x, ++it) {
-      const int st = it & 1;
-      const int nb = a.offsets[b], ne = a.offsets[b + 1];
-      const float* sg_stage = s_g + (size_t)st * T * d;
-      if (nt == 0 && ne > nb && a.ldv == d)  // V' rows are needed by the epilogues only: start them towards L2
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.Vp + (size_t)nb * a.ldv), "r"((uint32_t)(ne - nb) * row_bytes) : "memory");
-      bool waited = false;
-      for (int n0 = nb; n0 < ne; n0 += NTN) {
-        const int ncnt = min(NTN, ne - n0);
-        rs_named_bar(1, NOTE_THREADS);  // the previous pass (or sample) has consumed s_w / s_c
-        for (int i = nt; i < T * NTN; i += NOTE_THREADS) {
-          const int tt = i / NTN, u = i % NTN;
-          float wv = 0.f, cc = 0.f;
-          if (u < ncnt) {
-            const float delta = fmaxf(a.t_hat[(size_t)b * a.t_bstride + tt] - __ldg(a.tau + n0 + u), 0.f);
-            const float rr = delta / sigma;
-            wv = expf(-(rr * rr));
-            cc = wv * 2.f * rr * rr;
-          }
-          s_w[tt][u] = wv;
-          s_c[tt][u] = cc;
-        }
-        rs_named_bar(1, NOTE_THREADS);
-        if (!waited) {  // the weights of the first pass do not depend on dS: computed before the wait
-          rs_mbar_wait(rs_smem_u32(&s_full[st]), (uint32_t)((it >> 1) & 1));
-          waited = true;
-        }
-        if (nt < NTN) {  // sum_t c_nt d(den_t), thread u owns note u
-          float sc_term = 0.f;
-          for (int tt = 0; tt < T; ++tt) sc_term = fmaf(s_c[tt][nt], s_dw[st][tt], sc_term);
-          dls += (double)sc_term;
-        }
-        bool need_lo = true, need_hi = true;
-        if (SKIPQ) {
-          const float4 z0 = lane < T ? *reinterpret_cast<const float4*>(&s_c[lane][0]) : f4_zero();
-          const float4 z1 = lane < T ? *reinterpret_cast<const float4*>(&s_c[lane][4]) : f4_zero();
-          need_lo = __any_sync(0xffffffffu, z0.x != 0.f || z0.y != 0.f || z0.z != 0.f || z0.w != 0.f);
-          need_hi = __any_sync(0xffffffffu, z1.x != 0.f || z1.y != 0.f || z1.z != 0.f || z1.w != 0.f);
-        }
-        if (nt < d4) {
-          float4 accw[NTN], accc[NTN];
-#pragma unroll
-          for (int u = 0; u < NTN; ++u) { accw[u] = f4_zero(); accc[u] = f4_zero(); }
-          const float4* gp = reinterpret_cast<const float4*>(sg_stage) + nt;
-          const bool half = ncnt <= 4;  // half-empty pass: skip the empty note slots
-          for (int tt = 0; tt < T; ++tt) {
-            const float4 g = gp[(size_t)tt * d4];
-            const float4 w0 = *reinterpret_cast<const float4*>(&s_w[tt][0]);
-            f4_fma(accw[0], w0.x, g); f4_fma(accw[1], w0.y, g); f4_fma(accw[2], w0.z, g); f4_fma(accw[3], w0.w, g);
-            if (need_lo) {
-              const float4 c0 = *reinterpret_cast<const float4*>(&s_c[tt][0]);
-              f4_fma(accc[0], c0.x, g); f4_fma(accc[1], c0.y, g); f4_fma(accc[2], c0.z, g); f4_fma(accc[3], c0.w, g);
-            }
-            if (!half) {
-              const float4 w1 = *reinterpret_cast<const float4*>(&s_w[tt][4]);
-              f4_fma(accw[4], w1.x, g); f4_fma(accw[5], w1.y, g); f4_fma(accw[6], w1.z, g); f4_fma(accw[7], w1.w, g);
-              if (need_hi) {
-                const float4 c1 = *reinterpret_cast<const float4*>(&s_c[tt][4]);
-                f4_fma(accc[4], c1.x, g); f4_fma(accc[5], c1.y, g); f4_fma(accc[6], c1.z, g); f4_fma(accc[7], c1.w, g);
-              }
-            }
-          }
-#pragma unroll
-          for (int h0 = 0; h0 < NTN; h0 += 4) {  // four V' rows requested before the first store
-            float4 vv[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-              vv[u] = h0 + u < ncnt ? __ldg(reinterpret_cast<const float4*>(a.Vp + (size_t)(n0 + h0 + u) * a.ldv) + nt) : f4_zero();
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const float4 q = accc[h0 + u], v = vv[u];  // empty slots: q == v == 0
-              dls += (double)q.x * v.x + (double)q.y * v.y + (double)q.z * v.z + (double)q.w * v.w;
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-              if (h0 + u < ncnt) reinterpret_cast<float4*>(a.dVp + (size_t)(n0 + h0 + u) * a.lddv)[nt] = accw[h0 + u];
-          }
-        }
-      }
-      if (!waited) rs_mbar_wait(rs_smem_u32(&s_full[st]), (uint32_t)((it >> 1) & 1));  // sample without notes: keep the phases in step
-      __syncwarp();
-      if (lane == 0) rs_mbar_arrive(rs_smem_u32(&s_empty[st]));  // this warp no longer reads stage st
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) dls += __shfl_xor_sync(0xffffffffu, dls, o);
-    if (lane == 0) atomicAdd(a.dlog_sigma, dls);
-  }
-}
-
-template <int NC, bool TAG, bool SKIPQ>
-static void launch_bwd_pipe2(const PoolArgs& a, cudaStream_t st) {
-  const size_t smem = (size_t)(2 * a.T + 16) * a.d * sizeof(float);
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    cudaFuncSetAttribute(recavg_bwd_pipe_kernel<NC, TAG, SKIPQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    smem_set = smem;
-  }
-  const int grid = a.B < 148 ? a.B : 148;
-  recavg_bwd_pipe_kernel<NC, TAG, SKIPQ><<<grid, 256 + 64 * NC, smem, st>>>(a);
-}
-template <int NC>
-static void launch_bwd_pipe(const PoolArgs& a, cudaStream_t st) {
-  const char* e = getenv("IMMTSF_RECAVG_SKIPQ");
-  const bool skipq = e && atoi(e) != 0;
-  if (a.maskbit) { if (skipq) launch_bwd_pipe2<NC, true, true>(a, st); else launch_bwd_pipe2<NC, true, false>(a, st); }
-  else { if (skipq) launch_bwd_pipe2<NC, false, true>(a, st); else launch_bwd_pipe2<NC, false, false>(a, st); }
-}
-
-// Keep flags in the LSB of E_raw (experimental, see tag_keep): decided from what BOTH entry points see, so that the forward
-// and the backward of one step agree; read per call (tests A/B the two conventions inside one process).
-static int recavg_maskbit(int d, int N_max) {
-  const char* e = getenv("IMMTSF_RECAVG_MASKBIT");
-  if (!e || atoi(e) == 0) return 0;
-  const char* t = getenv("IMMTSF_RECAVG_TMA");
-  return rowwarp_nc(d) > 0 && N_max <= 32 && !(t && t[0] == '0');
+  recavg_bwd_fused_kernel<NC, NTN>
+      <<<resident_grid((const void*)recavg_bwd_fused_kernel<NC, NTN>, 256, smem, a.B, 2), 256, smem, st>>>(a);
 }
 
 static int pool_geometry(int d, int& nch, int& threads) {
@@ -1709,7 +1214,6 @@ extern "C" int immtsf_recavg_pool_fwd(const float* Vp, int ldv, const float* tau
   a.Vp = Vp; a.ldv = ldv; a.tau = tau_flat; a.offsets = offsets; a.t_hat = t_hat; a.t_bstride = t_hat_bstride;
   a.log_sigma = log_sigma; a.gamma = gamma; a.beta = beta; a.B = B; a.T = T; a.d = d; a.eps = eps;
   a.thr = drop_thr; a.seed = make_seed(seed); a.E_drop = E_drop; a.E_raw = E_raw; a.mean = mean; a.rstd = rstd; a.wsum = wsum;
-  a.maskbit = recavg_maskbit(d, N_max);
   cudaStream_t st = (cudaStream_t)stream;
   // Short segments (Time-IMM: a handful of notes per window): one warp per query time, the 8 warps of a CTA share
   // the segment through L1.  Long segments: the CTA-tile kernel streams each V' row once per 8 query times.
@@ -1727,14 +1231,6 @@ extern "C" int immtsf_recavg_pool_fwd(const float* Vp, int ldv, const float* tau
       int tpw_s = (nc <= 3 && T > 16) ? 3 : 1;  // measured (profiles/r1_sweep_hbm_v4.json): T 24: 3 > 1 > 2; T 16: 1 > 2 > 3
       static const int tpw_env = []() { const char* e = getenv("IMMTSF_RECAVG_TPW"); return e ? atoi(e) : 0; }();
       if (tpw_env >= 1 && tpw_env <= 3 && nc <= 3) tpw_s = tpw_env;
-      const char* pe = getenv("IMMTSF_RECAVG_FWD_PERSIST");  // experimental, read per call (A/B inside one process)
-      if (pe && atoi(pe) != 0 && nc <= 3 && N_max <= RS && tpw_s != 2) {
-        if (nc == 1) launch_fwd_p<1>(a, tpw_s, RS, st);
-        else if (nc == 2) launch_fwd_p<2>(a, tpw_s, RS, st);
-        else launch_fwd_p<3>(a, tpw_s, RS, st);
-        IMMTSF_CHECK_LAUNCH("recavg_pool_fwd_p");
-        return IMMTSF_OK;
-      }
       if (nc == 1) launch_fwd_s<1>(a, tpw_s, T, B, RS, smem_s, st);
       else if (nc == 2) launch_fwd_s<2>(a, tpw_s, T, B, RS, smem_s, st);
       else if (nc == 3) launch_fwd_s<3>(a, tpw_s, T, B, RS, smem_s, st);
@@ -1742,7 +1238,6 @@ extern "C" int immtsf_recavg_pool_fwd(const float* Vp, int ldv, const float* tau
       IMMTSF_CHECK_LAUNCH("recavg_pool_fwd_s");
       return IMMTSF_OK;
     }
-    IMMTSF_REQUIRE(!a.maskbit, "recavg_pool_fwd: IMMTSF_RECAVG_MASKBIT needs the staged kernel (16B-aligned V', ld %% 4 == 0)");
 #define FWD_W(NCV)                                                                    \
   do {                                                                                \
     if (tpw == 3) recavg_pool_fwd_w_kernel<NCV, 3><<<gridw, 256, 0, st>>>(a);         \
@@ -1757,7 +1252,6 @@ extern "C" int immtsf_recavg_pool_fwd(const float* Vp, int ldv, const float* tau
     IMMTSF_CHECK_LAUNCH("recavg_pool_fwd_w");
     return IMMTSF_OK;
   }
-  IMMTSF_REQUIRE(!a.maskbit, "recavg_pool_fwd: IMMTSF_RECAVG_MASKBIT needs 16B-aligned gamma / beta / E_drop / E_raw");
   const int TT = 8 / nch;
   dim3 grid(ceil_div(T, TT), B);
   if (nch == 1) recavg_pool_fwd_kernel<1><<<grid, threads, 0, st>>>(a);
@@ -1788,7 +1282,6 @@ extern "C" int immtsf_recavg_pool_bwd(const float* dE_drop, const float* E_raw, 
   a.rstd = const_cast<float*>(rstd); a.wsum = const_cast<float*>(wsum);
   a.dE_drop = dE_drop; a.dVp = dVp; a.lddv = lddv; a.dgamma = dgamma; a.dbeta = dbeta; a.dlog_sigma = dlog_sigma;
   a.dS = dS; a.N_max = N_max;
-  a.maskbit = recavg_maskbit(d, N_max);
   cudaStream_t st = (cudaStream_t)stream;
   const int nc = rowwarp_nc(d);
   // Short prediction windows and segments (N_max <= 32: at N <= 64, T 28 the two-kernel path measured 272 us against 339 us,
@@ -1797,17 +1290,6 @@ extern "C" int immtsf_recavg_pool_bwd(const float* dE_drop, const float* E_raw, 
   const char* fused_env = getenv("IMMTSF_RECAVG_FUSED_BWD");  // read per call: tests A/B the two paths inside one process
   const char* tma_env = getenv("IMMTSF_RECAVG_TMA");  // =0 means "no bulk-copy kernels at all": the fused kernel is one
   const int fused = (tma_env && tma_env[0] == '0') ? 0 : (fused_env ? atoi(fused_env) : IMMTSF_RECAVG_FUSED_BWD_DEFAULT);
-  const char* pipe_env = getenv("IMMTSF_RECAVG_BWD_PIPE");  // experimental warp-specialised backward, read per call
-  if (pipe_env && atoi(pipe_env) != 0 && fused && nc > 0 && T <= POOL_TB && N_max <= 32 &&
-      (size_t)(2 * T + 16) * d * sizeof(float) <= 220 * 1024 && ((uintptr_t)gamma & 15) == 0 && ((uintptr_t)dE_drop & 15) == 0 &&
-      ((uintptr_t)E_raw & 15) == 0) {
-    if (nc == 1) launch_bwd_pipe<1>(a, st);
-    else if (nc == 2) launch_bwd_pipe<2>(a, st);
-    else if (nc == 3) launch_bwd_pipe<3>(a, st);
-    else launch_bwd_pipe<4>(a, st);
-    IMMTSF_CHECK_LAUNCH("recavg_bwd_pipe");
-    return IMMTSF_OK;
-  }
   if (fused && nc > 0 && T <= POOL_TB && N_max <= 32 && (size_t)(T + 8) * d * sizeof(float) <= 108 * 1024 && ((uintptr_t)gamma & 15) == 0 &&
       ((uintptr_t)dE_drop & 15) == 0 && ((uintptr_t)E_raw & 15) == 0) {
 #define BWD_F(NCV) do { if (fused == 4) launch_bwd_fused<NCV, 4>(a, st); else launch_bwd_fused<NCV, 8>(a, st); } while (0)
@@ -1828,18 +1310,15 @@ extern "C" int immtsf_recavg_pool_bwd(const float* dE_drop, const float* E_raw, 
       else if (nc == 3) launch_rows_s<3>(a, want, st);
       else launch_rows_s<4>(a, want, st);
     } else {
-#define ROWS_W2(NCV, TAGV) recavg_bwd_rows_w_kernel<NCV, TAGV><<<resident_grid((const void*)recavg_bwd_rows_w_kernel<NCV, TAGV>, 128, 0, want, 4), 128, 0, st>>>(a)
-#define ROWS_W(NCV) do { if (a.maskbit) ROWS_W2(NCV, true); else ROWS_W2(NCV, false); } while (0)
+#define ROWS_W(NCV) recavg_bwd_rows_w_kernel<NCV><<<resident_grid((const void*)recavg_bwd_rows_w_kernel<NCV>, 128, 0, want, 4), 128, 0, st>>>(a)
     if (nc == 1) ROWS_W(1);
     else if (nc == 2) ROWS_W(2);
     else if (nc == 3) ROWS_W(3);
     else ROWS_W(4);
 #undef ROWS_W
-#undef ROWS_W2
     }
     IMMTSF_CHECK_LAUNCH("recavg_bwd_rows_w");
   } else {
-    IMMTSF_REQUIRE(!a.maskbit, "recavg_pool_bwd: IMMTSF_RECAVG_MASKBIT needs 16B-aligned gamma / dE_drop / E_raw");
     const int TT = 8 / nch;
     dim3 grid1(ceil_div(T, TT), B);
     if (nch == 1) recavg_bwd_rows_kernel<1><<<grid1, threads, 0, st>>>(a);

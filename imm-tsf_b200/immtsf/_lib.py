@@ -43,7 +43,7 @@ SIGNATURES = {
     "immtsf_recavg_pool_fwd": [P, I, P, P, P, I, P, P, P, I, I, I, I, F, U32, U64, P, P, P, P, P, P],
     "immtsf_recavg_pool_bwd": [P, P, P, P, P, P, I, P, P, P, I, P, P, I, I, I, I, U32, U64, P, P, I, P, P, P, P],
     "immtsf_time2vec_fwd": [P, P, P, P, P, I, P, I, P, I, P, I, P],
-    "immtsf_time2vec_bwd": [P, I, P, P, P, I, P, P, P, P, P, I, P],
+    "immtsf_time2vec_bwd": [P, I, P, P, P, I, P, P, P, P, P, I, P, SZ, P, P],
     "immtsf_segattn_fwd": [P, P, P, I, I, I, I, I, I, U32, U64, P, P, P],
     "immtsf_segattn_bwd": [P, P, P, P, P, I, I, I, I, I, I, U32, U64, P, P, P],
     "immtsf_t2vq_attn_fwd": [P, I, P, P, P, P, P, I, P, P, P, P, I, I, I, I, I, I, I, U32, U64, P, P, P, P, P],
@@ -109,6 +109,8 @@ def load():
     lib.immtsf_gemm_workspace_bytes.restype = SZ
     lib.immtsf_t2vq_bwd_workspace_bytes.argtypes = [I, I, I]
     lib.immtsf_t2vq_bwd_workspace_bytes.restype = SZ
+    lib.immtsf_time2vec_bwd_workspace_bytes.argtypes = [I]
+    lib.immtsf_time2vec_bwd_workspace_bytes.restype = SZ
     lib.immtsf_masked_mse_workspace_bytes.argtypes = [I]
     lib.immtsf_masked_mse_workspace_bytes.restype = SZ
     lib.immtsf_gemm_batched_workspace_bytes.argtypes = [I, I, I, I, I, I, L, L, I, L, L, I, I]
@@ -142,10 +144,25 @@ def profile_gemm_tc(max_records: int = 4096):
     return cm()
 
 
+# bench.py: {entry name: []} -> every call of a listed entry point is bracketed by a CUDA-event pair on the current
+# (= launching) stream and (ev0, ev1) is appended to its list.  None: no instrumentation.
+PROFILE = None
+
+
 def call(name, *args):
     """Call an entry point; raise ImmtsfError with the library's message on failure."""
     lib = load()
-    rc = getattr(lib, name)(*args)
+    prof = PROFILE
+    if prof is not None and name in prof:
+        import torch
+
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        rc = getattr(lib, name)(*args)
+        ev1.record()
+        prof[name].append((ev0, ev1))
+    else:
+        rc = getattr(lib, name)(*args)
     if rc != 0:
         msg = lib.immtsf_last_error_string()
         raise ImmtsfError(f"{name} failed (rc={rc}): {msg.decode() if msg else ''}")

@@ -106,6 +106,19 @@ def nan_check(x: torch.Tensor, flags: torch.Tensor, slot: int):
     _lib.call("immtsf_nan_check", _p(x), x.numel(), _p(flags), slot, _stream())
 
 
+_TICKET = {}
+
+
+def ticket(dev) -> torch.Tensor:
+    """One zero-initialised device counter per device for the kernels that end with a last-CTA ordered reduction (they leave
+    it at zero).  Launches that use it are ordered on a stream or run in different steps."""
+    key = torch.device(dev).index
+    t = _TICKET.get(key)
+    if t is None:
+        t = _TICKET[key] = torch.zeros(4, dtype=torch.int32, device=dev)
+    return t
+
+
 def zero_pad_rows(X: torch.Tensor, ncols: int, m_dev: torch.Tensor, M_alloc: int):
     _lib.call("immtsf_zero_pad_rows", _p(X), X.stride(0), ncols, _p(m_dev), M_alloc, _stream())
 
@@ -446,12 +459,13 @@ def time2vec_fwd(r: RaggedNotes, w_lin, b_lin, w_per, b_per, d_tau, out_view, lo
 
 def time2vec_bwd(dphi_view, r: RaggedNotes, w_per, b_per, d_tau):
     dev = dphi_view.device
-    dwl = torch.zeros(1, 1, dtype=torch.float32, device=dev)
-    dbl = torch.zeros(1, dtype=torch.float32, device=dev)
-    dwp = torch.zeros(d_tau - 1, 1, dtype=torch.float32, device=dev)
-    dbp = torch.zeros(d_tau - 1, dtype=torch.float32, device=dev)
+    dwl = torch.empty(1, 1, dtype=torch.float32, device=dev)
+    dbl = torch.empty(1, dtype=torch.float32, device=dev)
+    dwp = torch.empty(d_tau - 1, 1, dtype=torch.float32, device=dev)
+    dbp = torch.empty(d_tau - 1, dtype=torch.float32, device=dev)
+    ws = torch.empty(_lib.load().immtsf_time2vec_bwd_workspace_bytes(d_tau) // 8, dtype=torch.float64, device=dev)
     _lib.call("immtsf_time2vec_bwd", _p(dphi_view), dphi_view.stride(0), _p(r.tau_flat), _p(w_per), _p(b_per), d_tau,
-              _p(dwl), _p(dbl), _p(dwp), _p(dbp), _p(r.m_dev), r.M_alloc, _stream())
+              _p(dwl), _p(dbl), _p(dwp), _p(dbp), _p(r.m_dev), r.M_alloc, _p(ws), ws.numel() * 8, _p(ticket(dev)), _stream())
     return dwl, dbl, dwp, dbp
 
 

@@ -97,7 +97,7 @@ def mha(
     q = q * math.sqrt(1.0 / float(hd))
     s = q @ k.transpose(-1, -2)  # [Bq,H,L,S]
     if key_padding_mask is not None:
-        neg = torch.zeros(Bq, 1, 1, S, dtype=s.dtype)
+        neg = torch.zeros(Bq, 1, 1, S, dtype=s.dtype, device=s.device)
         neg = neg.masked_fill(key_padding_mask.view(Bq, 1, 1, S), float("-inf"))
         s = s + neg
     a = torch.softmax(s, dim=-1)
@@ -112,7 +112,7 @@ def gru(x: Tensor, w_ih: Tensor, w_hh: Tensor, b_ih: Tensor, b_hh: Tensor) -> Te
     (fusions/MMF_GR_Add.py:20-22,46)."""
     B, T, _ = x.shape
     Hd = w_hh.shape[1]
-    h = torch.zeros(B, Hd, dtype=x.dtype)
+    h = torch.zeros(B, Hd, dtype=x.dtype, device=x.device)
     gi_all = linear(x, w_ih, b_ih)  # [B,T,3H]
     outs = []
     for t in range(T):
