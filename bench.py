@@ -464,7 +464,9 @@ def run_gpu_arm(args, w):
             e0.record()
             src = d_in if resident else h_in
             if graphed is not None:
-                loss = graphed(*src)  # copies into the static buffers (H2D when src is pinned host memory) + one replay
+                if resident:
+                    src = graphed.static_in  # resident = the batch already sits in the step's input buffers: no copy at all
+                loss = graphed(*src)  # (host source: H2D into the static buffers) + one replay
                 if world > 1 and graphed.group is None:
                     dp.allreduce_grads(params, flat=graphed.flat_grads)  # (in-graph mode: the replay already reduced)
                 if check:

@@ -40,56 +40,35 @@ __global__ void time2vec_fwd_kernel(const float* __restrict__ tau, const float* 
   }
 }
 
-// grid.x over feature tiles of 32, grid.y over row chunks; 32x8 threads.  The linear unit's gradients (and, less so, the
-// periodic ones) are signed sums over every note with heavy cancellation (the reference's own fp32-vs-fp64 gap on them is
-// 4e-5 relative), so they are accumulated in DOUBLE end to end: per thread, per CTA, and across CTAs -- every CTA writes
-// its partials, the last one (ticket) adds them in CTA order.  Deterministic, no atomics on data.
+// grid.x over feature tiles of 32, grid.y over row chunks; 32x8 threads
 __global__ void time2vec_bwd_kernel(const float* __restrict__ dphi, int ld, const float* __restrict__ tau,
                                     const float* __restrict__ w_per, const float* __restrict__ b_per, int d_tau,
                                     float* __restrict__ dw_lin, float* __restrict__ db_lin, float* __restrict__ dw_per,
-                                    float* __restrict__ db_per, const int32_t* __restrict__ m_dev, int M_alloc,
-                                    double* __restrict__ partial, unsigned int* __restrict__ ticket) {
-  __shared__ double rw[8][33], rb[8][33];
-  __shared__ bool s_last;
+                                    float* __restrict__ db_per, const int32_t* __restrict__ m_dev, int M_alloc) {
+  __shared__ float rw[8][33], rb[8][33];
   const int m = ragged_rows(M_alloc, m_dev);
   const int k = blockIdx.x * 32 + threadIdx.x;
-  double sw = 0.0, sb = 0.0;
+  float sw = 0.f, sb = 0.f;
   if (k < d_tau) {
     const float wk = k == 0 ? 0.f : w_per[k - 1], bk = k == 0 ? 0.f : b_per[k - 1];
     for (int n = blockIdx.y * 8 + threadIdx.y; n < m; n += gridDim.y * 8) {
       const float t = tau[n];
       const float g = dphi[(size_t)n * ld + k];
       const float dpre = k == 0 ? g : g * cosf(fmaf(wk, t, bk));
-      sw += (double)dpre * (double)t;
-      sb += (double)dpre;
+      sw = fmaf(dpre, t, sw);
+      sb += dpre;
     }
   }
   rw[threadIdx.y][threadIdx.x] = sw;
   rb[threadIdx.y][threadIdx.x] = sb;
   __syncthreads();
   if (threadIdx.y == 0 && k < d_tau) {
-    double a = 0.0, c = 0.0;
+    float a = 0.f, c = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) { a += rw[i][threadIdx.x]; c += rb[i][threadIdx.x]; }
-    partial[((size_t)blockIdx.y * 2 + 0) * d_tau + k] = a;
-    partial[((size_t)blockIdx.y * 2 + 1) * d_tau + k] = c;
+    if (k == 0) { atomicAdd(dw_lin, a); atomicAdd(db_lin, c); }
+    else { atomicAdd(dw_per + k - 1, a); atomicAdd(db_per + k - 1, c); }
   }
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0 && threadIdx.y == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x * gridDim.y - 1;
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  for (int kk = threadIdx.y * 32 + threadIdx.x; kk < d_tau; kk += 256) {
-    double a = 0.0, c = 0.0;
-    for (unsigned int g = 0; g < gridDim.y; ++g) {
-      a += partial[((size_t)g * 2 + 0) * d_tau + kk];
-      c += partial[((size_t)g * 2 + 1) * d_tau + kk];
-    }
-    if (kk == 0) { *dw_lin = (float)a; *db_lin = (float)c; }
-    else { dw_per[kk - 1] = (float)a; db_per[kk - 1] = (float)c; }
-  }
-  if (threadIdx.x == 0 && threadIdx.y == 0) *ticket = 0u;  // ready for the next launch
 }
 
 extern "C" int immtsf_time2vec_fwd(const float* tau_flat, const float* w_lin, const float* b_lin, const float* w_per,
@@ -106,21 +85,16 @@ extern "C" int immtsf_time2vec_fwd(const float* tau_flat, const float* w_lin, co
   return IMMTSF_OK;
 }
 
-extern "C" size_t immtsf_time2vec_bwd_workspace_bytes(int d_tau) { return (size_t)64 * 2 * (d_tau > 0 ? d_tau : 0) * sizeof(double); }
-
 extern "C" int immtsf_time2vec_bwd(const float* dphi, int ld, const float* tau_flat, const float* w_per,
                                    const float* b_per, int d_tau, float* dw_lin, float* db_lin, float* dw_per,
-                                   float* db_per, const int32_t* m_dev, int M_alloc, void* workspace, size_t workspace_bytes,
-                                   uint32_t* ticket, void* stream) {
+                                   float* db_per, const int32_t* m_dev, int M_alloc, void* stream) {
   if (M_alloc == 0) return IMMTSF_OK;
-  IMMTSF_REQUIRE(dphi && tau_flat && w_per && b_per && dw_lin && db_lin && dw_per && db_per && m_dev && ticket, "time2vec_bwd: null pointer");
+  IMMTSF_REQUIRE(dphi && tau_flat && w_per && b_per && dw_lin && db_lin && dw_per && db_per && m_dev, "time2vec_bwd: null pointer");
   int gy = ceil_div(M_alloc, 64);
   if (gy > 64) gy = 64;
-  IMMTSF_REQUIRE(workspace && ((uintptr_t)workspace & 7) == 0 && workspace_bytes >= immtsf_time2vec_bwd_workspace_bytes(d_tau),
-                 "time2vec_bwd: workspace too small or misaligned");
   dim3 grid(ceil_div(d_tau, 32), gy);
   time2vec_bwd_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(dphi, ld, tau_flat, w_per, b_per, d_tau, dw_lin, db_lin,
-                                                                       dw_per, db_per, m_dev, M_alloc, (double*)workspace, ticket);
+                                                                       dw_per, db_per, m_dev, M_alloc);
   IMMTSF_CHECK_LAUNCH("time2vec_bwd");
   return IMMTSF_OK;
 }

@@ -10,6 +10,8 @@ eval / dropout-0 mode the T_f identical output rows are computed once and
 returned as a broadcast view."""
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -79,7 +81,9 @@ class TTF_T2V_XAttn(nn.Module):
                   at.out_proj.weight, at.out_proj.bias, self.layer_norm.weight, self.layer_norm.bias,
                   self.proj_out.weight, self.proj_out.bias)
         save = F_._need_save(*params)
-        E_txt = F_.T2VXAttnFn.apply(r, T, self.n_heads, thr, seed, save, bool(defer), *params)
+        # one head in train mode: the collapsed schedule (key projection = one vector, input_proj folded into KV_proj)
+        fn = F_.T2VXAttnFoldFn if (thr != 0 and self.n_heads == 1 and os.environ.get("IMMTSF_T2V_COLLAPSE", "1") != "0") else F_.T2VXAttnFn
+        E_txt = fn.apply(r, T, self.n_heads, thr, seed, save, bool(defer), *params)
         return E_txt, cm.m_txt_bool(r)
 
     def forward(self, notes_input, tau: torch.Tensor, t_hat: torch.Tensor):

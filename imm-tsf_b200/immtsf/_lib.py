@@ -43,7 +43,7 @@ SIGNATURES = {
     "immtsf_recavg_pool_fwd": [P, I, P, P, P, I, P, P, P, I, I, I, I, F, U32, U64, P, P, P, P, P, P],
     "immtsf_recavg_pool_bwd": [P, P, P, P, P, P, I, P, P, P, I, P, P, I, I, I, I, U32, U64, P, P, I, P, P, P, P],
     "immtsf_time2vec_fwd": [P, P, P, P, P, I, P, I, P, I, P, I, P],
-    "immtsf_time2vec_bwd": [P, I, P, P, P, I, P, P, P, P, P, I, P, SZ, P, P],
+    "immtsf_time2vec_bwd": [P, I, P, P, P, I, P, P, P, P, P, I, P],
     "immtsf_segattn_fwd": [P, P, P, I, I, I, I, I, I, U32, U64, P, P, P],
     "immtsf_segattn_bwd": [P, P, P, P, P, I, I, I, I, I, I, U32, U64, P, P, P],
     "immtsf_t2vq_attn_fwd": [P, I, P, P, P, P, P, I, P, P, P, P, I, I, I, I, I, I, I, U32, U64, P, P, P, P, P],
@@ -109,8 +109,6 @@ def load():
     lib.immtsf_gemm_workspace_bytes.restype = SZ
     lib.immtsf_t2vq_bwd_workspace_bytes.argtypes = [I, I, I]
     lib.immtsf_t2vq_bwd_workspace_bytes.restype = SZ
-    lib.immtsf_time2vec_bwd_workspace_bytes.argtypes = [I]
-    lib.immtsf_time2vec_bwd_workspace_bytes.restype = SZ
     lib.immtsf_masked_mse_workspace_bytes.argtypes = [I]
     lib.immtsf_masked_mse_workspace_bytes.restype = SZ
     lib.immtsf_gemm_batched_workspace_bytes.argtypes = [I, I, I, I, I, I, L, L, I, L, L, I, I]

@@ -72,10 +72,9 @@ class RecAvgFn(torch.autograd.Function):
 
 # ============================================================== TTF_T2V_XAttn
 class T2VXAttnFn(torch.autograd.Function):
-    """TTF_T2V_XAttn.py:93-184.  K/V projections run once per note.  With one head and attention dropout (train mode:
-    every (sample, query) row is distinct) the MHA out-projection is folded into the value projection in weight
-    space -- sum_n p_n (v_n W_o^T) = (sum_n p_n v_n) W_o^T -- so it also runs once per note instead of once per
-    (sample, query) row; its bias is added inside the LayerNorm kernel (xbias)."""
+    """TTF_T2V_XAttn.py:93-184, general schedule (any head count; eval mode).  K/V projections run once per note.  In eval /
+    dropout-0 mode the T_f output rows of a sample are identical: they are computed once and returned as a broadcast view.
+    (One head in train mode takes T2VXAttnFoldFn below.)"""
 
     @staticmethod
     def forward(ctx, r: RaggedNotes, T, H, thr, seed, save, defer, Qp, W_in, b_in, w_lin, b_lin, w_per, b_per, W_kv, b_kv,
@@ -90,55 +89,41 @@ class T2VXAttnFn(torch.autograd.Function):
         step = ops.step_ctx()
         lo = step.lo
         per_query = thr != 0  # attention dropout makes every (sample, query) row distinct
-        fold = per_query and H == 1
         # [V' ; phi] concat buffer (TTF_T2V_XAttn.py:139) and its tcgen05 lo operand, both written in place by the
         # two producers (input_proj epilogue / Time2Vec kernel): no separate split pass
         Xcat, Xcat_lo = new(r.M_alloc, d + dt), new(r.M_alloc, ops.round_up(d + dt, 4))
-        # every weight matrix's lo, and the packed [W_k ; W_o W_v] operand's first half, in one launch
-        extra = []
-        if fold:
-            Wkv, bkv, Wkv_lo = new(2 * d, d), new(2 * d), new(2 * d, d)
-            extra = [(in_w[d:2 * d], Wkv[:d], Wkv_lo[:d]), (in_b[d:2 * d], bkv[:d], None)]
-        if W_in is None:
-            extra.append((r.emb_flat, Xcat[:, :d], Xcat_lo[:, :d]))
+        extra = [(r.emb_flat, Xcat[:, :d], Xcat_lo[:, :d])] if W_in is None else []
         ws = [(W_in, [])] if W_in is not None else []
-        ws += [(W_kv, []), (in_w, [slice(d, None), slice(2 * d, None)]), (out_w, [])] + ([] if defer else [(W_po, [])])
-        ops.weight_los(lo, ws, extra)
+        ws += [(W_kv, []), (in_w, [slice(d, None)]), (out_w, [])] + ([] if defer else [(W_po, [])])
+        ops.weight_los(lo, ws, extra)  # every weight matrix's lo in one launch
         if W_in is not None:
             ops.gemm(r.emb_flat, W_in, Xcat[:, :d], transB=True, bias=b_in, ragged=r.m_dev, ragged_dim=1, lo=lo,
                      emit_lo=Xcat_lo[:, :d])
         ops.time2vec_fwd(r, w_lin, b_lin, w_per, b_per, dt, Xcat[:, d:], Xcat_lo[:, d:])
         lo.put(Xcat, Xcat_lo)
         X = ops.linear_fwd(Xcat, W_kv, b_kv, ragged=r.m_dev, lo=lo, emit_lo=True)  # :140
-        if fold:
-            ops.gemm(out_w, in_w[2 * d:], Wkv[d:], lo=lo, emit_lo=Wkv_lo[d:])  # W_o W_v
-            ops.gemm(in_b[2 * d:].view(1, d), out_w, bkv[d:].view(1, d), transB=True)  # W_o b_v
-            lo.put(Wkv, Wkv_lo)
-        else:
-            Wkv, bkv = in_w[d:], in_b[d:]
-        KVp = ops.linear_fwd(X, Wkv, bkv, ragged=r.m_dev, lo=lo)  # MHA k/v in-projection, once per note
+        KVp = ops.linear_fwd(X, in_w[d:], in_b[d:], ragged=r.m_dev, lo=lo)  # MHA k/v in-projection, once per note
         scale = math.sqrt(1.0 / float(d // H))
         q0 = ops.linear_fwd(Qp.view(1, d), in_w[:d], in_b[:d])
         q = ops.axpby(q0, scale, torch.empty_like(q0), False)
         attn_cat, probs = ops.segattn_fwd(q, KVp, r, T, H, d, per_query, thr, seed, save)
-        attn_out = attn_cat if fold else ops.linear_fwd(attn_cat, out_w, out_b, lo=lo)
+        attn_out = ops.linear_fwd(attn_cat, out_w, out_b, lo=lo)
         rps = T if per_query else 1
-        y, mean, rstd = ops.ln_fwd(attn_out, Qp.view(d), r.m_txt, rps, gamma, beta, thr, seed, ops.SITE_TTF_DROPOUT, save,
-                                   xbias=out_b if fold else None)
+        y, mean, rstd = ops.ln_fwd(attn_out, Qp.view(d), r.m_txt, rps, gamma, beta, thr, seed, ops.SITE_TTF_DROPOUT, save)
         assert not defer or per_query, "defer needs per-(sample, query) rows"
         E = y if defer else ops.linear_fwd(y, W_po, b_po, lo=lo, emit_lo=step.e_txt_feeds_tc)
         if save:
             ctx.r, ctx.T, ctx.H, ctx.thr, ctx.seed, ctx.lo, ctx.defer = r, T, H, thr, seed, lo, defer
-            ctx.has_in, ctx.per_query, ctx.scale, ctx.fold = W_in is not None, per_query, scale, fold
-            ctx.save_for_backward(Qp, w_per, b_per, W_kv, in_w, in_b, out_w, out_b, gamma, W_po, Xcat, X, Wkv, KVp, q, attn_cat,
-                                  probs, attn_out, y, mean, rstd)
+            ctx.has_in, ctx.per_query, ctx.scale = W_in is not None, per_query, scale
+            ctx.save_for_backward(Qp, w_per, b_per, W_kv, in_w, in_b, out_w, gamma, W_po, Xcat, X, KVp, q, attn_cat, probs,
+                                  attn_out, y, mean, rstd)
         return E.view(B, T, d) if per_query else E.view(B, 1, d).expand(B, T, d)
 
     @staticmethod
     def backward(ctx, dE_txt):
-        (Qp, w_per, b_per, W_kv, in_w, in_b, out_w, out_b, gamma, W_po, Xcat, X, Wkv, KVp, q, attn_cat, probs, attn_out, y,
-         mean, rstd) = ctx.saved_tensors
-        r, T, H, thr, seed, lo, fold = ctx.r, ctx.T, ctx.H, ctx.thr, ctx.seed, ctx.lo, ctx.fold
+        (Qp, w_per, b_per, W_kv, in_w, in_b, out_w, gamma, W_po, Xcat, X, KVp, q, attn_cat, probs, attn_out, y, mean,
+         rstd) = ctx.saved_tensors
+        r, T, H, thr, seed, lo = ctx.r, ctx.T, ctx.H, ctx.thr, ctx.seed, ctx.lo
         ctx.lo = None
         B, d = r.B, W_po.shape[0]
         dt = d // 2
@@ -156,76 +141,207 @@ class T2VXAttnFn(torch.autograd.Function):
             dy = ops.linear_dgrad(dE, W_po, lo=lo)
         rps = T if per_query else 1
         dx, dres, dgamma, dbeta = ops.ln_bwd(dy, attn_out, Qp.view(d), r.m_txt, rps, gamma, mean, rstd, thr, seed,
-                                             ops.SITE_TTF_DROPOUT, xbias=out_b if fold else None)
-        if fold:
-            d_attn_cat = dx
-        else:
-            dW_o = ops.linear_wgrad(dx, attn_cat, lo=lo)
-            d_attn_cat = ops.linear_dgrad(dx, out_w, lo=lo)
+                                             ops.SITE_TTF_DROPOUT)
+        dW_o = ops.linear_wgrad(dx, attn_cat, lo=lo)
+        db_o = ops.colsum(dx)
+        d_attn_cat = ops.linear_dgrad(dx, out_w, lo=lo)
         dKVp, dq_partial = ops.segattn_bwd(d_attn_cat, q, KVp, probs, r, T, H, d, per_query, thr, seed)
-        # Everything that only feeds parameter gradients goes to the wgrad stream (ops.Fork); the current stream keeps the
-        # data-gradient chain dKVp -> dX -> dXcat.  dKVp is read by both: its lo is split before the fork.
-        fk = ops.Fork(dev, enabled=fold)
-        if fold and ops.gemm_backend() != ops.BACKEND_FFMA:
-            lo.lo_for(dKVp, r.m_dev)
         d_in_w = torch.empty_like(in_w)
         d_in_b = new(3 * d)
-        res = {}
-
-        def params_from_attention():
-            res["db_o"] = ops.colsum(dx)
-            # query path: q = (Qp W_q^T + b_q) * scale
-            dq = ops.colsum(dq_partial)
-            dq_pre = ops.axpby(dq, ctx.scale, torch.empty_like(dq), False).view(1, d)
-            ops.linear_wgrad(dq_pre, Qp.view(1, d), out=d_in_w[:d])
-            d_in_b[:d].copy_(dq_pre.view(d))
-            dQp = ops.linear_dgrad(dq_pre, in_w[:d])  # [1,d]
-            ops.axpby(dres, 1.0, dQp.view(d), True)
-            res["dQp"] = dQp
-            # key/value path, once per note
-            if fold:
-                dWkv, dWkv_lo = new(2 * d, d), new(2 * d, d)
-                ops.linear_wgrad(dKVp, X, out=dWkv, ragged=r.m_dev, lo=lo, emit_lo=dWkv_lo)  # rows [d,2d) are d(W_o W_v)
-                lo.put(dWkv[d:], dWkv_lo[d:])
-                dbkv = ops.colsum(dKVp, ragged=r.m_dev)
-                d_in_w[d:2 * d].copy_(dWkv[:d])
-                d_in_b[d:2 * d].copy_(dbkv[:d])
-                # un-fold W_f = W_o W_v, b_f = W_o b_v
-                dW_o = new(d, d)
-                ops.gemm_group([dict(A=dWkv[d:], B=in_w[2 * d:], C=dW_o, transB=True),
-                                dict(A=out_w, B=dWkv[d:], C=d_in_w[2 * d:], transA=True)], lo)
-                ops.gemm(dbkv[d:].view(d, 1), in_b[2 * d:].view(1, d), dW_o, beta=1.0)
-                ops.gemm(dbkv[d:].view(1, d), out_w, d_in_b[2 * d:].view(1, d))
-                res["dW_o"] = dW_o
-            else:
-                ops.linear_wgrad(dKVp, X, out=d_in_w[d:], ragged=r.m_dev, lo=lo)
-                ops.colsum(dKVp, out=d_in_b[d:], ragged=r.m_dev)
-
-        fk.run(params_from_attention, dx, dq_partial, dres, dKVp, d_in_w, d_in_b)
-        dX = ops.linear_dgrad(dKVp, Wkv, ragged=r.m_dev, lo=lo, emit_lo=True)
-
-        def params_from_dX():
-            res["dW_kv"] = ops.linear_wgrad(dX, Xcat, ragged=r.m_dev, lo=lo)
-            res["db_kv"] = ops.colsum(dX, ragged=r.m_dev)
-
-        fk.run(params_from_dX, dX, *([lo.lo_for(dX, r.m_dev)] if fk.side is not None and ops.gemm_backend() != ops.BACKEND_FFMA else []))
+        # query path: q = (Qp W_q^T + b_q) * scale
+        dq = ops.colsum(dq_partial)
+        dq_pre = ops.axpby(dq, ctx.scale, torch.empty_like(dq), False).view(1, d)
+        ops.linear_wgrad(dq_pre, Qp.view(1, d), out=d_in_w[:d])
+        ops.axpby(dq_pre, 1.0, d_in_b[:d], False)
+        dQp = ops.linear_dgrad(dq_pre, in_w[:d])  # [1,d]
+        ops.axpby(dres, 1.0, dQp.view(d), True)
+        # key/value path, once per note
+        ops.linear_wgrad(dKVp, X, out=d_in_w[d:], ragged=r.m_dev, lo=lo)
+        ops.colsum(dKVp, out=d_in_b[d:], ragged=r.m_dev)
+        dX = ops.linear_dgrad(dKVp, in_w[d:], ragged=r.m_dev, lo=lo, emit_lo=True)
+        dW_kv = ops.linear_wgrad(dX, Xcat, ragged=r.m_dev, lo=lo)
+        db_kv = ops.colsum(dX, ragged=r.m_dev)
         dXcat_lo = new(r.M_alloc, ops.round_up(d + dt, 4)) if ctx.has_in else False
         dXcat = ops.linear_dgrad(dX, W_kv, ragged=r.m_dev, lo=lo, emit_lo=dXcat_lo)
         if ctx.has_in:
             lo.put(dXcat[:, :d], dXcat_lo[:, :d])
+        dwl, dbl, dwp, dbp = ops.time2vec_bwd(dXcat[:, d:], r, w_per, b_per, dt)
+        dW_in = db_in = None
+        if ctx.has_in:
+            dW_in = ops.linear_wgrad(dXcat[:, :d], r.emb_flat, ragged=r.m_dev, lo=lo)
+            db_in = ops.colsum(dXcat[:, :d], ragged=r.m_dev)
+        return (None, None, None, None, None, None, None, dQp.view(1, 1, d), dW_in, db_in, dwl, dbl, dwp, dbp, dW_kv, db_kv,
+                d_in_w, d_in_b, dW_o, db_o, dgamma, dbeta, dW_po, db_po)
 
-        def params_from_dXcat():
-            res["t2v"] = ops.time2vec_bwd(dXcat[:, d:], r, w_per, b_per, dt)
-            res["dW_in"] = res["db_in"] = None
-            if ctx.has_in:
-                res["dW_in"] = ops.linear_wgrad(dXcat[:, :d], r.emb_flat, ragged=r.m_dev, lo=lo)
-                res["db_in"] = ops.colsum(dXcat[:, :d], ragged=r.m_dev)
 
-        fk.run(params_from_dXcat, dXcat, *([dXcat_lo] if ctx.has_in else []))
+# ============================================================== TTF_T2V_XAttn, one head, train mode: collapsed schedule
+class T2VXAttnFoldFn(torch.autograd.Function):
+    """TTF_T2V_XAttn.py:93-184 for ONE head in train mode (attention dropout makes every (sample, query) row distinct).
+    Exact reassociations of the reference's linear maps -- the per-note work is two dense products instead of four:
+
+      * input_proj (:121) and the note half of KV_proj (:140) are consecutive linear maps: X = [emb ; phi] [W_a W_in | W_phi]^T
+        + (W_a b_in + b_kv), with KV_proj.weight = [W_a | W_phi]; the d x d_model fold W_a W_in is a weight-space product;
+      * ONE learned query: score_n = q . (W_k X_n + b_k) = (W_k^T q) . X_n + const, and the constant cancels in the softmax
+        (d b_k = 0 exactly), so the key projection is one VECTOR u = W_k^T q and never a per-note product; dW_k = q (x) du;
+      * the MHA out-projection is folded into the value projection (sum_n p_n (v_n W_o^T) = (sum_n p_n v_n) W_o^T).
+
+    Per note: X (K = d_model + d_tau) and V' = X (W_o W_v)^T; backward: dX = dV' (W_o W_v) + ds (x) u, d phi = dX W_phi and the
+    two weight gradients.  Everything that depends on parameters only runs on a side lane beside the data chain, and every
+    weight gradient on one of three lanes beside the data-gradient chain (ops.Fork).  X lives in the K half and V' in the V half
+    of the packed [rows, 2d] buffer the segment-attention kernels read (csrc/t2v_segattn.cu), with u in the place of q."""
+
+    @staticmethod
+    def forward(ctx, r: RaggedNotes, T, H, thr, seed, save, defer, Qp, W_in, b_in, w_lin, b_lin, w_per, b_per, W_kv, b_kv,
+                in_w, in_b, out_w, out_b, gamma, beta, W_po, b_po):
+        assert H == 1 and thr != 0
+        B, d = r.B, W_po.shape[0]
+        dt, dm = d // 2, r.d_m
+        has_in = W_in is not None
+        Kx = dm + dt
+        dev = Qp.device
+        new = lambda *s: torch.empty(*s, dtype=_f32, device=dev)
+        step = ops.step_ctx()
+        lo = step.lo
+        W_a, W_phi = W_kv[:, :d], W_kv[:, d:]
+        W_q, W_k, W_v = in_w[:d], in_w[d:2 * d], in_w[2 * d:]
+        Ecat, Ecat_lo = new(r.M_alloc, Kx), new(r.M_alloc, ops.round_up(Kx, 4))  # [emb ; phi] and its tcgen05 lo operand
+        KVp = new(r.M_alloc, 2 * d)  # [X | V']
+        Wvf, Wvf_lo, bvf = new(d, d), new(d, d), new(d)
+        if has_in:
+            Wx, Wx_lo, bX = new(d, Kx), new(d, ops.round_up(Kx, 4)), new(d)
+        else:
+            Wx, bX = W_kv, b_kv
+        scale = math.sqrt(1.0 / float(d))
+        box = {}
+        fkw = ops.Fork(dev, name="t2v_fwd")
+
+        def weights():
+            ws = [(out_w, []), (in_w, [slice(2 * d, None)])] + ([] if defer else [(W_po, [])])
+            extra = []
+            if has_in:
+                ws += [(W_in, []), (W_kv, [(slice(None), slice(0, d))])]
+                extra.append((W_phi, Wx[:, dm:], Wx_lo[:, dm:]))
+            else:
+                ws.append((W_kv, [(slice(None), slice(d, None))]))
+            ops.weight_los(lo, ws, extra)
+            if has_in:
+                ops.gemm(W_a, W_in, Wx[:, :dm], lo=lo, emit_lo=Wx_lo[:, :dm])  # W_a W_in
+                ops.gemm(b_in.view(1, d), W_a, bX.view(1, d), transB=True, bias=b_kv)  # W_a b_in + b_kv
+                lo.put(Wx, Wx_lo)
+                lo.put(Wx[:, dm:], Wx_lo[:, dm:])
+            box["ev_x"] = fkw.mark()
+            ops.gemm(out_w, W_v, Wvf, lo=lo, emit_lo=Wvf_lo)  # W_o W_v
+            ops.gemm(in_b[2 * d:].view(1, d), out_w, bvf.view(1, d), transB=True)  # W_o b_v
+            q0 = ops.linear_fwd(Qp.view(1, d), W_q, in_b[:d])
+            q = ops.axpby(q0, scale, torch.empty_like(q0), False)
+            box["q"], box["u"] = q, ops.gemm(q, W_k, new(1, d))  # u = W_k^T q
+            box["ev_v"] = fkw.mark()
+
+        fkw.run(weights)
+        # data chain: [emb ; phi] (the copy of the notes rides with its lo split), X, V'
+        ops.multi_split([(r.emb_flat, Ecat[:, :dm], Ecat_lo[:, :dm])])
+        ops.time2vec_fwd(r, w_lin, b_lin, w_per, b_per, dt, Ecat[:, dm:], Ecat_lo[:, dm:])
+        lo.put(Ecat, Ecat_lo)
+        fkw.wait(box["ev_x"], Wx, bX)
+        X = ops.gemm(Ecat, Wx, KVp[:, :d], transB=True, bias=bX, ragged=r.m_dev, ragged_dim=1, lo=lo, emit_lo=True)
+        u = box["u"]
+        fkw.wait(box["ev_v"], Wvf, Wvf_lo, bvf, u, box["q"])
+        ops.gemm(X, Wvf, KVp[:, d:], transB=True, bias=bvf, ragged=r.m_dev, ragged_dim=1, lo=lo)
+        fkw.join()
+        attn_cat, probs = ops.segattn_fwd(u, KVp, r, T, 1, d, True, thr, seed, save)
+        y, mean, rstd = ops.ln_fwd(attn_cat, Qp.view(d), r.m_txt, T, gamma, beta, thr, seed, ops.SITE_TTF_DROPOUT, save, xbias=out_b)
+        E = y if defer else ops.linear_fwd(y, W_po, b_po, lo=lo, emit_lo=step.e_txt_feeds_tc)
+        if save:
+            ctx.r, ctx.T, ctx.thr, ctx.seed, ctx.lo, ctx.defer, ctx.has_in, ctx.scale = r, T, thr, seed, lo, defer, has_in, scale
+            ctx.save_for_backward(Qp, w_per, b_per, W_in, b_in, W_kv, in_w, in_b, out_w, out_b, gamma, W_po, Ecat, KVp, Wx, Wvf,
+                                  box["q"], u, attn_cat, probs, y, mean, rstd)
+        return E.view(B, T, d)
+
+    @staticmethod
+    def backward(ctx, dE_txt):
+        (Qp, w_per, b_per, W_in, b_in, W_kv, in_w, in_b, out_w, out_b, gamma, W_po, Ecat, KVp, Wx, Wvf, q, u, attn_cat, probs, y,
+         mean, rstd) = ctx.saved_tensors
+        r, T, thr, seed, lo, has_in = ctx.r, ctx.T, ctx.thr, ctx.seed, ctx.lo, ctx.has_in
+        ctx.lo = None
+        B, d = r.B, W_po.shape[0]
+        dt, dm = d // 2, r.d_m
+        dev = Qp.device
+        new = lambda *s: torch.empty(*s, dtype=_f32, device=dev)
+        W_a = W_kv[:, :d]
+        W_q, W_k, W_v = in_w[:d], in_w[d:2 * d], in_w[2 * d:]
+        tc = ops.gemm_backend() != ops.BACKEND_FFMA
+        dE = dE_txt.contiguous().view(B * T, d)
+        if ctx.defer:
+            dW_po = db_po = None  # the consumer returns these
+            dy = dE
+        else:
+            dW_po = ops.linear_wgrad(dE, y, lo=lo)
+            db_po = ops.colsum(dE)
+            dy = ops.linear_dgrad(dE, W_po, lo=lo)
+        dx, dres, dgamma, dbeta = ops.ln_bwd(dy, attn_cat, Qp.view(d), r.m_txt, T, gamma, mean, rstd, thr, seed, ops.SITE_TTF_DROPOUT,
+                                             xbias=out_b)
+        # K half of dKVp: ds_n u (the score path's contribution to dX); V half: dV'; dq_partial: sum_n ds_n X_n = du per sample
+        dKVp, du_partial = ops.segattn_bwd(dx, u, KVp, probs, r, T, 1, d, True, thr, seed)
+        X, dXk, dVf = KVp[:, :d], dKVp[:, :d], dKVp[:, d:]
+        fk = ops.Fork(dev, lanes=3)
+        if tc:
+            lo.lo_for(dVf, r.m_dev)  # read on two streams: split before the fork
+        d_in_w, d_in_b = torch.empty_like(in_w), new(3 * d)
+        res = {}
+
+        def params_value():  # V' = X (W_o W_v)^T + W_o b_v
+            dWvf, dWvf_lo = new(d, d), new(d, d)
+            ops.linear_wgrad(dVf, X, out=dWvf, ragged=r.m_dev, lo=lo, emit_lo=dWvf_lo)
+            dbvf = ops.colsum(dVf, ragged=r.m_dev)
+            dW_o = new(d, d)
+            ops.gemm_group([dict(A=dWvf, B=W_v, C=dW_o, transB=True), dict(A=out_w, B=dWvf, C=d_in_w[2 * d:], transA=True)], lo)
+            ops.gemm(dbvf.view(d, 1), in_b[2 * d:].view(1, d), dW_o, beta=1.0)
+            ops.gemm(dbvf.view(1, d), out_w, d_in_b[2 * d:].view(1, d))
+            res["dW_o"] = dW_o
+
+        def params_query():  # u = W_k^T q,  q = (Qp W_q^T + b_q) scale
+            res["db_o"] = ops.colsum(dx)
+            du = ops.colsum(du_partial).view(1, d)
+            ops.gemm(q.view(d, 1), du, d_in_w[d:2 * d])  # dW_k = q (x) du
+            ops.axpby(du, 0.0, d_in_b[d:2 * d], False)  # d b_k = 0: q . b_k is constant over a segment
+            dq = ops.gemm(du, W_k, new(1, d), transB=True)
+            dq_pre = ops.axpby(dq, ctx.scale, torch.empty_like(dq), False)
+            ops.linear_wgrad(dq_pre, Qp.view(1, d), out=d_in_w[:d])
+            ops.axpby(dq_pre, 1.0, d_in_b[:d], False)
+            dQp = ops.linear_dgrad(dq_pre, W_q)
+            ops.axpby(dres, 1.0, dQp.view(d), True)
+            res["dQp"] = dQp
+
+        fk.run(params_value, dKVp, d_in_w, d_in_b, lane=0)
+        fk.run(params_query, dx, du_partial, dres, d_in_w, d_in_b, lane=1)
+        dX = ops.gemm(dVf, Wvf, dXk, beta=1.0, ragged=r.m_dev, ragged_dim=1, lo=lo, emit_lo=True)  # + ds (x) u, in place
+
+        def params_x():  # X = [emb ; phi] [W_a W_in | W_phi]^T + (W_a b_in + b_kv)
+            dbX = ops.colsum(dX, ragged=r.m_dev)
+            if not has_in:
+                res["dW_kv"], res["db_kv"], res["dW_in"], res["db_in"] = ops.linear_wgrad(dX, Ecat, ragged=r.m_dev, lo=lo), dbX, None, None
+                return
+            Kx = dm + dt
+            dWx, dWx_lo = new(d, Kx), new(d, ops.round_up(Kx, 4))
+            ops.linear_wgrad(dX, Ecat, out=dWx, ragged=r.m_dev, lo=lo, emit_lo=dWx_lo)
+            dP1 = dWx[:, :dm]
+            lo.put(dP1, dWx_lo[:, :dm])
+            dW_kv, dW_in, db_in = new(d, d + dt), new(d, dm), new(d)
+            ops.gemm_group([dict(A=dP1, B=W_in, C=dW_kv[:, :d], transB=True), dict(A=W_a, B=dP1, C=dW_in, transA=True)], lo)
+            ops.gemm(dbX.view(d, 1), b_in.view(1, d), dW_kv[:, :d], beta=1.0)  # W_a b_in also depends on W_a
+            ops.gemm(dbX.view(1, d), W_a, db_in.view(1, d))
+            ops.multi_split([(dWx[:, dm:], dW_kv[:, d:], None)])
+            res["dW_kv"], res["db_kv"], res["dW_in"], res["db_in"] = dW_kv, dbX, dW_in, db_in
+
+        fk.run(params_x, dX, *([lo.lo_for(dX, r.m_dev)] if fk.side is not None and tc else []), lane=2)
+        dphi = ops.gemm(dX, Wx[:, dm:], new(r.M_alloc, dt), ragged=r.m_dev, ragged_dim=1, lo=lo)
+
+        def params_t2v():
+            res["t2v"] = ops.time2vec_bwd(dphi, r, w_per, b_per, dt)
+
+        fk.run(params_t2v, dphi, lane=1)
         dwl, dbl, dwp, dbp = res["t2v"]
-        dQp, dW_kv, db_kv, dW_in, db_in, db_o = res["dQp"], res["dW_kv"], res["db_kv"], res["dW_in"], res["db_in"], res["db_o"]
-        if fold:
-            dW_o = res["dW_o"]
+        dQp, dW_kv, db_kv, dW_in, db_in, dW_o, db_o = (res[k] for k in ("dQp", "dW_kv", "db_kv", "dW_in", "db_in", "dW_o", "db_o"))
         fk.join(dQp, dW_in, db_in, dwl, dbl, dwp, dbp, dW_kv, db_kv, d_in_w, d_in_b, dW_o, db_o)
         return (None, None, None, None, None, None, None, dQp.view(1, 1, d), dW_in, db_in, dwl, dbl, dwp, dbp, dW_kv, db_kv,
                 d_in_w, d_in_b, dW_o, db_o, dgamma, dbeta, dW_po, db_po)

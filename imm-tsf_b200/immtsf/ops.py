@@ -213,34 +213,62 @@ def side_streams_enabled() -> bool:
 
 
 class Fork:
-    """Parameter-gradient work of a backward pass on a second stream.  Weight and bias gradients are not needed until
-    the end of the step, while the data-gradient chain (dgrad products, attention / LayerNorm backward) is the critical
-    path and its ragged products leave a third of the SMs idle: `run` enqueues a closure on the wgrad stream after
-    everything issued so far on the current stream, `join` makes the current stream wait for all of it.  Captured in a
-    CUDA graph these are parallel branches.  Operands read on both streams must have their lo split BEFORE the fork."""
+    """Work that is off the critical path on side streams ("lanes").  In a backward pass weight and bias gradients are not
+    needed until the end of the step, while the data-gradient chain (dgrad products, attention / LayerNorm backward) is the
+    critical path and its ragged products leave a third of the SMs idle; in a forward pass everything that depends on
+    parameters only (operand splits, weight-space folds, the query path) can run beside the data chain.  `run` enqueues a
+    closure on a lane after everything issued so far on the current stream, `mark` / `wait` order the current stream after
+    a point of a lane, `join` after all lanes.  Captured in a CUDA graph the lanes are parallel branches (the timeline of
+    round 1's single wgrad lane showed 265 us of serial weight-gradient work after a 95 us data chain).  Operands read on
+    several streams must have their lo split BEFORE the fork."""
 
-    def __init__(self, device, enabled: bool = True):
+    def __init__(self, device, enabled: bool = True, lanes: int = 1, name: str = "wgrad"):
         self.cur = torch.cuda.current_stream(device)
-        self.side = None
+        self.lanes = []
         if enabled and side_streams_enabled():
-            key = (device, "wgrad")
-            self.side = _SIDE.get(key)
-            if self.side is None:
-                self.side = _SIDE[key] = torch.cuda.Stream(device=device)
+            for i in range(lanes):
+                key = (device, name, i)
+                st = _SIDE.get(key)
+                if st is None:
+                    st = _SIDE[key] = torch.cuda.Stream(device=device)
+                self.lanes.append(st)
+        self.side = self.lanes[0] if self.lanes else None
+        self._used = set()
 
-    def run(self, fn, *reads):
-        if self.side is None:
+    def run(self, fn, *reads, lane: int = 0, after_current: bool = True):
+        if not self.lanes:
             return fn()
-        self.side.wait_stream(self.cur)
+        st = self.lanes[lane % len(self.lanes)]
+        if after_current or st not in self._used:
+            st.wait_stream(self.cur)
+        self._used.add(st)
         for t in reads:
-            t.record_stream(self.side)
-        with torch.cuda.stream(self.side):
+            if t is not None:
+                t.record_stream(st)
+        with torch.cuda.stream(st):
             return fn()
+
+    def mark(self, lane: int = 0):
+        """An event at the current end of a lane (None when the fork is disabled)."""
+        if not self.lanes:
+            return None
+        ev = torch.cuda.Event()
+        ev.record(self.lanes[lane % len(self.lanes)])
+        return ev
+
+    def wait(self, ev, *tensors):
+        if ev is not None:
+            self.cur.wait_event(ev)
+            for t in tensors:
+                if t is not None:
+                    t.record_stream(self.cur)
 
     def join(self, *tensors):
-        if self.side is None:
+        if not self.lanes:
             return
-        self.cur.wait_stream(self.side)
+        for st in self.lanes:
+            if st in self._used:
+                self.cur.wait_stream(st)
         for t in tensors:
             if t is not None:
                 t.record_stream(self.cur)
@@ -459,13 +487,12 @@ def time2vec_fwd(r: RaggedNotes, w_lin, b_lin, w_per, b_per, d_tau, out_view, lo
 
 def time2vec_bwd(dphi_view, r: RaggedNotes, w_per, b_per, d_tau):
     dev = dphi_view.device
-    dwl = torch.empty(1, 1, dtype=torch.float32, device=dev)
-    dbl = torch.empty(1, dtype=torch.float32, device=dev)
-    dwp = torch.empty(d_tau - 1, 1, dtype=torch.float32, device=dev)
-    dbp = torch.empty(d_tau - 1, dtype=torch.float32, device=dev)
-    ws = torch.empty(_lib.load().immtsf_time2vec_bwd_workspace_bytes(d_tau) // 8, dtype=torch.float64, device=dev)
+    dwl = torch.zeros(1, 1, dtype=torch.float32, device=dev)
+    dbl = torch.zeros(1, dtype=torch.float32, device=dev)
+    dwp = torch.zeros(d_tau - 1, 1, dtype=torch.float32, device=dev)
+    dbp = torch.zeros(d_tau - 1, dtype=torch.float32, device=dev)
     _lib.call("immtsf_time2vec_bwd", _p(dphi_view), dphi_view.stride(0), _p(r.tau_flat), _p(w_per), _p(b_per), d_tau,
-              _p(dwl), _p(dbl), _p(dwp), _p(dbp), _p(r.m_dev), r.M_alloc, _p(ws), ws.numel() * 8, _p(ticket(dev)), _stream())
+              _p(dwl), _p(dbl), _p(dwp), _p(dbp), _p(r.m_dev), r.M_alloc, _stream())
     return dwl, dbl, dwp, dbp
 
 

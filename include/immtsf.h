@@ -164,14 +164,9 @@ int immtsf_recavg_pool_bwd(const float* dE_drop, const float* E_raw, const float
 int immtsf_time2vec_fwd(const float* tau_flat, const float* w_lin, const float* b_lin, const float* w_per,
                         const float* b_per, int d_tau, float* out, int ld, float* out_lo, int ld_lo,
                         const int32_t* m_dev, int M_alloc, void* stream);
-/* backward: the four parameter gradients are OVERWRITTEN (not accumulated).  They are signed sums over every note with heavy
- * cancellation, summed in double: `workspace` (>= immtsf_time2vec_bwd_workspace_bytes, 8-byte aligned) holds per-CTA double
- * partials, `ticket` is one device uint32 that is 0 on entry and left 0 (last-CTA fixed-order reduction: deterministic). */
-size_t immtsf_time2vec_bwd_workspace_bytes(int d_tau);
 int immtsf_time2vec_bwd(const float* dphi, int ld, const float* tau_flat, const float* w_per,
                         const float* b_per, int d_tau, float* dw_lin, float* db_lin, float* dw_per,
-                        float* db_per, const int32_t* m_dev, int M_alloc, void* workspace, size_t workspace_bytes,
-                        uint32_t* ticket, void* stream);
+                        float* db_per, const int32_t* m_dev, int M_alloc, void* stream);
 
 /* ---- K3: single-learned-query attention over each ragged segment
  * (TTF_T2V_XAttn.py:143-166 + the softmax/dropout/bmm inside
