@@ -110,25 +110,24 @@ class FusionModel(nn.Module):
         side = os.environ.get("IMMTSF_SIDE_STREAM", "1") != "0"
         if defer:
             W_p, b_p = self.ttf.final_proj()
-            wts = self.mmf.rank_weights((W_p, b_p), side=side)
+            # E_txt_true = E_txt W_p^T + b_p has a NaN iff one of its three factors has one: W_p and b_p are checked beside the
+            # weight-space work, E_txt by the rank form's data kernel while it reads it
+            wts = self.mmf.rank_weights((W_p, b_p), side=side, flags=flags if check else None)
             E_txt, M_txt = self.ttf.forward_ragged(r, t_hat, defer=True)
             if side:
                 self.mmf.wait_rank_weights(wts)
-            if check:  # E_txt_true has a NaN iff one of its three factors has one
-                for t in (E_txt, W_p, b_p):
-                    ops.nan_check(t, flags, ops.FLAG_E)
-            Y_out = self.mmf.forward_flags(Y32, E_txt, M_txt, flags, final_proj=(W_p, b_p), rank_weights=wts)
+            Y_out = self.mmf.forward_flags(Y32, E_txt, M_txt, flags if check else False, final_proj=(W_p, b_p), rank_weights=wts)
             runtime.raise_on_flags(flags)
             return Y_out
         wts = self.mmf.rank_weights(None, side=side) if rank else None
         E_txt, M_txt = self.ttf.forward_ragged(r, t_hat)
         if rank and side:
             self.mmf.wait_rank_weights(wts)
-        if check:
+        if check and not rank:
             # the broadcast view of T2V eval mode has B distinct rows: check those only
             ops.nan_check(E_txt[:, :1] if E_txt.stride(1) == 0 else E_txt, flags, ops.FLAG_E)
-        if rank:
-            Y_out = self.mmf.forward_flags(Y32, E_txt, M_txt, flags, rank_weights=wts)
+        if rank:  # (the rank form's data kernel checks E_txt while it reads it)
+            Y_out = self.mmf.forward_flags(Y32, E_txt, M_txt, flags if check else False, rank_weights=wts)
         else:
             Y_out = self.mmf.forward_flags(Y32, E_txt, M_txt, flags)
         runtime.raise_on_flags(flags)

@@ -34,19 +34,25 @@ class MMF_XAttn_Add(nn.Module):
                 at.out_proj.weight, at.out_proj.bias, self.residual_head.weight, self.residual_head.bias,
                 self.layer_norm.weight, self.layer_norm.bias)
 
-    def rank_weights(self, final_proj=None, side: bool = False):
+    def rank_weights(self, final_proj=None, side: bool = False, flags=None):
         """Weight-space half of the rank form (functional.XAttnRankWeightsFn): (Wr, br, bo_f).  final_proj = (W_p, b_p)
         folds the producer's deferred last projection in.  side=True runs it on ops.side_stream() -- it depends on
         parameters only, so FusionModel starts it before the TTF forward; join with `wait_rank_weights`."""
         W_p, b_p = final_proj if final_proj is not None else (None, None)
         args = (self.n_heads, self.C) + self._params()[:9] + (W_p, b_p)
-        if not side:
+        def work():
+            if flags is not None and W_p is not None:  # NaN guard of the folded projection (FusionModel.py:107-108)
+                ops.nan_check(W_p, flags, ops.FLAG_E)
+                ops.nan_check(b_p, flags, ops.FLAG_E)
             return F_.XAttnRankWeightsFn.apply(*args)
+
+        if not side:
+            return work()
         cur = torch.cuda.current_stream()
         st = ops.side_stream(cur.device)
         st.wait_stream(cur)
         with torch.cuda.stream(st):
-            out = F_.XAttnRankWeightsFn.apply(*args)
+            out = work()
         return out
 
     @staticmethod
@@ -66,7 +72,8 @@ class MMF_XAttn_Add(nn.Module):
         thr, seed = cm.dropout_args(self.dropout.p, self.training, self)
         params = self._params()
         save = F_._need_save(Y_ts, E_txt, *params)
-        own_flags = flags if flags is not None else runtime.new_flags(Y_ts.device)
+        # flags: None = standalone call (own flags, delta_y ValueError below); False = the caller does not want NaN flags
+        own_flags = None if flags is False else (flags if flags is not None else runtime.new_flags(Y_ts.device))
         # Time-IMM shapes (T <= 32, few channels): the rank-(2C+1) form -- one skinny pass over E_txt, no tensor of width d
         if self.rank_path(T):
             Wr, br, bo_f = rank_weights if rank_weights is not None else self.rank_weights(final_proj)
@@ -78,7 +85,7 @@ class MMF_XAttn_Add(nn.Module):
                 raise RuntimeError("MMF_XAttn_Add: a deferred projection needs the rank path")
             out = F_.XAttnAddFn.apply(cm.as_f32(Y_ts), cm.as_f32(E_txt), cm.m_txt_u8(M_txt, B), self.n_heads, float(self.kappa),
                                       thr, seed, save, own_flags, *params)
-        if flags is None:  # standalone call: keep the reference's "delta_y contains NaN" ValueError (:84-91)
+        if flags is None and own_flags is not None:  # standalone call: keep the reference's "delta_y contains NaN" ValueError (:84-91)
             if runtime.nan_check_enabled() and own_flags.tolist()[ops.FLAG_OUT]:
                 raise ValueError("delta_y contains NaN values.")
         return out

@@ -33,10 +33,13 @@ def fix_t_hat(t_hat: torch.Tensor, B: int):
 
 
 def m_txt_bool(r: ops.RaggedNotes) -> torch.Tensor:
-    return r.m_txt[: r.B].view(r.B, 1).bool()
+    """M_txt [B, 1] bool (TTF_RecAvg.py:110): the kernels' 0/1 bytes reinterpreted, no conversion launch."""
+    return r.m_txt[: r.B].view(r.B, 1).view(torch.bool)
 
 
 def m_txt_u8(M_txt: torch.Tensor, B: int) -> torch.Tensor:
+    if M_txt.dtype == torch.bool and M_txt.is_contiguous():
+        return M_txt.reshape(B).view(torch.uint8)  # same bytes
     return M_txt.reshape(B).to(torch.uint8).contiguous()
 
 

@@ -63,6 +63,9 @@ SIGNATURES = {
     "immtsf_xattn_rank_ok": [I, I, I, I],
     "immtsf_xattn_rank_fwd": [P, I, P, I, P, P, I, I, I, I, I, U32, U64, P, P, P],
     "immtsf_xattn_rank_bwd": [P, P, I, P, I, P, P, I, I, I, I, I, U32, U64, P, I, P, P],
+    "immtsf_xattn_rank_fused_ok": [I, I, I, I, I],
+    "immtsf_xattn_rank_fused_fwd": [P, I, I, P, I, P, P, I, P, P, P, P, I, I, I, I, I, F, F, U32, U64, P, I, P, P, P, P, P],
+    "immtsf_xattn_rank_fused_bwd": [P, P, P, P, I, P, I, P, P, P, I, I, P, I, I, I, I, I, I, F, F, U32, U64, P, I, P, P, P, P, SZ, P],
     "immtsf_gemm_batched": [I, I, I, I, I, F, P, P, I, L, L, P, P, I, L, L, F, P, I, L, L, I, I, P, SZ, P],
     "immtsf_softmax_rows_fwd": [P, P, P, I, I, I, I, F, U32, U64, P],
     "immtsf_softmax_rows_bwd": [P, P, P, P, I, I, I, I, F, U32, U64, P],
@@ -109,6 +112,8 @@ def load():
     lib.immtsf_gemm_workspace_bytes.restype = SZ
     lib.immtsf_t2vq_bwd_workspace_bytes.argtypes = [I, I, I]
     lib.immtsf_t2vq_bwd_workspace_bytes.restype = SZ
+    lib.immtsf_xattn_rank_fused_bwd_workspace_bytes.argtypes = [I, I, I, I]
+    lib.immtsf_xattn_rank_fused_bwd_workspace_bytes.restype = SZ
     lib.immtsf_masked_mse_workspace_bytes.argtypes = [I]
     lib.immtsf_masked_mse_workspace_bytes.restype = SZ
     lib.immtsf_gemm_batched_workspace_bytes.argtypes = [I, I, I, I, I, I, L, L, I, L, L, I, I]

@@ -745,20 +745,30 @@ class XAttnRankWeightsFn(torch.autograd.Function):
 
 class XAttnRankDataFn(torch.autograd.Function):
     """Data half of the rank form: R = E Wr^T + br (the one skinny pass over the text-side tensor), the T x (2C+1)
-    attention (immtsf_xattn_rank_*) and the LayerNorm / dropout / kappa-blend tail (MMF_XAttn_Add.py:83-102)."""
+    attention (immtsf_xattn_rank_*) and the LayerNorm / dropout / kappa-blend tail (MMF_XAttn_Add.py:83-102).  One launch
+    per direction (+ a small ordered reduction of the weight-gradient partials) when csrc/xattn_rank_fused.cu applies
+    (H (2C+1) <= 16, d <= 1024); otherwise the three-kernel forward / separate skinny products."""
 
     @staticmethod
     def forward(ctx, Y, E, m_txt, H, kappa, thr, seed, save, flags, d, Wr, br, bo_f, gamma, beta):
         B, T, C = Y.shape
         nr = H * (2 * C + 1)
-        nrp = ops.round_up(nr, 4)  # rows of R / dR are padded to 16 bytes (vector loads in the skinny kernels); pads unused
         Y2 = Y.contiguous().view(B * T, C)
         E2 = E.contiguous().view(B * T, E.shape[2])
-        R = ops.gemm(E2, Wr, torch.empty(B * T, nrp, dtype=_f32, device=Y.device)[:, :nr], transB=True, bias=br)
-        delta_y, probs = ops.xattn_rank_fwd(Y2, R, bo_f, m_txt, B, T, H, d, C, thr, seed, save)
-        Y_out = ops.xattn_tail_fwd(Y2, delta_y, gamma, beta, m_txt, B, T, C, kappa, thr, seed, flags)
+        Wr = Wr.contiguous()
+        fused = ops.xattn_rank_fused_ok(T, H, d, C, E2, Wr)
+        if fused:
+            Y_out, R, delta_y, probs = ops.xattn_rank_fused_fwd(Y2, E2, Wr, br, bo_f, gamma, beta, m_txt, B, T, H, d, C, kappa, thr, seed,
+                                                                 save, flags)
+        else:
+            nrp = ops.round_up(nr, 4)  # rows of R / dR are padded to 16 bytes (vector loads in the skinny kernels); pads unused
+            if flags is not None:
+                ops.nan_check(E2, flags, ops.FLAG_E)
+            R = ops.gemm(E2, Wr, torch.empty(B * T, nrp, dtype=_f32, device=Y.device)[:, :nr], transB=True, bias=br)
+            delta_y, probs = ops.xattn_rank_fwd(Y2, R, bo_f, m_txt, B, T, H, d, C, thr, seed, save)
+            Y_out = ops.xattn_tail_fwd(Y2, delta_y, gamma, beta, m_txt, B, T, C, kappa, thr, seed, flags)
         if save:
-            ctx.H, ctx.kappa, ctx.thr, ctx.seed, ctx.dims = H, kappa, thr, seed, (B, T, C, d)
+            ctx.H, ctx.kappa, ctx.thr, ctx.seed, ctx.dims, ctx.fused = H, kappa, thr, seed, (B, T, C, d), fused
             ctx.save_for_backward(m_txt, Y2, E2, Wr, gamma, R, probs, delta_y)
         return Y_out
 
@@ -769,11 +779,15 @@ class XAttnRankDataFn(torch.autograd.Function):
         H, kappa, thr, seed = ctx.H, ctx.kappa, ctx.thr, ctx.seed
         nr, dk = Wr.shape
         dY_out = dY_out.contiguous()
-        d_delta, dgamma, dbeta = ops.xattn_tail_bwd(dY_out, delta_y, gamma, m_txt, B, T, C, kappa, thr, seed)
-        dbo_f = ops.colsum(d_delta)  # = d(b_r)
-        dR, dY = ops.xattn_rank_bwd(d_delta, Y2, R, probs, m_txt, B, T, H, d, C, thr, seed)
-        ops.axpby(dY_out.view(B * T, C), 1.0 / (1.0 + kappa), dY, True)  # the blend passes Y straight through
-        dWr = ops.gemm(dR, E2, torch.empty(nr, dk, dtype=_f32, device=dR.device), transA=True)
-        dbr = ops.colsum(dR)
-        dE = ops.gemm(dR, Wr, torch.empty(B * T, dk, dtype=_f32, device=dR.device))
+        if ctx.fused:
+            dE, dY, dWr, dbr, dbo_f, dgamma, dbeta = ops.xattn_rank_fused_bwd(dY_out, delta_y, gamma, Y2, R, probs, m_txt, E2, Wr, B, T, H,
+                                                                              d, C, kappa, thr, seed)
+        else:
+            d_delta, dgamma, dbeta = ops.xattn_tail_bwd(dY_out, delta_y, gamma, m_txt, B, T, C, kappa, thr, seed)
+            dbo_f = ops.colsum(d_delta)  # = d(b_r)
+            dR, dY = ops.xattn_rank_bwd(d_delta, Y2, R, probs, m_txt, B, T, H, d, C, thr, seed)
+            ops.axpby(dY_out.view(B * T, C), 1.0 / (1.0 + kappa), dY, True)  # the blend passes Y straight through
+            dWr = ops.gemm(dR, E2, torch.empty(nr, dk, dtype=_f32, device=dR.device), transA=True)
+            dbr = ops.colsum(dR)
+            dE = ops.gemm(dR, Wr, torch.empty(B * T, dk, dtype=_f32, device=dR.device))
         return dY.view(B, T, C), dE.view(B, T, dk), None, None, None, None, None, None, None, None, dWr, dbr, dbo_f, dgamma, dbeta

@@ -742,6 +742,46 @@ def xattn_rank_bwd(d_delta, Y2, R, probs, m_txt, B, T, H, d, C, thr, seed):
     return dR, dY
 
 
+def xattn_rank_fused_ok(T, H, d, C, E2, Wr) -> bool:
+    """The one-launch-per-direction data half of the rank form applies (csrc/xattn_rank_fused.cu)."""
+    if os.environ.get("IMMTSF_XATTN_FUSED", "1") == "0":
+        return False
+    al = all(t.dim() == 2 and t.stride(1) == 1 and t.data_ptr() % 16 == 0 and t.stride(0) % 4 == 0 for t in (E2, Wr))
+    return al and bool(_lib.load().immtsf_xattn_rank_fused_ok(T, H, d, C, E2.shape[1]))
+
+
+def xattn_rank_fused_fwd(Y2, E2, Wr, br, bo, gamma, beta, m_txt, B, T, H, d, C, kappa, thr, seed, save, flags):
+    """R = E Wr^T + br, the T x (2C+1) attention and the LayerNorm_C / dropout / blend tail in one launch.
+    Returns Y_out [B, T, C] and what backward needs: R [B*T, nr], delta_y [B*T, C], probs [B, H, T, T] (None unless save)."""
+    dev = E2.device
+    nr = H * (2 * C + 1)
+    R = torch.empty(B * T, round_up(nr, 4), dtype=torch.float32, device=dev)[:, :nr]
+    delta_y = torch.empty(B * T, C, dtype=torch.float32, device=dev)
+    probs = torch.empty(B, H, T, T, dtype=torch.float32, device=dev) if save else None
+    Y_out = torch.empty(B, T, C, dtype=torch.float32, device=dev)
+    _lib.call("immtsf_xattn_rank_fused_fwd", _p(E2), E2.stride(0), E2.shape[1], _p(Wr), Wr.stride(0), _p(br), _p(Y2), Y2.stride(0),
+              _p(bo), _p(gamma), _p(beta), _p(m_txt), B, T, H, d, C, LN_EPS, float(kappa), thr, seed, _p(R), R.stride(0),
+              _p(delta_y), _p(probs), _p(Y_out), _p(flags), _stream())
+    return Y_out, R, delta_y, probs
+
+
+def xattn_rank_fused_bwd(dY_out, delta_y, gamma, Y2, R, probs, m_txt, E2, Wr, B, T, H, d, C, kappa, thr, seed):
+    """Returns dE [B*T, de], dY [B*T, C], dWr [nr, de], dbr [nr], d(bo_f) [C], dgamma [C], dbeta [C]."""
+    dev = E2.device
+    nr, de = Wr.shape
+    dE = torch.empty(B * T, de, dtype=torch.float32, device=dev)
+    dY = torch.empty(B * T, C, dtype=torch.float32, device=dev)
+    dWr = torch.empty(nr, de, dtype=torch.float32, device=dev)
+    small = torch.empty(nr + 3 * C, dtype=torch.float32, device=dev)
+    need = _lib.load().immtsf_xattn_rank_fused_bwd_workspace_bytes(B, H, C, de)
+    ws = _workspace(dev, need + 256)
+    off = (-ws.data_ptr()) % 16
+    _lib.call("immtsf_xattn_rank_fused_bwd", _p(dY_out), _p(delta_y), _p(gamma), _p(Y2), Y2.stride(0), _p(R), R.stride(0), _p(probs),
+              _p(m_txt), _p(E2), E2.stride(0), de, _p(Wr), Wr.stride(0), B, T, H, d, C, LN_EPS, float(kappa), thr, seed, _p(dE),
+              dE.stride(0), _p(dY), _p(dWr), _p(small), ws.data_ptr() + off, ws.numel() - off, _stream())
+    return dE, dY, dWr, small[:nr], small[nr:nr + C], small[nr + C:nr + 2 * C], small[nr + 2 * C:]
+
+
 def xattn_tail_fwd(Y, delta_y, gamma, beta, m_txt, B, T, C, kappa, thr, seed, flags):
     Y_out = torch.empty(B, T, C, dtype=torch.float32, device=Y.device)
     _lib.call("immtsf_xattn_tail_fwd", _p(Y), _p(delta_y), _p(gamma), _p(beta), _p(m_txt), B, T, C, LN_EPS, float(kappa), thr,

@@ -281,6 +281,25 @@ int immtsf_xattn_rank_fwd(const float* y, int ldy, const float* r, int ldr, cons
 int immtsf_xattn_rank_bwd(const float* d_delta, const float* y, int ldy, const float* r, int ldr, const float* probs,
                           const uint8_t* m_txt, int B, int T, int H, int d, int C, uint32_t drop_thr, uint64_t seed,
                           float* dr, int lddr, float* dy, void* stream);
+
+/* ---- the data half of the rank form in ONE launch per direction (csrc/xattn_rank_fused.cu): R = E Wr^T + br from the
+ * sample's own rows of E, the T x (2C+1) attention, and the LayerNorm_C / dropout / kappa-blend tail (MMF_XAttn_Add.py:83-102)
+ * -> Y_out; backward: tail, attention, dE = dR Wr and dWr = dR^T E in one pass over E, per-CTA partials reduced in CTA
+ * order by a second launch.  small = [dbr (nr) | d bo (C) | dgamma (C) | dbeta (C)].  Sets FLAG_E when E holds a NaN and
+ * FLAG_OUT when delta / Y_out do.  Needs immtsf_xattn_rank_fused_ok; operands 16-byte aligned, ld % 4 == 0. */
+int immtsf_xattn_rank_fused_ok(int T, int H, int d, int C, int de);
+size_t immtsf_xattn_rank_fused_bwd_workspace_bytes(int B, int H, int C, int de);
+int immtsf_xattn_rank_fused_fwd(const float* e, int lde, int de, const float* wr, int ldwr, const float* br,
+                                const float* y, int ldy, const float* bo, const float* gamma, const float* beta,
+                                const uint8_t* m_txt, int B, int T, int H, int d, int C, float eps, float kappa,
+                                uint32_t drop_thr, uint64_t seed, float* r, int ldr, float* delta_y, float* probs,
+                                float* y_out, int32_t* flags, void* stream);
+int immtsf_xattn_rank_fused_bwd(const float* dy_out, const float* delta_y, const float* gamma, const float* y, int ldy,
+                                const float* r, int ldr, const float* probs, const uint8_t* m_txt, const float* e,
+                                int lde, int de, const float* wr, int ldwr, int B, int T, int H, int d, int C,
+                                float eps, float kappa, uint32_t drop_thr, uint64_t seed, float* de_out, int ldde,
+                                float* dy, float* dwr, float* small, void* workspace, size_t workspace_bytes,
+                                void* stream);
 /* Large-T form of the same core (T > 32: the T x T contractions are dense products and run on tcgen05):
  *   S = Q K^T (immtsf_gemm_batched) -> immtsf_softmax_rows_fwd -> O = P~ V (immtsf_gemm_batched), and in backward
  *   dP~ = dO V^T -> immtsf_softmax_rows_bwd -> dQ = dS K, dK = dS^T Q, dV = P~^T dO.
