@@ -546,9 +546,11 @@ def run_gpu_arm(args, w):
         if world > 1 and args.dp_mode == "ingraph":
             try:
                 graphed = runtime.GraphedStep(fm, example=d_in, warmup=2, allreduce_group=True)
-                dp_mode = ("NCCL captured in the step graph: rank-form upstream gradients (KBs) reduced mid-backward on the side stream, "
-                           "one %s of the remaining gradients at the end; %d of %d gradient floats are never communicated"
-                           % ("coalesced all-reduce (no flat bucket)" if graphed.coalesced else "all-reduce of the flat bucket", graphed.n_first, graphed.n_total))
+                dp_mode = ("NCCL captured in the step graph: the autograd Functions all-reduce the sufficient statistics of their parameter "
+                           "gradients (packed weight-gradient outputs before the weight-space un-folds) on the backward lanes; "
+                           "%d collectives and %.2f MB per step per GPU for %d gradient floats (%.2f MB); gradients of %d floats are born reduced"
+                           % (graphed.dp_calls_per_step, graphed.dp_floats_per_step * 4 / 1e6, graphed.n_total, graphed.n_total * 4 / 1e6,
+                              graphed.n_first))
             except Exception as e:  # capture of NCCL refused: fall back to one all-reduce after the replay
                 print(f"[bench] in-graph all-reduce unavailable ({type(e).__name__}: {e}); reducing after the replay", file=sys.stderr)
                 torch.cuda.synchronize()

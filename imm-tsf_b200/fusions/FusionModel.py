@@ -73,14 +73,18 @@ class FusionModel(nn.Module):
         return rank, defer
 
     def dp_prereduced_params(self, T):
-        """Parameters whose gradients come out of the rank form's weight-space backward: under in-graph data parallelism
-        (runtime.GraphedStep(allreduce_group=...)) their three small upstream tensors are all-reduced instead of them."""
+        """Parameters whose gradients are born all-reduced under in-graph data parallelism (runtime.GraphedStep(allreduce_group=
+        ...)): their Functions all-reduce the sufficient statistics of the gradients (ops.dp_allreduce) before the weight-space
+        un-folds -- the rank form's [dWr | dbr | d bo | dgamma | dbeta], the collapsed T2V schedule's packed weight gradients."""
         rank, defer = self._schedule(T)
         ps = []
         if rank:
-            ps += list(self.mmf._params()[:9])
+            ps += list(self.mmf._params())
             if defer:
                 ps += list(self.ttf.final_proj())
+        if hasattr(self.ttf, "dp_prereduced_params"):
+            have = {id(p) for p in ps}
+            ps += [p for p in self.ttf.dp_prereduced_params() if id(p) not in have]
         return ps
 
     def forward_csr(self, r, t_hat, Y_ts):

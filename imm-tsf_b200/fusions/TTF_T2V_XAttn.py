@@ -70,6 +70,15 @@ class TTF_T2V_XAttn(nn.Module):
         of a sample are one broadcast row."""
         return self.training and ops.drop_thr(self.dropout.p) != 0
 
+    def _collapsed(self, thr: int) -> bool:
+        """One head in train mode with attention dropout: the collapsed schedule (functional.T2VXAttnFoldFn)."""
+        return thr != 0 and self.n_heads == 1 and os.environ.get("IMMTSF_T2V_COLLAPSE", "1") != "0"
+
+    def dp_prereduced_params(self):
+        """The collapsed schedule all-reduces the sufficient statistics of every gradient of this module itself."""
+        thr = ops.drop_thr(self.dropout.p) if self.training else 0
+        return list(self.parameters()) if self._collapsed(thr) else []
+
     def forward_ragged(self, r: ops.RaggedNotes, t_hat: torch.Tensor, defer: bool = False):
         """defer=True: return dropout(LN(attn + Q)) without proj_out; the caller applies final_proj()."""
         _, T = cm.fix_t_hat(t_hat, r.B)  # only the length of t_hat matters (reference :143,150)
@@ -82,7 +91,7 @@ class TTF_T2V_XAttn(nn.Module):
                   self.proj_out.weight, self.proj_out.bias)
         save = F_._need_save(*params)
         # one head in train mode: the collapsed schedule (key projection = one vector, input_proj folded into KV_proj)
-        fn = F_.T2VXAttnFoldFn if (thr != 0 and self.n_heads == 1 and os.environ.get("IMMTSF_T2V_COLLAPSE", "1") != "0") else F_.T2VXAttnFn
+        fn = F_.T2VXAttnFoldFn if self._collapsed(thr) else F_.T2VXAttnFn
         E_txt = fn.apply(r, T, self.n_heads, thr, seed, save, bool(defer), *params)
         return E_txt, cm.m_txt_bool(r)
 

@@ -259,40 +259,54 @@ class T2VXAttnFoldFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dE_txt):
+        """Data parallel (ops.DP_GROUP set by runtime.GraphedStep): every parameter gradient of this module is a linear function
+        (with replicated parameters) of five packed buffers -- [dW_vf | db_vf], [dW_x | db_x], [dres | dgamma | dbeta | du | db_o],
+        the Time2Vec gradients and, when proj_out is not deferred, [dW_po | db_po] -- so THOSE are all-reduced, each on the lane
+        that produces it and before the weight-space un-folds: 1.5 M floats instead of the module's 3.8 M at cfg2, overlapped
+        with the other lanes, and nothing is left to reduce when backward ends."""
         (Qp, w_per, b_per, W_in, b_in, W_kv, in_w, in_b, out_w, out_b, gamma, W_po, Ecat, KVp, Wx, Wvf, q, u, attn_cat, probs, y,
          mean, rstd) = ctx.saved_tensors
         r, T, thr, seed, lo, has_in = ctx.r, ctx.T, ctx.thr, ctx.seed, ctx.lo, ctx.has_in
         ctx.lo = None
         B, d = r.B, W_po.shape[0]
         dt, dm = d // 2, r.d_m
+        Kx = dm + dt
         dev = Qp.device
         new = lambda *s: torch.empty(*s, dtype=_f32, device=dev)
         W_a = W_kv[:, :d]
         W_q, W_k, W_v = in_w[:d], in_w[d:2 * d], in_w[2 * d:]
         tc = ops.gemm_backend() != ops.BACKEND_FFMA
+        dp = ops.DP_GROUP is not None
+        fk = ops.Fork(dev, lanes=3)
         dE = dE_txt.contiguous().view(B * T, d)
         if ctx.defer:
             dW_po = db_po = None  # the consumer returns these
             dy = dE
         else:
-            dW_po = ops.linear_wgrad(dE, y, lo=lo)
-            db_po = ops.colsum(dE)
+            pack_po = new(d * d + d)
+            dW_po, db_po = pack_po[:d * d].view(d, d), pack_po[d * d:]
+            ops.linear_wgrad(dE, y, out=dW_po, lo=lo)
+            ops.colsum(dE, out=db_po)
+            if dp:
+                fk.run(lambda: ops.dp_allreduce(pack_po), pack_po, lane=0)
             dy = ops.linear_dgrad(dE, W_po, lo=lo)
+        pack_q = torch.zeros(5 * d, dtype=_f32, device=dev)  # dres | dgamma | dbeta (accumulated by ln_bwd) | du | db_o
         dx, dres, dgamma, dbeta = ops.ln_bwd(dy, attn_cat, Qp.view(d), r.m_txt, T, gamma, mean, rstd, thr, seed, ops.SITE_TTF_DROPOUT,
-                                             xbias=out_b)
+                                             xbias=out_b, acc=pack_q[:3 * d])
         # K half of dKVp: ds_n u (the score path's contribution to dX); V half: dV'; dq_partial: sum_n ds_n X_n = du per sample
         dKVp, du_partial = ops.segattn_bwd(dx, u, KVp, probs, r, T, 1, d, True, thr, seed)
         X, dXk, dVf = KVp[:, :d], dKVp[:, :d], dKVp[:, d:]
-        fk = ops.Fork(dev, lanes=3)
         if tc:
             lo.lo_for(dVf, r.m_dev)  # read on two streams: split before the fork
         d_in_w, d_in_b = torch.empty_like(in_w), new(3 * d)
         res = {}
 
         def params_value():  # V' = X (W_o W_v)^T + W_o b_v
-            dWvf, dWvf_lo = new(d, d), new(d, d)
-            ops.linear_wgrad(dVf, X, out=dWvf, ragged=r.m_dev, lo=lo, emit_lo=dWvf_lo)
-            dbvf = ops.colsum(dVf, ragged=r.m_dev)
+            pack_v = new(d * d + d)
+            dWvf, dbvf = pack_v[:d * d].view(d, d), pack_v[d * d:]
+            ops.linear_wgrad(dVf, X, out=dWvf, ragged=r.m_dev, lo=lo, emit_lo=False if dp else new(d, d))
+            ops.colsum(dVf, out=dbvf, ragged=r.m_dev)
+            ops.dp_allreduce(pack_v)
             dW_o = new(d, d)
             ops.gemm_group([dict(A=dWvf, B=W_v, C=dW_o, transB=True), dict(A=out_w, B=dWvf, C=d_in_w[2 * d:], transA=True)], lo)
             ops.gemm(dbvf.view(d, 1), in_b[2 * d:].view(1, d), dW_o, beta=1.0)
@@ -300,8 +314,9 @@ class T2VXAttnFoldFn(torch.autograd.Function):
             res["dW_o"] = dW_o
 
         def params_query():  # u = W_k^T q,  q = (Qp W_q^T + b_q) scale
-            res["db_o"] = ops.colsum(dx)
-            du = ops.colsum(du_partial).view(1, d)
+            du = ops.colsum(du_partial, out=pack_q[3 * d:4 * d]).view(1, d)
+            res["db_o"] = ops.colsum(dx, out=pack_q[4 * d:])
+            ops.dp_allreduce(pack_q)
             ops.gemm(q.view(d, 1), du, d_in_w[d:2 * d])  # dW_k = q (x) du
             ops.axpby(du, 0.0, d_in_b[d:2 * d], False)  # d b_k = 0: q . b_k is constant over a segment
             dq = ops.gemm(du, W_k, new(1, d), transB=True)
@@ -313,19 +328,22 @@ class T2VXAttnFoldFn(torch.autograd.Function):
             res["dQp"] = dQp
 
         fk.run(params_value, dKVp, d_in_w, d_in_b, lane=0)
-        fk.run(params_query, dx, du_partial, dres, d_in_w, d_in_b, lane=1)
+        fk.run(params_query, dx, du_partial, pack_q, d_in_w, d_in_b, lane=1)
         dX = ops.gemm(dVf, Wvf, dXk, beta=1.0, ragged=r.m_dev, ragged_dim=1, lo=lo, emit_lo=True)  # + ds (x) u, in place
 
         def params_x():  # X = [emb ; phi] [W_a W_in | W_phi]^T + (W_a b_in + b_kv)
-            dbX = ops.colsum(dX, ragged=r.m_dev)
-            if not has_in:
-                res["dW_kv"], res["db_kv"], res["dW_in"], res["db_in"] = ops.linear_wgrad(dX, Ecat, ragged=r.m_dev, lo=lo), dbX, None, None
-                return
-            Kx = dm + dt
-            dWx, dWx_lo = new(d, Kx), new(d, ops.round_up(Kx, 4))
+            pack_x = new(d * Kx + d)
+            dWx, dbX = pack_x[:d * Kx].view(d, Kx), pack_x[d * Kx:]
+            dWx_lo = new(d, ops.round_up(Kx, 4)) if (has_in and not dp) else False
             ops.linear_wgrad(dX, Ecat, out=dWx, ragged=r.m_dev, lo=lo, emit_lo=dWx_lo)
+            ops.colsum(dX, out=dbX, ragged=r.m_dev)
+            ops.dp_allreduce(pack_x)
+            if not has_in:
+                res["dW_kv"], res["db_kv"], res["dW_in"], res["db_in"] = dWx, dbX, None, None
+                return
             dP1 = dWx[:, :dm]
-            lo.put(dP1, dWx_lo[:, :dm])
+            if dWx_lo is not False:
+                lo.put(dP1, dWx_lo[:, :dm])
             dW_kv, dW_in, db_in = new(d, d + dt), new(d, dm), new(d)
             ops.gemm_group([dict(A=dP1, B=W_in, C=dW_kv[:, :d], transB=True), dict(A=W_a, B=dP1, C=dW_in, transA=True)], lo)
             ops.gemm(dbX.view(d, 1), b_in.view(1, d), dW_kv[:, :d], beta=1.0)  # W_a b_in also depends on W_a
@@ -337,12 +355,14 @@ class T2VXAttnFoldFn(torch.autograd.Function):
         dphi = ops.gemm(dX, Wx[:, dm:], new(r.M_alloc, dt), ragged=r.m_dev, ragged_dim=1, lo=lo)
 
         def params_t2v():
-            res["t2v"] = ops.time2vec_bwd(dphi, r, w_per, b_per, dt)
+            buf = torch.zeros(2 * dt, dtype=_f32, device=dev)
+            res["t2v"] = ops.time2vec_bwd(dphi, r, w_per, b_per, dt, buf=buf)
+            ops.dp_allreduce(buf)
 
         fk.run(params_t2v, dphi, lane=1)
         dwl, dbl, dwp, dbp = res["t2v"]
         dQp, dW_kv, db_kv, dW_in, db_in, dW_o, db_o = (res[k] for k in ("dQp", "dW_kv", "db_kv", "dW_in", "db_in", "dW_o", "db_o"))
-        fk.join(dQp, dW_in, db_in, dwl, dbl, dwp, dbp, dW_kv, db_kv, d_in_w, d_in_b, dW_o, db_o)
+        fk.join(dQp, dW_in, db_in, dwl, dbl, dwp, dbp, dW_kv, db_kv, d_in_w, d_in_b, dW_o, db_o, pack_q, dW_po, db_po)
         return (None, None, None, None, None, None, None, dQp.view(1, 1, d), dW_in, db_in, dwl, dbl, dwp, dbp, dW_kv, db_kv,
                 d_in_w, d_in_b, dW_o, db_o, dgamma, dbeta, dW_po, db_po)
 
@@ -692,15 +712,8 @@ class XAttnRankWeightsFn(torch.autograd.Function):
         new = lambda *s: torch.empty(*s, dtype=_f32, device=dev)
         in_k, in_v, b_k, b_v = in_w[d:2 * d], in_w[2 * d:], in_b[d:2 * d], in_b[2 * d:]
         dWr_eff, dbr, dbo_f = dWr_eff.contiguous(), dbr_eff.contiguous(), dbo_f.contiguous()
-        if ops.DP_GROUP is not None:
-            # data parallel: every gradient below is linear in these three small tensors and the parameters are replicated,
-            # so reducing THEM (H(2C+1) x (d+1) + C floats) gives all-reduced parameter gradients with no further traffic
-            import torch.distributed as dist
-
-            pack = torch.cat([dWr_eff.reshape(-1), dbr.reshape(-1), dbo_f.reshape(-1)])
-            dist.all_reduce(pack, op=dist.ReduceOp.SUM, group=ops.DP_GROUP)
-            n0 = dWr_eff.numel()
-            dWr_eff, dbr, dbo_f = pack[:n0].view_as(dWr_eff), pack[n0:n0 + nr], pack[n0 + nr:]
+        # (data parallel: dWr_eff, dbr_eff, dbo_f arrive already all-reduced from XAttnRankDataFn.backward -- every gradient below
+        # is linear in them and the parameters are replicated, so all of them are born reduced with no further traffic)
         dW_p = db_p = None
         if W_p is None:
             dWr = dWr_eff
@@ -780,8 +793,9 @@ class XAttnRankDataFn(torch.autograd.Function):
         nr, dk = Wr.shape
         dY_out = dY_out.contiguous()
         if ctx.fused:
-            dE, dY, dWr, dbr, dbo_f, dgamma, dbeta = ops.xattn_rank_fused_bwd(dY_out, delta_y, gamma, Y2, R, probs, m_txt, E2, Wr, B, T, H,
-                                                                              d, C, kappa, thr, seed)
+            dE, dY, dWr, dbr, dbo_f, dgamma, dbeta, pack = ops.xattn_rank_fused_bwd(dY_out, delta_y, gamma, Y2, R, probs, m_txt, E2, Wr, B, T,
+                                                                                    H, d, C, kappa, thr, seed)
+            ops.dp_allreduce(pack)  # [dWr | dbr | d bo_f | dgamma | dbeta]: the sufficient statistics of every MMF gradient
         else:
             d_delta, dgamma, dbeta = ops.xattn_tail_bwd(dY_out, delta_y, gamma, m_txt, B, T, C, kappa, thr, seed)
             dbo_f = ops.colsum(d_delta)  # = d(b_r)
@@ -790,4 +804,9 @@ class XAttnRankDataFn(torch.autograd.Function):
             dWr = ops.gemm(dR, E2, torch.empty(nr, dk, dtype=_f32, device=dR.device), transA=True)
             dbr = ops.colsum(dR)
             dE = ops.gemm(dR, Wr, torch.empty(B * T, dk, dtype=_f32, device=dR.device))
+            if ops.DP_GROUP is not None:
+                pack = torch.cat([dWr.reshape(-1), dbr, dbo_f, dgamma, dbeta])
+                ops.dp_allreduce(pack)
+                n0, o = dWr.numel(), dWr.numel() + nr
+                dWr, dbr, dbo_f, dgamma, dbeta = pack[:n0].view_as(dWr), pack[n0:o], pack[o:o + C], pack[o + C:o + 2 * C], pack[o + 2 * C:]
         return dY.view(B, T, C), dE.view(B, T, dk), None, None, None, None, None, None, None, None, dWr, dbr, dbo_f, dgamma, dbeta

@@ -196,6 +196,22 @@ _SIDE = {}
 # process group for in-graph data parallelism (runtime.GraphedStep(allreduce_group=...)): while set, the weight-space
 # backward of the rank form all-reduces its upstream gradients and so produces already-reduced parameter gradients
 DP_GROUP = None
+DP_STATS = {"floats": 0, "calls": 0}  # what dp_allreduce moved since it was last cleared (runtime.GraphedStep: per captured step)
+
+
+def dp_allreduce(buf: torch.Tensor) -> torch.Tensor:
+    """SUM all-reduce of `buf` over DP_GROUP on the current stream (no-op without a group).  The autograd Functions call it
+    on the SUFFICIENT STATISTICS of their parameter gradients -- the packed outputs of the weight-gradient products before
+    the weight-space un-folds, which are linear in them with replicated parameters -- so the parameter gradients are born
+    reduced, fewer floats cross NVLink than the parameters have, and no collective is left for the end of the step."""
+    if DP_GROUP is None:
+        return buf
+    import torch.distributed as dist
+
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=DP_GROUP)
+    DP_STATS["floats"] += buf.numel()
+    DP_STATS["calls"] += 1
+    return buf
 
 
 def side_stream(dev) -> "torch.cuda.Stream":
@@ -485,12 +501,13 @@ def time2vec_fwd(r: RaggedNotes, w_lin, b_lin, w_per, b_per, d_tau, out_view, lo
               out_view.stride(0), _p(lo_view), lo_view.stride(0) if lo_view is not None else 0, _p(r.m_dev), r.M_alloc, _stream())
 
 
-def time2vec_bwd(dphi_view, r: RaggedNotes, w_per, b_per, d_tau):
+def time2vec_bwd(dphi_view, r: RaggedNotes, w_per, b_per, d_tau, buf=None):
+    """buf: optional ZEROED [2 * d_tau] buffer the four gradients are accumulated into (views of it are returned)."""
     dev = dphi_view.device
-    dwl = torch.zeros(1, 1, dtype=torch.float32, device=dev)
-    dbl = torch.zeros(1, dtype=torch.float32, device=dev)
-    dwp = torch.zeros(d_tau - 1, 1, dtype=torch.float32, device=dev)
-    dbp = torch.zeros(d_tau - 1, dtype=torch.float32, device=dev)
+    if buf is None:
+        buf = torch.zeros(2 * d_tau, dtype=torch.float32, device=dev)
+    dwl, dbl = buf[0:1].view(1, 1), buf[1:2]
+    dwp, dbp = buf[2:d_tau + 1].view(d_tau - 1, 1), buf[d_tau + 1:2 * d_tau]
     _lib.call("immtsf_time2vec_bwd", _p(dphi_view), dphi_view.stride(0), _p(r.tau_flat), _p(w_per), _p(b_per), d_tau,
               _p(dwl), _p(dbl), _p(dwp), _p(dbp), _p(r.m_dev), r.M_alloc, _stream())
     return dwl, dbl, dwp, dbp
@@ -562,13 +579,15 @@ def ln_fwd(x, res, valid, rows_per_sample, gamma, beta, thr, seed, site, save, x
     return y, mean, rstd
 
 
-def ln_bwd(dy, x, res, valid, rows_per_sample, gamma, mean, rstd, thr, seed, site, xbias=None):
+def ln_bwd(dy, x, res, valid, rows_per_sample, gamma, mean, rstd, thr, seed, site, xbias=None, acc=None):
+    """acc: optional ZEROED [3 * d] buffer for (dres, dgamma, dbeta) -- one fill instead of three; views of it are returned."""
     R, d = x.shape
     dev = x.device
     dx = torch.empty(R, d, dtype=torch.float32, device=dev)
-    dres = torch.zeros(d, dtype=torch.float32, device=dev) if res is not None else None
-    dgamma = torch.zeros(d, dtype=torch.float32, device=dev)
-    dbeta = torch.zeros(d, dtype=torch.float32, device=dev)
+    if acc is None:
+        acc = torch.zeros(3 * d, dtype=torch.float32, device=dev)
+    dres = acc[0:d] if res is not None else None
+    dgamma, dbeta = acc[d:2 * d], acc[2 * d:3 * d]
     _lib.call("immtsf_ln_bwd", _p(dy), _p(x), x.stride(0), _p(xbias), _p(res), _p(valid), rows_per_sample, _p(gamma), _p(mean), _p(rstd),
               R, d, thr, seed, site, _p(dx), _p(dres), _p(dgamma), _p(dbeta), _stream())
     return dx, dres, dgamma, dbeta
@@ -766,20 +785,21 @@ def xattn_rank_fused_fwd(Y2, E2, Wr, br, bo, gamma, beta, m_txt, B, T, H, d, C, 
 
 
 def xattn_rank_fused_bwd(dY_out, delta_y, gamma, Y2, R, probs, m_txt, E2, Wr, B, T, H, d, C, kappa, thr, seed):
-    """Returns dE [B*T, de], dY [B*T, C], dWr [nr, de], dbr [nr], d(bo_f) [C], dgamma [C], dbeta [C]."""
+    """Returns dE [B*T, de], dY [B*T, C], dWr [nr, de], dbr [nr], d(bo_f) [C], dgamma [C], dbeta [C] and the buffer the last five
+    are views of."""
     dev = E2.device
     nr, de = Wr.shape
     dE = torch.empty(B * T, de, dtype=torch.float32, device=dev)
     dY = torch.empty(B * T, C, dtype=torch.float32, device=dev)
-    dWr = torch.empty(nr, de, dtype=torch.float32, device=dev)
-    small = torch.empty(nr + 3 * C, dtype=torch.float32, device=dev)
+    pack = torch.empty(nr * de + nr + 3 * C, dtype=torch.float32, device=dev)  # one buffer: the data-parallel all-reduce takes it whole
+    dWr, small = pack[:nr * de].view(nr, de), pack[nr * de:]
     need = _lib.load().immtsf_xattn_rank_fused_bwd_workspace_bytes(B, H, C, de)
     ws = _workspace(dev, need + 256)
     off = (-ws.data_ptr()) % 16
     _lib.call("immtsf_xattn_rank_fused_bwd", _p(dY_out), _p(delta_y), _p(gamma), _p(Y2), Y2.stride(0), _p(R), R.stride(0), _p(probs),
               _p(m_txt), _p(E2), E2.stride(0), de, _p(Wr), Wr.stride(0), B, T, H, d, C, LN_EPS, float(kappa), thr, seed, _p(dE),
               dE.stride(0), _p(dY), _p(dWr), _p(small), ws.data_ptr() + off, ws.numel() - off, _stream())
-    return dE, dY, dWr, small[:nr], small[nr:nr + C], small[nr + C:nr + 2 * C], small[nr + 2 * C:]
+    return dE, dY, dWr, small[:nr], small[nr:nr + C], small[nr + C:nr + 2 * C], small[nr + 2 * C:], pack
 
 
 def xattn_tail_fwd(Y, delta_y, gamma, beta, m_txt, B, T, C, kappa, thr, seed, flags):

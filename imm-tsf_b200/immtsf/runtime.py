@@ -166,6 +166,7 @@ class GraphedStep:
         try:
             # NCCL's watchdog thread may touch CUDA while we capture: thread-local capture mode tolerates that
             mode = dict(capture_error_mode="thread_local") if self.group is not None else {}
+            ops.DP_STATS["floats"] = ops.DP_STATS["calls"] = 0
             with torch.cuda.graph(self.graph, stream=side, **mode):
                 _lib.call("immtsf_seed_advance", self.seed_offset.data_ptr(), 1, ops._stream())
                 if self.flat_grads is not None:
@@ -175,6 +176,8 @@ class GraphedStep:
                     self._reduce_rest()
         finally:
             ops.DP_GROUP = None
+        # what one replay sends through the all-reduces captured inside the Functions (floats, collectives)
+        self.dp_floats_per_step, self.dp_calls_per_step = ops.DP_STATS["floats"], ops.DP_STATS["calls"]
         self.Y_out, self.loss = out.detach(), loss.detach()
         self.flags = getattr(fusion, "_last_flags", None)
 
@@ -185,10 +188,14 @@ class GraphedStep:
         if self.coalesced:
             todo = [p.grad for p in self.params if id(p) not in self._pre_ids and p.grad is not None]
             if todo:
+                ops.DP_STATS["floats"] += sum(g.numel() for g in todo)
+                ops.DP_STATS["calls"] += 1
                 with dist._coalescing_manager(group=self.group, device=todo[0].device):
                     for g in todo:
                         dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group)
         elif self.n_first < self.flat_grads.numel():
+            ops.DP_STATS["floats"] += self.flat_grads.numel() - self.n_first
+            ops.DP_STATS["calls"] += 1
             dist.all_reduce(self.flat_grads[self.n_first:], op=dist.ReduceOp.SUM, group=self.group)
 
     def _eager(self):

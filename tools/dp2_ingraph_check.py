@@ -33,7 +33,8 @@ def main():
         # rank form: the MMF weight gradients (and RecAvg's folded `proj`) are born reduced and not communicated
         assert step.group is not None and (step.n_first > 0) == (mmf == "MMF_XAttn_Add"), step.n_first
         if rank == 0:
-            print(f"{ttf}+{mmf}: {step.n_first} of {step.n_total} gradient floats never communicated", flush=True)
+            print(f"{ttf}+{mmf}: {step.n_first} of {step.n_total} gradient floats born reduced; {step.dp_calls_per_step} collectives, "
+                  f"{step.dp_floats_per_step} floats per step", flush=True)
         try:
             for _ in range(2):  # replays re-zero the flat bucket and reduce again
                 step(*mine)
