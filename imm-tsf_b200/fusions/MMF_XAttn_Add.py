@@ -39,7 +39,7 @@ class MMF_XAttn_Add(nn.Module):
         folds the producer's deferred last projection in.  side=True runs it on ops.side_stream() -- it depends on
         parameters only, so FusionModel starts it before the TTF forward; join with `wait_rank_weights`."""
         W_p, b_p = final_proj if final_proj is not None else (None, None)
-        args = (self.n_heads, self.C) + self._params()[:9] + (W_p, b_p)
+        args = (self.n_heads, self.C) + self._params()[:9] + (W_p, b_p, self.layer_norm.weight, self.layer_norm.bias)
         def work():
             if flags is not None and W_p is not None:  # NaN guard of the folded projection (FusionModel.py:107-108)
                 ops.nan_check(W_p, flags, ops.FLAG_E)
@@ -76,10 +76,9 @@ class MMF_XAttn_Add(nn.Module):
         own_flags = None if flags is False else (flags if flags is not None else runtime.new_flags(Y_ts.device))
         # Time-IMM shapes (T <= 32, few channels): the rank-(2C+1) form -- one skinny pass over E_txt, no tensor of width d
         if self.rank_path(T):
-            Wr, br, bo_f = rank_weights if rank_weights is not None else self.rank_weights(final_proj)
+            Wr, br, bo_f, gamma, beta = rank_weights if rank_weights is not None else self.rank_weights(final_proj)
             out = F_.XAttnRankDataFn.apply(cm.as_f32(Y_ts), cm.as_f32(E_txt), cm.m_txt_u8(M_txt, B), self.n_heads,
-                                           float(self.kappa), thr, seed, save, own_flags, self.d_attn, Wr, br, bo_f,
-                                           self.layer_norm.weight, self.layer_norm.bias)
+                                           float(self.kappa), thr, seed, save, own_flags, self.d_attn, Wr, br, bo_f, gamma, beta)
         else:
             if final_proj is not None or rank_weights is not None:
                 raise RuntimeError("MMF_XAttn_Add: a deferred projection needs the rank path")

@@ -290,23 +290,35 @@ class T2VXAttnFoldFn(torch.autograd.Function):
             if dp:
                 fk.run(lambda: ops.dp_allreduce(pack_po), pack_po, lane=0)
             dy = ops.linear_dgrad(dE, W_po, lo=lo)
-        pack_q = torch.zeros(5 * d, dtype=_f32, device=dev)  # dres | dgamma | dbeta (accumulated by ln_bwd) | du | db_o
+        # two packed buffers hold every gradient statistic of the module (data parallel: ONE all-reduce each, issued on a lane
+        # as soon as the last contribution has landed; the lanes wait for each other through events, the data chain never waits)
+        pack_qv = new(5 * d + d * d + d)  # dres | dgamma | dbeta (accumulated by ln_bwd) | du | db_o | dW_vf | db_vf
+        pack_qv[:3 * d].zero_()
+        pack_x = new(d * Kx + d + 2 * dt)  # dW_x | db_x | Time2Vec gradients (accumulated)
+        pack_x[d * Kx + d:].zero_()
         dx, dres, dgamma, dbeta = ops.ln_bwd(dy, attn_cat, Qp.view(d), r.m_txt, T, gamma, mean, rstd, thr, seed, ops.SITE_TTF_DROPOUT,
-                                             xbias=out_b, acc=pack_q[:3 * d])
+                                             xbias=out_b, acc=pack_qv[:3 * d])
         # K half of dKVp: ds_n u (the score path's contribution to dX); V half: dV'; dq_partial: sum_n ds_n X_n = du per sample
         dKVp, du_partial = ops.segattn_bwd(dx, u, KVp, probs, r, T, 1, d, True, thr, seed)
         X, dXk, dVf = KVp[:, :d], dKVp[:, :d], dKVp[:, d:]
         if tc:
             lo.lo_for(dVf, r.m_dev)  # read on two streams: split before the fork
         d_in_w, d_in_b = torch.empty_like(in_w), new(3 * d)
-        res = {}
+        res, ev = {}, {}
+
+        def sums_query():
+            res["du"] = ops.colsum(du_partial, out=pack_qv[3 * d:4 * d]).view(1, d)
+            res["db_o"] = ops.colsum(dx, out=pack_qv[4 * d:5 * d])
+            ev["q"] = fk.mark(1)
 
         def params_value():  # V' = X (W_o W_v)^T + W_o b_v
-            pack_v = new(d * d + d)
-            dWvf, dbvf = pack_v[:d * d].view(d, d), pack_v[d * d:]
+            dWvf, dbvf = pack_qv[5 * d:5 * d + d * d].view(d, d), pack_qv[5 * d + d * d:]
             ops.linear_wgrad(dVf, X, out=dWvf, ragged=r.m_dev, lo=lo, emit_lo=False if dp else new(d, d))
             ops.colsum(dVf, out=dbvf, ragged=r.m_dev)
-            ops.dp_allreduce(pack_v)
+            if dp:
+                fk.lane_wait(0, ev["q"])
+                ops.dp_allreduce(pack_qv)
+                ev["qv"] = fk.mark(0)
             dW_o = new(d, d)
             ops.gemm_group([dict(A=dWvf, B=W_v, C=dW_o, transB=True), dict(A=out_w, B=dWvf, C=d_in_w[2 * d:], transA=True)], lo)
             ops.gemm(dbvf.view(d, 1), in_b[2 * d:].view(1, d), dW_o, beta=1.0)
@@ -314,9 +326,9 @@ class T2VXAttnFoldFn(torch.autograd.Function):
             res["dW_o"] = dW_o
 
         def params_query():  # u = W_k^T q,  q = (Qp W_q^T + b_q) scale
-            du = ops.colsum(du_partial, out=pack_q[3 * d:4 * d]).view(1, d)
-            res["db_o"] = ops.colsum(dx, out=pack_q[4 * d:])
-            ops.dp_allreduce(pack_q)
+            if dp:
+                fk.lane_wait(1, ev["qv"])
+            du = res["du"]
             ops.gemm(q.view(d, 1), du, d_in_w[d:2 * d])  # dW_k = q (x) du
             ops.axpby(du, 0.0, d_in_b[d:2 * d], False)  # d b_k = 0: q . b_k is constant over a segment
             dq = ops.gemm(du, W_k, new(1, d), transB=True)
@@ -327,17 +339,26 @@ class T2VXAttnFoldFn(torch.autograd.Function):
             ops.axpby(dres, 1.0, dQp.view(d), True)
             res["dQp"] = dQp
 
-        fk.run(params_value, dKVp, d_in_w, d_in_b, lane=0)
-        fk.run(params_query, dx, du_partial, pack_q, d_in_w, d_in_b, lane=1)
+        fk.run(sums_query, dx, du_partial, pack_qv, lane=1)
+        fk.run(params_value, dKVp, pack_qv, d_in_w, d_in_b, lane=0)
+        fk.run(params_query, d_in_w, d_in_b, lane=1, after_current=False)
         dX = ops.gemm(dVf, Wvf, dXk, beta=1.0, ragged=r.m_dev, ragged_dim=1, lo=lo, emit_lo=True)  # + ds (x) u, in place
+        dWx, dbX = pack_x[:d * Kx].view(d, Kx), pack_x[d * Kx:d * Kx + d]
+        dWx_lo = new(d, ops.round_up(Kx, 4)) if (has_in and not dp) else False
 
-        def params_x():  # X = [emb ; phi] [W_a W_in | W_phi]^T + (W_a b_in + b_kv)
-            pack_x = new(d * Kx + d)
-            dWx, dbX = pack_x[:d * Kx].view(d, Kx), pack_x[d * Kx:]
-            dWx_lo = new(d, ops.round_up(Kx, 4)) if (has_in and not dp) else False
+        def sums_x():  # X = [emb ; phi] [W_a W_in | W_phi]^T + (W_a b_in + b_kv)
             ops.linear_wgrad(dX, Ecat, out=dWx, ragged=r.m_dev, lo=lo, emit_lo=dWx_lo)
             ops.colsum(dX, out=dbX, ragged=r.m_dev)
-            ops.dp_allreduce(pack_x)
+
+        fk.run(sums_x, dX, pack_x, *([lo.lo_for(dX, r.m_dev)] if fk.side is not None and tc else []), lane=2)
+        dphi = ops.gemm(dX, Wx[:, dm:], new(r.M_alloc, dt), ragged=r.m_dev, ragged_dim=1, lo=lo)
+
+        def params_t2v():
+            res["t2v"] = ops.time2vec_bwd(dphi, r, w_per, b_per, dt, buf=pack_x[d * Kx + d:])
+
+        def params_x():
+            if dp:
+                ops.dp_allreduce(pack_x)
             if not has_in:
                 res["dW_kv"], res["db_kv"], res["dW_in"], res["db_in"] = dWx, dbX, None, None
                 return
@@ -351,18 +372,12 @@ class T2VXAttnFoldFn(torch.autograd.Function):
             ops.multi_split([(dWx[:, dm:], dW_kv[:, d:], None)])
             res["dW_kv"], res["db_kv"], res["dW_in"], res["db_in"] = dW_kv, dbX, dW_in, db_in
 
-        fk.run(params_x, dX, *([lo.lo_for(dX, r.m_dev)] if fk.side is not None and tc else []), lane=2)
-        dphi = ops.gemm(dX, Wx[:, dm:], new(r.M_alloc, dt), ragged=r.m_dev, ragged_dim=1, lo=lo)
-
-        def params_t2v():
-            buf = torch.zeros(2 * dt, dtype=_f32, device=dev)
-            res["t2v"] = ops.time2vec_bwd(dphi, r, w_per, b_per, dt, buf=buf)
-            ops.dp_allreduce(buf)
-
-        fk.run(params_t2v, dphi, lane=1)
+        fk.run(params_t2v, dphi, pack_x, lane=2)  # (same lane as dW_x: the lane's all-reduce follows both)
+        fk.run(params_x, lane=2, after_current=False)
+        db_o = res["db_o"]
         dwl, dbl, dwp, dbp = res["t2v"]
-        dQp, dW_kv, db_kv, dW_in, db_in, dW_o, db_o = (res[k] for k in ("dQp", "dW_kv", "db_kv", "dW_in", "db_in", "dW_o", "db_o"))
-        fk.join(dQp, dW_in, db_in, dwl, dbl, dwp, dbp, dW_kv, db_kv, d_in_w, d_in_b, dW_o, db_o, pack_q, dW_po, db_po)
+        dQp, dW_kv, db_kv, dW_in, db_in, dW_o = (res[k] for k in ("dQp", "dW_kv", "db_kv", "dW_in", "db_in", "dW_o"))
+        fk.join(dQp, dW_in, db_in, dW_kv, d_in_w, d_in_b, dW_o, pack_qv, pack_x, dW_po, db_po)
         return (None, None, None, None, None, None, None, dQp.view(1, 1, d), dW_in, db_in, dwl, dbl, dwp, dbp, dW_kv, db_kv,
                 d_in_w, d_in_b, dW_o, db_o, dgamma, dbeta, dW_po, db_po)
 
@@ -669,7 +684,10 @@ class XAttnRankWeightsFn(torch.autograd.Function):
     to the TTF forward, and autograd runs its backward on that stream next to the TTF backward."""
 
     @staticmethod
-    def forward(ctx, H, C, W_Q, W_K, W_V, in_w, in_b, out_w, out_b, W_r, b_r, W_p, b_p):
+    def forward(ctx, H, C, W_Q, W_K, W_V, in_w, in_b, out_w, out_b, W_r, b_r, W_p, b_p, gamma=None, beta=None):
+        """gamma, beta (the module's LayerNorm parameters) are handed through unchanged: their gradients then come back through
+        THIS Function's backward, which runs on the side stream after the data-parallel all-reduce of the packed upstream
+        gradients -- the data chain of the step never waits for that collective."""
         d, de = W_Q.shape[0], W_K.shape[1]
         hd, C1 = d // H, C + 1
         n1, nr = H * C1, H * (2 * C + 1)
@@ -697,12 +715,14 @@ class XAttnRankWeightsFn(torch.autograd.Function):
             ops.axpby(br, 1.0, br_eff, True)
         else:
             Wr_eff, br_eff = Wr, br
-        ctx.H, ctx.C, ctx.dims = H, C, (d, de)
+        ctx.H, ctx.C, ctx.dims, ctx.ln = H, C, (d, de), gamma is not None
         ctx.save_for_backward(W_Q, W_K, W_V, in_w, in_b, out_w, out_b, W_r, Wq_aug, Wo_f, P1, P2, Wr, W_p, b_p)
+        if gamma is not None:
+            return Wr_eff, br_eff, bo_f, gamma.view_as(gamma), beta.view_as(beta)
         return Wr_eff, br_eff, bo_f
 
     @staticmethod
-    def backward(ctx, dWr_eff, dbr_eff, dbo_f):
+    def backward(ctx, dWr_eff, dbr_eff, dbo_f, dgamma=None, dbeta=None):
         W_Q, W_K, W_V, in_w, in_b, out_w, out_b, W_r, Wq_aug, Wo_f, P1, P2, Wr, W_p, b_p = ctx.saved_tensors
         H, C = ctx.H, ctx.C
         d, de = ctx.dims
@@ -712,8 +732,24 @@ class XAttnRankWeightsFn(torch.autograd.Function):
         new = lambda *s: torch.empty(*s, dtype=_f32, device=dev)
         in_k, in_v, b_k, b_v = in_w[d:2 * d], in_w[2 * d:], in_b[d:2 * d], in_b[2 * d:]
         dWr_eff, dbr, dbo_f = dWr_eff.contiguous(), dbr_eff.contiguous(), dbo_f.contiguous()
-        # (data parallel: dWr_eff, dbr_eff, dbo_f arrive already all-reduced from XAttnRankDataFn.backward -- every gradient below
-        # is linear in them and the parameters are replicated, so all of them are born reduced with no further traffic)
+        if ops.DP_GROUP is not None:
+            # data parallel: every gradient below is linear in these upstream tensors and the parameters are replicated, so
+            # reducing THEM (H(2C+1) x (d+1) + 3C floats) gives all-reduced parameter gradients with no further traffic.
+            # XAttnRankDataFn.backward wrote them into one buffer (ops.RANK_PACK): one collective, no gather copy.
+            pack = ops.RANK_PACK
+            ops.RANK_PACK = None
+            if pack is not None and pack.data_ptr() == dWr_eff.data_ptr():
+                pass  # already reduced on this (side) stream by XAttnRankDataFn.backward
+            else:
+                parts = [dWr_eff, dbr, dbo_f] + ([dgamma, dbeta] if dgamma is not None else [])
+                pack = ops.dp_allreduce(torch.cat([t.reshape(-1) for t in parts]))
+                outs, o = [], 0
+                for t in parts:
+                    outs.append(pack[o:o + t.numel()].view_as(t))
+                    o += t.numel()
+                dWr_eff, dbr, dbo_f = outs[:3]
+                if dgamma is not None:
+                    dgamma, dbeta = outs[3:]
         dW_p = db_p = None
         if W_p is None:
             dWr = dWr_eff
@@ -753,7 +789,7 @@ class XAttnRankWeightsFn(torch.autograd.Function):
         ops.gemm(dWq_f, W_Q, d_in_w[:d], transB=True)
         dW_Q = ops.gemm(in_w[:d], dWq_f, new(d, C), transA=True)
         ops.multi_split([(dWq_aug[:, C:], d_in_b[:d].view(d, 1), None)])
-        return None, None, dW_Q, dW_K, dW_V, d_in_w, d_in_b, dW_o, db_o, dW_r, dbo_f, dW_p, db_p
+        return None, None, dW_Q, dW_K, dW_V, d_in_w, d_in_b, dW_o, db_o, dW_r, dbo_f, dW_p, db_p, dgamma, dbeta
 
 
 class XAttnRankDataFn(torch.autograd.Function):
@@ -795,7 +831,17 @@ class XAttnRankDataFn(torch.autograd.Function):
         if ctx.fused:
             dE, dY, dWr, dbr, dbo_f, dgamma, dbeta, pack = ops.xattn_rank_fused_bwd(dY_out, delta_y, gamma, Y2, R, probs, m_txt, E2, Wr, B, T,
                                                                                     H, d, C, kappa, thr, seed)
-            ops.dp_allreduce(pack)  # [dWr | dbr | d bo_f | dgamma | dbeta]: the sufficient statistics of every MMF gradient
+            if ops.DP_GROUP is not None:
+                # [dWr | dbr | d bo_f | dgamma | dbeta] are the sufficient statistics of every MMF gradient: all-reduced HERE (first in
+                # the step's collective order) but on the SIDE stream, where XAttnRankWeightsFn.backward -- their only consumer, the
+                # LayerNorm gradients included -- runs; the data chain does not wait for the collective
+                cur = torch.cuda.current_stream()
+                side = ops.side_stream(cur.device)
+                side.wait_stream(cur)
+                pack.record_stream(side)
+                with torch.cuda.stream(side):
+                    ops.dp_allreduce(pack)
+                ops.RANK_PACK = pack
         else:
             d_delta, dgamma, dbeta = ops.xattn_tail_bwd(dY_out, delta_y, gamma, m_txt, B, T, C, kappa, thr, seed)
             dbo_f = ops.colsum(d_delta)  # = d(b_r)
@@ -804,9 +850,4 @@ class XAttnRankDataFn(torch.autograd.Function):
             dWr = ops.gemm(dR, E2, torch.empty(nr, dk, dtype=_f32, device=dR.device), transA=True)
             dbr = ops.colsum(dR)
             dE = ops.gemm(dR, Wr, torch.empty(B * T, dk, dtype=_f32, device=dR.device))
-            if ops.DP_GROUP is not None:
-                pack = torch.cat([dWr.reshape(-1), dbr, dbo_f, dgamma, dbeta])
-                ops.dp_allreduce(pack)
-                n0, o = dWr.numel(), dWr.numel() + nr
-                dWr, dbr, dbo_f, dgamma, dbeta = pack[:n0].view_as(dWr), pack[n0:o], pack[o:o + C], pack[o + C:o + 2 * C], pack[o + 2 * C:]
         return dY.view(B, T, C), dE.view(B, T, dk), None, None, None, None, None, None, None, None, dWr, dbr, dbo_f, dgamma, dbeta

@@ -196,6 +196,7 @@ _SIDE = {}
 # process group for in-graph data parallelism (runtime.GraphedStep(allreduce_group=...)): while set, the weight-space
 # backward of the rank form all-reduces its upstream gradients and so produces already-reduced parameter gradients
 DP_GROUP = None
+RANK_PACK = None  # hand-off of the rank form's packed upstream gradients from the data Function to the weights Function
 DP_STATS = {"floats": 0, "calls": 0}  # what dp_allreduce moved since it was last cleared (runtime.GraphedStep: per captured step)
 
 
@@ -271,6 +272,11 @@ class Fork:
         ev = torch.cuda.Event()
         ev.record(self.lanes[lane % len(self.lanes)])
         return ev
+
+    def lane_wait(self, lane: int, ev):
+        """Order lane `lane` after event `ev` (an event of another lane)."""
+        if ev is not None and self.lanes:
+            self.lanes[lane % len(self.lanes)].wait_event(ev)
 
     def wait(self, ev, *tensors):
         if ev is not None:

@@ -24,8 +24,8 @@ def timeit(fn, n=30):
     t = torch.tensor([e0.elapsed_time(e1) / n], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return t.item() * 1e3
 
-for mb in (4, 15.4, 32):
-    n = int(mb * 1e6 / 4) // 1024 * 1024
+for mb in ([float(a) for a in sys.argv[1:]] or [4, 15.4, 32]):
+    n = max(int(mb * 1e6 / 4) // 1024 * 1024, 1024)
     x = torch.randn(n, device=dev)
     res = {"nccl": timeit(lambda: dist.all_reduce(x))}
     try:
