@@ -551,6 +551,8 @@ def run_gpu_arm(args, w):
                            "%d collectives and %.2f MB per step per GPU for %d gradient floats (%.2f MB); gradients of %d floats are born reduced"
                            % (graphed.dp_calls_per_step, graphed.dp_floats_per_step * 4 / 1e6, graphed.n_total, graphed.n_total * 4 / 1e6,
                               graphed.n_first))
+                dp_mode += ("; %d of the collectives are the hand-written NVSwitch multimem all-reduce (csrc/nvls.cu), the rest NCCL"
+                            % graphed.dp_nvls_calls_per_step)
             except Exception as e:  # capture of NCCL refused: fall back to one all-reduce after the replay
                 print(f"[bench] in-graph all-reduce unavailable ({type(e).__name__}: {e}); reducing after the replay", file=sys.stderr)
                 torch.cuda.synchronize()

@@ -78,6 +78,7 @@ SIGNATURES = {
     "immtsf_exclusive_scan_i32": [P, I, P, P, P],
     "immtsf_window_fill": [P, P, P, P, P, I, P, P, P, P],
     "immtsf_batch_gather": [P, I, I, P, P, P, P, P, I, I, P, I, P, P],
+    "immtsf_nvls_allreduce_f32": [P, P, SZ, SZ, SZ, I, I, P, P],
     "immtsf_axpby": [P, F, P, I, SZ, P],
     "immtsf_group_sum_rows": [P, I, I, I, I, P, P],
 }
@@ -114,6 +115,8 @@ def load():
     lib.immtsf_t2vq_bwd_workspace_bytes.restype = SZ
     lib.immtsf_xattn_rank_fused_bwd_workspace_bytes.argtypes = [I, I, I, I]
     lib.immtsf_xattn_rank_fused_bwd_workspace_bytes.restype = SZ
+    lib.immtsf_nvls_flag_bytes.argtypes = [I]
+    lib.immtsf_nvls_flag_bytes.restype = SZ
     lib.immtsf_masked_mse_workspace_bytes.argtypes = [I]
     lib.immtsf_masked_mse_workspace_bytes.restype = SZ
     lib.immtsf_gemm_batched_workspace_bytes.argtypes = [I, I, I, I, I, I, L, L, I, L, L, I, I]

@@ -283,7 +283,7 @@ class T2VXAttnFoldFn(torch.autograd.Function):
             dW_po = db_po = None  # the consumer returns these
             dy = dE
         else:
-            pack_po = new(d * d + d)
+            pack_po = ops.dp_pack(d * d + d, dev)
             dW_po, db_po = pack_po[:d * d].view(d, d), pack_po[d * d:]
             ops.linear_wgrad(dE, y, out=dW_po, lo=lo)
             ops.colsum(dE, out=db_po)
@@ -292,9 +292,9 @@ class T2VXAttnFoldFn(torch.autograd.Function):
             dy = ops.linear_dgrad(dE, W_po, lo=lo)
         # two packed buffers hold every gradient statistic of the module (data parallel: ONE all-reduce each, issued on a lane
         # as soon as the last contribution has landed; the lanes wait for each other through events, the data chain never waits)
-        pack_qv = new(5 * d + d * d + d)  # dres | dgamma | dbeta (accumulated by ln_bwd) | du | db_o | dW_vf | db_vf
+        pack_qv = ops.dp_pack(5 * d + d * d + d, dev)  # dres | dgamma | dbeta (accumulated by ln_bwd) | du | db_o | dW_vf | db_vf
         pack_qv[:3 * d].zero_()
-        pack_x = new(d * Kx + d + 2 * dt)  # dW_x | db_x | Time2Vec gradients (accumulated)
+        pack_x = ops.dp_pack(d * Kx + d + 2 * dt, dev)  # dW_x | db_x | Time2Vec gradients (accumulated)
         pack_x[d * Kx + d:].zero_()
         dx, dres, dgamma, dbeta = ops.ln_bwd(dy, attn_cat, Qp.view(d), r.m_txt, T, gamma, mean, rstd, thr, seed, ops.SITE_TTF_DROPOUT,
                                              xbias=out_b, acc=pack_qv[:3 * d])

@@ -183,6 +183,8 @@ _STEP: Optional[StepCtx] = None
 
 def begin_step(e_txt_feeds_tc: bool) -> StepCtx:
     global _STEP
+    if DP_NVLS is not None:
+        DP_NVLS.reset()  # the statistics buffers of a step sit at the same arena offsets in every step
     _STEP = StepCtx(e_txt_feeds_tc=e_txt_feeds_tc)
     return _STEP
 
@@ -207,12 +209,29 @@ def dp_allreduce(buf: torch.Tensor) -> torch.Tensor:
     reduced, fewer floats cross NVLink than the parameters have, and no collective is left for the end of the step."""
     if DP_GROUP is None:
         return buf
+    DP_STATS["floats"] += buf.numel()
+    DP_STATS["calls"] += 1
+    if DP_NVLS is not None and DP_NVLS.owns(buf):
+        DP_NVLS.all_reduce(buf)  # hand-written in-switch all-reduce (csrc/nvls.cu)
+        DP_STATS["nvls"] = DP_STATS.get("nvls", 0) + 1
+        return buf
     import torch.distributed as dist
 
     dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=DP_GROUP)
-    DP_STATS["floats"] += buf.numel()
-    DP_STATS["calls"] += 1
     return buf
+
+
+DP_NVLS = None  # immtsf.nvls.NvlsComm of DP_GROUP when the fabric has NVSwitch multicast
+
+
+def dp_pack(n: int, device) -> torch.Tensor:
+    """Buffer for `n` floats of gradient statistics: a piece of the symmetric arena when the in-switch all-reduce is
+    available (the producing kernels then write straight into memory every peer has mapped), else plain device memory."""
+    if DP_GROUP is not None and DP_NVLS is not None:
+        t = DP_NVLS.alloc(n)
+        if t is not None:
+            return t
+    return torch.empty(n, dtype=torch.float32, device=device)
 
 
 def side_stream(dev) -> "torch.cuda.Stream":
@@ -797,7 +816,7 @@ def xattn_rank_fused_bwd(dY_out, delta_y, gamma, Y2, R, probs, m_txt, E2, Wr, B,
     nr, de = Wr.shape
     dE = torch.empty(B * T, de, dtype=torch.float32, device=dev)
     dY = torch.empty(B * T, C, dtype=torch.float32, device=dev)
-    pack = torch.empty(nr * de + nr + 3 * C, dtype=torch.float32, device=dev)  # one buffer: the data-parallel all-reduce takes it whole
+    pack = dp_pack(nr * de + nr + 3 * C, dev)  # one buffer: the data-parallel all-reduce takes it whole
     dWr, small = pack[:nr * de].view(nr, de), pack[nr * de:]
     need = _lib.load().immtsf_xattn_rank_fused_bwd_workspace_bytes(B, H, C, de)
     ws = _workspace(dev, need + 256)

@@ -62,6 +62,19 @@ SEEDS = SeedSource()
 
 
 _CAPTURE = {}
+_NVLS = {}
+
+
+def nvls_comm(group):
+    """The symmetric-memory arena + in-switch all-reduce of a process group (immtsf/nvls.py), created once; None when the
+    fabric has no multicast (NCCL then carries the statistics)."""
+    from . import nvls
+
+    key = getattr(group, "group_name", id(group))
+    if key not in _NVLS:
+        _NVLS[key] = nvls.NvlsComm.create(group)
+    return _NVLS[key]
+
 
 
 def capture_stream(dev) -> "torch.cuda.Stream":
@@ -141,6 +154,7 @@ class GraphedStep:
         side = capture_stream(dev)
         side.wait_stream(torch.cuda.current_stream())
         ops.DP_GROUP = self.group if self.n_first > 0 else None
+        ops.DP_NVLS = nvls_comm(self.group) if ops.DP_GROUP is not None else None
         with torch.cuda.stream(side):  # lazy allocations (workspaces, side streams) happen here, outside the graph's pool
             for _ in range(max(warmup, 1)):
                 self._eager()
@@ -166,7 +180,7 @@ class GraphedStep:
         try:
             # NCCL's watchdog thread may touch CUDA while we capture: thread-local capture mode tolerates that
             mode = dict(capture_error_mode="thread_local") if self.group is not None else {}
-            ops.DP_STATS["floats"] = ops.DP_STATS["calls"] = 0
+            ops.DP_STATS["floats"] = ops.DP_STATS["calls"] = ops.DP_STATS["nvls"] = 0
             with torch.cuda.graph(self.graph, stream=side, **mode):
                 _lib.call("immtsf_seed_advance", self.seed_offset.data_ptr(), 1, ops._stream())
                 if self.flat_grads is not None:
@@ -176,8 +190,10 @@ class GraphedStep:
                     self._reduce_rest()
         finally:
             ops.DP_GROUP = None
+            self.nvls, ops.DP_NVLS = ops.DP_NVLS, None
         # what one replay sends through the all-reduces captured inside the Functions (floats, collectives)
         self.dp_floats_per_step, self.dp_calls_per_step = ops.DP_STATS["floats"], ops.DP_STATS["calls"]
+        self.dp_nvls_calls_per_step = ops.DP_STATS.get("nvls", 0)
         self.Y_out, self.loss = out.detach(), loss.detach()
         self.flags = getattr(fusion, "_last_flags", None)
 
@@ -251,6 +267,11 @@ class GraphedStep:
                     s.copy_(t, non_blocking=True)
         self.graph.replay()
         return self.loss
+
+    def check_comm(self):
+        """Raise if a rank never arrived at a barrier of the in-switch all-reduce (one device->host read)."""
+        if getattr(self, "nvls", None) is not None:
+            self.nvls.check()
 
     def check_nan(self):
         """The reference's ValueErrors (fusions/FusionModel.py:103-112) for the last replay; one device->host read."""

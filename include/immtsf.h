@@ -370,6 +370,16 @@ int immtsf_batch_gather(const float* emb_all, int ld, int d_m, const int32_t* ch
                         const float* chunk_tau, const int32_t* chunk_ids, const int32_t* offsets, int B, int N_max,
                         float* emb_flat, int ld_out, float* tau_flat, void* stream);
 
+/* ---- data-parallel all-reduce of the gradient statistics, in the NVSwitch (csrc/nvls.cu).  The reference has no
+ * distributed code; this is the one collective of the path (8e).  mc_base = multicast address of a symmetric
+ * arena, peer_bases_dev = DEVICE array of world pointers (this process's mapping of every rank's replica); the range
+ * [off_floats, off_floats + n_floats) is summed over the ranks in place on every rank (multimem.ld_reduce / multimem.st of
+ * this rank's slice between two rank barriers).  The first immtsf_nvls_flag_bytes(world) bytes at flag_off_floats of every
+ * replica are barrier flags, zero before the first call.  err_flag_dev is set to 1 if a rank never arrives (bounded spin). */
+size_t immtsf_nvls_flag_bytes(int world);
+int immtsf_nvls_allreduce_f32(void* mc_base, void* const* peer_bases_dev, size_t off_floats, size_t n_floats,
+                              size_t flag_off_floats, int rank, int world, int* err_flag_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -56,7 +56,7 @@ def test_binding_signatures_match_header():
                 assert ct.__name__ == C2CT[base], (name, carg, ct.__name__)
     assert set(decls) - set(_lib.SIGNATURES) == {"immtsf_last_error_string", "immtsf_launch_count", "immtsf_gemm_workspace_bytes",
                                                    "immtsf_gemm_batched_workspace_bytes", "immtsf_masked_mse_workspace_bytes",
-                                                   "immtsf_t2vq_bwd_workspace_bytes", "immtsf_xattn_rank_fused_bwd_workspace_bytes"}
+                                                   "immtsf_t2vq_bwd_workspace_bytes", "immtsf_xattn_rank_fused_bwd_workspace_bytes", "immtsf_nvls_flag_bytes"}
 
 
 def test_library_contains_sm100a_code_only():

@@ -34,10 +34,11 @@ def main():
         assert step.group is not None and (step.n_first > 0) == (mmf == "MMF_XAttn_Add"), step.n_first
         if rank == 0:
             print(f"{ttf}+{mmf}: {step.n_first} of {step.n_total} gradient floats born reduced; {step.dp_calls_per_step} collectives, "
-                  f"{step.dp_floats_per_step} floats per step", flush=True)
+                  f"{step.dp_floats_per_step} floats per step, {step.dp_nvls_calls_per_step} in-switch", flush=True)
         try:
             for _ in range(2):  # replays re-zero the flat bucket and reduce again
                 step(*mine)
+            step.check_comm()
             got = {k: p.grad.clone() for k, p in fm.named_parameters()}
             # reference: the same modules, eager, over the WHOLE batch in this process
             ref = G.gpu_run(fm, notes, tau, t_hat, Y, Gw, train=True)
