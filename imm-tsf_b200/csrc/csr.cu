@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(256) csr_gather_kernel(const float* __restrict
                                                          const int32_t* __restrict__ offsets, int B, int N, int d_m,
                                                          int32_t* __restrict__ rows, int32_t* __restrict__ seg,
                                                          float* __restrict__ tau_flat, float* __restrict__ emb_flat,
-                                                         int M_alloc) {
+                                                         int ld_emb, float* __restrict__ emb_lo, int ld_lo, int M_alloc) {
   const int lane = threadIdx.x & 31;
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
   const int total_src = B * N;
@@ -127,18 +127,32 @@ __global__ void __launch_bounds__(256) csr_gather_kernel(const float* __restrict
       }
       const int p = offsets[b] + before;
       if (lane == 0) { rows[p] = i; seg[p] = b; tau_flat[p] = tau[i]; }
-      dst = emb_flat + (size_t)p * d_m;
+      dst = emb_flat + (size_t)p * ld_emb;
       src = notes + (size_t)i * d_m;
     } else {
-      dst = emb_flat + (size_t)(total + (i - total_src)) * d_m;
+      dst = emb_flat + (size_t)(total + (i - total_src)) * ld_emb;
     }
     if (emb_flat == nullptr) continue;
-    if ((d_m & 3) == 0 && ((uintptr_t)dst & 15) == 0 && (src == nullptr || ((uintptr_t)src & 15) == 0)) {
+    // optional second output: the row's tcgen05 lo operand x - trunc_tf32(x) (the consumer's 3xTF32 product needs it)
+    float* dlo = emb_lo != nullptr ? emb_lo + (size_t)(dst - emb_flat) / ld_emb * ld_lo : nullptr;
+    if ((d_m & 3) == 0 && ((uintptr_t)dst & 15) == 0 && (src == nullptr || ((uintptr_t)src & 15) == 0) &&
+        (dlo == nullptr || ((uintptr_t)dlo & 15) == 0)) {
       float4* d4 = reinterpret_cast<float4*>(dst);
+      float4* l4 = reinterpret_cast<float4*>(dlo);
       const float4* s4 = reinterpret_cast<const float4*>(src);
-      for (int k = lane; k < (d_m >> 2); k += 32) d4[k] = src ? __ldg(s4 + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int k = lane; k < (d_m >> 2); k += 32) {
+        const float4 v = src ? __ldg(s4 + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+        d4[k] = v;
+        if (dlo != nullptr)
+          l4[k] = make_float4(v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u), v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u),
+                              v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u), v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u));
+      }
     } else {
-      for (int k = lane; k < d_m; k += 32) dst[k] = src ? __ldg(src + k) : 0.f;
+      for (int k = lane; k < d_m; k += 32) {
+        const float v = src ? __ldg(src + k) : 0.f;
+        dst[k] = v;
+        if (dlo != nullptr) dlo[k] = v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+      }
     }
   }
 }
@@ -146,6 +160,14 @@ __global__ void __launch_bounds__(256) csr_gather_kernel(const float* __restrict
 extern "C" int immtsf_csr_build(const float* notes, const float* tau, int B, int N, int d_m, uint8_t* note_mask,
                                 int32_t* offsets, int32_t* rows, int32_t* seg, float* emb_flat, float* tau_flat,
                                 uint8_t* m_txt, int32_t* flags, int M_alloc, void* stream) {
+  return immtsf_csr_build_ex(notes, tau, B, N, d_m, note_mask, offsets, rows, seg, emb_flat, d_m, nullptr, 0, tau_flat, m_txt, flags,
+                             M_alloc, stream);
+}
+
+extern "C" int immtsf_csr_build_ex(const float* notes, const float* tau, int B, int N, int d_m, uint8_t* note_mask,
+                                   int32_t* offsets, int32_t* rows, int32_t* seg, float* emb_flat, int ld_emb, float* emb_lo,
+                                   int ld_lo, float* tau_flat, uint8_t* m_txt, int32_t* flags, int M_alloc, void* stream) {
+  IMMTSF_REQUIRE(ld_emb >= d_m && (emb_lo == nullptr || ld_lo >= d_m), "csr_build: leading dimension smaller than d_model");
   IMMTSF_REQUIRE(B >= 0 && N >= 0 && d_m >= 0, "csr_build: negative size");
   IMMTSF_REQUIRE(offsets && m_txt && flags, "csr_build: null output");
   IMMTSF_REQUIRE(M_alloc >= B * N, "csr_build: M_alloc (%d) < B*N (%d)", M_alloc, B * N);
@@ -164,7 +186,7 @@ extern "C" int immtsf_csr_build(const float* notes, const float* tau, int B, int
     int grid = ceil_div(total_rows + 128, 8);
     if (grid > 148 * 16) grid = 148 * 16;
     csr_gather_kernel<<<grid, 256, 0, st>>>(notes, tau, note_mask, offsets, B, N, d_m, rows, seg, tau_flat,
-                                            d_m > 0 ? emb_flat : nullptr, M_alloc);
+                                            d_m > 0 ? emb_flat : nullptr, ld_emb, d_m > 0 ? emb_lo : nullptr, ld_lo, M_alloc);
     IMMTSF_CHECK_LAUNCH("csr_gather");
   }
   return IMMTSF_OK;

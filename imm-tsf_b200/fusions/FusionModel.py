@@ -63,7 +63,8 @@ class FusionModel(nn.Module):
                 raise ValueError("Y_out contains NaN values.")
             return Y_out
         flags = runtime.new_flags(Y_ts.device)
-        r = ops.csr_build(cm.as_f32(notes_input), cm.as_f32(tau), flags)
+        pad = self.ttf.csr_pad_cols() if hasattr(self.ttf, "csr_pad_cols") else 0
+        r = ops.csr_build(cm.as_f32(notes_input), cm.as_f32(tau), flags, pad_cols=pad)
         return self.forward_csr(r, t_hat, Y_ts)
 
     def _schedule(self, T):

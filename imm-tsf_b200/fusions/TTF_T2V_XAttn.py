@@ -74,6 +74,12 @@ class TTF_T2V_XAttn(nn.Module):
         """One head in train mode with attention dropout: the collapsed schedule (functional.T2VXAttnFoldFn)."""
         return thr != 0 and self.n_heads == 1 and os.environ.get("IMMTSF_T2V_COLLAPSE", "1") != "0"
 
+    def csr_pad_cols(self) -> int:
+        """Extra columns the pad -> CSR gather should leave to the right of the compacted notes: the collapsed schedule appends the
+        Time2Vec features there and multiplies the whole buffer (ops.csr_build(pad_cols=...))."""
+        thr = ops.drop_thr(self.dropout.p) if self.training else 0
+        return self.d_tau if self._collapsed(thr) else 0
+
     def dp_prereduced_params(self):
         """The collapsed schedule all-reduces the sufficient statistics of every gradient of this module itself."""
         thr = ops.drop_thr(self.dropout.p) if self.training else 0
@@ -97,7 +103,7 @@ class TTF_T2V_XAttn(nn.Module):
 
     def forward(self, notes_input, tau: torch.Tensor, t_hat: torch.Tensor):
         cm.require_cuda(notes_input, "TTF_T2V_XAttn")
-        r = ops.csr_build(cm.as_f32(notes_input), cm.as_f32(tau))
+        r = ops.csr_build(cm.as_f32(notes_input), cm.as_f32(tau), pad_cols=self.csr_pad_cols())
         out = self.forward_ragged(r, t_hat)
         runtime.raise_on_flags(r.flags, (ops.FLAG_V,))
         return out

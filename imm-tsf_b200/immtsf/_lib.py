@@ -31,6 +31,7 @@ SIGNATURES = {
     "immtsf_profile_end": [P, P, P, P, P, I],
     "immtsf_gemm_trace": [P],
     "immtsf_csr_build": [P, P, I, I, I, P, P, P, P, P, P, P, P, I, P],
+    "immtsf_csr_build_ex": [P, P, I, I, I, P, P, P, P, P, I, P, I, P, P, P, I, P],
     "immtsf_nan_check": [P, SZ, P, I, P],
     "immtsf_zero_pad_rows": [P, I, I, P, I, P],
     "immtsf_gemm": [I, I, I, I, I, F, P, I, P, I, F, P, I, P, P, I, I, P, SZ, P],

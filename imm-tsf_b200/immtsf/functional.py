@@ -204,7 +204,13 @@ class T2VXAttnFoldFn(torch.autograd.Function):
         lo = step.lo
         W_a, W_phi = W_kv[:, :d], W_kv[:, d:]
         W_q, W_k, W_v = in_w[:d], in_w[d:2 * d], in_w[2 * d:]
-        Ecat, Ecat_lo = new(r.M_alloc, Kx), new(r.M_alloc, ops.round_up(Kx, 4))  # [emb ; phi] and its tcgen05 lo operand
+        # [emb ; phi] and its tcgen05 lo operand: the pad -> CSR gather wrote the notes (and their lo) into the left columns
+        # already when the caller asked for the wide layout (FusionModel does); otherwise they are copied in here
+        prefilled = r.emb_wide is not None and r.emb_wide.shape[1] == Kx
+        if prefilled:
+            Ecat, Ecat_lo = r.emb_wide, r.emb_wide_lo
+        else:
+            Ecat, Ecat_lo = new(r.M_alloc, Kx), new(r.M_alloc, ops.round_up(Kx, 4))
         KVp = new(r.M_alloc, 2 * d)  # [X | V']
         Wvf, Wvf_lo, bvf = new(d, d), new(d, d), new(d)
         if has_in:
@@ -213,40 +219,49 @@ class T2VXAttnFoldFn(torch.autograd.Function):
             Wx, bX = W_kv, b_kv
         scale = math.sqrt(1.0 / float(d))
         box = {}
-        fkw = ops.Fork(dev, name="t2v_fwd")
+        # parameter-only work on three lanes beside the data chain; the data chain waits for the operand it needs next
+        fkw = ops.Fork(dev, lanes=3, name="t2v_fwd")
 
-        def weights():
-            ws = [(out_w, []), (in_w, [slice(2 * d, None)])] + ([] if defer else [(W_po, [])])
-            extra = []
+        def weights_x():  # lane 0: the operand of the first product
             if has_in:
-                ws += [(W_in, []), (W_kv, [(slice(None), slice(0, d))])]
-                extra.append((W_phi, Wx[:, dm:], Wx_lo[:, dm:]))
-            else:
-                ws.append((W_kv, [(slice(None), slice(d, None))]))
-            ops.weight_los(lo, ws, extra)
-            if has_in:
+                ops.weight_los(lo, [(W_in, []), (W_kv, [(slice(None), slice(0, d))])], [(W_phi, Wx[:, dm:], Wx_lo[:, dm:])])
                 ops.gemm(W_a, W_in, Wx[:, :dm], lo=lo, emit_lo=Wx_lo[:, :dm])  # W_a W_in
-                ops.gemm(b_in.view(1, d), W_a, bX.view(1, d), transB=True, bias=b_kv)  # W_a b_in + b_kv
                 lo.put(Wx, Wx_lo)
                 lo.put(Wx[:, dm:], Wx_lo[:, dm:])
-            box["ev_x"] = fkw.mark()
+            else:
+                ops.weight_los(lo, [(W_kv, [(slice(None), slice(d, None))])])
+            box["ev_x"] = fkw.mark(0)
+
+        def weights_v():  # lane 1: the operand of the second product
+            ops.weight_los(lo, [(out_w, []), (in_w, [slice(2 * d, None)])] + ([] if defer else [(W_po, [])]))
             ops.gemm(out_w, W_v, Wvf, lo=lo, emit_lo=Wvf_lo)  # W_o W_v
             ops.gemm(in_b[2 * d:].view(1, d), out_w, bvf.view(1, d), transB=True)  # W_o b_v
+            box["ev_v"] = fkw.mark(1)
+
+        def vectors():  # lane 2: biases and the query side
+            if has_in:
+                ops.gemm(b_in.view(1, d), W_a, bX.view(1, d), transB=True, bias=b_kv)  # W_a b_in + b_kv
+            box["ev_bx"] = fkw.mark(2)
             q0 = ops.linear_fwd(Qp.view(1, d), W_q, in_b[:d])
             q = ops.axpby(q0, scale, torch.empty_like(q0), False)
             box["q"], box["u"] = q, ops.gemm(q, W_k, new(1, d))  # u = W_k^T q
-            box["ev_v"] = fkw.mark()
+            box["ev_q"] = fkw.mark(2)
 
-        fkw.run(weights)
-        # data chain: [emb ; phi] (the copy of the notes rides with its lo split), X, V'
-        ops.multi_split([(r.emb_flat, Ecat[:, :dm], Ecat_lo[:, :dm])])
+        fkw.run(weights_x, lane=0)
+        fkw.run(weights_v, lane=1)
+        fkw.run(vectors, lane=2)
+        # data chain: [emb ; phi], X, V'
+        if not prefilled:
+            ops.multi_split([(r.emb_flat, Ecat[:, :dm], Ecat_lo[:, :dm])])
         ops.time2vec_fwd(r, w_lin, b_lin, w_per, b_per, dt, Ecat[:, dm:], Ecat_lo[:, dm:])
         lo.put(Ecat, Ecat_lo)
-        fkw.wait(box["ev_x"], Wx, bX)
-        X = ops.gemm(Ecat, Wx, KVp[:, :d], transB=True, bias=bX, ragged=r.m_dev, ragged_dim=1, lo=lo, emit_lo=True)
         u = box["u"]
-        fkw.wait(box["ev_v"], Wvf, Wvf_lo, bvf, u, box["q"])
+        fkw.wait(box["ev_x"], Wx)
+        fkw.wait(box["ev_bx"], bX)
+        X = ops.gemm(Ecat, Wx, KVp[:, :d], transB=True, bias=bX, ragged=r.m_dev, ragged_dim=1, lo=lo, emit_lo=True)
+        fkw.wait(box["ev_v"], Wvf, Wvf_lo, bvf)
         ops.gemm(X, Wvf, KVp[:, d:], transB=True, bias=bvf, ragged=r.m_dev, ragged_dim=1, lo=lo)
+        fkw.wait(box["ev_q"], u, box["q"])
         fkw.join()
         attn_cat, probs = ops.segattn_fwd(u, KVp, r, T, 1, d, True, thr, seed, save)
         y, mean, rstd = ops.ln_fwd(attn_cat, Qp.view(d), r.m_txt, T, gamma, beta, thr, seed, ops.SITE_TTF_DROPOUT, save, xbias=out_b)
@@ -694,27 +709,44 @@ class XAttnRankWeightsFn(torch.autograd.Function):
         dev = W_Q.device
         new = lambda *s: torch.empty(*s, dtype=_f32, device=dev)
         in_k, in_v, b_k, b_v = in_w[d:2 * d], in_w[2 * d:], in_b[d:2 * d], in_b[2 * d:]
-        Wq_aug = new(d, C1)
-        ops.multi_split([(in_b[:d].view(d, 1), Wq_aug[:, C:], None)])
-        ops.gemm(in_w[:d], W_Q, Wq_aug[:, :C])
-        Wo_f = ops.gemm(W_r, out_w, new(C, d))
-        bo_f = ops.gemm(out_b.view(1, d), W_r, new(1, C), transB=True, bias=b_r).view(C)
+        # Two independent chains of skinny products -- the key side (Wq_aug -> P1 -> A -> A W_p) and the value side (Wo_f -> P2 ->
+        # G -> G W_p) -- on two lanes: depth 4 instead of one serial chain of ~16 launches (170 us on the cfg2 timeline).
+        Wq_aug, Wo_f, bo_f = new(d, C1), new(C, d), new(C)
         Wr, br = new(nr, de), new(nr)
         P1, P2 = new(H, C1, d), new(H, C, d)
-        for h in range(H):
-            hs, ra, rg = slice(h * hd, (h + 1) * hd), slice(h * C1, (h + 1) * C1), slice(n1 + h * C, n1 + (h + 1) * C)
-            ops.gemm(Wq_aug[hs], in_k[hs], P1[h], transA=True)  # Wq_aug_h^T in_k_h            [C1, d]
-            ops.gemm(P1[h], W_K, Wr[ra])  # A_h                                                  [C1, de]
-            ops.gemm(b_k[hs].view(1, hd), Wq_aug[hs], br[ra].view(1, C1))  # a0_h^T = b_k_h^T Wq_aug_h
-            ops.gemm(Wo_f[:, hs], in_v[hs], P2[h])  # Wo_f_h in_v_h                              [C, d]
-            ops.gemm(P2[h], W_V, Wr[rg])  # G_h                                                  [C, de]
-            ops.gemm(Wo_f[:, hs], b_v[hs].view(hd, 1), br[rg].view(C, 1))  # g0_h
-        if W_p is not None:  # fold the producer's last projection: Wr_eff = Wr W_p, br_eff = Wr b_p + br
-            Wr_eff = ops.gemm(Wr, W_p, new(nr, W_p.shape[1]))
-            br_eff = ops.gemm(Wr, b_p.view(de, 1), new(nr, 1)).view(nr)  # one warp per row of Wr
-            ops.axpby(br, 1.0, br_eff, True)
-        else:
-            Wr_eff, br_eff = Wr, br
+        fold = W_p is not None
+        Wr_eff, br_eff = (new(nr, W_p.shape[1]), new(nr)) if fold else (Wr, br)
+        fk = ops.Fork(dev, lanes=2, name="rankw_fwd")
+
+        def fold_rows(rs):  # Wr_eff = Wr W_p, br_eff = Wr b_p + br, for a block of rows
+            if fold:
+                ops.gemm(Wr[rs], W_p, Wr_eff[rs])
+                ops.gemm(Wr[rs], b_p.view(de, 1), br_eff[rs].view(-1, 1))  # one warp per row of Wr
+                ops.axpby(br[rs], 1.0, br_eff[rs], True)
+
+        def key_side():
+            ops.multi_split([(in_b[:d].view(d, 1), Wq_aug[:, C:], None)])
+            ops.gemm(in_w[:d], W_Q, Wq_aug[:, :C])
+            for h in range(H):
+                hs, ra = slice(h * hd, (h + 1) * hd), slice(h * C1, (h + 1) * C1)
+                ops.gemm(Wq_aug[hs], in_k[hs], P1[h], transA=True)  # Wq_aug_h^T in_k_h            [C1, d]
+                ops.gemm(P1[h], W_K, Wr[ra])  # A_h                                                  [C1, de]
+                ops.gemm(b_k[hs].view(1, hd), Wq_aug[hs], br[ra].view(1, C1))  # a0_h^T = b_k_h^T Wq_aug_h
+            fold_rows(slice(0, n1))
+
+        def value_side():
+            ops.gemm(W_r, out_w, Wo_f)
+            ops.gemm(out_b.view(1, d), W_r, bo_f.view(1, C), transB=True, bias=b_r)
+            for h in range(H):
+                hs, rg = slice(h * hd, (h + 1) * hd), slice(n1 + h * C, n1 + (h + 1) * C)
+                ops.gemm(Wo_f[:, hs], in_v[hs], P2[h])  # Wo_f_h in_v_h                              [C, d]
+                ops.gemm(P2[h], W_V, Wr[rg])  # G_h                                                  [C, de]
+                ops.gemm(Wo_f[:, hs], b_v[hs].view(hd, 1), br[rg].view(C, 1))  # g0_h
+            fold_rows(slice(n1, nr))
+
+        fk.run(key_side, lane=0)
+        fk.run(value_side, lane=1)
+        fk.join(Wq_aug, Wo_f, bo_f, Wr, br, P1, P2, Wr_eff, br_eff)
         ctx.H, ctx.C, ctx.dims, ctx.ln = H, C, (d, de), gamma is not None
         ctx.save_for_backward(W_Q, W_K, W_V, in_w, in_b, out_w, out_b, W_r, Wq_aug, Wo_f, P1, P2, Wr, W_p, b_p)
         if gamma is not None:
@@ -750,45 +782,63 @@ class XAttnRankWeightsFn(torch.autograd.Function):
                 dWr_eff, dbr, dbo_f = outs[:3]
                 if dgamma is not None:
                     dgamma, dbeta = outs[3:]
+        # the chain rule of the two forward chains, again on two lanes (key side / value side); a third lane takes the gradient of
+        # the folded projection, which needs nothing from the chains
         dW_p = db_p = None
-        if W_p is None:
-            dWr = dWr_eff
-        else:  # un-fold Wr_eff = Wr W_p, br_eff = Wr b_p + br
-            dk = W_p.shape[1]
-            dWr = ops.gemm(dWr_eff, W_p, new(nr, de), transB=True)
-            ops.gemm(dbr.view(nr, 1), b_p.view(1, de), dWr, beta=1.0)
-            dW_p = ops.gemm(Wr, dWr_eff, new(de, dk), transA=True)
-            db_p = ops.gemm(Wr, dbr.view(nr, 1), new(de, 1), transA=True).view(de)
+        fold = W_p is not None
+        dWr = new(nr, de) if fold else dWr_eff
         d_in_w, d_in_b = torch.empty_like(in_w), new(3 * d)
         d_in_k, d_in_v, db_k, db_v = d_in_w[d:2 * d], d_in_w[2 * d:], d_in_b[d:2 * d], d_in_b[2 * d:]
         dWq_aug, dWo_f, dW_K, dW_V = new(d, C1), new(C, d), new(d, de), new(d, de)
-        for h in range(H):
-            hs, ra, rg = slice(h * hd, (h + 1) * hd), slice(h * C1, (h + 1) * C1), slice(n1 + h * C, n1 + (h + 1) * C)
-            acc = 1.0 if h > 0 else 0.0
-            # G_h = P2_h W_V ; P2_h = Wo_f_h in_v_h ; g0_h = Wo_f_h b_v_h
-            dP2 = ops.gemm(dWr[rg], W_V, new(C, d), transB=True)
-            ops.gemm(P2[h], dWr[rg], dW_V, transA=True, beta=acc)
-            ops.gemm(dP2, in_v[hs], dWo_f[:, hs], transB=True)
-            ops.gemm(Wo_f[:, hs], dP2, d_in_v[hs], transA=True)
-            ops.gemm(dbr[rg].view(C, 1), b_v[hs].view(1, hd), dWo_f[:, hs], beta=1.0)
-            ops.gemm(Wo_f[:, hs], dbr[rg].view(C, 1), db_v[hs].view(hd, 1), transA=True)
-            # A_h = P1_h W_K ; P1_h = Wq_aug_h^T in_k_h ; a0_h = Wq_aug_h^T b_k_h
-            dP1 = ops.gemm(dWr[ra], W_K, new(C1, d), transB=True)
-            ops.gemm(P1[h], dWr[ra], dW_K, transA=True, beta=acc)
-            ops.gemm(in_k[hs], dP1, dWq_aug[hs], transB=True)
-            ops.gemm(Wq_aug[hs], dP1, d_in_k[hs])
-            ops.gemm(b_k[hs].view(hd, 1), dbr[ra].view(1, C1), dWq_aug[hs], beta=1.0)
-            ops.gemm(Wq_aug[hs], dbr[ra].view(C1, 1), db_k[hs].view(hd, 1))
-        # Wo_f = W_r W_o ; bo_f = W_r b_o + b_r
-        dW_r = ops.gemm(dWo_f, out_w, new(C, d), transB=True)
-        ops.gemm(dbo_f.view(C, 1), out_b.view(1, d), dW_r, beta=1.0)
-        dW_o = ops.gemm(W_r, dWo_f, new(d, d), transA=True)
-        db_o = ops.gemm(dbo_f.view(1, C), W_r, new(1, d)).view(d)
-        # Wq_aug = [in_q W_Q | b_q]
-        dWq_f = dWq_aug[:, :C]
-        ops.gemm(dWq_f, W_Q, d_in_w[:d], transB=True)
-        dW_Q = ops.gemm(in_w[:d], dWq_f, new(d, C), transA=True)
-        ops.multi_split([(dWq_aug[:, C:], d_in_b[:d].view(d, 1), None)])
+        dW_Q, dW_r, dW_o, db_o = new(d, C), new(C, d), new(d, d), new(d)
+        if fold:
+            dW_p, db_p = new(de, W_p.shape[1]), new(de)
+        fk = ops.Fork(dev, lanes=3, name="rankw_bwd")
+
+        def unfold_rows(rs):  # Wr_eff = Wr W_p, br_eff = Wr b_p + br
+            if fold:
+                ops.gemm(dWr_eff[rs], W_p, dWr[rs], transB=True)
+                ops.gemm(dbr[rs].view(-1, 1), b_p.view(1, de), dWr[rs], beta=1.0)
+
+        def key_side():  # A_h = P1_h W_K ; P1_h = Wq_aug_h^T in_k_h ; a0_h = Wq_aug_h^T b_k_h ; Wq_aug = [in_q W_Q | b_q]
+            unfold_rows(slice(0, n1))
+            for h in range(H):
+                hs, ra = slice(h * hd, (h + 1) * hd), slice(h * C1, (h + 1) * C1)
+                dP1 = ops.gemm(dWr[ra], W_K, new(C1, d), transB=True)
+                ops.gemm(in_k[hs], dP1, dWq_aug[hs], transB=True)
+                ops.gemm(b_k[hs].view(hd, 1), dbr[ra].view(1, C1), dWq_aug[hs], beta=1.0)
+                ops.gemm(P1[h], dWr[ra], dW_K, transA=True, beta=1.0 if h > 0 else 0.0)
+                ops.gemm(Wq_aug[hs], dP1, d_in_k[hs])
+                ops.gemm(Wq_aug[hs], dbr[ra].view(C1, 1), db_k[hs].view(hd, 1))
+            dWq_f = dWq_aug[:, :C]
+            ops.gemm(dWq_f, W_Q, d_in_w[:d], transB=True)
+            ops.gemm(in_w[:d], dWq_f, dW_Q, transA=True)
+            ops.multi_split([(dWq_aug[:, C:], d_in_b[:d].view(d, 1), None)])
+
+        def value_side():  # G_h = P2_h W_V ; P2_h = Wo_f_h in_v_h ; g0_h = Wo_f_h b_v_h ; Wo_f = W_r W_o ; bo_f = W_r b_o + b_r
+            unfold_rows(slice(n1, nr))
+            for h in range(H):
+                hs, rg = slice(h * hd, (h + 1) * hd), slice(n1 + h * C, n1 + (h + 1) * C)
+                dP2 = ops.gemm(dWr[rg], W_V, new(C, d), transB=True)
+                ops.gemm(dP2, in_v[hs], dWo_f[:, hs], transB=True)
+                ops.gemm(dbr[rg].view(C, 1), b_v[hs].view(1, hd), dWo_f[:, hs], beta=1.0)
+                ops.gemm(P2[h], dWr[rg], dW_V, transA=True, beta=1.0 if h > 0 else 0.0)
+                ops.gemm(Wo_f[:, hs], dP2, d_in_v[hs], transA=True)
+                ops.gemm(Wo_f[:, hs], dbr[rg].view(C, 1), db_v[hs].view(hd, 1), transA=True)
+            ops.gemm(dWo_f, out_w, dW_r, transB=True)
+            ops.gemm(dbo_f.view(C, 1), out_b.view(1, d), dW_r, beta=1.0)
+            ops.gemm(W_r, dWo_f, dW_o, transA=True)
+            ops.gemm(dbo_f.view(1, C), W_r, db_o.view(1, d))
+
+        def folded_projection():
+            ops.gemm(Wr, dWr_eff, dW_p, transA=True)
+            ops.gemm(Wr, dbr.view(nr, 1), db_p.view(de, 1), transA=True)
+
+        fk.run(key_side, lane=0)
+        fk.run(value_side, lane=1)
+        if fold:
+            fk.run(folded_projection, lane=2)
+        fk.join(d_in_w, d_in_b, dW_Q, dW_K, dW_V, dW_r, dW_o, db_o, dW_p, db_p)
         return None, None, dW_Q, dW_K, dW_V, d_in_w, d_in_b, dW_o, db_o, dW_r, dbo_f, dW_p, db_p, dgamma, dbeta
 
 

@@ -69,17 +69,22 @@ class RaggedNotes:
     offsets: torch.Tensor  # [B+1] i32
     rows: torch.Tensor  # [B*N] i32
     seg: torch.Tensor  # [B*N] i32
-    emb_flat: torch.Tensor  # [M_alloc, d_m]
+    emb_flat: torch.Tensor  # [M_alloc, d_m] (a view of emb_wide's left columns when the consumer asked for a wider buffer)
     tau_flat: torch.Tensor  # [M_alloc]
     m_txt: torch.Tensor  # [B] u8
     flags: torch.Tensor  # [4] i32
+    emb_wide: Optional[torch.Tensor] = None  # [M_alloc, d_m + pad_cols]: compacted rows + room for the consumer's extra columns
+    emb_wide_lo: Optional[torch.Tensor] = None  # its tcgen05 lo operand (the left d_m columns are written by the gather)
 
     @property
     def m_dev(self) -> torch.Tensor:
         return self.offsets[self.B:]
 
 
-def csr_build(notes: torch.Tensor, tau: torch.Tensor, flags: Optional[torch.Tensor] = None) -> RaggedNotes:
+def csr_build(notes: torch.Tensor, tau: torch.Tensor, flags: Optional[torch.Tensor] = None, pad_cols: int = 0) -> RaggedNotes:
+    """pad_cols > 0: the compacted rows are written into the left columns of a [M_alloc, d_m + pad_cols] buffer (emb_wide) together
+    with their tcgen05 lo operand -- the collapsed T2V schedule appends the Time2Vec features there and uses the buffer as the
+    operand of its first product, so the notes are neither copied nor split again."""
     _chk(notes, "notes"), _chk(tau, "tau")
     if notes.dim() != 3 or tau.dim() != 2 or tau.shape[0] != notes.shape[0] or tau.shape[1] != notes.shape[1]:
         raise ValueError(f"notes must be [B,N,d_model] and tau [B,N]; got {tuple(notes.shape)} and {tuple(tau.shape)}")
@@ -88,16 +93,24 @@ def csr_build(notes: torch.Tensor, tau: torch.Tensor, flags: Optional[torch.Tens
     dev = notes.device
     M_alloc = max(round_up(B * N, 128), 128)
     i32, u8 = torch.int32, torch.uint8
+    wide = wide_lo = None
+    if pad_cols > 0 and d_m > 0 and d_m % 4 == 0:
+        wide = torch.empty(M_alloc, d_m + pad_cols, dtype=torch.float32, device=dev)
+        wide_lo = torch.empty(M_alloc, round_up(d_m + pad_cols, 4), dtype=torch.float32, device=dev)
+        emb = wide[:, :d_m]
+    else:
+        emb = torch.empty(M_alloc, max(d_m, 1), dtype=torch.float32, device=dev)
     r = RaggedNotes(
         B, N, d_m, M_alloc,
         torch.empty(max(B * N, 1), dtype=u8, device=dev), torch.empty(B + 1, dtype=i32, device=dev),
         torch.empty(max(B * N, 1), dtype=i32, device=dev), torch.empty(max(B * N, 1), dtype=i32, device=dev),
-        torch.empty(M_alloc, max(d_m, 1), dtype=torch.float32, device=dev),
+        emb,
         torch.empty(M_alloc, dtype=torch.float32, device=dev), torch.empty(max(B, 1), dtype=u8, device=dev),
-        flags if flags is not None else torch.zeros(4, dtype=i32, device=dev),
+        flags if flags is not None else torch.zeros(4, dtype=i32, device=dev), wide, wide_lo,
     )
-    _lib.call("immtsf_csr_build", _p(notes), _p(tau), B, N, d_m, _p(r.note_mask), _p(r.offsets), _p(r.rows), _p(r.seg),
-              _p(r.emb_flat), _p(r.tau_flat), _p(r.m_txt), _p(r.flags), M_alloc, _stream())
+    _lib.call("immtsf_csr_build_ex", _p(notes), _p(tau), B, N, d_m, _p(r.note_mask), _p(r.offsets), _p(r.rows), _p(r.seg),
+              _p(r.emb_flat), r.emb_flat.stride(0), _p(wide_lo), wide_lo.stride(0) if wide_lo is not None else 0, _p(r.tau_flat),
+              _p(r.m_txt), _p(r.flags), M_alloc, _stream())
     return r
 
 

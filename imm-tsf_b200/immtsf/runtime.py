@@ -82,7 +82,10 @@ def capture_stream(dev) -> "torch.cuda.Stream":
     key = dev.index if dev.index is not None else torch.cuda.current_device()
     st = _CAPTURE.get(key)
     if st is None:
-        st = _CAPTURE[key] = torch.cuda.Stream(device=dev)
+        # HIGH priority: the captured kernel nodes inherit it, so the data chain of the step (which runs on this stream) gets SM
+        # slots before the weight-space work on the side lanes (default priority) whenever both have blocks pending -- on the
+        # cfg2 timeline a one-block kernel of the data chain waited 16 us behind a lane's 300-CTA skinny product
+        st = _CAPTURE[key] = torch.cuda.Stream(device=dev, priority=int(os.environ.get("IMMTSF_CAPTURE_PRIORITY", "-1")))
     return st
 
 

@@ -74,6 +74,12 @@ int immtsf_csr_build(const float* notes, const float* tau, int B, int N, int d_m
                      uint8_t* note_mask, int32_t* offsets, int32_t* rows, int32_t* seg,
                      float* emb_flat, float* tau_flat, uint8_t* m_txt, int32_t* flags,
                      int M_alloc, void* stream);
+/* same, with the compacted rows written at a leading dimension ld_emb >= d_model (the rows then sit in the left columns of a
+ * wider buffer, e.g. the [emb ; phi] operand of the collapsed T2V schedule) and, when emb_lo != NULL, their tcgen05 lo
+ * operand x - trunc_tf32(x) written beside them (leading dimension ld_lo). */
+int immtsf_csr_build_ex(const float* notes, const float* tau, int B, int N, int d_m, uint8_t* note_mask,
+                        int32_t* offsets, int32_t* rows, int32_t* seg, float* emb_flat, int ld_emb, float* emb_lo,
+                        int ld_lo, float* tau_flat, uint8_t* m_txt, int32_t* flags, int M_alloc, void* stream);
 /* flags[slot] = 1 if x[0..n) holds a NaN (FusionModel.py:103,107,111) */
 int immtsf_nan_check(const float* x, size_t n, int32_t* flags, int slot, void* stream);
 /* zero rows [sumN, min(roundup(sumN,128), M_alloc)) of X[M_alloc, ncols] (ld) */
