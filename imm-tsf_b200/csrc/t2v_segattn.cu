@@ -10,6 +10,7 @@
 // per sample (R = B rows); with attention dropout every (t,h,n) weight gets
 // its own Philox keep bit and R = B*T rows.
 #include "tile32.cuh"
+#include "rowwarp.cuh"
 #include "../../include/immtsf.h"
 
 // ------------------------------------------------------------------ Time2Vec
@@ -189,6 +190,188 @@ __global__ void __launch_bounds__(256) segattn_fwd_kernel(const SegArgs a) {
           reinterpret_cast<float4*>(a.attn_cat + ((size_t)b * Teff + t0 + tt) * d)[col4] = acc[tt];
     }
   }
+}
+
+// ------------------------------------------------------------- one head, train mode: attention + residual + LayerNorm + dropout
+// TTF_T2V_XAttn.py:143-179 for ONE head with attention dropout (every (sample, query) row distinct), in one launch:
+// softmax over the sample's notes, dropout on the weights, pooling of the value rows, + out-projection bias + learned query,
+// LayerNorm, dropout.  Round 1 ran this as segattn_fwd (one CTA per sample, four query rows per pass: six passes over the
+// value rows, 30 us at cfg2) followed by ln_fwd (17 us): 256 CTAs on 148 SMs, latency-bound.  Here a CTA owns EIGHT query
+// rows of a sample (grid = T/8 x B = 768 CTAs at cfg2): the scores are recomputed per tile (N_i dot products), the value
+// rows are staged in shared memory once per CTA, and warp w owns query row w -- its pooled row never leaves registers
+// before the LayerNorm statistics (warp shuffles), so the [B*T, d] attention output is written once (saved for backward)
+// and never read back.  Same summation order and lane ownership as the two kernels it replaces: bit-identical results.
+constexpr int SL_TQ = 8;    // query rows per CTA = warps per CTA
+constexpr int SL_NS = 16;   // value rows staged per pass
+
+struct SegLnArgs {
+  const float* q; const float* KVp; const int32_t* offsets;
+  int B, T, d, N_max; uint32_t thr; SeedArg seed; float eps;
+  const float* xbias; const float* res; const float* gamma; const float* beta;
+  float* attn_cat; float* probs; float* y; float* mean; float* rstd;
+};
+
+// smem: s_v [SL_NS][d] | s_p [N_max] | s_pt [SL_TQ][N_max]
+template <int NC>
+__global__ void __launch_bounds__(SL_TQ * 32) segattn_ln_fwd_kernel(const SegLnArgs a) {
+  extern __shared__ __align__(16) float sl_smem[];
+  const int d = a.d, d8 = d >> 3, d4 = d >> 2, NM = a.N_max, ld = 2 * d;
+  float* s_v = sl_smem;
+  float* s_p = s_v + (size_t)SL_NS * d;
+  float* s_pt = s_p + NM;
+  const int b = blockIdx.y, t0 = blockIdx.x * SL_TQ;
+  const int nb = a.offsets[b], nn = a.offsets[b + 1] - nb;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int t = t0 + w;
+  const bool row_ok = t < a.T;
+  const float inv_keep = inv_keep_from_thr(a.thr), inv_d = 1.f / (float)d;
+  const uint64_t seed = resolve_seed(a.seed);
+  float acc[NC][8];
+#pragma unroll
+  for (int i = 0; i < NC; ++i) zero8(acc[i]);
+  if (nn > 0) {
+    // scores and softmax over the segment (recomputed by every tile of the sample; tile 0 saves the probabilities)
+    for (int n = w; n < nn; n += SL_TQ) {
+      const float sc = warp_dot(a.q, a.KVp + (size_t)(nb + n) * ld, d, lane);
+      if (lane == 0) s_p[n] = sc;
+    }
+    __syncthreads();
+    if (w == 0) {
+      float mx = -INFINITY;
+      for (int n = lane; n < nn; n += 32) mx = fmaxf(mx, s_p[n]);
+      mx = warp_max(mx);
+      float sum = 0.f;
+      for (int n = lane; n < nn; n += 32) {
+        const float e = expf(s_p[n] - mx);
+        s_p[n] = e;
+        sum += e;
+      }
+      sum = warp_sum(sum);
+      for (int n = lane; n < nn; n += 32) {
+        const float p = s_p[n] / sum;
+        s_p[n] = p;
+        if (a.probs && blockIdx.x == 0) a.probs[nb + n] = p;
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < SL_TQ * nn; i += blockDim.x) {
+      const int tt = i / nn, n = i % nn;
+      float p = 0.f;
+      if (t0 + tt < a.T)
+        p = s_p[n] * dropout_scale(seed, IMMTSF_SITE_TTF_ATTN, ((uint64_t)b * a.T + t0 + tt) * NM + n, a.thr, inv_keep);
+      s_pt[tt * NM + n] = p;
+    }
+    // pooling: value rows through shared memory, SL_NS at a time; warp w accumulates query row t0 + w
+    for (int n0 = 0; n0 < nn; n0 += SL_NS) {
+      const int cnt = min(SL_NS, nn - n0);
+      __syncthreads();  // (also orders the s_pt writes above before their first use)
+      for (int i = threadIdx.x; i < cnt * d4; i += blockDim.x) {
+        const int r = i / d4, c = i % d4;
+        reinterpret_cast<float4*>(s_v)[(size_t)r * d4 + c] = __ldg(reinterpret_cast<const float4*>(a.KVp + (size_t)(nb + n0 + r) * ld + d) + c);
+      }
+      __syncthreads();
+      if (row_ok) {
+        for (int r = 0; r < cnt; ++r) {
+          const float p = s_pt[w * NM + n0 + r];
+#pragma unroll
+          for (int i = 0; i < NC; ++i) {
+            const int k = lane + 32 * i;
+            if (k < d8) {
+              const float4 v0 = reinterpret_cast<const float4*>(s_v + (size_t)r * d)[2 * k];
+              const float4 v1 = reinterpret_cast<const float4*>(s_v + (size_t)r * d)[2 * k + 1];
+              acc[i][0] = fmaf(p, v0.x, acc[i][0]); acc[i][1] = fmaf(p, v0.y, acc[i][1]);
+              acc[i][2] = fmaf(p, v0.z, acc[i][2]); acc[i][3] = fmaf(p, v0.w, acc[i][3]);
+              acc[i][4] = fmaf(p, v1.x, acc[i][4]); acc[i][5] = fmaf(p, v1.y, acc[i][5]);
+              acc[i][6] = fmaf(p, v1.z, acc[i][6]); acc[i][7] = fmaf(p, v1.w, acc[i][7]);
+            }
+          }
+        }
+      }
+    }
+  }
+  if (!row_ok) return;
+  // the pooled row (saved: LayerNorm backward needs it), then + bias + learned query, LayerNorm, dropout
+  const size_t rowi = (size_t)b * a.T + t;
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NC; ++i) {
+    const int k = lane + 32 * i;
+    if (k < d8) {
+      store8(a.attn_cat + rowi * d, k, acc[i]);
+      if (nn > 0 && a.xbias) { float tb[8]; load8(a.xbias, k, tb);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[i][e] += tb[e]; }
+      if (a.res) { float tr[8]; load8(a.res, k, tr);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[i][e] += tr[e]; }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s += acc[i][e];
+    }
+  }
+  const float mu = warp_sum(s) * inv_d;
+  float qv = 0.f;
+#pragma unroll
+  for (int i = 0; i < NC; ++i)
+    if (lane + 32 * i < d8)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) qv = fmaf(acc[i][e] - mu, acc[i][e] - mu, qv);
+  const float rs = 1.f / sqrtf(warp_sum(qv) * inv_d + a.eps);
+#pragma unroll
+  for (int i = 0; i < NC; ++i) {
+    const int k = lane + 32 * i;
+    if (k < d8) {
+      float g[8], be[8], ks[8], yv[8];
+      load8(a.gamma, k, g);
+      load8(a.beta, k, be);
+      dropout_scale8(seed, IMMTSF_SITE_TTF_DROPOUT, (uint64_t)rowi * d8 + k, a.thr, inv_keep, ks);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) yv[e] = ((acc[i][e] - mu) * rs * g[e] + be[e]) * ks[e];
+      store8(a.y + rowi * d, k, yv);
+    }
+  }
+  if (lane == 0) {
+    if (a.mean) a.mean[rowi] = mu;
+    if (a.rstd) a.rstd[rowi] = rs;
+  }
+}
+
+extern "C" int immtsf_segattn_ln_ok(int d, int N_max) {
+  return rowwarp_nc(d) > 0 && ((size_t)SL_NS * d + (size_t)(SL_TQ + 1) * N_max) * sizeof(float) <= 160 * 1024;
+}
+
+extern "C" int immtsf_segattn_ln_fwd(const float* q, const float* KVp, const int32_t* offsets, int B, int T, int d, int N_max,
+                                     uint32_t drop_thr, uint64_t seed, const float* xbias, const float* res, const float* gamma,
+                                     const float* beta, float eps, float* attn_cat, float* probs, float* y, float* mean,
+                                     float* rstd, void* stream) {
+  if (B == 0 || T == 0) return IMMTSF_OK;
+  IMMTSF_REQUIRE(q && KVp && offsets && gamma && beta && attn_cat && y, "segattn_ln_fwd: null pointer");
+  IMMTSF_REQUIRE(immtsf_segattn_ln_ok(d, N_max) && N_max >= 1, "segattn_ln_fwd: needs d %% 8 == 0, d <= 1024 (d=%d N_max=%d)", d, N_max);
+  IMMTSF_REQUIRE(B <= 65535, "segattn_ln_fwd: B > 65535");
+  for (const void* p : {(const void*)q, (const void*)KVp, (const void*)xbias, (const void*)res, (const void*)gamma, (const void*)beta,
+                        (const void*)attn_cat, (const void*)y})
+    IMMTSF_REQUIRE(((uintptr_t)p & 15) == 0, "segattn_ln_fwd: buffers must be 16B aligned");
+  SegLnArgs a = {};
+  a.q = q; a.KVp = KVp; a.offsets = offsets; a.B = B; a.T = T; a.d = d; a.N_max = N_max; a.thr = drop_thr; a.seed = make_seed(seed);
+  a.eps = eps; a.xbias = xbias; a.res = res; a.gamma = gamma; a.beta = beta; a.attn_cat = attn_cat; a.probs = probs; a.y = y;
+  a.mean = mean; a.rstd = rstd;
+  const size_t smem = ((size_t)SL_NS * d + (size_t)(SL_TQ + 1) * N_max) * sizeof(float);
+  const dim3 grid(ceil_div(T, SL_TQ), B);
+  const int nc = rowwarp_nc(d);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(segattn_ln_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    cudaFuncSetAttribute(segattn_ln_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    cudaFuncSetAttribute(segattn_ln_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    cudaFuncSetAttribute(segattn_ln_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    attr = true;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (nc == 1) segattn_ln_fwd_kernel<1><<<grid, SL_TQ * 32, smem, st>>>(a);
+  else if (nc == 2) segattn_ln_fwd_kernel<2><<<grid, SL_TQ * 32, smem, st>>>(a);
+  else if (nc == 3) segattn_ln_fwd_kernel<3><<<grid, SL_TQ * 32, smem, st>>>(a);
+  else segattn_ln_fwd_kernel<4><<<grid, SL_TQ * 32, smem, st>>>(a);
+  IMMTSF_CHECK_LAUNCH("segattn_ln_fwd");
+  return IMMTSF_OK;
 }
 
 // Backward.  smem: tile32 staging | s_out [32*32] | s_p [H][NM] | s_ds [H][NM] | s_dp [TT][H][NM]

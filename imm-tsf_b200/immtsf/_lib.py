@@ -46,6 +46,8 @@ SIGNATURES = {
     "immtsf_time2vec_fwd": [P, P, P, P, P, I, P, I, P, I, P, I, P],
     "immtsf_time2vec_bwd": [P, I, P, P, P, I, P, P, P, P, P, I, P],
     "immtsf_segattn_fwd": [P, P, P, I, I, I, I, I, I, U32, U64, P, P, P],
+    "immtsf_segattn_ln_ok": [I, I],
+    "immtsf_segattn_ln_fwd": [P, P, P, I, I, I, I, U32, U64, P, P, P, P, F, P, P, P, P, P, P],
     "immtsf_segattn_bwd": [P, P, P, P, P, I, I, I, I, I, I, U32, U64, P, P, P],
     "immtsf_t2vq_attn_fwd": [P, I, P, P, P, P, P, I, P, P, P, P, I, I, I, I, I, I, I, U32, U64, P, P, P, P, P],
     "immtsf_t2vq_bwd_tiles": [I, I, I],

@@ -263,8 +263,11 @@ class T2VXAttnFoldFn(torch.autograd.Function):
         ops.gemm(X, Wvf, KVp[:, d:], transB=True, bias=bvf, ragged=r.m_dev, ragged_dim=1, lo=lo)
         fkw.wait(box["ev_q"], u, box["q"])
         fkw.join()
-        attn_cat, probs = ops.segattn_fwd(u, KVp, r, T, 1, d, True, thr, seed, save)
-        y, mean, rstd = ops.ln_fwd(attn_cat, Qp.view(d), r.m_txt, T, gamma, beta, thr, seed, ops.SITE_TTF_DROPOUT, save, xbias=out_b)
+        if ops.segattn_ln_ok(d, r.N):
+            y, attn_cat, probs, mean, rstd = ops.segattn_ln_fwd(u, KVp, r, T, d, thr, seed, out_b, Qp.view(d), gamma, beta, save)
+        else:
+            attn_cat, probs = ops.segattn_fwd(u, KVp, r, T, 1, d, True, thr, seed, save)
+            y, mean, rstd = ops.ln_fwd(attn_cat, Qp.view(d), r.m_txt, T, gamma, beta, thr, seed, ops.SITE_TTF_DROPOUT, save, xbias=out_b)
         E = y if defer else ops.linear_fwd(y, W_po, b_po, lo=lo, emit_lo=step.e_txt_feeds_tc)
         if save:
             ctx.r, ctx.T, ctx.thr, ctx.seed, ctx.lo, ctx.defer, ctx.has_in, ctx.scale = r, T, thr, seed, lo, defer, has_in, scale
@@ -387,8 +390,12 @@ class T2VXAttnFoldFn(torch.autograd.Function):
             ops.multi_split([(dWx[:, dm:], dW_kv[:, d:], None)])
             res["dW_kv"], res["db_kv"], res["dW_in"], res["db_in"] = dW_kv, dbX, dW_in, db_in
 
-        fk.run(params_t2v, dphi, pack_x, lane=2)  # (same lane as dW_x: the lane's all-reduce follows both)
-        fk.run(params_x, lane=2, after_current=False)
+        if dp:
+            fk.run(params_t2v, dphi, pack_x, lane=2)  # same lane as dW_x: the lane's all-reduce follows both
+            fk.run(params_x, lane=2, after_current=False)
+        else:
+            fk.run(params_x, lane=2, after_current=False)  # the un-fold does not wait for d phi
+            fk.run(params_t2v, dphi, pack_x, lane=1)
         db_o = res["db_o"]
         dwl, dbl, dwp, dbp = res["t2v"]
         dQp, dW_kv, db_kv, dW_in, db_in, dW_o = (res[k] for k in ("dQp", "dW_kv", "db_kv", "dW_in", "db_in", "dW_o"))

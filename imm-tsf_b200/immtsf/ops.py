@@ -560,6 +560,25 @@ def segattn_fwd(q, KVp, r: RaggedNotes, T, H, d, per_query, thr, seed, save):
     return attn_cat, probs
 
 
+def segattn_ln_ok(d, N_max) -> bool:
+    return os.environ.get("IMMTSF_SEGATTN_FUSED", "1") != "0" and bool(_lib.load().immtsf_segattn_ln_ok(d, max(N_max, 1)))
+
+
+def segattn_ln_fwd(q, KVp, r: RaggedNotes, T, d, thr, seed, xbias, res, gamma, beta, save):
+    """One head, train mode: segment attention + bias + residual + LayerNorm + dropout in one launch (csrc/t2v_segattn.cu).
+    Returns y [B*T, d] and what backward needs: attn_cat [B*T, d], probs [M_alloc, 1], mean, rstd [B*T]."""
+    dev = KVp.device
+    R = r.B * T
+    attn_cat = torch.empty(R, d, dtype=torch.float32, device=dev)
+    y = torch.empty(R, d, dtype=torch.float32, device=dev)
+    probs = torch.empty(r.M_alloc, 1, dtype=torch.float32, device=dev) if save else None
+    mean = torch.empty(R, dtype=torch.float32, device=dev) if save else None
+    rstd = torch.empty(R, dtype=torch.float32, device=dev) if save else None
+    _lib.call("immtsf_segattn_ln_fwd", _p(q), _p(KVp), _p(r.offsets), r.B, T, d, max(r.N, 1), thr, seed, _p(xbias), _p(res), _p(gamma),
+              _p(beta), LN_EPS, _p(attn_cat), _p(probs), _p(y), _p(mean), _p(rstd), _stream())
+    return y, attn_cat, probs, mean, rstd
+
+
 def segattn_bwd(d_attn_cat, q, KVp, probs, r: RaggedNotes, T, H, d, per_query, thr, seed):
     dKVp = torch.empty(r.M_alloc, 2 * d, dtype=torch.float32, device=KVp.device)
     dq_partial = torch.empty(r.B, d, dtype=torch.float32, device=KVp.device)

@@ -187,6 +187,16 @@ int immtsf_segattn_bwd(const float* d_attn_cat, const float* q, const float* KVp
                        const int32_t* offsets, int B, int T, int H, int d, int N_max, int per_query,
                        uint32_t drop_thr, uint64_t seed, float* dKVp, float* dq_partial, void* stream);
 
+/* ---- one head, train mode: the attention above + out-projection bias + learned query residual + LayerNorm + dropout
+ * (TTF_T2V_XAttn.py:143-179) in ONE launch, eight query rows per CTA; attn_cat [B*T, d] (the pooled rows, saved for backward),
+ * probs [sum N] and mean / rstd [B*T] are what immtsf_ln_bwd / immtsf_segattn_bwd need.  Same results as immtsf_segattn_fwd
+ * (H = 1, per_query = 1) followed by immtsf_ln_fwd(x = attn_cat, xbias, res, valid = "sample has notes", rows_per_sample = T). */
+int immtsf_segattn_ln_ok(int d, int N_max);
+int immtsf_segattn_ln_fwd(const float* q, const float* KVp, const int32_t* offsets, int B, int T, int d, int N_max,
+                          uint32_t drop_thr, uint64_t seed, const float* xbias, const float* res, const float* gamma,
+                          const float* beta, float eps, float* attn_cat, float* probs, float* y, float* mean,
+                          float* rstd, void* stream);
+
 /* ---- K3b: per-(note, query) Time2Vec attention (fusions/TTF_T2V_XAttn_old.py:119-143 -- Time2Vec
  * of the clamped lag max(t_hat - tau, 0) of every (note, query) pair enters keys and values).  With
  * X_nt = A_n + W_phi phi_nt (A = V' W_a^T + b_kv once per note, KV_proj.weight = [W_a | W_phi]) the caller supplies
