@@ -592,6 +592,39 @@ def run_gpu_arm(args, w):
         ms_checked = statistics.median(rounds(lambda: timed(K, False, graphed, check=True), min(R, 3)))
     clk = clocks.stop() if rank == 0 else None
 
+    # ---- the UNMODIFIED caller's loop (lib/evaluation.py:95-100 + loss.backward(), main.py:1097) through the public API with
+    # the transparent graph cache (immtsf/autograph.py): padded shapes change from batch to batch (N_max of the batch)
+    autograph_sps = autograph_graphs = None
+    if world == 1 and not args.eager:
+        variants = []
+        for i, nmax in enumerate((w["N"], max(w["N"] - 3, 1), max(w["N"] // 2, 1), w["N"])):
+            nb = synth.synth_batch(Bl, nmax, w["T"], w["d_model"], w["C"], 4000 + i, history=w["history"], pred=w["pred"])
+            variants.append([t.to(dev) for t in nb[:4]])
+        fm.enable_graphs(True)
+
+        def api_steps(n):
+            pairs = []
+            for i in range(n):
+                flush.fill_(1.0)
+                v = variants[i % len(variants)]
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for p in params:
+                    p.grad = None
+                out = fm(v[0], v[1], v[2], v[3].detach().requires_grad_(True))
+                out.square().mean().backward()
+                e1.record()
+                pairs.append((e0, e1))
+            torch.cuda.synchronize()
+            return sum(e0.elapsed_time(e1) for e0, e1 in pairs)
+
+        api_steps(2 * len(variants))
+        ms_api = statistics.median([api_steps(K) for _ in range(min(R, 3))])
+        autograph_sps = Bl * K / (ms_api / 1e3)
+        autograph_graphs = fm._autograph.captures
+        fm.enable_graphs(False)
+        fm.clear_graphs()
+
     # instrumented pass (eager): CUDA-event pairs, on the launching stream, around every launch of the workload's dominant
     # kernel family -- the tcgen05 GEMMs (recorded inside the library: immtsf_profile_begin/end; ragged launches are issued
     # over M_alloc rows but only sumN are live: live work only is counted) and the HBM-bound RecAvg / GR_Add kernels.
@@ -685,6 +718,10 @@ def run_gpu_arm(args, w):
                    "launch": "eager (one host call per kernel)" if args.eager else "runtime.GraphedStep (whole step replayed as one CUDA graph)",
                    "rounds": R, "round_ms_per_step": [x / K for x in res_rounds], "value_is": "median round",
                    "eager_samples_per_s": samples / (ms_eager / 1e3), "kernels_per_step": launches_per_step,
+                   "public_api_varying_shapes_samples_per_s": autograph_sps,
+                   "public_api_note": "fusion(notes, tau, t_hat, Y_ts); loss.backward() through FusionModel with enable_graphs(): one captured "
+                                      "forward/backward graph pair per padded shape (%s pairs for 4 batch shapes, N_max bucketed to 8), NaN "
+                                      "ValueError check (one host sync) after every forward" % autograph_graphs,
                    "algorithmic_gflop_fwd_bwd_reference_schedule": fb_f / 1e9},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / K, "round_ms_per_step": [x / K for x in e2e_rounds],

@@ -231,9 +231,34 @@ __global__ void __launch_bounds__(SL_TQ * 32) segattn_ln_fwd_kernel(const SegLnA
   for (int i = 0; i < NC; ++i) zero8(acc[i]);
   if (nn > 0) {
     // scores and softmax over the segment (recomputed by every tile of the sample; tile 0 saves the probabilities)
-    for (int n = w; n < nn; n += SL_TQ) {
-      const float sc = warp_dot(a.q, a.KVp + (size_t)(nb + n) * ld, d, lane);
-      if (lane == 0) s_p[n] = sc;
+    // the first SL_NS value rows start their way into shared memory now (cp.async) and land while the scores, the softmax and
+    // the dropout weights are computed
+    {
+      const int cnt0 = min(SL_NS, nn);
+      for (int i = threadIdx.x; i < cnt0 * d4; i += blockDim.x) {
+        const int r = i / d4, c = i % d4;
+        const unsigned int dst = (unsigned int)__cvta_generic_to_shared(reinterpret_cast<float4*>(s_v) + (size_t)r * d4 + c);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(reinterpret_cast<const float4*>(a.KVp + (size_t)(nb + r) * ld + d) + c) : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    {
+      float4 qv[(NC * 2)];  // this lane's part of the query vector: float4 chunks lane, lane + 32, ...
+#pragma unroll
+      for (int j = 0; j < NC * 2; ++j) qv[j] = lane + 32 * j < d4 ? __ldg(reinterpret_cast<const float4*>(a.q) + lane + 32 * j) : f4_zero();
+      for (int n = w; n < nn; n += SL_TQ) {
+        const float4* kp = reinterpret_cast<const float4*>(a.KVp + (size_t)(nb + n) * ld);
+        float sc = 0.f;
+#pragma unroll
+        for (int j = 0; j < NC * 2; ++j) {
+          if (lane + 32 * j < d4) {
+            const float4 kv = __ldg(kp + lane + 32 * j);
+            sc = fmaf(qv[j].x, kv.x, fmaf(qv[j].y, kv.y, fmaf(qv[j].z, kv.z, fmaf(qv[j].w, kv.w, sc))));
+          }
+        }
+        sc = warp_sum(sc);
+        if (lane == 0) s_p[n] = sc;
+      }
     }
     __syncthreads();
     if (w == 0) {
@@ -265,9 +290,13 @@ __global__ void __launch_bounds__(SL_TQ * 32) segattn_ln_fwd_kernel(const SegLnA
     for (int n0 = 0; n0 < nn; n0 += SL_NS) {
       const int cnt = min(SL_NS, nn - n0);
       __syncthreads();  // (also orders the s_pt writes above before their first use)
-      for (int i = threadIdx.x; i < cnt * d4; i += blockDim.x) {
-        const int r = i / d4, c = i % d4;
-        reinterpret_cast<float4*>(s_v)[(size_t)r * d4 + c] = __ldg(reinterpret_cast<const float4*>(a.KVp + (size_t)(nb + n0 + r) * ld + d) + c);
+      if (n0 > 0) {
+        for (int i = threadIdx.x; i < cnt * d4; i += blockDim.x) {
+          const int r = i / d4, c = i % d4;
+          reinterpret_cast<float4*>(s_v)[(size_t)r * d4 + c] = __ldg(reinterpret_cast<const float4*>(a.KVp + (size_t)(nb + n0 + r) * ld + d) + c);
+        }
+      } else {
+        asm volatile("cp.async.wait_all;" ::: "memory");
       }
       __syncthreads();
       if (row_ok) {

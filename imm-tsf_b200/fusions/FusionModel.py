@@ -49,8 +49,30 @@ class FusionModel(nn.Module):
             self.mmf = MMF_cls(d_txt=d_txt, C=args.C, d_attn=d_txt, n_heads_fusion=args.n_heads_fusion,
                                dropout=args.dropout, kappa=args.kappa)
 
+    def enable_graphs(self, on: bool = True):
+        """Transparent CUDA-graph replay of forward and backward, one captured pair per input shape (immtsf/autograph.py): the
+        unmodified caller (lib/evaluation.py:95-100 + loss.backward(), main.py:1097) runs at graph speed.  Also IMMTSF_AUTOGRAPH=1."""
+        self._autograph_on = bool(on)  # (captured graphs are kept when switched off; clear_graphs() drops them)
+        return self
+
+    def clear_graphs(self):
+        self._autograph = None
+
     def forward(self, notes_input, tau, t_hat, Y_ts):
         cm.require_cuda(notes_input, "FusionModel")
+        on = getattr(self, "_autograph_on", None)
+        if on is None:
+            on = self._autograph_on = os.environ.get("IMMTSF_AUTOGRAPH", "0") == "1"
+        if (on and hasattr(self.ttf, "forward_ragged") and hasattr(self.mmf, "forward_flags") and not torch.cuda.is_current_stream_capturing()
+                and notes_input.dim() == 3 and Y_ts.is_cuda and t_hat.is_cuda and tau.is_cuda):
+            if getattr(self, "_autograph", None) is None:
+                from immtsf import autograph
+
+                self._autograph = autograph.GraphCache(self)
+            return self._autograph(notes_input, tau, t_hat, Y_ts)
+        return self._forward_eager(notes_input, tau, t_hat, Y_ts)
+
+    def _forward_eager(self, notes_input, tau, t_hat, Y_ts):
         if not (hasattr(self.ttf, "forward_ragged") and hasattr(self.mmf, "forward_flags")):
             # a user-supplied TTF/MMF class: plain composition, reference order of checks
             if torch.isnan(Y_ts).any():
@@ -103,7 +125,12 @@ class FusionModel(nn.Module):
         # rank form of MMF_XAttn_Add: E_txt only enters through one skinny product, so the TTF's final projection is folded
         # into that operand in weight space and E_txt [B, T, d] is never materialised (IMMTSF_FUSE_PROJ=0 keeps it)
         rank, defer = self._schedule(T)
-        ops.begin_step(e_txt_feeds_tc=isinstance(self.mmf, MMF_XAttn_Add) and not rank)
+        x_cat, d_txt = None, self.ttf.d_txt
+        if isinstance(self.mmf, MMF_GR_Add):
+            # MMF_GR_Add reads x = [E ; Y]: the TTF's final projection writes E_txt straight into that buffer
+            C = Y32.shape[-1]
+            x_cat = torch.empty(Y32.shape[0] * T, ops.round_up(C + d_txt, 4), dtype=torch.float32, device=Y32.device)
+        ops.begin_step(e_txt_feeds_tc=isinstance(self.mmf, MMF_XAttn_Add) and not rank, x_cat=x_cat, d_txt=d_txt)
         try:
             return self._forward_step(r, t_hat, Y32, flags, check, defer, rank)
         finally:

@@ -41,7 +41,7 @@ class RecAvgFn(torch.autograd.Function):
         if defer:
             E_txt = E_drop.view(B, T, d)
         else:
-            E_txt = ops.linear_fwd(E_drop.view(B * T, d), W_p, b_p, lo=lo, emit_lo=step.e_txt_feeds_tc).view(B, T, d)
+            E_txt = ops.linear_fwd(E_drop.view(B * T, d), W_p, b_p, out=step.final_out(B * T, d), lo=lo, emit_lo=step.e_txt_feeds_tc).view(B, T, d)
         if save:
             ctx.r, ctx.T, ctx.thr, ctx.seed, ctx.has_in, ctx.lo, ctx.defer = r, T, thr, seed, W_in is not None, lo, defer
             ctx.save_for_backward(t_hat, log_sigma, W_in, gamma, W_p, Vp, E_drop, E_raw, mean, rstd, wsum)
@@ -268,7 +268,7 @@ class T2VXAttnFoldFn(torch.autograd.Function):
         else:
             attn_cat, probs = ops.segattn_fwd(u, KVp, r, T, 1, d, True, thr, seed, save)
             y, mean, rstd = ops.ln_fwd(attn_cat, Qp.view(d), r.m_txt, T, gamma, beta, thr, seed, ops.SITE_TTF_DROPOUT, save, xbias=out_b)
-        E = y if defer else ops.linear_fwd(y, W_po, b_po, lo=lo, emit_lo=step.e_txt_feeds_tc)
+        E = y if defer else ops.linear_fwd(y, W_po, b_po, out=step.final_out(B * T, d), lo=lo, emit_lo=step.e_txt_feeds_tc)
         if save:
             ctx.r, ctx.T, ctx.thr, ctx.seed, ctx.lo, ctx.defer, ctx.has_in, ctx.scale = r, T, thr, seed, lo, defer, has_in, scale
             ctx.save_for_backward(Qp, w_per, b_per, W_in, b_in, W_kv, in_w, in_b, out_w, out_b, gamma, W_po, Ecat, KVp, Wx, Wvf,
@@ -453,7 +453,7 @@ class T2VPerQueryFn(torch.autograd.Function):
             ops.gemm(spv[:, h:h + 1], b_v[hs].view(1, hd), O[:, hs], beta=1.0)  # sum_n P~ b_v (P~ does not sum to 1 under dropout)
         attn_out = ops.linear_fwd(O, out_w, out_b, lo=lo)
         y, mean, rstd = ops.ln_fwd(attn_out, Qp.view(d), r.m_txt, T, gamma, beta, thr, seed, ops.SITE_TTF_DROPOUT, save)
-        E = ops.linear_fwd(y, W_po, b_po, lo=lo, emit_lo=step.e_txt_feeds_tc)
+        E = ops.linear_fwd(y, W_po, b_po, out=step.final_out(B * T, d), lo=lo, emit_lo=step.e_txt_feeds_tc)
         if save:
             ctx.r, ctx.T, ctx.H, ctx.thr, ctx.seed, ctx.lo, ctx.scale = r, T, H, thr, seed, lo, scale
             ctx.has_in = W_in is not None
@@ -529,24 +529,37 @@ class T2VPerQueryFn(torch.autograd.Function):
 
 # ============================================================== MMF_GR_Add
 class GRAddFn(torch.autograd.Function):
+    """MMF_GR_Add.py:31-61.  x = [E ; Y] (the reference's [Y ; E] with the two blocks swapped, so that the wide block starts
+    16-byte aligned and the TTF's final projection can write E_txt straight into it -- ops.StepCtx.x_cat; the columns of
+    [W_ih ; W_g] are permuted the same way): the GRU input map and the gate net read x once, as ONE skinny product.
+    No ATen kernel on the path: Y, the permuted weights and the biases are placed by one immtsf_multi_split launch."""
+
     @staticmethod
     def forward(ctx, Y, E, m_txt, thr, seed, save, flags, W_ih, W_hh, b_ih, b_hh, W_r, b_r, W_g, b_g, gamma, beta):
         B, T, C = Y.shape
         d = E.shape[2]
+        dev = Y.device
         Yc = Y.contiguous()
-        # x = [Y ; E] (MMF_GR_Add.py:43) and [W_ih ; W_g] (GRU input map and gate net read x once), both with the
-        # row length C+d padded to a multiple of 4 floats so that every row is 16-byte aligned
-        Kp = ops.round_up(C + d, 4)
-        X = torch.empty(B * T, Kp, dtype=_f32, device=Y.device)
-        X[:, :C].copy_(Yc.view(B * T, C))
-        X[:, C:C + d].copy_(E.reshape(B * T, d))
-        Wcat = torch.empty(4 * C, Kp, dtype=_f32, device=Y.device)
-        Wcat[:3 * C, :C + d].copy_(W_ih)
-        Wcat[3 * C:, :C + d].copy_(W_g)
+        Kp = ops.round_up(C + d, 4)  # row length padded to 16 bytes
+        step = ops.step_ctx()
+        X = step.x_cat
+        in_place = (X is not None and tuple(X.shape) == (B * T, Kp) and E.data_ptr() == X.data_ptr() and E.stride(-1) == 1
+                    and E.stride(-2) == Kp and (T == 1 or E.stride(0) == T * Kp))
+        tasks = []
+        if not in_place:
+            X = torch.empty(B * T, Kp, dtype=_f32, device=dev)
+            E2 = E.reshape(B * T, d)  # (a broadcast view -- T2V eval mode -- is materialised here)
+            tasks.append((E2, X[:, :d], None))
+        Wcat = torch.empty(4 * C, Kp, dtype=_f32, device=dev)
+        bcat = torch.empty(4 * C, dtype=_f32, device=dev)
+        tasks += [(Yc.view(B * T, C), X[:, d:d + C], None),
+                  (W_ih[:, C:], Wcat[:3 * C, :d], None), (W_ih[:, :C], Wcat[:3 * C, d:d + C], None),
+                  (W_g[:, C:], Wcat[3 * C:, :d], None), (W_g[:, :C], Wcat[3 * C:, d:d + C], None),
+                  (b_ih, bcat[:3 * C], None), (b_g, bcat[3 * C:], None)]
         if Kp > C + d:
-            X[:, C + d:].zero_()
-            Wcat[:, C + d:].zero_()
-        bcat = torch.cat([b_ih, b_g], dim=0)
+            z = ops.zeros_cached(dev, max(B * T, 4 * C), Kp - C - d)
+            tasks += [(z[:B * T], X[:, C + d:], None), (z[:4 * C], Wcat[:, C + d:], None)]
+        ops.multi_split(tasks)
         G4 = ops.linear_fwd(X, Wcat, bcat)
         W_hh_c, b_hh_c, W_r_c = W_hh.contiguous(), b_hh.contiguous(), W_r.contiguous()
         h_all, h_prev, gates = ops.gru_scan_fwd(G4, W_hh_c, b_hh_c, B, T, C)
@@ -560,6 +573,7 @@ class GRAddFn(torch.autograd.Function):
     def backward(ctx, dY_out):
         m_txt, X, Wcat, G4, h_all, h_prev, W_hh, b_hh, W_r, b_r, gamma, beta, gates = ctx.saved_tensors
         B, T, C, d = ctx.dims
+        dev = X.device
         dY_out = dY_out.contiguous()
         dG4 = torch.empty_like(G4)
         d_delta, dh_out, dgamma, dbeta = ops.gr_tail_bwd(dY_out, G4, h_all, W_r, b_r, gamma, beta, m_txt, B, T, C, ctx.thr,
@@ -571,13 +585,16 @@ class GRAddFn(torch.autograd.Function):
         db_hh = ops.colsum(dGh)
         dWcat = ops.linear_wgrad(dG4, X)
         dbcat = ops.colsum(dG4)
-        # dY = dY_out (blend passes Y straight through) + dG4 Wcat[:, :C] ;  dE = dG4 Wcat[:, C:]
-        dY = dY_out.view(B * T, C).clone()
-        ops.gemm(dG4, Wcat[:, :C], dY, beta=1.0)
-        dE = torch.empty(B * T, d, dtype=_f32, device=X.device)
-        ops.gemm(dG4, Wcat[:, C:C + d], dE)
-        return (dY.view(B, T, C), dE.view(B, T, d), None, None, None, None, None, dWcat[: 3 * C, :C + d], dW_hh, dbcat[: 3 * C],
-                db_hh, dW_r, db_r, dWcat[3 * C:, :C + d], dbcat[3 * C:], dgamma, dbeta)
+        # dY = dY_out (the blend passes Y straight through) + dG4 Wcat[:, Y block] ;  dE = dG4 Wcat[:, E block]
+        dY = ops.gemm(dG4, Wcat[:, d:d + C], torch.empty(B * T, C, dtype=_f32, device=dev))
+        ops.axpby(dY_out.view(B * T, C), 1.0, dY, True)
+        dE = ops.gemm(dG4, Wcat[:, :d], torch.empty(B * T, d, dtype=_f32, device=dev))
+        # back to the reference's column order [Y block | E block]
+        dW_ih, dW_g = torch.empty(3 * C, C + d, dtype=_f32, device=dev), torch.empty(C, C + d, dtype=_f32, device=dev)
+        ops.multi_split([(dWcat[:3 * C, d:d + C], dW_ih[:, :C], None), (dWcat[:3 * C, :d], dW_ih[:, C:], None),
+                         (dWcat[3 * C:, d:d + C], dW_g[:, :C], None), (dWcat[3 * C:, :d], dW_g[:, C:], None)])
+        return (dY.view(B, T, C), dE.view(B, T, d), None, None, None, None, None, dW_ih, dW_hh, dbcat[: 3 * C],
+                db_hh, dW_r, db_r, dW_g, dbcat[3 * C:], dgamma, dbeta)
 
 
 # ============================================================== MMF_XAttn_Add

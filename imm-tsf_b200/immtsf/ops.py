@@ -132,6 +132,18 @@ def ticket(dev) -> torch.Tensor:
     return t
 
 
+_ZEROS = {}
+
+
+def zeros_cached(dev, rows: int, cols: int) -> torch.Tensor:
+    """A read-only block of zeros (source of pad columns in immtsf_multi_split copies); grown on demand, never written."""
+    key = (torch.device(dev).index, cols)
+    z = _ZEROS.get(key)
+    if z is None or z.shape[0] < rows:
+        z = _ZEROS[key] = torch.zeros(rows, cols, dtype=torch.float32, device=dev)
+    return z
+
+
 def zero_pad_rows(X: torch.Tensor, ncols: int, m_dev: torch.Tensor, M_alloc: int):
     _lib.call("immtsf_zero_pad_rows", _p(X), X.stride(0), ncols, _p(m_dev), M_alloc, _stream())
 
@@ -189,16 +201,28 @@ class StepCtx:
     def __init__(self, lo=None, e_txt_feeds_tc=False):
         self.lo = lo if lo is not None else LoCache()
         self.e_txt_feeds_tc = e_txt_feeds_tc
+        # MMF_GR_Add reads x = [E ; Y] (MMF_GR_Add.py:43): FusionModel allocates that buffer BEFORE the TTF forward and the
+        # TTF's final projection writes E_txt straight into its left columns (e_out_rows x d view, leading dimension = the
+        # buffer's), so E_txt is never copied.  x_cat is the whole buffer.
+        self.x_cat = None
+        self.e_out = None
+
+    def final_out(self, rows: int, d: int):
+        """Destination of a TTF's final projection when the consumer wants E_txt in place (else None)."""
+        e = self.e_out
+        return e if e is not None and tuple(e.shape) == (rows, d) else None
 
 
 _STEP: Optional[StepCtx] = None
 
 
-def begin_step(e_txt_feeds_tc: bool) -> StepCtx:
+def begin_step(e_txt_feeds_tc: bool, x_cat=None, d_txt: int = 0) -> StepCtx:
     global _STEP
     if DP_NVLS is not None:
         DP_NVLS.reset()  # the statistics buffers of a step sit at the same arena offsets in every step
     _STEP = StepCtx(e_txt_feeds_tc=e_txt_feeds_tc)
+    if x_cat is not None:
+        _STEP.x_cat, _STEP.e_out = x_cat, x_cat[:, :d_txt]
     return _STEP
 
 

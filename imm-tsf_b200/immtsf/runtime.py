@@ -218,7 +218,8 @@ class GraphedStep:
             dist.all_reduce(self.flat_grads[self.n_first:], op=dist.ReduceOp.SUM, group=self.group)
 
     def _eager(self):
-        out = self.fusion(self.static_in[0], self.static_in[1], self.static_in[2], self.static_in[3])
+        fwd = getattr(self.fusion, "_forward_eager", self.fusion)  # (never through the transparent graph cache)
+        out = fwd(self.static_in[0], self.static_in[1], self.static_in[2], self.static_in[3])
         loss = self.loss_fn(out, *self.static_extra)
         loss.backward()
         return out, loss
