@@ -203,40 +203,59 @@ __device__ __forceinline__ void epilogue_store(const float (&acc)[128], uint32_t
   }
   const bool full4 = n + 3 < ncols;
   const int nrows = min(32, Mfull - row0);
-  for (int rr = 0; rr < nrows; ++rr) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-                 : "r"(stage + (uint32_t)((rr * EPI_LD + lane * 4) * 4)));
-    float* p = out + (size_t)rr * ld + lane * 4;
-    if (!partial) {
-      const bool live = row0 + rr < Mlive;
-      v.x = live ? fmaf(alpha, v.x, b[0]) : 0.f; v.y = live ? fmaf(alpha, v.y, b[1]) : 0.f;
-      v.z = live ? fmaf(alpha, v.z, b[2]) : 0.f; v.w = live ? fmaf(alpha, v.w, b[3]) : 0.f;
-      if (beta != 0.f && live) {
-        if (full4) {
-          const float4 cc = *reinterpret_cast<const float4*>(p);
-          v.x = fmaf(beta, cc.x, v.x); v.y = fmaf(beta, cc.y, v.y); v.z = fmaf(beta, cc.z, v.z); v.w = fmaf(beta, cc.w, v.w);
-        } else {
-          v.x = fmaf(beta, p[0], v.x);
-          if (n + 1 < ncols) v.y = fmaf(beta, p[1], v.y);
-          if (n + 2 < ncols) v.z = fmaf(beta, p[2], v.z);
+  const bool use_beta = !partial && beta != 0.f;
+  for (int r8 = 0; r8 < nrows; r8 += 8) {
+    // beta * C: the eight rows' old values are requested together, ahead of their use (one dependent global load per row
+    // made the accumulate-into-C epilogue 18 us longer than the plain one at 4096 x 768 x 768)
+    float4 cc[8];
+    if (use_beta) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        cc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int rr = r8 + u;
+        if (rr < nrows && row0 + rr < Mlive) {
+          const float* p = out + (size_t)rr * ld + lane * 4;
+          if (full4) {
+            cc[u] = *reinterpret_cast<const float4*>(p);
+          } else {
+            cc[u].x = p[0];
+            if (n + 1 < ncols) cc[u].y = p[1];
+            if (n + 2 < ncols) cc[u].z = p[2];
+          }
         }
       }
     }
-    if (full4) {
-      *reinterpret_cast<float4*>(p) = v;
-    } else {
-      p[0] = v.x;
-      if (n + 1 < ncols) p[1] = v.y;
-      if (n + 2 < ncols) p[2] = v.z;
-    }
-    if (out_lo != nullptr) {  // ld_lo is a multiple of 4 and >= roundup(ncols, 4): the whole float4 is in bounds
-      float4 l;
-      l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-      l.y = n + 1 < ncols ? v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u) : 0.f;
-      l.z = n + 2 < ncols ? v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u) : 0.f;
-      l.w = n + 3 < ncols ? v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u) : 0.f;
-      *reinterpret_cast<float4*>(out_lo + (size_t)rr * ld_lo + lane * 4) = l;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int rr = r8 + u;
+      if (rr >= nrows) break;
+      float4 v;
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                   : "r"(stage + (uint32_t)((rr * EPI_LD + lane * 4) * 4)));
+      float* p = out + (size_t)rr * ld + lane * 4;
+      if (!partial) {
+        const bool live = row0 + rr < Mlive;
+        v.x = live ? fmaf(alpha, v.x, b[0]) : 0.f; v.y = live ? fmaf(alpha, v.y, b[1]) : 0.f;
+        v.z = live ? fmaf(alpha, v.z, b[2]) : 0.f; v.w = live ? fmaf(alpha, v.w, b[3]) : 0.f;
+        if (use_beta && live) {
+          v.x = fmaf(beta, cc[u].x, v.x); v.y = fmaf(beta, cc[u].y, v.y); v.z = fmaf(beta, cc[u].z, v.z); v.w = fmaf(beta, cc[u].w, v.w);
+        }
+      }
+      if (full4) {
+        *reinterpret_cast<float4*>(p) = v;
+      } else {
+        p[0] = v.x;
+        if (n + 1 < ncols) p[1] = v.y;
+        if (n + 2 < ncols) p[2] = v.z;
+      }
+      if (out_lo != nullptr) {  // ld_lo is a multiple of 4 and >= roundup(ncols, 4): the whole float4 is in bounds
+        float4 l;
+        l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+        l.y = n + 1 < ncols ? v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u) : 0.f;
+        l.z = n + 2 < ncols ? v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u) : 0.f;
+        l.w = n + 3 < ncols ? v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u) : 0.f;
+        *reinterpret_cast<float4*>(out_lo + (size_t)rr * ld_lo + lane * 4) = l;
+      }
     }
   }
 }
@@ -686,12 +705,30 @@ __global__ void splitk_reduce_kernel(float* __restrict__ C, int ldc, int M, int 
     const int r = (int)(i / n4), c = (int)(i % n4) * 4;
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
     if (r < Meff)
-      for (int z = 0; z < splitk; ++z) {
-        const float4 p = *reinterpret_cast<const float4*>(partial + ((size_t)z * M + r) * ldp + c);
-        s.x += p.x; s.y += p.y; s.z += p.z; s.w += p.w;
+      for (int z0 = 0; z0 < splitk; z0 += 8) {  // eight partial tiles requested together, added in split order
+        float4 p[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          p[u] = z0 + u < splitk ? __ldcs(reinterpret_cast<const float4*>(partial + ((size_t)(z0 + u) * M + r) * ldp + c))
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { s.x += p[u].x; s.y += p[u].y; s.z += p[u].z; s.w += p[u].w; }
       }
     const float v[4] = {s.x, s.y, s.z, s.w};
     float* out = C + (size_t)r * ldc + c;
+    if (c + 3 < N && beta == 0.f && (((uintptr_t)out) & 15) == 0 && (C_lo == nullptr || (((uintptr_t)(C_lo + (size_t)r * ldc_lo + c)) & 15) == 0)) {
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < Meff) {
+        x = make_float4(alpha * v[0], alpha * v[1], alpha * v[2], alpha * v[3]);
+        if (bias != nullptr) { x.x += bias[c]; x.y += bias[c + 1]; x.z += bias[c + 2]; x.w += bias[c + 3]; }
+      }
+      *reinterpret_cast<float4*>(out) = x;
+      if (C_lo != nullptr)
+        *reinterpret_cast<float4*>(C_lo + (size_t)r * ldc_lo + c) =
+            make_float4(x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u), x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u),
+                        x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u), x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u));
+      continue;
+    }
     for (int e = 0; e < 4 && c + e < N; ++e) {
       float x = 0.f;
       if (r < Meff) {
@@ -985,6 +1022,40 @@ extern "C" int immtsf_split_lo(const float* src, int ld, int rows, int cols, flo
   IMMTSF_REQUIRE(((uintptr_t)src & 15) == 0 && (ld & 3) == 0 && ((uintptr_t)lo & 15) == 0 && (ld_lo & 3) == 0 && ld_lo >= cols,
                  "split_lo: operands must be 16B aligned with ld %% 4 == 0 and ld_lo >= cols");
   return launch_split_lo(src, ld, rows, cols, lo, ld_lo, ragged, ragged != nullptr, (cudaStream_t)stream);
+}
+
+// dst[c][r] = src[r][c] (32 x 32 tiles through shared memory) and, when lo != NULL, lo[c][r] = dst - trunc_tf32(dst).
+// The tcgen05 kernel reads K-major operands with 128B-swizzled boxes at full rate; an MN-major fp32 operand goes through the
+// "32B atom" path, measured 1.7x slower on the data-gradient products (dx = dy W: 46 us against 28 us at 4096 x 768 x 768).
+// Transposing the WEIGHT once (2.4 MB) is cheaper than paying that on every row of the batch.
+__global__ void __launch_bounds__(256) transpose_split_kernel(const float* __restrict__ src, int ld, int rows, int cols,
+                                                               float* __restrict__ dst, int ldd, float* __restrict__ lo, int ldl) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int j = ty; j < 32; j += 8) {
+    const int r = r0 + j, c = c0 + tx;
+    tile[j][tx] = (r < rows && c < cols) ? __ldg(src + (size_t)r * ld + c) : 0.f;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int c = c0 + j, r = r0 + tx;  // output row = source column
+    if (c < cols && r < rows) {
+      const float v = tile[tx][j];
+      dst[(size_t)c * ldd + r] = v;
+      if (lo != nullptr) lo[(size_t)c * ldl + r] = v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+    }
+  }
+}
+
+extern "C" int immtsf_transpose_split(const float* src, int ld, int rows, int cols, float* dst, int ldd, float* lo, int ldl,
+                                      void* stream) {
+  if (rows == 0 || cols == 0) return IMMTSF_OK;
+  IMMTSF_REQUIRE(src && dst && ld >= cols && ldd >= rows && (lo == nullptr || ldl >= rows), "transpose_split: bad arguments");
+  transpose_split_kernel<<<dim3(ceil_div(cols, 32), ceil_div(rows, 32)), 256, 0, (cudaStream_t)stream>>>(src, ld, rows, cols, dst, ldd,
+                                                                                                       lo, ldl);
+  IMMTSF_CHECK_LAUNCH("transpose_split");
+  return IMMTSF_OK;
 }
 
 // n <= 16 tasks: task i reads src[i] (rows[i] x cols[i], ld_src[i]) and writes a copy to hi[i] (nullable, ld_hi[i])

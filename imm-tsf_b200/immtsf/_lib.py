@@ -38,6 +38,7 @@ SIGNATURES = {
     "immtsf_gemm_ex": [I, I, I, I, I, F, P, I, P, I, P, I, P, I, F, P, I, P, I, P, P, I, I, P, SZ, P],
     "immtsf_split_lo": [P, I, I, I, P, I, P, P],
     "immtsf_gemm_group": [I] + [P] * 19 + [P],
+    "immtsf_transpose_split": [P, I, I, I, P, I, P, I, P],
     "immtsf_multi_split": [I, P, P, P, P, P, P, P, P, P],
     "immtsf_gemm_plan": [I, I, I, I, I, P, I, P, I, P, I, I],
     "immtsf_colsum": [P, I, I, I, P, F, P, P, SZ, P],

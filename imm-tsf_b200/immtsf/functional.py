@@ -231,12 +231,16 @@ class T2VXAttnFoldFn(torch.autograd.Function):
             else:
                 ops.weight_los(lo, [(W_kv, [(slice(None), slice(d, None))])])
             box["ev_x"] = fkw.mark(0)
+            if save:
+                lo.transposed(Wx[:, dm:])  # W_phi^T for d phi = dX W_phi (backward), off the critical path here
 
         def weights_v():  # lane 1: the operand of the second product
             ops.weight_los(lo, [(out_w, []), (in_w, [slice(2 * d, None)])] + ([] if defer else [(W_po, [])]))
             ops.gemm(out_w, W_v, Wvf, lo=lo, emit_lo=Wvf_lo)  # W_o W_v
             ops.gemm(in_b[2 * d:].view(1, d), out_w, bvf.view(1, d), transB=True)  # W_o b_v
             box["ev_v"] = fkw.mark(1)
+            if save:
+                lo.transposed(Wvf)  # (W_o W_v)^T for dX = dV' (W_o W_v) (backward)
 
         def vectors():  # lane 2: biases and the query side
             if has_in:
@@ -329,18 +333,18 @@ class T2VXAttnFoldFn(torch.autograd.Function):
             res["db_o"] = ops.colsum(dx, out=pack_qv[4 * d:5 * d])
             ev["q"] = fk.mark(1)
 
-        def params_value():  # V' = X (W_o W_v)^T + W_o b_v
-            dWvf, dbvf = pack_qv[5 * d:5 * d + d * d].view(d, d), pack_qv[5 * d + d * d:]
+        dWvf, dbvf = pack_qv[5 * d:5 * d + d * d].view(d, d), pack_qv[5 * d + d * d:]
+        dW_o = new(d, d)
+
+        def params_value():  # V' = X (W_o W_v)^T + W_o b_v: the statistics; the un-fold joins the X side's (one grouped launch)
             ops.linear_wgrad(dVf, X, out=dWvf, ragged=r.m_dev, lo=lo, emit_lo=False if dp else new(d, d))
             ops.colsum(dVf, out=dbvf, ragged=r.m_dev)
             if dp:
                 fk.lane_wait(0, ev["q"])
                 ops.dp_allreduce(pack_qv)
                 ev["qv"] = fk.mark(0)
-            dW_o = new(d, d)
-            ops.gemm_group([dict(A=dWvf, B=W_v, C=dW_o, transB=True), dict(A=out_w, B=dWvf, C=d_in_w[2 * d:], transA=True)], lo)
-            ops.gemm(dbvf.view(d, 1), in_b[2 * d:].view(1, d), dW_o, beta=1.0)
             ops.gemm(dbvf.view(1, d), out_w, d_in_b[2 * d:].view(1, d))
+            ev["v"] = fk.mark(0)
             res["dW_o"] = dW_o
 
         def params_query():  # u = W_k^T q,  q = (Qp W_q^T + b_q) scale
@@ -360,7 +364,7 @@ class T2VXAttnFoldFn(torch.autograd.Function):
         fk.run(sums_query, dx, du_partial, pack_qv, lane=1)
         fk.run(params_value, dKVp, pack_qv, d_in_w, d_in_b, lane=0)
         fk.run(params_query, d_in_w, d_in_b, lane=1, after_current=False)
-        dX = ops.gemm(dVf, Wvf, dXk, beta=1.0, ragged=r.m_dev, ragged_dim=1, lo=lo, emit_lo=True)  # + ds (x) u, in place
+        dX = ops.linear_dgrad(dVf, Wvf, out=dXk, beta=1.0, ragged=r.m_dev, lo=lo, emit_lo=True)  # + ds (x) u, in place
         dWx, dbX = pack_x[:d * Kx].view(d, Kx), pack_x[d * Kx:d * Kx + d]
         dWx_lo = new(d, ops.round_up(Kx, 4)) if (has_in and not dp) else False
 
@@ -369,7 +373,7 @@ class T2VXAttnFoldFn(torch.autograd.Function):
             ops.colsum(dX, out=dbX, ragged=r.m_dev)
 
         fk.run(sums_x, dX, pack_x, *([lo.lo_for(dX, r.m_dev)] if fk.side is not None and tc else []), lane=2)
-        dphi = ops.gemm(dX, Wx[:, dm:], new(r.M_alloc, dt), ragged=r.m_dev, ragged_dim=1, lo=lo)
+        dphi = ops.linear_dgrad(dX, Wx[:, dm:], out=new(r.M_alloc, dt), ragged=r.m_dev, lo=lo)
 
         def params_t2v():
             res["t2v"] = ops.time2vec_bwd(dphi, r, w_per, b_per, dt, buf=pack_x[d * Kx + d:])
@@ -377,14 +381,20 @@ class T2VXAttnFoldFn(torch.autograd.Function):
         def params_x():
             if dp:
                 ops.dp_allreduce(pack_x)
+            unfold_v = [dict(A=dWvf, B=W_v, C=dW_o, transB=True), dict(A=out_w, B=dWvf, C=d_in_w[2 * d:], transA=True)]
             if not has_in:
+                fk.lane_wait(2, ev["v"])
+                ops.gemm_group(unfold_v, lo)
+                ops.gemm(dbvf.view(d, 1), in_b[2 * d:].view(1, d), dW_o, beta=1.0)
                 res["dW_kv"], res["db_kv"], res["dW_in"], res["db_in"] = dWx, dbX, None, None
                 return
             dP1 = dWx[:, :dm]
             if dWx_lo is not False:
                 lo.put(dP1, dWx_lo[:, :dm])
             dW_kv, dW_in, db_in = new(d, d + dt), new(d, dm), new(d)
-            ops.gemm_group([dict(A=dP1, B=W_in, C=dW_kv[:, :d], transB=True), dict(A=W_a, B=dP1, C=dW_in, transA=True)], lo)
+            fk.lane_wait(2, ev["v"])  # both weight-space un-folds (four d x d products) in ONE grouped launch
+            ops.gemm_group(unfold_v + [dict(A=dP1, B=W_in, C=dW_kv[:, :d], transB=True), dict(A=W_a, B=dP1, C=dW_in, transA=True)], lo)
+            ops.gemm(dbvf.view(d, 1), in_b[2 * d:].view(1, d), dW_o, beta=1.0)
             ops.gemm(dbX.view(d, 1), b_in.view(1, d), dW_kv[:, :d], beta=1.0)  # W_a b_in also depends on W_a
             ops.gemm(dbX.view(1, d), W_a, db_in.view(1, d))
             ops.multi_split([(dWx[:, dm:], dW_kv[:, d:], None)])

@@ -186,6 +186,21 @@ class LoCache(dict):
             self[key] = e
         return e[1]
 
+    def transposed(self, w: torch.Tensor) -> torch.Tensor:
+        """w^T (contiguous) with its lo registered, made once per step per weight (immtsf_transpose_split): the data-gradient
+        products read it as a K-major operand."""
+        key = (w.data_ptr(), tuple(w.shape), w.stride(0), "T")
+        e = self.get(key)
+        if e is None:
+            rows, cols = w.shape
+            wT = torch.empty(cols, rows, dtype=torch.float32, device=w.device)
+            wT_lo = torch.empty(cols, round_up(rows, 4), dtype=torch.float32, device=w.device)
+            _lib.call("immtsf_transpose_split", _p(w), w.stride(0), rows, cols, _p(wT), wT.stride(0), _p(wT_lo), wT_lo.stride(0), _stream())
+            self.put(wT, wT_lo)
+            e = (w, wT)
+            self[key] = e
+        return e[1]
+
     def put(self, t: torch.Tensor, lo: torch.Tensor):
         """Register a lo that a producer kernel wrote together with t (GEMM epilogue, immtsf_gemm_ex C_lo).  Valid
         for ragged and non-ragged consumers alike: rows past the ragged bound are never live in a product."""
@@ -490,10 +505,15 @@ def linear_fwd(x, w, b, out=None, ragged=None, lo=None, emit_lo=False):
 
 
 def linear_dgrad(dy, w, out=None, ragged=None, beta=0.0, lo=None, emit_lo=False):
-    """dx[M,K] = dy[M,N] w[N,K]."""
+    """dx[M,K] = dy[M,N] w[N,K].  On the tcgen05 path the weight is read TRANSPOSED (K-major, made once per step:
+    LoCache.transposed) -- an MN-major fp32 operand costs the kernel 1.7x on these products."""
     if out is None:
         out = torch.empty(dy.shape[0], w.shape[1], dtype=torch.float32, device=dy.device)
-    return gemm(dy, w, out, beta=beta, ragged=ragged, ragged_dim=1 if ragged is not None else 0, lo=lo, emit_lo=emit_lo)
+    rd = 1 if ragged is not None else 0
+    if (lo is not None and gemm_backend() != BACKEND_FFMA and min(w.shape) >= 64 and dy.shape[0] >= 256 and w.stride(1) == 1
+            and os.environ.get("IMMTSF_DGRAD_T", "1") != "0"):
+        return gemm(dy, lo.transposed(w), out, transB=True, beta=beta, ragged=ragged, ragged_dim=rd, lo=lo, emit_lo=emit_lo)
+    return gemm(dy, w, out, beta=beta, ragged=ragged, ragged_dim=rd, lo=lo, emit_lo=emit_lo)
 
 
 def linear_wgrad(dy, x, out=None, ragged=None, beta=0.0, lo=None, emit_lo=False):

@@ -131,6 +131,11 @@ int immtsf_gemm_group(int n, const int* transA, const int* transB, const int* M,
                       const int* lda_lo, const float* const* B, const float* const* B_lo, const int* ldb,
                       const int* ldb_lo, const float* beta, float* const* C, const int* ldc, float* const* C_lo,
                       const int* ldc_lo, void* stream);
+/* dst [cols, rows] = src^T and (lo != NULL) lo = dst - trunc_tf32(dst): a weight transposed ONCE so that the data-gradient
+ * product dx = dy W reads a K-major operand (the tcgen05 kernel's fast path) instead of an MN-major one. */
+int immtsf_transpose_split(const float* src, int ld, int rows, int cols, float* dst, int ldd, float* lo, int ldl,
+                           void* stream);
+
 /* One launch for up to 16 small tensors (a module's weight matrices): task i reads src[i] (rows[i] x cols[i],
  * leading dimension ld_src[i]) and writes a plain copy to hi[i] (nullable: e.g. a slice of a packed operand) and
  * src - trunc_tf32(src) to lo[i] (nullable).  The arrays are host arrays of length n. */
