@@ -201,7 +201,10 @@ __global__ void __launch_bounds__(256) segattn_fwd_kernel(const SegArgs a) {
 // rows are staged in shared memory once per CTA, and warp w owns query row w -- its pooled row never leaves registers
 // before the LayerNorm statistics (warp shuffles), so the [B*T, d] attention output is written once (saved for backward)
 // and never read back.  Same summation order and lane ownership as the two kernels it replaces: bit-identical results.
-constexpr int SL_TQ = 8;    // query rows per CTA = warps per CTA
+constexpr int SL_TQ = 12;   // query rows per CTA (T 24: two tiles per sample = 512 CTAs, one wave at 4 CTAs per SM)
+constexpr int SL_RW = 3;    // query rows per warp: every staged value chunk read from shared memory feeds all of them (ncu on the
+                            // one-row-per-warp version: short-scoreboard 5.1 per issue -- bound by shared-memory loads)
+constexpr int SL_WARPS = SL_TQ / SL_RW;
 constexpr int SL_NS = 16;   // value rows staged per pass
 
 struct SegLnArgs {
@@ -213,7 +216,7 @@ struct SegLnArgs {
 
 // smem: s_v [SL_NS][d] | s_p [N_max] | s_pt [SL_TQ][N_max]
 template <int NC>
-__global__ void __launch_bounds__(SL_TQ * 32) segattn_ln_fwd_kernel(const SegLnArgs a) {
+__global__ void __launch_bounds__(SL_WARPS * 32) segattn_ln_fwd_kernel(const SegLnArgs a) {
   extern __shared__ __align__(16) float sl_smem[];
   const int d = a.d, d8 = d >> 3, d4 = d >> 2, NM = a.N_max, ld = 2 * d;
   float* s_v = sl_smem;
@@ -222,15 +225,14 @@ __global__ void __launch_bounds__(SL_TQ * 32) segattn_ln_fwd_kernel(const SegLnA
   const int b = blockIdx.y, t0 = blockIdx.x * SL_TQ;
   const int nb = a.offsets[b], nn = a.offsets[b + 1] - nb;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int t = t0 + w;
-  const bool row_ok = t < a.T;
   const float inv_keep = inv_keep_from_thr(a.thr), inv_d = 1.f / (float)d;
   const uint64_t seed = resolve_seed(a.seed);
-  float acc[NC][8];
+  float acc[SL_RW][NC][8];
 #pragma unroll
-  for (int i = 0; i < NC; ++i) zero8(acc[i]);
+  for (int q = 0; q < SL_RW; ++q)
+#pragma unroll
+    for (int i = 0; i < NC; ++i) zero8(acc[q][i]);
   if (nn > 0) {
-    // scores and softmax over the segment (recomputed by every tile of the sample; tile 0 saves the probabilities)
     // the first SL_NS value rows start their way into shared memory now (cp.async) and land while the scores, the softmax and
     // the dropout weights are computed
     {
@@ -246,7 +248,7 @@ __global__ void __launch_bounds__(SL_TQ * 32) segattn_ln_fwd_kernel(const SegLnA
       float4 qv[(NC * 2)];  // this lane's part of the query vector: float4 chunks lane, lane + 32, ...
 #pragma unroll
       for (int j = 0; j < NC * 2; ++j) qv[j] = lane + 32 * j < d4 ? __ldg(reinterpret_cast<const float4*>(a.q) + lane + 32 * j) : f4_zero();
-      for (int n = w; n < nn; n += SL_TQ) {
+      for (int n = w; n < nn; n += SL_WARPS) {
         const float4* kp = reinterpret_cast<const float4*>(a.KVp + (size_t)(nb + n) * ld);
         float sc = 0.f;
 #pragma unroll
@@ -286,7 +288,7 @@ __global__ void __launch_bounds__(SL_TQ * 32) segattn_ln_fwd_kernel(const SegLnA
         p = s_p[n] * dropout_scale(seed, IMMTSF_SITE_TTF_ATTN, ((uint64_t)b * a.T + t0 + tt) * NM + n, a.thr, inv_keep);
       s_pt[tt * NM + n] = p;
     }
-    // pooling: value rows through shared memory, SL_NS at a time; warp w accumulates query row t0 + w
+    // pooling: value rows through shared memory, SL_NS at a time; warp w accumulates query rows t0 + SL_RW w ..
     for (int n0 = 0; n0 < nn; n0 += SL_NS) {
       const int cnt = min(SL_NS, nn - n0);
       __syncthreads();  // (also orders the s_pt writes above before their first use)
@@ -299,68 +301,75 @@ __global__ void __launch_bounds__(SL_TQ * 32) segattn_ln_fwd_kernel(const SegLnA
         asm volatile("cp.async.wait_all;" ::: "memory");
       }
       __syncthreads();
-      if (row_ok) {
-        for (int r = 0; r < cnt; ++r) {
-          const float p = s_pt[w * NM + n0 + r];
+      for (int r = 0; r < cnt; ++r) {
+        float p[SL_RW];
 #pragma unroll
-          for (int i = 0; i < NC; ++i) {
-            const int k = lane + 32 * i;
-            if (k < d8) {
-              const float4 v0 = reinterpret_cast<const float4*>(s_v + (size_t)r * d)[2 * k];
-              const float4 v1 = reinterpret_cast<const float4*>(s_v + (size_t)r * d)[2 * k + 1];
-              acc[i][0] = fmaf(p, v0.x, acc[i][0]); acc[i][1] = fmaf(p, v0.y, acc[i][1]);
-              acc[i][2] = fmaf(p, v0.z, acc[i][2]); acc[i][3] = fmaf(p, v0.w, acc[i][3]);
-              acc[i][4] = fmaf(p, v1.x, acc[i][4]); acc[i][5] = fmaf(p, v1.y, acc[i][5]);
-              acc[i][6] = fmaf(p, v1.z, acc[i][6]); acc[i][7] = fmaf(p, v1.w, acc[i][7]);
+        for (int q = 0; q < SL_RW; ++q) p[q] = s_pt[(w * SL_RW + q) * NM + n0 + r];  // (0 for rows past T)
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+          const int k = lane + 32 * i;
+          if (k < d8) {
+            const float4 v0 = reinterpret_cast<const float4*>(s_v + (size_t)r * d)[2 * k];
+            const float4 v1 = reinterpret_cast<const float4*>(s_v + (size_t)r * d)[2 * k + 1];
+#pragma unroll
+            for (int q = 0; q < SL_RW; ++q) {
+              acc[q][i][0] = fmaf(p[q], v0.x, acc[q][i][0]); acc[q][i][1] = fmaf(p[q], v0.y, acc[q][i][1]);
+              acc[q][i][2] = fmaf(p[q], v0.z, acc[q][i][2]); acc[q][i][3] = fmaf(p[q], v0.w, acc[q][i][3]);
+              acc[q][i][4] = fmaf(p[q], v1.x, acc[q][i][4]); acc[q][i][5] = fmaf(p[q], v1.y, acc[q][i][5]);
+              acc[q][i][6] = fmaf(p[q], v1.z, acc[q][i][6]); acc[q][i][7] = fmaf(p[q], v1.w, acc[q][i][7]);
             }
           }
         }
       }
     }
   }
-  if (!row_ok) return;
-  // the pooled row (saved: LayerNorm backward needs it), then + bias + learned query, LayerNorm, dropout
-  const size_t rowi = (size_t)b * a.T + t;
-  float s = 0.f;
+  // the pooled rows (saved: LayerNorm backward needs them), then + bias + learned query, LayerNorm, dropout
 #pragma unroll
-  for (int i = 0; i < NC; ++i) {
-    const int k = lane + 32 * i;
-    if (k < d8) {
-      store8(a.attn_cat + rowi * d, k, acc[i]);
-      if (nn > 0 && a.xbias) { float tb[8]; load8(a.xbias, k, tb);
+  for (int q = 0; q < SL_RW; ++q) {
+    const int t = t0 + w * SL_RW + q;
+    if (t >= a.T) break;
+    const size_t rowi = (size_t)b * a.T + t;
+    float s = 0.f;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[i][e] += tb[e]; }
-      if (a.res) { float tr[8]; load8(a.res, k, tr);
+    for (int i = 0; i < NC; ++i) {
+      const int k = lane + 32 * i;
+      if (k < d8) {
+        store8(a.attn_cat + rowi * d, k, acc[q][i]);
+        if (nn > 0 && a.xbias) { float tb[8]; load8(a.xbias, k, tb);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[i][e] += tr[e]; }
+          for (int e = 0; e < 8; ++e) acc[q][i][e] += tb[e]; }
+        if (a.res) { float tr[8]; load8(a.res, k, tr);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) s += acc[i][e];
+          for (int e = 0; e < 8; ++e) acc[q][i][e] += tr[e]; }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s += acc[q][i][e];
+      }
     }
-  }
-  const float mu = warp_sum(s) * inv_d;
-  float qv = 0.f;
+    const float mu = warp_sum(s) * inv_d;
+    float qv = 0.f;
 #pragma unroll
-  for (int i = 0; i < NC; ++i)
-    if (lane + 32 * i < d8)
+    for (int i = 0; i < NC; ++i)
+      if (lane + 32 * i < d8)
 #pragma unroll
-      for (int e = 0; e < 8; ++e) qv = fmaf(acc[i][e] - mu, acc[i][e] - mu, qv);
-  const float rs = 1.f / sqrtf(warp_sum(qv) * inv_d + a.eps);
+        for (int e = 0; e < 8; ++e) qv = fmaf(acc[q][i][e] - mu, acc[q][i][e] - mu, qv);
+    const float rs = 1.f / sqrtf(warp_sum(qv) * inv_d + a.eps);
 #pragma unroll
-  for (int i = 0; i < NC; ++i) {
-    const int k = lane + 32 * i;
-    if (k < d8) {
-      float g[8], be[8], ks[8], yv[8];
-      load8(a.gamma, k, g);
-      load8(a.beta, k, be);
-      dropout_scale8(seed, IMMTSF_SITE_TTF_DROPOUT, (uint64_t)rowi * d8 + k, a.thr, inv_keep, ks);
+    for (int i = 0; i < NC; ++i) {
+      const int k = lane + 32 * i;
+      if (k < d8) {
+        float g[8], be[8], ks[8], yv[8];
+        load8(a.gamma, k, g);
+        load8(a.beta, k, be);
+        dropout_scale8(seed, IMMTSF_SITE_TTF_DROPOUT, (uint64_t)rowi * d8 + k, a.thr, inv_keep, ks);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) yv[e] = ((acc[i][e] - mu) * rs * g[e] + be[e]) * ks[e];
-      store8(a.y + rowi * d, k, yv);
+        for (int e = 0; e < 8; ++e) yv[e] = ((acc[q][i][e] - mu) * rs * g[e] + be[e]) * ks[e];
+        store8(a.y + rowi * d, k, yv);
+      }
     }
-  }
-  if (lane == 0) {
-    if (a.mean) a.mean[rowi] = mu;
-    if (a.rstd) a.rstd[rowi] = rs;
+    if (lane == 0) {
+      if (a.mean) a.mean[rowi] = mu;
+      if (a.rstd) a.rstd[rowi] = rs;
+    }
   }
 }
 
@@ -395,10 +404,10 @@ extern "C" int immtsf_segattn_ln_fwd(const float* q, const float* KVp, const int
     attr = true;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  if (nc == 1) segattn_ln_fwd_kernel<1><<<grid, SL_TQ * 32, smem, st>>>(a);
-  else if (nc == 2) segattn_ln_fwd_kernel<2><<<grid, SL_TQ * 32, smem, st>>>(a);
-  else if (nc == 3) segattn_ln_fwd_kernel<3><<<grid, SL_TQ * 32, smem, st>>>(a);
-  else segattn_ln_fwd_kernel<4><<<grid, SL_TQ * 32, smem, st>>>(a);
+  if (nc == 1) segattn_ln_fwd_kernel<1><<<grid, SL_WARPS * 32, smem, st>>>(a);
+  else if (nc == 2) segattn_ln_fwd_kernel<2><<<grid, SL_WARPS * 32, smem, st>>>(a);
+  else if (nc == 3) segattn_ln_fwd_kernel<3><<<grid, SL_WARPS * 32, smem, st>>>(a);
+  else segattn_ln_fwd_kernel<4><<<grid, SL_WARPS * 32, smem, st>>>(a);
   IMMTSF_CHECK_LAUNCH("segattn_ln_fwd");
   return IMMTSF_OK;
 }

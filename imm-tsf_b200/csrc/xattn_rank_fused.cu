@@ -50,29 +50,40 @@ __device__ __forceinline__ bool rows_times_wr(const XfArgs& a, const float* __re
                                               float (*s_r)[XF_NR + 1]) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5, de4 = a.de >> 2;
   bool bad = false;
-  for (int t = w; t < T; t += nw) {
-    float acc[NR];
+  // two rows per pass: both rows' loads are requested before either row's arithmetic (ncu: 4.5 long-scoreboard stalls per
+  // issue with one row in flight), and every Wr chunk read from shared memory feeds both rows
+  for (int t = w; t < T; t += 2 * nw) {
+    const bool two = t + nw < T;
+    float acc0[NR], acc1[NR];
 #pragma unroll
-    for (int c = 0; c < NR; ++c) acc[c] = 0.f;
-    const float4* ep = reinterpret_cast<const float4*>(a.e + (rbase + t) * a.lde);
+    for (int c = 0; c < NR; ++c) { acc0[c] = 0.f; acc1[c] = 0.f; }
+    const float4* ep0 = reinterpret_cast<const float4*>(a.e + (rbase + t) * a.lde);
+    const float4* ep1 = reinterpret_cast<const float4*>(a.e + (rbase + (two ? t + nw : t)) * a.lde);
     for (int k4 = lane; k4 < de4; k4 += 32) {
-      const float4 ev = __ldg(ep + k4);
-      bad |= (ev.x != ev.x) | (ev.y != ev.y) | (ev.z != ev.z) | (ev.w != ev.w);
+      const float4 e0 = __ldg(ep0 + k4);
+      const float4 e1 = __ldg(ep1 + k4);
+      bad |= (e0.x != e0.x) | (e0.y != e0.y) | (e0.z != e0.z) | (e0.w != e0.w) | (e1.x != e1.x) | (e1.y != e1.y) | (e1.z != e1.z) | (e1.w != e1.w);
 #pragma unroll
       for (int c = 0; c < NR; ++c) {
         if (c < nr) {
           const float4 wv = *reinterpret_cast<const float4*>(s_wr + (size_t)c * a.de + 4 * k4);
-          acc[c] = fmaf(ev.x, wv.x, fmaf(ev.y, wv.y, fmaf(ev.z, wv.z, fmaf(ev.w, wv.w, acc[c]))));
+          acc0[c] = fmaf(e0.x, wv.x, fmaf(e0.y, wv.y, fmaf(e0.z, wv.z, fmaf(e0.w, wv.w, acc0[c]))));
+          acc1[c] = fmaf(e1.x, wv.x, fmaf(e1.y, wv.y, fmaf(e1.z, wv.z, fmaf(e1.w, wv.w, acc1[c]))));
         }
       }
     }
 #pragma unroll
     for (int c = 0; c < NR; ++c) {
       if (c < nr) {
-        const float v = warp_sum(acc[c]) + __ldg(a.br + c);
+        const float bc = __ldg(a.br + c);
+        const float v0 = warp_sum(acc0[c]) + bc, v1 = warp_sum(acc1[c]) + bc;
         if (lane == 0) {
-          s_r[t][c] = v;
-          a.r[(rbase + t) * a.ldr + c] = v;
+          s_r[t][c] = v0;
+          a.r[(rbase + t) * a.ldr + c] = v0;
+          if (two) {
+            s_r[t + nw][c] = v1;
+            a.r[(rbase + t + nw) * a.ldr + c] = v1;
+          }
         }
       }
     }

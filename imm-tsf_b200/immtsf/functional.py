@@ -381,23 +381,26 @@ class T2VXAttnFoldFn(torch.autograd.Function):
         def params_x():
             if dp:
                 ops.dp_allreduce(pack_x)
-            unfold_v = [dict(A=dWvf, B=W_v, C=dW_o, transB=True), dict(A=out_w, B=dWvf, C=d_in_w[2 * d:], transA=True)]
+            # the rank-1 bias terms first (K = 1 products, they overwrite), the grouped d x d products then ACCUMULATE onto them:
+            # nothing is left to do after the big launch
+            unfold_v = [dict(A=dWvf, B=W_v, C=dW_o, transB=True, beta=1.0), dict(A=out_w, B=dWvf, C=d_in_w[2 * d:], transA=True)]
             if not has_in:
                 fk.lane_wait(2, ev["v"])
+                ops.gemm(dbvf.view(d, 1), in_b[2 * d:].view(1, d), dW_o)  # W_o b_v also depends on W_o
                 ops.gemm_group(unfold_v, lo)
-                ops.gemm(dbvf.view(d, 1), in_b[2 * d:].view(1, d), dW_o, beta=1.0)
                 res["dW_kv"], res["db_kv"], res["dW_in"], res["db_in"] = dWx, dbX, None, None
                 return
             dP1 = dWx[:, :dm]
             if dWx_lo is not False:
                 lo.put(dP1, dWx_lo[:, :dm])
             dW_kv, dW_in, db_in = new(d, d + dt), new(d, dm), new(d)
-            fk.lane_wait(2, ev["v"])  # both weight-space un-folds (four d x d products) in ONE grouped launch
-            ops.gemm_group(unfold_v + [dict(A=dP1, B=W_in, C=dW_kv[:, :d], transB=True), dict(A=W_a, B=dP1, C=dW_in, transA=True)], lo)
-            ops.gemm(dbvf.view(d, 1), in_b[2 * d:].view(1, d), dW_o, beta=1.0)
-            ops.gemm(dbX.view(d, 1), b_in.view(1, d), dW_kv[:, :d], beta=1.0)  # W_a b_in also depends on W_a
+            ops.gemm(dbX.view(d, 1), b_in.view(1, d), dW_kv[:, :d])  # W_a b_in also depends on W_a
             ops.gemm(dbX.view(1, d), W_a, db_in.view(1, d))
             ops.multi_split([(dWx[:, dm:], dW_kv[:, d:], None)])
+            fk.lane_wait(2, ev["v"])  # the value side's statistics (lane 0) are final
+            ops.gemm(dbvf.view(d, 1), in_b[2 * d:].view(1, d), dW_o)  # W_o b_v also depends on W_o
+            # both weight-space un-folds (four d x d products) in ONE grouped launch
+            ops.gemm_group(unfold_v + [dict(A=dP1, B=W_in, C=dW_kv[:, :d], transB=True, beta=1.0), dict(A=W_a, B=dP1, C=dW_in, transA=True)], lo)
             res["dW_kv"], res["db_kv"], res["dW_in"], res["db_in"] = dW_kv, dbX, dW_in, db_in
 
         if dp:
