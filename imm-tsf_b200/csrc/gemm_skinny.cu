@@ -294,7 +294,9 @@ inline bool al16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 int launch_smalln(const SkArgs& g, cudaStream_t st) {
   // many rows and a B' that fits shared memory: stage it (persistent-style grid, every CTA stages B' once)
   const size_t bbytes = (size_t)g.N * g.K * sizeof(float);
-  if (g.M >= 256 && g.N > 4 && bbytes <= 96 * 1024) {
+  // (staging costs N*K*4 bytes per CTA: at a few hundred rows the staging IS the kernel -- 28.8 us at 768 x 16 x 772 on the cfg1
+  // timeline -- so few-row products take the plain variant below with one row per warp)
+  if (g.M >= 2048 && g.N > 4 && bbytes <= 96 * 1024) {
     static bool attr = false;
     if (!attr) {
       cudaFuncSetAttribute(gemm_smalln_kernel<8, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
@@ -313,7 +315,7 @@ int launch_smalln(const SkArgs& g, cudaStream_t st) {
     return IMMTSF_OK;
   }
   const bool few = g.M < 148 * 16 * 4;  // few rows: one or two rows per warp so that every SM has warps to hide latency
-  const int R = g.N <= 8 ? (few ? (g.M < 148 * 16 * 2 ? 1 : 2) : 4) : (g.N <= 16 ? 2 : 1);
+  const int R = g.N <= 8 ? (few ? (g.M < 148 * 16 * 2 ? 1 : 2) : 4) : (g.N <= 16 && !few ? 2 : 1);
   const int warps = ceil_div(g.M, R);
   int grid = ceil_div(warps, 8);
   if (grid > 148 * 8) grid = 148 * 8;
@@ -323,7 +325,8 @@ int launch_smalln(const SkArgs& g, cudaStream_t st) {
   else if (g.N <= 8 && R == 4) gemm_smalln_kernel<8, 4><<<grid, 256, 0, st>>>(g);
   else if (g.N <= 8 && R == 2) gemm_smalln_kernel<8, 2><<<grid, 256, 0, st>>>(g);
   else if (g.N <= 8) gemm_smalln_kernel<8, 1><<<grid, 256, 0, st>>>(g);
-  else if (g.N <= 16) gemm_smalln_kernel<16, 2><<<grid, 256, 0, st>>>(g);
+  else if (g.N <= 16 && R == 2) gemm_smalln_kernel<16, 2><<<grid, 256, 0, st>>>(g);
+  else if (g.N <= 16) gemm_smalln_kernel<16, 1><<<grid, 256, 0, st>>>(g);
   else gemm_smalln_kernel<32, 1><<<grid, 256, 0, st>>>(g);
   IMMTSF_CHECK_LAUNCH("gemm_smalln");
   return IMMTSF_OK;

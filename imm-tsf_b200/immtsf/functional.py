@@ -54,19 +54,27 @@ class RecAvgFn(torch.autograd.Function):
         ctx.lo = None
         B, d = r.B, W_p.shape[0]
         dE = dE_txt.contiguous().view(B * T, d)
+        fk = ops.Fork(dE.device, name="recavg_bwd")  # weight / bias gradients beside the data-gradient chain
+        res = {"dW_p": None, "db_p": None, "dW_in": None, "db_in": None}
         if ctx.defer:
-            dW_p = db_p = None  # the consumer returns these
-            dE_drop = dE
+            dE_drop = dE  # (the consumer returns dW_p, db_p)
         else:
-            dW_p = ops.linear_wgrad(dE, E_drop.view(B * T, d), lo=lo)
-            db_p = ops.colsum(dE)
+            if lo is not None and ops.gemm_backend() != ops.BACKEND_FFMA and B * T >= 64:
+                lo.lo_for(dE, None)  # read on both streams: split before the fork
+
+            def params_p():
+                res["dW_p"] = ops.linear_wgrad(dE, E_drop.view(B * T, d), lo=lo)
+                res["db_p"] = ops.colsum(dE)
+
+            fk.run(params_p, dE, E_drop)
             dE_drop = ops.linear_dgrad(dE, W_p, lo=lo)
         dVp, dgamma, dbeta, dls = ops.recavg_pool_bwd(dE_drop, E_raw, mean, rstd, wsum, Vp, r, t_hat, log_sigma, gamma, T, d,
                                                       ctx.thr, ctx.seed)
-        dW_in = db_in = None
         if ctx.has_in:
-            dW_in = ops.linear_wgrad(dVp, r.emb_flat, ragged=r.m_dev, lo=lo)
-            db_in = ops.colsum(dVp, ragged=r.m_dev)
+            res["dW_in"] = ops.linear_wgrad(dVp, r.emb_flat, ragged=r.m_dev, lo=lo)
+            res["db_in"] = ops.colsum(dVp, ragged=r.m_dev)
+        fk.join(res["dW_p"], res["db_p"])
+        dW_p, db_p, dW_in, db_in = res["dW_p"], res["db_p"], res["dW_in"], res["db_in"]
         return None, None, None, None, None, None, None, dls, dW_in, db_in, dgamma, dbeta, dW_p, db_p
 
 
@@ -592,20 +600,29 @@ class GRAddFn(torch.autograd.Function):
         d_delta, dh_out, dgamma, dbeta = ops.gr_tail_bwd(dY_out, G4, h_all, W_r, b_r, gamma, beta, m_txt, B, T, C, ctx.thr,
                                                          ctx.seed, dG4)
         dGh = ops.gru_scan_bwd(G4, h_prev, W_hh, b_hh, dh_out, B, T, C, dG4, gates)
-        dW_r = ops.linear_wgrad(d_delta, h_all)
-        db_r = ops.colsum(d_delta)
-        dW_hh = ops.linear_wgrad(dGh, h_prev)
-        db_hh = ops.colsum(dGh)
-        dWcat = ops.linear_wgrad(dG4, X)
-        dbcat = ops.colsum(dG4)
+        fk = ops.Fork(dev, name="gr_bwd")  # every weight / bias gradient beside the data-gradient products (dY, dE)
+        res = {}
+
+        def params():
+            res["dW_r"] = ops.linear_wgrad(d_delta, h_all)
+            res["db_r"] = ops.colsum(d_delta)
+            res["dW_hh"] = ops.linear_wgrad(dGh, h_prev)
+            res["db_hh"] = ops.colsum(dGh)
+            dWcat = ops.linear_wgrad(dG4, X)
+            res["dbcat"] = ops.colsum(dG4)
+            # back to the reference's column order [Y block | E block]
+            dW_ih, dW_g = torch.empty(3 * C, C + d, dtype=_f32, device=dev), torch.empty(C, C + d, dtype=_f32, device=dev)
+            ops.multi_split([(dWcat[:3 * C, d:d + C], dW_ih[:, :C], None), (dWcat[:3 * C, :d], dW_ih[:, C:], None),
+                             (dWcat[3 * C:, d:d + C], dW_g[:, :C], None), (dWcat[3 * C:, :d], dW_g[:, C:], None)])
+            res["dW_ih"], res["dW_g"] = dW_ih, dW_g
+
+        fk.run(params, d_delta, h_all, dGh, h_prev, dG4, X)
         # dY = dY_out (the blend passes Y straight through) + dG4 Wcat[:, Y block] ;  dE = dG4 Wcat[:, E block]
         dY = ops.gemm(dG4, Wcat[:, d:d + C], torch.empty(B * T, C, dtype=_f32, device=dev))
         ops.axpby(dY_out.view(B * T, C), 1.0, dY, True)
         dE = ops.gemm(dG4, Wcat[:, :d], torch.empty(B * T, d, dtype=_f32, device=dev))
-        # back to the reference's column order [Y block | E block]
-        dW_ih, dW_g = torch.empty(3 * C, C + d, dtype=_f32, device=dev), torch.empty(C, C + d, dtype=_f32, device=dev)
-        ops.multi_split([(dWcat[:3 * C, d:d + C], dW_ih[:, :C], None), (dWcat[:3 * C, :d], dW_ih[:, C:], None),
-                         (dWcat[3 * C:, d:d + C], dW_g[:, :C], None), (dWcat[3 * C:, :d], dW_g[:, C:], None)])
+        dW_r, db_r, dW_hh, db_hh, dbcat, dW_ih, dW_g = (res[k] for k in ("dW_r", "db_r", "dW_hh", "db_hh", "dbcat", "dW_ih", "dW_g"))
+        fk.join(dW_r, db_r, dW_hh, db_hh, dbcat, dW_ih, dW_g)
         return (dY.view(B, T, C), dE.view(B, T, d), None, None, None, None, None, dW_ih, dW_hh, dbcat[: 3 * C],
                 db_hh, dW_r, db_r, dW_g, dbcat[3 * C:], dgamma, dbeta)
 

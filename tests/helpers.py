@@ -12,7 +12,7 @@ def golden_names():
     """Fusion-path cases (oracle/make_golden.py); loss_mse.npz (oracle/make_golden_loss.py) and pq_*.npz
     (oracle/make_golden_perquery.py) and store_chunks.npz (oracle/make_golden_store.py) have their own tests."""
     names = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
-    return [n for n in names if not n.startswith(("loss_", "pq_", "store_"))]
+    return [n for n in names if not n.startswith(("loss_", "pq_", "store_", "caller_"))]
 
 
 def load_golden(name):

@@ -212,3 +212,34 @@ def test_launcher_swaps_fusions_under_an_unmodified_script(tmp_path):
     assert os.path.join("imm-tsf_b200", "fusions", "FusionModel.py") in r.stdout
     assert "CTX 1024" in r.stdout and "ARGS ['--x', '1']" in r.stdout
     assert "['TTF_RecAvg', 'TTF_T2V_XAttn', 'TTF_T2V_XAttn_old'] ['MMF_GR_Add', 'MMF_XAttn_Add']" in r.stdout
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="the reference tree exists in the build container only")
+def test_reference_caller_reaches_the_dropin():
+    """lib/evaluation.py:72-164 `compute_all_losses`, imported UNMODIFIED, calls whatever `fusion` object it is given positionally
+    (:95-100).  Handed the drop-in FusionModel on a CPU box it must reach the drop-in's forward -- which refuses CPU tensors
+    (no CPU fallback) -- i.e. the caller-side wiring needs no change.  (The numerical check of this call sequence runs on the
+    GPU: tests/test_gpu_caller.py, against golden vectors produced by this very function with the reference FusionModel.)"""
+    code = r"""
+import sys, types, torch
+sys.path[:0] = ["%(root)s/imm-tsf_b200", "%(root)s/tools", "/root/reference"]
+import run_with_immtsf; run_with_immtsf.install()
+import fusions.load_llm as L; L.register_d_model("TINY", 48)
+from fusions.FusionModel import FusionModel
+import lib.evaluation as E
+assert "imm-tsf_b200" in sys.modules["fusions.FusionModel"].__file__
+a = types.SimpleNamespace(TTF_module="TTF_T2V_XAttn", MMF_module="MMF_XAttn_Add", llm_model_fusion="TINY", llm_layers_fusion=1, max_length=1024,
+                          device="cpu", use_text_embeddings=True, recency_sigma=1.0, dropout=0.0, d_txt=32, n_heads_fusion=1, C=4, kappa=0.5)
+fm = FusionModel(a)
+class M(torch.nn.Module):
+    def forecasting(self, tp, x, t, m): return torch.zeros(tp.shape[0], tp.shape[1], 4)
+b = dict(notes_embeddings=torch.randn(2, 3, 48), tau=torch.rand(2, 3), tp_to_predict=torch.rand(2, 5), observed_data=torch.zeros(2, 4, 4),
+         observed_tp=torch.zeros(2, 4), observed_mask=torch.ones(2, 4, 4), data_to_predict=torch.zeros(2, 5, 4), mask_predicted_data=torch.ones(2, 5, 4))
+try:
+    E.compute_all_losses(M(), fm, b)
+except RuntimeError as e:
+    assert "no CPU fallback" in str(e), e
+    print("REACHED_DROPIN")
+""" % dict(root=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert "REACHED_DROPIN" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]

@@ -19,7 +19,10 @@ PKG = os.path.join(ROOT, "imm-tsf_b200")
 
 
 def install():
-    """Make `import fusions...` resolve to the B200 drop-in for the rest of this process."""
+    """Make `import fusions...` resolve to the B200 drop-in for the rest of this process.  Also switches on the transparent
+    CUDA-graph replay of FusionModel.forward / backward (immtsf/autograph.py) unless IMMTSF_AUTOGRAPH is already set: the
+    reference's loop then runs the fusion path at graph speed without any change to main.py."""
+    os.environ.setdefault("IMMTSF_AUTOGRAPH", "1")
     if PKG not in sys.path:
         sys.path.insert(0, PKG)
     for name in [m for m in sys.modules if m == "fusions" or m.startswith("fusions.")]:
