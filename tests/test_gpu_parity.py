@@ -325,6 +325,9 @@ def test_recavg_bwd_fused_equals_two_kernel(B, N, T, d, p, monkeypatch):
         monkeypatch.setenv("IMMTSF_RECAVG_FUSED_BWD", mode)
         outs[mode] = [x.clone() for x in ops.recavg_pool_bwd(dE, E_raw, mean, rstd, wsum, r.emb_flat, r, t_hat, ls, gamma, T, d, thr, seed)]
     torch.cuda.synchronize()
+    live = (int(r.offsets[B].item()) + 127) // 128 * 128  # rows past roundup(sum N, 128) of dV' are never written (torch.empty)
+    for mode in ("0", "8", "4"):
+        outs[mode][0] = outs[mode][0][:live]
     for mode in ("8", "4"):
         for name, ref, got in zip(("dVp", "dgamma", "dbeta", "dlog_sigma"), outs["0"], outs[mode]):
             assert torch.isfinite(got).all(), (mode, name)
