@@ -20,7 +20,7 @@ namespace {
 constexpr int NV_MAX_WORLD = 16;
 constexpr int NV_MAX_BLOCKS = 32;
 constexpr int NV_THREADS = 512;
-constexpr unsigned long long NV_SPIN_LIMIT = 1ull << 27;  // ~ seconds; then give up and flag the error
+constexpr unsigned long long NV_SPIN_LIMIT = 1ull << 25;  // x (poll + 40 ns back-off) ~ seconds; then give up and flag the error
 
 __device__ __forceinline__ float4 mm_ld_reduce_add(const float* mc) {
   float4 v;
@@ -47,11 +47,17 @@ __device__ __forceinline__ bool rank_barrier(float* const* bases, size_t flag_of
     unsigned int* local = reinterpret_cast<unsigned int*>(bases[rank] + flag_off_floats) + (size_t)blockIdx.x * world + peer;
     unsigned long long spins = 0;
     __threadfence_system();
-    while (atomicCAS_system(remote, 0u, 1u) != 0u)
+    // (the waiting CTAs sit on SMs that other lanes' kernels are using: back off between polls instead of hammering the
+    // issue slots and the NVLink with atomics)
+    while (atomicCAS_system(remote, 0u, 1u) != 0u) {
       if (++spins > NV_SPIN_LIMIT) { s_bad = 1; break; }
+      __nanosleep(40);
+    }
     spins = 0;
-    while (atomicCAS_system(local, 1u, 0u) != 1u)
+    while (atomicCAS_system(local, 1u, 0u) != 1u) {
       if (++spins > NV_SPIN_LIMIT) { s_bad = 1; break; }
+      __nanosleep(40);
+    }
     __threadfence_system();
   }
   __syncthreads();
