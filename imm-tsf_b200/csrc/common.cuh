@@ -84,7 +84,14 @@ struct Philox4 {
   uint32_t x, y, z, w;
 };
 __host__ __device__ __forceinline__ void philox_mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
+#ifdef __CUDA_ARCH__
+  // one IMAD.WIDE.U32 (the C++ form below compiles to IMAD.WIDE plus an add of a zero high word per product: 20 wasted
+  // instructions per Philox call, ~7 % of the instructions of the RecAvg backward's rows phase)
+  uint64_t p;
+  asm("mul.wide.u32 %0, %1, %2;" : "=l"(p) : "r"(a), "r"(b));
+#else
   const uint64_t p = (uint64_t)a * (uint64_t)b;
+#endif
   hi = (uint32_t)(p >> 32);
   lo = (uint32_t)p;
 }
@@ -132,6 +139,39 @@ __device__ __forceinline__ void dropout_scale8(uint64_t seed, uint32_t site, uin
   for (int k = 0; k < 4; ++k) {
     o[2 * k] = (w[k] & 0xFFFFu) >= thr ? inv_keep : 0.f;
     o[2 * k + 1] = (w[k] >> 16) >= thr ? inv_keep : 0.f;
+  }
+}
+
+// Round keys of Philox4x32-10 for one seed (the Weyl sequence of common.cuh's philox4x32_10), computed once per kernel:
+// the key schedule is 20 of the ~85 instructions of a call when it is redone per call.
+struct PhiloxKeys { uint32_t k0[10], k1[10]; };
+__device__ __forceinline__ PhiloxKeys philox_keys(uint64_t seed) {
+  PhiloxKeys k;
+  uint32_t a = (uint32_t)seed, b = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) { k.k0[r] = a; k.k1[r] = b; a += 0x9E3779B9u; b += 0xBB67AE85u; }
+  return k;
+}
+// keep-scales of chunk idx8 with the halves in the lane's order: o[0..3] = the float4 the lane reads first (p = 1: the second
+// one).  Same mask as dropout_scale8 (one Philox4x32-10 call, 16-bit fields against thr); thr == 0 keeps everything
+// (every field >= 0) without a branch.
+__device__ __forceinline__ void dropout_scale8_sw(const PhiloxKeys& key, uint32_t site, uint64_t idx8, uint32_t thr, float inv_keep, int p,
+                                                  float (&o)[8]) {
+  uint32_t c0 = (uint32_t)idx8, c1 = (uint32_t)(idx8 >> 32), c2 = site, c3 = 0u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0, lo0, hi1, lo1;
+    philox_mulhilo(0xD2511F53u, c0, hi0, lo0);
+    philox_mulhilo(0xCD9E8D57u, c2, hi1, lo1);
+    const uint32_t n0 = hi1 ^ c1 ^ key.k0[r], n2 = hi0 ^ c3 ^ key.k1[r];
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+  }
+  const uint32_t w[4] = {p ? c2 : c0, p ? c3 : c1, p ? c0 : c2, p ? c1 : c3};
+  const uint32_t thr_hi = thr << 16;  // (w >> 16) >= thr  <=>  w >= thr << 16 (thr <= 0xFFFF)
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    o[2 * k] = (w[k] << 16) >= thr_hi ? inv_keep : 0.f;
+    o[2 * k + 1] = w[k] >= thr_hi ? inv_keep : 0.f;
   }
 }
 

@@ -35,10 +35,11 @@ struct PoolArgs {
   float* E_drop; float* E_raw; float* mean; float* rstd; float* wsum;
   // backward only
   const float* dE_drop; float* dVp; int lddv; float* dgamma; float* dbeta; double* dlog_sigma; float* dS; int N_max;
+  int flags;  // bit 0: no L2 prefetch in recavg_bwd_mma_kernel (IMMTSF_RECAVG_MMA_NOPF=1, A/B runs)
 };
 
 #ifndef IMMTSF_RECAVG_FUSED_BWD_DEFAULT
-#define IMMTSF_RECAVG_FUSED_BWD_DEFAULT 8  // one-launch backward (232 GPU tests green with it; =0: two-kernel path)
+#define IMMTSF_RECAVG_FUSED_BWD_DEFAULT 1  // one-launch backward (the whole GPU suite is green with it; =0: two-kernel path)
 #endif
 constexpr int POOL_NB = 32;  // notes per shared-memory weight block
 
@@ -286,8 +287,16 @@ __device__ __forceinline__ void rs_bulk_g2s(uint32_t dst, const void* src, uint3
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
                "r"(bytes), "r"(bar) : "memory");
 }
-__device__ __forceinline__ void f4_fma_s(float4& acc, float s, const float4& v) {
+__device__ __forceinline__ void f4_fma_s1(float4& acc, float s, const float4& v) {
   acc.x = fmaf(s, v.x, acc.x); acc.y = fmaf(s, v.y, acc.y); acc.z = fmaf(s, v.z, acc.z); acc.w = fmaf(s, v.w, acc.w);
+}
+// acc += s * v on the packed FP32 pipe: two FFMA2 (sm_100 fma.rn.f32x2: two IEEE fused multiply-adds per instruction,
+// bit-identical to four fmaf) instead of four FFMA -- these kernels are bound by instruction issue, not by FP32 lanes.
+__device__ __forceinline__ void f4_fma_s(float4& acc, float s, const float4& v) {
+  const float2 ss = make_float2(s, s);
+  const float2 lo = __ffma2_rn(ss, make_float2(v.x, v.y), make_float2(acc.x, acc.y));
+  const float2 hi = __ffma2_rn(ss, make_float2(v.z, v.w), make_float2(acc.z, acc.w));
+  acc = make_float4(lo.x, lo.y, hi.x, hi.y);
 }
 
 constexpr int POOL_TB = 32;  // query rows per shared-memory weight block
@@ -610,7 +619,10 @@ __global__ void __launch_bounds__(256) recavg_pool_fwd_w_kernel(const PoolArgs a
 // (p = 1) and keep their halves swapped in registers until the epilogue; every LDS.128 wavefront then covers 8 distinct
 // 16-byte bank groups.
 // smem: s_v [RS][d] (RS <= 32 rows per stage).  grid (ceil(T / (8*TPW)), B), 256 threads.
-template <int NC, int TPW, int MINB, bool FULL>
+// VAR (A/B of the epilogue, IMMTSF_RECAVG_FWD_VAR): 0 = round-1 epilogue (one full Philox call with its key schedule per chunk, scalar
+// arithmetic, scalar pooling FFMAs); 2 = Philox round keys in uniform registers + word-swapped thresholds, scalar arithmetic;
+// 1 = 2 + packed FP32 (FFMA2 / FMUL2 / FADD2) in the pooling loop and the epilogue.
+template <int NC, int TPW, int MINB, bool FULL, int VAR>
 __global__ void __launch_bounds__(256, MINB) recavg_pool_fwd_s_kernel(const PoolArgs a, int RS) {
   extern __shared__ __align__(128) float s_v[];
   __shared__ __align__(8) unsigned long long s_bar;
@@ -623,6 +635,11 @@ __global__ void __launch_bounds__(256, MINB) recavg_pool_fwd_s_kernel(const Pool
   if (threadIdx.x == 0) rs_mbar_init(bar, 1);
   __syncthreads();
   const float inv_sigma = 1.f / expf(__ldg(a.log_sigma));
+  // Philox round keys, computed while control flow is still uniform: they live in uniform registers and are operands of
+  // the epilogue's LOP3s (20 vector registers would spill under this kernel's register caps)
+  const uint64_t seed0 = resolve_seed(a.seed);
+  PhiloxKeys pkey;
+  if (VAR != 0) pkey = philox_keys(seed0);
   const int p = (lane >> 2) & 1;
   float th[TPW], wsum_l[TPW];
   float4 accA[TPW][NC], accB[TPW][NC];
@@ -671,14 +688,16 @@ __global__ void __launch_bounds__(256, MINB) recavg_pool_fwd_s_kernel(const Pool
         for (int q = 0; q < TPW; ++q) {
           const float w0 = __shfl_sync(0xffffffffu, wl[q], j);
 #pragma unroll
-          for (int i = 0; i < NC; ++i) { f4_fma_s(accA[q][i], w0, vA[i]); f4_fma_s(accB[q][i], w0, vB[i]); }
+          for (int i = 0; i < NC; ++i) {
+            if (VAR == 1) { f4_fma_s(accA[q][i], w0, vA[i]); f4_fma_s(accB[q][i], w0, vB[i]); }
+            else { f4_fma_s1(accA[q][i], w0, vA[i]); f4_fma_s1(accB[q][i], w0, vB[i]); }
+          }
         }
       }
     }
   }
   if (!active) return;
   const float inv_keep = inv_keep_from_thr(a.thr);
-  const uint64_t seed = resolve_seed(a.seed);
   const float inv_d = 1.f / (float)a.d;
 #pragma unroll
   for (int q = 0; q < TPW; ++q) {
@@ -686,43 +705,78 @@ __global__ void __launch_bounds__(256, MINB) recavg_pool_fwd_s_kernel(const Pool
     if (t >= a.T) break;
     const float wsum = warp_sum(wsum_l[q]);
     const float inv_den = 1.f / fmaxf(wsum, 1e-6f);  // E_raw = E_wsum / clamp_min(denom, 1e-6)
-    float s = 0.f;
+    float mu, rs;
+    if (VAR == 1) {
+      float2 s2 = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int i = 0; i < NC; ++i) {  // chunks beyond d are exactly 0
-      float4& A = accA[q][i];
-      float4& Bv = accB[q][i];
-      A.x *= inv_den; A.y *= inv_den; A.z *= inv_den; A.w *= inv_den;
-      Bv.x *= inv_den; Bv.y *= inv_den; Bv.z *= inv_den; Bv.w *= inv_den;
-      s += (A.x + A.y) + (A.z + A.w) + (Bv.x + Bv.y) + (Bv.z + Bv.w);
-    }
-    const float mu = warp_sum(s) * inv_d;
-    float qq = 0.f;
-#pragma unroll
-    for (int i = 0; i < NC; ++i)
-      if (FULL || lane + 32 * i < d8) {
-        const float4 A = accA[q][i], Bv = accB[q][i];
-        qq = fmaf(A.x - mu, A.x - mu, qq); qq = fmaf(A.y - mu, A.y - mu, qq); qq = fmaf(A.z - mu, A.z - mu, qq); qq = fmaf(A.w - mu, A.w - mu, qq);
-        qq = fmaf(Bv.x - mu, Bv.x - mu, qq); qq = fmaf(Bv.y - mu, Bv.y - mu, qq); qq = fmaf(Bv.z - mu, Bv.z - mu, qq); qq = fmaf(Bv.w - mu, Bv.w - mu, qq);
+      for (int i = 0; i < NC; ++i) {  // chunks beyond d are exactly 0
+        accA[q][i] = f4_muls(accA[q][i], inv_den);
+        accB[q][i] = f4_muls(accB[q][i], inv_den);
+        f2_acc_sum(s2, accA[q][i]);
+        f2_acc_sum(s2, accB[q][i]);
       }
-    const float rs = 1.f / sqrtf(warp_sum(qq) * inv_d + a.eps);
+      mu = warp_sum(s2.x + s2.y) * inv_d;
+      float2 q2 = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < NC; ++i)
+        if (FULL || lane + 32 * i < d8) {
+          const float4 cA = f4_adds(accA[q][i], -mu), cB = f4_adds(accB[q][i], -mu);
+          f2_acc_dot(q2, cA, cA);
+          f2_acc_dot(q2, cB, cB);
+        }
+      rs = 1.f / sqrtf(warp_sum(q2.x + q2.y) * inv_d + a.eps);
+    } else {
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < NC; ++i) {  // chunks beyond d are exactly 0
+        float4& A = accA[q][i];
+        float4& Bv = accB[q][i];
+        A.x *= inv_den; A.y *= inv_den; A.z *= inv_den; A.w *= inv_den;
+        Bv.x *= inv_den; Bv.y *= inv_den; Bv.z *= inv_den; Bv.w *= inv_den;
+        s += (A.x + A.y) + (A.z + A.w) + (Bv.x + Bv.y) + (Bv.z + Bv.w);
+      }
+      mu = warp_sum(s) * inv_d;
+      float qq = 0.f;
+#pragma unroll
+      for (int i = 0; i < NC; ++i)
+        if (FULL || lane + 32 * i < d8) {
+          const float4 A = accA[q][i], Bv = accB[q][i];
+          qq = fmaf(A.x - mu, A.x - mu, qq); qq = fmaf(A.y - mu, A.y - mu, qq); qq = fmaf(A.z - mu, A.z - mu, qq); qq = fmaf(A.w - mu, A.w - mu, qq);
+          qq = fmaf(Bv.x - mu, Bv.x - mu, qq); qq = fmaf(Bv.y - mu, Bv.y - mu, qq); qq = fmaf(Bv.z - mu, Bv.z - mu, qq); qq = fmaf(Bv.w - mu, Bv.w - mu, qq);
+        }
+      rs = 1.f / sqrtf(warp_sum(qq) * inv_d + a.eps);
+    }
     const size_t rowi = (size_t)b * a.T + t;
+    const uint64_t idx8_0 = rowi * d8 + lane;  // Philox counter of the lane's first chunk of this row
 #pragma unroll
     for (int i = 0; i < NC; ++i) {
       const int k = lane + 32 * i;
       if (FULL || k < d8) {
-        float ks[8];
-        dropout_scale8(seed, IMMTSF_SITE_TTF_DROPOUT, rowi * d8 + k, a.thr, inv_keep, ks);
         const int oA = 2 * k + p, oB = 2 * k + 1 - p;  // float4 index of each half within the row
         const float4 gA = __ldg(reinterpret_cast<const float4*>(a.gamma) + oA), gB = __ldg(reinterpret_cast<const float4*>(a.gamma) + oB);
         const float4 bA = __ldg(reinterpret_cast<const float4*>(a.beta) + oA), bB = __ldg(reinterpret_cast<const float4*>(a.beta) + oB);
         const float4 A = accA[q][i], Bv = accB[q][i];
         float4 kA, kB, yA, yB;
-        kA.x = p ? ks[4] : ks[0]; kA.y = p ? ks[5] : ks[1]; kA.z = p ? ks[6] : ks[2]; kA.w = p ? ks[7] : ks[3];
-        kB.x = p ? ks[0] : ks[4]; kB.y = p ? ks[1] : ks[5]; kB.z = p ? ks[2] : ks[6]; kB.w = p ? ks[3] : ks[7];
-        yA.x = ((A.x - mu) * rs * gA.x + bA.x) * kA.x; yA.y = ((A.y - mu) * rs * gA.y + bA.y) * kA.y;
-        yA.z = ((A.z - mu) * rs * gA.z + bA.z) * kA.z; yA.w = ((A.w - mu) * rs * gA.w + bA.w) * kA.w;
-        yB.x = ((Bv.x - mu) * rs * gB.x + bB.x) * kB.x; yB.y = ((Bv.y - mu) * rs * gB.y + bB.y) * kB.y;
-        yB.z = ((Bv.z - mu) * rs * gB.z + bB.z) * kB.z; yB.w = ((Bv.w - mu) * rs * gB.w + bB.w) * kB.w;
+        if (VAR == 0) {
+          float ks[8];
+          dropout_scale8(seed0, IMMTSF_SITE_TTF_DROPOUT, rowi * d8 + k, a.thr, inv_keep, ks);
+          kA.x = p ? ks[4] : ks[0]; kA.y = p ? ks[5] : ks[1]; kA.z = p ? ks[6] : ks[2]; kA.w = p ? ks[7] : ks[3];
+          kB.x = p ? ks[0] : ks[4]; kB.y = p ? ks[1] : ks[5]; kB.z = p ? ks[2] : ks[6]; kB.w = p ? ks[3] : ks[7];
+        } else {
+          float ks[8];  // the halves in the lane's order (the Philox words are swapped, not the eight scales)
+          dropout_scale8_sw(pkey, IMMTSF_SITE_TTF_DROPOUT, idx8_0 + (uint64_t)(32 * i), a.thr, inv_keep, p, ks);
+          kA = make_float4(ks[0], ks[1], ks[2], ks[3]);
+          kB = make_float4(ks[4], ks[5], ks[6], ks[7]);
+        }
+        if (VAR == 1) {  // ((x - mu) * rstd * gamma + beta) * keep, rounded as the scalar expression
+          yA = f4_mul(f4_fma3(f4_muls(f4_adds(A, -mu), rs), gA, bA), kA);
+          yB = f4_mul(f4_fma3(f4_muls(f4_adds(Bv, -mu), rs), gB, bB), kB);
+        } else {
+          yA.x = ((A.x - mu) * rs * gA.x + bA.x) * kA.x; yA.y = ((A.y - mu) * rs * gA.y + bA.y) * kA.y;
+          yA.z = ((A.z - mu) * rs * gA.z + bA.z) * kA.z; yA.w = ((A.w - mu) * rs * gA.w + bA.w) * kA.w;
+          yB.x = ((Bv.x - mu) * rs * gB.x + bB.x) * kB.x; yB.y = ((Bv.y - mu) * rs * gB.y + bB.y) * kB.y;
+          yB.z = ((Bv.z - mu) * rs * gB.z + bB.z) * kB.z; yB.w = ((Bv.w - mu) * rs * gB.w + bB.w) * kB.w;
+        }
         float4* eo = reinterpret_cast<float4*>(a.E_drop + rowi * a.d);
         eo[oA] = yA;
         eo[oB] = yB;
@@ -741,22 +795,33 @@ __global__ void __launch_bounds__(256, MINB) recavg_pool_fwd_s_kernel(const Pool
   }
 }
 
-template <int NC, int TPW, int MINB, bool FULL>
-static void launch_fwd_s2(const PoolArgs& a, dim3 grid, int RS, size_t smem, cudaStream_t st) {
+template <int NC, int TPW, int MINB, bool FULL, int VAR>
+static void launch_fwd_s3(const PoolArgs& a, dim3 grid, int RS, size_t smem, cudaStream_t st) {
   static size_t smem_set = 0;
   if (smem + 1024 > 48 * 1024 && smem > smem_set) {  // (the kernel also has 128 B of static shared memory)
-    cudaFuncSetAttribute(recavg_pool_fwd_s_kernel<NC, TPW, MINB, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(recavg_pool_fwd_s_kernel<NC, TPW, MINB, FULL, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     smem_set = smem;
   }
-  recavg_pool_fwd_s_kernel<NC, TPW, MINB, FULL><<<grid, 256, smem, st>>>(a, RS);
+  recavg_pool_fwd_s_kernel<NC, TPW, MINB, FULL, VAR><<<grid, 256, smem, st>>>(a, RS);
 }
-// tpw: query times per warp.  3: capped at 128 registers, 2 CTAs per SM (MINB = 2); 2: capped at 80 registers, 3 CTAs per SM (MINB = 3).
+#ifndef IMMTSF_RECAVG_FWD_VAR_DEFAULT
+#define IMMTSF_RECAVG_FWD_VAR_DEFAULT 1
+#endif
+template <int NC, int TPW, int MINB, bool FULL>
+static void launch_fwd_s2(const PoolArgs& a, dim3 grid, int RS, size_t smem, cudaStream_t st) {
+  const char* e = getenv("IMMTSF_RECAVG_FWD_VAR");  // read per call (A/B runs inside one process)
+  const int var = e ? atoi(e) : IMMTSF_RECAVG_FWD_VAR_DEFAULT;
+  if (var == 0) launch_fwd_s3<NC, TPW, MINB, FULL, 0>(a, grid, RS, smem, st);
+  else if (var == 2) launch_fwd_s3<NC, TPW, MINB, FULL, 2>(a, grid, RS, smem, st);
+  else launch_fwd_s3<NC, TPW, MINB, FULL, 1>(a, grid, RS, smem, st);
+}
+// tpw: query times per warp.  3: capped at 128 registers, 2 CTAs per SM (MINB = 2); 1: capped at 80 registers, 3 CTAs per SM (MINB = 3).
 template <int NC>
 static void launch_fwd_s(const PoolArgs& a, int tpw, int T, int B, int RS, size_t smem, cudaStream_t st) {
   const bool full = (a.d >> 3) == 32 * NC;
+  if (tpw != 3) tpw = 1;
   dim3 grid(ceil_div(T, 8 * tpw), B);
   if (tpw == 3) { if (full) launch_fwd_s2<NC, 3, 2, true>(a, grid, RS, smem, st); else launch_fwd_s2<NC, 3, 2, false>(a, grid, RS, smem, st); }
-  else if (tpw == 2) { if (full) launch_fwd_s2<NC, 2, 3, true>(a, grid, RS, smem, st); else launch_fwd_s2<NC, 2, 3, false>(a, grid, RS, smem, st); }
   else { if (full) launch_fwd_s2<NC, 1, 3, true>(a, grid, RS, smem, st); else launch_fwd_s2<NC, 1, 3, false>(a, grid, RS, smem, st); }
 }
 
@@ -961,43 +1026,92 @@ static void launch_rows_s(const PoolArgs& a, int want, cudaStream_t st) {
 // The two-kernel backward writes dS [B*T, d] to HBM and reads it back once per tile of 8 notes (B 2048, N <= 16, T 24, d 768:
 // 151 MB written + up to 302 MB read against 405 MB of algorithmic traffic).  Here a persistent CTA owns one sample at a time and
 // dS never leaves shared memory:
-//   1. one bulk asynchronous copy brings the sample's dE_drop rows [T][d] (contiguous) into s_g; each warp streams its E_raw
-//      rows (t = w, w + 8, ...) through a private one-row buffer with its own mbarrier;
+//   1. per-row bulk asynchronous copies bring the sample's dE_drop rows [T][d] into s_g (one mbarrier per row: a row warp starts
+//      when ITS row has landed); each warp streams its E_raw rows (t = w, w + 8, ...) through a private one-row buffer;
 //   2. rows phase, warp per query row, two passes over shared memory (so that g and x^ need no registers across the warp
 //      reductions): s_g row <- dy*keep*gamma, then s_g row <- dS_t; d(den_t) -> s_dw[t];
 //   3. the warps' dgamma / dbeta partials of the sample are exchanged through the (now idle) E_raw buffers and summed by
-//      column-owner threads into two float4 registers that live for the whole kernel (48 accumulator registers per lane
-//      would not survive the note phase under the 128-register cap);
-//   4. note phase, thread per float4 column, NTN notes per pass: dV'_n = sum_t w_nt dS_t, Q_n = sum_t c_nt dS_t from s_g.
-// Requires T <= POOL_TB, d % 8 == 0, d <= 1024 and (T + 8) * d * 4 bytes of dynamic shared memory (2 CTAs per SM at T 24, d 768).
-__device__ __forceinline__ void sts8(float* row, int k, const float (&v)[8]) {
-  reinterpret_cast<float4*>(row)[2 * k] = make_float4(v[0], v[1], v[2], v[3]);
-  reinterpret_cast<float4*>(row)[2 * k + 1] = make_float4(v[4], v[5], v[6], v[7]);
+//      column-owner threads into shared-memory accumulators that live for the whole kernel;
+//   4. note phase on tensor cores (below).
+// Round 1's version of this kernel (note phase on CUDA cores, one tile barrier, Philox with its key schedule per call) was
+// bound by instruction issue at 16 resident warps (profiles/r1_ncu_recavg_fused_bwd_summary.txt: 41 k warp instructions per
+// sample, 27 % of them the note phase's FFMAs, 18 % Philox, 37 % of the shared-memory wavefronts 2-way bank conflicts); this
+// one executes 26 k (profiles/r2_ncu_recavg_bwd_mma_summary.txt).  What changed:
+//   * the note phase is ONE small matrix product per pass of 8 notes, [w ; c] (16 x T) times dS (T x d), on mma.sync
+//     m16n8k8 TF32 with the 3xTF32 split (lo*hi + hi*lo + hi*hi, fp32 accumulate: fp32-exact to ~1e-6 like the tcgen05
+//     GEMM, and T <= 32 keeps the accumulation chain short).  Rows 0-7 of the A operand are the recency weights w_nt of the
+//     pass's notes, rows 8-15 their log-sigma sensitivities c_nt, so accumulator registers c0,c1 of a lane are dV'_n and c2,c3
+//     are Q_n of the SAME note and columns: the Q_n . V'_n contraction needs no exchange.  A lane's A fragment is (note g =
+//     lane/4, times 8ks + lane%4 and + 4): every lane evaluates its own 2 x T/8 weights -- no s_w / s_c arrays and no CTA
+//     barrier inside the note phase.  ~9 instructions per (8 columns x 8 times) tile instead of 64 FFMA + 5 LDS.128.
+//   * dS rows are padded to d + 8 floats: the B-fragment loads (4 times x 8 columns per instruction) hit 32 distinct banks.
+//   * float8 lane ownership with swapped halves in the rows phase (lanes 4-7 of a quarter warp read the second float4 of
+//     their chunk first, as in recavg_pool_fwd_s_kernel): LDS.128 / STS.128 without bank conflicts.
+//   * L2 prefetch (cp.async.bulk.prefetch.L2) of the sample's own E_raw rows and of the NEXT sample's dE_drop / E_raw when
+//     a sample starts: the per-warp row copies and the next sample's tile copy find their data in L2.
+// Requires T <= POOL_TB, d % 8 == 0, d <= 1024; dynamic shared memory T * (d + 8) * 4 + 8 * d * 4 bytes.
+__device__ __forceinline__ void mma_tf32_m16n8k8(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-template <int NC, int NTN>
-__global__ void __launch_bounds__(256, 2) recavg_bwd_fused_kernel(const PoolArgs a) {
-  static_assert(NTN == 4 || NTN == 8, "notes per pass");
-  extern __shared__ __align__(128) float s_dyn[];  // s_g [T][d] | s_x [8 warps][d]
-  __shared__ __align__(16) float s_w[POOL_TB][NTN];
-  __shared__ __align__(16) float s_c[POOL_TB][NTN];
+// x = hi + lo exactly, hi = x with the 13 low mantissa bits cleared (what a TF32 operand keeps)
+__device__ __forceinline__ void tf32_split(float x, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(x) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void f4_to8(const float4& lo, const float4& hi, float (&o)[8]) {
+  o[0] = lo.x; o[1] = lo.y; o[2] = lo.z; o[3] = lo.w; o[4] = hi.x; o[5] = hi.y; o[6] = hi.z; o[7] = hi.w;
+}
+// one k-step (8 query times) of a warp's 8-column tiles: acc[j] += [w ; c] (16 x 8) x dS (8 x 8), 3xTF32.
+// r0 / r1: the lane's B-fragment rows (times tl and tl + 4 of the k-step) at the warp's first tile.
+template <int NTW, bool GUARD>
+__device__ __forceinline__ void note_tiles(float (&acc)[NTW][4], const uint32_t (&ah)[4], const uint32_t (&al)[4],
+                                           const float* r0, const float* r1, int nlive) {
+#pragma unroll
+  for (int j = 0; j < NTW; ++j) {
+    if (!GUARD || j < nlive) {  // (warp-uniform)
+      uint32_t bh0, bl0, bh1, bl1;
+      tf32_split(r0[8 * j], bh0, bl0);
+      tf32_split(r1[8 * j], bh1, bl1);
+      mma_tf32_m16n8k8(acc[j], al, bh0, bh1);
+      mma_tf32_m16n8k8(acc[j], ah, bl0, bl1);
+      mma_tf32_m16n8k8(acc[j], ah, bh0, bh1);
+    }
+  }
+}
+template <int NC, bool FULL>
+__global__ void __launch_bounds__(256, 2) recavg_bwd_mma_kernel(const PoolArgs a) {
+  constexpr int NTW = 4 * NC;  // 8-column tiles per warp in the note phase (8 warps x NTW x 8 >= 256 * NC >= d)
+  extern __shared__ __align__(128) float s_dyn[];  // s_g [T][d + 8] | s_x [8 warps][d] | s_col [2][d] | s_gamma [d]
   __shared__ float s_dw[POOL_TB];
+  __shared__ float s_th[POOL_TB];
+  __shared__ float s_tau[32];  // the sample's note times (N_max <= 32 on this path)
   __shared__ double s_redd[8];
-  __shared__ __align__(8) unsigned long long s_barg;
-  __shared__ __align__(8) unsigned long long s_barx[8];
-  const int d = a.d, d8 = d >> 3, d4 = d >> 2, T = a.T;
+  __shared__ __align__(8) unsigned long long s_barr[POOL_TB];  // one per dE_drop row
+  __shared__ __align__(8) unsigned long long s_barx[8];        // one per warp (its E_raw row)
+  const int d = a.d, d8 = d >> 3, d4 = d >> 2, T = a.T, ldg = d + 8;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int p = (lane >> 2) & 1;           // rows phase: which half of its float8 chunk the lane reads first
+  const int g = lane >> 2, tl = lane & 3;  // note phase: fragment coordinates
   float* s_g = s_dyn;
-  float* s_x = s_dyn + (size_t)T * d;
+  float* s_x = s_dyn + (size_t)T * ldg;
   float* s_xw = s_x + (size_t)w * d;
-  const uint32_t barg = rs_smem_u32(&s_barg), barx = rs_smem_u32(&s_barx[w]);
-  if (threadIdx.x == 0) rs_mbar_init(barg, 1);
+  float4* s_col4 = reinterpret_cast<float4*>(s_x + (size_t)8 * d);  // dgamma [d] | dbeta [d] of this CTA, over all its samples
+  float4* s_ga4 = s_col4 + 2 * d4;  // gamma (the global loads sat on the rows phase's critical path: 4.5 % of the stall samples)
+  const uint32_t barx = rs_smem_u32(&s_barx[w]);
+  if (threadIdx.x < POOL_TB) rs_mbar_init(rs_smem_u32(&s_barr[threadIdx.x]), 1);
   if (lane == 0) rs_mbar_init(barx, 1);
+  for (int i = threadIdx.x; i < 2 * d4; i += blockDim.x) s_col4[i] = f4_zero();
+  for (int i = threadIdx.x; i < d4; i += blockDim.x) s_ga4[i] = __ldg(reinterpret_cast<const float4*>(a.gamma) + i);
   __syncthreads();
   const float inv_keep = inv_keep_from_thr(a.thr), inv_d = 1.f / (float)d;
-  const uint64_t seed = resolve_seed(a.seed);
-  const float sigma = expf(__ldg(a.log_sigma));
+  const PhiloxKeys pkey = philox_keys(resolve_seed(a.seed));
+  const float inv_sigma = 1.f / expf(__ldg(a.log_sigma));  // (the forward's expression)
   const uint32_t row_bytes = (uint32_t)d * 4u;
-  float4 colg = f4_zero(), colb = f4_zero();  // dgamma / dbeta of float4 column threadIdx.x, over every sample of this CTA
+  const int per = (d8 + 7) >> 3, nt0 = w * per;  // this warp's 8-column tiles: nt0 .. nt0 + nlive - 1 (per <= NTW)
+  const int nlive = max(0, min(per, d8 - nt0));
+  const bool fullw = nlive == NTW;
   double dls = 0.0;
   uint32_t phg = 0, phx = 0;
   for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
@@ -1005,69 +1119,85 @@ __global__ void __launch_bounds__(256, 2) recavg_bwd_fused_kernel(const PoolArgs
     // generic-proxy writes of the previous sample (dS rows, gradient partials) are ordered before the bulk copies below
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
-    if (threadIdx.x == 0) {
-      rs_mbar_expect_tx(barg, (uint32_t)T * row_bytes);
-      rs_bulk_g2s(rs_smem_u32(s_g), a.dE_drop + (size_t)b * T * d, (uint32_t)T * row_bytes, barg);
-      // the sample's V' rows are only needed by the note phase's epilogue: start them towards L2 now
-      if (ne > nb && a.ldv == d)
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.Vp + (size_t)nb * a.ldv), "r"((uint32_t)(ne - nb) * row_bytes) : "memory");
+    if (w == 0) {
+      if (lane < T) {  // one padded row per lane, each on its own barrier: the row warps start as soon as THEIR row has landed
+        const uint32_t bar = rs_smem_u32(&s_barr[lane]);
+        rs_mbar_expect_tx(bar, row_bytes);
+        rs_bulk_g2s(rs_smem_u32(s_g + (size_t)lane * ldg), a.dE_drop + ((size_t)b * T + lane) * d, row_bytes, bar);
+      }
+      if (lane == 0 && !(a.flags & 1)) {
+        if (T > 8)  // rows 8.. of E_raw are copied later, one per warp at a time: have them in L2 by then
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.E_raw + ((size_t)b * T + 8) * d), "r"((uint32_t)(T - 8) * row_bytes) : "memory");
+        if (ne > nb && a.ldv == d)  // V' is only needed by the note phase
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.Vp + (size_t)nb * a.ldv), "r"((uint32_t)(ne - nb) * row_bytes) : "memory");
+        const int bn = b + (int)gridDim.x;
+        if (bn < a.B) {  // the next sample of this CTA
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.dE_drop + (size_t)bn * T * d), "r"((uint32_t)T * row_bytes) : "memory");
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.E_raw + (size_t)bn * T * d), "r"((uint32_t)min(T, 8) * row_bytes) : "memory");
+        }
+      }
     }
     if (w < T && lane == 0) {
       rs_mbar_expect_tx(barx, row_bytes);
       rs_bulk_g2s(rs_smem_u32(s_xw), a.E_raw + ((size_t)b * T + w) * d, row_bytes, barx);
     }
-    float dgam[NC][8], dbet[NC][8];
+    // read by the note phase (after the rows phase's barriers)
+    if (w == 1 && lane < T) s_th[lane] = a.t_hat[(size_t)b * a.t_bstride + lane];
+    if (w == 2 && lane < ne - nb) s_tau[lane] = __ldg(a.tau + nb + lane);
+    float4 dgam[NC][2], dbet[NC][2];  // [chunk][half], halves in the lane's order
 #pragma unroll
-    for (int i = 0; i < NC; ++i) { zero8(dgam[i]); zero8(dbet[i]); }
-    // LayerNorm statistics of the warp's first row are requested before the wait on the copy, the next row's one row ahead
+    for (int i = 0; i < NC; ++i) { dgam[i][0] = f4_zero(); dgam[i][1] = f4_zero(); dbet[i][0] = f4_zero(); dbet[i][1] = f4_zero(); }
     float mu_n = 0.f, rs_n = 0.f, ws_n = 0.f;
     if (w < T) { const size_t r0 = (size_t)b * T + w; mu_n = a.mean[r0]; rs_n = a.rstd[r0]; ws_n = a.wsum[r0]; }
-    rs_mbar_wait(barg, phg);
-    phg ^= 1u;
     for (int t = w; t < T; t += 8) {
       const size_t r = (size_t)b * T + t;
       const float mu = mu_n, rs = rs_n, ws = ws_n;
       if (t + 8 < T) { mu_n = a.mean[r + 8]; rs_n = a.rstd[r + 8]; ws_n = a.wsum[r + 8]; }  // consumed one row later
       const float den = fmaxf(ws, 1e-6f);
-      float* sg = s_g + (size_t)t * d;
+      float4* sg4 = reinterpret_cast<float4*>(s_g + (size_t)t * ldg);
+      const float4* sx4 = reinterpret_cast<const float4*>(s_xw);
+      rs_mbar_wait(rs_smem_u32(&s_barr[t]), phg);
       rs_mbar_wait(barx, phx);
       phx ^= 1u;
-      float p1 = 0.f, p2 = 0.f;
+      const float nmr = -mu * rs;
+      const uint64_t idx8_0 = (uint64_t)r * d8 + lane;  // Philox counter of the lane's first chunk of this row
+      float2 p1 = make_float2(0.f, 0.f), p2 = make_float2(0.f, 0.f);
 #pragma unroll
       for (int i = 0; i < NC; ++i) {
         const int k = lane + 32 * i;
-        if (k < d8) {
-          float dy[8], x[8], ga[8], ks[8], gg[8];
-          lds8(sg, k, dy);
-          lds8(s_xw, k, x);
-          load8(a.gamma, k, ga);
-          dropout_scale8(seed, IMMTSF_SITE_TTF_DROPOUT, (uint64_t)r * d8 + k, a.thr, inv_keep, ks);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const float dye = dy[e] * ks[e];
-            const float he = (x[e] - mu) * rs;
-            dgam[i][e] = fmaf(dye, he, dgam[i][e]);
-            dbet[i][e] += dye;
-            gg[e] = dye * ga[e];
-            p1 += gg[e];
-            p2 = fmaf(gg[e], he, p2);
-          }
-          sts8(sg, k, gg);  // re-read below by this lane only
+        if (FULL || k < d8) {
+          const int fA = 2 * k + p, fB = 2 * k + 1 - p;
+          float ks[8];
+          dropout_scale8_sw(pkey, IMMTSF_SITE_TTF_DROPOUT, idx8_0 + (uint64_t)(32 * i), a.thr, inv_keep, p, ks);
+          // x^ = x * rstd - mu * rstd;  dy~ = dy * keep;  dgamma += dy~ x^;  dbeta += dy~;  g = dy~ gamma;  p1 += g;  p2 += g x^
+          const float4 dyA = f4_mul(sg4[fA], make_float4(ks[0], ks[1], ks[2], ks[3]));
+          const float4 dyB = f4_mul(sg4[fB], make_float4(ks[4], ks[5], ks[6], ks[7]));
+          const float4 hA = f4_fmass(sx4[fA], rs, nmr), hB = f4_fmass(sx4[fB], rs, nmr);
+          dgam[i][0] = f4_fma3(dyA, hA, dgam[i][0]);
+          dgam[i][1] = f4_fma3(dyB, hB, dgam[i][1]);
+          dbet[i][0] = cat4(__fadd2_rn(lo2(dbet[i][0]), lo2(dyA)), __fadd2_rn(hi2(dbet[i][0]), hi2(dyA)));
+          dbet[i][1] = cat4(__fadd2_rn(lo2(dbet[i][1]), lo2(dyB)), __fadd2_rn(hi2(dbet[i][1]), hi2(dyB)));
+          const float4 gA = f4_mul(dyA, s_ga4[fA]), gB = f4_mul(dyB, s_ga4[fB]);
+          f2_acc_sum(p1, gA);
+          f2_acc_sum(p1, gB);
+          f2_acc_dot(p2, gA, hA);
+          f2_acc_dot(p2, gB, hB);
+          sg4[fA] = gA;  // re-read below by this lane only
+          sg4[fB] = gB;
         }
       }
-      const float s2 = warp_sum(p2);
-      const float m1 = warp_sum(p1) * inv_d, m2 = s2 * inv_d;
+      const float s2 = warp_sum(p2.x + p2.y);
+      const float m1 = warp_sum(p1.x + p1.y) * inv_d, m2 = s2 * inv_d;
       const float sc = rs / den;
+      // dE_raw = rstd * (g - mean(g) - xhat * mean(g*xhat)), dS = dE_raw / den:  dS = sc*g + kx*x + k0
+      const float kx = -sc * m2 * rs, k0 = -sc * (m1 + m2 * nmr);
 #pragma unroll
       for (int i = 0; i < NC; ++i) {
         const int k = lane + 32 * i;
-        if (k < d8) {
-          float gg[8], x[8], o[8];  // dE_raw = rstd * (g - mean(g) - xhat * mean(g*xhat));  dS = dE_raw / den
-          lds8(sg, k, gg);
-          lds8(s_xw, k, x);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) o[e] = sc * (gg[e] - m1 - ((x[e] - mu) * rs) * m2);
-          sts8(sg, k, o);
+        if (FULL || k < d8) {
+          const int fA = 2 * k + p, fB = 2 * k + 1 - p;
+          sg4[fA] = f4_fmas(sg4[fA], sc, f4_fmass(sx4[fA], kx, k0));
+          sg4[fB] = f4_fmas(sg4[fB], sc, f4_fmass(sx4[fB], kx, k0));
         }
       }
       // d(den) = -sum_j dE_raw_j E_raw_j / den = -(s2 * eps * rstd^2) / den ; clamp_min passes gradient where wsum >= 1e-6
@@ -1078,93 +1208,102 @@ __global__ void __launch_bounds__(256, 2) recavg_bwd_fused_kernel(const PoolArgs
         rs_bulk_g2s(rs_smem_u32(s_xw), a.E_raw + (r + 8) * d, row_bytes, barx);
       }
     }
+    phg ^= 1u;
     // the warps' dgamma, then dbeta, partials of this sample -> column owners (through the idle E_raw buffers)
     __syncwarp();
+    float4* sxw4 = reinterpret_cast<float4*>(s_xw);
 #pragma unroll
-    for (int i = 0; i < NC; ++i)
-      if (lane + 32 * i < d8) sts8(s_xw, lane + 32 * i, dgam[i]);
-    __syncthreads();  // also: dS and d(den) of every query row are in shared memory
+    for (int i = 0; i < NC; ++i) {
+      const int k = lane + 32 * i;
+      if (FULL || k < d8) {
+        sxw4[2 * k + p] = dgam[i][0];
+        sxw4[2 * k + 1 - p] = dgam[i][1];
+      }
+    }
+    __syncthreads();  // also: dS, d(den) and t_hat of every query row are in shared memory
     if ((int)threadIdx.x < d4) {
+      float4 c = s_col4[threadIdx.x];
 #pragma unroll
-      for (int ww = 0; ww < 8; ++ww) f4_add(colg, reinterpret_cast<const float4*>(s_x + (size_t)ww * d)[threadIdx.x]);
+      for (int ww = 0; ww < 8; ++ww) f4_add(c, reinterpret_cast<const float4*>(s_x + (size_t)ww * d)[threadIdx.x]);
+      s_col4[threadIdx.x] = c;
     }
     __syncthreads();
 #pragma unroll
-    for (int i = 0; i < NC; ++i)
-      if (lane + 32 * i < d8) sts8(s_xw, lane + 32 * i, dbet[i]);
+    for (int i = 0; i < NC; ++i) {
+      const int k = lane + 32 * i;
+      if (FULL || k < d8) {
+        sxw4[2 * k + p] = dbet[i][0];
+        sxw4[2 * k + 1 - p] = dbet[i][1];
+      }
+    }
     __syncthreads();
     if ((int)threadIdx.x < d4) {
+      float4 c = s_col4[d4 + threadIdx.x];
 #pragma unroll
-      for (int ww = 0; ww < 8; ++ww) f4_add(colb, reinterpret_cast<const float4*>(s_x + (size_t)ww * d)[threadIdx.x]);
+      for (int ww = 0; ww < 8; ++ww) f4_add(c, reinterpret_cast<const float4*>(s_x + (size_t)ww * d)[threadIdx.x]);
+      s_col4[d4 + threadIdx.x] = c;
     }
-    // note phase
-    for (int n0 = nb; n0 < ne; n0 += NTN) {
-      const int ncnt = min(NTN, ne - n0);
-      if (n0 != nb) __syncthreads();  // the previous pass has consumed s_w / s_c
-      for (int i = threadIdx.x; i < T * NTN; i += blockDim.x) {
-        const int tt = i / NTN, u = i % NTN;
-        float wv = 0.f, cc = 0.f;
-        if (u < ncnt) {
-          const float delta = fmaxf(a.t_hat[(size_t)b * a.t_bstride + tt] - __ldg(a.tau + n0 + u), 0.f);
-          const float rr = delta / sigma;
-          wv = expf(-(rr * rr));
-          cc = wv * 2.f * rr * rr;
-        }
-        s_w[tt][u] = wv;
-        s_c[tt][u] = cc;
-      }
-      __syncthreads();
-      if (threadIdx.x < NTN) {  // sum_t c_nt d(den_t), thread u owns note u
-        float sc_term = 0.f;
-        for (int tt = 0; tt < T; ++tt) sc_term = fmaf(s_c[tt][threadIdx.x], s_dw[tt], sc_term);
-        dls += (double)sc_term;
-      }
-      if ((int)threadIdx.x < d4) {
-        float4 accw[NTN], accc[NTN];
+    // note phase (reads s_g, s_dw and s_th only; no barrier until the next sample's)
+    for (int n0 = nb; n0 < ne; n0 += 8) {
+      const bool nv = g < ne - n0;  // this lane's note exists
+      const float tn = nv ? s_tau[n0 - nb + g] : 0.f;
+      // lane (g, tl) ends up with dV'_n in acc[j][0..1] and Q_n in acc[j][2..3] of note n0 + g at columns 8 (nt0 + j) + 2 tl, + 1:
+      // its V' values are requested now and used after the products
+      const float* vrow = a.Vp + (size_t)(n0 + (nv ? g : 0)) * a.ldv + 8 * nt0 + 2 * tl;
+      float2 vv[NTW];
 #pragma unroll
-        for (int u = 0; u < NTN; ++u) { accw[u] = f4_zero(); accc[u] = f4_zero(); }
-        const float4* gp = reinterpret_cast<const float4*>(s_g) + threadIdx.x;
-        const bool half = NTN == 8 && ncnt <= 4;  // half-empty pass (CTA-uniform): skip the empty note slots
-        for (int tt = 0; tt < T; ++tt) {
-          const float4 g = gp[(size_t)tt * d4];
-          const float4 w0 = *reinterpret_cast<const float4*>(&s_w[tt][0]), c0 = *reinterpret_cast<const float4*>(&s_c[tt][0]);
-          f4_fma(accw[0], w0.x, g); f4_fma(accc[0], c0.x, g);
-          f4_fma(accw[1], w0.y, g); f4_fma(accc[1], c0.y, g);
-          f4_fma(accw[2], w0.z, g); f4_fma(accc[2], c0.z, g);
-          f4_fma(accw[3], w0.w, g); f4_fma(accc[3], c0.w, g);
-          if (NTN == 8 && !half) {
-            const float4 w1 = *reinterpret_cast<const float4*>(&s_w[tt][NTN - 4]), c1 = *reinterpret_cast<const float4*>(&s_c[tt][NTN - 4]);
-            f4_fma(accw[NTN - 4], w1.x, g); f4_fma(accc[NTN - 4], c1.x, g);
-            f4_fma(accw[NTN - 3], w1.y, g); f4_fma(accc[NTN - 3], c1.y, g);
-            f4_fma(accw[NTN - 2], w1.z, g); f4_fma(accc[NTN - 2], c1.z, g);
-            f4_fma(accw[NTN - 1], w1.w, g); f4_fma(accc[NTN - 1], c1.w, g);
+      for (int j = 0; j < NTW; ++j)
+        vv[j] = (nv && j < nlive) ? __ldg(reinterpret_cast<const float2*>(vrow + 8 * j)) : make_float2(0.f, 0.f);
+      float acc[NTW][4];
+#pragma unroll
+      for (int j = 0; j < NTW; ++j) { acc[j][0] = 0.f; acc[j][1] = 0.f; acc[j][2] = 0.f; acc[j][3] = 0.f; }
+      float scl = 0.f;  // sum_t c_nt d(den_t) over this lane's (note, times)
+#pragma unroll
+      for (int ks = 0; ks < POOL_TB / 8; ++ks) {
+        if (8 * ks < T) {
+          const int t0 = 8 * ks + tl, t1 = t0 + 4;
+          const int t0c = min(t0, T - 1), t1c = min(t1, T - 1);  // rows past T: weight 0 times a finite dS row
+          float w0 = 0.f, c0 = 0.f, w1 = 0.f, c1 = 0.f;
+          if (nv && t0 < T) {
+            const float rr = fmaxf(s_th[t0] - tn, 0.f) * inv_sigma;
+            w0 = expf(-(rr * rr));
+            c0 = w0 * 2.f * rr * rr;
           }
-        }
-        // every V' row of the pass is requested before the first store (stores to dV' may alias as far as the compiler
-        // knows, which serialised one DRAM round trip per note: 15 % of the stall samples of the first version)
-#pragma unroll
-        for (int h0 = 0; h0 < NTN; h0 += 4) {  // four notes at a time (register budget)
-          float4 vv[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
-            vv[u] = h0 + u < ncnt ? __ldg(reinterpret_cast<const float4*>(a.Vp + (size_t)(n0 + h0 + u) * a.ldv) + threadIdx.x) : f4_zero();
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const float4 q = accc[h0 + u], v = vv[u];  // empty slots: q == v == 0
-            dls += (double)q.x * v.x + (double)q.y * v.y + (double)q.z * v.z + (double)q.w * v.w;
+          if (nv && t1 < T) {
+            const float rr = fmaxf(s_th[t1] - tn, 0.f) * inv_sigma;
+            w1 = expf(-(rr * rr));
+            c1 = w1 * 2.f * rr * rr;
           }
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
-            if (h0 + u < ncnt) reinterpret_cast<float4*>(a.dVp + (size_t)(n0 + h0 + u) * a.lddv)[threadIdx.x] = accw[h0 + u];
+          scl = fmaf(c0, s_dw[t0c], fmaf(c1, s_dw[t1c], scl));
+          uint32_t ah[4], al[4];
+          tf32_split(w0, ah[0], al[0]);
+          tf32_split(c0, ah[1], al[1]);
+          tf32_split(w1, ah[2], al[2]);
+          tf32_split(c1, ah[3], al[3]);
+          const float* r0 = s_g + (size_t)t0c * ldg + 8 * nt0 + g;
+          const float* r1 = s_g + (size_t)t1c * ldg + 8 * nt0 + g;
+          if (fullw) note_tiles<NTW, false>(acc, ah, al, r0, r1, NTW);
+          else note_tiles<NTW, true>(acc, ah, al, r0, r1, nlive);
         }
+      }
+      if (w == 0) dls += (double)scl;  // (every warp holds the same A fragments)
+      if (nv) {
+        float* drow = a.dVp + (size_t)(n0 + g) * a.lddv + 8 * nt0 + 2 * tl;
+        float qv = 0.f;
+#pragma unroll
+        for (int j = 0; j < NTW; ++j)
+          if (j < nlive) {
+            qv = fmaf(acc[j][2], vv[j].x, fmaf(acc[j][3], vv[j].y, qv));
+            *reinterpret_cast<float2*>(drow + 8 * j) = make_float2(acc[j][0], acc[j][1]);
+          }
+        dls += (double)qv;
       }
     }
   }
-  if ((int)threadIdx.x < d4) {
-    float* pg = a.dgamma + 4 * threadIdx.x;
-    float* pb = a.dbeta + 4 * threadIdx.x;
-    atomicAdd(pg + 0, colg.x); atomicAdd(pg + 1, colg.y); atomicAdd(pg + 2, colg.z); atomicAdd(pg + 3, colg.w);
-    atomicAdd(pb + 0, colb.x); atomicAdd(pb + 1, colb.y); atomicAdd(pb + 2, colb.z); atomicAdd(pb + 3, colb.w);
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * d; i += blockDim.x) {
+    const float v = reinterpret_cast<const float*>(s_col4)[i];
+    atomicAdd(i < d ? a.dgamma + i : a.dbeta + (i - d), v);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) dls += __shfl_xor_sync(0xffffffffu, dls, o);
@@ -1177,16 +1316,21 @@ __global__ void __launch_bounds__(256, 2) recavg_bwd_fused_kernel(const PoolArgs
   }
 }
 
-template <int NC, int NTN>
-static void launch_bwd_fused(const PoolArgs& a, cudaStream_t st) {
-  const size_t smem = (size_t)(a.T + 8) * a.d * sizeof(float);
+static inline size_t bwd_mma_smem(int T, int d) { return ((size_t)T * (d + 8) + (size_t)11 * d) * sizeof(float); }
+template <int NC, bool FULL>
+static void launch_bwd_mma2(const PoolArgs& a, cudaStream_t st) {
+  const size_t smem = bwd_mma_smem(a.T, a.d);
   static size_t smem_set = 0;
   if (smem + 4096 > 48 * 1024 && smem > smem_set) {
-    cudaFuncSetAttribute(recavg_bwd_fused_kernel<NC, NTN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(recavg_bwd_mma_kernel<NC, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     smem_set = smem;
   }
-  recavg_bwd_fused_kernel<NC, NTN>
-      <<<resident_grid((const void*)recavg_bwd_fused_kernel<NC, NTN>, 256, smem, a.B, 2), 256, smem, st>>>(a);
+  recavg_bwd_mma_kernel<NC, FULL><<<resident_grid((const void*)recavg_bwd_mma_kernel<NC, FULL>, 256, smem, a.B, 2), 256, smem, st>>>(a);
+}
+template <int NC>
+static void launch_bwd_mma(const PoolArgs& a, cudaStream_t st) {
+  if ((a.d >> 3) == 32 * NC) launch_bwd_mma2<NC, true>(a, st);
+  else launch_bwd_mma2<NC, false>(a, st);
 }
 
 static int pool_geometry(int d, int& nch, int& threads) {
@@ -1230,7 +1374,7 @@ extern "C" int immtsf_recavg_pool_fwd(const float* Vp, int ldv, const float* tau
     if (use_tma && ((uintptr_t)Vp & 15) == 0 && (ldv & 3) == 0 && (d & 7) == 0) {
       int tpw_s = (nc <= 3 && T > 16) ? 3 : 1;  // measured (profiles/r1_sweep_hbm_v4.json): T 24: 3 > 1 > 2; T 16: 1 > 2 > 3
       static const int tpw_env = []() { const char* e = getenv("IMMTSF_RECAVG_TPW"); return e ? atoi(e) : 0; }();
-      if (tpw_env >= 1 && tpw_env <= 3 && nc <= 3) tpw_s = tpw_env;
+      if ((tpw_env == 1 || tpw_env == 3) && nc <= 3) tpw_s = tpw_env;
       if (nc == 1) launch_fwd_s<1>(a, tpw_s, T, B, RS, smem_s, st);
       else if (nc == 2) launch_fwd_s<2>(a, tpw_s, T, B, RS, smem_s, st);
       else if (nc == 3) launch_fwd_s<3>(a, tpw_s, T, B, RS, smem_s, st);
@@ -1286,19 +1430,19 @@ extern "C" int immtsf_recavg_pool_bwd(const float* dE_drop, const float* E_raw, 
   const int nc = rowwarp_nc(d);
   // Short prediction windows and segments (N_max <= 32: at N <= 64, T 28 the two-kernel path measured 272 us against 339 us,
   // profiles/r1_sweep_hbm_v6_fused.json): one launch, dS stays in shared memory (IMMTSF_RECAVG_FUSED_BWD=0 keeps the
-  // two-kernel path, =4 / =8 picks the notes per pass).
+  // two-kernel path).
   const char* fused_env = getenv("IMMTSF_RECAVG_FUSED_BWD");  // read per call: tests A/B the two paths inside one process
   const char* tma_env = getenv("IMMTSF_RECAVG_TMA");  // =0 means "no bulk-copy kernels at all": the fused kernel is one
   const int fused = (tma_env && tma_env[0] == '0') ? 0 : (fused_env ? atoi(fused_env) : IMMTSF_RECAVG_FUSED_BWD_DEFAULT);
-  if (fused && nc > 0 && T <= POOL_TB && N_max <= 32 && (size_t)(T + 8) * d * sizeof(float) <= 108 * 1024 && ((uintptr_t)gamma & 15) == 0 &&
+  if (fused && nc > 0 && T <= POOL_TB && N_max <= 32 && bwd_mma_smem(T, d) <= 108 * 1024 && ((uintptr_t)gamma & 15) == 0 &&
       ((uintptr_t)dE_drop & 15) == 0 && ((uintptr_t)E_raw & 15) == 0) {
-#define BWD_F(NCV) do { if (fused == 4) launch_bwd_fused<NCV, 4>(a, st); else launch_bwd_fused<NCV, 8>(a, st); } while (0)
-    if (nc == 1) BWD_F(1);
-    else if (nc == 2) BWD_F(2);
-    else if (nc == 3) BWD_F(3);
-    else BWD_F(4);
-#undef BWD_F
-    IMMTSF_CHECK_LAUNCH("recavg_bwd_fused");
+    const char* nopf = getenv("IMMTSF_RECAVG_MMA_NOPF");
+    a.flags = (nopf && nopf[0] == '1') ? 1 : 0;
+    if (nc == 1) launch_bwd_mma<1>(a, st);
+    else if (nc == 2) launch_bwd_mma<2>(a, st);
+    else if (nc == 3) launch_bwd_mma<3>(a, st);
+    else launch_bwd_mma<4>(a, st);
+    IMMTSF_CHECK_LAUNCH("recavg_bwd_mma");
     return IMMTSF_OK;
   }
   if (nc > 0 && ((uintptr_t)gamma & 15) == 0 && ((uintptr_t)dE_drop & 15) == 0 && ((uintptr_t)E_raw & 15) == 0) {

@@ -37,6 +37,39 @@ __device__ __forceinline__ void f4_add(float4& acc, const float4& v) {
   acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
 }
 
+// ---- packed FP32 (sm_100 FFMA2 / FMUL2 / FADD2: two IEEE operations per issued instruction, each lane rounded like the
+// scalar op).  The row kernels are bound by instruction issue, so their elementwise LayerNorm / dropout arithmetic runs
+// on float4 halves.
+__device__ __forceinline__ float2 lo2(const float4& a) { return make_float2(a.x, a.y); }
+__device__ __forceinline__ float2 hi2(const float4& a) { return make_float2(a.z, a.w); }
+__device__ __forceinline__ float4 cat4(const float2& l, const float2& h) { return make_float4(l.x, l.y, h.x, h.y); }
+__device__ __forceinline__ float2 bc2(float s) { return make_float2(s, s); }
+// a * s
+__device__ __forceinline__ float4 f4_muls(const float4& a, float s) { return cat4(__fmul2_rn(lo2(a), bc2(s)), __fmul2_rn(hi2(a), bc2(s))); }
+// a + s
+__device__ __forceinline__ float4 f4_adds(const float4& a, float s) { return cat4(__fadd2_rn(lo2(a), bc2(s)), __fadd2_rn(hi2(a), bc2(s))); }
+// a * b
+__device__ __forceinline__ float4 f4_mul(const float4& a, const float4& b) { return cat4(__fmul2_rn(lo2(a), lo2(b)), __fmul2_rn(hi2(a), hi2(b))); }
+// a * b + c
+__device__ __forceinline__ float4 f4_fma3(const float4& a, const float4& b, const float4& c) {
+  return cat4(__ffma2_rn(lo2(a), lo2(b), lo2(c)), __ffma2_rn(hi2(a), hi2(b), hi2(c)));
+}
+// a * s + c (s scalar)
+__device__ __forceinline__ float4 f4_fmas(const float4& a, float s, const float4& c) {
+  return cat4(__ffma2_rn(lo2(a), bc2(s), lo2(c)), __ffma2_rn(hi2(a), bc2(s), hi2(c)));
+}
+// a * s + t (s, t scalars)
+__device__ __forceinline__ float4 f4_fmass(const float4& a, float s, float t) {
+  return cat4(__ffma2_rn(lo2(a), bc2(s), bc2(t)), __ffma2_rn(hi2(a), bc2(s), bc2(t)));
+}
+// acc2 += lo(a) + hi(a)  (pairwise partial sums of a row; the caller adds acc2.x + acc2.y at the end)
+__device__ __forceinline__ void f2_acc_sum(float2& acc2, const float4& a) { acc2 = __fadd2_rn(acc2, __fadd2_rn(lo2(a), hi2(a))); }
+// acc2 += lo(a)*lo(b) + hi(a)*hi(b)
+__device__ __forceinline__ void f2_acc_dot(float2& acc2, const float4& a, const float4& b) {
+  acc2 = __ffma2_rn(lo2(a), lo2(b), acc2);
+  acc2 = __ffma2_rn(hi2(a), hi2(b), acc2);
+}
+
 // dropout keep-scales for the 4 consecutive elements whose flat index / 4 == idx4 (half of a Philox call, common.cuh)
 __device__ __forceinline__ float4 dropout_scale4(uint64_t seed, uint32_t site, uint64_t idx4, uint32_t thr, float inv_keep) {
   if (thr == 0u) return make_float4(1.f, 1.f, 1.f, 1.f);

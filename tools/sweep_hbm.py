@@ -44,14 +44,18 @@ def ragged(B, N, d, full, seed=0):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=None)
+    ap.add_argument("--only-recavg", action="store_true", help="the three Time-IMM-sized RecAvg rows only (A/B runs of kernel variants)")
     args = ap.parse_args()
     dev = torch.device("cuda")
     peak, src = peak_hbm()
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
     rows = []
     d = 768
-    for (B, N, T, full) in [(256, 16, 24, False), (2048, 16, 24, False), (2048, 16, 24, True), (1024, 64, 28, False),
-                            (512, 256, 64, False), (64, 1024, 256, False), (4096, 4, 16, False)]:
+    shapes = [(256, 16, 24, False), (2048, 16, 24, False), (2048, 16, 24, True), (1024, 64, 28, False),
+              (512, 256, 64, False), (64, 1024, 256, False), (4096, 4, 16, False)]
+    if args.only_recavg:
+        shapes = [(256, 16, 24, False), (2048, 16, 24, False), (2048, 16, 24, True), (4096, 4, 16, False)]
+    for (B, N, T, full) in shapes:
         notes, tau, sumN = ragged(B, N, d, full)
         r = ops.csr_build(notes, tau)
         t_hat = (0.5 + 0.5 * torch.rand(B, T)).sort(dim=1)[0].cuda()
@@ -81,7 +85,7 @@ def main():
         del notes, tau, r, Vp, E_drop, E_raw, dE, out
         torch.cuda.empty_cache()
     # skinny streaming kernels at the cfg2 / large-batch row counts
-    for M in (6144, 49152):
+    for M in (() if args.only_recavg else (6144, 49152)):
         X = torch.randn(M, d, device=dev)
         W4 = torch.randn(4, d, device=dev)
         Y4 = torch.randn(M, 4, device=dev)
@@ -96,7 +100,7 @@ def main():
             ms = timeit(fn, flush)
             rows.append(dict(kernel=name, rows=M, d=d, ms=ms, alg_bytes=byt, GBps=byt / ms / 1e6, frac=byt / ms / 1e6 / peak))
     # GR_Add scan + tail (latency-bound T-step recurrence)
-    for (B, T, C) in [(256, 24, 4), (2048, 24, 4), (256, 192, 96)]:
+    for (B, T, C) in ([] if args.only_recavg else [(256, 24, 4), (2048, 24, 4), (256, 192, 96)]):
         G4 = torch.randn(B * T, 4 * C, device=dev)
         w_hh, b_hh = torch.randn(3 * C, C, device=dev) * 0.1, torch.zeros(3 * C, device=dev)
         ms = timeit(lambda: ops.gru_scan_fwd(G4, w_hh, b_hh, B, T, C), flush)  # C > 32: wide recurrence
