@@ -71,11 +71,12 @@ TRAFFIC_NCU = 36.26e6
 TRAFFIC_NOTE = ("bytes per launch of the longest GEMM of the cfg2 step, dX = dKVp Wkv (gemm_tc_kernel<0,1,128>, 2134 live of "
                 "4096 rows, N768, K1536), cold L2: dram read 36.23 MB + write 0.03 MB, profiles/r1_ncu_step_gemms_summary.txt "
                 "(algorithmic operand bytes 35.6e6: A and A_lo 26.2 MB, B and B_lo 9.4 MB; the output stays in L2)")
-# recavg_pool_fwd_s_kernel + recavg_bwd_fused_kernel at B 2048, N<=16, T 24, d 768 (ncu --set full, profiles/r1_ncu_recavg_v4_summary.txt and
+# recavg_pool_fwd_s_kernel + recavg_bwd_mma_kernel at B 2048, N<=16, T 24, d 768 (ncu --set full, profiles/r1_ncu_recavg_v4_summary.txt and
 # profiles/r1_ncu_recavg_fused_bwd_summary.txt): dram read + write per launch, summed over the two kernels
-TRAFFIC_RECAVG_NCU = 295.7e6 + 394.9e6
+TRAFFIC_RECAVG_NCU = 295.7e6 + 425.0e6
 TRAFFIC_RECAVG_NOTE = ("dram__bytes_read.sum + dram__bytes_write.sum of the two pooling kernels at B 2048, N<=16, T 24, d 768 (forward 51.8 + 243.9 MB, "
-                       "one-launch backward 394.9 MB; algorithmic 353.7 + 404.9 MB): no re-reads; per launch at that batch, not at this line's batch")
+                       "one-launch backward recavg_bwd_mma_kernel 383.6 + 41.4 MB, profiles/r2_ncu_recavg_bwd_mma_summary.txt; algorithmic 353.7 + 404.9 MB): "
+                       "no re-reads; per launch at that batch, not at this line's batch")
 METRIC = "fused TTF+MMF fwd+bwd throughput"
 UNIT = "samples/s"
 
@@ -684,7 +685,7 @@ def run_gpu_arm(args, w):
         t_ms = sum(sum(hbm_ms[k]) for k in ks)
         byt = sum(hbm_algorithmic_bytes(k, Bl, w["T"], d, w["C"], sumN) * len(hbm_ms[k]) for k in ks)
         achieved = byt / t_ms / 1e6 if t_ms > 0 else 0.0
-        roofline = {"bound": "hbm", "kernel": "recavg_pool_fwd_s_kernel + recavg_bwd_fused_kernel (immtsf_recavg_pool_fwd / _bwd: TMA-staged "
+        roofline = {"bound": "hbm", "kernel": "recavg_pool_fwd_s_kernel + recavg_bwd_mma_kernel (immtsf_recavg_pool_fwd / _bwd: TMA-staged "
                                               "segments, in-register recency weights, fused LayerNorm + dropout; 2 launches/step)",
                     "achieved": achieved, "peak": peaks["hbm"], "unit": "GB/s", "frac": achieved / peaks["hbm"],
                     "traffic": TRAFFIC_RECAVG_NCU, "traffic_note": TRAFFIC_RECAVG_NOTE, "peak_source": peaks["src"],

@@ -35,7 +35,6 @@ struct PoolArgs {
   float* E_drop; float* E_raw; float* mean; float* rstd; float* wsum;
   // backward only
   const float* dE_drop; float* dVp; int lddv; float* dgamma; float* dbeta; double* dlog_sigma; float* dS; int N_max;
-  int flags;  // bit 0: no L2 prefetch in recavg_bwd_mma_kernel (IMMTSF_RECAVG_MMA_NOPF=1, A/B runs)
 };
 
 #ifndef IMMTSF_RECAVG_FUSED_BWD_DEFAULT
@@ -287,16 +286,8 @@ __device__ __forceinline__ void rs_bulk_g2s(uint32_t dst, const void* src, uint3
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
                "r"(bytes), "r"(bar) : "memory");
 }
-__device__ __forceinline__ void f4_fma_s1(float4& acc, float s, const float4& v) {
-  acc.x = fmaf(s, v.x, acc.x); acc.y = fmaf(s, v.y, acc.y); acc.z = fmaf(s, v.z, acc.z); acc.w = fmaf(s, v.w, acc.w);
-}
-// acc += s * v on the packed FP32 pipe: two FFMA2 (sm_100 fma.rn.f32x2: two IEEE fused multiply-adds per instruction,
-// bit-identical to four fmaf) instead of four FFMA -- these kernels are bound by instruction issue, not by FP32 lanes.
 __device__ __forceinline__ void f4_fma_s(float4& acc, float s, const float4& v) {
-  const float2 ss = make_float2(s, s);
-  const float2 lo = __ffma2_rn(ss, make_float2(v.x, v.y), make_float2(acc.x, acc.y));
-  const float2 hi = __ffma2_rn(ss, make_float2(v.z, v.w), make_float2(acc.z, acc.w));
-  acc = make_float4(lo.x, lo.y, hi.x, hi.y);
+  acc.x = fmaf(s, v.x, acc.x); acc.y = fmaf(s, v.y, acc.y); acc.z = fmaf(s, v.z, acc.z); acc.w = fmaf(s, v.w, acc.w);
 }
 
 constexpr int POOL_TB = 32;  // query rows per shared-memory weight block
@@ -619,10 +610,10 @@ __global__ void __launch_bounds__(256) recavg_pool_fwd_w_kernel(const PoolArgs a
 // (p = 1) and keep their halves swapped in registers until the epilogue; every LDS.128 wavefront then covers 8 distinct
 // 16-byte bank groups.
 // smem: s_v [RS][d] (RS <= 32 rows per stage).  grid (ceil(T / (8*TPW)), B), 256 threads.
-// VAR (A/B of the epilogue, IMMTSF_RECAVG_FWD_VAR): 0 = round-1 epilogue (one full Philox call with its key schedule per chunk, scalar
-// arithmetic, scalar pooling FFMAs); 2 = Philox round keys in uniform registers + word-swapped thresholds, scalar arithmetic;
-// 1 = 2 + packed FP32 (FFMA2 / FMUL2 / FADD2) in the pooling loop and the epilogue.
-template <int NC, int TPW, int MINB, bool FULL, int VAR>
+// (Round 2 A/B-ed three other epilogues on a B200 -- Philox round keys in uniform registers, packed FFMA2 / FMUL2 / FADD2
+// arithmetic, both -- which execute 11-20 % fewer instructions and were all 3-11 % SLOWER than this one
+// (profiles/r2_ab_recavg_fwd_bwd.txt); what did help is the mul.wide.u32 in common.cuh's Philox: 106.5 -> 99.4 us.)
+template <int NC, int TPW, int MINB, bool FULL>
 __global__ void __launch_bounds__(256, MINB) recavg_pool_fwd_s_kernel(const PoolArgs a, int RS) {
   extern __shared__ __align__(128) float s_v[];
   __shared__ __align__(8) unsigned long long s_bar;
@@ -635,11 +626,6 @@ __global__ void __launch_bounds__(256, MINB) recavg_pool_fwd_s_kernel(const Pool
   if (threadIdx.x == 0) rs_mbar_init(bar, 1);
   __syncthreads();
   const float inv_sigma = 1.f / expf(__ldg(a.log_sigma));
-  // Philox round keys, computed while control flow is still uniform: they live in uniform registers and are operands of
-  // the epilogue's LOP3s (20 vector registers would spill under this kernel's register caps)
-  const uint64_t seed0 = resolve_seed(a.seed);
-  PhiloxKeys pkey;
-  if (VAR != 0) pkey = philox_keys(seed0);
   const int p = (lane >> 2) & 1;
   float th[TPW], wsum_l[TPW];
   float4 accA[TPW][NC], accB[TPW][NC];
@@ -688,16 +674,14 @@ __global__ void __launch_bounds__(256, MINB) recavg_pool_fwd_s_kernel(const Pool
         for (int q = 0; q < TPW; ++q) {
           const float w0 = __shfl_sync(0xffffffffu, wl[q], j);
 #pragma unroll
-          for (int i = 0; i < NC; ++i) {
-            if (VAR == 1) { f4_fma_s(accA[q][i], w0, vA[i]); f4_fma_s(accB[q][i], w0, vB[i]); }
-            else { f4_fma_s1(accA[q][i], w0, vA[i]); f4_fma_s1(accB[q][i], w0, vB[i]); }
-          }
+          for (int i = 0; i < NC; ++i) { f4_fma_s(accA[q][i], w0, vA[i]); f4_fma_s(accB[q][i], w0, vB[i]); }
         }
       }
     }
   }
   if (!active) return;
   const float inv_keep = inv_keep_from_thr(a.thr);
+  const uint64_t seed = resolve_seed(a.seed);
   const float inv_d = 1.f / (float)a.d;
 #pragma unroll
   for (int q = 0; q < TPW; ++q) {
@@ -705,78 +689,43 @@ __global__ void __launch_bounds__(256, MINB) recavg_pool_fwd_s_kernel(const Pool
     if (t >= a.T) break;
     const float wsum = warp_sum(wsum_l[q]);
     const float inv_den = 1.f / fmaxf(wsum, 1e-6f);  // E_raw = E_wsum / clamp_min(denom, 1e-6)
-    float mu, rs;
-    if (VAR == 1) {
-      float2 s2 = make_float2(0.f, 0.f);
+    float s = 0.f;
 #pragma unroll
-      for (int i = 0; i < NC; ++i) {  // chunks beyond d are exactly 0
-        accA[q][i] = f4_muls(accA[q][i], inv_den);
-        accB[q][i] = f4_muls(accB[q][i], inv_den);
-        f2_acc_sum(s2, accA[q][i]);
-        f2_acc_sum(s2, accB[q][i]);
-      }
-      mu = warp_sum(s2.x + s2.y) * inv_d;
-      float2 q2 = make_float2(0.f, 0.f);
-#pragma unroll
-      for (int i = 0; i < NC; ++i)
-        if (FULL || lane + 32 * i < d8) {
-          const float4 cA = f4_adds(accA[q][i], -mu), cB = f4_adds(accB[q][i], -mu);
-          f2_acc_dot(q2, cA, cA);
-          f2_acc_dot(q2, cB, cB);
-        }
-      rs = 1.f / sqrtf(warp_sum(q2.x + q2.y) * inv_d + a.eps);
-    } else {
-      float s = 0.f;
-#pragma unroll
-      for (int i = 0; i < NC; ++i) {  // chunks beyond d are exactly 0
-        float4& A = accA[q][i];
-        float4& Bv = accB[q][i];
-        A.x *= inv_den; A.y *= inv_den; A.z *= inv_den; A.w *= inv_den;
-        Bv.x *= inv_den; Bv.y *= inv_den; Bv.z *= inv_den; Bv.w *= inv_den;
-        s += (A.x + A.y) + (A.z + A.w) + (Bv.x + Bv.y) + (Bv.z + Bv.w);
-      }
-      mu = warp_sum(s) * inv_d;
-      float qq = 0.f;
-#pragma unroll
-      for (int i = 0; i < NC; ++i)
-        if (FULL || lane + 32 * i < d8) {
-          const float4 A = accA[q][i], Bv = accB[q][i];
-          qq = fmaf(A.x - mu, A.x - mu, qq); qq = fmaf(A.y - mu, A.y - mu, qq); qq = fmaf(A.z - mu, A.z - mu, qq); qq = fmaf(A.w - mu, A.w - mu, qq);
-          qq = fmaf(Bv.x - mu, Bv.x - mu, qq); qq = fmaf(Bv.y - mu, Bv.y - mu, qq); qq = fmaf(Bv.z - mu, Bv.z - mu, qq); qq = fmaf(Bv.w - mu, Bv.w - mu, qq);
-        }
-      rs = 1.f / sqrtf(warp_sum(qq) * inv_d + a.eps);
+    for (int i = 0; i < NC; ++i) {  // chunks beyond d are exactly 0
+      float4& A = accA[q][i];
+      float4& Bv = accB[q][i];
+      A.x *= inv_den; A.y *= inv_den; A.z *= inv_den; A.w *= inv_den;
+      Bv.x *= inv_den; Bv.y *= inv_den; Bv.z *= inv_den; Bv.w *= inv_den;
+      s += (A.x + A.y) + (A.z + A.w) + (Bv.x + Bv.y) + (Bv.z + Bv.w);
     }
+    const float mu = warp_sum(s) * inv_d;
+    float qq = 0.f;
+#pragma unroll
+    for (int i = 0; i < NC; ++i)
+      if (FULL || lane + 32 * i < d8) {
+        const float4 A = accA[q][i], Bv = accB[q][i];
+        qq = fmaf(A.x - mu, A.x - mu, qq); qq = fmaf(A.y - mu, A.y - mu, qq); qq = fmaf(A.z - mu, A.z - mu, qq); qq = fmaf(A.w - mu, A.w - mu, qq);
+        qq = fmaf(Bv.x - mu, Bv.x - mu, qq); qq = fmaf(Bv.y - mu, Bv.y - mu, qq); qq = fmaf(Bv.z - mu, Bv.z - mu, qq); qq = fmaf(Bv.w - mu, Bv.w - mu, qq);
+      }
+    const float rs = 1.f / sqrtf(warp_sum(qq) * inv_d + a.eps);
     const size_t rowi = (size_t)b * a.T + t;
-    const uint64_t idx8_0 = rowi * d8 + lane;  // Philox counter of the lane's first chunk of this row
 #pragma unroll
     for (int i = 0; i < NC; ++i) {
       const int k = lane + 32 * i;
       if (FULL || k < d8) {
+        float ks[8];
+        dropout_scale8(seed, IMMTSF_SITE_TTF_DROPOUT, rowi * d8 + k, a.thr, inv_keep, ks);
         const int oA = 2 * k + p, oB = 2 * k + 1 - p;  // float4 index of each half within the row
         const float4 gA = __ldg(reinterpret_cast<const float4*>(a.gamma) + oA), gB = __ldg(reinterpret_cast<const float4*>(a.gamma) + oB);
         const float4 bA = __ldg(reinterpret_cast<const float4*>(a.beta) + oA), bB = __ldg(reinterpret_cast<const float4*>(a.beta) + oB);
         const float4 A = accA[q][i], Bv = accB[q][i];
         float4 kA, kB, yA, yB;
-        if (VAR == 0) {
-          float ks[8];
-          dropout_scale8(seed0, IMMTSF_SITE_TTF_DROPOUT, rowi * d8 + k, a.thr, inv_keep, ks);
-          kA.x = p ? ks[4] : ks[0]; kA.y = p ? ks[5] : ks[1]; kA.z = p ? ks[6] : ks[2]; kA.w = p ? ks[7] : ks[3];
-          kB.x = p ? ks[0] : ks[4]; kB.y = p ? ks[1] : ks[5]; kB.z = p ? ks[2] : ks[6]; kB.w = p ? ks[3] : ks[7];
-        } else {
-          float ks[8];  // the halves in the lane's order (the Philox words are swapped, not the eight scales)
-          dropout_scale8_sw(pkey, IMMTSF_SITE_TTF_DROPOUT, idx8_0 + (uint64_t)(32 * i), a.thr, inv_keep, p, ks);
-          kA = make_float4(ks[0], ks[1], ks[2], ks[3]);
-          kB = make_float4(ks[4], ks[5], ks[6], ks[7]);
-        }
-        if (VAR == 1) {  // ((x - mu) * rstd * gamma + beta) * keep, rounded as the scalar expression
-          yA = f4_mul(f4_fma3(f4_muls(f4_adds(A, -mu), rs), gA, bA), kA);
-          yB = f4_mul(f4_fma3(f4_muls(f4_adds(Bv, -mu), rs), gB, bB), kB);
-        } else {
-          yA.x = ((A.x - mu) * rs * gA.x + bA.x) * kA.x; yA.y = ((A.y - mu) * rs * gA.y + bA.y) * kA.y;
-          yA.z = ((A.z - mu) * rs * gA.z + bA.z) * kA.z; yA.w = ((A.w - mu) * rs * gA.w + bA.w) * kA.w;
-          yB.x = ((Bv.x - mu) * rs * gB.x + bB.x) * kB.x; yB.y = ((Bv.y - mu) * rs * gB.y + bB.y) * kB.y;
-          yB.z = ((Bv.z - mu) * rs * gB.z + bB.z) * kB.z; yB.w = ((Bv.w - mu) * rs * gB.w + bB.w) * kB.w;
-        }
+        kA.x = p ? ks[4] : ks[0]; kA.y = p ? ks[5] : ks[1]; kA.z = p ? ks[6] : ks[2]; kA.w = p ? ks[7] : ks[3];
+        kB.x = p ? ks[0] : ks[4]; kB.y = p ? ks[1] : ks[5]; kB.z = p ? ks[2] : ks[6]; kB.w = p ? ks[3] : ks[7];
+        yA.x = ((A.x - mu) * rs * gA.x + bA.x) * kA.x; yA.y = ((A.y - mu) * rs * gA.y + bA.y) * kA.y;
+        yA.z = ((A.z - mu) * rs * gA.z + bA.z) * kA.z; yA.w = ((A.w - mu) * rs * gA.w + bA.w) * kA.w;
+        yB.x = ((Bv.x - mu) * rs * gB.x + bB.x) * kB.x; yB.y = ((Bv.y - mu) * rs * gB.y + bB.y) * kB.y;
+        yB.z = ((Bv.z - mu) * rs * gB.z + bB.z) * kB.z; yB.w = ((Bv.w - mu) * rs * gB.w + bB.w) * kB.w;
         float4* eo = reinterpret_cast<float4*>(a.E_drop + rowi * a.d);
         eo[oA] = yA;
         eo[oB] = yB;
@@ -795,25 +744,14 @@ __global__ void __launch_bounds__(256, MINB) recavg_pool_fwd_s_kernel(const Pool
   }
 }
 
-template <int NC, int TPW, int MINB, bool FULL, int VAR>
-static void launch_fwd_s3(const PoolArgs& a, dim3 grid, int RS, size_t smem, cudaStream_t st) {
-  static size_t smem_set = 0;
-  if (smem + 1024 > 48 * 1024 && smem > smem_set) {  // (the kernel also has 128 B of static shared memory)
-    cudaFuncSetAttribute(recavg_pool_fwd_s_kernel<NC, TPW, MINB, FULL, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    smem_set = smem;
-  }
-  recavg_pool_fwd_s_kernel<NC, TPW, MINB, FULL, VAR><<<grid, 256, smem, st>>>(a, RS);
-}
-#ifndef IMMTSF_RECAVG_FWD_VAR_DEFAULT
-#define IMMTSF_RECAVG_FWD_VAR_DEFAULT 1
-#endif
 template <int NC, int TPW, int MINB, bool FULL>
 static void launch_fwd_s2(const PoolArgs& a, dim3 grid, int RS, size_t smem, cudaStream_t st) {
-  const char* e = getenv("IMMTSF_RECAVG_FWD_VAR");  // read per call (A/B runs inside one process)
-  const int var = e ? atoi(e) : IMMTSF_RECAVG_FWD_VAR_DEFAULT;
-  if (var == 0) launch_fwd_s3<NC, TPW, MINB, FULL, 0>(a, grid, RS, smem, st);
-  else if (var == 2) launch_fwd_s3<NC, TPW, MINB, FULL, 2>(a, grid, RS, smem, st);
-  else launch_fwd_s3<NC, TPW, MINB, FULL, 1>(a, grid, RS, smem, st);
+  static size_t smem_set = 0;
+  if (smem + 1024 > 48 * 1024 && smem > smem_set) {  // (the kernel also has 128 B of static shared memory)
+    cudaFuncSetAttribute(recavg_pool_fwd_s_kernel<NC, TPW, MINB, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    smem_set = smem;
+  }
+  recavg_pool_fwd_s_kernel<NC, TPW, MINB, FULL><<<grid, 256, smem, st>>>(a, RS);
 }
 // tpw: query times per warp.  3: capped at 128 registers, 2 CTAs per SM (MINB = 2); 1: capped at 80 registers, 3 CTAs per SM (MINB = 3).
 template <int NC>
@@ -1047,8 +985,8 @@ static void launch_rows_s(const PoolArgs& a, int want, cudaStream_t st) {
 //   * dS rows are padded to d + 8 floats: the B-fragment loads (4 times x 8 columns per instruction) hit 32 distinct banks.
 //   * float8 lane ownership with swapped halves in the rows phase (lanes 4-7 of a quarter warp read the second float4 of
 //     their chunk first, as in recavg_pool_fwd_s_kernel): LDS.128 / STS.128 without bank conflicts.
-//   * L2 prefetch (cp.async.bulk.prefetch.L2) of the sample's own E_raw rows and of the NEXT sample's dE_drop / E_raw when
-//     a sample starts: the per-warp row copies and the next sample's tile copy find their data in L2.
+//   * one mbarrier per dE_drop row, so a row warp starts when ITS row has landed.  (L2 prefetches of the sample's later E_raw rows
+//     and of the next sample's tiles, cp.async.bulk.prefetch.L2, measured neutral to 5 % slower and were removed.)
 // Requires T <= POOL_TB, d % 8 == 0, d <= 1024; dynamic shared memory T * (d + 8) * 4 + 8 * d * 4 bytes.
 __device__ __forceinline__ void mma_tf32_m16n8k8(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -1083,10 +1021,9 @@ __device__ __forceinline__ void note_tiles(float (&acc)[NTW][4], const uint32_t 
 template <int NC, bool FULL>
 __global__ void __launch_bounds__(256, 2) recavg_bwd_mma_kernel(const PoolArgs a) {
   constexpr int NTW = 4 * NC;  // 8-column tiles per warp in the note phase (8 warps x NTW x 8 >= 256 * NC >= d)
-  extern __shared__ __align__(128) float s_dyn[];  // s_g [T][d + 8] | s_x [8 warps][d] | s_col [2][d] | s_gamma [d]
+  extern __shared__ __align__(128) float s_dyn[];  // s_g [T][d + 8] | s_x [8 warps][d] | s_col [2][d]
   __shared__ float s_dw[POOL_TB];
   __shared__ float s_th[POOL_TB];
-  __shared__ float s_tau[32];  // the sample's note times (N_max <= 32 on this path)
   __shared__ double s_redd[8];
   __shared__ __align__(8) unsigned long long s_barr[POOL_TB];  // one per dE_drop row
   __shared__ __align__(8) unsigned long long s_barx[8];        // one per warp (its E_raw row)
@@ -1098,15 +1035,13 @@ __global__ void __launch_bounds__(256, 2) recavg_bwd_mma_kernel(const PoolArgs a
   float* s_x = s_dyn + (size_t)T * ldg;
   float* s_xw = s_x + (size_t)w * d;
   float4* s_col4 = reinterpret_cast<float4*>(s_x + (size_t)8 * d);  // dgamma [d] | dbeta [d] of this CTA, over all its samples
-  float4* s_ga4 = s_col4 + 2 * d4;  // gamma (the global loads sat on the rows phase's critical path: 4.5 % of the stall samples)
   const uint32_t barx = rs_smem_u32(&s_barx[w]);
   if (threadIdx.x < POOL_TB) rs_mbar_init(rs_smem_u32(&s_barr[threadIdx.x]), 1);
   if (lane == 0) rs_mbar_init(barx, 1);
   for (int i = threadIdx.x; i < 2 * d4; i += blockDim.x) s_col4[i] = f4_zero();
-  for (int i = threadIdx.x; i < d4; i += blockDim.x) s_ga4[i] = __ldg(reinterpret_cast<const float4*>(a.gamma) + i);
   __syncthreads();
   const float inv_keep = inv_keep_from_thr(a.thr), inv_d = 1.f / (float)d;
-  const PhiloxKeys pkey = philox_keys(resolve_seed(a.seed));
+  const PhiloxKeys pkey = philox_keys(resolve_seed(a.seed));  // uniform registers: operands of the rows phase's LOP3s
   const float inv_sigma = 1.f / expf(__ldg(a.log_sigma));  // (the forward's expression)
   const uint32_t row_bytes = (uint32_t)d * 4u;
   const int per = (d8 + 7) >> 3, nt0 = w * per;  // this warp's 8-column tiles: nt0 .. nt0 + nlive - 1 (per <= NTW)
@@ -1125,17 +1060,6 @@ __global__ void __launch_bounds__(256, 2) recavg_bwd_mma_kernel(const PoolArgs a
         rs_mbar_expect_tx(bar, row_bytes);
         rs_bulk_g2s(rs_smem_u32(s_g + (size_t)lane * ldg), a.dE_drop + ((size_t)b * T + lane) * d, row_bytes, bar);
       }
-      if (lane == 0 && !(a.flags & 1)) {
-        if (T > 8)  // rows 8.. of E_raw are copied later, one per warp at a time: have them in L2 by then
-          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.E_raw + ((size_t)b * T + 8) * d), "r"((uint32_t)(T - 8) * row_bytes) : "memory");
-        if (ne > nb && a.ldv == d)  // V' is only needed by the note phase
-          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.Vp + (size_t)nb * a.ldv), "r"((uint32_t)(ne - nb) * row_bytes) : "memory");
-        const int bn = b + (int)gridDim.x;
-        if (bn < a.B) {  // the next sample of this CTA
-          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.dE_drop + (size_t)bn * T * d), "r"((uint32_t)T * row_bytes) : "memory");
-          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.E_raw + (size_t)bn * T * d), "r"((uint32_t)min(T, 8) * row_bytes) : "memory");
-        }
-      }
     }
     if (w < T && lane == 0) {
       rs_mbar_expect_tx(barx, row_bytes);
@@ -1143,7 +1067,6 @@ __global__ void __launch_bounds__(256, 2) recavg_bwd_mma_kernel(const PoolArgs a
     }
     // read by the note phase (after the rows phase's barriers)
     if (w == 1 && lane < T) s_th[lane] = a.t_hat[(size_t)b * a.t_bstride + lane];
-    if (w == 2 && lane < ne - nb) s_tau[lane] = __ldg(a.tau + nb + lane);
     float4 dgam[NC][2], dbet[NC][2];  // [chunk][half], halves in the lane's order
 #pragma unroll
     for (int i = 0; i < NC; ++i) { dgam[i][0] = f4_zero(); dgam[i][1] = f4_zero(); dbet[i][0] = f4_zero(); dbet[i][1] = f4_zero(); }
@@ -1156,6 +1079,7 @@ __global__ void __launch_bounds__(256, 2) recavg_bwd_mma_kernel(const PoolArgs a
       const float den = fmaxf(ws, 1e-6f);
       float4* sg4 = reinterpret_cast<float4*>(s_g + (size_t)t * ldg);
       const float4* sx4 = reinterpret_cast<const float4*>(s_xw);
+      const float4* ga4 = reinterpret_cast<const float4*>(a.gamma);
       rs_mbar_wait(rs_smem_u32(&s_barr[t]), phg);
       rs_mbar_wait(barx, phx);
       phx ^= 1u;
@@ -1177,7 +1101,7 @@ __global__ void __launch_bounds__(256, 2) recavg_bwd_mma_kernel(const PoolArgs a
           dgam[i][1] = f4_fma3(dyB, hB, dgam[i][1]);
           dbet[i][0] = cat4(__fadd2_rn(lo2(dbet[i][0]), lo2(dyA)), __fadd2_rn(hi2(dbet[i][0]), hi2(dyA)));
           dbet[i][1] = cat4(__fadd2_rn(lo2(dbet[i][1]), lo2(dyB)), __fadd2_rn(hi2(dbet[i][1]), hi2(dyB)));
-          const float4 gA = f4_mul(dyA, s_ga4[fA]), gB = f4_mul(dyB, s_ga4[fB]);
+          const float4 gA = f4_mul(dyA, __ldg(ga4 + fA)), gB = f4_mul(dyB, __ldg(ga4 + fB));
           f2_acc_sum(p1, gA);
           f2_acc_sum(p1, gB);
           f2_acc_dot(p2, gA, hA);
@@ -1246,7 +1170,7 @@ __global__ void __launch_bounds__(256, 2) recavg_bwd_mma_kernel(const PoolArgs a
     // note phase (reads s_g, s_dw and s_th only; no barrier until the next sample's)
     for (int n0 = nb; n0 < ne; n0 += 8) {
       const bool nv = g < ne - n0;  // this lane's note exists
-      const float tn = nv ? s_tau[n0 - nb + g] : 0.f;
+      const float tn = nv ? __ldg(a.tau + n0 + g) : 0.f;
       // lane (g, tl) ends up with dV'_n in acc[j][0..1] and Q_n in acc[j][2..3] of note n0 + g at columns 8 (nt0 + j) + 2 tl, + 1:
       // its V' values are requested now and used after the products
       const float* vrow = a.Vp + (size_t)(n0 + (nv ? g : 0)) * a.ldv + 8 * nt0 + 2 * tl;
@@ -1316,7 +1240,7 @@ __global__ void __launch_bounds__(256, 2) recavg_bwd_mma_kernel(const PoolArgs a
   }
 }
 
-static inline size_t bwd_mma_smem(int T, int d) { return ((size_t)T * (d + 8) + (size_t)11 * d) * sizeof(float); }
+static inline size_t bwd_mma_smem(int T, int d) { return ((size_t)T * (d + 8) + (size_t)10 * d) * sizeof(float); }
 template <int NC, bool FULL>
 static void launch_bwd_mma2(const PoolArgs& a, cudaStream_t st) {
   const size_t smem = bwd_mma_smem(a.T, a.d);
@@ -1436,8 +1360,6 @@ extern "C" int immtsf_recavg_pool_bwd(const float* dE_drop, const float* E_raw, 
   const int fused = (tma_env && tma_env[0] == '0') ? 0 : (fused_env ? atoi(fused_env) : IMMTSF_RECAVG_FUSED_BWD_DEFAULT);
   if (fused && nc > 0 && T <= POOL_TB && N_max <= 32 && bwd_mma_smem(T, d) <= 108 * 1024 && ((uintptr_t)gamma & 15) == 0 &&
       ((uintptr_t)dE_drop & 15) == 0 && ((uintptr_t)E_raw & 15) == 0) {
-    const char* nopf = getenv("IMMTSF_RECAVG_MMA_NOPF");
-    a.flags = (nopf && nopf[0] == '1') ? 1 : 0;
     if (nc == 1) launch_bwd_mma<1>(a, st);
     else if (nc == 2) launch_bwd_mma<2>(a, st);
     else if (nc == 3) launch_bwd_mma<3>(a, st);

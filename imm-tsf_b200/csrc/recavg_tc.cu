@@ -4,7 +4,8 @@
 // N, T ~ 64 that is tensor-core work, not a streaming kernel.  The products run on immtsf_gemm_batched
 // (3xTF32, fp32-exact to ~1e-6); this file supplies what surrounds them:
 //   immtsf_recavg_weights : Wn[b,t,n] = w_nt / max(sum_n w_nt, 1e-6)  (and Cn = c_nt / den, c_nt = w_nt 2 (delta/sigma)^2,
-//                           csum[b,t] = sum_n Cn) as dense [B, T, Np] operands, zero beyond the sample's N_i notes
+//                           csum[b,t] = sum_n Cn) as dense [B, T, Np] operands, zero beyond the sample's N_i notes;
+//                           the producers also write the operands' lo parts (x - trunc_tf32(x)): no separate split pass
 //   immtsf_csr_to_padded  : V' rows of the ragged layout -> [B, Np, d], zero rows beyond N_i (uniform batch strides for the
 //                           4-D tensor maps of the batched product)
 //   immtsf_padded_to_csr  : the inverse, for dV'
@@ -16,11 +17,15 @@
 
 namespace {
 
+// the lo operand of the 3xTF32 products: x - trunc_tf32(x) (what immtsf_split_lo writes), made by the producer of x
+__device__ __forceinline__ float tf32_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+
 // one warp per (sample, query time) row of the weight matrices
 __global__ void __launch_bounds__(256) recavg_weights_kernel(const float* __restrict__ tau, const int32_t* __restrict__ offsets,
                                                              const float* __restrict__ t_hat, int t_bstride,
                                                              const float* __restrict__ log_sigma, int B, int T, int Np,
                                                              float* __restrict__ Wn, float* __restrict__ Cn,
+                                                             float* __restrict__ Wn_lo, float* __restrict__ Cn_lo,
                                                              float* __restrict__ wsum, float* __restrict__ csum) {
   const int lane = threadIdx.x & 31;
   const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -47,7 +52,9 @@ __global__ void __launch_bounds__(256) recavg_weights_kernel(const float* __rest
       c = w * 2.f * r * r;
     }
     wrow[n] = w;
+    if (Wn_lo) Wn_lo[row * Np + n] = tf32_lo(w);
     if (crow) crow[n] = c;
+    if (Cn_lo) Cn_lo[row * Np + n] = tf32_lo(c);
     cs += c;
   }
   if (lane == 0 && wsum) wsum[row] = ws;
@@ -59,7 +66,7 @@ __global__ void __launch_bounds__(256) recavg_weights_kernel(const float* __rest
 
 // dst[b, n, :] = n < N_b ? src[offsets[b] + n, :] : 0      (float4 columns; grid-stride over B * Np rows)
 __global__ void __launch_bounds__(256) csr_to_padded_kernel(const float* __restrict__ src, int lds, const int32_t* __restrict__ offsets,
-                                                            int B, int Np, int d4, float* __restrict__ dst) {
+                                                            int B, int Np, int d4, float* __restrict__ dst, float* __restrict__ dst_lo) {
   const long total = (long)B * Np * d4;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const long rowp = i / d4;
@@ -68,6 +75,7 @@ __global__ void __launch_bounds__(256) csr_to_padded_kernel(const float* __restr
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (n < cnt) v = __ldg(reinterpret_cast<const float4*>(src + (size_t)(nb + n) * lds) + c);
     reinterpret_cast<float4*>(dst)[i] = v;
+    if (dst_lo) reinterpret_cast<float4*>(dst_lo)[i] = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
   }
 }
 
@@ -120,27 +128,27 @@ __global__ void __launch_bounds__(256) recavg_dls_kernel(const float* __restrict
 }  // namespace
 
 extern "C" int immtsf_recavg_weights(const float* tau_flat, const int32_t* offsets, const float* t_hat, int t_hat_bstride,
-                                     const float* log_sigma, int B, int T, int Np, float* Wn, float* Cn, float* wsum,
-                                     float* csum, void* stream) {
+                                     const float* log_sigma, int B, int T, int Np, float* Wn, float* Cn, float* Wn_lo,
+                                     float* Cn_lo, float* wsum, float* csum, void* stream) {
   if (B <= 0 || T <= 0 || Np <= 0) return IMMTSF_OK;
   IMMTSF_REQUIRE(tau_flat && offsets && t_hat && log_sigma && Wn, "recavg_weights: null pointer");
   IMMTSF_REQUIRE((Cn == nullptr) == (csum == nullptr), "recavg_weights: Cn and csum go together");
   const long rows = (long)B * T;
   recavg_weights_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(tau_flat, offsets, t_hat, t_hat_bstride, log_sigma,
-                                                                                     B, T, Np, Wn, Cn, wsum, csum);
+                                                                                     B, T, Np, Wn, Cn, Wn_lo, Cn_lo, wsum, csum);
   IMMTSF_CHECK_LAUNCH("recavg_weights");
   return IMMTSF_OK;
 }
 
 extern "C" int immtsf_csr_to_padded(const float* src, int lds, const int32_t* offsets, int B, int Np, int d, float* dst,
-                                    void* stream) {
+                                    float* dst_lo, void* stream) {
   if (B <= 0 || Np <= 0 || d <= 0) return IMMTSF_OK;
   IMMTSF_REQUIRE(src && offsets && dst, "csr_to_padded: null pointer");
-  IMMTSF_REQUIRE((d & 3) == 0 && (lds & 3) == 0 && ((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0,
+  IMMTSF_REQUIRE((d & 3) == 0 && (lds & 3) == 0 && ((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0 && ((uintptr_t)dst_lo & 15) == 0,
                  "csr_to_padded: d and lds must be multiples of 4, pointers 16B aligned");
   const long total = (long)B * Np * (d >> 2);
   const int grid = (int)((total + 255) / 256 < 148L * 16 ? (total + 255) / 256 : 148L * 16);
-  csr_to_padded_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, lds, offsets, B, Np, d >> 2, dst);
+  csr_to_padded_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, lds, offsets, B, Np, d >> 2, dst, dst_lo);
   IMMTSF_CHECK_LAUNCH("csr_to_padded");
   return IMMTSF_OK;
 }

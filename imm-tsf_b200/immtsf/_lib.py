@@ -44,6 +44,10 @@ SIGNATURES = {
     "immtsf_colsum": [P, I, I, I, P, F, P, P, SZ, P],
     "immtsf_recavg_pool_fwd": [P, I, P, P, P, I, P, P, P, I, I, I, I, F, U32, U64, P, P, P, P, P, P],
     "immtsf_recavg_pool_bwd": [P, P, P, P, P, P, I, P, P, P, I, P, P, I, I, I, I, U32, U64, P, P, I, P, P, P, P],
+    "immtsf_recavg_weights": [P, P, P, I, P, I, I, I, P, P, P, P, P, P, P],
+    "immtsf_csr_to_padded": [P, I, P, I, I, I, P, P, P],
+    "immtsf_padded_to_csr": [P, P, I, I, I, P, I, P],
+    "immtsf_recavg_dls": [P, P, P, P, L, I, P, P],
     "immtsf_time2vec_fwd": [P, P, P, P, P, I, P, I, P, I, P, I, P],
     "immtsf_time2vec_bwd": [P, I, P, P, P, I, P, P, P, P, P, I, P],
     "immtsf_segattn_fwd": [P, P, P, I, I, I, I, I, I, U32, U64, P, P, P],

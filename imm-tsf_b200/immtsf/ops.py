@@ -545,10 +545,91 @@ def group_sum_rows(x, R, T, d):
 
 
 # ------------------------------------------------------------------ RecAvg pooling
+# Long segments x long windows: the pooling is dense matrix work -> tcgen05.  Selection measured on a B200 against the
+# streaming kernels (profiles/r2_ab_recavg_fwd_bwd.txt): the forward wins at N 1024 x T 64 (1.4x), N 256 x T 256 (1.75x) and
+# N 1024 x T 256 (2.8x) and ties at N 256 x T 64; the backward (its dV' product contracts over T only) wins at
+# N 1024 x T 256 (1.43x) and loses at N 256 x T 256 and N 1024 x T 64.
+RECAVG_TC_FWD_MIN = (256, 64, 65536)    # N_max >=, T >=, N_max * T >=
+RECAVG_TC_BWD_MIN = (512, 128, 262144)
+
+
+def recavg_tc_ok(r: RaggedNotes, Vp, T: int, d: int, backward: bool = False) -> bool:
+    """The pooling of TTF_RecAvg.py:100 as batched tcgen05 products (csrc/recavg_tc.cu + immtsf_gemm_batched)
+    (IMMTSF_RECAVG_TC=0 keeps the streaming kernels, =1 forces this path for any size)."""
+    e = os.environ.get("IMMTSF_RECAVG_TC")
+    if e == "0" or gemm_backend() == BACKEND_FFMA:
+        return False
+    ok = d % 4 == 0 and Vp.stride(0) % 4 == 0 and Vp.data_ptr() % 16 == 0 and r.B <= 65535 and r.N >= 1
+    if e == "1":
+        return ok
+    n_min, t_min, nt_min = RECAVG_TC_BWD_MIN if backward else RECAVG_TC_FWD_MIN
+    return ok and r.N >= n_min and T >= t_min and r.N * T >= nt_min
+
+
+def _recavg_tc_operands(Vp, r: RaggedNotes, t_hat, log_sigma, T, d, with_c: bool):
+    """Dense operands of the batched products and a LoCache that already holds their lo parts (written by the producers)."""
+    B, Np = r.B, round_up(r.N, 4)
+    dev = Vp.device
+    f32 = torch.float32
+    new = lambda *s: torch.empty(*s, dtype=f32, device=dev)
+    Wn, Wn_lo = new(B, T, Np), new(B, T, Np)
+    Cn, Cn_lo = (new(B, T, Np), new(B, T, Np)) if with_c else (None, None)
+    wsum = new(B, T)
+    csum = new(B, T) if with_c else None
+    bstride = 0 if t_hat.dim() == 1 else t_hat.stride(0)
+    _lib.call("immtsf_recavg_weights", _p(r.tau_flat), _p(r.offsets), _p(t_hat), bstride, _p(log_sigma), B, T, Np, _p(Wn), _p(Cn),
+              _p(Wn_lo), _p(Cn_lo), _p(wsum), _p(csum), _stream())
+    Vpad, Vpad_lo = new(B, Np, d), new(B, Np, d)
+    _lib.call("immtsf_csr_to_padded", _p(Vp), Vp.stride(0), _p(r.offsets), B, Np, d, _p(Vpad), _p(Vpad_lo), _stream())
+    lo = LoCache()
+    for t, t_lo in ((Wn, Wn_lo), (Cn, Cn_lo), (Vpad, Vpad_lo)):
+        if t is not None:
+            lo[(t.data_ptr(), t.numel(), "flat")] = (t, t_lo)  # the key _flat_lo looks up (contiguous operands: extent = numel)
+    return Np, Wn, Cn, wsum, csum, Vpad, lo
+
+
+def _recavg_pool_fwd_tc(Vp, r: RaggedNotes, t_hat, log_sigma, gamma, beta, T, d, thr, seed, save):
+    """E_raw[b] = Wn[b] [T x Np] . V'pad[b] [Np x d] on tcgen05 (Wn carries the 1 / clamp_min(denominator, 1e-6) of
+    TTF_RecAvg.py:101-102), then dropout(LayerNorm(.)) with the streaming LayerNorm kernel (same dropout site and element
+    indices as the fused kernels: identical masks)."""
+    B = r.B
+    Np, Wn, _, wsum, _, Vpad, lo = _recavg_tc_operands(Vp, r, t_hat, log_sigma, T, d, False)
+    E_raw = torch.empty(B, T, d, dtype=torch.float32, device=Vp.device)
+    gemm_batched(Wn, Vpad, E_raw, T, d, Np, (Np, T * Np, 0), (d, Np * d, 0), (d, T * d, 0), B, 1, lo=lo)
+    E_drop, mean, rstd = ln_fwd(E_raw.view(B * T, d), None, None, T, gamma, beta, thr, seed, SITE_TTF_DROPOUT, save)
+    if not save:
+        return E_drop.view(B, T, d), None, None, None, None
+    return E_drop.view(B, T, d), E_raw, mean.view(B, T), rstd.view(B, T), wsum
+
+
+def _recavg_pool_bwd_tc(dE_drop, E_raw, mean, rstd, wsum, Vp, r: RaggedNotes, t_hat, log_sigma, gamma, T, d, thr, seed):
+    """dE_raw = LayerNorm/dropout backward (streaming kernel); dV'pad[b] = Wn[b]^T dE_raw[b]; with Cn = Wn 2 (delta/sigma)^2 and
+    R[b] = Cn[b] V'pad[b]:  dlog_sigma = sum dE_raw (R - csum E_raw)  (csrc/recavg_tc.cu).  Two batched tcgen05 products,
+    nothing of size N x T x d is formed."""
+    B = r.B
+    dev = Vp.device
+    f32 = torch.float32
+    dE_raw, _, dgamma, dbeta = ln_bwd(dE_drop.reshape(B * T, d), E_raw.view(B * T, d), None, None, T, gamma, mean.reshape(B * T),
+                                      rstd.reshape(B * T), thr, seed, SITE_TTF_DROPOUT)
+    Np, Wn, Cn, _, csum, Vpad, lo = _recavg_tc_operands(Vp, r, t_hat, log_sigma, T, d, True)
+    dVpad = torch.empty(B, Np, d, dtype=f32, device=dev)
+    gemm_batched(Wn, dE_raw, dVpad, Np, d, T, (Np, T * Np, 0), (d, T * d, 0), (d, Np * d, 0), B, 1, transA=True, lo=lo)
+    R = torch.empty(B, T, d, dtype=f32, device=dev)
+    gemm_batched(Cn, Vpad, R, T, d, Np, (Np, T * Np, 0), (d, Np * d, 0), (d, T * d, 0), B, 1, lo=lo)
+    dVp = torch.empty(r.M_alloc, d, dtype=f32, device=dev)
+    _lib.call("immtsf_padded_to_csr", _p(dVpad), _p(r.offsets), B, Np, d, _p(dVp), d, _stream())
+    zero_pad_rows(dVp, d, r.m_dev, r.M_alloc)
+    dls = torch.zeros((), dtype=torch.float64, device=dev)
+    _lib.call("immtsf_recavg_dls", _p(dE_raw), _p(R), _p(E_raw), _p(csum), B * T, d, _p(dls), _stream())
+    return dVp, dgamma, dbeta, dls.float()
+
+
 def recavg_pool_fwd(Vp, r: RaggedNotes, t_hat, log_sigma, gamma, beta, T, d, thr, seed, save):
     B = r.B
     _chk(t_hat, "t_hat")
     dev = Vp.device
+    if recavg_tc_ok(r, Vp, T, d):
+        return _recavg_pool_fwd_tc(Vp, r, t_hat, log_sigma, gamma, beta, T, d, thr, seed, save)
     E_drop = torch.empty(B, T, d, dtype=torch.float32, device=dev)
     E_raw = torch.empty(B, T, d, dtype=torch.float32, device=dev) if save else None
     mean = torch.empty(B, T, dtype=torch.float32, device=dev) if save else None
@@ -563,6 +644,8 @@ def recavg_pool_fwd(Vp, r: RaggedNotes, t_hat, log_sigma, gamma, beta, T, d, thr
 
 def recavg_pool_bwd(dE_drop, E_raw, mean, rstd, wsum, Vp, r: RaggedNotes, t_hat, log_sigma, gamma, T, d, thr, seed):
     dev = Vp.device
+    if recavg_tc_ok(r, Vp, T, d, backward=True):
+        return _recavg_pool_bwd_tc(dE_drop, E_raw, mean, rstd, wsum, Vp, r, t_hat, log_sigma, gamma, T, d, thr, seed)
     dVp = torch.empty(r.M_alloc, d, dtype=torch.float32, device=dev)
     dS = torch.empty(r.B * T * (d + 1), dtype=torch.float32, device=dev)  # rows [B*T, d] + one scalar per row
     dgamma = torch.zeros(d, dtype=torch.float32, device=dev)

@@ -169,6 +169,24 @@ int immtsf_recavg_pool_bwd(const float* dE_drop, const float* E_raw, const float
                            uint32_t drop_thr, uint64_t seed, float* dS, float* dVp, int lddv, float* dgamma,
                            float* dbeta, double* dlog_sigma, void* stream);
 
+/* ---- K2 at long segments x long windows (N_max, T >= 64): the pooling of TTF_RecAvg.py:100 is a dense [T x N_i] . [N_i x d]
+ * product per sample and runs on immtsf_gemm_batched (tcgen05, 3xTF32); these are the kernels around it
+ * (csrc/recavg_tc.cu).  Np = N_max rounded up to a multiple of 4 (the contraction / leading dimension).
+ *   recavg_weights: Wn [B, T, Np] = w_nt / max(sum_n w_nt, 1e-6) (zero for n >= N_b); wsum [B*T] (nullable) = sum_n w_nt;
+ *                   Cn [B, T, Np] (nullable, with csum [B*T]) = Wn * 2 (delta/sigma)^2, csum = sum_n Cn.
+ *   Wn_lo / Cn_lo / dst_lo (nullable, same shapes): the operands' 3xTF32 lo parts x - trunc_tf32(x), written by the producer.
+ *   csr_to_padded / padded_to_csr: ragged rows <-> [B, Np, d] with zero rows beyond N_b.
+ *   recavg_dls: *dlog_sigma (double, accumulated) += sum_{r,j} dE_raw[r,j] (R[r,j] - csum[r] E_raw[r,j]), R = Cn V'. */
+int immtsf_recavg_weights(const float* tau_flat, const int32_t* offsets, const float* t_hat, int t_hat_bstride,
+                          const float* log_sigma, int B, int T, int Np, float* Wn, float* Cn, float* Wn_lo,
+                          float* Cn_lo, float* wsum, float* csum, void* stream);
+int immtsf_csr_to_padded(const float* src, int lds, const int32_t* offsets, int B, int Np, int d, float* dst,
+                         float* dst_lo, void* stream);
+int immtsf_padded_to_csr(const float* src, const int32_t* offsets, int B, int Np, int d, float* dst, int ldd,
+                         void* stream);
+int immtsf_recavg_dls(const float* dE_raw, const float* R, const float* E_raw, const float* csum, long rows, int d,
+                      double* dlog_sigma, void* stream);
+
 /* ---- Time2Vec (TTF_T2V_XAttn.py:20-24,136) written straight into the
  * [V' ; phi] concat buffer (:139); out_lo (nullable): phi - trunc_tf32(phi) into the
  * matching columns of that buffer's tcgen05 lo operand ------------------- */

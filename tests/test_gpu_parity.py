@@ -306,7 +306,7 @@ def test_recavg_properties_full_size():
 def test_recavg_bwd_fused_equals_two_kernel(B, N, T, d, p, monkeypatch):
     """The one-launch backward (dS kept in shared memory, note phase on mma.sync 3xTF32; the default, IMMTSF_RECAVG_FUSED_BWD=1)
     against the two-kernel backward (=0) on the same inputs: same formulas, only the summation order of dgamma / dbeta /
-    dlog_sigma and the 3xTF32 split of dV' differ; also with the L2 prefetches off (IMMTSF_RECAVG_MMA_NOPF=1).
+    dlog_sigma and the 3xTF32 split of dV' differ.
     Includes T < 8 (idle row warps), N > 8 (several note passes), N > 32 (both modes take the two-kernel path), a sample
     without notes, d not a multiple of 256."""
     from immtsf import ops
@@ -322,15 +322,14 @@ def test_recavg_bwd_fused_equals_two_kernel(B, N, T, d, p, monkeypatch):
     E_drop, E_raw, mean, rstd, wsum = ops.recavg_pool_fwd(r.emb_flat, r, t_hat, ls, gamma, beta, T, d, thr, seed, True)
     dE = torch.randn(B, T, d, generator=g).cuda().view_as(E_drop)
     outs = {}
-    for mode in ("0", "1", "nopf"):
-        monkeypatch.setenv("IMMTSF_RECAVG_FUSED_BWD", "0" if mode == "0" else "1")
-        monkeypatch.setenv("IMMTSF_RECAVG_MMA_NOPF", "1" if mode == "nopf" else "0")
+    for mode in ("0", "1"):
+        monkeypatch.setenv("IMMTSF_RECAVG_FUSED_BWD", mode)
         outs[mode] = [x.clone() for x in ops.recavg_pool_bwd(dE, E_raw, mean, rstd, wsum, r.emb_flat, r, t_hat, ls, gamma, T, d, thr, seed)]
     torch.cuda.synchronize()
     live = (int(r.offsets[B].item()) + 127) // 128 * 128  # rows past roundup(sum N, 128) of dV' are never written (torch.empty)
-    for mode in ("0", "1", "nopf"):
+    for mode in ("0", "1"):
         outs[mode][0] = outs[mode][0][:live]
-    for mode in ("1", "nopf"):
+    for mode in ("1",):
         for name, ref, got in zip(("dVp", "dgamma", "dbeta", "dlog_sigma"), outs["0"], outs[mode]):
             assert torch.isfinite(got).all(), (mode, name)
             den = max(ref.abs().max().item(), 1e-6)

@@ -73,12 +73,23 @@ def test_benchmarked_step_through_graph_replay_vs_oracle(workload):
 
 
 # ------------------------------------------------------------------ (b) RecAvg + GR_Add: long segments, long windows, wide rows
-@pytest.mark.parametrize("N,T", [(40, 24), (64, 64), (256, 24), (64, 256), (1024, 64), (256, 256), (1024, 24)])
+@pytest.mark.parametrize("N,T", [(40, 24), (64, 64), (256, 24), (64, 256), (1024, 64), (256, 256), (1024, 24), (512, 128)])
 def test_recavg_gr_long_segments_vs_oracle(N, T):
-    """N > 16: multi-stage staged forward; N > 32 or T > 32: two-kernel backward; the large N x T cells use the
-    tensor-core / tiled contraction where it is selected."""
+    """N > 16: multi-stage staged forward; N > 32 or T > 32: two-kernel backward; at (1024, 64), (256, 256) and (512, 128)
+    the forward pooling runs as a batched tcgen05 product (csrc/recavg_tc.cu, ops.recavg_tc_ok; the backward switches at
+    N x T >= 2^18 and is covered at forced sizes by test_recavg_tensor_core_path_vs_oracle)."""
     cfg = dict(ttf="TTF_RecAvg", mmf="MMF_GR_Add", d_txt=768, C=4, H=1, kappa=0.5)
     _vs_oracle(cfg, 768, B=3 if N * T >= 65536 else 5, N=N, T=T, p=0.1, train=True, seed=900 + N + T)
+
+
+@pytest.mark.parametrize("N,T,dtxt", [(64, 64, 768), (70, 40, 768), (5, 7, 64), (130, 96, None)])
+def test_recavg_tensor_core_path_vs_oracle(N, T, dtxt, monkeypatch):
+    """The tensor-core form of the pooling forced at any size (IMMTSF_RECAVG_TC=1): N not a multiple of 4 (padded contraction
+    dimension), tiny shapes (tiles that overhang a sample are zero-filled by TMA), no input projection (V' = the ragged
+    embeddings themselves), samples without notes.  Same bars as every other path."""
+    monkeypatch.setenv("IMMTSF_RECAVG_TC", "1")
+    cfg = dict(ttf="TTF_RecAvg", mmf="MMF_GR_Add", d_txt=dtxt, C=4, H=1, kappa=0.5)
+    _vs_oracle(cfg, 768 if dtxt != 64 else 96, B=4, N=N, T=T, p=0.1, train=True, seed=1200 + N + T)
 
 
 @pytest.mark.parametrize("N,T", [(12, 24), (70, 28)])

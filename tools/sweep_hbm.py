@@ -45,6 +45,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=None)
     ap.add_argument("--only-recavg", action="store_true", help="the three Time-IMM-sized RecAvg rows only (A/B runs of kernel variants)")
+    ap.add_argument("--only-large", action="store_true", help="the long-segment x long-window RecAvg rows only (tensor-core path A/B)")
     args = ap.parse_args()
     dev = torch.device("cuda")
     peak, src = peak_hbm()
@@ -55,6 +56,9 @@ def main():
               (512, 256, 64, False), (64, 1024, 256, False), (4096, 4, 16, False)]
     if args.only_recavg:
         shapes = [(256, 16, 24, False), (2048, 16, 24, False), (2048, 16, 24, True), (4096, 4, 16, False)]
+    if args.only_large:
+        shapes = [(512, 256, 64, False), (128, 1024, 64, False), (128, 256, 256, False), (64, 1024, 256, False)]
+        args.only_recavg = True
     for (B, N, T, full) in shapes:
         notes, tau, sumN = ragged(B, N, d, full)
         r = ops.csr_build(notes, tau)
