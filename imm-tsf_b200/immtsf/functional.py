@@ -12,6 +12,7 @@ Reference semantics (file:line):
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 
@@ -307,7 +308,13 @@ class T2VXAttnFoldFn(torch.autograd.Function):
         W_q, W_k, W_v = in_w[:d], in_w[d:2 * d], in_w[2 * d:]
         tc = ops.gemm_backend() != ops.BACKEND_FFMA
         dp = ops.DP_GROUP is not None
-        fk = ops.Fork(dev, lanes=3)
+        # single GPU with an input projection: a fourth lane takes the X side's small products (everything that needs db_x only)
+        # and the Time2Vec gradients, so that the grouped un-fold starts as soon as the big weight gradient dW_x is reduced --
+        # the timeline of the step (profiles/r2_timeline_cfg2_n1_final.txt) had 40 us of tiny dependent kernels between the two
+        # at the very end of backward.  IMMTSF_T2V_TAIL_LANE=0 keeps the three-lane order (A/B runs); the data-parallel schedule
+        # is unchanged (its lane order carries the all-reduces).
+        tail_lane = (not dp) and has_in and os.environ.get("IMMTSF_T2V_TAIL_LANE", "1") != "0"
+        fk = ops.Fork(dev, lanes=4 if tail_lane else 3)
         dE = dE_txt.contiguous().view(B * T, d)
         if ctx.defer:
             dW_po = db_po = None  # the consumer returns these
@@ -352,6 +359,8 @@ class T2VXAttnFoldFn(torch.autograd.Function):
                 ops.dp_allreduce(pack_qv)
                 ev["qv"] = fk.mark(0)
             ops.gemm(dbvf.view(1, d), out_w, d_in_b[2 * d:].view(1, d))
+            if tail_lane:
+                ops.gemm(dbvf.view(d, 1), in_b[2 * d:].view(1, d), dW_o)  # W_o b_v also depends on W_o (the un-fold accumulates onto it)
             ev["v"] = fk.mark(0)
             res["dW_o"] = dW_o
 
@@ -378,9 +387,21 @@ class T2VXAttnFoldFn(torch.autograd.Function):
 
         def sums_x():  # X = [emb ; phi] [W_a W_in | W_phi]^T + (W_a b_in + b_kv)
             ops.linear_wgrad(dX, Ecat, out=dWx, ragged=r.m_dev, lo=lo, emit_lo=dWx_lo)
+            if not tail_lane:
+                ops.colsum(dX, out=dbX, ragged=r.m_dev)
+
+        if tail_lane:
+            dW_kv_t, dW_in_t, db_in_t = new(d, d + dt), new(d, dm), new(d)
+
+        def smalls_x():  # lane 3: db_x and the two products that need nothing else, beside the big weight gradient of lane 2
             ops.colsum(dX, out=dbX, ragged=r.m_dev)
+            ops.gemm(dbX.view(d, 1), b_in.view(1, d), dW_kv_t[:, :d])  # W_a b_in also depends on W_a (the un-fold accumulates onto it)
+            ops.gemm(dbX.view(1, d), W_a, db_in_t.view(1, d))
+            ev["xs"] = fk.mark(3)
 
         fk.run(sums_x, dX, pack_x, *([lo.lo_for(dX, r.m_dev)] if fk.side is not None and tc else []), lane=2)
+        if tail_lane:
+            fk.run(smalls_x, dX, pack_x, dW_kv_t, db_in_t, lane=3)
         dphi = ops.linear_dgrad(dX, Wx[:, dm:], out=new(r.M_alloc, dt), ragged=r.m_dev, lo=lo)
 
         def params_t2v():
@@ -401,6 +422,14 @@ class T2VXAttnFoldFn(torch.autograd.Function):
             dP1 = dWx[:, :dm]
             if dWx_lo is not False:
                 lo.put(dP1, dWx_lo[:, :dm])
+            if tail_lane:  # the small products are lane 3's: copy the phi columns, wait for both sides' rank-1 terms, un-fold
+                dW_kv, dW_in, db_in = dW_kv_t, dW_in_t, db_in_t
+                ops.multi_split([(dWx[:, dm:], dW_kv[:, d:], None)])
+                fk.lane_wait(2, ev["xs"])
+                fk.lane_wait(2, ev["v"])
+                ops.gemm_group(unfold_v + [dict(A=dP1, B=W_in, C=dW_kv[:, :d], transB=True, beta=1.0), dict(A=W_a, B=dP1, C=dW_in, transA=True)], lo)
+                res["dW_kv"], res["db_kv"], res["dW_in"], res["db_in"] = dW_kv, dbX, dW_in, db_in
+                return
             dW_kv, dW_in, db_in = new(d, d + dt), new(d, dm), new(d)
             ops.gemm(dbX.view(d, 1), b_in.view(1, d), dW_kv[:, :d])  # W_a b_in also depends on W_a
             ops.gemm(dbX.view(1, d), W_a, db_in.view(1, d))
@@ -414,6 +443,9 @@ class T2VXAttnFoldFn(torch.autograd.Function):
         if dp:
             fk.run(params_t2v, dphi, pack_x, lane=2)  # same lane as dW_x: the lane's all-reduce follows both
             fk.run(params_x, lane=2, after_current=False)
+        elif tail_lane:
+            fk.run(params_x, dW_kv_t, dW_in_t, db_in_t, lane=2, after_current=False)  # the un-fold does not wait for d phi
+            fk.run(params_t2v, dphi, pack_x, lane=3)  # (after lane 3's small products; not behind the query path of lane 1)
         else:
             fk.run(params_x, lane=2, after_current=False)  # the un-fold does not wait for d phi
             fk.run(params_t2v, dphi, pack_x, lane=1)
