@@ -313,8 +313,12 @@ class T2VXAttnFoldFn(torch.autograd.Function):
         # the timeline of the step (profiles/r2_timeline_cfg2_n1_final.txt) had 40 us of tiny dependent kernels between the two
         # at the very end of backward.  IMMTSF_T2V_TAIL_LANE=0 keeps the three-lane order (A/B runs); the data-parallel schedule
         # is unchanged (its lane order carries the all-reduces).
-        tail_lane = (not dp) and has_in and os.environ.get("IMMTSF_T2V_TAIL_LANE", "1") != "0"
-        fk = ops.Fork(dev, lanes=4 if tail_lane else 3)
+        lane4 = os.environ.get("IMMTSF_T2V_TAIL_LANE", "1") != "0"
+        tail_lane = (not dp) and has_in and lane4
+        # data parallel: the same fourth lane takes db_x and the Time2Vec gradients (both land in pack_x BEFORE its all-reduce), so
+        # lane 2's all-reduce follows the big weight gradient directly; the collectives, their order and their buffers are unchanged
+        dp_lane = dp and lane4
+        fk = ops.Fork(dev, lanes=4 if (tail_lane or dp_lane) else 3)
         dE = dE_txt.contiguous().view(B * T, d)
         if ctx.defer:
             dW_po = db_po = None  # the consumer returns these
@@ -359,7 +363,7 @@ class T2VXAttnFoldFn(torch.autograd.Function):
                 ops.dp_allreduce(pack_qv)
                 ev["qv"] = fk.mark(0)
             ops.gemm(dbvf.view(1, d), out_w, d_in_b[2 * d:].view(1, d))
-            if tail_lane:
+            if tail_lane or dp_lane:
                 ops.gemm(dbvf.view(d, 1), in_b[2 * d:].view(1, d), dW_o)  # W_o b_v also depends on W_o (the un-fold accumulates onto it)
             ev["v"] = fk.mark(0)
             res["dW_o"] = dW_o
@@ -387,7 +391,7 @@ class T2VXAttnFoldFn(torch.autograd.Function):
 
         def sums_x():  # X = [emb ; phi] [W_a W_in | W_phi]^T + (W_a b_in + b_kv)
             ops.linear_wgrad(dX, Ecat, out=dWx, ragged=r.m_dev, lo=lo, emit_lo=dWx_lo)
-            if not tail_lane:
+            if not (tail_lane or dp_lane):
                 ops.colsum(dX, out=dbX, ragged=r.m_dev)
 
         if tail_lane:
@@ -402,6 +406,8 @@ class T2VXAttnFoldFn(torch.autograd.Function):
         fk.run(sums_x, dX, pack_x, *([lo.lo_for(dX, r.m_dev)] if fk.side is not None and tc else []), lane=2)
         if tail_lane:
             fk.run(smalls_x, dX, pack_x, dW_kv_t, db_in_t, lane=3)
+        elif dp_lane:
+            fk.run(lambda: ops.colsum(dX, out=dbX, ragged=r.m_dev), dX, pack_x, lane=3)
         dphi = ops.linear_dgrad(dX, Wx[:, dm:], out=new(r.M_alloc, dt), ragged=r.m_dev, lo=lo)
 
         def params_t2v():
@@ -409,13 +415,16 @@ class T2VXAttnFoldFn(torch.autograd.Function):
 
         def params_x():
             if dp:
+                if dp_lane:
+                    fk.lane_wait(2, ev["x3"])  # db_x and the Time2Vec gradients (lane 3) are in pack_x
                 ops.dp_allreduce(pack_x)
             # the rank-1 bias terms first (K = 1 products, they overwrite), the grouped d x d products then ACCUMULATE onto them:
             # nothing is left to do after the big launch
             unfold_v = [dict(A=dWvf, B=W_v, C=dW_o, transB=True, beta=1.0), dict(A=out_w, B=dWvf, C=d_in_w[2 * d:], transA=True)]
             if not has_in:
                 fk.lane_wait(2, ev["v"])
-                ops.gemm(dbvf.view(d, 1), in_b[2 * d:].view(1, d), dW_o)  # W_o b_v also depends on W_o
+                if not dp_lane:
+                    ops.gemm(dbvf.view(d, 1), in_b[2 * d:].view(1, d), dW_o)  # W_o b_v also depends on W_o
                 ops.gemm_group(unfold_v, lo)
                 res["dW_kv"], res["db_kv"], res["dW_in"], res["db_in"] = dWx, dbX, None, None
                 return
@@ -435,12 +444,17 @@ class T2VXAttnFoldFn(torch.autograd.Function):
             ops.gemm(dbX.view(1, d), W_a, db_in.view(1, d))
             ops.multi_split([(dWx[:, dm:], dW_kv[:, d:], None)])
             fk.lane_wait(2, ev["v"])  # the value side's statistics (lane 0) are final
-            ops.gemm(dbvf.view(d, 1), in_b[2 * d:].view(1, d), dW_o)  # W_o b_v also depends on W_o
+            if not dp_lane:
+                ops.gemm(dbvf.view(d, 1), in_b[2 * d:].view(1, d), dW_o)  # W_o b_v also depends on W_o
             # both weight-space un-folds (four d x d products) in ONE grouped launch
             ops.gemm_group(unfold_v + [dict(A=dP1, B=W_in, C=dW_kv[:, :d], transB=True, beta=1.0), dict(A=W_a, B=dP1, C=dW_in, transA=True)], lo)
             res["dW_kv"], res["db_kv"], res["dW_in"], res["db_in"] = dW_kv, dbX, dW_in, db_in
 
-        if dp:
+        if dp_lane:
+            fk.run(params_t2v, dphi, pack_x, lane=3)
+            ev["x3"] = fk.mark(3)
+            fk.run(params_x, lane=2, after_current=False)
+        elif dp:
             fk.run(params_t2v, dphi, pack_x, lane=2)  # same lane as dW_x: the lane's all-reduce follows both
             fk.run(params_x, lane=2, after_current=False)
         elif tail_lane:
