@@ -126,8 +126,8 @@ __device__ __forceinline__ float dropout_scale(uint64_t seed, uint32_t site, uin
   return dropout_field(seed, site, idx) >= thr ? inv_keep : 0.f;
 }
 // keep-scales of the 8 consecutive elements idx8*8 .. idx8*8+7 (one Philox call)
-__device__ __forceinline__ void dropout_scale8(uint64_t seed, uint32_t site, uint64_t idx8, uint32_t thr, float inv_keep,
-                                               float (&o)[8]) {
+__host__ __device__ __forceinline__ void dropout_scale8(uint64_t seed, uint32_t site, uint64_t idx8, uint32_t thr, float inv_keep,
+                                                        float (&o)[8]) {
   if (thr == 0u) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) o[e] = 1.f;
@@ -145,7 +145,7 @@ __device__ __forceinline__ void dropout_scale8(uint64_t seed, uint32_t site, uin
 // Round keys of Philox4x32-10 for one seed (the Weyl sequence of common.cuh's philox4x32_10), computed once per kernel:
 // the key schedule is 20 of the ~85 instructions of a call when it is redone per call.
 struct PhiloxKeys { uint32_t k0[10], k1[10]; };
-__device__ __forceinline__ PhiloxKeys philox_keys(uint64_t seed) {
+__host__ __device__ __forceinline__ PhiloxKeys philox_keys(uint64_t seed) {
   PhiloxKeys k;
   uint32_t a = (uint32_t)seed, b = (uint32_t)(seed >> 32);
 #pragma unroll
@@ -155,7 +155,7 @@ __device__ __forceinline__ PhiloxKeys philox_keys(uint64_t seed) {
 // keep-scales of chunk idx8 with the halves in the lane's order: o[0..3] = the float4 the lane reads first (p = 1: the second
 // one).  Same mask as dropout_scale8 (one Philox4x32-10 call, 16-bit fields against thr); thr == 0 keeps everything
 // (every field >= 0) without a branch.
-__device__ __forceinline__ void dropout_scale8_sw(const PhiloxKeys& key, uint32_t site, uint64_t idx8, uint32_t thr, float inv_keep, int p,
+__host__ __device__ __forceinline__ void dropout_scale8_sw(const PhiloxKeys& key, uint32_t site, uint64_t idx8, uint32_t thr, float inv_keep, int p,
                                                   float (&o)[8]) {
   uint32_t c0 = (uint32_t)idx8, c1 = (uint32_t)(idx8 >> 32), c2 = site, c3 = 0u;
 #pragma unroll

@@ -187,6 +187,28 @@ def test_philox_mirror_matches_device_code(tmp_path):
         assert [int(x[0]) for x in got] == w
 
 
+def test_keyed_dropout_mask_equals_the_per_call_one(tmp_path):
+    """csrc/common.cuh compiled for the host: dropout_scale8_sw (Philox round keys computed once, thresholds on shifted words,
+    the float4 halves in the lane's order -- what the one-launch RecAvg backward uses) draws exactly the mask of
+    dropout_scale8 (one full Philox call per chunk -- what every forward kernel uses), for p = 0 (natural order) and p = 1
+    (halves swapped), at drop thresholds 0, 1, 0.1 * 2^16 and 0xFFFF."""
+    src = tmp_path / "k.cu"
+    src.write_text(
+        '#include "common.cuh"\nvoid immtsf_set_error(const char*, ...) {}\n'
+        "int main(){int bad=0;const uint32_t thrs[4]={0u,1u,6553u,65535u};"
+        "for(int t=0;t<4;++t)for(uint64_t s=1;s<40;s+=13){const uint64_t seed=s*0x9E3779B97F4A7C15ull;const PhiloxKeys k=philox_keys(seed);"
+        "const float ik=thrs[t]==0u?1.f:(float)(1.0/(1.0-(double)thrs[t]/65536.0));"
+        "for(uint64_t c=0;c<2000;++c){const uint64_t idx=c*0x10001ull+(c<<33);float a[8],b0[8],b1[8];"
+        "dropout_scale8(seed,1u,idx,thrs[t],ik,a);dropout_scale8_sw(k,1u,idx,thrs[t],ik,0,b0);dropout_scale8_sw(k,1u,idx,thrs[t],ik,1,b1);"
+        "for(int e=0;e<8;++e){if(a[e]!=b0[e])++bad;if(a[e]!=b1[e^4])++bad;}}}"
+        'printf("%d\\n",bad);return 0;}\n')
+    exe = tmp_path / "k"
+    r = subprocess.run(["nvcc", "-I", os.path.join(ROOT, "imm-tsf_b200", "csrc"), "-o", str(exe), str(src)], capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("nvcc unavailable: " + r.stderr[-300:])
+    assert subprocess.run([str(exe)], capture_output=True, text=True).stdout.strip() == "0"
+
+
 def test_launcher_swaps_fusions_under_an_unmodified_script(tmp_path):
     """tools/run_with_immtsf.py: a script that lives next to its own `fusions` package (as the reference's
     main.py does) must get the B200 drop-in from the same import statements (main.py:39-40)."""
